@@ -1,0 +1,108 @@
+/*
+ * patolette_b200.h - C ABI of libpatolette_b200.so (B200 / sm_100a).
+ *
+ * Part 1 is the reference's public interface, symbol for symbol: a caller that
+ * binds lib/include/patolette.h of big-nacho/patolette can load this library
+ * instead and get the same results, computed on the GPU.
+ *
+ * Part 2 (patolette_b200_*) is our extension surface: device selection, stage
+ * entry points used by the parity tests, timing read-back for bench.py.  None of
+ * the signatures carries a torch / CUDA type: plain pointers and sizes only.
+ */
+#pragma once
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(PATOLETTE_B200_BUILD)
+#define PB200_API __attribute__((visibility("default")))
+#else
+#define PB200_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- Part 1: reference ABI ------------------------------------------------ */
+
+/* replaces lib/include/patolette.h:7-11 */
+typedef enum patolette__ColorSpace {
+    patolette__sRGB,
+    patolette__CIELuv,
+    patolette__ICtCp
+} patolette__ColorSpace;
+
+/* replaces lib/include/patolette.h:13-20 (x86-64: offsets 0,1,4,8,16,24; sizeof 32) */
+typedef struct patolette__QuantizationOptions {
+    bool dither;
+    bool palette_only;
+    patolette__ColorSpace color_space;
+    int kmeans_niter;
+    size_t kmeans_max_samples;
+    bool verbose;
+} patolette__QuantizationOptions;
+
+/* replaces lib/include/patolette.h:22-32 / lib/src/patolette.c:157-343.
+ * data: width*height x 3 f64, column-major (all R, all G, all B), sRGB in [0,1],
+ * row-major pixel scan order.  weights: width*height f64 (each >= 1) or NULL.
+ * palette: caller-allocated palette_size x 3 f64 column-major; unused rows = -1.
+ * palette_map: caller-allocated width*height size_t (may be NULL iff palette_only).
+ * exit_code: 0 ok, -1 internal, -2 bad dims, -3 bad palette size, -4 too big;
+ * additionally -5 = CUDA failure (no GPU / out of memory), which the reference
+ * cannot produce.  Synchronous; inputs are never written. */
+PB200_API void patolette(size_t width, size_t height, const double *data, const double *weights,
+               size_t palette_size, const patolette__QuantizationOptions *options,
+               double *palette, size_t *palette_map, int *exit_code);
+
+/* replaces lib/include/patolette.h:34 / lib/src/patolette.c:97-105 */
+PB200_API const char *get_patolette_exit_code_info_message(int exit_code);
+
+/* replaces lib/include/patolette.h:35 / lib/src/patolette.c:107-119 (caller frees) */
+PB200_API patolette__QuantizationOptions *patolette_create_default_options(void);
+
+/* ---- Part 2: extensions ---------------------------------------------------- */
+
+/* CUDA device used by subsequent calls from this thread's process (default 0). */
+PB200_API int patolette_b200_set_device(int device);
+/* Number of visible CUDA devices, or a negative cudaError on failure. */
+PB200_API int patolette_b200_device_count(void);
+/* Shared object that provides LAPACK dsyev_ (the reference links one too,
+ * lib/src/math/eigen.c:50).  NULL restores the default search. */
+PB200_API void patolette_b200_set_lapack(const char *path);
+/* "path:symbol" of the dsyev_ in use, or "builtin-jacobi". */
+PB200_API const char *patolette_b200_lapack_source(void);
+
+/* Stage: one of the reference's matrix colour transforms in place on a host
+ * planar n x 3 array (lib/src/color/: 0 sRGB->ICtCp, 1 sRGB->CIELuv, 2 ICtCp->Rec2020,
+ * 3 CIELuv->Rec2020, 4 sRGB->Rec2020, 5 Rec2020->sRGB, 6 CIELuv->ICtCp via sRGB). */
+PB200_API int patolette_b200_color_transform(int which, double *planar, size_t n);
+/* Stage: out[i] = pow(x[i], y) with the glibc-exact device pow. */
+PB200_API int patolette_b200_pow(const double *x, double y, double *out, size_t n);
+/* Stage: GQ + LQ (lib/src/quantize/global.c:388, local.c:318) on colours that are
+ * already in the quantisation space.  labels[i] = palette slot of pixel i,
+ * centers = count x 3 row-major cluster centres (lib/src/palette/create.c:11-33). */
+PB200_API int patolette_b200_quantize_clusters(const double *planar, size_t n, const double *weights,
+                                     size_t palette_size, uint32_t *labels, double *centers,
+                                     size_t *count, size_t *gq_count);
+/* Stage: exact nearest-palette map (lib/src/palette/nearest.c:150-209).
+ * palette_rm: K x 3 row-major. */
+PB200_API int patolette_b200_nearest(const double *planar, size_t n, const double *palette_rm, size_t K,
+                           size_t *map);
+/* Stage: weighted KMeans refinement (lib/src/palette/refine.c:56-100 + faiss
+ * Clustering.cpp:587).  x: n x 3 row-major f32; centers: K x 3 f32 in/out. */
+PB200_API int patolette_b200_kmeans(const float *x, size_t n, size_t K, float *centers, const float *w,
+                          int niter, int max_points_per_centroid);
+/* Stage: Riemersma dither (lib/src/dither/riemersma.c:437) on linear-Rec2020 colours. */
+PB200_API int patolette_b200_dither(const double *planar, size_t width, size_t height,
+                          const double *palette_rm, size_t K, size_t *map);
+
+/* Timings of the last patolette() call on this process, milliseconds (CUDA events
+ * on the library's stream; h2d/d2h include the host copies).  Keys in order:
+ * total, h2d, color, gq, lq, kmeans, nearest, dither, d2h, and the number of
+ * kernels launched as the 10th value. */
+PB200_API int patolette_b200_last_timings(double *out10);
+
+#ifdef __cplusplus
+}
+#endif

@@ -331,10 +331,15 @@ ORC_API int orc_pca(const double *planar, size_t n_total, const double *weights,
 }
 
 /* The per-row arithmetic of cblas_dgemv(ColMajor, NoTrans, n, 3, 1, A, n, x, 1, 0, y, 1)
- * as OpenBLAS 0.3.31 (Haswell / SkylakeX dgemv_n) evaluates it: the 2-column
- * micro-kernel fuses a0*x0 onto the rounded a1*x1, the 1-column tail then
- * adds the rounded a2*x2.  Re-derived by orc_selftest_dgemv(). */
-static inline double dgemv_row3(double a0, double a1, double a2, const double x[3]) {
+ * as OpenBLAS 0.3.31 (x86-64 Haswell / SkylakeX dgemv_n, single thread) evaluates it:
+ *   - rows are processed four at a time: the 2-column micro-kernel fuses a0*x0 onto the
+ *     rounded a1*x1, the 1-column tail then adds the separately rounded a2*x2;
+ *   - the last (n mod 4) rows go through the scalar tail loop temp += a[j]*x[j], which the
+ *     FMA build contracts into fma(a2,x2, fma(a1,x1, a0*x0)).
+ * Re-derived against the live BLAS by orc_selftest_dgemv(). */
+static inline double dgemv_row3(double a0, double a1, double a2, const double x[3], size_t row,
+                                size_t n) {
+    if (row >= n - (n & 3)) return fma(a2, x[2], fma(a1, x[1], a0 * x[0]));
     return fma(a0, x[0], a1 * x[1]) + a2 * x[2];
 }
 
@@ -344,7 +349,7 @@ static void axis_sort(const orc_dataset *d, const uint32_t *idx, size_t n, const
     double *dots = malloc(sizeof(double) * (n ? n : 1));
     for (size_t i = 0; i < n; i++) {
         size_t p = idx ? idx[i] : i;
-        dots[i] = dgemv_row3(d->c0[p], d->c1[p], d->c2[p], axis);
+        dots[i] = dgemv_row3(d->c0[p], d->c1[p], d->c2[p], axis, i, n);
     }
     /* array/vector.c:26-46: strict comparisons, first extremum wins */
     double mn = dots[0], mx = dots[0];
@@ -382,7 +387,7 @@ ORC_API long orc_selftest_dgemv(const double *planar, size_t n, const double axi
     scipy_cblas_dgemv(102, 111, (int)n, 3, 1.0, planar, (int)n, axis, 1, 0.0, y, 1);
     long bad = 0;
     for (size_t i = 0; i < n; i++) {
-        double r = dgemv_row3(planar[i], planar[n + i], planar[2 * n + i], axis);
+        double r = dgemv_row3(planar[i], planar[n + i], planar[2 * n + i], axis, i, n);
         if (memcmp(&r, &y[i], 8) != 0) bad++;
     }
     free(y);

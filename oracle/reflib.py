@@ -19,6 +19,12 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
+# The reference's projections go through cblas_dgemv (quantize/sort.c:43).  A multi-threaded
+# OpenBLAS splits the rows between threads and each range gets its own differently-rounded
+# scalar tail, so results would depend on the thread count.  Pin the BLAS to one thread
+# (must happen before the library is first loaded); faiss' own OpenMP threading is unaffected.
+os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+
 ColorSpace_sRGB, ColorSpace_CIELuv, ColorSpace_ICtCp = 0, 1, 2
 
 

@@ -1,0 +1,88 @@
+"""patolette_b200 - B200-native drop-in for the pixel-array hot path of big-nacho/patolette.
+
+Public surface = the reference's Python module (src/patolette/__init__.py:1-10):
+``quantize``, ``ColorSpace_sRGB``, ``ColorSpace_CIELuv``, ``ColorSpace_ICtCp``.
+Everything runs through the C ABI of libpatolette_b200.so; there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+__version__ = "0.1.0"
+
+# reference: src/patolette/patolette.pyx:324-326
+ColorSpace_sRGB = 0
+ColorSpace_CIELuv = 1
+ColorSpace_ICtCp = 2
+
+# reference: src/patolette/patolette.pyx:328-330
+color_mismatch = "The number of colors doesn't match the supplied width and height."
+bad_channel_count = "Expected colors to be in sRGB[0, 1] space. Channel count mismatch: {} found."
+bad_tile_size = "tile_size parameter expected to be in the range [0, inf]"
+
+__all__ = ["__doc__", "__version__", "quantize", "ColorSpace_sRGB", "ColorSpace_CIELuv", "ColorSpace_ICtCp"]
+
+
+def quantize(width, height, colors, palette_size, dither=True, palette_only=False,
+             color_space=ColorSpace_ICtCp, tile_size=512, kmeans_niter=32,
+             kmeans_max_samples=512 ** 2, verbose=False, *, weights=None):
+    """Same contract as the reference ``quantize`` (src/patolette/patolette.pyx:332-466):
+    returns ``(success, palette[K,3] F-order f64 | None, palette_map[N] uintp | None, message)``.
+
+    Differences, both explicit:
+      * ``tile_size > 0`` asks the reference for saliency weights computed with scikit-image
+        (patolette.pyx:203-313).  That pre-processing is outside this package's scope
+        (SURVEY.md section 8f, N3): it raises NotImplementedError unless ``weights`` is given.
+        Pass ``tile_size=0`` for the unweighted path.
+      * ``weights`` (keyword-only, extension): per-pixel f64 weights >= 1 handed straight to
+        the C ABI's ``weights`` argument (lib/include/patolette.h:26).
+    """
+    colors = np.asarray(colors)
+    if colors.ndim != 2:
+        raise ValueError("colors must be a 2-D array")
+    color_count, channel_count = colors.shape
+    if channel_count != 3:
+        return (False, None, None, bad_channel_count.format(channel_count))
+    if color_count != width * height:
+        return (False, None, None, color_mismatch)
+    if tile_size < 0:
+        return (False, None, None, bad_tile_size)
+    if weights is None and tile_size > 0:
+        raise NotImplementedError(
+            "saliency weights (tile_size > 0) are not part of patolette_b200; pass tile_size=0 "
+            "or supply weights=...")
+    lib = _lib.load()
+    data = np.asfortranarray(colors, dtype=np.float64)
+    palette = np.zeros((palette_size, 3), dtype=np.float64, order="F")
+    pmap = None if palette_only else np.zeros(width * height, dtype=np.uintp)
+    w = None
+    if weights is not None:
+        w = np.ascontiguousarray(weights, dtype=np.float64)
+        if w.shape != (color_count,):
+            raise ValueError("weights must have one entry per pixel")
+    opts = _lib.QuantizationOptions(bool(dither), bool(palette_only), int(color_space), int(kmeans_niter),
+                                    int(kmeans_max_samples), bool(verbose))
+    code = C.c_int(0)
+    lib.patolette(width, height, data.ctypes.data if color_count else None,
+                  None if w is None else w.ctypes.data, palette_size, C.byref(opts),
+                  palette.ctypes.data if palette_size else None,
+                  None if pmap is None else pmap.ctypes.data, C.byref(code))
+    success = code.value == 0
+    message = lib.get_patolette_exit_code_info_message(code.value).decode("utf-8")
+    if not success:
+        return (success, None, None, message)
+    if palette_only:
+        return (success, palette, None, message)
+    return (success, palette, pmap, message)
+
+
+def last_timings() -> dict:
+    """Stage timings (ms) of the last quantize() in this process, for bench.py."""
+    out = (C.c_double * 10)()
+    _lib.load().patolette_b200_last_timings(out)
+    keys = ["total", "h2d", "color", "gq", "lq", "kmeans", "nearest", "dither", "d2h", "launches"]
+    return dict(zip(keys, list(out)))

@@ -1,0 +1,8 @@
+// pb_host.h - host-side internals shared between the pipeline and helpers.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+void pb_lapack_set_path(const char *path);
+const char *pb_lapack_source();
+bool pb_eigen_solve3(double a[9], double w[3]);

@@ -1,0 +1,77 @@
+// pb_kernels.h - host-callable launchers of the patolette_b200 kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "pb_common.cuh"
+
+// Colour transforms (pb_color.cu).  Values mirror oracle ORC_T_* for tests.
+enum {
+    PB_T_SRGB_TO_ICTCP = 0,
+    PB_T_SRGB_TO_CIELUV = 1,
+    PB_T_ICTCP_TO_REC2020 = 2,
+    PB_T_CIELUV_TO_REC2020 = 3,
+    PB_T_SRGB_TO_REC2020 = 4,
+    PB_T_REC2020_TO_SRGB = 5,
+    PB_T_CIELUV_TO_ICTCP = 6, // CIELuv -> Rec2020 -> sRGB -> ICtCp (patolette.c:305-314), fused
+};
+void pb_launch_color(int which, const double *const src[3], double *const dst[3], size_t n,
+                     int sm_count, cudaStream_t st);
+void pb_launch_pow(const double *x, double y, double *out, size_t n, int sm_count, cudaStream_t st);
+
+// ---- ordered-sum ("chain") kernels, pb_chain.cu --------------------------------------
+// Every reference statistic is a left-to-right f64 sum in ascending pixel order; these
+// kernels reproduce that order bit for bit (see pb_chain.cu for how).
+void pb_launch_pass_mean(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, bool weighted,
+                         PbStats *d_stats, cudaStream_t st);
+void pb_launch_pass_centered(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, bool weighted,
+                             PbStats *d_stats, cudaStream_t st);
+// Per-bucket ordered sums over bucket-sorted position lists.
+//   LQ (local.c:102-146): out[seg][b] = {size (as double bits of u64), sum c0*w, sum c1*w, sum c2*w}
+//   GQ (cells.c:53-116):  out[b] = {sum c0, c1, c2, sum |c|^2, sums c_r*c_s (r<=s: 00,01,11,02,12,22)}
+void pb_launch_bucket_chains_lq(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, bool weighted,
+                                const uint32_t *d_ord, const uint32_t *d_class_start,
+                                double *d_out /* nseg x 512 x 4 */, cudaStream_t st);
+void pb_launch_bucket_chains_gq(const PbPlanes &src, const uint32_t *d_ord,
+                                const uint32_t *d_class_start, double *d_out /* 512 x 10 */,
+                                cudaStream_t st);
+
+// ---- data-parallel kernels, pb_parallel.cu -------------------------------------------
+void pb_launch_dots_minmax(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t max_n,
+                           const double *d_axes /* nseg x 3 */, PbSplit *d_split, int sm_count,
+                           cudaStream_t st);
+void pb_launch_buckets(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t max_n,
+                       const double *d_axes, PbSplit *d_split, uint16_t *d_bucket, int sm_count,
+                       cudaStream_t st);
+void pb_launch_split_select(const double *d_bucket_sums, const uint32_t *d_class_start, int nseg,
+                            PbSplit *d_split, cudaStream_t st);
+
+// Stable multi-class ranking / scatter.  Class of a position is a function of its bucket
+// id; elements keep their relative order inside each class (the reference builds every
+// index list by an ascending scan: local.c:216-243, global.c:300-377).
+enum { PB_CLS_BUCKET = 0, PB_CLS_SPLIT = 1, PB_CLS_LUT = 2 };
+size_t pb_scatter_tiles(uint32_t n);
+// d_tile_hist: nseg * tiles(max_n) * nclass u32 ; d_class_start: nseg * (nclass + 1) u32
+void pb_launch_class_rank(int cls_mode, int nclass, const PbSeg *d_segs, int nseg, uint32_t max_n,
+                          const uint16_t *d_bucket, const PbSplit *d_split, const uint8_t *d_lut,
+                          uint32_t *d_tile_hist, uint32_t *d_class_start, cudaStream_t st);
+// ord[dst] = source position (the bucket sort feeding the ordered per-bucket sums)
+void pb_launch_scatter_ord(int cls_mode, int nclass, const PbSeg *d_segs, int nseg, uint32_t max_n,
+                           const uint16_t *d_bucket, const PbSplit *d_split, const uint8_t *d_lut,
+                           const uint32_t *d_tile_hist, const uint32_t *d_class_start, uint32_t *d_ord,
+                           cudaStream_t st);
+// move the payload (planes + weight + original index); segment s reads src[s.buf], writes dst[s.buf]
+void pb_launch_scatter_payload(int cls_mode, int nclass, const PbPlanes src[2], const PbPlanes dst[2],
+                               bool src_is_identity, const PbSeg *d_segs, int nseg, uint32_t max_n,
+                               const uint16_t *d_bucket, const PbSplit *d_split, const uint8_t *d_lut,
+                               const uint32_t *d_tile_hist, const uint32_t *d_class_start, cudaStream_t st);
+// child descriptors {lo, nleft, other buf}, {lo + nleft, n - nleft, other buf} from PbSplit
+void pb_launch_make_children(const PbSeg *d_segs, int nseg, const PbSplit *d_split,
+                             PbSeg *d_children /* 2 x nseg */, cudaStream_t st);
+
+// Nearest palette entry + cluster labels.
+void pb_launch_nearest(const double *const planes[3], size_t n, const double *d_palette_rm, int K,
+                       unsigned long long *d_map, int sm_count, cudaStream_t st);
+void pb_launch_labels(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t max_n,
+                      uint32_t *d_labels, int sm_count, cudaStream_t st);

@@ -1,0 +1,308 @@
+// pb_kmeans.cu - weighted KMeans palette refinement.
+//
+// Reference: lib/src/palette/refine.c:56-221 driving the vendored, patolette-modified
+// faiss 1.10.0 (lib/faiss/faiss/Clustering.cpp:267-603, IndexFlatL2 k=1 search through
+// utils/distances.cpp:259-343 on the generic build).  Restated, not linked:
+//   * f32 samples (n x 3) and centres, f32 weights (refine.c:102-163);
+//   * optional subsample of k * max_points_per_centroid points: the first entries of a
+//     forward Fisher-Yates permutation driven by std::mt19937(1234)
+//     (Clustering.cpp:70-120, utils/random.cpp:184-194).  Only a prefix of the
+//     permutation is ever read, so the host computes just that prefix with a sparse
+//     swap map - O(subsample), not O(N);
+//   * assignment: dis = (|x|^2 + |y|^2) - 2*ip clamped at 0, ip as sgemm_ evaluates a
+//     k=3 dot, strict '<' over ascending centroid index - one thread per sample, the
+//     centroids in shared memory;
+//   * centroid update: per centroid a SEQUENTIAL f32 sum in sample order
+//     (Clustering.cpp:178-187): samples are stably sorted by assignment
+//     (pb_parallel.cu) and one warp per centroid walks its run;
+//   * empty clusters are refilled on the host with faiss' own RNG protocol
+//     (Clustering.cpp:216-263).
+#include <math.h>
+#include <string.h>
+
+#include <unordered_map>
+#include <vector>
+
+#include "pb_common.cuh"
+#include "pb_kernels.h"
+#include "pb_pipeline.h"
+
+namespace {
+
+// std::mt19937 (faiss::RandomGenerator, utils/random.cpp:35-55)
+struct Mt19937 {
+    uint32_t s[624];
+    int i;
+    explicit Mt19937(uint32_t seed) {
+        s[0] = seed;
+        for (int k = 1; k < 624; k++) s[k] = 1812433253u * (s[k - 1] ^ (s[k - 1] >> 30)) + (uint32_t)k;
+        i = 624;
+    }
+    uint32_t next() {
+        if (i >= 624) {
+            for (int k = 0; k < 624; k++) {
+                uint32_t y = (s[k] & 0x80000000u) | (s[(k + 1) % 624] & 0x7fffffffu);
+                s[k] = s[(k + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            }
+            i = 0;
+        }
+        uint32_t y = s[i++];
+        y ^= y >> 11;
+        y ^= (y << 7) & 0x9d2c5680u;
+        y ^= (y << 15) & 0xefc60000u;
+        y ^= y >> 18;
+        return y;
+    }
+};
+
+// First `take` entries of faiss::rand_perm(n, seed) (random.cpp:184-194).
+std::vector<uint32_t> rand_perm_prefix(size_t n, size_t take, uint32_t seed) {
+    std::vector<uint32_t> out(take);
+    std::unordered_map<uint32_t, uint32_t> moved; // positions whose value is no longer the identity
+    moved.reserve(take * 2);
+    Mt19937 rng(seed);
+    auto get = [&](uint32_t pos) {
+        auto it = moved.find(pos);
+        return it == moved.end() ? pos : it->second;
+    };
+    for (size_t i = 0; i < take && i + 1 < n; i++) {
+        const uint32_t i2 = (uint32_t)(i + (size_t)((uint64_t)rng.next() % (uint64_t)(int)(n - i)));
+        const uint32_t vi = get((uint32_t)i), v2 = get(i2);
+        out[i] = v2;        // perm[i] is final after step i
+        moved[i2] = vi;
+    }
+    if (take == n && n > 0) out[n - 1] = get((uint32_t)(n - 1));
+    return out;
+}
+
+__global__ void k_to_f32(const double *__restrict__ c0, const double *__restrict__ c1,
+                         const double *__restrict__ c2, const double *__restrict__ w,
+                         const uint32_t *__restrict__ pick, size_t n, float *__restrict__ x0,
+                         float *__restrict__ x1, float *__restrict__ x2, float *__restrict__ wf,
+                         int *__restrict__ nonfinite) {
+    int bad = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t p = pick ? pick[i] : i;
+        const float a = (float)c0[p], b = (float)c1[p], c = (float)c2[p]; // refine.c:136-142
+        x0[i] = a; x1[i] = b; x2[i] = c;
+        if (wf) wf[i] = (float)w[p]; // refine.c:158
+        bad |= !(isfinite(a) && isfinite(b) && isfinite(c));
+    }
+    if (bad) atomicOr(nonfinite, 1);
+}
+
+// Clustering.cpp:295-304 scans ALL input samples for NaN/Inf before subsampling.
+__global__ void k_scan_finite(const double *__restrict__ c0, const double *__restrict__ c1,
+                              const double *__restrict__ c2, size_t n, int *__restrict__ nonfinite) {
+    int bad = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        bad |= !(isfinite((float)c0[i]) && isfinite((float)c1[i]) && isfinite((float)c2[i]));
+    if (bad) atomicOr(nonfinite, 1);
+}
+
+__global__ void __launch_bounds__(256) k_assign(const float *__restrict__ x0, const float *__restrict__ x1,
+                                                const float *__restrict__ x2, size_t nx,
+                                                const float *__restrict__ cen, int K, bool seq_path,
+                                                uint16_t *__restrict__ assign) {
+    extern __shared__ float s_cen[]; // K * 4: y0 y1 y2 |y|^2
+    for (int j = threadIdx.x; j < K; j += blockDim.x) {
+        const float a = cen[3 * j], b = cen[3 * j + 1], c = cen[3 * j + 2];
+        s_cen[4 * j] = a; s_cen[4 * j + 1] = b; s_cen[4 * j + 2] = c;
+        // fvec_norms_L2sqr: ((y0^2 + y1^2) + y2^2), separately rounded
+        s_cen[4 * j + 3] = __fadd_rn(__fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b)), __fmul_rn(c, c));
+    }
+    __syncthreads();
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nx; i += (size_t)gridDim.x * blockDim.x) {
+        const float a = x0[i], b = x1[i], c = x2[i];
+        const float xn = __fadd_rn(__fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b)), __fmul_rn(c, c));
+        float bd = 0.f;
+        int best = 0;
+        for (int j = 0; j < K; j++) {
+            float dd;
+            if (seq_path) { // fewer than 20 queries: exhaustive_L2sqr_seq -> fvec_L2sqr
+                const float d0 = __fsub_rn(a, s_cen[4 * j]), d1 = __fsub_rn(b, s_cen[4 * j + 1]),
+                            d2 = __fsub_rn(c, s_cen[4 * j + 2]);
+                dd = __fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2));
+            } else { // distances.cpp:259-343: dis = x_norms + y_norms - 2 * ip, ip from sgemm_ (k = 3)
+                const float ip = __fmaf_rn(c, s_cen[4 * j + 2], __fmaf_rn(b, s_cen[4 * j + 1], __fmul_rn(a, s_cen[4 * j])));
+                dd = __fsub_rn(__fadd_rn(xn, s_cen[4 * j + 3]), __fmul_rn(2.f, ip));
+                if (dd < 0) dd = 0;
+            }
+            if (j == 0 || dd < bd) { bd = dd; best = j; }
+        }
+        assign[i] = (uint16_t)best;
+    }
+}
+
+constexpr int KM_TILE = 64;
+constexpr int KM_WARPS = 4;
+// One warp per centroid: lanes 0..3 chain {hassign, c0, c1, c2} in sample order (Clustering.cpp:178-187).
+template <bool WEIGHTED>
+__global__ void __launch_bounds__(KM_WARPS * 32) k_centroid_chains(const float *__restrict__ x0, const float *__restrict__ x1,
+                                                                   const float *__restrict__ x2, const float *__restrict__ wf,
+                                                                   const uint32_t *__restrict__ ord,
+                                                                   const uint32_t *__restrict__ class_start, int K,
+                                                                   float *__restrict__ out /* K x 4 */) {
+    __shared__ float sm_all[KM_WARPS][4][KM_TILE + 1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int c = blockIdx.x * KM_WARPS + warp;
+    if (c >= K) return;
+    float(*sm)[KM_TILE + 1] = sm_all[warp];
+    const uint32_t beg = class_start[c], end = class_start[c + 1];
+    float acc = 0.f;
+    for (uint32_t i0 = beg; i0 < end; i0 += KM_TILE) {
+        const uint32_t cnt = min((uint32_t)KM_TILE, end - i0);
+#pragma unroll
+        for (int q = 0; q < KM_TILE / 32; q++) {
+            const uint32_t e = q * 32 + lane;
+            if (e < cnt) {
+                const uint32_t p = ord[i0 + e];
+                sm[0][e] = WEIGHTED ? wf[p] : 1.0f;
+                sm[1][e] = x0[p]; sm[2][e] = x1[p]; sm[3][e] = x2[p];
+            }
+        }
+        __syncwarp();
+        if (lane < 4) {
+            const float *vp = sm[lane];
+#pragma unroll 8
+            for (uint32_t e = 0; e < cnt; e++) {
+                const float w = sm[0][e];
+                // hassign += w ; c[j] += x[j] * w   (unweighted: += 1.0 ; += x[j])
+                const float term = lane == 0 ? w : (WEIGHTED ? __fmul_rn(vp[e], w) : vp[e]);
+                acc = __fadd_rn(acc, term);
+            }
+        }
+        __syncwarp();
+    }
+    if (lane < 4) out[4 * c + lane] = acc;
+}
+
+struct DevMem {
+    std::vector<void *> ptrs;
+    template <typename T>
+    T *alloc(size_t count) {
+        void *p = nullptr;
+        PB_CUDA_OK(cudaMalloc(&p, (count ? count : 1) * sizeof(T)));
+        ptrs.push_back(p);
+        return (T *)p;
+    }
+    ~DevMem() {
+        for (void *p : ptrs) cudaFree(p);
+    }
+};
+
+} // namespace
+
+// planes: device f64 colours in the quantisation space (original pixel order); d_w: device f64
+// weights or nullptr; pal_rm: K x 3 row-major f64 centres, refined in place.
+void pb_kmeans_device(const float *d_x0, const float *d_x1, const float *d_x2, const float *d_wf, size_t nx,
+                      std::vector<float> &cen, int K, int niter, int sm_count, cudaStream_t st, long *launches) {
+    DevMem mem;
+    uint16_t *d_assign = mem.alloc<uint16_t>(nx);
+    uint32_t *d_ord = mem.alloc<uint32_t>(nx);
+    const size_t tiles = pb_scatter_tiles((uint32_t)nx);
+    uint32_t *d_tile_hist = mem.alloc<uint32_t>(tiles * (size_t)K + 64);
+    uint32_t *d_cstart = mem.alloc<uint32_t>((size_t)K + 1);
+    float *d_cen = mem.alloc<float>((size_t)K * 3);
+    float *d_sums = mem.alloc<float>((size_t)K * 4);
+    PbSeg *d_seg = mem.alloc<PbSeg>(1);
+    PbSeg whole{0u, (uint32_t)nx, 0u, 0u};
+    PB_CUDA_OK(cudaMemcpyAsync(d_seg, &whole, sizeof whole, cudaMemcpyHostToDevice, st));
+    size_t want = (nx + 255) / 256, cap = (size_t)sm_count * 8;
+    const int grid = (int)(want < cap ? (want ? want : 1) : cap);
+    const size_t smem = (size_t)K * 4 * sizeof(float);
+    if (smem > 48 * 1024)
+        PB_CUDA_OK(cudaFuncSetAttribute(k_assign, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    std::vector<float> sums((size_t)K * 4);
+    for (int it = 0; it < niter; it++) { // Clustering.cpp:442-530
+        PB_CUDA_OK(cudaMemcpyAsync(d_cen, cen.data(), cen.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+        k_assign<<<grid, 256, smem, st>>>(d_x0, d_x1, d_x2, nx, d_cen, K, nx < 20, d_assign);
+        pb_launch_class_rank(PB_CLS_BUCKET, K, d_seg, 1, (uint32_t)nx, d_assign, nullptr, nullptr, d_tile_hist,
+                             d_cstart, st);
+        pb_launch_scatter_ord(PB_CLS_BUCKET, K, d_seg, 1, (uint32_t)nx, d_assign, nullptr, nullptr, d_tile_hist,
+                              d_cstart, d_ord, st);
+        const int cg = (K + KM_WARPS - 1) / KM_WARPS;
+        if (d_wf) k_centroid_chains<true><<<cg, KM_WARPS * 32, 0, st>>>(d_x0, d_x1, d_x2, d_wf, d_ord, d_cstart, K, d_sums);
+        else k_centroid_chains<false><<<cg, KM_WARPS * 32, 0, st>>>(d_x0, d_x1, d_x2, d_wf, d_ord, d_cstart, K, d_sums);
+        PB_CUDA_OK(cudaGetLastError());
+        if (launches) *launches += 6;
+        PB_CUDA_OK(cudaMemcpyAsync(sums.data(), d_sums, sums.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
+        PB_CUDA_OK(cudaStreamSynchronize(st));
+        // compute_centroids epilogue (Clustering.cpp:194-203)
+        std::vector<float> hassign(K);
+        for (int c = 0; c < K; c++) {
+            hassign[c] = sums[4 * c];
+            for (int j = 0; j < 3; j++) cen[3 * c + j] = sums[4 * c + 1 + j];
+            if (hassign[c] == 0) continue;
+            const float norm = 1 / hassign[c];
+            for (int j = 0; j < 3; j++) cen[3 * c + j] *= norm;
+        }
+        // split_clusters (Clustering.cpp:216-263)
+        Mt19937 rng(1234u);
+        for (int ci = 0; ci < K; ci++) {
+            if (hassign[ci] != 0) continue;
+            int cj;
+            for (cj = 0; true; cj = (cj + 1) % K) {
+                float p = (hassign[cj] - 1.0) / (float)(nx - (size_t)K);
+                float r = (float)(uint64_t)rng.next() / 4294967295.0f; // mt() / float(mt.max())
+                if (r < p) break;
+            }
+            memcpy(&cen[3 * ci], &cen[3 * cj], 3 * sizeof(float));
+            for (int j = 0; j < 3; j++) {
+                if (j % 2 == 0) { cen[3 * ci + j] *= 1 + (1 / 1024.); cen[3 * cj + j] *= 1 - (1 / 1024.); }
+                else { cen[3 * ci + j] *= 1 - (1 / 1024.); cen[3 * cj + j] *= 1 + (1 / 1024.); }
+            }
+            hassign[ci] = hassign[cj] / 2;
+            hassign[cj] -= hassign[ci];
+        }
+    }
+}
+
+void pb_kmeans_refine(const double *const planes[3], const double *d_w, size_t n, std::vector<double> &pal_rm,
+                      int niter, int max_points_per_centroid, int sm_count, cudaStream_t st, long *launches) {
+    const size_t K = pal_rm.size() / 3;
+    std::vector<float> cen(3 * K);
+    for (size_t j = 0; j < 3 * K; j++) cen[j] = (float)pal_rm[j]; // refine.c:108-120
+    auto finish = [&]() { // refine.c:202-212 runs whatever faiss did (error code ignored, bug B8)
+        for (size_t j = 0; j < 3 * K; j++) pal_rm[j] = (double)cen[j];
+    };
+    if (n < K || K > 65535) { finish(); return; } // Clustering.cpp:273-279 throws; K > 65535: not supported
+    DevMem mem;
+    int *d_flag = mem.alloc<int>(1);
+    PB_CUDA_OK(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
+    size_t want = (n + 255) / 256, cap = (size_t)sm_count * 8;
+    const int grid = (int)(want < cap ? want : cap);
+    size_t nx = n;
+    uint32_t *d_pick = nullptr;
+    const bool subsample = n > K * (size_t)max_points_per_centroid; // Clustering.cpp:311
+    if (subsample) {
+        k_scan_finite<<<grid, 256, 0, st>>>(planes[0], planes[1], planes[2], n, d_flag);
+        nx = K * (size_t)max_points_per_centroid;
+        std::vector<uint32_t> pick = rand_perm_prefix(n, nx, 1234u);
+        d_pick = mem.alloc<uint32_t>(nx);
+        PB_CUDA_OK(cudaMemcpyAsync(d_pick, pick.data(), nx * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        PB_CUDA_OK(cudaStreamSynchronize(st));
+    }
+    float *d_x0 = mem.alloc<float>(nx), *d_x1 = mem.alloc<float>(nx), *d_x2 = mem.alloc<float>(nx);
+    float *d_wf = d_w ? mem.alloc<float>(nx) : nullptr;
+    k_to_f32<<<grid, 256, 0, st>>>(planes[0], planes[1], planes[2], d_w, d_pick, nx, d_x0, d_x1, d_x2, d_wf, d_flag);
+    PB_CUDA_OK(cudaGetLastError());
+    if (launches) *launches += 2;
+    int flag = 0;
+    PB_CUDA_OK(cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PB_CUDA_OK(cudaStreamSynchronize(st));
+    if (flag) { finish(); return; } // "input contains NaN's or Inf's" -> exception -> unrefined centres
+    if (nx == K) { // Clustering.cpp:330-352: centroids = the first k input vectors
+        std::vector<float> h(3 * K);
+        for (int j = 0; j < 3; j++) {
+            std::vector<double> tmp(K);
+            PB_CUDA_OK(cudaMemcpy(tmp.data(), planes[j], K * sizeof(double), cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < K; i++) h[3 * i + j] = (float)tmp[i];
+        }
+        cen = h;
+        finish();
+        return;
+    }
+    pb_kmeans_device(d_x0, d_x1, d_x2, d_wf, nx, cen, (int)K, niter, sm_count, st, launches);
+    finish();
+}

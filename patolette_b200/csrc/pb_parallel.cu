@@ -1,0 +1,438 @@
+// pb_parallel.cu - the order-independent (exactly parallelisable) kernels:
+// projections + min/max, bucket ids, split objective, stable multi-class scatter,
+// nearest-palette assignment.  All are HBM-streaming kernels over planar f64.
+#include "pb_common.cuh"
+#include "pb_kernels.h"
+
+namespace {
+
+constexpr int PAR_THREADS = 256;
+constexpr int PAR_CHUNK = 4096; // pixels per CTA visit
+
+// ---------------------------------------------------------------------------------
+// Projections on the principal axis + exact min / max (sort.c:43-59).
+// min/max are order-independent, so a block reduction + one ordered-uint atomic per
+// CTA is bit-exact.  24 B read per pixel.
+// ---------------------------------------------------------------------------------
+__global__ void k_split_init(PbSplit *sp, int nseg) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nseg) {
+        sp[i].mn_enc = ~0ULL;
+        sp[i].mx_enc = 0ULL;
+        sp[i].split = 0;
+        sp[i].nleft = 0;
+    }
+}
+
+__global__ void __launch_bounds__(PAR_THREADS) k_dots_minmax(PbPlanes b0, PbPlanes b1,
+                                                             const PbSeg *__restrict__ segs,
+                                                             const double *__restrict__ axes,
+                                                             PbSplit *__restrict__ sp) {
+    const int seg = blockIdx.y;
+    const PbSeg sg = segs[seg];
+    const PbPlanes &P = sg.buf ? b1 : b0;
+    const double x0 = axes[seg * 3], x1 = axes[seg * 3 + 1], x2 = axes[seg * 3 + 2];
+    const double *c0 = P.c[0] + sg.lo, *c1 = P.c[1] + sg.lo, *c2 = P.c[2] + sg.lo;
+    unsigned long long mn = ~0ULL, mx = 0ULL;
+    const uint32_t tail0 = sg.n - (sg.n & 3u); // first row of dgemv's scalar tail
+    for (uint32_t base = blockIdx.x * PAR_CHUNK; base < sg.n; base += gridDim.x * PAR_CHUNK) {
+        const uint32_t end = min(base + (uint32_t)PAR_CHUNK, sg.n);
+        for (uint32_t i = base + threadIdx.x; i < end; i += PAR_THREADS) {
+            const unsigned long long e = pb_ord_encode(pb_dgemv_row3(c0[i], c1[i], c2[i], x0, x1, x2, i >= tail0));
+            mn = min(mn, e);
+            mx = max(mx, e);
+        }
+    }
+    for (int o = 16; o; o >>= 1) {
+        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    __shared__ unsigned long long smn[PAR_THREADS / 32], smx[PAR_THREADS / 32];
+    if ((threadIdx.x & 31) == 0) { smn[threadIdx.x >> 5] = mn; smx[threadIdx.x >> 5] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < PAR_THREADS / 32; w++) { mn = min(mn, smn[w]); mx = max(mx, smx[w]); }
+        if (mn != ~0ULL || mx != 0ULL) {
+            atomicMin(&sp[seg].mn_enc, mn);
+            atomicMax(&sp[seg].mx_enc, mx);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// Bucket ids (sort.c:61-87).  24 B read + 2 B written per pixel.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(PAR_THREADS) k_buckets(PbPlanes b0, PbPlanes b1,
+                                                         const PbSeg *__restrict__ segs,
+                                                         const double *__restrict__ axes,
+                                                         PbSplit *__restrict__ sp,
+                                                         uint16_t *__restrict__ bucket) {
+    const int seg = blockIdx.y;
+    const PbSeg sg = segs[seg];
+    const PbPlanes &P = sg.buf ? b1 : b0;
+    const double x0 = axes[seg * 3], x1 = axes[seg * 3 + 1], x2 = axes[seg * 3 + 2];
+    const double *c0 = P.c[0] + sg.lo, *c1 = P.c[1] + sg.lo, *c2 = P.c[2] + sg.lo;
+    uint16_t *bk = bucket + sg.lo;
+    const double mn = pb_ord_decode(sp[seg].mn_enc), mx = pb_ord_decode(sp[seg].mx_enc);
+    const bool degenerate = __dsub_rn(mx, mn) < PB_DELTA;
+    const double s = 1.0 / __dsub_rn(mx, mn);
+    const uint32_t tail0 = sg.n - (sg.n & 3u);
+    if (blockIdx.x == 0 && threadIdx.x == 0) sp[seg].degenerate = degenerate;
+    for (uint32_t base = blockIdx.x * PAR_CHUNK; base < sg.n; base += gridDim.x * PAR_CHUNK) {
+        const uint32_t end = min(base + (uint32_t)PAR_CHUNK, sg.n);
+        for (uint32_t i = base + threadIdx.x; i < end; i += PAR_THREADS) {
+            uint32_t b;
+            if (degenerate) {
+                b = i % PB_BUCKETS; // sort.c:66-75 round-robin
+            } else {
+                const double dot = pb_dgemv_row3(c0[i], c1[i], c2[i], x0, x1, x2, i >= tail0);
+                const double ratio = __dmul_rn(__dsub_rn(dot, mn), s);
+                const unsigned long long q = (unsigned long long)__dmul_rn((double)PB_BUCKETS, ratio);
+                b = q < PB_BUCKETS - 1 ? (uint32_t)q : PB_BUCKETS - 1;
+            }
+            bk[i] = (uint16_t)b;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// Split objective over the 512 cumulative bucket sums (local.c:137-171).
+// One CTA of 512 threads per cluster.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(PB_BUCKETS) k_split_select(const double *__restrict__ bsums,
+                                                             const uint32_t *__restrict__ class_start,
+                                                             PbSplit *__restrict__ sp) {
+    __shared__ double cs[3][PB_BUCKETS];
+    __shared__ unsigned long long sz[PB_BUCKETS];
+    __shared__ double obj[PB_BUCKETS];
+    __shared__ int loc[PB_BUCKETS];
+    const int seg = blockIdx.x, i = threadIdx.x;
+    const double *in = bsums + (size_t)seg * PB_BUCKETS * 4;
+    sz[i] = (unsigned long long)__double_as_longlong(in[i * 4]);
+    cs[0][i] = in[i * 4 + 1];
+    cs[1][i] = in[i * 4 + 2];
+    cs[2][i] = in[i * 4 + 3];
+    __syncthreads();
+    if (i < 3) { // local.c:137-141: sums[i] += sums[i-1], strictly left to right
+        double run = cs[i][0];
+        for (int b = 1; b < PB_BUCKETS; b++) { run = __dadd_rn(cs[i][b], run); cs[i][b] = run; }
+    } else if (i == 3) { // local.c:144-146
+        unsigned long long run = sz[0];
+        for (int b = 1; b < PB_BUCKETS; b++) { run += sz[b]; sz[b] = run; }
+    }
+    __syncthreads();
+    double o = 0.0;
+    const double sl = (double)sz[i], sr = (double)(sz[PB_BUCKETS - 1] - sz[i]);
+#pragma unroll
+    for (int j = 0; j < 3; j++) { // local.c:149-168
+        const double csl = cs[j][i];
+        const double csr = __dsub_rn(cs[j][PB_BUCKETS - 1], csl);
+        double v = 0.0;
+        if (sl != 0) v = __dadd_rn(v, __ddiv_rn(__dmul_rn(csl, csl), sl));
+        if (sr != 0) v = __dadd_rn(v, __ddiv_rn(__dmul_rn(csr, csr), sr));
+        o = __dadd_rn(o, v);
+    }
+    obj[i] = o;
+    loc[i] = i;
+    __syncthreads();
+    // vector.c:26-46 maxloc: strict '>' scanning upward == lowest index among the maxima
+    for (int half = PB_BUCKETS / 2; half; half >>= 1) {
+        if (i < half) {
+            const double a = obj[i], b = obj[i + half];
+            if (b > a || (b == a && loc[i + half] < loc[i])) { obj[i] = b; loc[i] = loc[i + half]; }
+        }
+        __syncthreads();
+    }
+    if (i == 0) {
+        const uint32_t *cst = class_start + (size_t)seg * (PB_BUCKETS + 1);
+        sp[seg].split = (uint32_t)loc[0];
+        sp[seg].nleft = cst[loc[0] + 1] - cst[0];
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// Stable multi-class ranking and scatter.
+// A warp owns a tile of SC_TILE consecutive positions and walks it row by row (32
+// positions per row) so that ranks follow position order.  Phase 1 counts classes per
+// tile, phase 2 turns the [tile][class] table into exclusive offsets (class-major
+// order, i.e. all of class 0 first), phase 3 re-walks each tile and uses
+// __match_any_sync to rank same-class lanes inside a row against a running per-class
+// counter in shared memory.
+// ---------------------------------------------------------------------------------
+constexpr int SC_ROWS = 64;
+constexpr int SC_TILE = SC_ROWS * 32;
+
+struct ClsCtx {
+    int mode;
+    const uint16_t *bucket;
+    const PbSplit *sp;
+    const uint8_t *lut;
+};
+__device__ __forceinline__ uint32_t cls_of(const ClsCtx &c, int seg, uint32_t pos) {
+    const uint32_t b = c.bucket[pos];
+    if (c.mode == PB_CLS_BUCKET) return b;
+    if (c.mode == PB_CLS_SPLIT) return b <= c.sp[seg].split ? 0u : 1u;
+    return c.lut[b];
+}
+
+__global__ void k_tile_hist(ClsCtx cc, int nclass, const PbSeg *__restrict__ segs, uint32_t tiles_cap,
+                            uint32_t *__restrict__ tile_hist) {
+    extern __shared__ uint32_t s_cnt[];
+    const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int seg = blockIdx.y;
+    const PbSeg sg = segs[seg];
+    const uint32_t tile = blockIdx.x * warps + warp;
+    uint32_t *cnt = s_cnt + warp * nclass;
+    if ((size_t)tile * SC_TILE >= sg.n) return;
+    for (int c = lane; c < nclass; c += 32) cnt[c] = 0;
+    __syncwarp();
+    const uint32_t beg = tile * SC_TILE, end = min(beg + (uint32_t)SC_TILE, sg.n);
+    for (uint32_t i = beg + lane; i < end; i += 32) atomicAdd(&cnt[cls_of(cc, seg, sg.lo + i)], 1u);
+    __syncwarp();
+    uint32_t *out = tile_hist + ((size_t)seg * tiles_cap + tile) * nclass;
+    for (int c = lane; c < nclass; c += 32) out[c] = cnt[c];
+}
+
+// One warp per (segment, class): lanes split the tile range into 32 chunks, scan their
+// chunk serially, warp-scan the chunk totals, then write exclusive per-tile offsets.
+__global__ void k_tile_scan(int nclass, const PbSeg *__restrict__ segs, uint32_t tiles_cap,
+                            uint32_t *__restrict__ tile_hist, uint32_t *__restrict__ class_tot) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int seg = blockIdx.y;
+    if (warp >= nclass) return;
+    const uint32_t ntiles = (segs[seg].n + SC_TILE - 1) / SC_TILE;
+    uint32_t *h = tile_hist + (size_t)seg * tiles_cap * nclass + warp;
+    const uint32_t per = (ntiles + 31) / 32;
+    const uint32_t t0 = min(lane * per, ntiles), t1 = min(t0 + per, ntiles);
+    uint32_t sum = 0;
+    for (uint32_t t = t0; t < t1; t++) sum += h[(size_t)t * nclass];
+    uint32_t incl = sum;
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    uint32_t run = incl - sum;
+    for (uint32_t t = t0; t < t1; t++) {
+        const uint32_t v = h[(size_t)t * nclass];
+        h[(size_t)t * nclass] = run;
+        run += v;
+    }
+    if (lane == 31) class_tot[(size_t)seg * (nclass + 1) + warp] = incl;
+}
+
+// class_start[seg][c] = seg.lo + sum_{c' < c} tot[c']   (in place over class_tot)
+__global__ void k_class_start(int nclass, const PbSeg *__restrict__ segs, uint32_t *__restrict__ class_start) {
+    const int seg = blockIdx.x;
+    if (threadIdx.x != 0) return;
+    uint32_t *cs = class_start + (size_t)seg * (nclass + 1);
+    uint32_t run = segs[seg].lo;
+    for (int c = 0; c < nclass; c++) { const uint32_t v = cs[c]; cs[c] = run; run += v; }
+    cs[nclass] = run;
+}
+
+template <bool PAYLOAD>
+__global__ void k_scatter(ClsCtx cc, int nclass, const PbSeg *__restrict__ segs, uint32_t tiles_cap,
+                          const uint32_t *__restrict__ tile_hist, const uint32_t *__restrict__ class_start,
+                          uint32_t *__restrict__ ord, PbPlanes src0, PbPlanes src1, PbPlanes dst0, PbPlanes dst1,
+                          bool src_is_identity) {
+    extern __shared__ uint32_t s_cnt[];
+    const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int seg = blockIdx.y;
+    const PbSeg sg = segs[seg];
+    const uint32_t tile = blockIdx.x * warps + warp;
+    if ((size_t)tile * SC_TILE >= sg.n) return;
+    uint32_t *cnt = s_cnt + warp * (nclass + 1);
+    const uint32_t *hist = tile_hist + ((size_t)seg * tiles_cap + tile) * nclass;
+    const uint32_t *cst = class_start + (size_t)seg * (nclass + 1);
+    for (int c = lane; c < nclass; c += 32) cnt[c] = hist[c] + cst[c];
+    if (lane == 0) cnt[nclass] = 0;
+    __syncwarp();
+    const PbPlanes &S = sg.buf ? src1 : src0;
+    const PbPlanes &D = sg.buf ? dst1 : dst0;
+    const uint32_t beg = tile * SC_TILE, end = min(beg + (uint32_t)SC_TILE, sg.n);
+    for (uint32_t row = beg; row < end; row += 32) {
+        const uint32_t i = row + lane;
+        const bool valid = i < end;
+        const uint32_t pos = sg.lo + i;
+        const uint32_t c = valid ? cls_of(cc, seg, pos) : (uint32_t)nclass;
+        const uint32_t peers = __match_any_sync(0xffffffffu, c);
+        const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+        const uint32_t base = cnt[c];
+        __syncwarp();
+        if (rank == 0) cnt[c] = base + __popc(peers);
+        __syncwarp();
+        if (valid) {
+            const uint32_t dst = base + rank;
+            if (PAYLOAD) {
+                D.c[0][dst] = S.c[0][pos];
+                D.c[1][dst] = S.c[1][pos];
+                D.c[2][dst] = S.c[2][pos];
+                if (S.w) D.w[dst] = S.w[pos];
+                if (D.idx) D.idx[dst] = src_is_identity ? pos : S.idx[pos];
+            } else {
+                ord[dst] = pos;
+            }
+        }
+    }
+}
+
+__global__ void k_make_children(const PbSeg *__restrict__ segs, int nseg, const PbSplit *__restrict__ sp,
+                                PbSeg *__restrict__ children) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nseg) return;
+    const PbSeg sg = segs[i];
+    const uint32_t nl = sp[i].nleft;
+    children[2 * i] = PbSeg{sg.lo, nl, sg.buf ^ 1u, 0u};
+    children[2 * i + 1] = PbSeg{sg.lo + nl, sg.n - nl, sg.buf ^ 1u, 0u};
+}
+
+// ---------------------------------------------------------------------------------
+// Nearest palette entry (nearest.c:150-209 + the FLANN exact-1-NN contract): squared
+// L2 in f64, dimensions summed in order 0,1,2, strict '<' over ascending palette index.
+// Palette in shared memory (broadcast reads); 24 B read + 8 B written per pixel but
+// 9*K FP64 operations, so FP64-pipe bound for K >= ~16.
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_nearest(const double *__restrict__ c0, const double *__restrict__ c1,
+                                                 const double *__restrict__ c2, size_t n,
+                                                 const double *__restrict__ pal, int K,
+                                                 unsigned long long *__restrict__ map) {
+    extern __shared__ double s_pal[];
+    for (int i = threadIdx.x; i < K * 3; i += blockDim.x) s_pal[i] = pal[i];
+    __syncthreads();
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double x = c0[i], y = c1[i], z = c2[i];
+        double bd = 0.0;
+        int best = 0;
+#pragma unroll 4
+        for (int j = 0; j < K; j++) {
+            const double dx = __dsub_rn(x, s_pal[3 * j]), dy = __dsub_rn(y, s_pal[3 * j + 1]),
+                         dz = __dsub_rn(z, s_pal[3 * j + 2]);
+            const double dd = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+            if (j == 0 || dd < bd) { bd = dd; best = j; }
+        }
+        map[i] = (unsigned long long)best;
+    }
+}
+
+__global__ void k_labels(PbPlanes b0, PbPlanes b1, const PbSeg *__restrict__ segs, uint32_t *__restrict__ labels) {
+    const int seg = blockIdx.y;
+    const PbSeg sg = segs[seg];
+    const PbPlanes &P = sg.buf ? b1 : b0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < sg.n; i += gridDim.x * blockDim.x)
+        labels[P.idx[sg.lo + i]] = (uint32_t)seg;
+}
+
+inline int blocks_for(uint32_t max_n, int sm_count) {
+    uint32_t want = (max_n + PAR_CHUNK - 1) / PAR_CHUNK;
+    uint32_t cap = (uint32_t)sm_count * 8;
+    return (int)(want < cap ? (want ? want : 1) : cap);
+}
+
+} // namespace
+
+void pb_launch_dots_minmax(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t max_n,
+                           const double *d_axes, PbSplit *d_split, int sm_count, cudaStream_t st) {
+    if (nseg <= 0) return;
+    k_split_init<<<(nseg + 63) / 64, 64, 0, st>>>(d_split, nseg);
+    dim3 grid(blocks_for(max_n, sm_count), nseg);
+    k_dots_minmax<<<grid, PAR_THREADS, 0, st>>>(bufs[0], bufs[1], d_segs, d_axes, d_split);
+    PB_CUDA_OK(cudaGetLastError());
+}
+
+void pb_launch_buckets(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t max_n,
+                       const double *d_axes, PbSplit *d_split, uint16_t *d_bucket, int sm_count,
+                       cudaStream_t st) {
+    if (nseg <= 0) return;
+    dim3 grid(blocks_for(max_n, sm_count), nseg);
+    k_buckets<<<grid, PAR_THREADS, 0, st>>>(bufs[0], bufs[1], d_segs, d_axes, d_split, d_bucket);
+    PB_CUDA_OK(cudaGetLastError());
+}
+
+void pb_launch_split_select(const double *d_bucket_sums, const uint32_t *d_class_start, int nseg,
+                            PbSplit *d_split, cudaStream_t st) {
+    if (nseg <= 0) return;
+    k_split_select<<<nseg, PB_BUCKETS, 0, st>>>(d_bucket_sums, d_class_start, d_split);
+    PB_CUDA_OK(cudaGetLastError());
+}
+
+size_t pb_scatter_tiles(uint32_t n) { return ((size_t)n + SC_TILE - 1) / SC_TILE; }
+
+static int scatter_warps(int nclass) { return nclass <= 16 ? 8 : (nclass <= 1024 ? 4 : (nclass <= 8192 ? 2 : 1)); }
+
+void pb_launch_class_rank(int cls_mode, int nclass, const PbSeg *d_segs, int nseg, uint32_t max_n,
+                          const uint16_t *d_bucket, const PbSplit *d_split, const uint8_t *d_lut,
+                          uint32_t *d_tile_hist, uint32_t *d_class_start, cudaStream_t st) {
+    if (nseg <= 0) return;
+    const uint32_t tiles_cap = (uint32_t)pb_scatter_tiles(max_n ? max_n : 1);
+    const int warps = scatter_warps(nclass);
+    ClsCtx cc{cls_mode, d_bucket, d_split, d_lut};
+    dim3 g1((tiles_cap + warps - 1) / warps, nseg);
+    if ((size_t)warps * nclass * 4 > 48 * 1024)
+        PB_CUDA_OK(cudaFuncSetAttribute(k_tile_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, warps * nclass * 4));
+    k_tile_hist<<<g1, warps * 32, (size_t)warps * nclass * 4, st>>>(cc, nclass, d_segs, tiles_cap, d_tile_hist);
+    dim3 g2((nclass + 7) / 8, nseg);
+    k_tile_scan<<<g2, 256, 0, st>>>(nclass, d_segs, tiles_cap, d_tile_hist, d_class_start);
+    k_class_start<<<nseg, 32, 0, st>>>(nclass, d_segs, d_class_start);
+    PB_CUDA_OK(cudaGetLastError());
+}
+
+void pb_launch_scatter_ord(int cls_mode, int nclass, const PbSeg *d_segs, int nseg, uint32_t max_n,
+                           const uint16_t *d_bucket, const PbSplit *d_split, const uint8_t *d_lut,
+                           const uint32_t *d_tile_hist, const uint32_t *d_class_start, uint32_t *d_ord,
+                           cudaStream_t st) {
+    if (nseg <= 0) return;
+    const uint32_t tiles_cap = (uint32_t)pb_scatter_tiles(max_n ? max_n : 1);
+    const int warps = scatter_warps(nclass);
+    ClsCtx cc{cls_mode, d_bucket, d_split, d_lut};
+    dim3 g((tiles_cap + warps - 1) / warps, nseg);
+    PbPlanes none{};
+    if ((size_t)warps * (nclass + 1) * 4 > 48 * 1024)
+        PB_CUDA_OK(cudaFuncSetAttribute(k_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        warps * (nclass + 1) * 4));
+    k_scatter<false><<<g, warps * 32, (size_t)warps * (nclass + 1) * 4, st>>>(
+        cc, nclass, d_segs, tiles_cap, d_tile_hist, d_class_start, d_ord, none, none, none, none, false);
+    PB_CUDA_OK(cudaGetLastError());
+}
+
+void pb_launch_scatter_payload(int cls_mode, int nclass, const PbPlanes src[2], const PbPlanes dst[2],
+                               bool src_is_identity, const PbSeg *d_segs, int nseg, uint32_t max_n,
+                               const uint16_t *d_bucket, const PbSplit *d_split, const uint8_t *d_lut,
+                               const uint32_t *d_tile_hist, const uint32_t *d_class_start, cudaStream_t st) {
+    if (nseg <= 0) return;
+    const uint32_t tiles_cap = (uint32_t)pb_scatter_tiles(max_n ? max_n : 1);
+    const int warps = scatter_warps(nclass);
+    ClsCtx cc{cls_mode, d_bucket, d_split, d_lut};
+    dim3 g((tiles_cap + warps - 1) / warps, nseg);
+    k_scatter<true><<<g, warps * 32, (size_t)warps * (nclass + 1) * 4, st>>>(
+        cc, nclass, d_segs, tiles_cap, d_tile_hist, d_class_start, nullptr, src[0], src[1], dst[0], dst[1],
+        src_is_identity);
+    PB_CUDA_OK(cudaGetLastError());
+}
+
+void pb_launch_make_children(const PbSeg *d_segs, int nseg, const PbSplit *d_split, PbSeg *d_children,
+                             cudaStream_t st) {
+    if (nseg <= 0) return;
+    k_make_children<<<(nseg + 63) / 64, 64, 0, st>>>(d_segs, nseg, d_split, d_children);
+    PB_CUDA_OK(cudaGetLastError());
+}
+
+void pb_launch_nearest(const double *const planes[3], size_t n, const double *d_palette_rm, int K,
+                       unsigned long long *d_map, int sm_count, cudaStream_t st) {
+    if (n == 0) return;
+    size_t want = (n + 255) / 256, cap = (size_t)sm_count * 8;
+    const int grid = (int)(want < cap ? want : cap);
+    const size_t smem = (size_t)K * 3 * sizeof(double);
+    if (smem > 48 * 1024)
+        PB_CUDA_OK(cudaFuncSetAttribute(k_nearest, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_nearest<<<grid, 256, smem, st>>>(planes[0], planes[1], planes[2], n, d_palette_rm, K, d_map);
+    PB_CUDA_OK(cudaGetLastError());
+}
+
+void pb_launch_labels(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t max_n,
+                      uint32_t *d_labels, int sm_count, cudaStream_t st) {
+    if (nseg <= 0) return;
+    dim3 grid(blocks_for(max_n, sm_count), nseg);
+    k_labels<<<grid, 256, 0, st>>>(bufs[0], bufs[1], d_segs, d_labels);
+    PB_CUDA_OK(cudaGetLastError());
+}

@@ -1,0 +1,764 @@
+// pb_pipeline.cu - host orchestration of the pixel-array hot path and the C ABI.
+//
+// Mirrors the stage sequence of the reference's only public entry point
+// (lib/src/patolette.c:157-343): colour transform -> GQ (quantize/global.c) -> LQ
+// (quantize/local.c) -> palette (palette/create.c | refine.c) -> nearest map
+// (palette/nearest.c) | Riemersma dither (dither/riemersma.c) -> palette back to sRGB.
+// Every O(N) step is a CUDA kernel (pb_color.cu, pb_chain.cu, pb_parallel.cu,
+// pb_kmeans.cu, pb_dither.cu); the host keeps only O(K)/O(512^2) control logic: the
+// 3x3 eigen solves, the Wu dynamic programme over 512 buckets and the greedy
+// best-first selection.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../include/patolette_b200.h"
+#include "pb_common.cuh"
+#include "pb_host.h"
+#include "pb_kernels.h"
+#include "pb_pipeline.h"
+
+namespace {
+
+int g_device = 0;
+double g_timings[10] = {0};
+
+template <typename T>
+struct DevArr {
+    T *p = nullptr;
+    size_t n = 0;
+    void alloc(size_t count) {
+        release();
+        n = count;
+        if (count) PB_CUDA_OK(cudaMalloc(&p, count * sizeof(T)));
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    ~DevArr() { release(); }
+    DevArr() = default;
+    DevArr(const DevArr &) = delete;
+    DevArr &operator=(const DevArr &) = delete;
+};
+
+struct Timer {
+    cudaEvent_t e[2];
+    cudaStream_t st;
+    explicit Timer(cudaStream_t s) : st(s) {
+        cudaEventCreate(&e[0]);
+        cudaEventCreate(&e[1]);
+    }
+    ~Timer() {
+        cudaEventDestroy(e[0]);
+        cudaEventDestroy(e[1]);
+    }
+    void start() { cudaEventRecord(e[0], st); }
+    double stop() {
+        cudaEventRecord(e[1], st);
+        cudaEventSynchronize(e[1]);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e[0], e[1]);
+        return ms;
+    }
+};
+
+// ------------------------------------------------------------------------------------
+// GQ host logic: cumulative cell moments and Wu's dynamic programme
+// (quantize/cells.c:118-328, quantize/global.c:72-298).  512 buckets -> O(12 * 512^2).
+// ------------------------------------------------------------------------------------
+constexpr int CELLS = PB_BUCKETS + 1;
+struct CellMoments {
+    uint64_t w0[CELLS];
+    double w1[3][CELLS];
+    double w2[CELLS];
+    double wrs[3][3][CELLS]; // [r][s], r <= s
+};
+
+inline double sq(double x) { return x * x; }
+
+double cell_distortion(size_t a, size_t b, const CellMoments &m) { // cells.c:141-182
+    if (m.w0[a] == m.w0[b]) return 0;
+    return m.w2[b] - m.w2[a] -
+           (sq(m.w1[0][b] - m.w1[0][a]) + sq(m.w1[1][b] - m.w1[1][a]) + sq(m.w1[2][b] - m.w1[2][a])) /
+               (double)(m.w0[b] - m.w0[a]);
+}
+
+bool pca_axis_from_vcov(double v[9], double axis[3]) { // pca.c:122-149
+    double w[3];
+    if (!pb_eigen_solve3(v, w)) return false;
+    axis[0] = v[6]; axis[1] = v[7]; axis[2] = v[8];
+    return true;
+}
+
+bool cell_pca(size_t a, size_t b, const CellMoments &m, double axis[3]) { // cells.c:184-278
+    double v[9] = {0};
+    for (int s = 0; s < 3; s++)
+        for (int r = 0; r <= s; r++) {
+            double e = 0;
+            if (m.w0[a] != m.w0[b]) {
+                double cnt = (double)(m.w0[b] - m.w0[a]);
+                e = (m.wrs[r][s][b] - m.wrs[r][s][a]) / cnt -
+                    (m.w1[r][b] - m.w1[r][a]) * (m.w1[s][b] - m.w1[s][a]) / sq(cnt);
+            }
+            v[s * 3 + r] = e;
+        }
+    v[0 * 3 + 2] = v[2 * 3 + 0];
+    v[0 * 3 + 1] = v[1 * 3 + 0];
+    v[1 * 3 + 2] = v[2 * 3 + 1];
+    return pca_axis_from_vcov(v, axis);
+}
+
+double norm3(const double v[3]) { // vector.c:135-159
+    double s = 0;
+    for (int i = 0; i < 3; i++) s += pow(v[i], 2);
+    return sqrt(s);
+}
+
+double cell_bias(size_t a, size_t b, const double axis[3], const CellMoments &m) { // cells.c:280-328
+    double ca[3];
+    if (!cell_pca(a, b, m, ca)) return -1;
+    double norms = norm3(axis) * norm3(ca);
+    if (norms < PB_DELTA) return 0;
+    double dot = ca[0] * axis[0] + ca[1] * axis[1] + ca[2] * axis[2];
+    return fmin(1, fabs(dot / norms));
+}
+
+bool gq_should_terminate(const size_t *q, size_t qlen, const double axis[3], const CellMoments &m) {
+    // global.c:99-187 (thresholds :19-21)
+    double distortion = 0;
+    for (size_t j = 0; j + 1 < qlen; j++) distortion += cell_distortion(q[j], q[j + 1], m);
+    if (distortion < PB_DELTA) return true;
+    double bias = 0;
+    for (size_t i = 0; i + 1 < qlen; i++) {
+        double cd = cell_distortion(q[i], q[i + 1], m);
+        double cb = cell_bias(q[i], q[i + 1], axis, m);
+        if (cb < 0) return true;
+        if (cb < 0.9) continue;
+        bias += (cd / distortion) * cb;
+    }
+    return bias < 0.1;
+}
+
+void l_chain(const std::vector<double> &L, size_t ld, size_t k, size_t N, size_t *chain) { // global.c:72-97
+    size_t t = N;
+    for (size_t j = k - 1; j >= 1; j--) {
+        t = (size_t)L[t * ld + (j + 1)];
+        chain[j] = t;
+    }
+    chain[0] = 0;
+    chain[k] = N;
+}
+
+size_t principal_quantizer(size_t K, const CellMoments &m, size_t *q) { // global.c:189-298
+    const size_t N = CELLS - 1, max_k = 12;
+    double axis[3];
+    if (!cell_pca(0, N, m, axis)) return 0;
+    std::vector<double> E(N + 1, 0.0), E2(N + 1, 0.0);
+    size_t ls = std::max(K, N) + 1;
+    std::vector<double> L;
+    try {
+        L.assign(ls * ls, 0.0);
+    } catch (...) { return 0; }
+    for (size_t i = 1; i <= N; i++) E[i] = cell_distortion(0, i, m);
+    for (size_t i = 1; i <= K && i < ls; i++) L[i * ls + i] = (double)i;
+    size_t k_out = 1;
+    l_chain(L, ls, 1, N, q);
+    size_t kmax = std::min(max_k, K);
+    for (size_t k = 2; k <= kmax; k++) {
+        if (gq_should_terminate(q, k_out + 1, axis, m)) break;
+        E2 = E;
+        for (size_t n = k + 1; n <= N; n++) {
+            double cut = (double)(n - 1);
+            double e = E2[n - 1];
+            for (size_t t = n - 2; t >= k - 1; t--) {
+                double c = E2[t] + cell_distortion(t, n, m);
+                if (c < e) { cut = (double)t; e = c; }
+            }
+            L[n * ls + k] = cut;
+            E[n] = e;
+        }
+        l_chain(L, ls, k, N, q);
+        k_out = k;
+    }
+    return k_out;
+}
+
+// ------------------------------------------------------------------------------------
+// Device workspace for one image.
+// ------------------------------------------------------------------------------------
+struct HNode {
+    PbSeg seg;
+    PbStats st;
+};
+struct HPair {
+    bool valid = false;
+    HNode l, r;
+};
+
+struct Quantizer {
+    size_t N = 0;
+    bool weighted = false;
+    int sm_count = 148;
+    cudaStream_t st = nullptr;
+    long launches = 0;
+
+    DevArr<double> col[3], wgt;                // original order, quantisation space
+    DevArr<double> pc[2][3], pw[2];            // ping-pong permuted planes
+    DevArr<uint32_t> pidx[2];
+    DevArr<uint16_t> bucket;
+    DevArr<uint32_t> ord, tile_hist, cstart_b, cstart_s;
+    DevArr<double> bsums, axes;
+    DevArr<PbSeg> segs, children;
+    DevArr<PbStats> stats;
+    DevArr<PbSplit> split;
+    DevArr<uint8_t> lut;
+    PbPlanes orig{}, bufs[2]{};
+
+    static constexpr int MAXB = 16; // segments per batch
+
+    void init(size_t n, bool with_weights) {
+        N = n;
+        weighted = with_weights;
+        cudaDeviceProp prop;
+        PB_CUDA_OK(cudaSetDevice(g_device));
+        PB_CUDA_OK(cudaGetDeviceProperties(&prop, g_device));
+        sm_count = prop.multiProcessorCount;
+        PB_CUDA_OK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        for (int j = 0; j < 3; j++) col[j].alloc(n);
+        if (weighted) wgt.alloc(n);
+        orig = PbPlanes{{col[0].p, col[1].p, col[2].p}, nullptr, nullptr};
+    }
+    void init_tree() {
+        for (int b = 0; b < 2; b++) {
+            for (int j = 0; j < 3; j++) pc[b][j].alloc(N);
+            if (weighted) pw[b].alloc(N);
+            pidx[b].alloc(N);
+            bufs[b] = PbPlanes{{pc[b][0].p, pc[b][1].p, pc[b][2].p}, weighted ? pw[b].p : nullptr, pidx[b].p};
+        }
+        bucket.alloc(N);
+        ord.alloc(N);
+        tile_hist.alloc(2 * pb_scatter_tiles((uint32_t)N) * PB_BUCKETS + 64);
+        cstart_b.alloc(2 * (PB_BUCKETS + 1));
+        cstart_s.alloc(2 * 17);
+        bsums.alloc(2 * PB_BUCKETS * 10);
+        axes.alloc(MAXB * 3);
+        segs.alloc(MAXB);
+        children.alloc(2 * MAXB);
+        stats.alloc(2 * MAXB);
+        split.alloc(MAXB);
+        lut.alloc(PB_BUCKETS);
+    }
+    ~Quantizer() {
+        if (st) cudaStreamDestroy(st);
+    }
+    void sync() { PB_CUDA_OK(cudaStreamSynchronize(st)); }
+    template <typename T>
+    void h2d(T *dst, const T *src, size_t count) {
+        PB_CUDA_OK(cudaMemcpyAsync(dst, src, count * sizeof(T), cudaMemcpyHostToDevice, st));
+    }
+    template <typename T>
+    void d2h(T *dst, const T *src, size_t count) {
+        PB_CUDA_OK(cudaMemcpyAsync(dst, src, count * sizeof(T), cudaMemcpyDeviceToHost, st));
+    }
+
+    // ---- GQ (global.c:388-443): returns cluster count, 0 on error -------------------
+    size_t run_gq(size_t K, std::vector<HNode> &out) {
+        PbSeg whole{0u, (uint32_t)N, 0u, 0u};
+        PbStats hst;
+        const PbPlanes gq[2] = {orig, orig};
+        h2d(segs.p, &whole, 1);
+        pb_launch_pass_mean(gq, segs.p, 1, false, stats.p, st);     // global.c:407: UNWEIGHTED PCA
+        pb_launch_pass_centered(gq, segs.p, 1, false, stats.p, st);
+        launches += 2;
+        d2h(&hst, stats.p, 1);
+        sync();
+        double v[9], axis[3];
+        fill_vcov(hst, v);
+        if (!pca_axis_from_vcov(v, axis)) return 0;
+        h2d(axes.p, axis, 3);
+        pb_launch_dots_minmax(gq, segs.p, 1, (uint32_t)N, axes.p, split.p, sm_count, st);
+        pb_launch_buckets(gq, segs.p, 1, (uint32_t)N, axes.p, split.p, bucket.p, sm_count, st);
+        pb_launch_class_rank(PB_CLS_BUCKET, PB_BUCKETS, segs.p, 1, (uint32_t)N, bucket.p, split.p, lut.p,
+                             tile_hist.p, cstart_b.p, st);
+        pb_launch_scatter_ord(PB_CLS_BUCKET, PB_BUCKETS, segs.p, 1, (uint32_t)N, bucket.p, split.p, lut.p,
+                              tile_hist.p, cstart_b.p, ord.p, st);
+        pb_launch_bucket_chains_gq(orig, ord.p, cstart_b.p, bsums.p, st);
+        launches += 9;
+        std::vector<double> hs(PB_BUCKETS * 10);
+        std::vector<uint32_t> hcs(PB_BUCKETS + 1);
+        d2h(hs.data(), bsums.p, hs.size());
+        d2h(hcs.data(), cstart_b.p, hcs.size());
+        sync();
+        // cells.c:53-139: bucket b lives in 1-based slot b + 1; then prefix sums
+        static thread_local CellMoments m;
+        memset(&m, 0, sizeof m);
+        for (int b = 0; b < PB_BUCKETS; b++) {
+            const double *s = &hs[(size_t)b * 10];
+            m.w0[b + 1] = hcs[b + 1] - hcs[b];
+            m.w1[0][b + 1] = s[0]; m.w1[1][b + 1] = s[1]; m.w1[2][b + 1] = s[2];
+            m.w2[b + 1] = s[3];
+            m.wrs[0][0][b + 1] = s[4]; m.wrs[0][1][b + 1] = s[5]; m.wrs[1][1][b + 1] = s[6];
+            m.wrs[0][2][b + 1] = s[7]; m.wrs[1][2][b + 1] = s[8]; m.wrs[2][2][b + 1] = s[9];
+        }
+        for (int i = 1; i < CELLS; i++) {
+            m.w0[i] += m.w0[i - 1];
+            m.w2[i] += m.w2[i - 1];
+            for (int j = 0; j < 3; j++) m.w1[j][i] += m.w1[j][i - 1];
+            for (int s = 0; s < 3; s++)
+                for (int r = 0; r <= s; r++) m.wrs[r][s][i] += m.wrs[r][s][i - 1];
+        }
+        size_t q[16];
+        size_t cells = principal_quantizer(K, m, q);
+        if (cells == 0) return 0;
+        // global.c:322-332: bucket -> first cell j with bucket + 1 <= q[j + 1]
+        uint8_t hl[PB_BUCKETS];
+        for (size_t b = 0; b < PB_BUCKETS; b++) {
+            hl[b] = 0;
+            for (size_t j = 0; j < cells; j++)
+                if (b + 1 <= q[j + 1]) { hl[b] = (uint8_t)j; break; }
+        }
+        h2d(lut.p, hl, PB_BUCKETS);
+        // global.c:334-356: per-cell ascending index lists == stable scatter by cell
+        pb_launch_class_rank(PB_CLS_LUT, (int)cells, segs.p, 1, (uint32_t)N, bucket.p, split.p, lut.p,
+                             tile_hist.p, cstart_s.p, st);
+        PbPlanes src = orig;
+        src.w = weighted ? wgt.p : nullptr;
+        const PbPlanes srcs[2] = {src, src};
+        pb_launch_scatter_payload(PB_CLS_LUT, (int)cells, srcs, bufs, true, segs.p, 1, (uint32_t)N, bucket.p,
+                                  split.p, lut.p, tile_hist.p, cstart_s.p, st);
+        launches += 4;
+        std::vector<uint32_t> cst(cells + 1);
+        d2h(cst.data(), cstart_s.p, cells + 1);
+        sync();
+        out.resize(cells);
+        std::vector<PbSeg> hsegs(cells);
+        for (size_t j = 0; j < cells; j++) hsegs[j] = PbSeg{cst[j], cst[j + 1] - cst[j], 0u, 0u};
+        h2d(segs.p, hsegs.data(), cells);
+        pb_launch_pass_mean(bufs, segs.p, (int)cells, weighted, stats.p, st);
+        pb_launch_pass_centered(bufs, segs.p, (int)cells, weighted, stats.p, st);
+        launches += 2;
+        std::vector<PbStats> hstats(cells);
+        d2h(hstats.data(), stats.p, cells);
+        sync();
+        for (size_t j = 0; j < cells; j++) out[j] = HNode{hsegs[j], hstats[j]};
+        return cells;
+    }
+
+    static void fill_vcov(const PbStats &s, double v[9]) {
+        // pca.c:84-97: V(j,k) = sum / w_sum; column-major, dsyev reads the lower triangle (j >= k)
+        static const int jj[6] = {0, 1, 1, 2, 2, 2}, kk[6] = {0, 0, 1, 0, 1, 2};
+        for (int t = 0; t < 6; t++) {
+            double e = s.cov[t] / s.wsum;
+            v[kk[t] * 3 + jj[t]] = e;
+            v[jj[t] * 3 + kk[t]] = e;
+        }
+    }
+
+    // ---- split_cluster (local.c:179-254) for up to two clusters at once -------------
+    void eval_split(HNode *const nodes[], HPair *const outs[], int count) {
+        PbSeg hsegs[2];
+        double haxes[6];
+        int map[2], nb = 0;
+        uint32_t max_n = 0;
+        for (int i = 0; i < count; i++) {
+            outs[i]->valid = false;
+            if (nodes[i]->seg.n <= 1) continue; // local.c:187
+            double v[9], axis[3];
+            fill_vcov(nodes[i]->st, v);
+            if (!pca_axis_from_vcov(v, axis)) continue; // local.c:193-196
+            hsegs[nb] = nodes[i]->seg;
+            memcpy(&haxes[3 * nb], axis, sizeof axis);
+            max_n = std::max(max_n, nodes[i]->seg.n);
+            map[nb++] = i;
+        }
+        if (nb == 0) return;
+        h2d(segs.p, hsegs, nb);
+        h2d(axes.p, haxes, 3 * nb);
+        pb_launch_dots_minmax(bufs, segs.p, nb, max_n, axes.p, split.p, sm_count, st);
+        pb_launch_buckets(bufs, segs.p, nb, max_n, axes.p, split.p, bucket.p, sm_count, st);
+        pb_launch_class_rank(PB_CLS_BUCKET, PB_BUCKETS, segs.p, nb, max_n, bucket.p, split.p, lut.p, tile_hist.p,
+                             cstart_b.p, st);
+        pb_launch_scatter_ord(PB_CLS_BUCKET, PB_BUCKETS, segs.p, nb, max_n, bucket.p, split.p, lut.p, tile_hist.p,
+                              cstart_b.p, ord.p, st);
+        pb_launch_bucket_chains_lq(bufs, segs.p, nb, weighted, ord.p, cstart_b.p, bsums.p, st);
+        pb_launch_split_select(bsums.p, cstart_b.p, nb, split.p, st);
+        pb_launch_class_rank(PB_CLS_SPLIT, 2, segs.p, nb, max_n, bucket.p, split.p, lut.p, tile_hist.p, cstart_s.p,
+                             st);
+        const PbPlanes swapped[2] = {bufs[1], bufs[0]};
+        pb_launch_scatter_payload(PB_CLS_SPLIT, 2, bufs, swapped, false, segs.p, nb, max_n, bucket.p, split.p,
+                                  lut.p, tile_hist.p, cstart_s.p, st);
+        pb_launch_make_children(segs.p, nb, split.p, children.p, st);
+        pb_launch_pass_mean(bufs, children.p, 2 * nb, weighted, stats.p, st);
+        pb_launch_pass_centered(bufs, children.p, 2 * nb, weighted, stats.p, st);
+        launches += 17;
+        PbSeg hch[4];
+        PbStats hst[4];
+        d2h(hch, children.p, 2 * nb);
+        d2h(hst, stats.p, 2 * nb);
+        sync();
+        for (int b = 0; b < nb; b++) {
+            HPair *o = outs[map[b]];
+            o->valid = true;
+            o->l = HNode{hch[2 * b], hst[2 * b]};
+            o->r = HNode{hch[2 * b + 1], hst[2 * b + 1]};
+        }
+    }
+
+    // ---- LQ (local.c:318-404) -------------------------------------------------------
+    void run_lq(std::vector<HNode> &clusters, size_t K) {
+        size_t len = clusters.size();
+        if (len >= K) return;
+        clusters.resize(K);
+        std::vector<HPair> children(K);
+        for (size_t i = 0; i < len; i += 2) {
+            HNode *nn[2] = {&clusters[i], i + 1 < len ? &clusters[i + 1] : nullptr};
+            HPair *oo[2] = {&children[i], i + 1 < len ? &children[i + 1] : nullptr};
+            eval_split(nn, oo, i + 1 < len ? 2 : 1);
+        }
+        size_t i;
+        for (i = len; i < K; i++) {
+            // local.c:277-307 + vector.c:26-46: first maximum of d - (dl + dr)
+            size_t best = 0;
+            double bb = 0;
+            for (size_t j = 0; j < i; j++) {
+                double b = children[j].valid
+                               ? clusters[j].st.dist - (children[j].l.st.dist + children[j].r.st.dist)
+                               : 0;
+                if (j == 0 || b > bb) { bb = b; best = j; }
+            }
+            if (bb < PB_DELTA) break; // local.c:365-370
+            clusters[i] = children[best].l;     // local.c:375
+            clusters[best] = children[best].r;  // local.c:376
+            HNode *nn[2] = {&clusters[i], &clusters[best]};
+            HPair *oo[2] = {&children[i], &children[best]};
+            eval_split(nn, oo, 2);
+        }
+        clusters.resize(i);
+    }
+};
+
+void set_timing(int slot, double ms) { g_timings[slot] = ms; }
+
+const char *k_messages[6] = {
+    "Quantization successful.",
+    "Internal quantization error.",
+    "Image dimensions should be greater than 0.",
+    "Palette size should be greater than 0.",
+    "Image dimensions are too big.",
+    "CUDA error (no usable sm_100 device, or out of device memory).",
+};
+
+// Palette (K x 3 row-major, host) through one of the colour kernels.
+void palette_transform(Quantizer &qz, int which, std::vector<double> &pal_rm) {
+    const size_t K = pal_rm.size() / 3;
+    if (!K) return;
+    std::vector<double> planar(3 * K);
+    for (size_t j = 0; j < K; j++)
+        for (int c = 0; c < 3; c++) planar[c * K + j] = pal_rm[3 * j + c];
+    DevArr<double> d;
+    d.alloc(3 * K);
+    qz.h2d(d.p, planar.data(), 3 * K);
+    const double *src[3] = {d.p, d.p + K, d.p + 2 * K};
+    double *dst[3] = {d.p, d.p + K, d.p + 2 * K};
+    pb_launch_color(which, src, dst, K, qz.sm_count, qz.st);
+    qz.launches++;
+    qz.d2h(planar.data(), d.p, 3 * K);
+    qz.sync();
+    for (size_t j = 0; j < K; j++)
+        for (int c = 0; c < 3; c++) pal_rm[3 * j + c] = planar[c * K + j];
+}
+
+void colors_transform(Quantizer &qz, int which) {
+    const double *src[3] = {qz.col[0].p, qz.col[1].p, qz.col[2].p};
+    double *dst[3] = {qz.col[0].p, qz.col[1].p, qz.col[2].p};
+    pb_launch_color(which, src, dst, qz.N, qz.sm_count, qz.st);
+    qz.launches++;
+}
+
+void run_patolette(size_t width, size_t height, const double *data, const double *weights, size_t K,
+                   const patolette__QuantizationOptions *opt, double *palette, size_t *palette_map,
+                   int *exit_code) {
+    const size_t n = width * height;
+    memset(g_timings, 0, sizeof g_timings);
+    Quantizer qz;
+    qz.init(n, weights != nullptr);
+    Timer total(qz.st), stage(qz.st);
+    total.start();
+
+    stage.start(); // patolette.c:187-199: the library works on its own copy
+    for (int j = 0; j < 3; j++) qz.h2d(qz.col[j].p, data + (size_t)j * n, n);
+    if (weights) qz.h2d(qz.wgt.p, weights, n);
+    set_timing(1, stage.stop());
+
+    stage.start(); // patolette.c:201-207
+    if (opt->color_space == patolette__CIELuv) colors_transform(qz, PB_T_SRGB_TO_CIELUV);
+    else if (opt->color_space == patolette__ICtCp) colors_transform(qz, PB_T_SRGB_TO_ICTCP);
+    set_timing(2, stage.stop());
+    if (opt->verbose) printf("patolette ======== Palette generation \n");
+
+    qz.init_tree();
+    stage.start();
+    std::vector<HNode> clusters;
+    size_t count = qz.run_gq(K, clusters); // patolette.c:213
+    set_timing(3, stage.stop());
+    if (count == 0) { *exit_code = -1; return; }
+    if (opt->verbose) printf("patolette ======== Base cluster count: %zu\n", count);
+    stage.start();
+    qz.run_lq(clusters, K); // patolette.c:231
+    set_timing(4, stage.stop());
+    count = clusters.size();
+
+    std::vector<double> pal(3 * count); // palette/create.c:11-33
+    for (size_t j = 0; j < count; j++)
+        for (int c = 0; c < 3; c++) pal[3 * j + c] = clusters[j].st.mean[c];
+
+    if (opt->kmeans_niter > 0) { // patolette.c:248-261 -> refine.c:165-221
+        if (opt->verbose) printf("patolette ======== KMeans refinement\n");
+        stage.start();
+        const double *planes[3] = {qz.col[0].p, qz.col[1].p, qz.col[2].p};
+        size_t ms = opt->kmeans_max_samples > 65536 ? opt->kmeans_max_samples : 65536; // refine.c:21,87
+        pb_kmeans_refine(planes, qz.weighted ? qz.wgt.p : nullptr, n, pal, opt->kmeans_niter,
+                         (int)(ms / count), qz.sm_count, qz.st, &qz.launches);
+        set_timing(5, stage.stop());
+    }
+
+    if (!opt->palette_only) {
+        DevArr<unsigned long long> dmap;
+        dmap.alloc(n);
+        if (opt->dither) { // patolette.c:268-299
+            if (opt->verbose) printf("patolette ======== Dithering\n");
+            stage.start();
+            const int t = opt->color_space == patolette__CIELuv  ? PB_T_CIELUV_TO_REC2020
+                          : opt->color_space == patolette__ICtCp ? PB_T_ICTCP_TO_REC2020
+                                                                 : PB_T_SRGB_TO_REC2020;
+            colors_transform(qz, t);
+            palette_transform(qz, t, pal);
+            const double *planes[3] = {qz.col[0].p, qz.col[1].p, qz.col[2].p};
+            // riemersma.c:452-456: a 1x1 image is never dithered; the map keeps the caller's bytes
+            if (palette_map) qz.h2d(dmap.p, (const unsigned long long *)palette_map, n <= 1 ? n : 0);
+            pb_dither_riemersma(planes, width, height, pal, dmap.p, qz.sm_count, qz.st, &qz.launches);
+            palette_transform(qz, PB_T_REC2020_TO_SRGB, pal);
+            set_timing(7, stage.stop());
+        } else { // patolette.c:300-324
+            if (opt->verbose) printf("patolette ======== NN mapping\n");
+            stage.start();
+            if (opt->color_space == patolette__CIELuv) {
+                colors_transform(qz, PB_T_CIELUV_TO_ICTCP);
+                palette_transform(qz, PB_T_CIELUV_TO_ICTCP, pal);
+            }
+            DevArr<double> dpal;
+            dpal.alloc(3 * count);
+            qz.h2d(dpal.p, pal.data(), 3 * count);
+            const double *planes[3] = {qz.col[0].p, qz.col[1].p, qz.col[2].p};
+            pb_launch_nearest(planes, n, dpal.p, (int)count, dmap.p, qz.sm_count, qz.st);
+            qz.launches++;
+            qz.sync();
+            // patolette.c:322-323, applied whatever the colour space was (reference bug B1)
+            palette_transform(qz, PB_T_ICTCP_TO_REC2020, pal);
+            palette_transform(qz, PB_T_REC2020_TO_SRGB, pal);
+            set_timing(6, stage.stop());
+        }
+        stage.start();
+        qz.d2h((unsigned long long *)palette_map, dmap.p, n);
+        set_timing(8, stage.stop());
+    }
+    for (size_t j = 0; j < K * 3; j++) palette[j] = -1.0; // patolette.c:328-330
+    for (int c = 0; c < 3; c++)
+        for (size_t j = 0; j < count; j++) palette[K * c + j] = pal[3 * j + c];
+    set_timing(0, total.stop());
+    g_timings[9] = (double)qz.launches;
+    *exit_code = 0;
+}
+
+} // namespace
+
+// ======================================================================================
+// C ABI
+// ======================================================================================
+extern "C" {
+
+void patolette(size_t width, size_t height, const double *data, const double *weights, size_t palette_size,
+               const patolette__QuantizationOptions *options, double *palette, size_t *palette_map,
+               int *exit_code) {
+    *exit_code = 0; // validate_arguments, patolette.c:61-95 (same order)
+    if (width * height == 0) { *exit_code = -2; return; }
+    if (palette_size < 1) { *exit_code = -3; return; }
+    if (width * height > (size_t)40000 * 40000) { *exit_code = -4; return; }
+    try {
+        run_patolette(width, height, data, weights, palette_size, options, palette, palette_map, exit_code);
+    } catch (const pb_cuda_error &) {
+        cudaGetLastError();
+        *exit_code = -5;
+    } catch (const std::bad_alloc &) {
+        *exit_code = -1;
+    }
+}
+
+const char *get_patolette_exit_code_info_message(int exit_code) {
+    int i = -exit_code;
+    if (i < 0 || i > 5) i = 1;
+    return k_messages[i];
+}
+
+patolette__QuantizationOptions *patolette_create_default_options(void) { // patolette.c:107-119
+    patolette__QuantizationOptions *o = (patolette__QuantizationOptions *)malloc(sizeof *o);
+    o->dither = true;
+    o->palette_only = false;
+    o->color_space = patolette__ICtCp;
+    o->kmeans_niter = 32;
+    o->kmeans_max_samples = 512 * 512;
+    o->verbose = false;
+    return o;
+}
+
+int patolette_b200_set_device(int device) {
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return -(int)e;
+    g_device = device;
+    return 0;
+}
+
+int patolette_b200_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    return e == cudaSuccess ? n : -(int)e;
+}
+
+void patolette_b200_set_lapack(const char *path) { pb_lapack_set_path(path); }
+const char *patolette_b200_lapack_source(void) { return pb_lapack_source(); }
+
+int patolette_b200_last_timings(double *out10) {
+    memcpy(out10, g_timings, sizeof g_timings);
+    return 0;
+}
+
+int patolette_b200_color_transform(int which, double *planar, size_t n) {
+    try {
+        Quantizer qz;
+        qz.init(n, false);
+        for (int j = 0; j < 3; j++) qz.h2d(qz.col[j].p, planar + (size_t)j * n, n);
+        colors_transform(qz, which);
+        for (int j = 0; j < 3; j++) qz.d2h(planar + (size_t)j * n, qz.col[j].p, n);
+        qz.sync();
+        return 0;
+    } catch (const pb_cuda_error &e) { return -(int)e.code; }
+}
+
+int patolette_b200_pow(const double *x, double y, double *out, size_t n) {
+    try {
+        Quantizer qz;
+        qz.init(n, false);
+        qz.h2d(qz.col[0].p, x, n);
+        pb_launch_pow(qz.col[0].p, y, qz.col[1].p, n, qz.sm_count, qz.st);
+        qz.d2h(out, qz.col[1].p, n);
+        qz.sync();
+        return 0;
+    } catch (const pb_cuda_error &e) { return -(int)e.code; }
+}
+
+int patolette_b200_quantize_clusters(const double *planar, size_t n, const double *weights, size_t palette_size,
+                                     uint32_t *labels, double *centers, size_t *count, size_t *gq_count) {
+    try {
+        Quantizer qz;
+        qz.init(n, weights != nullptr);
+        for (int j = 0; j < 3; j++) qz.h2d(qz.col[j].p, planar + (size_t)j * n, n);
+        if (weights) qz.h2d(qz.wgt.p, weights, n);
+        qz.init_tree();
+        std::vector<HNode> clusters;
+        size_t c = qz.run_gq(palette_size, clusters);
+        if (gq_count) *gq_count = c;
+        if (c == 0) return -1;
+        qz.run_lq(clusters, palette_size);
+        *count = clusters.size();
+        if (centers)
+            for (size_t j = 0; j < clusters.size(); j++)
+                for (int k = 0; k < 3; k++) centers[3 * j + k] = clusters[j].st.mean[k];
+        if (labels) {
+            DevArr<PbSeg> dsegs;
+            DevArr<uint32_t> dlab;
+            std::vector<PbSeg> hs(clusters.size());
+            uint32_t max_n = 0;
+            for (size_t j = 0; j < clusters.size(); j++) { hs[j] = clusters[j].seg; max_n = std::max(max_n, hs[j].n); }
+            dsegs.alloc(hs.size());
+            dlab.alloc(n);
+            qz.h2d(dsegs.p, hs.data(), hs.size());
+            pb_launch_labels(qz.bufs, dsegs.p, (int)hs.size(), max_n, dlab.p, qz.sm_count, qz.st);
+            qz.d2h(labels, dlab.p, n);
+            qz.sync();
+        }
+        return 0;
+    } catch (const pb_cuda_error &e) { return -(int)e.code; }
+}
+
+int patolette_b200_nearest(const double *planar, size_t n, const double *palette_rm, size_t K, size_t *map) {
+    try {
+        Quantizer qz;
+        qz.init(n, false);
+        for (int j = 0; j < 3; j++) qz.h2d(qz.col[j].p, planar + (size_t)j * n, n);
+        DevArr<double> dpal;
+        DevArr<unsigned long long> dmap;
+        dpal.alloc(3 * K);
+        dmap.alloc(n);
+        qz.h2d(dpal.p, palette_rm, 3 * K);
+        const double *planes[3] = {qz.col[0].p, qz.col[1].p, qz.col[2].p};
+        pb_launch_nearest(planes, n, dpal.p, (int)K, dmap.p, qz.sm_count, qz.st);
+        qz.d2h((unsigned long long *)map, dmap.p, n);
+        qz.sync();
+        return 0;
+    } catch (const pb_cuda_error &e) { return -(int)e.code; }
+}
+
+int patolette_b200_kmeans(const float *x, size_t n, size_t K, float *centers, const float *w, int niter,
+                          int max_points_per_centroid) {
+    // Mirrors faiss kmeans_clustering (Clustering.cpp:587-603) on host-provided f32 samples by
+    // widening them to the f64 planes the pipeline keeps on the device ((float)(double)f == f).
+    try {
+        if (n < K) return -1;
+        Quantizer qz;
+        qz.init(n, w != nullptr);
+        std::vector<double> tmp(n);
+        for (int j = 0; j < 3; j++) {
+            for (size_t i = 0; i < n; i++) tmp[i] = (double)x[3 * i + j];
+            qz.h2d(qz.col[j].p, tmp.data(), n);
+            qz.sync();
+        }
+        if (w) {
+            for (size_t i = 0; i < n; i++) tmp[i] = (double)w[i];
+            qz.h2d(qz.wgt.p, tmp.data(), n);
+            qz.sync();
+        }
+        std::vector<double> pal(3 * K);
+        for (size_t j = 0; j < 3 * K; j++) pal[j] = (double)centers[j];
+        const double *planes[3] = {qz.col[0].p, qz.col[1].p, qz.col[2].p};
+        pb_kmeans_refine(planes, w ? qz.wgt.p : nullptr, n, pal, niter, max_points_per_centroid, qz.sm_count, qz.st,
+                         &qz.launches);
+        for (size_t j = 0; j < 3 * K; j++) centers[j] = (float)pal[j];
+        return 0;
+    } catch (const pb_cuda_error &e) { return -(int)e.code; }
+}
+
+int patolette_b200_dither(const double *planar, size_t width, size_t height, const double *palette_rm, size_t K,
+                          size_t *map) {
+    try {
+        const size_t n = width * height;
+        Quantizer qz;
+        qz.init(n, false);
+        for (int j = 0; j < 3; j++) qz.h2d(qz.col[j].p, planar + (size_t)j * n, n);
+        DevArr<unsigned long long> dmap;
+        dmap.alloc(n);
+        qz.h2d(dmap.p, (const unsigned long long *)map, n);
+        std::vector<double> pal(palette_rm, palette_rm + 3 * K);
+        const double *planes[3] = {qz.col[0].p, qz.col[1].p, qz.col[2].p};
+        pb_dither_riemersma(planes, width, height, pal, dmap.p, qz.sm_count, qz.st, &qz.launches);
+        qz.d2h((unsigned long long *)map, dmap.p, n);
+        qz.sync();
+        return 0;
+    } catch (const pb_cuda_error &e) { return -(int)e.code; }
+}
+
+} // extern "C"

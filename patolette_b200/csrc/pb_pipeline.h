@@ -1,0 +1,18 @@
+// pb_pipeline.h - stage entry points implemented outside pb_pipeline.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+#include <vector>
+
+// KMeans refinement of the palette (pb_kmeans.cu).  planes: device f64 colours in the
+// quantisation space, original pixel order; d_w: device f64 weights or nullptr.
+void pb_kmeans_refine(const double *const planes[3], const double *d_w, size_t n, std::vector<double> &pal_rm,
+                      int niter, int max_points_per_centroid, int sm_count, cudaStream_t st, long *launches);
+// KMeans on device-resident planar f32 samples (used by the stage test entry point too).
+void pb_kmeans_device(const float *d_x0, const float *d_x1, const float *d_x2, const float *d_wf, size_t nx,
+                      std::vector<float> &cen, int K, int niter, int sm_count, cudaStream_t st, long *launches);
+// Riemersma dither (pb_dither.cu).  planes: device f64 linear-Rec2020 colours; writes d_map.
+void pb_dither_riemersma(const double *const planes[3], size_t width, size_t height,
+                         const std::vector<double> &pal_rm, unsigned long long *d_map, int sm_count,
+                         cudaStream_t st, long *launches);

@@ -1,0 +1,72 @@
+"""Seeded synthetic inputs shared by the golden generator, the tests and bench.py."""
+from __future__ import annotations
+
+import numpy as np
+
+
+def uniform_colors(width: int, height: int, seed: int) -> np.ndarray:
+    """N x 3 uniform [0,1) f64 ("sRGB by definition")."""
+    return np.random.default_rng(seed).random((width * height, 3))
+
+
+def image_like_colors(width: int, height: int, seed: int) -> np.ndarray:
+    """Smooth gradients + noise, quantised to 8 bits (/255): many duplicate colours and exact ties,
+    which uniform noise never produces."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:height, 0:width]
+    base = np.stack([xx / max(width, 1), yy / max(height, 1), (xx + yy) / max(width + height, 1)], -1).reshape(-1, 3)
+    c = base * 0.8 + 0.2 * rng.random((width * height, 3))
+    return np.round(c * 255) / 255
+
+
+def saliency_like_weights(width: int, height: int, seed: int) -> np.ndarray:
+    """w = 1 + 1024 * s^2 in [1, 1025] (mirrors 1 + sal^2 * N / tile^2 of patolette.pyx:313)."""
+    rng = np.random.default_rng(seed + 1000)
+    yy, xx = np.mgrid[0:height, 0:width]
+    s = 0.25 * (1 + np.sin(6 * np.pi * xx / width)) * (1 + np.cos(4 * np.pi * yy / height)) * rng.random((height, width))
+    return (1 + 1024 * s ** 2).reshape(-1)
+
+
+# name -> kwargs.  Small enough for the CPU checkers to finish in seconds.
+GOLDEN_CASES = {
+    "c1_512_k16_srgb": dict(w=512, h=512, K=16, seed=0, color_space=0, dither=False, kmeans_niter=0),
+    "512_k16_ictcp": dict(w=512, h=512, K=16, seed=0, color_space=2, dither=False, kmeans_niter=0),
+    "512_k16_cieluv": dict(w=512, h=512, K=16, seed=0, color_space=1, dither=False, kmeans_niter=0),
+    "512_k16_ictcp_dither": dict(w=512, h=512, K=16, seed=0, color_space=2, dither=True, kmeans_niter=0),
+    "512_k16_ictcp_kmeans10": dict(w=512, h=512, K=16, seed=0, color_space=2, dither=False, kmeans_niter=10),
+    "64_k256_ictcp": dict(w=64, h=64, K=256, seed=0, color_space=2, dither=False, kmeans_niter=0),
+    "1x1_k4_dither": dict(w=1, h=1, K=4, seed=0, color_space=2, dither=True, kmeans_niter=0),
+    "5x3_k64_kmeans": dict(w=5, h=3, K=64, seed=3, color_space=2, dither=True, kmeans_niter=3),
+    "4x4_k8_kmeans_seq": dict(w=4, h=4, K=8, seed=4, color_space=0, dither=False, kmeans_niter=3),
+    "300x200_k64_weighted": dict(w=300, h=200, K=64, seed=5, color_space=2, dither=True, kmeans_niter=5, weighted=True),
+    "300x200_k64_luv_weighted": dict(w=300, h=200, K=64, seed=6, color_space=1, dither=False, kmeans_niter=0, weighted=True),
+    "256_k64_imagelike": dict(w=256, h=256, K=64, seed=7, color_space=2, dither=False, kmeans_niter=0, image_like=True),
+    "256_k256_imagelike_luv": dict(w=256, h=256, K=256, seed=8, color_space=1, dither=True, kmeans_niter=4,
+                                   image_like=True, weighted=True),
+    "400x300_k32_palette_only": dict(w=400, h=300, K=32, seed=9, color_space=0, dither=True, kmeans_niter=4,
+                                     image_like=True, palette_only=True),
+    "333x77_k100_srgb_dither": dict(w=333, h=77, K=100, seed=10, color_space=0, dither=True, kmeans_niter=0),
+    "256_k200_fullkmeans": dict(w=256, h=256, K=200, seed=11, color_space=2, dither=False, kmeans_niter=6,
+                                kmeans_max_samples=256 * 256),
+    "constant_image": dict(w=32, h=32, K=8, seed=12, color_space=2, dither=True, kmeans_niter=0, constant=True),
+    "two_colors": dict(w=40, h=25, K=16, seed=13, color_space=2, dither=False, kmeans_niter=2, two_colors=True),
+}
+
+
+def make_case(spec: dict):
+    """-> (colors, weights | None, quantize kwargs)"""
+    w, h = spec["w"], spec["h"]
+    if spec.get("constant"):
+        colors = np.tile(np.array([[0.25, 0.5, 0.75]]), (w * h, 1))
+    elif spec.get("two_colors"):
+        rng = np.random.default_rng(spec["seed"])
+        pick = rng.integers(0, 2, w * h)
+        colors = np.where(pick[:, None] == 0, np.array([[0.1, 0.2, 0.3]]), np.array([[0.9, 0.6, 0.2]]))
+    elif spec.get("image_like"):
+        colors = image_like_colors(w, h, spec["seed"])
+    else:
+        colors = uniform_colors(w, h, spec["seed"])
+    weights = saliency_like_weights(w, h, spec["seed"]) if spec.get("weighted") else None
+    kw = dict(dither=spec["dither"], palette_only=spec.get("palette_only", False), color_space=spec["color_space"],
+              kmeans_niter=spec["kmeans_niter"], kmeans_max_samples=spec.get("kmeans_max_samples", 512 ** 2))
+    return np.ascontiguousarray(colors, dtype=np.float64), weights, kw

@@ -1,0 +1,213 @@
+"""GPU suite (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle on the
+same seeded inputs, against the frozen reference outputs, and - at sizes the oracle cannot
+reach in seconds - through size-independent properties.
+
+Bars (BASELINE.json north_star): palette_map bit-exact, palette floats bit-exact (tighter than
+the stated 1 ULP), pow/colour transforms bit-exact, dithered maps bit-exact (tighter than the
+stated +-1 LSB).  Nothing here reads /root/reference."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import sha
+from synth import GOLDEN_CASES, make_case, uniform_colors, image_like_colors, saliency_like_weights
+
+pytestmark = pytest.mark.gpu
+
+
+def cuda_quantize(lib, w, h, colors, K, weights=None, **kw):
+    from oracle.reflib import quantize_with
+    return quantize_with(lib, w, h, colors, K, weights=weights, **kw)
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float64).view(np.uint64)
+
+
+def assert_same_floats(a, b, what):
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    nan = np.isnan(a) & np.isnan(b)  # NaN payloads are not comparable across x86 and the GPU
+    same = (bits(a) == bits(b)) | nan
+    assert same.all(), f"{what}: {int((~same).sum())} of {same.size} values differ, max abs diff " \
+                       f"{np.nanmax(np.abs(a - b)[~same])}"
+
+
+# ---------------------------------------------------------------------------------- pow / colour
+@pytest.fixture(scope="module")
+def libm_pow(tmp_path_factory):
+    """out[i] = pow(x[i], y) through the host libm (numpy's own pow may use SVML, not glibc)."""
+    import os, subprocess
+    from conftest import ROOT
+    so = tmp_path_factory.mktemp("libm") / "libm_helper.so"
+    subprocess.run(["gcc", "-O2", "-shared", "-fPIC", os.path.join(ROOT, "tests", "native", "libm_helper.c"), "-o", str(so), "-lm"], check=True)
+    lib = C.CDLL(str(so))
+    lib.libm_pow.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_size_t]
+    lib.libm_pow.restype = None
+
+    def run(x, y, out):
+        lib.libm_pow(x.ctypes.data, y, out.ctypes.data, x.size)
+    return run
+
+
+@pytest.mark.parametrize("y", [2.4, 1 / 2.4, 0.1593017578125, 78.84375, 1 / 0.1593017578125, 1 / 78.84375, 1 / 3, 3.0])
+def test_device_pow_is_bit_exact_with_host_libm(cuda_lib, libm_pow, y):
+    rng = np.random.default_rng(int(y * 1000) % 97)
+    n = 1 << 20
+    x = np.concatenate([rng.random(n // 4), rng.random(n // 4) * 1e4, rng.random(n // 4) * 1e-4,
+                        np.exp((rng.random(n // 8) - 0.5) * 1400), -rng.random(n // 16),
+                        np.array([0.0, 1.0, np.inf, 5e-324, 1e-310, 1e308])])
+    out = np.empty_like(x)
+    assert cuda_lib.patolette_b200_pow(x.ctypes.data, y, out.ctypes.data, x.size) == 0
+    want = np.empty_like(x)
+    libm_pow(x, y, want)
+    assert_same_floats(out, want, f"pow(x, {y})")
+
+
+@pytest.mark.parametrize("which", range(6))
+def test_colour_transforms_bit_exact(cuda_lib, oracle, which):
+    n = 200_003
+    rng = np.random.default_rng(which)
+    src = rng.random((n, 3))
+    if which == 2:  # ICtCp input: take it from real sRGB colours
+        tmp = np.asfortranarray(src); oracle.lib.orc_color_transform(0, tmp.ctypes.data_as(C.c_void_p), C.c_size_t(n)); src = tmp
+    if which == 3:
+        tmp = np.asfortranarray(src); oracle.lib.orc_color_transform(1, tmp.ctypes.data_as(C.c_void_p), C.c_size_t(n)); src = tmp
+    if which == 5:
+        src = src * 1.2 - 0.1  # out-of-gamut linear values exercise the clamps
+    a = np.asfortranarray(src).copy(order="F"); b = a.copy(order="F")
+    oracle.lib.orc_color_transform(which, a.ctypes.data_as(C.c_void_p), C.c_size_t(n))
+    assert cuda_lib.patolette_b200_color_transform(which, b.ctypes.data, n) == 0
+    assert_same_floats(b, a, f"colour transform {which}")
+
+
+# ---------------------------------------------------------------------------------- stages
+@pytest.mark.parametrize("n,K,weighted,image_like", [(100_003, 32, False, False), (65_536, 64, True, False),
+                                                      (50_000, 16, False, True), (3, 8, False, False),
+                                                      (200_000, 256, True, True)])
+def test_cluster_tree_matches_oracle(cuda_lib, oracle, n, K, weighted, image_like):
+    """GQ + LQ on colours already in the quantisation space: identical partition and centres."""
+    w = h = None
+    side = int(np.ceil(np.sqrt(n)))
+    base = image_like_colors(side, side, 3)[:n] if image_like else uniform_colors(side, side, 3)[:n]
+    planar = np.asfortranarray(base)
+    wts = saliency_like_weights(side, side, 3)[:n].copy() if weighted else None
+    res = {}
+    for name, lib, fn in (("oracle", oracle.lib, "orc_quantize_clusters"), ("cuda", cuda_lib, "patolette_b200_quantize_clusters")):
+        labels = np.zeros(n, dtype=np.uint32); centers = np.zeros((K, 3)); cnt = C.c_size_t(0); gq = C.c_size_t(0)
+        f = getattr(lib, fn)
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+        rc = f(planar.ctypes.data, n, None if wts is None else wts.ctypes.data, K, labels.ctypes.data, centers.ctypes.data, C.byref(cnt), C.byref(gq))
+        assert rc == 0
+        res[name] = (labels, centers[:cnt.value].copy(), cnt.value, gq.value)
+    assert res["cuda"][2:] == res["oracle"][2:], "cluster counts differ"
+    assert np.array_equal(res["cuda"][0], res["oracle"][0]), "cluster membership differs"
+    assert_same_floats(res["cuda"][1], res["oracle"][1], "cluster centres")
+
+
+def test_nearest_map_matches_oracle(cuda_lib, oracle):
+    n, K = 300_001, 256
+    rng = np.random.default_rng(8)
+    planar = np.asfortranarray(rng.random((n, 3)))
+    pal = rng.random((K, 3)); pal[17] = pal[3]  # duplicate entry: lowest index must win
+    a = np.zeros(n, dtype=np.uintp); b = np.zeros(n, dtype=np.uintp)
+    oracle.lib.orc_fill_palette_map_nearest(planar.ctypes.data_as(C.c_void_p), C.c_size_t(n), pal.ctypes.data_as(C.c_void_p), C.c_size_t(K), a.ctypes.data_as(C.c_void_p))
+    assert cuda_lib.patolette_b200_nearest(planar.ctypes.data, n, pal.ctypes.data, K, b.ctypes.data) == 0
+    assert np.array_equal(a, b)
+    assert 17 not in b
+
+
+@pytest.mark.parametrize("n,K,weighted,mppc", [(40_000, 64, False, 10_000), (300_000, 32, True, 1024), (16, 8, False, 8192),
+                                                 (8, 8, False, 100), (5, 8, False, 100)])
+def test_kmeans_matches_oracle(cuda_lib, oracle, n, K, weighted, mppc):
+    rng = np.random.default_rng(n)
+    x = rng.random((n, 3)).astype(np.float32)
+    w = (1 + 50 * rng.random(n)).astype(np.float32) if weighted else None
+    c0 = x[rng.choice(n, K, replace=n < K)].copy() + np.float32(0.01)
+    ca, cb = c0.copy(), c0.copy()
+    f = oracle.lib.orc_kmeans
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    ra = f(x.ctypes.data, n, K, ca.ctypes.data, None if w is None else w.ctypes.data, 5, mppc)
+    rb = cuda_lib.patolette_b200_kmeans(x.ctypes.data, n, K, cb.ctypes.data, None if w is None else w.ctypes.data, 5, mppc)
+    assert (ra == 0) == (rb == 0)
+    assert np.array_equal(ca.view(np.uint32), cb.view(np.uint32)), f"max diff {np.abs(ca - cb).max()}"
+
+
+@pytest.mark.parametrize("W,H,K", [(64, 64, 16), (100, 37, 40), (1, 7, 4), (130, 257, 256), (1, 1, 3)])
+def test_dither_matches_oracle(cuda_lib, oracle, W, H, K):
+    n = W * H
+    rng = np.random.default_rng(W * 1000 + H)
+    planar = np.asfortranarray(rng.random((n, 3)))
+    pal = rng.random((K, 3))
+    a = np.full(n, 7, dtype=np.uintp); b = np.full(n, 7, dtype=np.uintp)
+    oracle.lib.orc_dither_riemersma(planar.ctypes.data_as(C.c_void_p), C.c_size_t(W), C.c_size_t(H), pal.ctypes.data_as(C.c_void_p), C.c_size_t(K), a.ctypes.data_as(C.c_void_p))
+    assert cuda_lib.patolette_b200_dither(planar.ctypes.data, W, H, pal.ctypes.data, K, b.ctypes.data) == 0
+    assert np.array_equal(a, b), f"{int((a != b).sum())} of {n} indices differ, first at {int(np.argmax(a != b))}"
+
+
+# ---------------------------------------------------------------------------------- end to end
+@pytest.mark.parametrize("name", sorted(GOLDEN_CASES))
+def test_pipeline_matches_golden_and_oracle(cuda_lib, oracle, golden, name):
+    spec = GOLDEN_CASES[name]
+    colors, weights, kw = make_case(spec)
+    code, pal, pmap = cuda_quantize(cuda_lib, spec["w"], spec["h"], colors, spec["K"], weights=weights, **kw)
+    ocode, opal, omap = oracle.quantize(spec["w"], spec["h"], colors, spec["K"], weights=weights, **kw)
+    assert code == ocode == golden["cases"][name]["exit_code"]
+    assert_same_floats(pal, opal, "palette vs oracle")
+    if omap is None:
+        assert pmap is None
+    else:
+        assert np.array_equal(pmap, omap), f"{int((pmap != omap).sum())} map entries differ from the oracle"
+        assert sha(pmap) == golden["cases"][name]["map_sha256"], "map differs from the frozen reference output"
+    if not np.isnan(opal).any():
+        assert sha(pal.ravel(order="F")) == golden["cases"][name]["palette_sha256"]
+
+
+def test_python_quantize_surface_on_gpu(cuda_lib, oracle):
+    import patolette_b200 as pb
+    colors = uniform_colors(96, 80, 21)
+    ok, pal, pmap, msg = pb.quantize(96, 80, colors, 24, dither=False, color_space=pb.ColorSpace_ICtCp, tile_size=0, kmeans_niter=0)
+    assert ok and msg == "Quantization successful."
+    assert pal.shape == (24, 3) and pal.flags.f_contiguous and pmap.dtype == np.uintp and pmap.shape == (96 * 80,)
+    code, opal, omap = oracle.quantize(96, 80, colors, 24, dither=False, color_space=2, kmeans_niter=0)
+    assert np.array_equal(pmap, omap)
+    assert_same_floats(pal, opal, "palette")
+    t = pb.last_timings()
+    assert t["launches"] > 0 and t["total"] > 0
+    ok, pal2, pmap2, _ = pb.quantize(96, 80, colors, 24, dither=False, tile_size=0, kmeans_niter=0, palette_only=True)
+    assert ok and pmap2 is None
+    ocode, opal2, _ = oracle.quantize(96, 80, colors, 24, dither=False, kmeans_niter=0, palette_only=True)
+    assert_same_floats(pal2, opal2, "palette_only palette (quantisation space, bug B2)")
+
+
+def test_unused_palette_rows_are_minus_one(cuda_lib):
+    colors = uniform_colors(5, 3, 1)
+    code, pal, pmap = cuda_quantize(cuda_lib, 5, 3, colors, 64, dither=False, color_space=2, kmeans_niter=0)
+    assert code == 0 and (pal[15:] == -1).all() and (pal[:15] != -1).any() and pmap.max() < 15
+
+
+# ---------------------------------------------------------------------------------- large-size properties
+def test_config2_scale_properties(cuda_lib):
+    """2048 x 2048, K=256, ICtCp, dither off (BASELINE config 2 at a quarter of the pixels): size-independent
+    invariants the domain offers.  (1) the map is idempotent under re-quantisation of the palette image in the NN
+    space: every pixel is assigned to its exact nearest palette entry (checked with an f64 brute force on a sample);
+    (2) determinism: two runs give identical bits; (3) all K entries are used on uniform noise."""
+    W = H = 2048; K = 256
+    colors = uniform_colors(W, H, 2)
+    code, pal, pmap = cuda_quantize(cuda_lib, W, H, colors, K, dither=False, color_space=2, kmeans_niter=0)
+    assert code == 0
+    code2, pal2, pmap2 = cuda_quantize(cuda_lib, W, H, colors, K, dither=False, color_space=2, kmeans_niter=0)
+    assert np.array_equal(pmap, pmap2) and np.array_equal(bits(pal), bits(pal2))
+    assert len(np.unique(pmap)) == K and pmap.max() == K - 1
+    assert ((pal >= 0) & (pal <= 1)).all()
+    # reconstruct in ICtCp on the device and verify nearest-ness on a 20k sample
+    idx = np.random.default_rng(0).choice(W * H, 20_000, replace=False)
+    sample = np.asfortranarray(colors[idx]); assert cuda_lib.patolette_b200_color_transform(0, sample.ctypes.data, idx.size) == 0
+    p = np.asfortranarray(pal.copy()); assert cuda_lib.patolette_b200_color_transform(0, p.ctypes.data, K) == 0
+    d = ((sample[:, None, :] - p[None, :, :]) ** 2).sum(-1)
+    best = d.min(1)
+    chosen = d[np.arange(idx.size), pmap[idx]]
+    # the returned palette went ICtCp -> sRGB -> ICtCp, so allow the round-trip's rounding in the comparison
+    assert (chosen <= best * (1 + 1e-9) + 1e-18).all()
