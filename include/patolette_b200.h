@@ -97,6 +97,20 @@ PB200_API int patolette_b200_kmeans(const float *x, size_t n, size_t K, float *c
 PB200_API int patolette_b200_dither(const double *planar, size_t width, size_t height,
                           const double *palette_rm, size_t K, size_t *map);
 
+/* Same pipeline with DEVICE-resident I/O: d_data / d_weights / d_palette_map are CUDA device
+ * pointers on the current device (layouts as for patolette()); palette stays a host pointer.
+ * Inputs are copied device-to-device first (never written), as patolette.c:187-199 copies. */
+PB200_API void patolette_b200_device(size_t width, size_t height, const double *d_data, const double *d_weights,
+                                     size_t palette_size, const patolette__QuantizationOptions *options,
+                                     double *palette, size_t *d_palette_map, int *exit_code);
+/* Run subsequent calls on the caller's CUDA stream (a cudaStream_t passed as void*; enable = 0
+ * restores the library's private stream).  Lets a harness bracket calls with its own events. */
+PB200_API int patolette_b200_set_stream(void *cuda_stream, int enable);
+/* Per-kernel CUDA-event profile: enable(1) resets and starts recording; json() resolves pending
+ * events and writes {"kernel": {"launches", "ms", "bytes"}} (returns the size needed). */
+PB200_API int patolette_b200_profile_enable(int on);
+PB200_API size_t patolette_b200_profile_json(char *buf, size_t cap);
+
 /* Timings of the last patolette() call on this process, milliseconds (CUDA events
  * on the library's stream; h2d/d2h include the host copies).  Keys in order:
  * total, h2d, color, gq, lq, kmeans, nearest, dither, d2h, and the number of

@@ -67,8 +67,10 @@ def quantize_with(lib, width, height, colors, palette_size, dither=True, palette
     opts = QuantizationOptions(bool(dither), bool(palette_only), int(color_space),
                                int(kmeans_niter), int(kmeans_max_samples), bool(verbose))
     code = C.c_int(0)
+    # each library binds its own (layout-identical) options class: cast to whatever it declared
+    popts = C.cast(C.pointer(opts), lib.patolette.argtypes[5])
     lib.patolette(width, height, data.ctypes.data if n else None,
-                  None if w is None else w.ctypes.data, palette_size, C.byref(opts),
+                  None if w is None else w.ctypes.data, palette_size, popts,
                   palette.ctypes.data if palette_size else None,
                   None if pmap is None else pmap.ctypes.data, C.byref(code))
     return code.value, palette, pmap

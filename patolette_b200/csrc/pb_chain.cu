@@ -22,6 +22,7 @@
 // staying bit-identical).
 #include "pb_common.cuh"
 #include "pb_kernels.h"
+#include "pb_prof.h"
 
 namespace {
 
@@ -275,6 +276,7 @@ __global__ void __launch_bounds__(BK_WARPS * 32) k_bucket_chains_gq(PbPlanes src
 void pb_launch_pass_mean(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, bool weighted,
                          PbStats *d_stats, cudaStream_t st) {
     if (nseg <= 0) return;
+    PbProfScope _prof("k_pass_mean", st);
     if (weighted) k_pass_mean<true><<<nseg, 32, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats);
     else k_pass_mean<false><<<nseg, 32, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats);
     PB_CUDA_OK(cudaGetLastError());
@@ -283,6 +285,7 @@ void pb_launch_pass_mean(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, 
 void pb_launch_pass_centered(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, bool weighted,
                              PbStats *d_stats, cudaStream_t st) {
     if (nseg <= 0) return;
+    PbProfScope _prof("k_pass_centered", st);
     if (weighted) k_pass_centered<true><<<nseg, 32, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats);
     else k_pass_centered<false><<<nseg, 32, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats);
     PB_CUDA_OK(cudaGetLastError());
@@ -294,14 +297,20 @@ void pb_launch_bucket_chains_lq(const PbPlanes bufs[2], const PbSeg *d_segs, int
     if (nseg <= 0) return;
     const int grid = (nseg * PB_BUCKETS + BK_WARPS - 1) / BK_WARPS;
     if (weighted)
+        { PbProfScope _prof("k_bucket_chains_lq", st);
         k_bucket_chains_lq<true><<<grid, BK_WARPS * 32, 0, st>>>(bufs[0], bufs[1], d_segs, nseg, d_ord, d_class_start, d_out);
+        }
     else
+        { PbProfScope _prof("k_bucket_chains_lq", st);
         k_bucket_chains_lq<false><<<grid, BK_WARPS * 32, 0, st>>>(bufs[0], bufs[1], d_segs, nseg, d_ord, d_class_start, d_out);
+        }
     PB_CUDA_OK(cudaGetLastError());
 }
 
 void pb_launch_bucket_chains_gq(const PbPlanes &src, const uint32_t *d_ord, const uint32_t *d_class_start,
                                 double *d_out, cudaStream_t st) {
+    { PbProfScope _prof("k_bucket_chains_gq", st);
     k_bucket_chains_gq<<<PB_BUCKETS / BK_WARPS, BK_WARPS * 32, 0, st>>>(src, d_ord, d_class_start, d_out);
+    }
     PB_CUDA_OK(cudaGetLastError());
 }

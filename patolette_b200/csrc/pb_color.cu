@@ -8,6 +8,7 @@
 // memory (lane-divergent table look-ups would serialise in constant memory).
 #include "pb_common.cuh"
 #include "pb_kernels.h"
+#include "pb_prof.h"
 #include "pow_glibc.h"
 
 namespace {
@@ -235,6 +236,7 @@ void pb_launch_color(int which, const double *const src[3], double *const dst[3]
     if (n == 0) return;
     ensure_tabs();
     int grid = grid_for(n, 256, sm_count);
+    PbProfScope _prof("k_color", st);
 #define PB_CASE(W) \
     case W: k_color<W><<<grid, 256, 0, st>>>(src[0], src[1], src[2], dst[0], dst[1], dst[2], n); break;
     switch (which) {
@@ -254,6 +256,8 @@ void pb_launch_color(int which, const double *const src[3], double *const dst[3]
 void pb_launch_pow(const double *x, double y, double *out, size_t n, int sm_count, cudaStream_t st) {
     if (n == 0) return;
     ensure_tabs();
+    { PbProfScope _prof("k_pow", st);
     k_pow<<<grid_for(n, 256, sm_count), 256, 0, st>>>(x, y, out, n);
+    }
     PB_CUDA_OK(cudaGetLastError());
 }

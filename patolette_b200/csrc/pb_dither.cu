@@ -23,6 +23,7 @@
 
 #include "pb_common.cuh"
 #include "pb_kernels.h"
+#include "pb_prof.h"
 #include "pb_pipeline.h"
 
 namespace {
@@ -214,16 +215,23 @@ void pb_dither_riemersma(const double *const planes[3], size_t width, size_t hei
         PB_CUDA_OK(cudaMemcpyAsync(d_qw, qw, sizeof qw, cudaMemcpyHostToDevice, st));
         size_t want = (n + 255) / 256, cap = (size_t)sm_count * 8;
         const int grid = (int)(want < cap ? want : cap);
+        { PbProfScope _prof("k_hilbert_rank", st);
         k_hilbert_rank<<<grid, 256, 0, st>>>((uint32_t)width, (uint32_t)height, level, d_rank);
+        }
+        { PbProfScope _prof("k_permute", st);
         k_permute<<<grid, 256, 0, st>>>(planes[0], planes[1], planes[2], d_rank, n, d_h[0], d_h[1], d_h[2]);
+        }
         const size_t smem = ((size_t)K * 6 + 2 * 3 * DT_TILE) * sizeof(double);
         if (smem > 48 * 1024)
             PB_CUDA_OK(cudaFuncSetAttribute(k_riemersma_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        { PbProfScope _prof("k_riemersma_chain", st);
         k_riemersma_chain<<<1, 32, smem, st>>>(d_h[0], d_h[1], d_h[2], n, d_pal, d_palw, K, d_qw, d_hidx);
+        }
+        { PbProfScope _prof("k_unpermute", st);
         k_unpermute<<<grid, 256, 0, st>>>(d_rank, d_hidx, n, d_map);
+        }
         PB_CUDA_OK(cudaGetLastError());
         PB_CUDA_OK(cudaStreamSynchronize(st));
-        if (launches) *launches += 4;
     } catch (...) {
         cleanup();
         throw;

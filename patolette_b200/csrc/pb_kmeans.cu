@@ -25,6 +25,7 @@
 
 #include "pb_common.cuh"
 #include "pb_kernels.h"
+#include "pb_prof.h"
 #include "pb_pipeline.h"
 
 namespace {
@@ -216,16 +217,18 @@ void pb_kmeans_device(const float *d_x0, const float *d_x1, const float *d_x2, c
     std::vector<float> sums((size_t)K * 4);
     for (int it = 0; it < niter; it++) { // Clustering.cpp:442-530
         PB_CUDA_OK(cudaMemcpyAsync(d_cen, cen.data(), cen.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+        { PbProfScope _prof("k_assign", st);
         k_assign<<<grid, 256, smem, st>>>(d_x0, d_x1, d_x2, nx, d_cen, K, nx < 20, d_assign);
+        }
         pb_launch_class_rank(PB_CLS_BUCKET, K, d_seg, 1, (uint32_t)nx, d_assign, nullptr, nullptr, d_tile_hist,
                              d_cstart, st);
         pb_launch_scatter_ord(PB_CLS_BUCKET, K, d_seg, 1, (uint32_t)nx, d_assign, nullptr, nullptr, d_tile_hist,
                               d_cstart, d_ord, st);
         const int cg = (K + KM_WARPS - 1) / KM_WARPS;
+        PbProfScope _prof("k_centroid_chains", st);
         if (d_wf) k_centroid_chains<true><<<cg, KM_WARPS * 32, 0, st>>>(d_x0, d_x1, d_x2, d_wf, d_ord, d_cstart, K, d_sums);
         else k_centroid_chains<false><<<cg, KM_WARPS * 32, 0, st>>>(d_x0, d_x1, d_x2, d_wf, d_ord, d_cstart, K, d_sums);
         PB_CUDA_OK(cudaGetLastError());
-        if (launches) *launches += 6;
         PB_CUDA_OK(cudaMemcpyAsync(sums.data(), d_sums, sums.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
         PB_CUDA_OK(cudaStreamSynchronize(st));
         // compute_centroids epilogue (Clustering.cpp:194-203)
@@ -276,7 +279,9 @@ void pb_kmeans_refine(const double *const planes[3], const double *d_w, size_t n
     uint32_t *d_pick = nullptr;
     const bool subsample = n > K * (size_t)max_points_per_centroid; // Clustering.cpp:311
     if (subsample) {
+        { PbProfScope _prof("k_scan_finite", st);
         k_scan_finite<<<grid, 256, 0, st>>>(planes[0], planes[1], planes[2], n, d_flag);
+        }
         nx = K * (size_t)max_points_per_centroid;
         std::vector<uint32_t> pick = rand_perm_prefix(n, nx, 1234u);
         d_pick = mem.alloc<uint32_t>(nx);
@@ -285,9 +290,10 @@ void pb_kmeans_refine(const double *const planes[3], const double *d_w, size_t n
     }
     float *d_x0 = mem.alloc<float>(nx), *d_x1 = mem.alloc<float>(nx), *d_x2 = mem.alloc<float>(nx);
     float *d_wf = d_w ? mem.alloc<float>(nx) : nullptr;
+    { PbProfScope _prof("k_to_f32", st);
     k_to_f32<<<grid, 256, 0, st>>>(planes[0], planes[1], planes[2], d_w, d_pick, nx, d_x0, d_x1, d_x2, d_wf, d_flag);
+    }
     PB_CUDA_OK(cudaGetLastError());
-    if (launches) *launches += 2;
     int flag = 0;
     PB_CUDA_OK(cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
     PB_CUDA_OK(cudaStreamSynchronize(st));

@@ -3,6 +3,7 @@
 // nearest-palette assignment.  All are HBM-streaming kernels over planar f64.
 #include "pb_common.cuh"
 #include "pb_kernels.h"
+#include "pb_prof.h"
 
 namespace {
 
@@ -334,9 +335,13 @@ inline int blocks_for(uint32_t max_n, int sm_count) {
 void pb_launch_dots_minmax(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t max_n,
                            const double *d_axes, PbSplit *d_split, int sm_count, cudaStream_t st) {
     if (nseg <= 0) return;
+    { PbProfScope _prof("k_split_init", st, false);
     k_split_init<<<(nseg + 63) / 64, 64, 0, st>>>(d_split, nseg);
+    }
     dim3 grid(blocks_for(max_n, sm_count), nseg);
+    { PbProfScope _prof("k_dots_minmax", st);
     k_dots_minmax<<<grid, PAR_THREADS, 0, st>>>(bufs[0], bufs[1], d_segs, d_axes, d_split);
+    }
     PB_CUDA_OK(cudaGetLastError());
 }
 
@@ -345,14 +350,18 @@ void pb_launch_buckets(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, ui
                        cudaStream_t st) {
     if (nseg <= 0) return;
     dim3 grid(blocks_for(max_n, sm_count), nseg);
+    { PbProfScope _prof("k_buckets", st);
     k_buckets<<<grid, PAR_THREADS, 0, st>>>(bufs[0], bufs[1], d_segs, d_axes, d_split, d_bucket);
+    }
     PB_CUDA_OK(cudaGetLastError());
 }
 
 void pb_launch_split_select(const double *d_bucket_sums, const uint32_t *d_class_start, int nseg,
                             PbSplit *d_split, cudaStream_t st) {
     if (nseg <= 0) return;
+    { PbProfScope _prof("k_split_select", st);
     k_split_select<<<nseg, PB_BUCKETS, 0, st>>>(d_bucket_sums, d_class_start, d_split);
+    }
     PB_CUDA_OK(cudaGetLastError());
 }
 
@@ -370,10 +379,16 @@ void pb_launch_class_rank(int cls_mode, int nclass, const PbSeg *d_segs, int nse
     dim3 g1((tiles_cap + warps - 1) / warps, nseg);
     if ((size_t)warps * nclass * 4 > 48 * 1024)
         PB_CUDA_OK(cudaFuncSetAttribute(k_tile_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, warps * nclass * 4));
+    { PbProfScope _prof("k_tile_hist", st, false);
     k_tile_hist<<<g1, warps * 32, (size_t)warps * nclass * 4, st>>>(cc, nclass, d_segs, tiles_cap, d_tile_hist);
+    }
     dim3 g2((nclass + 7) / 8, nseg);
+    { PbProfScope _prof("k_tile_scan", st, false);
     k_tile_scan<<<g2, 256, 0, st>>>(nclass, d_segs, tiles_cap, d_tile_hist, d_class_start);
+    }
+    { PbProfScope _prof("k_class_start", st, false);
     k_class_start<<<nseg, 32, 0, st>>>(nclass, d_segs, d_class_start);
+    }
     PB_CUDA_OK(cudaGetLastError());
 }
 
@@ -390,8 +405,10 @@ void pb_launch_scatter_ord(int cls_mode, int nclass, const PbSeg *d_segs, int ns
     if ((size_t)warps * (nclass + 1) * 4 > 48 * 1024)
         PB_CUDA_OK(cudaFuncSetAttribute(k_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         warps * (nclass + 1) * 4));
+    { PbProfScope _prof("k_scatter", st);
     k_scatter<false><<<g, warps * 32, (size_t)warps * (nclass + 1) * 4, st>>>(
         cc, nclass, d_segs, tiles_cap, d_tile_hist, d_class_start, d_ord, none, none, none, none, false);
+    }
     PB_CUDA_OK(cudaGetLastError());
 }
 
@@ -404,16 +421,20 @@ void pb_launch_scatter_payload(int cls_mode, int nclass, const PbPlanes src[2], 
     const int warps = scatter_warps(nclass);
     ClsCtx cc{cls_mode, d_bucket, d_split, d_lut};
     dim3 g((tiles_cap + warps - 1) / warps, nseg);
+    { PbProfScope _prof("k_scatter", st);
     k_scatter<true><<<g, warps * 32, (size_t)warps * (nclass + 1) * 4, st>>>(
         cc, nclass, d_segs, tiles_cap, d_tile_hist, d_class_start, nullptr, src[0], src[1], dst[0], dst[1],
         src_is_identity);
+    }
     PB_CUDA_OK(cudaGetLastError());
 }
 
 void pb_launch_make_children(const PbSeg *d_segs, int nseg, const PbSplit *d_split, PbSeg *d_children,
                              cudaStream_t st) {
     if (nseg <= 0) return;
+    { PbProfScope _prof("k_make_children", st, false);
     k_make_children<<<(nseg + 63) / 64, 64, 0, st>>>(d_segs, nseg, d_split, d_children);
+    }
     PB_CUDA_OK(cudaGetLastError());
 }
 
@@ -425,7 +446,9 @@ void pb_launch_nearest(const double *const planes[3], size_t n, const double *d_
     const size_t smem = (size_t)K * 3 * sizeof(double);
     if (smem > 48 * 1024)
         PB_CUDA_OK(cudaFuncSetAttribute(k_nearest, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { PbProfScope _prof("k_nearest", st);
     k_nearest<<<grid, 256, smem, st>>>(planes[0], planes[1], planes[2], n, d_palette_rm, K, d_map);
+    }
     PB_CUDA_OK(cudaGetLastError());
 }
 
@@ -433,6 +456,8 @@ void pb_launch_labels(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uin
                       uint32_t *d_labels, int sm_count, cudaStream_t st) {
     if (nseg <= 0) return;
     dim3 grid(blocks_for(max_n, sm_count), nseg);
+    { PbProfScope _prof("k_labels", st);
     k_labels<<<grid, 256, 0, st>>>(bufs[0], bufs[1], d_segs, d_labels);
+    }
     PB_CUDA_OK(cudaGetLastError());
 }

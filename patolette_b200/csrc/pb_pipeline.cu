@@ -20,10 +20,13 @@
 #include "pb_host.h"
 #include "pb_kernels.h"
 #include "pb_pipeline.h"
+#include "pb_prof.h"
 
 namespace {
 
 int g_device = 0;
+cudaStream_t g_user_stream = nullptr;
+bool g_use_user_stream = false;
 double g_timings[10] = {0};
 
 template <typename T>
@@ -205,6 +208,7 @@ struct Quantizer {
     bool weighted = false;
     int sm_count = 148;
     cudaStream_t st = nullptr;
+    bool own_stream = true;
     long launches = 0;
 
     DevArr<double> col[3], wgt;                // original order, quantisation space
@@ -228,7 +232,8 @@ struct Quantizer {
         PB_CUDA_OK(cudaSetDevice(g_device));
         PB_CUDA_OK(cudaGetDeviceProperties(&prop, g_device));
         sm_count = prop.multiProcessorCount;
-        PB_CUDA_OK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        if (g_use_user_stream) { st = g_user_stream; own_stream = false; }
+        else PB_CUDA_OK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         for (int j = 0; j < 3; j++) col[j].alloc(n);
         if (weighted) wgt.alloc(n);
         orig = PbPlanes{{col[0].p, col[1].p, col[2].p}, nullptr, nullptr};
@@ -254,7 +259,7 @@ struct Quantizer {
         lut.alloc(PB_BUCKETS);
     }
     ~Quantizer() {
-        if (st) cudaStreamDestroy(st);
+        if (st && own_stream) cudaStreamDestroy(st);
     }
     void sync() { PB_CUDA_OK(cudaStreamSynchronize(st)); }
     template <typename T>
@@ -272,23 +277,25 @@ struct Quantizer {
         PbStats hst;
         const PbPlanes gq[2] = {orig, orig};
         h2d(segs.p, &whole, 1);
+        pb_prof_next_bytes(24.0 * N);
         pb_launch_pass_mean(gq, segs.p, 1, false, stats.p, st);     // global.c:407: UNWEIGHTED PCA
+        pb_prof_next_bytes(24.0 * N);
         pb_launch_pass_centered(gq, segs.p, 1, false, stats.p, st);
-        launches += 2;
         d2h(&hst, stats.p, 1);
         sync();
         double v[9], axis[3];
         fill_vcov(hst, v);
         if (!pca_axis_from_vcov(v, axis)) return 0;
         h2d(axes.p, axis, 3);
+        pb_prof_next_bytes(24.0 * N);
         pb_launch_dots_minmax(gq, segs.p, 1, (uint32_t)N, axes.p, split.p, sm_count, st);
+        pb_prof_next_bytes(26.0 * N);
         pb_launch_buckets(gq, segs.p, 1, (uint32_t)N, axes.p, split.p, bucket.p, sm_count, st);
         pb_launch_class_rank(PB_CLS_BUCKET, PB_BUCKETS, segs.p, 1, (uint32_t)N, bucket.p, split.p, lut.p,
                              tile_hist.p, cstart_b.p, st);
         pb_launch_scatter_ord(PB_CLS_BUCKET, PB_BUCKETS, segs.p, 1, (uint32_t)N, bucket.p, split.p, lut.p,
                               tile_hist.p, cstart_b.p, ord.p, st);
         pb_launch_bucket_chains_gq(orig, ord.p, cstart_b.p, bsums.p, st);
-        launches += 9;
         std::vector<double> hs(PB_BUCKETS * 10);
         std::vector<uint32_t> hcs(PB_BUCKETS + 1);
         d2h(hs.data(), bsums.p, hs.size());
@@ -331,7 +338,6 @@ struct Quantizer {
         const PbPlanes srcs[2] = {src, src};
         pb_launch_scatter_payload(PB_CLS_LUT, (int)cells, srcs, bufs, true, segs.p, 1, (uint32_t)N, bucket.p,
                                   split.p, lut.p, tile_hist.p, cstart_s.p, st);
-        launches += 4;
         std::vector<uint32_t> cst(cells + 1);
         d2h(cst.data(), cstart_s.p, cells + 1);
         sync();
@@ -339,9 +345,10 @@ struct Quantizer {
         std::vector<PbSeg> hsegs(cells);
         for (size_t j = 0; j < cells; j++) hsegs[j] = PbSeg{cst[j], cst[j + 1] - cst[j], 0u, 0u};
         h2d(segs.p, hsegs.data(), cells);
+        pb_prof_next_bytes((weighted ? 32.0 : 24.0) * N);
         pb_launch_pass_mean(bufs, segs.p, (int)cells, weighted, stats.p, st);
+        pb_prof_next_bytes((weighted ? 32.0 : 24.0) * N);
         pb_launch_pass_centered(bufs, segs.p, (int)cells, weighted, stats.p, st);
-        launches += 2;
         std::vector<PbStats> hstats(cells);
         d2h(hstats.data(), stats.p, cells);
         sync();
@@ -379,23 +386,31 @@ struct Quantizer {
         if (nb == 0) return;
         h2d(segs.p, hsegs, nb);
         h2d(axes.p, haxes, 3 * nb);
+        double tot_n = 0;
+        for (int b = 0; b < nb; b++) tot_n += hsegs[b].n;
+        const double bpp = weighted ? 32.0 : 24.0; // planar f64 payload per pixel
+        pb_prof_next_bytes(24.0 * tot_n);
         pb_launch_dots_minmax(bufs, segs.p, nb, max_n, axes.p, split.p, sm_count, st);
+        pb_prof_next_bytes(26.0 * tot_n);
         pb_launch_buckets(bufs, segs.p, nb, max_n, axes.p, split.p, bucket.p, sm_count, st);
         pb_launch_class_rank(PB_CLS_BUCKET, PB_BUCKETS, segs.p, nb, max_n, bucket.p, split.p, lut.p, tile_hist.p,
                              cstart_b.p, st);
         pb_launch_scatter_ord(PB_CLS_BUCKET, PB_BUCKETS, segs.p, nb, max_n, bucket.p, split.p, lut.p, tile_hist.p,
                               cstart_b.p, ord.p, st);
+        pb_prof_next_bytes((bpp + 4.0) * tot_n);
         pb_launch_bucket_chains_lq(bufs, segs.p, nb, weighted, ord.p, cstart_b.p, bsums.p, st);
         pb_launch_split_select(bsums.p, cstart_b.p, nb, split.p, st);
         pb_launch_class_rank(PB_CLS_SPLIT, 2, segs.p, nb, max_n, bucket.p, split.p, lut.p, tile_hist.p, cstart_s.p,
                              st);
         const PbPlanes swapped[2] = {bufs[1], bufs[0]};
+        pb_prof_next_bytes((2 * (bpp + 4.0) + 2.0) * tot_n);
         pb_launch_scatter_payload(PB_CLS_SPLIT, 2, bufs, swapped, false, segs.p, nb, max_n, bucket.p, split.p,
                                   lut.p, tile_hist.p, cstart_s.p, st);
         pb_launch_make_children(segs.p, nb, split.p, children.p, st);
+        pb_prof_next_bytes(bpp * tot_n);
         pb_launch_pass_mean(bufs, children.p, 2 * nb, weighted, stats.p, st);
+        pb_prof_next_bytes(bpp * tot_n);
         pb_launch_pass_centered(bufs, children.p, 2 * nb, weighted, stats.p, st);
-        launches += 17;
         PbSeg hch[4];
         PbStats hst[4];
         d2h(hch, children.p, 2 * nb);
@@ -466,7 +481,6 @@ void palette_transform(Quantizer &qz, int which, std::vector<double> &pal_rm) {
     const double *src[3] = {d.p, d.p + K, d.p + 2 * K};
     double *dst[3] = {d.p, d.p + K, d.p + 2 * K};
     pb_launch_color(which, src, dst, K, qz.sm_count, qz.st);
-    qz.launches++;
     qz.d2h(planar.data(), d.p, 3 * K);
     qz.sync();
     for (size_t j = 0; j < K; j++)
@@ -476,23 +490,26 @@ void palette_transform(Quantizer &qz, int which, std::vector<double> &pal_rm) {
 void colors_transform(Quantizer &qz, int which) {
     const double *src[3] = {qz.col[0].p, qz.col[1].p, qz.col[2].p};
     double *dst[3] = {qz.col[0].p, qz.col[1].p, qz.col[2].p};
+    pb_prof_next_bytes(48.0 * qz.N);
     pb_launch_color(which, src, dst, qz.N, qz.sm_count, qz.st);
-    qz.launches++;
 }
 
 void run_patolette(size_t width, size_t height, const double *data, const double *weights, size_t K,
                    const patolette__QuantizationOptions *opt, double *palette, size_t *palette_map,
-                   int *exit_code) {
+                   int *exit_code, bool device_io) {
     const size_t n = width * height;
     memset(g_timings, 0, sizeof g_timings);
+    const long launches0 = pb_prof_launch_count();
     Quantizer qz;
     qz.init(n, weights != nullptr);
     Timer total(qz.st), stage(qz.st);
     total.start();
 
     stage.start(); // patolette.c:187-199: the library works on its own copy
-    for (int j = 0; j < 3; j++) qz.h2d(qz.col[j].p, data + (size_t)j * n, n);
-    if (weights) qz.h2d(qz.wgt.p, weights, n);
+    const cudaMemcpyKind in_kind = device_io ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    for (int j = 0; j < 3; j++)
+        PB_CUDA_OK(cudaMemcpyAsync(qz.col[j].p, data + (size_t)j * n, n * sizeof(double), in_kind, qz.st));
+    if (weights) PB_CUDA_OK(cudaMemcpyAsync(qz.wgt.p, weights, n * sizeof(double), in_kind, qz.st));
     set_timing(1, stage.stop());
 
     stage.start(); // patolette.c:201-207
@@ -540,7 +557,8 @@ void run_patolette(size_t width, size_t height, const double *data, const double
             palette_transform(qz, t, pal);
             const double *planes[3] = {qz.col[0].p, qz.col[1].p, qz.col[2].p};
             // riemersma.c:452-456: a 1x1 image is never dithered; the map keeps the caller's bytes
-            if (palette_map) qz.h2d(dmap.p, (const unsigned long long *)palette_map, n <= 1 ? n : 0);
+            if (palette_map && n == 1)
+                PB_CUDA_OK(cudaMemcpyAsync(dmap.p, palette_map, sizeof(size_t), in_kind, qz.st));
             pb_dither_riemersma(planes, width, height, pal, dmap.p, qz.sm_count, qz.st, &qz.launches);
             palette_transform(qz, PB_T_REC2020_TO_SRGB, pal);
             set_timing(7, stage.stop());
@@ -555,8 +573,8 @@ void run_patolette(size_t width, size_t height, const double *data, const double
             dpal.alloc(3 * count);
             qz.h2d(dpal.p, pal.data(), 3 * count);
             const double *planes[3] = {qz.col[0].p, qz.col[1].p, qz.col[2].p};
+            pb_prof_next_bytes(32.0 * n);
             pb_launch_nearest(planes, n, dpal.p, (int)count, dmap.p, qz.sm_count, qz.st);
-            qz.launches++;
             qz.sync();
             // patolette.c:322-323, applied whatever the colour space was (reference bug B1)
             palette_transform(qz, PB_T_ICTCP_TO_REC2020, pal);
@@ -564,14 +582,15 @@ void run_patolette(size_t width, size_t height, const double *data, const double
             set_timing(6, stage.stop());
         }
         stage.start();
-        qz.d2h((unsigned long long *)palette_map, dmap.p, n);
+        PB_CUDA_OK(cudaMemcpyAsync(palette_map, dmap.p, n * sizeof(size_t),
+                                   device_io ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, qz.st));
         set_timing(8, stage.stop());
     }
     for (size_t j = 0; j < K * 3; j++) palette[j] = -1.0; // patolette.c:328-330
     for (int c = 0; c < 3; c++)
         for (size_t j = 0; j < count; j++) palette[K * c + j] = pal[3 * j + c];
     set_timing(0, total.stop());
-    g_timings[9] = (double)qz.launches;
+    g_timings[9] = (double)(pb_prof_launch_count() - launches0);
     *exit_code = 0;
 }
 
@@ -590,13 +609,52 @@ void patolette(size_t width, size_t height, const double *data, const double *we
     if (palette_size < 1) { *exit_code = -3; return; }
     if (width * height > (size_t)40000 * 40000) { *exit_code = -4; return; }
     try {
-        run_patolette(width, height, data, weights, palette_size, options, palette, palette_map, exit_code);
+        run_patolette(width, height, data, weights, palette_size, options, palette, palette_map, exit_code, false);
     } catch (const pb_cuda_error &) {
         cudaGetLastError();
         *exit_code = -5;
     } catch (const std::bad_alloc &) {
         *exit_code = -1;
     }
+}
+
+void patolette_b200_device(size_t width, size_t height, const double *d_data, const double *d_weights,
+                           size_t palette_size, const patolette__QuantizationOptions *options, double *palette,
+                           size_t *d_palette_map, int *exit_code) {
+    *exit_code = 0;
+    if (width * height == 0) { *exit_code = -2; return; }
+    if (palette_size < 1) { *exit_code = -3; return; }
+    if (width * height > (size_t)40000 * 40000) { *exit_code = -4; return; }
+    try {
+        run_patolette(width, height, d_data, d_weights, palette_size, options, palette, d_palette_map, exit_code, true);
+    } catch (const pb_cuda_error &) {
+        cudaGetLastError();
+        *exit_code = -5;
+    } catch (const std::bad_alloc &) {
+        *exit_code = -1;
+    }
+}
+
+int patolette_b200_set_stream(void *cuda_stream, int enable) {
+    g_user_stream = (cudaStream_t)cuda_stream;
+    g_use_user_stream = enable != 0;
+    return 0;
+}
+
+int patolette_b200_profile_enable(int on) {
+    pb_prof_enable(on != 0);
+    if (on) pb_prof_reset();
+    return 0;
+}
+
+size_t patolette_b200_profile_json(char *buf, size_t cap) {
+    std::string js = pb_prof_json();
+    if (buf && cap) {
+        size_t m = js.size() < cap - 1 ? js.size() : cap - 1;
+        memcpy(buf, js.data(), m);
+        buf[m] = 0;
+    }
+    return js.size() + 1;
 }
 
 const char *get_patolette_exit_code_info_message(int exit_code) {

@@ -1,0 +1,89 @@
+#include "pb_prof.h"
+
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <sstream>
+#include <vector>
+
+namespace {
+std::atomic<long> g_launches{0};
+std::atomic<bool> g_on{false};
+double g_next_bytes = 0;
+struct Pending {
+    const char *name;
+    cudaEvent_t a, b;
+    double bytes;
+};
+std::mutex g_mu;
+std::vector<Pending> g_pending;
+struct Acc {
+    long launches = 0;
+    double ms = 0, bytes = 0;
+};
+std::map<std::string, Acc> g_acc;
+} // namespace
+
+void pb_prof_enable(bool on) { g_on = on; }
+bool pb_prof_enabled() { return g_on; }
+long pb_prof_launch_count() { return g_launches; }
+void pb_prof_next_bytes(double bytes) { g_next_bytes = bytes; }
+
+void pb_prof_reset() {
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (auto &p : g_pending) {
+        cudaEventDestroy(p.a);
+        cudaEventDestroy(p.b);
+    }
+    g_pending.clear();
+    g_acc.clear();
+}
+
+PbProfScope::PbProfScope(const char *kernel_name, cudaStream_t stream, bool takes_bytes)
+    : st(stream), name(kernel_name) {
+    g_launches++;
+    if (takes_bytes) {
+        bytes = g_next_bytes;
+        g_next_bytes = 0;
+    }
+    if (g_on) {
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        cudaEventRecord(a, st);
+    }
+}
+
+PbProfScope::~PbProfScope() {
+    if (a) {
+        cudaEventRecord(b, st);
+        std::lock_guard<std::mutex> lk(g_mu);
+        g_pending.push_back(Pending{name, a, b, bytes});
+    }
+}
+
+std::string pb_prof_json() {
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (auto &p : g_pending) {
+        cudaEventSynchronize(p.b);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, p.a, p.b);
+        Acc &acc = g_acc[p.name];
+        acc.launches++;
+        acc.ms += ms;
+        acc.bytes += p.bytes;
+        cudaEventDestroy(p.a);
+        cudaEventDestroy(p.b);
+    }
+    g_pending.clear();
+    std::ostringstream os;
+    os << "{";
+    bool first = true;
+    for (auto &kv : g_acc) {
+        if (!first) os << ", ";
+        first = false;
+        os << "\"" << kv.first << "\": {\"launches\": " << kv.second.launches << ", \"ms\": " << kv.second.ms
+           << ", \"bytes\": " << kv.second.bytes << "}";
+    }
+    os << "}";
+    return os.str();
+}
