@@ -1,4 +1,5 @@
-// pb_chain.cu - ordered ("chain") sums.
+// pb_chain.cu - ordered ("chain") per-bucket sums.  (The per-cluster mean / covariance /
+// distortion passes live in pb_ordered.cu, which adds the binade-speculative fast path.)
 //
 // Every statistic the reference derives from a cluster - weighted mean
 // (array/matrix2D.c:200-233), centred covariance (math/pca.c:84-97), distortion
@@ -25,144 +26,6 @@
 #include "pb_prof.h"
 
 namespace {
-
-constexpr int CH_TILE = 256;           // elements staged per tile
-constexpr int CH_STRIDE = CH_TILE + 2; // +2 doubles: planes land 4 banks apart
-constexpr int CH_PER_LANE = CH_TILE / 32;
-
-// ------------------------------------------------------------------------------------
-// Pass A: wsum = sum w, S_j = sum c_j * w  ->  mean_j = S_j * (1 / wsum)
-// ------------------------------------------------------------------------------------
-template <bool WEIGHTED>
-__global__ void __launch_bounds__(32) k_pass_mean(PbPlanes b0, PbPlanes b1, const PbSeg *__restrict__ segs,
-                                                  PbStats *__restrict__ stats) {
-    __shared__ double sm[2][4][CH_STRIDE];
-    const PbSeg sg = segs[blockIdx.x];
-    const PbPlanes &P = sg.buf ? b1 : b0;
-    const int lane = threadIdx.x;
-    const double *src[4] = {WEIGHTED ? P.w + sg.lo : nullptr, P.c[0] + sg.lo, P.c[1] + sg.lo, P.c[2] + sg.lo};
-    const uint32_t n = sg.n;
-    const uint32_t ntiles = (n + CH_TILE - 1) / CH_TILE;
-    double reg[4][CH_PER_LANE];
-    double acc = 0.0; // lane 0: sum w; lanes 1..3: sum c_{lane-1} * w
-
-    auto load_tile = [&](uint32_t t) {
-        const uint32_t base = t * CH_TILE;
-#pragma unroll
-        for (int a = WEIGHTED ? 0 : 1; a < 4; a++)
-#pragma unroll
-            for (int k = 0; k < CH_PER_LANE; k++) {
-                uint32_t e = base + k * 32 + lane;
-                reg[a][k] = e < n ? src[a][e] : 0.0;
-            }
-    };
-    auto stash_tile = [&](int buf) {
-#pragma unroll
-        for (int a = WEIGHTED ? 0 : 1; a < 4; a++)
-#pragma unroll
-            for (int k = 0; k < CH_PER_LANE; k++) sm[buf][a][k * 32 + lane] = reg[a][k];
-    };
-
-    if (ntiles) { load_tile(0); stash_tile(0); }
-    __syncwarp();
-    for (uint32_t t = 0; t < ntiles; t++) {
-        const int cur = t & 1;
-        if (t + 1 < ntiles) load_tile(t + 1); // in flight while the chain below runs
-        const uint32_t cnt = min((uint32_t)CH_TILE, n - t * CH_TILE);
-        if (lane < 4) {
-            const double *vp = sm[cur][lane];
-            const double *wp = sm[cur][0];
-            // one instruction stream for all four chain lanes (lane 0 sums the weights)
-#pragma unroll 8
-            for (uint32_t e = 0; e < cnt; e++) {
-                const double w = WEIGHTED ? wp[e] : 1.0;
-                const double term = lane == 0 ? w : (WEIGHTED ? __dmul_rn(vp[e], w) : vp[e]);
-                acc = __dadd_rn(acc, term);
-            }
-        }
-        __syncwarp();
-        if (t + 1 < ntiles) stash_tile(cur ^ 1);
-        __syncwarp();
-    }
-    // matrix2D.c:230-231: s = 1 / wsum (or 1 / rows); mean *= s
-    double wsum = __shfl_sync(0xffffffffu, acc, 0);
-    if (!WEIGHTED) wsum = (double)n;
-    double s = 1.0 / wsum;
-    if (lane == 0) stats[blockIdx.x].wsum = wsum;
-    if (lane >= 1 && lane <= 3) stats[blockIdx.x].mean[lane - 1] = __dmul_rn(acc, s);
-}
-
-// ------------------------------------------------------------------------------------
-// Pass B: six centred second moments (lower triangle, what dsyev('L') reads) and the
-// distortion, all against the mean of pass A.
-// ------------------------------------------------------------------------------------
-template <bool WEIGHTED>
-__global__ void __launch_bounds__(32) k_pass_centered(PbPlanes b0, PbPlanes b1,
-                                                      const PbSeg *__restrict__ segs,
-                                                      PbStats *__restrict__ stats) {
-    __shared__ double sm[2][4][CH_STRIDE];
-    const PbSeg sg = segs[blockIdx.x];
-    const PbPlanes &P = sg.buf ? b1 : b0;
-    const int lane = threadIdx.x;
-    const double *src[4] = {WEIGHTED ? P.w + sg.lo : nullptr, P.c[0] + sg.lo, P.c[1] + sg.lo, P.c[2] + sg.lo};
-    const uint32_t n = sg.n;
-    const uint32_t ntiles = (n + CH_TILE - 1) / CH_TILE;
-    const double m0 = stats[blockIdx.x].mean[0], m1 = stats[blockIdx.x].mean[1], m2 = stats[blockIdx.x].mean[2];
-    // lane -> (j, k), j >= k : (0,0) (1,0) (1,1) (2,0) (2,1) (2,2); lane 6 = distortion
-    const int j = lane == 0 ? 0 : (lane <= 2 ? 1 : 2);
-    const int k = (lane == 0 || lane == 1 || lane == 3) ? 0 : ((lane == 2 || lane == 4) ? 1 : 2);
-    double reg[4][CH_PER_LANE];
-    double acc = 0.0;
-
-    auto load_tile = [&](uint32_t t) {
-        const uint32_t base = t * CH_TILE;
-#pragma unroll
-        for (int a = WEIGHTED ? 0 : 1; a < 4; a++)
-#pragma unroll
-            for (int q = 0; q < CH_PER_LANE; q++) {
-                uint32_t e = base + q * 32 + lane;
-                reg[a][q] = e < n ? src[a][e] : 0.0;
-            }
-    };
-    auto stash_tile = [&](int buf) {
-#pragma unroll
-        for (int a = WEIGHTED ? 0 : 1; a < 4; a++)
-#pragma unroll
-            for (int q = 0; q < CH_PER_LANE; q++) sm[buf][a][q * 32 + lane] = reg[a][q];
-    };
-
-    if (ntiles) { load_tile(0); stash_tile(0); }
-    __syncwarp();
-    for (uint32_t t = 0; t < ntiles; t++) {
-        const int cur = t & 1;
-        if (t + 1 < ntiles) load_tile(t + 1);
-        const uint32_t cnt = min((uint32_t)CH_TILE, n - t * CH_TILE);
-        if (lane < 7) {
-            const double *p0 = sm[cur][1], *p1 = sm[cur][2], *p2 = sm[cur][3], *wp = sm[cur][0];
-#pragma unroll 4
-            for (uint32_t e = 0; e < cnt; e++) {
-                const double d0 = __dsub_rn(p0[e], m0), d1 = __dsub_rn(p1[e], m1), d2 = __dsub_rn(p2[e], m2);
-                double term;
-                if (lane < 6) {
-                    const double dj = j == 0 ? d0 : (j == 1 ? d1 : d2);
-                    const double dk = k == 0 ? d0 : (k == 1 ? d1 : d2);
-                    // pca.c:92: value += weight * cij * cik  == (w * c^_j) * c^_k
-                    term = WEIGHTED ? __dmul_rn(__dmul_rn(wp[e], dj), dk) : __dmul_rn(dj, dk);
-                } else {
-                    // cluster.c:141-147: (SQ(dx) + SQ(dy) + SQ(dz)) * weight
-                    term = __dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), __dmul_rn(d2, d2));
-                    if (WEIGHTED) term = __dmul_rn(term, wp[e]);
-                }
-                acc = __dadd_rn(acc, term);
-            }
-        }
-        __syncwarp();
-        if (t + 1 < ntiles) stash_tile(cur ^ 1);
-        __syncwarp();
-    }
-    if (lane < 6) stats[blockIdx.x].cov[lane] = acc;
-    if (lane == 6) stats[blockIdx.x].dist = acc;
-}
 
 // ------------------------------------------------------------------------------------
 // Per-bucket ordered sums.  The members of bucket b of a cluster, in ascending pixel
@@ -272,24 +135,6 @@ __global__ void __launch_bounds__(BK_WARPS * 32) k_bucket_chains_gq(PbPlanes src
 }
 
 } // namespace
-
-void pb_launch_pass_mean(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, bool weighted,
-                         PbStats *d_stats, cudaStream_t st) {
-    if (nseg <= 0) return;
-    PbProfScope _prof("k_pass_mean", st);
-    if (weighted) k_pass_mean<true><<<nseg, 32, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats);
-    else k_pass_mean<false><<<nseg, 32, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats);
-    PB_CUDA_OK(cudaGetLastError());
-}
-
-void pb_launch_pass_centered(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, bool weighted,
-                             PbStats *d_stats, cudaStream_t st) {
-    if (nseg <= 0) return;
-    PbProfScope _prof("k_pass_centered", st);
-    if (weighted) k_pass_centered<true><<<nseg, 32, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats);
-    else k_pass_centered<false><<<nseg, 32, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats);
-    PB_CUDA_OK(cudaGetLastError());
-}
 
 void pb_launch_bucket_chains_lq(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, bool weighted,
                                 const uint32_t *d_ord, const uint32_t *d_class_start, double *d_out,

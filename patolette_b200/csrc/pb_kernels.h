@@ -20,13 +20,16 @@ void pb_launch_color(int which, const double *const src[3], double *const dst[3]
                      int sm_count, cudaStream_t st);
 void pb_launch_pow(const double *x, double y, double *out, size_t n, int sm_count, cudaStream_t st);
 
-// ---- ordered-sum ("chain") kernels, pb_chain.cu --------------------------------------
+// ---- ordered-sum kernels, pb_ordered.cu / pb_chain.cu ----------------------------------
 // Every reference statistic is a left-to-right f64 sum in ascending pixel order; these
 // kernels reproduce that order bit for bit (see pb_chain.cu for how).
-void pb_launch_pass_mean(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, bool weighted,
-                         PbStats *d_stats, cudaStream_t st);
-void pb_launch_pass_centered(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, bool weighted,
-                             PbStats *d_stats, cudaStream_t st);
+// max_n = largest segment of the batch; d_scratch (pb_ordered_scratch_bytes) enables the
+// speculative block-summary path, without it (or for small segments) the sums run as chains.
+size_t pb_ordered_scratch_bytes(int nseg, uint32_t max_n);
+void pb_launch_pass_mean(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t max_n, bool weighted,
+                         PbStats *d_stats, void *d_scratch, size_t scratch_bytes, cudaStream_t st);
+void pb_launch_pass_centered(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t max_n, bool weighted,
+                             PbStats *d_stats, void *d_scratch, size_t scratch_bytes, cudaStream_t st);
 // Per-bucket ordered sums over bucket-sorted position lists.
 //   LQ (local.c:102-146): out[seg][b] = {size (as double bits of u64), sum c0*w, sum c1*w, sum c2*w}
 //   GQ (cells.c:53-116):  out[b] = {sum c0, c1, c2, sum |c|^2, sums c_r*c_s (r<=s: 00,01,11,02,12,22)}

@@ -221,6 +221,7 @@ struct Quantizer {
     DevArr<PbStats> stats;
     DevArr<PbSplit> split;
     DevArr<uint8_t> lut;
+    DevArr<char> oscratch; // block sums + summaries of the speculative ordered sums
     PbPlanes orig{}, bufs[2]{};
 
     static constexpr int MAXB = 16; // segments per batch
@@ -257,6 +258,7 @@ struct Quantizer {
         stats.alloc(2 * MAXB);
         split.alloc(MAXB);
         lut.alloc(PB_BUCKETS);
+        oscratch.alloc(pb_ordered_scratch_bytes(MAXB, (uint32_t)N));
     }
     ~Quantizer() {
         if (st && own_stream) cudaStreamDestroy(st);
@@ -278,9 +280,9 @@ struct Quantizer {
         const PbPlanes gq[2] = {orig, orig};
         h2d(segs.p, &whole, 1);
         pb_prof_next_bytes(24.0 * N);
-        pb_launch_pass_mean(gq, segs.p, 1, false, stats.p, st);     // global.c:407: UNWEIGHTED PCA
+        pb_launch_pass_mean(gq, segs.p, 1, (uint32_t)N, false, stats.p, oscratch.p, oscratch.n, st);     // global.c:407: UNWEIGHTED PCA
         pb_prof_next_bytes(24.0 * N);
-        pb_launch_pass_centered(gq, segs.p, 1, false, stats.p, st);
+        pb_launch_pass_centered(gq, segs.p, 1, (uint32_t)N, false, stats.p, oscratch.p, oscratch.n, st);
         d2h(&hst, stats.p, 1);
         sync();
         double v[9], axis[3];
@@ -345,10 +347,12 @@ struct Quantizer {
         std::vector<PbSeg> hsegs(cells);
         for (size_t j = 0; j < cells; j++) hsegs[j] = PbSeg{cst[j], cst[j + 1] - cst[j], 0u, 0u};
         h2d(segs.p, hsegs.data(), cells);
+        uint32_t cmax = 0;
+        for (size_t j = 0; j < cells; j++) cmax = std::max(cmax, hsegs[j].n);
         pb_prof_next_bytes((weighted ? 32.0 : 24.0) * N);
-        pb_launch_pass_mean(bufs, segs.p, (int)cells, weighted, stats.p, st);
+        pb_launch_pass_mean(bufs, segs.p, (int)cells, cmax, weighted, stats.p, oscratch.p, oscratch.n, st);
         pb_prof_next_bytes((weighted ? 32.0 : 24.0) * N);
-        pb_launch_pass_centered(bufs, segs.p, (int)cells, weighted, stats.p, st);
+        pb_launch_pass_centered(bufs, segs.p, (int)cells, cmax, weighted, stats.p, oscratch.p, oscratch.n, st);
         std::vector<PbStats> hstats(cells);
         d2h(hstats.data(), stats.p, cells);
         sync();
@@ -408,9 +412,9 @@ struct Quantizer {
                                   lut.p, tile_hist.p, cstart_s.p, st);
         pb_launch_make_children(segs.p, nb, split.p, children.p, st);
         pb_prof_next_bytes(bpp * tot_n);
-        pb_launch_pass_mean(bufs, children.p, 2 * nb, weighted, stats.p, st);
+        pb_launch_pass_mean(bufs, children.p, 2 * nb, max_n, weighted, stats.p, oscratch.p, oscratch.n, st);
         pb_prof_next_bytes(bpp * tot_n);
-        pb_launch_pass_centered(bufs, children.p, 2 * nb, weighted, stats.p, st);
+        pb_launch_pass_centered(bufs, children.p, 2 * nb, max_n, weighted, stats.p, oscratch.p, oscratch.n, st);
         PbSeg hch[4];
         PbStats hst[4];
         d2h(hch, children.p, 2 * nb);

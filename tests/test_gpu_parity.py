@@ -106,6 +106,39 @@ def test_cluster_tree_matches_oracle(cuda_lib, oracle, n, K, weighted, image_lik
     assert_same_floats(res["cuda"][1], res["oracle"][1], "cluster centres")
 
 
+@pytest.mark.parametrize("kind", ["dyadic", "narrow", "signed", "spiky", "sorted"])
+def test_ordered_sums_adversarial(cuda_lib, oracle, kind):
+    """Inputs chosen to stress the binade-speculative ordered sums (pb_ordered.cu): exact ties
+    (dyadic values), catastrophic cancellation (narrow range), sign changes of the running sum,
+    isolated huge terms, and monotone data.  Partition and centres must still be bit-identical."""
+    n, K = 150_001, 24
+    rng = np.random.default_rng(hash(kind) % 1000)
+    if kind == "dyadic":
+        c = rng.integers(0, 257, (n, 3)) / 256.0
+    elif kind == "narrow":
+        c = 0.5 + (rng.random((n, 3)) - 0.5) * 1e-9
+    elif kind == "signed":
+        c = rng.standard_normal((n, 3)) * np.array([1.0, 1e-3, 50.0])
+    elif kind == "spiky":
+        c = rng.random((n, 3)) * 1e-3
+        c[rng.choice(n, 40, replace=False)] += rng.random((40, 3)) * 1e4
+    else:
+        c = np.sort(rng.random((n, 3)), axis=0)
+    planar = np.asfortranarray(c)
+    wts = (1 + 1000 * rng.random(n) ** 4) if kind in ("signed", "spiky") else None
+    res = {}
+    for name, lib, fn in (("oracle", oracle.lib, "orc_quantize_clusters"), ("cuda", cuda_lib, "patolette_b200_quantize_clusters")):
+        labels = np.zeros(n, dtype=np.uint32); centers = np.zeros((K, 3)); cnt = C.c_size_t(0); gq = C.c_size_t(0)
+        f = getattr(lib, fn)
+        f.restype = C.c_int
+        f.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+        assert f(planar.ctypes.data, n, None if wts is None else wts.ctypes.data, K, labels.ctypes.data, centers.ctypes.data, C.byref(cnt), C.byref(gq)) == 0
+        res[name] = (labels, centers[:cnt.value].copy(), cnt.value, gq.value)
+    assert res["cuda"][2:] == res["oracle"][2:]
+    assert np.array_equal(res["cuda"][0], res["oracle"][0]), "cluster membership differs"
+    assert_same_floats(res["cuda"][1], res["oracle"][1], "cluster centres")
+
+
 def test_nearest_map_matches_oracle(cuda_lib, oracle):
     n, K = 300_001, 256
     rng = np.random.default_rng(8)
