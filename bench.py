@@ -236,6 +236,8 @@ def run_ours(args):
 
     # ---------------- per-kernel profile (untimed extra step) -> roofline ----------------
     lib.patolette_b200_set_stream(C.c_void_p(stream.cuda_stream), 1)
+    cnt = (C.c_ulonglong * 2)()
+    lib.patolette_b200_ordered_counts(cnt, 1)
     lib.patolette_b200_profile_enable(1)
     step_resident()
     torch.cuda.synchronize()
@@ -244,6 +246,8 @@ def run_ours(args):
     lib.patolette_b200_profile_enable(0)
     lib.patolette_b200_set_stream(None, 0)
     prof = json.loads(buf.value.decode())
+    lib.patolette_b200_ordered_counts(cnt, 0)
+    ord_acc, ord_rep = int(cnt[0]), int(cnt[1])
     peak, peak_src = measured_peaks()
     kernels = sorted(prof.items(), key=lambda kv: -kv[1]["ms"])
     top_name, top = kernels[0]
@@ -280,6 +284,8 @@ def run_ours(args):
         "gpu_launches_per_step": launches,
         "stage_ms": {k: round(v, 3) for k, v in stage.items()},
         "roofline": roofline, "clocks": clocks,
+        "ordered_sums": {"blocks_accepted": ord_acc, "blocks_replayed": ord_rep,
+                         "replay_frac": ord_rep / max(ord_acc + ord_rep, 1)},
     }
     if cpu_baseline is not None:
         line["cpu_baseline"] = cpu_baseline

@@ -26,6 +26,8 @@ void pb_launch_pow(const double *x, double y, double *out, size_t n, int sm_coun
 // max_n = largest segment of the batch; d_scratch (pb_ordered_scratch_bytes) enables the
 // speculative block-summary path, without it (or for small segments) the sums run as chains.
 size_t pb_ordered_scratch_bytes(int nseg, uint32_t max_n);
+// {blocks accepted from summaries, blocks replayed sequentially} per chain since the last reset
+void pb_ordered_counts(unsigned long long out[2], bool reset);
 void pb_launch_pass_mean(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t max_n, bool weighted,
                          PbStats *d_stats, void *d_scratch, size_t scratch_bytes, cudaStream_t st);
 void pb_launch_pass_centered(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t max_n, bool weighted,

@@ -16,15 +16,15 @@
 //   Speculate, summarise, verify.
 //     S1  k_ord_blocksum : plain (unordered) f64 sum of every block of OB elements, per chain.
 //     S2  k_ord_prefix   : approximate running total at each block start -> guessed binade e.
-//     S3  k_ord_summary  : per block and chain, with q = 2^(e-52): P+ = sum of positive
-//                          rint(a/q), P- = sum of negative ones (exact, order-free), and a flag
-//                          if any term was a tie or too large to quantise.
+//     S3  k_ord_summary  : per block and chain, with q = 2^(e-52): D = sum of rint(a/q) and the
+//                          min / max over the block's in-order prefix sums (exact integers; an
+//                          in-order monoid reduction), plus a flag if any term was a tie or too
+//                          large to quantise.
 //     S4  k_ord_resolve  : one lane per chain walks the BLOCKS in order holding the exact
 //                          state (M, e).  A block is accepted iff the guess was right, no flag
-//                          is set and M - P- >= 2^52 and M + P+ < 2^53 (every intermediate value
-//                          provably stayed in the binade, whatever the order inside the block);
-//                          then M += P+ - P-.  Otherwise the lane replays that one block
-//                          element by element - the literal reference loop.
+//                          is set and 2^52 < M + min .. M + max < 2^53 (every intermediate value
+//                          provably stayed in the binade); then M += D.  Otherwise the lane
+//                          replays that one block element by element - the literal reference loop.
 //   The guess only decides SPEED: every accepted block is proven equal to the sequential
 //   result, every other block IS the sequential loop.  Binade crossings (~log2 n per chain),
 //   ties (~2 ln n) and the first block take the slow path; everything else is parallel.
@@ -44,10 +44,13 @@ constexpr double MAGIC = 6755399441055744.0;      // 1.5 * 2^52: (t + MAGIC) - M
 constexpr double TWO51 = 2251799813685248.0;
 constexpr long long TWO52 = 1LL << 52, TWO53 = 1LL << 53;
 
+// blocks accepted from their summary / blocks replayed sequentially (per chain), since last reset
+__device__ unsigned long long g_ord_counts[2];
+
 struct OrdSummary {
-    double ppos, pneg; // sums of the positive / negated negative quantised terms (integers)
-    int e;             // guessed binade of the running sum across this block
-    int flag;          // non-zero: replay the block
+    double sum, mn, mx; // quantised terms of the block: total, min and max over its in-order prefixes
+    int e;              // guessed binade of the running sum across this block
+    int flag;           // non-zero: replay the block
 };
 
 enum { KIND_MEAN = 0, KIND_CENTERED = 1 };
@@ -174,12 +177,22 @@ __global__ void __launch_bounds__(32) k_ord_prefix(const PbSeg *__restrict__ seg
 }
 
 // ---- S3: quantised block summaries --------------------------------------------------------------
+// (sum, min prefix, max prefix) of a sequence of integers is a monoid under in-order concatenation:
+//   (a ++ b).sum = a.sum + b.sum ; (a ++ b).mn = min(a.mn, a.sum + b.mn) ; likewise mx.
+// Each thread owns 4 CONSECUTIVE elements, warps reduce in lane order, warp 0..3 in warp order, so
+// mn / mx are the exact extremes of the running integer sum in element order.
+struct Tri { double sum, mn, mx; };
+__device__ __forceinline__ Tri tri_cat(const Tri &a, const Tri &b) {
+    return Tri{a.sum + b.sum, fmin(a.mn, a.sum + b.mn), fmax(a.mx, a.sum + b.mx)};
+}
+
 template <int KIND, bool W>
 __global__ void __launch_bounds__(OB_THREADS) k_ord_summary(PbPlanes b0, PbPlanes b1, const PbSeg *__restrict__ segs,
                                                             const PbStats *__restrict__ stats, uint32_t blk_cap,
                                                             OrdSummary *__restrict__ sum) {
     constexpr int C = NChains<KIND>::C;
-    __shared__ double red[OB_THREADS / 32];
+    constexpr int PER = OB / OB_THREADS;
+    __shared__ Tri s_tri[OB_THREADS / 32][C];
     __shared__ int s_flag[C];
     const int seg = blockIdx.y;
     const PbSeg sg = segs[seg];
@@ -189,45 +202,60 @@ __global__ void __launch_bounds__(OB_THREADS) k_ord_summary(PbPlanes b0, PbPlane
     OrdSummary *out = sum + ((size_t)seg * blk_cap + blockIdx.x) * C;
     double m0 = 0, m1 = 0, m2 = 0;
     if (KIND == KIND_CENTERED) { m0 = stats[seg].mean[0]; m1 = stats[seg].mean[1]; m2 = stats[seg].mean[2]; }
-    double scale[C], pos[C], neg[C];
+    double scale[C];
+    Tri tri[C];
     int flag[C];
 #pragma unroll
     for (int c = 0; c < C; c++) {
         const int e = out[c].e;
         flag[c] = e == E_NOGUESS;
         scale[c] = flag[c] ? 0.0 : scalbn(1.0, 52 - e); // 1 / q
-        pos[c] = 0.0;
-        neg[c] = 0.0;
+        tri[c] = Tri{0.0, 1e300, -1e300};                 // empty sequence
     }
     if (threadIdx.x < C) s_flag[threadIdx.x] = 0;
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < OB / OB_THREADS; k++) {
-        const uint32_t i = base + k * OB_THREADS + threadIdx.x;
+    for (int k = 0; k < PER; k++) {
+        const uint32_t i = base + threadIdx.x * PER + k; // consecutive elements per thread
         if (i < sg.n) {
             const size_t p = (size_t)sg.lo + i;
             double t[C];
             terms_all<KIND, W>(W ? P.w[p] : 1.0, P.c[0][p], P.c[1][p], P.c[2][p], m0, m1, m2, t);
 #pragma unroll
             for (int c = 0; c < C; c++) {
-                const double u = __dmul_rn(t[c], scale[c]);               // a / q, exact (power of two)
-                const double d = __dsub_rn(__dadd_rn(u, MAGIC), MAGIC);   // rint(u)
-                const double r = __dsub_rn(u, d);                         // exact remainder
-                flag[c] |= !(fabs(u) < TWO51) | (fabs(r) == 0.5);         // unquantisable / tie / NaN
-                pos[c] += fmax(d, 0.0);
-                neg[c] += fmax(-d, 0.0);
+                const double u = __dmul_rn(t[c], scale[c]);             // a / q, exact (power of two)
+                const double d = __dsub_rn(__dadd_rn(u, MAGIC), MAGIC); // rint(u)
+                const double r = __dsub_rn(u, d);                       // exact remainder
+                flag[c] |= !(fabs(u) < TWO51) | (fabs(r) == 0.5);       // unquantisable / tie / NaN
+                const double ps = tri[c].sum + d;
+                tri[c] = Tri{ps, fmin(tri[c].mn, ps), fmax(tri[c].mx, ps)};
             }
         }
     }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int c = 0; c < C; c++) {
         if (flag[c]) atomicOr(&s_flag[c], 1);
-        const double rp = block_reduce_sum(pos[c], red); // integers < 2^53: exact in any order
-        const double rn = block_reduce_sum(neg[c], red);
-        if (threadIdx.x == 0) { out[c].ppos = rp; out[c].pneg = rn; }
+        Tri v = tri[c];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { // in-order tree: lane i absorbs lane i + o
+            Tri r;
+            r.sum = __shfl_down_sync(0xffffffffu, v.sum, o);
+            r.mn = __shfl_down_sync(0xffffffffu, v.mn, o);
+            r.mx = __shfl_down_sync(0xffffffffu, v.mx, o);
+            if ((lane & (2 * o - 1)) == 0) v = tri_cat(v, r);
+        }
+        if (lane == 0) s_tri[warp][c] = v;
     }
     __syncthreads();
-    if (threadIdx.x < C) out[threadIdx.x].flag = s_flag[threadIdx.x];
+    if (threadIdx.x < C) {
+        Tri v = s_tri[0][threadIdx.x];
+        for (int w = 1; w < OB_THREADS / 32; w++) v = tri_cat(v, s_tri[w][threadIdx.x]);
+        out[threadIdx.x].sum = v.sum;
+        out[threadIdx.x].mn = v.mn;
+        out[threadIdx.x].mx = v.mx;
+        out[threadIdx.x].flag = s_flag[threadIdx.x];
+    }
 }
 
 // ---- S4: ordered resolve (and the plain sequential chain when use_summaries == false) ---------------
@@ -246,26 +274,41 @@ __global__ void __launch_bounds__(32) k_ord_resolve(PbPlanes b0, PbPlanes b1, co
     const bool chain = lane < C;
     // exact state of this lane's chain: s = M * 2^(e-52) while in integer mode, else the double s
     double s = 0.0;
-    const OrdSummary *srow = sum + (size_t)seg * blk_cap * C + (chain ? lane : 0);
+    unsigned int n_acc = 0, n_rep = 0;
+    constexpr int GRP = 32; // summaries of GRP blocks are staged in shared memory at a time
+    __shared__ OrdSummary s_sum[GRP * C];
+    const OrdSummary *sbase = sum + (size_t)seg * blk_cap * C;
     for (uint32_t b = 0; b < nblk; b++) {
         bool accept = false;
+        if (use_summaries && (b % GRP) == 0) {
+            __syncwarp();
+            const uint32_t cnt = min((uint32_t)GRP, nblk - b) * C * (sizeof(OrdSummary) / 8);
+            const unsigned long long *src = (const unsigned long long *)(sbase + (size_t)b * C);
+            unsigned long long *dst = (unsigned long long *)s_sum;
+            for (uint32_t i = lane; i < cnt; i += 32) dst[i] = src[i];
+            __syncwarp();
+        }
         if (use_summaries && chain) {
-            const OrdSummary sm = srow[(size_t)b * C];
+            const OrdSummary sm = s_sum[(b % GRP) * C + lane];
             const long long bits = __double_as_longlong(s);
             const int es = (int)((bits >> 52) & 0x7ff) - 1023;
             if (sm.flag == 0 && es == sm.e && es > -1000) {
                 const long long M = (bits & 0x000fffffffffffffLL) | TWO52; // |s| / q
-                const long long pp = (long long)sm.ppos, pn = (long long)sm.pneg;
                 const bool negs = bits < 0;
-                const long long up = negs ? pn : pp, dn = negs ? pp : pn; // growth / shrink of |s|
-                if (M - dn > TWO52 && M + up < TWO53) { // strict below: M + t itself must stay >= 2^52
-                    const long long M2 = M + up - dn;
+                // |s| / q after k elements = M + prefix_k (s > 0) or M - prefix_k (s < 0)
+                const long long d = (long long)sm.sum, lo = (long long)sm.mn, hi = (long long)sm.mx;
+                const long long vmin = negs ? M - hi : M + lo, vmax = negs ? M - lo : M + hi;
+                // strictly above 2^52: the unrounded M + t must itself stay inside the binade
+                if (vmin > TWO52 && vmax < TWO53) {
+                    const long long M2 = negs ? M - d : M + d;
                     s = __longlong_as_double((bits & 0xfff0000000000000LL) | (M2 & 0x000fffffffffffffLL));
                     accept = true;
                 }
             }
         }
         const bool need = chain && !accept;
+        n_acc += accept;
+        n_rep += need;
         if (__any_sync(0xffffffffu, need)) {
             // replay this block sequentially for the lanes that need it (the literal reference loop)
             const uint32_t base = b * OB, cnt = min((uint32_t)OB, n - base);
@@ -294,6 +337,10 @@ __global__ void __launch_bounds__(32) k_ord_resolve(PbPlanes b0, PbPlanes b1, co
                     s = __dadd_rn(s, term_one<KIND, W>(lane, tile[0][i], tile[1][i], tile[2][i], tile[3][i], m0, m1, m2));
             }
         }
+    }
+    if (chain && use_summaries) {
+        atomicAdd(&g_ord_counts[0], (unsigned long long)n_acc);
+        atomicAdd(&g_ord_counts[1], (unsigned long long)n_rep);
     }
     if (KIND == KIND_MEAN) {
         // matrix2D.c:230-231: s = 1 / wsum (1 / rows when unweighted); mean *= s
@@ -334,6 +381,14 @@ void launch_pass(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t
 }
 
 } // namespace
+
+void pb_ordered_counts(unsigned long long out[2], bool reset) {
+    PB_CUDA_OK(cudaMemcpyFromSymbol(out, g_ord_counts, sizeof(unsigned long long) * 2));
+    if (reset) {
+        unsigned long long z[2] = {0, 0};
+        PB_CUDA_OK(cudaMemcpyToSymbol(g_ord_counts, z, sizeof z));
+    }
+}
 
 size_t pb_ordered_scratch_bytes(int nseg, uint32_t max_n) {
     const size_t blk_cap = ((size_t)max_n + OB - 1) / OB;

@@ -639,6 +639,13 @@ void patolette_b200_device(size_t width, size_t height, const double *d_data, co
     }
 }
 
+int patolette_b200_ordered_counts(unsigned long long *out2, int reset) {
+    try {
+        pb_ordered_counts(out2, reset != 0);
+        return 0;
+    } catch (const pb_cuda_error &e) { return -(int)e.code; }
+}
+
 int patolette_b200_set_stream(void *cuda_stream, int enable) {
     g_user_stream = (cudaStream_t)cuda_stream;
     g_use_user_stream = enable != 0;
