@@ -38,7 +38,6 @@ namespace {
 
 constexpr int OB = 512;         // elements per summary block
 constexpr int OB_THREADS = 128; // S1/S3: 4 elements per thread
-constexpr int OB_STRIDE = OB + 2;
 constexpr int E_NOGUESS = 0x7fffffff;
 constexpr double MAGIC = 6755399441055744.0;      // 1.5 * 2^52: (t + MAGIC) - MAGIC == rint(t) for |t| < 2^51
 constexpr double TWO51 = 2251799813685248.0;
@@ -258,100 +257,165 @@ __global__ void __launch_bounds__(OB_THREADS) k_ord_summary(PbPlanes b0, PbPlane
     }
 }
 
-// ---- S4: ordered resolve (and the plain sequential chain when use_summaries == false) ---------------
+// ---- S4: ordered resolve ---------------------------------------------------------------------------
+// One CTA per cluster, one WARP per chain.  The warp's state is the exact running sum s (uniform
+// across lanes).  Blocks are taken 32 at a time, lane b holding the summary of block b: an in-order
+// warp scan of the block totals gives every lane the exact state its block would start from IF all
+// earlier blocks are accepted, each lane validates its own block against that state, and a ballot
+// finds the first block that cannot be accepted.  Everything before it is applied in one step; that
+// block is replayed; the walk resumes behind it.
+//
+// Replaying a block uses the same idea one level down, now with the EXACT binade (s is known):
+// each lane quantises its 16 consecutive elements, the warp scans / validates / ballots, accepted
+// sub-chunks are applied at once and only the sub-chunk where the binade changes (or a tie sits) is
+// added element by element - the literal reference loop, 16 elements long.
+constexpr int SUB = OB / 32; // elements per lane in a replay
+
+__device__ __forceinline__ long long warp_incl_scan(long long v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long u = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += u;
+    }
+    return v;
+}
+
+// Applies blocks / sub-chunks [next, limit) held one per lane as (ok, d, lo, hi) to the state s as far
+// as they validate.  Returns the first index that does not (limit if all do) and updates s.
+__device__ __forceinline__ uint32_t apply_run(double &s, int lane, uint32_t next, uint32_t limit, bool ok,
+                                             long long d, long long lo, long long hi) {
+    const long long bits = __double_as_longlong(s);
+    const long long M = (bits & 0x000fffffffffffffLL) | TWO52; // |s| / q
+    const bool negs = bits < 0;
+    const bool mine = lane >= (int)next && lane < (int)limit;
+    const long long inc = (mine && ok) ? d : 0;
+    const long long incl = warp_incl_scan(inc, lane);
+    const long long pre = incl - inc;
+    // |s| / q after k elements of this item = cur +- prefix_k
+    const long long cur = negs ? M - pre : M + pre;
+    const long long vmin = negs ? cur - hi : cur + lo, vmax = negs ? cur - lo : cur + hi;
+    // strictly above 2^52: the unrounded value must itself stay inside the binade
+    const bool valid = ok && vmin > TWO52 && vmax < TWO53;
+    const unsigned fails = __ballot_sync(0xffffffffu, mine && !valid);
+    const uint32_t f = fails ? (uint32_t)(__ffs(fails) - 1) : limit;
+    if (f > next) {
+        const long long tot = __shfl_sync(0xffffffffu, f < limit ? pre : incl, f < limit ? (int)f : (int)limit - 1);
+        const long long M2 = negs ? M - tot : M + tot;
+        s = __longlong_as_double((bits & 0xfff0000000000000LL) | (M2 & 0x000fffffffffffffLL));
+    }
+    return f;
+}
+
 template <int KIND, bool W>
-__global__ void __launch_bounds__(32) k_ord_resolve(PbPlanes b0, PbPlanes b1, const PbSeg *__restrict__ segs,
-                                                    PbStats *__restrict__ stats, uint32_t blk_cap,
-                                                    const OrdSummary *__restrict__ sum, bool use_summaries) {
+__device__ __forceinline__ double replay_block(const PbPlanes &P, size_t first, uint32_t cnt, int chain, double m0,
+                                               double m1, double m2, double s, int lane) {
+    double t[SUB];
+    const int my = max(0, min(SUB, (int)cnt - lane * SUB));
+#pragma unroll
+    for (int k = 0; k < SUB; k++) {
+        t[k] = 0.0;
+        if (k < my) {
+            const size_t p = first + (size_t)lane * SUB + k;
+            t[k] = term_one<KIND, W>(chain, W ? P.w[p] : 1.0, P.c[0][p], P.c[1][p], P.c[2][p], m0, m1, m2);
+        }
+    }
+    const uint32_t nl = (cnt + SUB - 1) / SUB; // lanes that hold elements
+    uint32_t next = 0;
+    while (next < nl) {
+        const long long bits = __double_as_longlong(s);
+        const int ef = (int)((bits >> 52) & 0x7ff);
+        uint32_t f = next;
+        if (ef > 24 && ef < 2000) { // a normal, finite state: quantise against its exact binade
+            const double scale = scalbn(1.0, 52 - (ef - 1023));
+            Tri tri{0.0, 0.0, 0.0};
+            int flag = 0;
+#pragma unroll
+            for (int k = 0; k < SUB; k++) {
+                if (k < my) {
+                    const double u = __dmul_rn(t[k], scale);
+                    const double d = __dsub_rn(__dadd_rn(u, MAGIC), MAGIC);
+                    flag |= !(fabs(u) < TWO51) | (fabs(__dsub_rn(u, d)) == 0.5);
+                    const double ps = tri.sum + d;
+                    tri.mn = k == 0 ? ps : fmin(tri.mn, ps);
+                    tri.mx = k == 0 ? ps : fmax(tri.mx, ps);
+                    tri.sum = ps;
+                }
+            }
+            f = apply_run(s, lane, next, nl, !flag && my > 0, (long long)tri.sum, (long long)tri.mn, (long long)tri.mx);
+        }
+        if (f < nl) { // sub-chunk f: element by element (binade change, tie, or a zero / subnormal state)
+            double v = s;
+            if (lane == (int)f) {
+#pragma unroll
+                for (int k = 0; k < SUB; k++)
+                    if (k < my) v = __dadd_rn(v, t[k]);
+            }
+            s = __shfl_sync(0xffffffffu, v, (int)f);
+            next = f + 1;
+        } else {
+            next = nl;
+        }
+    }
+    return s;
+}
+
+template <int KIND, bool W>
+__global__ void __launch_bounds__(32 * NChains<KIND>::C) k_ord_resolve(PbPlanes b0, PbPlanes b1,
+                                                                       const PbSeg *__restrict__ segs,
+                                                                       PbStats *__restrict__ stats, uint32_t blk_cap,
+                                                                       const OrdSummary *__restrict__ sum,
+                                                                       bool use_summaries) {
     constexpr int C = NChains<KIND>::C;
-    __shared__ double tile[4][OB_STRIDE];
-    const int seg = blockIdx.x, lane = threadIdx.x;
+    __shared__ double s_res[C];
+    const int seg = blockIdx.x, chain = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const PbSeg sg = segs[seg];
     const PbPlanes &P = sg.buf ? b1 : b0;
     const uint32_t n = sg.n, nblk = (n + OB - 1) / OB;
     double m0 = 0, m1 = 0, m2 = 0;
     if (KIND == KIND_CENTERED) { m0 = stats[seg].mean[0]; m1 = stats[seg].mean[1]; m2 = stats[seg].mean[2]; }
-    const bool chain = lane < C;
-    // exact state of this lane's chain: s = M * 2^(e-52) while in integer mode, else the double s
-    double s = 0.0;
+    double s = 0.0; // exact running sum of this warp's chain
     unsigned int n_acc = 0, n_rep = 0;
-    constexpr int GRP = 32; // summaries of GRP blocks are staged in shared memory at a time
-    __shared__ OrdSummary s_sum[GRP * C];
-    const OrdSummary *sbase = sum + (size_t)seg * blk_cap * C;
-    for (uint32_t b = 0; b < nblk; b++) {
-        bool accept = false;
-        if (use_summaries && (b % GRP) == 0) {
-            __syncwarp();
-            const uint32_t cnt = min((uint32_t)GRP, nblk - b) * C * (sizeof(OrdSummary) / 8);
-            const unsigned long long *src = (const unsigned long long *)(sbase + (size_t)b * C);
-            unsigned long long *dst = (unsigned long long *)s_sum;
-            for (uint32_t i = lane; i < cnt; i += 32) dst[i] = src[i];
-            __syncwarp();
-        }
-        if (use_summaries && chain) {
-            const OrdSummary sm = s_sum[(b % GRP) * C + lane];
+    const OrdSummary *srow = sum + (size_t)seg * blk_cap * C + chain;
+    for (uint32_t g0 = 0; g0 < nblk; g0 += 32) {
+        const uint32_t gcnt = min(32u, nblk - g0);
+        OrdSummary sm{0.0, 0.0, 0.0, E_NOGUESS, 1};
+        if (use_summaries && lane < (int)gcnt) sm = srow[(size_t)(g0 + lane) * C];
+        uint32_t next = 0;
+        while (next < gcnt) {
             const long long bits = __double_as_longlong(s);
             const int es = (int)((bits >> 52) & 0x7ff) - 1023;
-            if (sm.flag == 0 && es == sm.e && es > -1000) {
-                const long long M = (bits & 0x000fffffffffffffLL) | TWO52; // |s| / q
-                const bool negs = bits < 0;
-                // |s| / q after k elements = M + prefix_k (s > 0) or M - prefix_k (s < 0)
-                const long long d = (long long)sm.sum, lo = (long long)sm.mn, hi = (long long)sm.mx;
-                const long long vmin = negs ? M - hi : M + lo, vmax = negs ? M - lo : M + hi;
-                // strictly above 2^52: the unrounded M + t must itself stay inside the binade
-                if (vmin > TWO52 && vmax < TWO53) {
-                    const long long M2 = negs ? M - d : M + d;
-                    s = __longlong_as_double((bits & 0xfff0000000000000LL) | (M2 & 0x000fffffffffffffLL));
-                    accept = true;
-                }
-            }
-        }
-        const bool need = chain && !accept;
-        n_acc += accept;
-        n_rep += need;
-        if (__any_sync(0xffffffffu, need)) {
-            // replay this block sequentially for the lanes that need it (the literal reference loop)
-            const uint32_t base = b * OB, cnt = min((uint32_t)OB, n - base);
-            __syncwarp();
-            for (uint32_t i = lane; i < cnt; i += 32) {
-                const size_t p = (size_t)sg.lo + base + i;
-                tile[0][i] = W ? P.w[p] : 1.0;
-                tile[1][i] = P.c[0][p];
-                tile[2][i] = P.c[1][p];
-                tile[3][i] = P.c[2][p];
-            }
-            __syncwarp();
-            if (need) {
-                uint32_t i = 0;
-                for (; i + 4 <= cnt; i += 4) {
-                    const double t0 = term_one<KIND, W>(lane, tile[0][i], tile[1][i], tile[2][i], tile[3][i], m0, m1, m2);
-                    const double t1 = term_one<KIND, W>(lane, tile[0][i + 1], tile[1][i + 1], tile[2][i + 1], tile[3][i + 1], m0, m1, m2);
-                    const double t2 = term_one<KIND, W>(lane, tile[0][i + 2], tile[1][i + 2], tile[2][i + 2], tile[3][i + 2], m0, m1, m2);
-                    const double t3 = term_one<KIND, W>(lane, tile[0][i + 3], tile[1][i + 3], tile[2][i + 3], tile[3][i + 3], m0, m1, m2);
-                    s = __dadd_rn(s, t0);
-                    s = __dadd_rn(s, t1);
-                    s = __dadd_rn(s, t2);
-                    s = __dadd_rn(s, t3);
-                }
-                for (; i < cnt; i++)
-                    s = __dadd_rn(s, term_one<KIND, W>(lane, tile[0][i], tile[1][i], tile[2][i], tile[3][i], m0, m1, m2));
+            const bool ok = use_summaries && sm.flag == 0 && sm.e == es && es > -1000 && es < 1000;
+            const uint32_t f = apply_run(s, lane, next, gcnt, ok, (long long)sm.sum, (long long)sm.mn, (long long)sm.mx);
+            n_acc += f - next;
+            if (f < gcnt) {
+                const uint32_t base = (g0 + f) * OB;
+                s = replay_block<KIND, W>(P, (size_t)sg.lo + base, min((uint32_t)OB, n - base), chain, m0, m1, m2, s, lane);
+                n_rep++;
+                next = f + 1;
+            } else {
+                next = gcnt;
             }
         }
     }
-    if (chain && use_summaries) {
-        atomicAdd(&g_ord_counts[0], (unsigned long long)n_acc);
-        atomicAdd(&g_ord_counts[1], (unsigned long long)n_rep);
+    if (lane == 0) {
+        s_res[chain] = s;
+        if (use_summaries) {
+            atomicAdd(&g_ord_counts[0], (unsigned long long)n_acc);
+            atomicAdd(&g_ord_counts[1], (unsigned long long)n_rep);
+        }
     }
-    if (KIND == KIND_MEAN) {
-        // matrix2D.c:230-231: s = 1 / wsum (1 / rows when unweighted); mean *= s
-        double wsum = __shfl_sync(0xffffffffu, s, 0);
-        if (!W) wsum = (double)n;
-        const double inv = 1.0 / wsum;
-        if (lane == 0) stats[seg].wsum = wsum;
-        if (lane >= 1 && lane <= 3) stats[seg].mean[lane - 1] = __dmul_rn(s, inv);
-    } else {
-        if (lane < 6) stats[seg].cov[lane] = s;
-        if (lane == 6) stats[seg].dist = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (KIND == KIND_MEAN) {
+            // matrix2D.c:230-231: scale = 1 / wsum (1 / rows when unweighted); mean *= scale
+            const double wsum = W ? s_res[0] : (double)n;
+            const double inv = 1.0 / wsum;
+            stats[seg].wsum = wsum;
+            for (int j = 0; j < 3; j++) stats[seg].mean[j] = __dmul_rn(s_res[1 + j], inv);
+        } else {
+            for (int j = 0; j < 6; j++) stats[seg].cov[j] = s_res[j];
+            stats[seg].dist = s_res[6];
+        }
     }
 }
 
@@ -376,7 +440,7 @@ void launch_pass(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t
           k_ord_summary<KIND, W><<<grid, OB_THREADS, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, blk_cap, sum); }
     }
     { PbProfScope p(KIND == KIND_MEAN ? "k_ord_resolve_mean" : "k_ord_resolve_centered", st, !speculative);
-      k_ord_resolve<KIND, W><<<nseg, 32, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, blk_cap, sum, speculative); }
+      k_ord_resolve<KIND, W><<<nseg, 32 * C, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, blk_cap, sum, speculative); }
     PB_CUDA_OK(cudaGetLastError());
 }
 
