@@ -30,9 +30,11 @@ struct pb_cuda_error {
 // A cluster = a contiguous range of the permuted pixel arrays (ascending original
 // pixel index inside the range, which is the order every reference sum runs in).
 struct PbSeg {
-    uint32_t lo;  // first permuted position
-    uint32_t n;   // pixel count
-    uint32_t buf; // which ping-pong buffer (0/1) holds it
+    uint32_t lo;    // first permuted position
+    uint32_t n;     // pixel count
+    uint32_t buf;   // which ping-pong buffer (0/1) holds it
+    uint32_t tbase; // first scatter tile of this segment in the packed per-batch tile table
+    uint32_t bbase; // first ordered-sum block of this segment in the packed per-batch block table
     uint32_t pad;
 };
 

@@ -23,15 +23,20 @@ void pb_launch_pow(const double *x, double y, double *out, size_t n, int sm_coun
 // ---- ordered-sum kernels, pb_ordered.cu / pb_chain.cu ----------------------------------
 // Every reference statistic is a left-to-right f64 sum in ascending pixel order; these
 // kernels reproduce that order bit for bit (see pb_chain.cu for how).
-// max_n = largest segment of the batch; d_scratch (pb_ordered_scratch_bytes) enables the
-// speculative block-summary path, without it (or for small segments) the sums run as chains.
-size_t pb_ordered_scratch_bytes(int nseg, uint32_t max_n);
+// max_n = largest segment of the batch (grid width); block tables are packed: segment s owns
+// blocks [s.bbase, s.bbase + blocks(s.n)) and total_blocks bounds the table.  With d_scratch
+// (pb_ordered_scratch_bytes(total_blocks)) large segments take the speculative block-summary
+// path, otherwise (and for small segments) the sums run as in-warp speculative replays only.
+uint32_t pb_ordered_blocks(uint32_t n);
+size_t pb_ordered_scratch_bytes(size_t total_blocks);
 // {blocks accepted from summaries, blocks replayed sequentially} per chain since the last reset
 void pb_ordered_counts(unsigned long long out[2], bool reset);
-void pb_launch_pass_mean(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t max_n, bool weighted,
-                         PbStats *d_stats, void *d_scratch, size_t scratch_bytes, cudaStream_t st);
-void pb_launch_pass_centered(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t max_n, bool weighted,
-                             PbStats *d_stats, void *d_scratch, size_t scratch_bytes, cudaStream_t st);
+void pb_launch_pass_mean(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t max_n,
+                         uint32_t total_blocks, bool weighted, PbStats *d_stats, void *d_scratch,
+                         size_t scratch_bytes, cudaStream_t st);
+void pb_launch_pass_centered(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t max_n,
+                             uint32_t total_blocks, bool weighted, PbStats *d_stats, void *d_scratch,
+                             size_t scratch_bytes, cudaStream_t st);
 // Per-bucket ordered sums over bucket-sorted position lists.
 //   LQ (local.c:102-146): out[seg][b] = {size (as double bits of u64), sum c0*w, sum c1*w, sum c2*w}
 //   GQ (cells.c:53-116):  out[b] = {sum c0, c1, c2, sum |c|^2, sums c_r*c_s (r<=s: 00,01,11,02,12,22)}
@@ -57,7 +62,7 @@ void pb_launch_split_select(const double *d_bucket_sums, const uint32_t *d_class
 // index list by an ascending scan: local.c:216-243, global.c:300-377).
 enum { PB_CLS_BUCKET = 0, PB_CLS_SPLIT = 1, PB_CLS_LUT = 2 };
 size_t pb_scatter_tiles(uint32_t n);
-// d_tile_hist: nseg * tiles(max_n) * nclass u32 ; d_class_start: nseg * (nclass + 1) u32
+// d_tile_hist: packed by PbSeg::tbase, (sum of tiles) * nclass u32 ; d_class_start: nseg * (nclass + 1) u32
 void pb_launch_class_rank(int cls_mode, int nclass, const PbSeg *d_segs, int nseg, uint32_t max_n,
                           const uint16_t *d_bucket, const PbSplit *d_split, const uint8_t *d_lut,
                           uint32_t *d_tile_hist, uint32_t *d_class_start, cudaStream_t st);

@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(OB_THREADS) k_ord_blocksum(PbPlanes b0, PbPlan
             for (int c = 0; c < C; c++) acc[c] += t[c];
         }
     }
-    double *out = psum + ((size_t)seg * blk_cap + blockIdx.x) * C;
+    double *out = psum + ((size_t)sg.bbase + blockIdx.x) * C;
 #pragma unroll
     for (int c = 0; c < C; c++) {
         const double r = block_reduce_sum(acc[c], red);
@@ -154,8 +154,8 @@ __global__ void __launch_bounds__(32) k_ord_prefix(const PbSeg *__restrict__ seg
                                                    const double *__restrict__ psum, OrdSummary *__restrict__ sum) {
     const int seg = blockIdx.y, c = blockIdx.x, lane = threadIdx.x;
     const uint32_t nblk = (segs[seg].n + OB - 1) / OB;
-    const double *in = psum + (size_t)seg * blk_cap * C + c;
-    OrdSummary *out = sum + (size_t)seg * blk_cap * C + c;
+    const double *in = psum + (size_t)segs[seg].bbase * C + c;
+    OrdSummary *out = sum + (size_t)segs[seg].bbase * C + c;
     const uint32_t per = (nblk + 31) / 32;
     const uint32_t b0 = min(lane * per, nblk), b1 = min(b0 + per, nblk);
     double s = 0.0;
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(OB_THREADS) k_ord_summary(PbPlanes b0, PbPlane
     const uint32_t base = blockIdx.x * OB;
     if (base >= sg.n) return;
     const PbPlanes &P = sg.buf ? b1 : b0;
-    OrdSummary *out = sum + ((size_t)seg * blk_cap + blockIdx.x) * C;
+    OrdSummary *out = sum + ((size_t)sg.bbase + blockIdx.x) * C;
     double m0 = 0, m1 = 0, m2 = 0;
     if (KIND == KIND_CENTERED) { m0 = stats[seg].mean[0]; m1 = stats[seg].mean[1]; m2 = stats[seg].mean[2]; }
     double scale[C];
@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(32 * NChains<KIND>::C) k_ord_resolve(PbPlanes 
     if (KIND == KIND_CENTERED) { m0 = stats[seg].mean[0]; m1 = stats[seg].mean[1]; m2 = stats[seg].mean[2]; }
     double s = 0.0; // exact running sum of this warp's chain
     unsigned int n_acc = 0, n_rep = 0;
-    const OrdSummary *srow = sum + (size_t)seg * blk_cap * C + chain;
+    const OrdSummary *srow = sum + (size_t)sg.bbase * C + chain;
     for (uint32_t g0 = 0; g0 < nblk; g0 += 32) {
         const uint32_t gcnt = min(32u, nblk - g0);
         OrdSummary sm{0.0, 0.0, 0.0, E_NOGUESS, 1};
@@ -420,14 +420,14 @@ __global__ void __launch_bounds__(32 * NChains<KIND>::C) k_ord_resolve(PbPlanes 
 }
 
 template <int KIND, bool W>
-void launch_pass(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t max_n, PbStats *d_stats,
-                 void *d_scratch, size_t scratch_bytes, cudaStream_t st) {
+void launch_pass(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t max_n, uint32_t total_blocks,
+                 PbStats *d_stats, void *d_scratch, size_t scratch_bytes, cudaStream_t st) {
     constexpr int C = NChains<KIND>::C;
-    const uint32_t blk_cap = (max_n + OB - 1) / OB;
-    const size_t need = (size_t)nseg * blk_cap * C * (sizeof(double) + sizeof(OrdSummary));
+    const uint32_t blk_cap = (max_n + OB - 1) / OB; // grid width; the tables are packed by PbSeg::bbase
+    const size_t need = (size_t)total_blocks * C * (sizeof(double) + sizeof(OrdSummary));
     const bool speculative = max_n >= 8 * OB && d_scratch && need <= scratch_bytes;
     double *psum = (double *)d_scratch;
-    OrdSummary *sum = (OrdSummary *)((char *)d_scratch + (size_t)nseg * blk_cap * C * sizeof(double));
+    OrdSummary *sum = (OrdSummary *)((char *)d_scratch + (size_t)total_blocks * C * sizeof(double));
     const double bytes = 0; // set by the caller through pb_prof_next_bytes for the resolve kernel
     (void)bytes;
     if (speculative) {
@@ -454,21 +454,24 @@ void pb_ordered_counts(unsigned long long out[2], bool reset) {
     }
 }
 
-size_t pb_ordered_scratch_bytes(int nseg, uint32_t max_n) {
-    const size_t blk_cap = ((size_t)max_n + OB - 1) / OB;
-    return (size_t)nseg * blk_cap * 7 * (sizeof(double) + sizeof(OrdSummary)) + 256;
+uint32_t pb_ordered_blocks(uint32_t n) { return (n + OB - 1) / OB; }
+
+size_t pb_ordered_scratch_bytes(size_t total_blocks) {
+    return total_blocks * 7 * (sizeof(double) + sizeof(OrdSummary)) + 256;
 }
 
-void pb_launch_pass_mean(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t max_n, bool weighted,
-                         PbStats *d_stats, void *d_scratch, size_t scratch_bytes, cudaStream_t st) {
+void pb_launch_pass_mean(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t max_n,
+                         uint32_t total_blocks, bool weighted, PbStats *d_stats, void *d_scratch,
+                         size_t scratch_bytes, cudaStream_t st) {
     if (nseg <= 0) return;
-    if (weighted) launch_pass<KIND_MEAN, true>(bufs, d_segs, nseg, max_n, d_stats, d_scratch, scratch_bytes, st);
-    else launch_pass<KIND_MEAN, false>(bufs, d_segs, nseg, max_n, d_stats, d_scratch, scratch_bytes, st);
+    if (weighted) launch_pass<KIND_MEAN, true>(bufs, d_segs, nseg, max_n, total_blocks, d_stats, d_scratch, scratch_bytes, st);
+    else launch_pass<KIND_MEAN, false>(bufs, d_segs, nseg, max_n, total_blocks, d_stats, d_scratch, scratch_bytes, st);
 }
 
-void pb_launch_pass_centered(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t max_n, bool weighted,
-                             PbStats *d_stats, void *d_scratch, size_t scratch_bytes, cudaStream_t st) {
+void pb_launch_pass_centered(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t max_n,
+                             uint32_t total_blocks, bool weighted, PbStats *d_stats, void *d_scratch,
+                             size_t scratch_bytes, cudaStream_t st) {
     if (nseg <= 0) return;
-    if (weighted) launch_pass<KIND_CENTERED, true>(bufs, d_segs, nseg, max_n, d_stats, d_scratch, scratch_bytes, st);
-    else launch_pass<KIND_CENTERED, false>(bufs, d_segs, nseg, max_n, d_stats, d_scratch, scratch_bytes, st);
+    if (weighted) launch_pass<KIND_CENTERED, true>(bufs, d_segs, nseg, max_n, total_blocks, d_stats, d_scratch, scratch_bytes, st);
+    else launch_pass<KIND_CENTERED, false>(bufs, d_segs, nseg, max_n, total_blocks, d_stats, d_scratch, scratch_bytes, st);
 }

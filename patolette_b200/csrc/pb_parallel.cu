@@ -190,7 +190,7 @@ __global__ void k_tile_hist(ClsCtx cc, int nclass, const PbSeg *__restrict__ seg
     const uint32_t beg = tile * SC_TILE, end = min(beg + (uint32_t)SC_TILE, sg.n);
     for (uint32_t i = beg + lane; i < end; i += 32) atomicAdd(&cnt[cls_of(cc, seg, sg.lo + i)], 1u);
     __syncwarp();
-    uint32_t *out = tile_hist + ((size_t)seg * tiles_cap + tile) * nclass;
+    uint32_t *out = tile_hist + ((size_t)sg.tbase + tile) * nclass;
     for (int c = lane; c < nclass; c += 32) out[c] = cnt[c];
 }
 
@@ -202,7 +202,7 @@ __global__ void k_tile_scan(int nclass, const PbSeg *__restrict__ segs, uint32_t
     const int seg = blockIdx.y;
     if (warp >= nclass) return;
     const uint32_t ntiles = (segs[seg].n + SC_TILE - 1) / SC_TILE;
-    uint32_t *h = tile_hist + (size_t)seg * tiles_cap * nclass + warp;
+    uint32_t *h = tile_hist + (size_t)segs[seg].tbase * nclass + warp;
     const uint32_t per = (ntiles + 31) / 32;
     const uint32_t t0 = min(lane * per, ntiles), t1 = min(t0 + per, ntiles);
     uint32_t sum = 0;
@@ -243,7 +243,7 @@ __global__ void k_scatter(ClsCtx cc, int nclass, const PbSeg *__restrict__ segs,
     const uint32_t tile = blockIdx.x * warps + warp;
     if ((size_t)tile * SC_TILE >= sg.n) return;
     uint32_t *cnt = s_cnt + warp * (nclass + 1);
-    const uint32_t *hist = tile_hist + ((size_t)seg * tiles_cap + tile) * nclass;
+    const uint32_t *hist = tile_hist + ((size_t)sg.tbase + tile) * nclass;
     const uint32_t *cst = class_start + (size_t)seg * (nclass + 1);
     for (int c = lane; c < nclass; c += 32) cnt[c] = hist[c] + cst[c];
     if (lane == 0) cnt[nclass] = 0;
@@ -283,8 +283,11 @@ __global__ void k_make_children(const PbSeg *__restrict__ segs, int nseg, const 
     if (i >= nseg) return;
     const PbSeg sg = segs[i];
     const uint32_t nl = sp[i].nleft;
-    children[2 * i] = PbSeg{sg.lo, nl, sg.buf ^ 1u, 0u};
-    children[2 * i + 1] = PbSeg{sg.lo + nl, sg.n - nl, sg.buf ^ 1u, 0u};
+    // each child gets an ordered-sum block region as large as its parent's (its own size is only
+    // known on the device): regions of a batch stay disjoint and total 2 * sum(parent blocks + 1)
+    const uint32_t pb = (sg.n + 511u) / 512u + 1u;
+    children[2 * i] = PbSeg{sg.lo, nl, sg.buf ^ 1u, 0u, 2u * sg.bbase, 0u};
+    children[2 * i + 1] = PbSeg{sg.lo + nl, sg.n - nl, sg.buf ^ 1u, 0u, 2u * sg.bbase + pb, 0u};
 }
 
 // ---------------------------------------------------------------------------------
@@ -321,7 +324,7 @@ __global__ void k_labels(PbPlanes b0, PbPlanes b1, const PbSeg *__restrict__ seg
     const PbSeg sg = segs[seg];
     const PbPlanes &P = sg.buf ? b1 : b0;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < sg.n; i += gridDim.x * blockDim.x)
-        labels[P.idx[sg.lo + i]] = (uint32_t)seg;
+        labels[P.idx[sg.lo + i]] = sg.pad; // the caller stores the cluster slot in PbSeg::pad
 }
 
 inline int blocks_for(uint32_t max_n, int sm_count) {

@@ -224,7 +224,8 @@ struct Quantizer {
     DevArr<char> oscratch; // block sums + summaries of the speculative ordered sums
     PbPlanes orig{}, bufs[2]{};
 
-    static constexpr int MAXB = 16; // segments per batch
+    static constexpr int MAXB = 16; // clusters evaluated per batch (their 2 * MAXB children get stats)
+    size_t max_blocks = 0;         // capacity of the packed ordered-sum block table
 
     void init(size_t n, bool with_weights) {
         N = n;
@@ -248,17 +249,18 @@ struct Quantizer {
         }
         bucket.alloc(N);
         ord.alloc(N);
-        tile_hist.alloc(2 * pb_scatter_tiles((uint32_t)N) * PB_BUCKETS + 64);
-        cstart_b.alloc(2 * (PB_BUCKETS + 1));
-        cstart_s.alloc(2 * 17);
-        bsums.alloc(2 * PB_BUCKETS * 10);
+        tile_hist.alloc((pb_scatter_tiles((uint32_t)N) + MAXB) * PB_BUCKETS + 64);
+        cstart_b.alloc(MAXB * (PB_BUCKETS + 1));
+        cstart_s.alloc(MAXB * 17);
+        bsums.alloc(MAXB * PB_BUCKETS * 10);
         axes.alloc(MAXB * 3);
         segs.alloc(MAXB);
         children.alloc(2 * MAXB);
         stats.alloc(2 * MAXB);
         split.alloc(MAXB);
         lut.alloc(PB_BUCKETS);
-        oscratch.alloc(pb_ordered_scratch_bytes(MAXB, (uint32_t)N));
+        max_blocks = 2 * ((size_t)pb_ordered_blocks((uint32_t)N) + 2 * MAXB) + 64;
+        oscratch.alloc(pb_ordered_scratch_bytes(max_blocks));
     }
     ~Quantizer() {
         if (st && own_stream) cudaStreamDestroy(st);
@@ -275,14 +277,14 @@ struct Quantizer {
 
     // ---- GQ (global.c:388-443): returns cluster count, 0 on error -------------------
     size_t run_gq(size_t K, std::vector<HNode> &out) {
-        PbSeg whole{0u, (uint32_t)N, 0u, 0u};
+        PbSeg whole{0u, (uint32_t)N, 0u, 0u, 0u, 0u};
         PbStats hst;
         const PbPlanes gq[2] = {orig, orig};
         h2d(segs.p, &whole, 1);
         pb_prof_next_bytes(24.0 * N);
-        pb_launch_pass_mean(gq, segs.p, 1, (uint32_t)N, false, stats.p, oscratch.p, oscratch.n, st);     // global.c:407: UNWEIGHTED PCA
+        pb_launch_pass_mean(gq, segs.p, 1, (uint32_t)N, (uint32_t)max_blocks, false, stats.p, oscratch.p, oscratch.n, st);     // global.c:407: UNWEIGHTED PCA
         pb_prof_next_bytes(24.0 * N);
-        pb_launch_pass_centered(gq, segs.p, 1, (uint32_t)N, false, stats.p, oscratch.p, oscratch.n, st);
+        pb_launch_pass_centered(gq, segs.p, 1, (uint32_t)N, (uint32_t)max_blocks, false, stats.p, oscratch.p, oscratch.n, st);
         d2h(&hst, stats.p, 1);
         sync();
         double v[9], axis[3];
@@ -345,14 +347,18 @@ struct Quantizer {
         sync();
         out.resize(cells);
         std::vector<PbSeg> hsegs(cells);
-        for (size_t j = 0; j < cells; j++) hsegs[j] = PbSeg{cst[j], cst[j + 1] - cst[j], 0u, 0u};
+        uint32_t bb = 0;
+        for (size_t j = 0; j < cells; j++) {
+            hsegs[j] = PbSeg{cst[j], cst[j + 1] - cst[j], 0u, 0u, bb, 0u};
+            bb += pb_ordered_blocks(hsegs[j].n) + 1;
+        }
         h2d(segs.p, hsegs.data(), cells);
         uint32_t cmax = 0;
         for (size_t j = 0; j < cells; j++) cmax = std::max(cmax, hsegs[j].n);
         pb_prof_next_bytes((weighted ? 32.0 : 24.0) * N);
-        pb_launch_pass_mean(bufs, segs.p, (int)cells, cmax, weighted, stats.p, oscratch.p, oscratch.n, st);
+        pb_launch_pass_mean(bufs, segs.p, (int)cells, cmax, (uint32_t)max_blocks, weighted, stats.p, oscratch.p, oscratch.n, st);
         pb_prof_next_bytes((weighted ? 32.0 : 24.0) * N);
-        pb_launch_pass_centered(bufs, segs.p, (int)cells, cmax, weighted, stats.p, oscratch.p, oscratch.n, st);
+        pb_launch_pass_centered(bufs, segs.p, (int)cells, cmax, (uint32_t)max_blocks, weighted, stats.p, oscratch.p, oscratch.n, st);
         std::vector<PbStats> hstats(cells);
         d2h(hstats.data(), stats.p, cells);
         sync();
@@ -370,12 +376,16 @@ struct Quantizer {
         }
     }
 
-    // ---- split_cluster (local.c:179-254) for up to two clusters at once -------------
+    // ---- split_cluster (local.c:179-254) for a batch of clusters ------------------------
+    // For every node: principal axis (host 3x3 eigen solve), projections, 512 buckets, ordered
+    // per-bucket sums, optimal cut, stable partition into the other ping-pong buffer, and the
+    // mean / covariance / distortion of both children.  One host synchronisation per batch.
     void eval_split(HNode *const nodes[], HPair *const outs[], int count) {
-        PbSeg hsegs[2];
-        double haxes[6];
-        int map[2], nb = 0;
-        uint32_t max_n = 0;
+        PbSeg hsegs[MAXB];
+        double haxes[3 * MAXB];
+        int map[MAXB], nb = 0;
+        uint32_t max_n = 0, tb = 0, bb = 0;
+        double tot_n = 0;
         for (int i = 0; i < count; i++) {
             outs[i]->valid = false;
             if (nodes[i]->seg.n <= 1) continue; // local.c:187
@@ -383,15 +393,18 @@ struct Quantizer {
             fill_vcov(nodes[i]->st, v);
             if (!pca_axis_from_vcov(v, axis)) continue; // local.c:193-196
             hsegs[nb] = nodes[i]->seg;
+            hsegs[nb].tbase = tb;
+            hsegs[nb].bbase = bb;
+            tb += (uint32_t)pb_scatter_tiles(hsegs[nb].n);
+            bb += pb_ordered_blocks(hsegs[nb].n) + 1;
             memcpy(&haxes[3 * nb], axis, sizeof axis);
             max_n = std::max(max_n, nodes[i]->seg.n);
+            tot_n += nodes[i]->seg.n;
             map[nb++] = i;
         }
         if (nb == 0) return;
         h2d(segs.p, hsegs, nb);
         h2d(axes.p, haxes, 3 * nb);
-        double tot_n = 0;
-        for (int b = 0; b < nb; b++) tot_n += hsegs[b].n;
         const double bpp = weighted ? 32.0 : 24.0; // planar f64 payload per pixel
         pb_prof_next_bytes(24.0 * tot_n);
         pb_launch_dots_minmax(bufs, segs.p, nb, max_n, axes.p, split.p, sm_count, st);
@@ -412,11 +425,13 @@ struct Quantizer {
                                   lut.p, tile_hist.p, cstart_s.p, st);
         pb_launch_make_children(segs.p, nb, split.p, children.p, st);
         pb_prof_next_bytes(bpp * tot_n);
-        pb_launch_pass_mean(bufs, children.p, 2 * nb, max_n, weighted, stats.p, oscratch.p, oscratch.n, st);
+        pb_launch_pass_mean(bufs, children.p, 2 * nb, max_n, (uint32_t)max_blocks, weighted, stats.p, oscratch.p,
+                            oscratch.n, st);
         pb_prof_next_bytes(bpp * tot_n);
-        pb_launch_pass_centered(bufs, children.p, 2 * nb, max_n, weighted, stats.p, oscratch.p, oscratch.n, st);
-        PbSeg hch[4];
-        PbStats hst[4];
+        pb_launch_pass_centered(bufs, children.p, 2 * nb, max_n, (uint32_t)max_blocks, weighted, stats.p,
+                                oscratch.p, oscratch.n, st);
+        PbSeg hch[2 * MAXB];
+        PbStats hst[2 * MAXB];
         d2h(hch, children.p, 2 * nb);
         d2h(hst, stats.p, 2 * nb);
         sync();
@@ -428,16 +443,35 @@ struct Quantizer {
         }
     }
 
-    // ---- LQ (local.c:318-404) -------------------------------------------------------
+    static double benefit_of(const HNode &c, const HPair &ch) { // local.c:256-275
+        return ch.valid ? c.st.dist - (ch.l.st.dist + ch.r.st.dist) : 0;
+    }
+
+    // ---- LQ (local.c:318-404) ---------------------------------------------------------
+    // The reference splits the best leaf, then evaluates split_cluster() of its two children
+    // before it can pick again (local.c:378-379): 2 clusters per step, K-1 dependent steps.
+    // split_cluster(c) is a pure function of c's pixel set, so the ORDER in which leaves get
+    // evaluated is free.  We therefore pre-evaluate the children of the leaves that will be
+    // picked soonest (the current top benefits) together with the ones needed right now - one
+    // batch of up to MAXB clusters per host round trip instead of two.  Picks, slot assignment
+    // and termination follow the reference exactly; only the scheduling differs.
+    struct Pre {
+        bool have = false;
+        HPair l, r; // split_cluster(children[slot].l), split_cluster(children[slot].r)
+    };
+
     void run_lq(std::vector<HNode> &clusters, size_t K) {
         size_t len = clusters.size();
         if (len >= K) return;
         clusters.resize(K);
         std::vector<HPair> children(K);
-        for (size_t i = 0; i < len; i += 2) {
-            HNode *nn[2] = {&clusters[i], i + 1 < len ? &clusters[i + 1] : nullptr};
-            HPair *oo[2] = {&children[i], i + 1 < len ? &children[i + 1] : nullptr};
-            eval_split(nn, oo, i + 1 < len ? 2 : 1);
+        std::vector<Pre> pre(K);
+        for (size_t i = 0; i < len; i += MAXB) { // local.c:342-345
+            HNode *nn[MAXB];
+            HPair *oo[MAXB];
+            int c = 0;
+            for (size_t j = i; j < len && c < MAXB; j++, c++) { nn[c] = &clusters[j]; oo[c] = &children[j]; }
+            eval_split(nn, oo, c);
         }
         size_t i;
         for (i = len; i < K; i++) {
@@ -445,20 +479,48 @@ struct Quantizer {
             size_t best = 0;
             double bb = 0;
             for (size_t j = 0; j < i; j++) {
-                double b = children[j].valid
-                               ? clusters[j].st.dist - (children[j].l.st.dist + children[j].r.st.dist)
-                               : 0;
+                const double b = benefit_of(clusters[j], children[j]);
                 if (j == 0 || b > bb) { bb = b; best = j; }
             }
             if (bb < PB_DELTA) break; // local.c:365-370
-            clusters[i] = children[best].l;     // local.c:375
-            clusters[best] = children[best].r;  // local.c:376
-            HNode *nn[2] = {&clusters[i], &clusters[best]};
-            HPair *oo[2] = {&children[i], &children[best]};
-            eval_split(nn, oo, 2);
+            if (!pre[best].have) {
+                // evaluate the grandchildren of `best` now, and speculatively those of the next
+                // most beneficial leaves (they are the next picks unless a new leaf overtakes them)
+                std::vector<size_t> cand;
+                for (size_t j = 0; j < i; j++)
+                    if (j != best && children[j].valid && !pre[j].have && benefit_of(clusters[j], children[j]) >= PB_DELTA)
+                        cand.push_back(j);
+                std::sort(cand.begin(), cand.end(), [&](size_t a, size_t b) {
+                    return benefit_of(clusters[a], children[a]) > benefit_of(clusters[b], children[b]);
+                });
+                const size_t remaining = K - i; // picks still to make, this one included
+                size_t take = std::min<size_t>({cand.size(), (size_t)MAXB / 2 - 1, remaining - 1});
+                HNode *nn[MAXB];
+                HPair *oo[MAXB];
+                int c = 0;
+                auto add = [&](size_t slot) {
+                    nn[c] = &children[slot].l; oo[c++] = &pre[slot].l;
+                    nn[c] = &children[slot].r; oo[c++] = &pre[slot].r;
+                    pre[slot].have = true;
+                };
+                add(best);
+                for (size_t t = 0; t < take; t++) add(cand[t]);
+                eval_split(nn, oo, c);
+            }
+            const Pre p = pre[best];
+            clusters[i] = children[best].l;    // local.c:375
+            clusters[best] = children[best].r; // local.c:376
+            children[i] = p.l;                 // local.c:378
+            children[best] = p.r;              // local.c:379
+            pre[i] = Pre{};
+            pre[best] = Pre{};
         }
         clusters.resize(i);
+        final_children.assign(children.begin(), children.begin() + i);
     }
+    // children of the final leaves: a leaf whose split was (pre-)evaluated had its own planes
+    // overwritten by its grandchildren's partition, so its members are read from its two children
+    std::vector<HPair> final_children;
 };
 
 void set_timing(int slot, double ms) { g_timings[slot] = ms; }
@@ -750,9 +812,19 @@ int patolette_b200_quantize_clusters(const double *planar, size_t n, const doubl
         if (labels) {
             DevArr<PbSeg> dsegs;
             DevArr<uint32_t> dlab;
-            std::vector<PbSeg> hs(clusters.size());
+            std::vector<PbSeg> hs;
             uint32_t max_n = 0;
-            for (size_t j = 0; j < clusters.size(); j++) { hs[j] = clusters[j].seg; max_n = std::max(max_n, hs[j].n); }
+            for (size_t j = 0; j < clusters.size(); j++) {
+                // a leaf whose split was evaluated is read through its two children (see run_lq)
+                const bool via_children = j < qz.final_children.size() && qz.final_children[j].valid;
+                PbSeg parts[2] = {via_children ? qz.final_children[j].l.seg : clusters[j].seg,
+                                  via_children ? qz.final_children[j].r.seg : PbSeg{}};
+                for (int t = 0; t < (via_children ? 2 : 1); t++) {
+                    parts[t].pad = (uint32_t)j;
+                    max_n = std::max(max_n, parts[t].n);
+                    hs.push_back(parts[t]);
+                }
+            }
             dsegs.alloc(hs.size());
             dlab.alloc(n);
             qz.h2d(dsegs.p, hs.data(), hs.size());
