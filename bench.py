@@ -236,7 +236,7 @@ def run_ours(args):
 
     # ---------------- per-kernel profile (untimed extra step) -> roofline ----------------
     lib.patolette_b200_set_stream(C.c_void_p(stream.cuda_stream), 1)
-    cnt = (C.c_ulonglong * 2)()
+    cnt = (C.c_ulonglong * 8)()
     lib.patolette_b200_ordered_counts(cnt, 1)
     lib.patolette_b200_profile_enable(1)
     step_resident()
@@ -285,7 +285,9 @@ def run_ours(args):
         "stage_ms": {k: round(v, 3) for k, v in stage.items()},
         "roofline": roofline, "clocks": clocks,
         "ordered_sums": {"blocks_accepted": ord_acc, "blocks_replayed": ord_rep,
-                         "replay_frac": ord_rep / max(ord_acc + ord_rep, 1)},
+                         "replay_frac": ord_rep / max(ord_acc + ord_rep, 1),
+                         "replay_reasons": {"flag": int(cnt[2]), "binade_guess": int(cnt[3]), "bounds": int(cnt[4])},
+                         "replay_rounds": int(cnt[5]), "elementwise_subchunks": int(cnt[6])},
     }
     if cpu_baseline is not None:
         line["cpu_baseline"] = cpu_baseline

@@ -111,9 +111,10 @@ PB200_API int patolette_b200_set_stream(void *cuda_stream, int enable);
 PB200_API int patolette_b200_profile_enable(int on);
 PB200_API size_t patolette_b200_profile_json(char *buf, size_t cap);
 
-/* Ordered-sum statistics since the last reset: out2[0] = (chain, block) pairs accepted from their
- * quantised summary, out2[1] = pairs replayed sequentially (pb_ordered.cu). */
-PB200_API int patolette_b200_ordered_counts(unsigned long long *out2, int reset);
+/* Ordered-sum statistics since the last reset (pb_ordered.cu), 8 counters: (chain, block) pairs
+ * accepted from their quantised summary, pairs replayed, replay reasons {tie/unquantisable flag,
+ * wrong binade guess, binade bounds}, replay rounds, element-wise 16-element sub-chunks, spare. */
+PB200_API int patolette_b200_ordered_counts(unsigned long long *out8, int reset);
 
 /* Timings of the last patolette() call on this process, milliseconds (CUDA events
  * on the library's stream; h2d/d2h include the host copies).  Keys in order:

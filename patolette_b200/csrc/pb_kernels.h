@@ -30,7 +30,7 @@ void pb_launch_pow(const double *x, double y, double *out, size_t n, int sm_coun
 uint32_t pb_ordered_blocks(uint32_t n);
 size_t pb_ordered_scratch_bytes(size_t total_blocks);
 // {blocks accepted from summaries, blocks replayed sequentially} per chain since the last reset
-void pb_ordered_counts(unsigned long long out[2], bool reset);
+void pb_ordered_counts(unsigned long long out[8], bool reset);
 void pb_launch_pass_mean(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t max_n,
                          uint32_t total_blocks, bool weighted, PbStats *d_stats, void *d_scratch,
                          size_t scratch_bytes, cudaStream_t st);

@@ -44,12 +44,21 @@ constexpr double TWO51 = 2251799813685248.0;
 constexpr long long TWO52 = 1LL << 52, TWO53 = 1LL << 53;
 
 // blocks accepted from their summary / blocks replayed sequentially (per chain), since last reset
-__device__ unsigned long long g_ord_counts[2];
+__device__ unsigned long long g_ord_counts[8]; // 0 accepted, 1 replayed, 2 flag, 3 binade guess, 4 bounds, 5 replay rounds, 6 element-wise sub-chunks
+
+// Quantised effect of a run of terms on the integer state M, for both parities of M at its start:
+// total, and min / max over the in-order prefixes.  The parity only matters through ties: a term
+// that lands exactly half-way (a/q = k + 0.5) is rounded to the EVEN neighbour, i.e. it adds k or
+// k + 1 depending on whether M + (everything before it) + k is even - a two-state transducer whose
+// composition is still associative.  After any element the parity of the state is
+// (p + prefix sum) mod 2, so no extra field is needed.
+struct Tri { double sum, mn, mx; };
+struct Tri2 { Tri p[2]; };
 
 struct OrdSummary {
-    double sum, mn, mx; // quantised terms of the block: total, min and max over its in-order prefixes
-    int e;              // guessed binade of the running sum across this block
-    int flag;           // non-zero: replay the block
+    Tri2 t;   // quantised terms of the block (integers stored as doubles)
+    int e;    // guessed binade of the running sum across this block
+    int flag; // non-zero: replay the block
 };
 
 enum { KIND_MEAN = 0, KIND_CENTERED = 1 };
@@ -180,9 +189,37 @@ __global__ void __launch_bounds__(32) k_ord_prefix(const PbSeg *__restrict__ seg
 //   (a ++ b).sum = a.sum + b.sum ; (a ++ b).mn = min(a.mn, a.sum + b.mn) ; likewise mx.
 // Each thread owns 4 CONSECUTIVE elements, warps reduce in lane order, warp 0..3 in warp order, so
 // mn / mx are the exact extremes of the running integer sum in element order.
-struct Tri { double sum, mn, mx; };
-__device__ __forceinline__ Tri tri_cat(const Tri &a, const Tri &b) {
-    return Tri{a.sum + b.sum, fmin(a.mn, a.sum + b.mn), fmax(a.mx, a.sum + b.mx)};
+__device__ __forceinline__ int dparity(double v) { return (int)((long long)v & 1LL); }
+
+// in-order concatenation a ++ b
+__device__ __forceinline__ Tri2 tri2_cat(const Tri2 &a, const Tri2 &b) {
+    Tri2 r;
+#pragma unroll
+    for (int p = 0; p < 2; p++) {
+        const Tri &x = a.p[p];
+        const Tri &y = b.p[(p + dparity(x.sum)) & 1];
+        r.p[p] = Tri{x.sum + y.sum, fmin(x.mn, x.sum + y.mn), fmax(x.mx, x.sum + y.mx)};
+    }
+    return r;
+}
+
+// append one term u = a / q to the run
+__device__ __forceinline__ void tri2_push(Tri2 &t, double u, int &flag, bool first) {
+    const double d = __dsub_rn(__dadd_rn(u, MAGIC), MAGIC); // rint(u), ties to even of u itself
+    const double r = __dsub_rn(u, d);                       // exact remainder
+    flag |= !(fabs(u) < TWO51);                             // unquantisable (or NaN)
+    const bool tie = fabs(r) == 0.5;
+    const double lo = tie ? floor(u) : d;                   // k  (u = k + 0.5)
+#pragma unroll
+    for (int p = 0; p < 2; p++) {
+        Tri &x = t.p[p];
+        // ties go to the neighbour that makes the state even: parity before = p + x.sum
+        const double dd = (tie && (((p + dparity(x.sum) + dparity(lo)) & 1) != 0)) ? lo + 1.0 : lo;
+        const double ps = x.sum + dd;
+        x.mn = first ? ps : fmin(x.mn, ps);
+        x.mx = first ? ps : fmax(x.mx, ps);
+        x.sum = ps;
+    }
 }
 
 template <int KIND, bool W>
@@ -191,7 +228,7 @@ __global__ void __launch_bounds__(OB_THREADS) k_ord_summary(PbPlanes b0, PbPlane
                                                             OrdSummary *__restrict__ sum) {
     constexpr int C = NChains<KIND>::C;
     constexpr int PER = OB / OB_THREADS;
-    __shared__ Tri s_tri[OB_THREADS / 32][C];
+    __shared__ Tri2 s_tri[OB_THREADS / 32][C];
     __shared__ int s_flag[C];
     const int seg = blockIdx.y;
     const PbSeg sg = segs[seg];
@@ -202,14 +239,15 @@ __global__ void __launch_bounds__(OB_THREADS) k_ord_summary(PbPlanes b0, PbPlane
     double m0 = 0, m1 = 0, m2 = 0;
     if (KIND == KIND_CENTERED) { m0 = stats[seg].mean[0]; m1 = stats[seg].mean[1]; m2 = stats[seg].mean[2]; }
     double scale[C];
-    Tri tri[C];
+    Tri2 tri[C];
     int flag[C];
+    bool any = false;
 #pragma unroll
     for (int c = 0; c < C; c++) {
         const int e = out[c].e;
         flag[c] = e == E_NOGUESS;
         scale[c] = flag[c] ? 0.0 : scalbn(1.0, 52 - e); // 1 / q
-        tri[c] = Tri{0.0, 1e300, -1e300};                 // empty sequence
+        tri[c].p[0] = tri[c].p[1] = Tri{0.0, 1e300, -1e300}; // empty run
     }
     if (threadIdx.x < C) s_flag[threadIdx.x] = 0;
     __syncthreads();
@@ -221,38 +259,33 @@ __global__ void __launch_bounds__(OB_THREADS) k_ord_summary(PbPlanes b0, PbPlane
             double t[C];
             terms_all<KIND, W>(W ? P.w[p] : 1.0, P.c[0][p], P.c[1][p], P.c[2][p], m0, m1, m2, t);
 #pragma unroll
-            for (int c = 0; c < C; c++) {
-                const double u = __dmul_rn(t[c], scale[c]);             // a / q, exact (power of two)
-                const double d = __dsub_rn(__dadd_rn(u, MAGIC), MAGIC); // rint(u)
-                const double r = __dsub_rn(u, d);                       // exact remainder
-                flag[c] |= !(fabs(u) < TWO51) | (fabs(r) == 0.5);       // unquantisable / tie / NaN
-                const double ps = tri[c].sum + d;
-                tri[c] = Tri{ps, fmin(tri[c].mn, ps), fmax(tri[c].mx, ps)};
-            }
+            for (int c = 0; c < C; c++) tri2_push(tri[c], __dmul_rn(t[c], scale[c]) /* a / q, exact */, flag[c], !any);
+            any = true;
         }
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int c = 0; c < C; c++) {
         if (flag[c]) atomicOr(&s_flag[c], 1);
-        Tri v = tri[c];
+        Tri2 v = tri[c];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { // in-order tree: lane i absorbs lane i + o
-            Tri r;
-            r.sum = __shfl_down_sync(0xffffffffu, v.sum, o);
-            r.mn = __shfl_down_sync(0xffffffffu, v.mn, o);
-            r.mx = __shfl_down_sync(0xffffffffu, v.mx, o);
-            if ((lane & (2 * o - 1)) == 0) v = tri_cat(v, r);
+            Tri2 r;
+#pragma unroll
+            for (int p = 0; p < 2; p++) {
+                r.p[p].sum = __shfl_down_sync(0xffffffffu, v.p[p].sum, o);
+                r.p[p].mn = __shfl_down_sync(0xffffffffu, v.p[p].mn, o);
+                r.p[p].mx = __shfl_down_sync(0xffffffffu, v.p[p].mx, o);
+            }
+            if ((lane & (2 * o - 1)) == 0) v = tri2_cat(v, r);
         }
         if (lane == 0) s_tri[warp][c] = v;
     }
     __syncthreads();
     if (threadIdx.x < C) {
-        Tri v = s_tri[0][threadIdx.x];
-        for (int w = 1; w < OB_THREADS / 32; w++) v = tri_cat(v, s_tri[w][threadIdx.x]);
-        out[threadIdx.x].sum = v.sum;
-        out[threadIdx.x].mn = v.mn;
-        out[threadIdx.x].mx = v.mx;
+        Tri2 v = s_tri[0][threadIdx.x];
+        for (int w = 1; w < OB_THREADS / 32; w++) v = tri2_cat(v, s_tri[w][threadIdx.x]);
+        out[threadIdx.x].t = v;
         out[threadIdx.x].flag = s_flag[threadIdx.x];
     }
 }
@@ -280,27 +313,52 @@ __device__ __forceinline__ long long warp_incl_scan(long long v, int lane) {
     return v;
 }
 
-// Applies blocks / sub-chunks [next, limit) held one per lane as (ok, d, lo, hi) to the state s as far
-// as they validate.  Returns the first index that does not (limit if all do) and updates s.
+// Applies the items [next, limit) held one per lane (each a Tri2, usable iff ok) to the state s as
+// far as they validate.  Returns the first index that does not (limit if all do) and updates s.
+// The parity each item starts from depends on the items before it, so the warp scans the Tri2
+// monoid itself (in order); item l then checks its own min / max against the exact state it would
+// start from if everything before it is accepted.
 __device__ __forceinline__ uint32_t apply_run(double &s, int lane, uint32_t next, uint32_t limit, bool ok,
-                                             long long d, long long lo, long long hi) {
+                                             const Tri2 &item) {
     const long long bits = __double_as_longlong(s);
     const long long M = (bits & 0x000fffffffffffffLL) | TWO52; // |s| / q
     const bool negs = bits < 0;
+    const int p0 = (int)(M & 1LL);
     const bool mine = lane >= (int)next && lane < (int)limit;
-    const long long inc = (mine && ok) ? d : 0;
-    const long long incl = warp_incl_scan(inc, lane);
-    const long long pre = incl - inc;
-    // |s| / q after k elements of this item = cur +- prefix_k
-    const long long cur = negs ? M - pre : M + pre;
-    const long long vmin = negs ? cur - hi : cur + lo, vmax = negs ? cur - lo : cur + hi;
-    // strictly above 2^52: the unrounded value must itself stay inside the binade
+    // inclusive in-order scan of the concatenation; lanes outside [next, limit) and unusable items
+    // act as the empty run (anything behind the first unusable item is discarded anyway)
+    Tri2 inc;
+    if (mine && ok) inc = item;
+    else inc.p[0] = inc.p[1] = Tri{0.0, 1e300, -1e300};
+    Tri2 run = inc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        Tri2 up;
+#pragma unroll
+        for (int p = 0; p < 2; p++) {
+            up.p[p].sum = __shfl_up_sync(0xffffffffu, run.p[p].sum, o);
+            up.p[p].mn = __shfl_up_sync(0xffffffffu, run.p[p].mn, o);
+            up.p[p].mx = __shfl_up_sync(0xffffffffu, run.p[p].mx, o);
+        }
+        if (lane >= o) run = tri2_cat(up, run);
+    }
+    // run.p[p0] = items next..lane applied to a state of parity p0: prefix extremes included
+    const long long tot = (long long)run.p[p0].sum;
+    const double rmn = run.p[p0].mn, rmx = run.p[p0].mx;
+    long long vmin, vmax;
+    {
+        const long long lo = rmn > 9e299 ? 0 : (long long)rmn, hi = rmx < -9e299 ? 0 : (long long)rmx;
+        vmin = negs ? M - hi : M + lo;
+        vmax = negs ? M - lo : M + hi;
+    }
+    // every prefix up to and including this item strictly inside (2^52, 2^53): the unrounded value
+    // must itself stay inside the binade
     const bool valid = ok && vmin > TWO52 && vmax < TWO53;
     const unsigned fails = __ballot_sync(0xffffffffu, mine && !valid);
     const uint32_t f = fails ? (uint32_t)(__ffs(fails) - 1) : limit;
     if (f > next) {
-        const long long tot = __shfl_sync(0xffffffffu, f < limit ? pre : incl, f < limit ? (int)f : (int)limit - 1);
-        const long long M2 = negs ? M - tot : M + tot;
+        const long long acc = __shfl_sync(0xffffffffu, tot, (int)f - 1); // inclusive total of lane f - 1
+        const long long M2 = negs ? M - acc : M + acc;
         s = __longlong_as_double((bits & 0xfff0000000000000LL) | (M2 & 0x000fffffffffffffLL));
     }
     return f;
@@ -321,27 +379,21 @@ __device__ __forceinline__ double replay_block(const PbPlanes &P, size_t first, 
     }
     const uint32_t nl = (cnt + SUB - 1) / SUB; // lanes that hold elements
     uint32_t next = 0;
+    unsigned int rounds = 0, elementwise = 0;
     while (next < nl) {
+        rounds++;
         const long long bits = __double_as_longlong(s);
         const int ef = (int)((bits >> 52) & 0x7ff);
         uint32_t f = next;
         if (ef > 24 && ef < 2000) { // a normal, finite state: quantise against its exact binade
             const double scale = scalbn(1.0, 52 - (ef - 1023));
-            Tri tri{0.0, 0.0, 0.0};
+            Tri2 tri;
+            tri.p[0] = tri.p[1] = Tri{0.0, 0.0, 0.0};
             int flag = 0;
 #pragma unroll
-            for (int k = 0; k < SUB; k++) {
-                if (k < my) {
-                    const double u = __dmul_rn(t[k], scale);
-                    const double d = __dsub_rn(__dadd_rn(u, MAGIC), MAGIC);
-                    flag |= !(fabs(u) < TWO51) | (fabs(__dsub_rn(u, d)) == 0.5);
-                    const double ps = tri.sum + d;
-                    tri.mn = k == 0 ? ps : fmin(tri.mn, ps);
-                    tri.mx = k == 0 ? ps : fmax(tri.mx, ps);
-                    tri.sum = ps;
-                }
-            }
-            f = apply_run(s, lane, next, nl, !flag && my > 0, (long long)tri.sum, (long long)tri.mn, (long long)tri.mx);
+            for (int k = 0; k < SUB; k++)
+                if (k < my) tri2_push(tri, __dmul_rn(t[k], scale), flag, k == 0);
+            f = apply_run(s, lane, next, nl, !flag && my > 0, tri);
         }
         if (f < nl) { // sub-chunk f: element by element (binade change, tie, or a zero / subnormal state)
             double v = s;
@@ -352,9 +404,14 @@ __device__ __forceinline__ double replay_block(const PbPlanes &P, size_t first, 
             }
             s = __shfl_sync(0xffffffffu, v, (int)f);
             next = f + 1;
+            elementwise++;
         } else {
             next = nl;
         }
+    }
+    if (lane == 0) {
+        atomicAdd(&g_ord_counts[5], (unsigned long long)rounds);
+        atomicAdd(&g_ord_counts[6], (unsigned long long)elementwise);
     }
     return s;
 }
@@ -374,19 +431,30 @@ __global__ void __launch_bounds__(32 * NChains<KIND>::C) k_ord_resolve(PbPlanes 
     double m0 = 0, m1 = 0, m2 = 0;
     if (KIND == KIND_CENTERED) { m0 = stats[seg].mean[0]; m1 = stats[seg].mean[1]; m2 = stats[seg].mean[2]; }
     double s = 0.0; // exact running sum of this warp's chain
-    unsigned int n_acc = 0, n_rep = 0;
+    unsigned int n_acc = 0, n_rep = 0, n_why[3] = {0, 0, 0};
     const OrdSummary *srow = sum + (size_t)sg.bbase * C + chain;
     for (uint32_t g0 = 0; g0 < nblk; g0 += 32) {
         const uint32_t gcnt = min(32u, nblk - g0);
-        OrdSummary sm{0.0, 0.0, 0.0, E_NOGUESS, 1};
+        OrdSummary sm;
+        sm.t.p[0] = sm.t.p[1] = Tri{0.0, 0.0, 0.0};
+        sm.e = E_NOGUESS;
+        sm.flag = 1;
         if (use_summaries && lane < (int)gcnt) sm = srow[(size_t)(g0 + lane) * C];
         uint32_t next = 0;
         while (next < gcnt) {
             const long long bits = __double_as_longlong(s);
             const int es = (int)((bits >> 52) & 0x7ff) - 1023;
             const bool ok = use_summaries && sm.flag == 0 && sm.e == es && es > -1000 && es < 1000;
-            const uint32_t f = apply_run(s, lane, next, gcnt, ok, (long long)sm.sum, (long long)sm.mn, (long long)sm.mx);
+            const uint32_t f = apply_run(s, lane, next, gcnt, ok, sm.t);
             n_acc += f - next;
+            if (f < gcnt && use_summaries) {
+                const int fl = __shfl_sync(0xffffffffu, sm.flag, (int)f), fe = __shfl_sync(0xffffffffu, sm.e, (int)f);
+                if (lane == 0) {
+                    if (fl) n_why[0]++;
+                    else if (fe != es) n_why[1]++;
+                    else n_why[2]++;
+                }
+            }
             if (f < gcnt) {
                 const uint32_t base = (g0 + f) * OB;
                 s = replay_block<KIND, W>(P, (size_t)sg.lo + base, min((uint32_t)OB, n - base), chain, m0, m1, m2, s, lane);
@@ -402,6 +470,7 @@ __global__ void __launch_bounds__(32 * NChains<KIND>::C) k_ord_resolve(PbPlanes 
         if (use_summaries) {
             atomicAdd(&g_ord_counts[0], (unsigned long long)n_acc);
             atomicAdd(&g_ord_counts[1], (unsigned long long)n_rep);
+            for (int r = 0; r < 3; r++) atomicAdd(&g_ord_counts[2 + r], (unsigned long long)n_why[r]);
         }
     }
     __syncthreads();
@@ -446,10 +515,10 @@ void launch_pass(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t
 
 } // namespace
 
-void pb_ordered_counts(unsigned long long out[2], bool reset) {
-    PB_CUDA_OK(cudaMemcpyFromSymbol(out, g_ord_counts, sizeof(unsigned long long) * 2));
+void pb_ordered_counts(unsigned long long out[8], bool reset) {
+    PB_CUDA_OK(cudaMemcpyFromSymbol(out, g_ord_counts, sizeof(unsigned long long) * 8));
     if (reset) {
-        unsigned long long z[2] = {0, 0};
+        unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         PB_CUDA_OK(cudaMemcpyToSymbol(g_ord_counts, z, sizeof z));
     }
 }
