@@ -103,6 +103,9 @@ PB200_API int patolette_b200_dither(const double *planar, size_t width, size_t h
 PB200_API void patolette_b200_device(size_t width, size_t height, const double *d_data, const double *d_weights,
                                      size_t palette_size, const patolette__QuantizationOptions *options,
                                      double *palette, size_t *d_palette_map, int *exit_code);
+/* Working buffers (~100 B per pixel) are cached between calls; this returns them to the driver
+ * (and reports how many bytes were held). */
+PB200_API size_t patolette_b200_release_cache(void);
 /* Run subsequent calls on the caller's CUDA stream (a cudaStream_t passed as void*; enable = 0
  * restores the library's private stream).  Lets a harness bracket calls with its own events. */
 PB200_API int patolette_b200_set_stream(void *cuda_stream, int enable);

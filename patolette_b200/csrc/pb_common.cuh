@@ -12,20 +12,7 @@
 #define PB_BUCKETS 512 /* reference: quantize/global.c:22, quantize/local.c:15 */
 #define PB_DELTA 1e-16 /* reference: math/misc.h:5 */
 
-#define PB_CUDA_OK(expr)                                                                    \
-    do {                                                                                    \
-        cudaError_t _e = (expr);                                                            \
-        if (_e != cudaSuccess) {                                                            \
-            fprintf(stderr, "patolette_b200: CUDA error %s at %s:%d: %s\n",               \
-                    cudaGetErrorName(_e), __FILE__, __LINE__, cudaGetErrorString(_e));      \
-            throw pb_cuda_error(_e);                                                        \
-        }                                                                                   \
-    } while (0)
-
-struct pb_cuda_error {
-    cudaError_t code;
-    explicit pb_cuda_error(cudaError_t c) : code(c) {}
-};
+#include "pb_error.h"
 
 // A cluster = a contiguous range of the permuted pixel arrays (ascending original
 // pixel index inside the range, which is the order every reference sum runs in).

@@ -25,6 +25,7 @@
 #include "pb_kernels.h"
 #include "pb_prof.h"
 #include "pb_pipeline.h"
+#include "pb_pool.h"
 
 namespace {
 
@@ -200,16 +201,16 @@ void pb_dither_riemersma(const double *const planes[3], size_t width, size_t hei
     double *d_h[3] = {nullptr, nullptr, nullptr}, *d_pal = nullptr, *d_palw = nullptr, *d_qw = nullptr;
     uint32_t *d_rank = nullptr, *d_hidx = nullptr;
     auto cleanup = [&]() {
-        for (int j = 0; j < 3; j++) cudaFree(d_h[j]);
-        cudaFree(d_pal); cudaFree(d_palw); cudaFree(d_qw); cudaFree(d_rank); cudaFree(d_hidx);
+        for (int j = 0; j < 3; j++) pb_pool_free(d_h[j]);
+        pb_pool_free(d_pal); pb_pool_free(d_palw); pb_pool_free(d_qw); pb_pool_free(d_rank); pb_pool_free(d_hidx);
     };
     try {
-        for (int j = 0; j < 3; j++) PB_CUDA_OK(cudaMalloc(&d_h[j], n * sizeof(double)));
-        PB_CUDA_OK(cudaMalloc(&d_pal, pal_rm.size() * sizeof(double)));
-        PB_CUDA_OK(cudaMalloc(&d_palw, pal_rm.size() * sizeof(double)));
-        PB_CUDA_OK(cudaMalloc(&d_qw, sizeof qw));
-        PB_CUDA_OK(cudaMalloc(&d_rank, n * sizeof(uint32_t)));
-        PB_CUDA_OK(cudaMalloc(&d_hidx, (n + DT_TILE) * sizeof(uint32_t)));
+        for (int j = 0; j < 3; j++) d_h[j] = (double *)pb_pool_alloc(n * sizeof(double));
+        d_pal = (double *)pb_pool_alloc(pal_rm.size() * sizeof(double));
+        d_palw = (double *)pb_pool_alloc(pal_rm.size() * sizeof(double));
+        d_qw = (double *)pb_pool_alloc(sizeof qw);
+        d_rank = (uint32_t *)pb_pool_alloc(n * sizeof(uint32_t));
+        d_hidx = (uint32_t *)pb_pool_alloc((n + DT_TILE) * sizeof(uint32_t));
         PB_CUDA_OK(cudaMemcpyAsync(d_pal, pal_rm.data(), pal_rm.size() * sizeof(double), cudaMemcpyHostToDevice, st));
         PB_CUDA_OK(cudaMemcpyAsync(d_palw, palw.data(), palw.size() * sizeof(double), cudaMemcpyHostToDevice, st));
         PB_CUDA_OK(cudaMemcpyAsync(d_qw, qw, sizeof qw, cudaMemcpyHostToDevice, st));

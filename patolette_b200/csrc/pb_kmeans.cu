@@ -27,6 +27,7 @@
 #include "pb_kernels.h"
 #include "pb_prof.h"
 #include "pb_pipeline.h"
+#include "pb_pool.h"
 
 namespace {
 
@@ -182,13 +183,12 @@ struct DevMem {
     std::vector<void *> ptrs;
     template <typename T>
     T *alloc(size_t count) {
-        void *p = nullptr;
-        PB_CUDA_OK(cudaMalloc(&p, (count ? count : 1) * sizeof(T)));
+        void *p = pb_pool_alloc((count ? count : 1) * sizeof(T));
         ptrs.push_back(p);
         return (T *)p;
     }
     ~DevMem() {
-        for (void *p : ptrs) cudaFree(p);
+        for (void *p : ptrs) pb_pool_free(p);
     }
 };
 

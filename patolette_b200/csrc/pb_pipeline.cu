@@ -20,6 +20,7 @@
 #include "pb_host.h"
 #include "pb_kernels.h"
 #include "pb_pipeline.h"
+#include "pb_pool.h"
 #include "pb_prof.h"
 
 namespace {
@@ -36,10 +37,10 @@ struct DevArr {
     void alloc(size_t count) {
         release();
         n = count;
-        if (count) PB_CUDA_OK(cudaMalloc(&p, count * sizeof(T)));
+        if (count) p = (T *)pb_pool_alloc(count * sizeof(T));
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p) pb_pool_free(p);
         p = nullptr;
         n = 0;
     }
@@ -706,6 +707,12 @@ int patolette_b200_ordered_counts(unsigned long long *out2, int reset) {
         pb_ordered_counts(out2, reset != 0);
         return 0;
     } catch (const pb_cuda_error &e) { return -(int)e.code; }
+}
+
+size_t patolette_b200_release_cache(void) {
+    const size_t held = pb_pool_cached_bytes();
+    pb_pool_release_all();
+    return held;
 }
 
 int patolette_b200_set_stream(void *cuda_stream, int enable) {
