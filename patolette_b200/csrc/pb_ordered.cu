@@ -380,7 +380,24 @@ __device__ __forceinline__ double replay_block(const PbPlanes &P, size_t first, 
     const uint32_t nl = (cnt + SUB - 1) / SUB; // lanes that hold elements
     uint32_t next = 0;
     unsigned int rounds = 0, elementwise = 0;
+    int poor = 0; // consecutive rounds that accepted fewer than two sub-chunks
     while (next < nl) {
+        if (poor >= 2) {
+            // The sum is hovering (state small against the terms: the binade changes every few
+            // elements, nothing validates).  A speculation round costs ~10x a 16-element chain, so
+            // finish the block as the plain sequential loop, lane after lane.
+            for (uint32_t l = next; l < nl; l++) {
+                double v = s;
+                if (lane == (int)l) {
+#pragma unroll
+                    for (int k = 0; k < SUB; k++)
+                        if (k < my) v = __dadd_rn(v, t[k]);
+                }
+                s = __shfl_sync(0xffffffffu, v, (int)l);
+            }
+            elementwise += nl - next;
+            break;
+        }
         rounds++;
         const long long bits = __double_as_longlong(s);
         const int ef = (int)((bits >> 52) & 0x7ff);
@@ -403,6 +420,7 @@ __device__ __forceinline__ double replay_block(const PbPlanes &P, size_t first, 
                     if (k < my) v = __dadd_rn(v, t[k]);
             }
             s = __shfl_sync(0xffffffffu, v, (int)f);
+            poor = (f - next < 2) ? poor + 1 : 0;
             next = f + 1;
             elementwise++;
         } else {
