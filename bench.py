@@ -180,7 +180,8 @@ def run_ours(args):
     # ---------------- device-resident arm (value) ----------------
     d_in = torch.from_numpy(planar.T.copy()).cuda()                 # 3 x N planes, contiguous
     d_map = torch.empty(n, dtype=torch.int64, device="cuda")
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()  # a non-blocking stream: the legacy NULL stream serialises against everything
+    torch.cuda.set_stream(stream)
     lib.patolette_b200_set_stream(C.c_void_p(stream.cuda_stream), 1)
 
     def step_resident():

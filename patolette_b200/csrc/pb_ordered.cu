@@ -366,7 +366,7 @@ __device__ __forceinline__ uint32_t apply_run(double &s, int lane, uint32_t next
 
 template <int KIND, bool W>
 __device__ __forceinline__ double replay_block(const PbPlanes &P, size_t first, uint32_t cnt, int chain, double m0,
-                                               double m1, double m2, double s, int lane) {
+                                               double m1, double m2, double s, int lane, int &hover) {
     double t[SUB];
     const int my = max(0, min(SUB, (int)cnt - lane * SUB));
 #pragma unroll
@@ -380,7 +380,10 @@ __device__ __forceinline__ double replay_block(const PbPlanes &P, size_t first, 
     const uint32_t nl = (cnt + SUB - 1) / SUB; // lanes that hold elements
     uint32_t next = 0;
     unsigned int rounds = 0, elementwise = 0;
-    int poor = 0; // consecutive rounds that accepted fewer than two sub-chunks
+    // hover > 0: the previous replays of this chain ended in the sequential tail - the sum is
+    // hovering near zero - so skip the speculation rounds, re-trying them every fourth replay
+    int poor = (hover > 0 && (hover & 3) != 0) ? 2 : 0; // consecutive rounds that accepted < 2 sub-chunks
+    bool tail = false;
     while (next < nl) {
         if (poor >= 2) {
             // The sum is hovering (state small against the terms: the binade changes every few
@@ -396,6 +399,7 @@ __device__ __forceinline__ double replay_block(const PbPlanes &P, size_t first, 
                 s = __shfl_sync(0xffffffffu, v, (int)l);
             }
             elementwise += nl - next;
+            tail = true;
             break;
         }
         rounds++;
@@ -427,6 +431,7 @@ __device__ __forceinline__ double replay_block(const PbPlanes &P, size_t first, 
             next = nl;
         }
     }
+    hover = tail ? hover + 1 : 0;
     if (lane == 0) {
         atomicAdd(&g_ord_counts[5], (unsigned long long)rounds);
         atomicAdd(&g_ord_counts[6], (unsigned long long)elementwise);
@@ -450,6 +455,7 @@ __global__ void __launch_bounds__(32 * NChains<KIND>::C) k_ord_resolve(PbPlanes 
     if (KIND == KIND_CENTERED) { m0 = stats[seg].mean[0]; m1 = stats[seg].mean[1]; m2 = stats[seg].mean[2]; }
     double s = 0.0; // exact running sum of this warp's chain
     unsigned int n_acc = 0, n_rep = 0, n_why[3] = {0, 0, 0};
+    int hover = 0;
     const OrdSummary *srow = sum + (size_t)sg.bbase * C + chain;
     for (uint32_t g0 = 0; g0 < nblk; g0 += 32) {
         const uint32_t gcnt = min(32u, nblk - g0);
@@ -475,7 +481,7 @@ __global__ void __launch_bounds__(32 * NChains<KIND>::C) k_ord_resolve(PbPlanes 
             }
             if (f < gcnt) {
                 const uint32_t base = (g0 + f) * OB;
-                s = replay_block<KIND, W>(P, (size_t)sg.lo + base, min((uint32_t)OB, n - base), chain, m0, m1, m2, s, lane);
+                s = replay_block<KIND, W>(P, (size_t)sg.lo + base, min((uint32_t)OB, n - base), chain, m0, m1, m2, s, lane, hover);
                 n_rep++;
                 next = f + 1;
             } else {

@@ -225,7 +225,7 @@ struct Quantizer {
     DevArr<char> oscratch; // block sums + summaries of the speculative ordered sums
     PbPlanes orig{}, bufs[2]{};
 
-    static constexpr int MAXB = 16; // clusters evaluated per batch (their 2 * MAXB children get stats)
+    static constexpr int MAXB = 32; // clusters evaluated per batch (their 2 * MAXB children get stats)
     size_t max_blocks = 0;         // capacity of the packed ordered-sum block table
 
     void init(size_t n, bool with_weights) {
