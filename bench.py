@@ -95,6 +95,21 @@ def measured_peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def reduce_max_ms(ms: float, dist, device="cuda") -> float:
+    """Step time of the job = the slowest rank's (contract: max over ranks, measured on the device)."""
+    if dist is None:
+        return ms
+    import torch
+    t = torch.tensor([ms], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def aggregate_throughput(n_pixels: int, world: int, ms_per_step: float) -> float:
+    """Whole-job Mpixels/s: every rank processes its own n_pixels image per step (replicas, weak scaling)."""
+    return world * n_pixels / (ms_per_step * 1e-3) / 1e6
+
+
 def host_cores() -> int:
     try:
         return len(os.sched_getaffinity(0))
@@ -204,10 +219,7 @@ def run_ours(args):
     ms_total = e0.elapsed_time(e1)
     clocks = sampler.stop()
     launches = int(pb.last_timings()["launches"])
-    t = torch.tensor([ms_total], device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = float(t.item()) / args.steps
+    ms_step = reduce_max_ms(ms_total, dist) / args.steps
     stage = pb.last_timings()
 
     # ---------------- end-to-end arm: host buffers through the reference ABI ----------------
@@ -228,10 +240,7 @@ def run_ours(args):
         step_e2e()
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / args.steps
-    te = torch.tensor([e2e_s], device="cuda")
-    if dist is not None:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_s = float(te.item())
+    e2e_s = reduce_max_ms(e2e_s * 1e3, dist) / 1e3
     e2e_stage = pb.last_timings()
     assert (h_map.numpy() == d_map.cpu().numpy()).all(), "host and device arms disagree"
 
@@ -271,7 +280,7 @@ def run_ours(args):
         cpu_baseline, _ = time_reference(1536, 1, 0)
     line = {
         "metric": "Mpixels/s end-to-end quantize() at K=256",
-        "value": world * n / (ms_step * 1e-3) / 1e6, "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps,
+        "value": aggregate_throughput(n, world, ms_step), "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD["name"] if not args.side else f"{side}x{side} debug size", "K": K,

@@ -244,3 +244,32 @@ def test_config2_scale_properties(cuda_lib):
     chosen = d[np.arange(idx.size), pmap[idx]]
     # the returned palette went ICtCp -> sRGB -> ICtCp, so allow the round-trip's rounding in the comparison
     assert (chosen <= best * (1 + 1e-9) + 1e-18).all()
+
+
+def test_dither_kmeans_1024_matches_oracle(cuda_lib, oracle):
+    """1024 x 1024, K=256, CIELuv, KMeans 3 iterations on the default subsample, Riemersma dither:
+    every stage of BASELINE config 3 at a size the CPU oracle finishes in seconds - bit-exact."""
+    W = H = 1024; K = 256
+    colors = image_like_colors(W, H, 31)
+    kw = dict(dither=True, color_space=1, kmeans_niter=3)
+    code, pal, pmap = cuda_quantize(cuda_lib, W, H, colors, K, **kw)
+    ocode, opal, omap = oracle.quantize(W, H, colors, K, **kw)
+    assert code == ocode == 0
+    assert_same_floats(pal, opal, "palette")
+    assert np.array_equal(pmap, omap), f"{int((pmap != omap).sum())} dithered indices differ"
+
+
+def test_config3_scale_8192_properties(cuda_lib):
+    """8192 x 8192 (BASELINE config 3/4 pixel count class), K=256, ICtCp, dither off: the pipeline runs at
+    67 M pixels (u32 positions, packed scratch tables, speculative batches), is deterministic, uses all K
+    entries, and agrees with itself when the image is fed as weights == 1 (the weighted code path must give
+    the same partition as the unweighted one: w*c == c, sum of ones == n)."""
+    W = H = 8192; K = 256
+    colors = uniform_colors(W, H, 3)
+    code, pal, pmap = cuda_quantize(cuda_lib, W, H, colors, K, dither=False, color_space=2, kmeans_niter=0)
+    assert code == 0 and len(np.unique(pmap)) == K
+    ones = np.ones(W * H)
+    code2, pal2, pmap2 = cuda_quantize(cuda_lib, W, H, colors, K, weights=ones, dither=False, color_space=2, kmeans_niter=0)
+    assert code2 == 0
+    assert np.array_equal(pmap, pmap2)
+    assert np.array_equal(bits(pal), bits(pal2))
