@@ -91,83 +91,167 @@ __global__ void k_unpermute(const uint32_t *__restrict__ rank, const uint32_t *_
         map[p] = hidx[rank[p]];
 }
 
-constexpr int DT_TILE = 128; // pixels staged per tile
+// ---- the recurrence ------------------------------------------------------------------------------
+// State of a chain = the 16-entry error queue; entry s is P_s - palette[idx_s], so the state after
+// pixel t is a function of the last 16 CHOICES only.  Two runs over the same pixels that make the
+// same 16 consecutive choices are in bit-identical states from then on.  That finite memory is what
+// lets the walk be cut into segments:
+//   k_riemersma_spec   : segment g is run by its own warp from an EMPTY queue, starting DT_WARM
+//                        pixels early; by the time it reaches its segment the warm-up has (almost
+//                        always) locked onto the true trajectory.  It also records its choices for
+//                        the 16 pixels just before the segment.
+//   k_riemersma_repair : one warp walks the segment boundaries in order.  If segment g's 16 recorded
+//                        warm-up choices equal what segment g-1 produced there, g started in the
+//                        true state - nothing to do.  Otherwise the true chain is continued from
+//                        the boundary, overwriting choices, until 16 consecutive choices agree with
+//                        the speculative ones again (measured: ~150 pixels on average).
+// Correct for ANY data - the speculation only buys parallelism; with no agreement at all the repair
+// kernel degenerates into the plain sequential walk.
+constexpr int DT_WARPS = 8;
 
-// One warp.  pal: K x 3 row-major (linear Rec2020); palw: same scaled by the float weights.
-__global__ void __launch_bounds__(32) k_riemersma_chain(const double *__restrict__ h0, const double *__restrict__ h1,
-                                                        const double *__restrict__ h2, size_t n,
-                                                        const double *__restrict__ pal,
-                                                        const double *__restrict__ palw, int K,
-                                                        const double *__restrict__ qweights,
-                                                        uint32_t *__restrict__ hidx) {
+struct DitherLane {
+    double q[16];  // error queue of this lane's channel (lanes 0..2), oldest first
+    double w[16];  // queue weights (riemersma.c:360-373)
+    double cw;     // sqrt-luma weight of this lane's channel, double precision (riemersma.c:30-34)
+    int ch;
+};
+
+// One pixel: returns the chosen palette index (uniform across the warp) and updates the queue.
+__device__ __forceinline__ int dither_step(DitherLane &L, double P, const double *__restrict__ s_pal,
+                                           const double *__restrict__ s_palw, int K, int lane) {
+    // riemersma.c:292-297: error = sum_i queue[i] * weight[i], i ascending
+    double err = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) err = __dadd_rn(err, __dmul_rn(L.q[i], L.w[i]));
+    const double C = __dadd_rn(P, err);   // :310-312, no clamping
+    const double Cw = __dmul_rn(L.cw, C); // :315-317
+    const double x = __shfl_sync(0xffffffffu, Cw, 0), y = __shfl_sync(0xffffffffu, Cw, 1),
+                 z = __shfl_sync(0xffffffffu, Cw, 2);
+    double bd = 0.0;
+    int best = 0x7fffffff;
+    for (int j = lane; j < K; j += 32) {
+        const double dx = __dsub_rn(x, s_palw[3 * j]), dy = __dsub_rn(y, s_palw[3 * j + 1]),
+                     dz = __dsub_rn(z, s_palw[3 * j + 2]);
+        const double dd = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+        if (best == 0x7fffffff || dd < bd) { bd = dd; best = j; }
+    }
+    // exact warp argmin, lowest index on ties, via integer reductions: squared distances are
+    // non-negative doubles, whose bit patterns order like unsigned integers
+    {
+        const unsigned long long key = best == 0x7fffffff ? ~0ULL : (unsigned long long)__double_as_longlong(bd);
+        const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+        const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+        const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
+        const bool win = hi == mhi && lo == mlo;
+        best = (int)__reduce_min_sync(0xffffffffu, win ? (unsigned)best : 0x7fffffffu);
+    }
+    // :332-340: shift the queue, append P - palette[best]
+#pragma unroll
+    for (int i = 0; i < 15; i++) L.q[i] = L.q[i + 1];
+    L.q[15] = __dsub_rn(P, s_pal[3 * best + L.ch]);
+    return best;
+}
+
+__device__ __forceinline__ void dither_lane_init(DitherLane &L, const double *__restrict__ qweights, int lane) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) { L.w[i] = qweights[i]; L.q[i] = 0.0; }
+    L.cw = lane == 0 ? 0.51254268114958 : (lane == 1 ? 0.8234075540095561 : 0.2435159132377184);
+    L.ch = lane < 3 ? lane : 0;
+}
+
+// Runs pixels [from, to) of the walk: 32 at a time, each lane fetches one pixel (coalesced) and the
+// values reach the channel lanes by shuffle; choices are collected one per lane and stored coalesced.
+// emit(pos, idx) decides where a choice goes.
+template <typename Emit>
+__device__ __forceinline__ void dither_run(DitherLane &L, const double *__restrict__ h0, const double *__restrict__ h1,
+                                           const double *__restrict__ h2, size_t from, size_t to,
+                                           const double *__restrict__ s_pal, const double *__restrict__ s_palw, int K,
+                                           int lane, Emit emit) {
+    for (size_t base = from; base < to; base += 32) {
+        const size_t i = base + lane;
+        double a = 0, b = 0, c = 0;
+        if (i < to) { a = h0[i]; b = h1[i]; c = h2[i]; }
+        const int cnt = (int)min((size_t)32, to - base);
+        int mine = 0;
+        for (int e = 0; e < cnt; e++) {
+            const double pa = __shfl_sync(0xffffffffu, a, e), pb = __shfl_sync(0xffffffffu, b, e),
+                         pc = __shfl_sync(0xffffffffu, c, e);
+            const double P = L.ch == 0 ? pa : (L.ch == 1 ? pb : pc);
+            const int best = dither_step(L, P, s_pal, s_palw, K, lane);
+            if (lane == e) mine = best;
+        }
+        if (lane < cnt) emit(i, mine);
+    }
+}
+
+__global__ void __launch_bounds__(DT_WARPS * 32) k_riemersma_spec(const double *__restrict__ h0, const double *__restrict__ h1,
+                                                                 const double *__restrict__ h2, size_t n, size_t seg,
+                                                                 size_t warm, const double *__restrict__ pal,
+                                                                 const double *__restrict__ palw, int K,
+                                                                 const double *__restrict__ qweights,
+                                                                 uint32_t *__restrict__ hidx, uint32_t *__restrict__ overlap) {
     extern __shared__ double s_mem[];
-    double *s_pal = s_mem;                 // K * 3
-    double *s_palw = s_mem + (size_t)K * 3; // K * 3
-    double *s_px = s_palw + (size_t)K * 3;  // 2 * 3 * DT_TILE
+    double *s_pal = s_mem, *s_palw = s_mem + (size_t)K * 3;
+    for (int i = threadIdx.x; i < K * 3; i += blockDim.x) { s_pal[i] = pal[i]; s_palw[i] = palw[i]; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const size_t g = (size_t)blockIdx.x * DT_WARPS + (threadIdx.x >> 5);
+    const size_t a = g * seg;
+    if (a >= n) return;
+    const size_t end = min(n, a + seg), start = a > warm ? a - warm : 0;
+    DitherLane L;
+    dither_lane_init(L, qweights, lane);
+    uint32_t *ov = overlap + g * 16;
+    dither_run(L, h0, h1, h2, start, end, s_pal, s_palw, K, lane, [&](size_t pos, int idx) {
+        if (pos >= a) hidx[pos] = (uint32_t)idx;
+        else if (pos + 16 >= a) ov[pos + 16 - a] = (uint32_t)idx;
+    });
+}
+
+__global__ void __launch_bounds__(32) k_riemersma_repair(const double *__restrict__ h0, const double *__restrict__ h1,
+                                                         const double *__restrict__ h2, size_t n, size_t seg,
+                                                         const double *__restrict__ pal, const double *__restrict__ palw,
+                                                         int K, const double *__restrict__ qweights,
+                                                         uint32_t *__restrict__ hidx, const uint32_t *__restrict__ overlap,
+                                                         unsigned long long *__restrict__ stats) {
+    extern __shared__ double s_mem[];
+    double *s_pal = s_mem, *s_palw = s_mem + (size_t)K * 3;
     const int lane = threadIdx.x;
     for (int i = lane; i < K * 3; i += 32) { s_pal[i] = pal[i]; s_palw[i] = palw[i]; }
-    double w[16];
-#pragma unroll
-    for (int i = 0; i < 16; i++) w[i] = qweights[i];
-    // riemersma.c:30-34 (double weights on the query side)
-    const double cw = lane == 0 ? 0.51254268114958 : (lane == 1 ? 0.8234075540095561 : 0.2435159132377184);
-    double q[16]; // error queue of this lane's channel (lanes 0..2), oldest first
-#pragma unroll
-    for (int i = 0; i < 16; i++) q[i] = 0.0;
-
-    const size_t ntiles = (n + DT_TILE - 1) / DT_TILE;
-    auto stage = [&](size_t t, int buf) {
-        const size_t base = t * DT_TILE;
-        for (int e = lane; e < DT_TILE; e += 32) {
-            const size_t i = base + e;
-            double a = 0, b = 0, c = 0;
-            if (i < n) { a = h0[i]; b = h1[i]; c = h2[i]; }
-            s_px[(buf * 3 + 0) * DT_TILE + e] = a;
-            s_px[(buf * 3 + 1) * DT_TILE + e] = b;
-            s_px[(buf * 3 + 2) * DT_TILE + e] = c;
-        }
-    };
-    if (ntiles) stage(0, 0);
     __syncwarp();
-    for (size_t t = 0; t < ntiles; t++) {
-        const int cur = (int)(t & 1);
-        if (t + 1 < ntiles) stage(t + 1, cur ^ 1); // loads overlap the chain below
-        const int cnt = (int)min((size_t)DT_TILE, n - t * DT_TILE);
-        const int ch = lane < 3 ? lane : 0;
-        for (int e = 0; e < cnt; e++) {
-            // riemersma.c:292-297: error = sum_i queue[i] * weight[i], i ascending
-            double err = 0.0;
+    const size_t nseg = (n + seg - 1) / seg;
+    DitherLane L;
+    dither_lane_init(L, qweights, lane);
+    const double *hp = L.ch == 0 ? h0 : (L.ch == 1 ? h1 : h2);
+    unsigned long long repaired_segments = 0, repaired_pixels = 0;
+    size_t g = 1;
+    while (g < nseg) {
+        const size_t a = g * seg;
+        const bool differ = lane < 16 && overlap[g * 16 + lane] != hidx[a - 16 + lane];
+        if (!__any_sync(0xffffffffu, differ)) { g++; continue; }
+        repaired_segments++;
+        // true state at a: queue entry i is P - palette[choice] of pixel a - 16 + i (riemersma.c:334-340)
 #pragma unroll
-            for (int i = 0; i < 16; i++) err = __dadd_rn(err, __dmul_rn(q[i], w[i]));
-            const double P = s_px[(cur * 3 + ch) * DT_TILE + e];
-            const double C = __dadd_rn(P, err);      // :310-312, no clamping
-            const double Cw = __dmul_rn(cw, C);      // :315-317
-            const double x = __shfl_sync(0xffffffffu, Cw, 0), y = __shfl_sync(0xffffffffu, Cw, 1),
-                         z = __shfl_sync(0xffffffffu, Cw, 2);
-            double bd = 0.0;
-            int best = 0x7fffffff;
-            for (int j = lane; j < K; j += 32) {
-                const double dx = __dsub_rn(x, s_palw[3 * j]), dy = __dsub_rn(y, s_palw[3 * j + 1]),
-                             dz = __dsub_rn(z, s_palw[3 * j + 2]);
-                const double dd = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-                if (best == 0x7fffffff || dd < bd) { bd = dd; best = j; }
-            }
-#pragma unroll
-            for (int o = 16; o; o >>= 1) {
-                const double od = __shfl_xor_sync(0xffffffffu, bd, o);
-                const int oj = __shfl_xor_sync(0xffffffffu, best, o);
-                // exact argmin, lowest index on ties; lanes with no candidate carry best = INT_MAX
-                const bool take = oj != 0x7fffffff && (best == 0x7fffffff || od < bd || (od == bd && oj < best));
-                if (take) { bd = od; best = oj; }
-            }
-            if (lane == 0) hidx[t * DT_TILE + e] = (uint32_t)best;
-            // :332-340: shift the queue, append P - palette[best]
-#pragma unroll
-            for (int i = 0; i < 15; i++) q[i] = q[i + 1];
-            q[15] = __dsub_rn(P, s_pal[3 * best + ch]);
+        for (int i = 0; i < 16; i++) L.q[i] = __dsub_rn(hp[a - 16 + i], s_pal[3 * hidx[a - 16 + i] + L.ch]);
+        // continue the true chain until it makes the same 16 consecutive choices as the speculative
+        // run that owns those pixels (agreements must not straddle a segment boundary: the stored
+        // choices on either side come from different speculative runs)
+        size_t pos = a;
+        int agree = 0;
+        while (pos < n && agree < 16) {
+            if (pos % seg == 0) agree = 0;
+            const double P = hp[pos];
+            const int best = dither_step(L, P, s_pal, s_palw, K, lane);
+            const uint32_t old = hidx[pos];
+            if ((uint32_t)best == old) agree++;
+            else { agree = 0; if (lane == 0) hidx[pos] = (uint32_t)best; }
+            __syncwarp();
+            pos++;
+            repaired_pixels++;
         }
-        __syncwarp();
+        g = (pos - 1) / seg + 1; // the segment holding the last repaired pixel is true through its end
     }
+    if (lane == 0 && stats) { stats[0] = repaired_segments; stats[1] = repaired_pixels; }
 }
 
 } // namespace
@@ -199,10 +283,11 @@ void pb_dither_riemersma(const double *const planes[3], size_t width, size_t hei
         palw[3 * j + 2] = pal_rm[3 * j + 2] * fz;
     }
     double *d_h[3] = {nullptr, nullptr, nullptr}, *d_pal = nullptr, *d_palw = nullptr, *d_qw = nullptr;
-    uint32_t *d_rank = nullptr, *d_hidx = nullptr;
+    uint32_t *d_rank = nullptr, *d_hidx = nullptr, *d_overlap = nullptr;
+    unsigned long long *d_stats = nullptr;
     auto cleanup = [&]() {
         for (int j = 0; j < 3; j++) pb_pool_free(d_h[j]);
-        pb_pool_free(d_pal); pb_pool_free(d_palw); pb_pool_free(d_qw); pb_pool_free(d_rank); pb_pool_free(d_hidx);
+        pb_pool_free(d_pal); pb_pool_free(d_palw); pb_pool_free(d_qw); pb_pool_free(d_rank); pb_pool_free(d_hidx); pb_pool_free(d_overlap); pb_pool_free(d_stats);
     };
     try {
         for (int j = 0; j < 3; j++) d_h[j] = (double *)pb_pool_alloc(n * sizeof(double));
@@ -210,7 +295,7 @@ void pb_dither_riemersma(const double *const planes[3], size_t width, size_t hei
         d_palw = (double *)pb_pool_alloc(pal_rm.size() * sizeof(double));
         d_qw = (double *)pb_pool_alloc(sizeof qw);
         d_rank = (uint32_t *)pb_pool_alloc(n * sizeof(uint32_t));
-        d_hidx = (uint32_t *)pb_pool_alloc((n + DT_TILE) * sizeof(uint32_t));
+        d_hidx = (uint32_t *)pb_pool_alloc((n + 64) * sizeof(uint32_t));
         PB_CUDA_OK(cudaMemcpyAsync(d_pal, pal_rm.data(), pal_rm.size() * sizeof(double), cudaMemcpyHostToDevice, st));
         PB_CUDA_OK(cudaMemcpyAsync(d_palw, palw.data(), palw.size() * sizeof(double), cudaMemcpyHostToDevice, st));
         PB_CUDA_OK(cudaMemcpyAsync(d_qw, qw, sizeof qw, cudaMemcpyHostToDevice, st));
@@ -222,11 +307,27 @@ void pb_dither_riemersma(const double *const planes[3], size_t width, size_t hei
         { PbProfScope _prof("k_permute", st);
         k_permute<<<grid, 256, 0, st>>>(planes[0], planes[1], planes[2], d_rank, n, d_h[0], d_h[1], d_h[2]);
         }
-        const size_t smem = ((size_t)K * 6 + 2 * 3 * DT_TILE) * sizeof(double);
-        if (smem > 48 * 1024)
-            PB_CUDA_OK(cudaFuncSetAttribute(k_riemersma_chain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        { PbProfScope _prof("k_riemersma_chain", st);
-        k_riemersma_chain<<<1, 32, smem, st>>>(d_h[0], d_h[1], d_h[2], n, d_pal, d_palw, K, d_qw, d_hidx);
+        // segment / warm-up lengths: enough segments to occupy the chip, warm-up long enough that
+        // almost every segment locks on before it starts (cold starts converge in ~150 pixels on
+        // average, ~1600 worst observed)
+        size_t seg = ((n / 2048 + 127) / 128) * 128;
+        seg = seg < 1024 ? 1024 : (seg > 8192 ? 8192 : seg);
+        const size_t warm = seg < 2048 ? seg : 2048;
+        const size_t nseg = (n + seg - 1) / seg;
+        d_overlap = (uint32_t *)pb_pool_alloc((nseg + 1) * 16 * sizeof(uint32_t));
+        d_stats = (unsigned long long *)pb_pool_alloc(2 * sizeof(unsigned long long));
+        const size_t smem = (size_t)K * 6 * sizeof(double);
+        if (smem > 48 * 1024) {
+            PB_CUDA_OK(cudaFuncSetAttribute(k_riemersma_spec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            PB_CUDA_OK(cudaFuncSetAttribute(k_riemersma_repair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
+        { PbProfScope _prof("k_riemersma_spec", st);
+        k_riemersma_spec<<<(unsigned)((nseg + DT_WARPS - 1) / DT_WARPS), DT_WARPS * 32, smem, st>>>(
+            d_h[0], d_h[1], d_h[2], n, seg, warm, d_pal, d_palw, K, d_qw, d_hidx, d_overlap);
+        }
+        { PbProfScope _prof("k_riemersma_repair", st);
+        k_riemersma_repair<<<1, 32, smem, st>>>(d_h[0], d_h[1], d_h[2], n, seg, d_pal, d_palw, K, d_qw, d_hidx,
+                                                d_overlap, d_stats);
         }
         { PbProfScope _prof("k_unpermute", st);
         k_unpermute<<<grid, 256, 0, st>>>(d_rank, d_hidx, n, d_map);

@@ -168,11 +168,13 @@ def test_kmeans_matches_oracle(cuda_lib, oracle, n, K, weighted, mppc):
     assert np.array_equal(ca.view(np.uint32), cb.view(np.uint32)), f"max diff {np.abs(ca - cb).max()}"
 
 
-@pytest.mark.parametrize("W,H,K", [(64, 64, 16), (100, 37, 40), (1, 7, 4), (130, 257, 256), (1, 1, 3)])
+@pytest.mark.parametrize("W,H,K", [(64, 64, 16), (100, 37, 40), (1, 7, 4), (130, 257, 256), (1, 1, 3), (700, 500, 8), (512, 384, 2)])
 def test_dither_matches_oracle(cuda_lib, oracle, W, H, K):
     n = W * H
     rng = np.random.default_rng(W * 1000 + H)
     planar = np.asfortranarray(rng.random((n, 3)))
+    if K == 2:  # flat image + two far colours: speculative segments lock on slowly, repairs must kick in
+        planar = np.asfortranarray(np.tile([[0.37, 0.52, 0.61]], (n, 1)) + 1e-3 * rng.random((n, 3)))
     pal = rng.random((K, 3))
     a = np.full(n, 7, dtype=np.uintp); b = np.full(n, 7, dtype=np.uintp)
     oracle.lib.orc_dither_riemersma(planar.ctypes.data_as(C.c_void_p), C.c_size_t(W), C.c_size_t(H), pal.ctypes.data_as(C.c_void_p), C.c_size_t(K), a.ctypes.data_as(C.c_void_p))
