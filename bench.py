@@ -251,7 +251,7 @@ def run_ours(args):
     lib.patolette_b200_profile_enable(1)
     step_resident()
     torch.cuda.synchronize()
-    buf = C.create_string_buffer(1 << 16)
+    buf = C.create_string_buffer(1 << 18)
     lib.patolette_b200_profile_json(buf, len(buf))
     lib.patolette_b200_profile_enable(0)
     lib.patolette_b200_set_stream(None, 0)
@@ -267,6 +267,7 @@ def run_ours(args):
                 "launches_per_step": top["launches"], "ms_per_step_in_kernel": top["ms"],
                 "algorithmic_bytes_per_step": top["bytes"],
                 "note": "ordered (bit-exact sequential) sums: latency-bound by design in round 1, see DESIGN.md",
+                "top_kernel_launch_ms": [round(x, 3) for x in top.get("each", [])],
                 "kernels": {k: {"ms": round(v["ms"], 3), "launches": v["launches"],
                                 "GB/s": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] > 0 and v["bytes"] else None}
                             for k, v in kernels[:12]}}

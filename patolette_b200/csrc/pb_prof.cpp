@@ -20,6 +20,7 @@ std::vector<Pending> g_pending;
 struct Acc {
     long launches = 0;
     double ms = 0, bytes = 0;
+    std::vector<float> each; // individual launch durations, in launch order
 };
 std::map<std::string, Acc> g_acc;
 } // namespace
@@ -71,6 +72,7 @@ std::string pb_prof_json() {
         acc.launches++;
         acc.ms += ms;
         acc.bytes += p.bytes;
+        acc.each.push_back(ms);
         cudaEventDestroy(p.a);
         cudaEventDestroy(p.b);
     }
@@ -82,7 +84,9 @@ std::string pb_prof_json() {
         if (!first) os << ", ";
         first = false;
         os << "\"" << kv.first << "\": {\"launches\": " << kv.second.launches << ", \"ms\": " << kv.second.ms
-           << ", \"bytes\": " << kv.second.bytes << "}";
+           << ", \"bytes\": " << kv.second.bytes << ", \"each\": [";
+        for (size_t i = 0; i < kv.second.each.size() && i < 64; i++) os << (i ? "," : "") << kv.second.each[i];
+        os << "]}";
     }
     os << "}";
     return os.str();
