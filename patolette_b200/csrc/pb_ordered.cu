@@ -222,10 +222,89 @@ __device__ __forceinline__ void tri2_push(Tri2 &t, double u, int &flag, bool fir
     }
 }
 
+// ---- S3a: the common case - no tie anywhere in the block: one parity-independent summary ----------
+constexpr int OS_THREADS = 64; // 8 consecutive elements per thread, two warps per block
+struct TriPlain { double sum, mn, mx; };
+__device__ __forceinline__ TriPlain trip_cat(const TriPlain &a, const TriPlain &b) {
+    return TriPlain{a.sum + b.sum, fmin(a.mn, a.sum + b.mn), fmax(a.mx, a.sum + b.mx)};
+}
+
 template <int KIND, bool W>
-__global__ void __launch_bounds__(OB_THREADS) k_ord_summary(PbPlanes b0, PbPlanes b1, const PbSeg *__restrict__ segs,
+__global__ void __launch_bounds__(OS_THREADS) k_ord_summary(PbPlanes b0, PbPlanes b1, const PbSeg *__restrict__ segs,
                                                             const PbStats *__restrict__ stats, uint32_t blk_cap,
                                                             OrdSummary *__restrict__ sum) {
+    constexpr int C = NChains<KIND>::C;
+    constexpr int PER = OB / OS_THREADS;
+    __shared__ TriPlain s_tri[OS_THREADS / 32][C];
+    __shared__ int s_flag[C];
+    const int seg = blockIdx.y;
+    const PbSeg sg = segs[seg];
+    const uint32_t base = blockIdx.x * OB;
+    if (base >= sg.n) return;
+    const PbPlanes &P = sg.buf ? b1 : b0;
+    OrdSummary *out = sum + ((size_t)sg.bbase + blockIdx.x) * C;
+    double m0 = 0, m1 = 0, m2 = 0;
+    if (KIND == KIND_CENTERED) { m0 = stats[seg].mean[0]; m1 = stats[seg].mean[1]; m2 = stats[seg].mean[2]; }
+    double scale[C];
+    TriPlain tri[C];
+    int flag[C]; // bit 0: unusable (no guess / unquantisable term), bit 1: a tie -> needs the tie-aware pass
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+        const int e = out[c].e;
+        flag[c] = e == E_NOGUESS;
+        scale[c] = flag[c] ? 0.0 : scalbn(1.0, 52 - e); // 1 / q
+        tri[c] = TriPlain{0.0, 1e300, -1e300};          // empty run
+    }
+    if (threadIdx.x < C) s_flag[threadIdx.x] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+        const uint32_t i = base + threadIdx.x * PER + k; // consecutive elements per thread
+        if (i < sg.n) {
+            const size_t p = (size_t)sg.lo + i;
+            double t[C];
+            terms_all<KIND, W>(W ? P.w[p] : 1.0, P.c[0][p], P.c[1][p], P.c[2][p], m0, m1, m2, t);
+#pragma unroll
+            for (int c = 0; c < C; c++) {
+                const double u = __dmul_rn(t[c], scale[c]);             // a / q, exact (power of two)
+                const double d = __dsub_rn(__dadd_rn(u, MAGIC), MAGIC); // rint(u)
+                flag[c] |= (!(fabs(u) < TWO51) ? 1 : 0) | (fabs(__dsub_rn(u, d)) == 0.5 ? 2 : 0);
+                const double ps = tri[c].sum + d;
+                tri[c] = TriPlain{ps, fmin(tri[c].mn, ps), fmax(tri[c].mx, ps)};
+            }
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+        if (flag[c]) atomicOr(&s_flag[c], flag[c]);
+        TriPlain v = tri[c];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { // in-order tree: lane i absorbs lane i + o
+            TriPlain r;
+            r.sum = __shfl_down_sync(0xffffffffu, v.sum, o);
+            r.mn = __shfl_down_sync(0xffffffffu, v.mn, o);
+            r.mx = __shfl_down_sync(0xffffffffu, v.mx, o);
+            if ((lane & (2 * o - 1)) == 0) v = trip_cat(v, r);
+        }
+        if (lane == 0) s_tri[warp][c] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < C) {
+        TriPlain v = s_tri[0][threadIdx.x];
+        for (int w = 1; w < OS_THREADS / 32; w++) v = trip_cat(v, s_tri[w][threadIdx.x]);
+        const Tri tt{v.sum, v.mn, v.mx};
+        out[threadIdx.x].t.p[0] = tt;
+        out[threadIdx.x].t.p[1] = tt;
+        out[threadIdx.x].flag = s_flag[threadIdx.x]; // 0 ok, odd: replay, 2: redo with k_ord_summary_tie
+    }
+}
+
+// ---- S3b: blocks that contain a tie: both start parities (the two-state transducer) --------------
+template <int KIND, bool W>
+__global__ void __launch_bounds__(OB_THREADS) k_ord_summary_tie(PbPlanes b0, PbPlanes b1, const PbSeg *__restrict__ segs,
+                                                                const PbStats *__restrict__ stats, uint32_t blk_cap,
+                                                                OrdSummary *__restrict__ sum) {
     constexpr int C = NChains<KIND>::C;
     constexpr int PER = OB / OB_THREADS;
     __shared__ Tri2 s_tri[OB_THREADS / 32][C];
@@ -236,6 +315,12 @@ __global__ void __launch_bounds__(OB_THREADS) k_ord_summary(PbPlanes b0, PbPlane
     if (base >= sg.n) return;
     const PbPlanes &P = sg.buf ? b1 : b0;
     OrdSummary *out = sum + ((size_t)sg.bbase + blockIdx.x) * C;
+    {
+        bool todo = false;
+#pragma unroll
+        for (int c = 0; c < C; c++) todo |= out[c].flag == 2;
+        if (!todo) return; // uniform across the CTA
+    }
     double m0 = 0, m1 = 0, m2 = 0;
     if (KIND == KIND_CENTERED) { m0 = stats[seg].mean[0]; m1 = stats[seg].mean[1]; m2 = stats[seg].mean[2]; }
     double scale[C];
@@ -282,7 +367,7 @@ __global__ void __launch_bounds__(OB_THREADS) k_ord_summary(PbPlanes b0, PbPlane
         if (lane == 0) s_tri[warp][c] = v;
     }
     __syncthreads();
-    if (threadIdx.x < C) {
+    if (threadIdx.x < C && out[threadIdx.x].flag == 2) {
         Tri2 v = s_tri[0][threadIdx.x];
         for (int w = 1; w < OB_THREADS / 32; w++) v = tri2_cat(v, s_tri[w][threadIdx.x]);
         out[threadIdx.x].t = v;
@@ -530,7 +615,9 @@ void launch_pass(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t
         { PbProfScope p("k_ord_prefix", st, false);
           k_ord_prefix<C><<<dim3(C, nseg), 32, 0, st>>>(d_segs, blk_cap, psum, sum); }
         { PbProfScope p(KIND == KIND_MEAN ? "k_ord_summary_mean" : "k_ord_summary_centered", st);
-          k_ord_summary<KIND, W><<<grid, OB_THREADS, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, blk_cap, sum); }
+          k_ord_summary<KIND, W><<<grid, OS_THREADS, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, blk_cap, sum); }
+        { PbProfScope p("k_ord_summary_tie", st, false);
+          k_ord_summary_tie<KIND, W><<<grid, OB_THREADS, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, blk_cap, sum); }
     }
     { PbProfScope p(KIND == KIND_MEAN ? "k_ord_resolve_mean" : "k_ord_resolve_centered", st, !speculative);
       k_ord_resolve<KIND, W><<<nseg, 32 * C, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, blk_cap, sum, speculative); }
