@@ -398,20 +398,58 @@ __device__ __forceinline__ long long warp_incl_scan(long long v, int lane) {
     return v;
 }
 
-// Applies the items [next, limit) held one per lane (each a Tri2, usable iff ok) to the state s as
-// far as they validate.  Returns the first index that does not (limit if all do) and updates s.
-// The parity each item starts from depends on the items before it, so the warp scans the Tri2
-// monoid itself (in order); item l then checks its own min / max against the exact state it would
-// start from if everything before it is accepted.
+// Applies the items [next, limit) held one per lane (usable iff ok) to the state s as far as they
+// validate.  Returns the first index that does not (limit if all do) and updates s.  Item l checks
+// its own prefix extremes against the exact state it would start from if everything before it is
+// accepted; that state comes from an in-order warp scan of the monoid.  `validate` turns the scanned
+// run of a lane into (usable, total).
+__device__ __forceinline__ uint32_t finish_run(double &s, long long bits, long long M, bool negs, bool mine, bool ok,
+                                              long long tot, double rmn, double rmx, uint32_t next, uint32_t limit) {
+    const long long lo = rmn > 9e299 ? 0 : (long long)rmn, hi = rmx < -9e299 ? 0 : (long long)rmx;
+    const long long vmin = negs ? M - hi : M + lo, vmax = negs ? M - lo : M + hi;
+    // every prefix up to and including this item strictly inside (2^52, 2^53): the unrounded value
+    // must itself stay inside the binade
+    const bool valid = ok && vmin > TWO52 && vmax < TWO53;
+    const unsigned fails = __ballot_sync(0xffffffffu, mine && !valid);
+    const uint32_t f = fails ? (uint32_t)(__ffs(fails) - 1) : limit;
+    if (f > next) {
+        const long long acc = __shfl_sync(0xffffffffu, tot, (int)f - 1); // inclusive total of lane f - 1
+        const long long M2 = negs ? M - acc : M + acc;
+        s = __longlong_as_double((bits & 0xfff0000000000000LL) | (M2 & 0x000fffffffffffffLL));
+    }
+    return f;
+}
+
+// items whose effect does not depend on the start parity (no tie inside): a 3-double scan
+__device__ __forceinline__ uint32_t apply_run_plain(double &s, int lane, uint32_t next, uint32_t limit, bool ok,
+                                                   const TriPlain &item) {
+    const long long bits = __double_as_longlong(s);
+    const long long M = (bits & 0x000fffffffffffffLL) | TWO52; // |s| / q
+    const bool mine = lane >= (int)next && lane < (int)limit;
+    TriPlain run = (mine && ok) ? item : TriPlain{0.0, 1e300, -1e300};
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        TriPlain up;
+        up.sum = __shfl_up_sync(0xffffffffu, run.sum, o);
+        up.mn = __shfl_up_sync(0xffffffffu, run.mn, o);
+        up.mx = __shfl_up_sync(0xffffffffu, run.mx, o);
+        if (lane >= o) run = trip_cat(up, run);
+    }
+    return finish_run(s, bits, M, bits < 0, mine, ok, (long long)run.sum, run.mn, run.mx, next, limit);
+}
+
+// general items: the parity each one starts from depends on the items before it, so the warp scans
+// the two-parity monoid
 __device__ __forceinline__ uint32_t apply_run(double &s, int lane, uint32_t next, uint32_t limit, bool ok,
                                              const Tri2 &item) {
     const long long bits = __double_as_longlong(s);
     const long long M = (bits & 0x000fffffffffffffLL) | TWO52; // |s| / q
-    const bool negs = bits < 0;
     const int p0 = (int)(M & 1LL);
     const bool mine = lane >= (int)next && lane < (int)limit;
-    // inclusive in-order scan of the concatenation; lanes outside [next, limit) and unusable items
-    // act as the empty run (anything behind the first unusable item is discarded anyway)
+    const bool parity_matters = mine && ok && (item.p[0].sum != item.p[1].sum || item.p[0].mn != item.p[1].mn ||
+                                               item.p[0].mx != item.p[1].mx);
+    if (!__any_sync(0xffffffffu, parity_matters))
+        return apply_run_plain(s, lane, next, limit, ok, TriPlain{item.p[0].sum, item.p[0].mn, item.p[0].mx});
     Tri2 inc;
     if (mine && ok) inc = item;
     else inc.p[0] = inc.p[1] = Tri{0.0, 1e300, -1e300};
@@ -428,25 +466,7 @@ __device__ __forceinline__ uint32_t apply_run(double &s, int lane, uint32_t next
         if (lane >= o) run = tri2_cat(up, run);
     }
     // run.p[p0] = items next..lane applied to a state of parity p0: prefix extremes included
-    const long long tot = (long long)run.p[p0].sum;
-    const double rmn = run.p[p0].mn, rmx = run.p[p0].mx;
-    long long vmin, vmax;
-    {
-        const long long lo = rmn > 9e299 ? 0 : (long long)rmn, hi = rmx < -9e299 ? 0 : (long long)rmx;
-        vmin = negs ? M - hi : M + lo;
-        vmax = negs ? M - lo : M + hi;
-    }
-    // every prefix up to and including this item strictly inside (2^52, 2^53): the unrounded value
-    // must itself stay inside the binade
-    const bool valid = ok && vmin > TWO52 && vmax < TWO53;
-    const unsigned fails = __ballot_sync(0xffffffffu, mine && !valid);
-    const uint32_t f = fails ? (uint32_t)(__ffs(fails) - 1) : limit;
-    if (f > next) {
-        const long long acc = __shfl_sync(0xffffffffu, tot, (int)f - 1); // inclusive total of lane f - 1
-        const long long M2 = negs ? M - acc : M + acc;
-        s = __longlong_as_double((bits & 0xfff0000000000000LL) | (M2 & 0x000fffffffffffffLL));
-    }
-    return f;
+    return finish_run(s, bits, M, bits < 0, mine, ok, (long long)run.p[p0].sum, run.p[p0].mn, run.p[p0].mx, next, limit);
 }
 
 template <int KIND, bool W>
@@ -493,13 +513,30 @@ __device__ __forceinline__ double replay_block(const PbPlanes &P, size_t first, 
         uint32_t f = next;
         if (ef > 24 && ef < 2000) { // a normal, finite state: quantise against its exact binade
             const double scale = scalbn(1.0, 52 - (ef - 1023));
-            Tri2 tri;
-            tri.p[0] = tri.p[1] = Tri{0.0, 0.0, 0.0};
-            int flag = 0;
+            TriPlain tp{0.0, 1e300, -1e300};
+            int flag = 0; // bit 0 unquantisable, bit 1 tie
 #pragma unroll
-            for (int k = 0; k < SUB; k++)
-                if (k < my) tri2_push(tri, __dmul_rn(t[k], scale), flag, k == 0);
-            f = apply_run(s, lane, next, nl, !flag && my > 0, tri);
+            for (int k = 0; k < SUB; k++) {
+                if (k < my) {
+                    const double u = __dmul_rn(t[k], scale);
+                    const double d = __dsub_rn(__dadd_rn(u, MAGIC), MAGIC);
+                    flag |= (!(fabs(u) < TWO51) ? 1 : 0) | (fabs(__dsub_rn(u, d)) == 0.5 ? 2 : 0);
+                    const double ps = tp.sum + d;
+                    tp = TriPlain{ps, fmin(tp.mn, ps), fmax(tp.mx, ps)};
+                }
+            }
+            const bool mine = lane >= (int)next && lane < (int)nl;
+            if (!__any_sync(0xffffffffu, mine && (flag & 2))) {
+                f = apply_run_plain(s, lane, next, nl, !flag && my > 0, tp);
+            } else { // some sub-chunk holds a tie: redo with both parities
+                Tri2 tri;
+                tri.p[0] = tri.p[1] = Tri{0.0, 0.0, 0.0};
+                int flag2 = 0;
+#pragma unroll
+                for (int k = 0; k < SUB; k++)
+                    if (k < my) tri2_push(tri, __dmul_rn(t[k], scale), flag2, k == 0);
+                f = apply_run(s, lane, next, nl, !flag2 && my > 0, tri);
+            }
         }
         if (f < nl) { // sub-chunk f: element by element (binade change, tie, or a zero / subnormal state)
             double v = s;
@@ -516,7 +553,7 @@ __device__ __forceinline__ double replay_block(const PbPlanes &P, size_t first, 
             next = nl;
         }
     }
-    hover = tail ? hover + 1 : 0;
+    hover = (tail || elementwise > 6) ? hover + 1 : 0;
     if (lane == 0) {
         atomicAdd(&g_ord_counts[5], (unsigned long long)rounds);
         atomicAdd(&g_ord_counts[6], (unsigned long long)elementwise);

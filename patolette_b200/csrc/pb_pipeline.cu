@@ -225,16 +225,19 @@ struct Quantizer {
     DevArr<char> oscratch; // block sums + summaries of the speculative ordered sums
     PbPlanes orig{}, bufs[2]{};
 
-    static constexpr int MAXB = 32; // clusters evaluated per batch (their 2 * MAXB children get stats)
+    static constexpr int MAXB = 64; // clusters evaluated per batch (their 2 * MAXB children get stats)
     size_t max_blocks = 0;         // capacity of the packed ordered-sum block table
 
     void init(size_t n, bool with_weights) {
         N = n;
         weighted = with_weights;
-        cudaDeviceProp prop;
         PB_CUDA_OK(cudaSetDevice(g_device));
-        PB_CUDA_OK(cudaGetDeviceProperties(&prop, g_device));
-        sm_count = prop.multiProcessorCount;
+        static int cached_dev = -1, cached_sms = 0;
+        if (cached_dev != g_device) {
+            PB_CUDA_OK(cudaDeviceGetAttribute(&cached_sms, cudaDevAttrMultiProcessorCount, g_device));
+            cached_dev = g_device;
+        }
+        sm_count = cached_sms;
         if (g_use_user_stream) { st = g_user_stream; own_stream = false; }
         else PB_CUDA_OK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         for (int j = 0; j < 3; j++) col[j].alloc(n);
