@@ -43,7 +43,7 @@ WORKLOAD = dict(name="4096x4096 uniform sRGB f64, K=256, ICtCp, dither off, kmea
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--side", type=int, default=0, help="override the image side (debug)")
