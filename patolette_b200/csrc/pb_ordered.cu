@@ -469,9 +469,52 @@ __device__ __forceinline__ uint32_t apply_run(double &s, int lane, uint32_t next
     return finish_run(s, bits, M, bits < 0, mine, ok, (long long)run.p[p0].sum, run.p[p0].mn, run.p[p0].mx, next, limit);
 }
 
+// One lane's 16 elements quantised against binade e: total, prefix extremes, exclusive prefix of the
+// totals over the lanes before it, and whether the sub-chunk is unusable (unquantisable term, or a tie,
+// whose rounding depends on the parity of the state - such a sub-chunk is simply added element-wise).
+struct SubVer {
+    int e;
+    int bad;
+    long long sum, mn, mx, pre;
+};
+
+__device__ __forceinline__ SubVer quantise_sub(const double *t, int my, int e, int lane) {
+    SubVer v;
+    v.e = e;
+    const double scale = scalbn(1.0, 52 - e);
+    double sum = 0.0, mn = 1e300, mx = -1e300;
+    int bad = my == 0;
+#pragma unroll
+    for (int k = 0; k < SUB; k++) {
+        if (k < my) {
+            const double u = __dmul_rn(t[k], scale);
+            const double d = __dsub_rn(__dadd_rn(u, MAGIC), MAGIC);
+            bad |= !(fabs(u) < TWO51) | (fabs(__dsub_rn(u, d)) == 0.5);
+            sum += d;
+            mn = fmin(mn, sum);
+            mx = fmax(mx, sum);
+        }
+    }
+    v.bad = bad;
+    v.sum = bad ? 0 : (long long)sum;
+    v.mn = bad ? 0 : (long long)mn;
+    v.mx = bad ? 0 : (long long)mx;
+    v.pre = warp_incl_scan(v.sum, lane) - v.sum;
+    return v;
+}
+
+// Replays one block exactly.  The exact state s is known, so each lane quantises its 16 consecutive
+// elements against the TRUE binade; prefix totals are scanned once per binade, after which finding the
+// first sub-chunk that cannot be applied is one ballot: lane l checks its own prefix extremes against
+// the state it would start from if every lane before it is applied.  Accepted sub-chunks are applied in
+// one step, the failing one (where the binade changes, or a tie sits) is added element by element - the
+// literal reference loop - and the walk resumes behind it with the quantisation of the new binade.
+// Sums that wander around a power of two bounce between adjacent binades, so the last three
+// quantisations are kept.
 template <int KIND, bool W>
 __device__ __forceinline__ double replay_block(const PbPlanes &P, size_t first, uint32_t cnt, int chain, double m0,
                                                double m1, double m2, double s, int lane, int &hover) {
+    (void)hover;
     double t[SUB];
     const int my = max(0, min(SUB, (int)cnt - lane * SUB));
 #pragma unroll
@@ -485,57 +528,35 @@ __device__ __forceinline__ double replay_block(const PbPlanes &P, size_t first, 
     const uint32_t nl = (cnt + SUB - 1) / SUB; // lanes that hold elements
     uint32_t next = 0;
     unsigned int rounds = 0, elementwise = 0;
-    // hover > 0: the previous replays of this chain ended in the sequential tail - the sum is
-    // hovering near zero - so skip the speculation rounds, re-trying them every fourth replay
-    int poor = (hover > 0 && (hover & 3) != 0) ? 2 : 0; // consecutive rounds that accepted < 2 sub-chunks
-    bool tail = false;
+    SubVer v0, v1, v2;
+    v0.e = v1.e = v2.e = E_NOGUESS;
+    int victim = 0;
     while (next < nl) {
-        if (poor >= 2) {
-            // The sum is hovering (state small against the terms: the binade changes every few
-            // elements, nothing validates).  A speculation round costs ~10x a 16-element chain, so
-            // finish the block as the plain sequential loop, lane after lane.
-            for (uint32_t l = next; l < nl; l++) {
-                double v = s;
-                if (lane == (int)l) {
-#pragma unroll
-                    for (int k = 0; k < SUB; k++)
-                        if (k < my) v = __dadd_rn(v, t[k]);
-                }
-                s = __shfl_sync(0xffffffffu, v, (int)l);
-            }
-            elementwise += nl - next;
-            tail = true;
-            break;
-        }
         rounds++;
         const long long bits = __double_as_longlong(s);
         const int ef = (int)((bits >> 52) & 0x7ff);
         uint32_t f = next;
-        if (ef > 24 && ef < 2000) { // a normal, finite state: quantise against its exact binade
-            const double scale = scalbn(1.0, 52 - (ef - 1023));
-            TriPlain tp{0.0, 1e300, -1e300};
-            int flag = 0; // bit 0 unquantisable, bit 1 tie
-#pragma unroll
-            for (int k = 0; k < SUB; k++) {
-                if (k < my) {
-                    const double u = __dmul_rn(t[k], scale);
-                    const double d = __dsub_rn(__dadd_rn(u, MAGIC), MAGIC);
-                    flag |= (!(fabs(u) < TWO51) ? 1 : 0) | (fabs(__dsub_rn(u, d)) == 0.5 ? 2 : 0);
-                    const double ps = tp.sum + d;
-                    tp = TriPlain{ps, fmin(tp.mn, ps), fmax(tp.mx, ps)};
-                }
+        if (ef > 24 && ef < 2000) { // a normal, finite state
+            const int es = ef - 1023;
+            if (v0.e != es && v1.e != es && v2.e != es) {
+                const SubVer nv = quantise_sub(t, my, es, lane);
+                if (victim == 0) v0 = nv; else if (victim == 1) v1 = nv; else v2 = nv;
+                victim = victim == 2 ? 0 : victim + 1;
             }
+            const SubVer &v = v0.e == es ? v0 : (v1.e == es ? v1 : v2);
+            const long long M = (bits & 0x000fffffffffffffLL) | TWO52; // |s| / q
+            const bool negs = bits < 0;
+            const long long p = v.pre - __shfl_sync(0xffffffffu, v.pre, (int)next); // lanes [next, lane)
+            const long long cur = negs ? M - p : M + p;
+            const long long vmin = negs ? cur - v.mx : cur + v.mn, vmax = negs ? cur - v.mn : cur + v.mx;
             const bool mine = lane >= (int)next && lane < (int)nl;
-            if (!__any_sync(0xffffffffu, mine && (flag & 2))) {
-                f = apply_run_plain(s, lane, next, nl, !flag && my > 0, tp);
-            } else { // some sub-chunk holds a tie: redo with both parities
-                Tri2 tri;
-                tri.p[0] = tri.p[1] = Tri{0.0, 0.0, 0.0};
-                int flag2 = 0;
-#pragma unroll
-                for (int k = 0; k < SUB; k++)
-                    if (k < my) tri2_push(tri, __dmul_rn(t[k], scale), flag2, k == 0);
-                f = apply_run(s, lane, next, nl, !flag2 && my > 0, tri);
+            const bool valid = !v.bad && vmin > TWO52 && vmax < TWO53;
+            const unsigned fails = __ballot_sync(0xffffffffu, mine && !valid);
+            f = fails ? (uint32_t)(__ffs(fails) - 1) : nl;
+            if (f > next) {
+                const long long acc = __shfl_sync(0xffffffffu, p + v.sum, (int)f - 1); // total of lanes [next, f)
+                const long long M2 = negs ? M - acc : M + acc;
+                s = __longlong_as_double((bits & 0xfff0000000000000LL) | (M2 & 0x000fffffffffffffLL));
             }
         }
         if (f < nl) { // sub-chunk f: element by element (binade change, tie, or a zero / subnormal state)
@@ -546,14 +567,12 @@ __device__ __forceinline__ double replay_block(const PbPlanes &P, size_t first, 
                     if (k < my) v = __dadd_rn(v, t[k]);
             }
             s = __shfl_sync(0xffffffffu, v, (int)f);
-            poor = (f - next < 2) ? poor + 1 : 0;
             next = f + 1;
             elementwise++;
         } else {
             next = nl;
         }
     }
-    hover = (tail || elementwise > 6) ? hover + 1 : 0;
     if (lane == 0) {
         atomicAdd(&g_ord_counts[5], (unsigned long long)rounds);
         atomicAdd(&g_ord_counts[6], (unsigned long long)elementwise);
