@@ -20,7 +20,7 @@
 #include <math.h>
 #include <string.h>
 
-#include <unordered_map>
+#include <mutex>
 #include <vector>
 
 #include "pb_common.cuh"
@@ -57,23 +57,44 @@ struct Mt19937 {
     }
 };
 
-// First `take` entries of faiss::rand_perm(n, seed) (random.cpp:184-194).
+// First `take` entries of faiss::rand_perm(n, seed) (random.cpp:184-194).  Forward Fisher-Yates
+// finalises perm[i] at step i and later steps only touch positions > i, so only `take` steps are
+// simulated; positions whose value is no longer the identity live in an open-addressing table.
+// The result depends on (n, take, seed) only and is cached across calls.
 std::vector<uint32_t> rand_perm_prefix(size_t n, size_t take, uint32_t seed) {
+    static std::mutex mu;
+    static size_t c_n = 0, c_take = 0;
+    static uint32_t c_seed = 0;
+    static std::vector<uint32_t> c_out;
+    std::lock_guard<std::mutex> lk(mu);
+    if (c_n == n && c_take == take && c_seed == seed && !c_out.empty()) return c_out;
     std::vector<uint32_t> out(take);
-    std::unordered_map<uint32_t, uint32_t> moved; // positions whose value is no longer the identity
-    moved.reserve(take * 2);
-    Mt19937 rng(seed);
+    size_t cap = 1;
+    while (cap < take * 4 + 16) cap <<= 1;
+    std::vector<uint64_t> tab(cap, ~0ULL); // (position << 32) | value
+    auto slot = [&](uint32_t k) { return (size_t)(k * 0x9E3779B1u) & (cap - 1); };
     auto get = [&](uint32_t pos) {
-        auto it = moved.find(pos);
-        return it == moved.end() ? pos : it->second;
+        for (size_t j = slot(pos);; j = (j + 1) & (cap - 1)) {
+            const uint64_t e = tab[j];
+            if (e == ~0ULL) return pos;
+            if ((uint32_t)(e >> 32) == pos) return (uint32_t)e;
+        }
     };
+    auto put = [&](uint32_t pos, uint32_t v) {
+        for (size_t j = slot(pos);; j = (j + 1) & (cap - 1)) {
+            const uint64_t e = tab[j];
+            if (e == ~0ULL || (uint32_t)(e >> 32) == pos) { tab[j] = ((uint64_t)pos << 32) | v; return; }
+        }
+    };
+    Mt19937 rng(seed);
     for (size_t i = 0; i < take && i + 1 < n; i++) {
         const uint32_t i2 = (uint32_t)(i + (size_t)((uint64_t)rng.next() % (uint64_t)(int)(n - i)));
         const uint32_t vi = get((uint32_t)i), v2 = get(i2);
-        out[i] = v2;        // perm[i] is final after step i
-        moved[i2] = vi;
+        out[i] = v2; // perm[i] is final after step i
+        put(i2, vi);
     }
     if (take == n && n > 0) out[n - 1] = get((uint32_t)(n - 1));
+    c_n = n; c_take = take; c_seed = seed; c_out = out;
     return out;
 }
 
@@ -105,8 +126,9 @@ __global__ void k_scan_finite(const double *__restrict__ c0, const double *__res
 __global__ void __launch_bounds__(256) k_assign(const float *__restrict__ x0, const float *__restrict__ x1,
                                                 const float *__restrict__ x2, size_t nx,
                                                 const float *__restrict__ cen, int K, bool seq_path,
-                                                uint16_t *__restrict__ assign) {
+                                                uint16_t *__restrict__ assign, const int *__restrict__ stop) {
     extern __shared__ float s_cen[]; // K * 4: y0 y1 y2 |y|^2
+    if (*stop) return; // an earlier iteration produced an empty cluster: the host takes over from there
     for (int j = threadIdx.x; j < K; j += blockDim.x) {
         const float a = cen[3 * j], b = cen[3 * j + 1], c = cen[3 * j + 2];
         s_cen[4 * j] = a; s_cen[4 * j + 1] = b; s_cen[4 * j + 2] = c;
@@ -144,8 +166,10 @@ __global__ void __launch_bounds__(KM_WARPS * 32) k_centroid_chains(const float *
                                                                    const float *__restrict__ x2, const float *__restrict__ wf,
                                                                    const uint32_t *__restrict__ ord,
                                                                    const uint32_t *__restrict__ class_start, int K,
-                                                                   float *__restrict__ out /* K x 4 */) {
+                                                                   float *__restrict__ out /* K x 4 */,
+                                                                   const int *__restrict__ stop) {
     __shared__ float sm_all[KM_WARPS][4][KM_TILE + 1];
+    if (*stop) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int c = blockIdx.x * KM_WARPS + warp;
     if (c >= K) return;
@@ -177,6 +201,28 @@ __global__ void __launch_bounds__(KM_WARPS * 32) k_centroid_chains(const float *
         __syncwarp();
     }
     if (lane < 4) out[4 * c + lane] = acc;
+}
+
+// compute_centroids epilogue (Clustering.cpp:194-203) on the device: centroid = sum * (1 / hassign).
+// An empty cluster needs faiss' RNG-driven split_clusters (Clustering.cpp:216-263), which stays on the
+// host: the kernel then records the iteration in *stop and leaves the sums untouched for the host.
+__global__ void k_finalize_centroids(const float *__restrict__ sums, int K, int iteration, float *__restrict__ cen,
+                                     int *__restrict__ stop) {
+    __shared__ int s_empty;
+    if (*stop) return;
+    if (threadIdx.x == 0) s_empty = 0;
+    __syncthreads();
+    for (int c = threadIdx.x; c < K; c += blockDim.x)
+        if (sums[4 * c] == 0.f) s_empty = 1;
+    __syncthreads();
+    if (s_empty) {
+        if (threadIdx.x == 0) *stop = iteration + 1;
+        return;
+    }
+    for (int c = threadIdx.x; c < K; c += blockDim.x) {
+        const float norm = __fdiv_rn(1.f, sums[4 * c]);
+        for (int j = 0; j < 3; j++) cen[3 * c + j] = __fmul_rn(sums[4 * c + 1 + j], norm);
+    }
 }
 
 struct DevMem {
@@ -214,34 +260,48 @@ void pb_kmeans_device(const float *d_x0, const float *d_x1, const float *d_x2, c
     const size_t smem = (size_t)K * 4 * sizeof(float);
     if (smem > 48 * 1024)
         PB_CUDA_OK(cudaFuncSetAttribute(k_assign, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int *d_stop = mem.alloc<int>(1);
     std::vector<float> sums((size_t)K * 4);
-    for (int it = 0; it < niter; it++) { // Clustering.cpp:442-530
+    // All iterations are enqueued back to back (Clustering.cpp:442-530); the centroid epilogue runs on the
+    // device.  Only an empty cluster (rare) hands control back to the host for faiss' split protocol.
+    int it = 0;
+    while (it < niter) {
         PB_CUDA_OK(cudaMemcpyAsync(d_cen, cen.data(), cen.size() * sizeof(float), cudaMemcpyHostToDevice, st));
-        { PbProfScope _prof("k_assign", st);
-        k_assign<<<grid, 256, smem, st>>>(d_x0, d_x1, d_x2, nx, d_cen, K, nx < 20, d_assign);
+        PB_CUDA_OK(cudaMemsetAsync(d_stop, 0, sizeof(int), st));
+        for (int i = it; i < niter; i++) {
+            { PbProfScope _prof("k_assign", st);
+            k_assign<<<grid, 256, smem, st>>>(d_x0, d_x1, d_x2, nx, d_cen, K, nx < 20, d_assign, d_stop);
+            }
+            pb_launch_class_rank(PB_CLS_BUCKET, K, d_seg, 1, (uint32_t)nx, d_assign, nullptr, nullptr, d_tile_hist,
+                                 d_cstart, st);
+            pb_launch_scatter_ord(PB_CLS_BUCKET, K, d_seg, 1, (uint32_t)nx, d_assign, nullptr, nullptr, d_tile_hist,
+                                  d_cstart, d_ord, st);
+            const int cg = (K + KM_WARPS - 1) / KM_WARPS;
+            { PbProfScope _prof("k_centroid_chains", st);
+            if (d_wf) k_centroid_chains<true><<<cg, KM_WARPS * 32, 0, st>>>(d_x0, d_x1, d_x2, d_wf, d_ord, d_cstart, K, d_sums, d_stop);
+            else k_centroid_chains<false><<<cg, KM_WARPS * 32, 0, st>>>(d_x0, d_x1, d_x2, d_wf, d_ord, d_cstart, K, d_sums, d_stop);
+            }
+            { PbProfScope _prof("k_finalize_centroids", st, false);
+            k_finalize_centroids<<<1, 256, 0, st>>>(d_sums, K, i, d_cen, d_stop);
+            }
         }
-        pb_launch_class_rank(PB_CLS_BUCKET, K, d_seg, 1, (uint32_t)nx, d_assign, nullptr, nullptr, d_tile_hist,
-                             d_cstart, st);
-        pb_launch_scatter_ord(PB_CLS_BUCKET, K, d_seg, 1, (uint32_t)nx, d_assign, nullptr, nullptr, d_tile_hist,
-                              d_cstart, d_ord, st);
-        const int cg = (K + KM_WARPS - 1) / KM_WARPS;
-        PbProfScope _prof("k_centroid_chains", st);
-        if (d_wf) k_centroid_chains<true><<<cg, KM_WARPS * 32, 0, st>>>(d_x0, d_x1, d_x2, d_wf, d_ord, d_cstart, K, d_sums);
-        else k_centroid_chains<false><<<cg, KM_WARPS * 32, 0, st>>>(d_x0, d_x1, d_x2, d_wf, d_ord, d_cstart, K, d_sums);
         PB_CUDA_OK(cudaGetLastError());
+        int stop = 0;
+        PB_CUDA_OK(cudaMemcpyAsync(&stop, d_stop, sizeof(int), cudaMemcpyDeviceToHost, st));
+        PB_CUDA_OK(cudaMemcpyAsync(cen.data(), d_cen, cen.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
         PB_CUDA_OK(cudaMemcpyAsync(sums.data(), d_sums, sums.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
         PB_CUDA_OK(cudaStreamSynchronize(st));
-        // compute_centroids epilogue (Clustering.cpp:194-203)
+        if (!stop) break; // all remaining iterations completed on the device
+        // iteration stop - 1 produced an empty cluster: finish it on the host exactly as faiss does
         std::vector<float> hassign(K);
-        for (int c = 0; c < K; c++) {
+        for (int c = 0; c < K; c++) { // compute_centroids epilogue (Clustering.cpp:194-203)
             hassign[c] = sums[4 * c];
             for (int j = 0; j < 3; j++) cen[3 * c + j] = sums[4 * c + 1 + j];
             if (hassign[c] == 0) continue;
             const float norm = 1 / hassign[c];
             for (int j = 0; j < 3; j++) cen[3 * c + j] *= norm;
         }
-        // split_clusters (Clustering.cpp:216-263)
-        Mt19937 rng(1234u);
+        Mt19937 rng(1234u); // split_clusters (Clustering.cpp:216-263)
         for (int ci = 0; ci < K; ci++) {
             if (hassign[ci] != 0) continue;
             int cj;
@@ -258,6 +318,7 @@ void pb_kmeans_device(const float *d_x0, const float *d_x1, const float *d_x2, c
             hassign[ci] = hassign[cj] / 2;
             hassign[cj] -= hassign[ci];
         }
+        it = stop; // resume with the next iteration
     }
 }
 
