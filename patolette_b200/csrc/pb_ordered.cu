@@ -232,7 +232,9 @@ __device__ __forceinline__ TriPlain trip_cat(const TriPlain &a, const TriPlain &
 template <int KIND, bool W>
 __global__ void __launch_bounds__(OS_THREADS) k_ord_summary(PbPlanes b0, PbPlanes b1, const PbSeg *__restrict__ segs,
                                                             const PbStats *__restrict__ stats, uint32_t blk_cap,
-                                                            OrdSummary *__restrict__ sum) {
+                                                            OrdSummary *__restrict__ sum,
+                                                            unsigned int *__restrict__ tie_count,
+                                                            uint2 *__restrict__ tie_list) {
     constexpr int C = NChains<KIND>::C;
     constexpr int PER = OB / OS_THREADS;
     __shared__ TriPlain s_tri[OS_THREADS / 32][C];
@@ -298,29 +300,32 @@ __global__ void __launch_bounds__(OS_THREADS) k_ord_summary(PbPlanes b0, PbPlane
         out[threadIdx.x].t.p[1] = tt;
         out[threadIdx.x].flag = s_flag[threadIdx.x]; // 0 ok, odd: replay, 2: redo with k_ord_summary_tie
     }
+    if (threadIdx.x == 0) { // blocks holding a tie go on the work list of the tie-aware pass
+        bool tie = false;
+        for (int c = 0; c < C; c++) tie |= s_flag[c] == 2;
+        if (tie) tie_list[atomicAdd(tie_count, 1u)] = make_uint2((unsigned)seg, blockIdx.x);
+    }
 }
 
 // ---- S3b: blocks that contain a tie: both start parities (the two-state transducer) --------------
 template <int KIND, bool W>
 __global__ void __launch_bounds__(OB_THREADS) k_ord_summary_tie(PbPlanes b0, PbPlanes b1, const PbSeg *__restrict__ segs,
                                                                 const PbStats *__restrict__ stats, uint32_t blk_cap,
-                                                                OrdSummary *__restrict__ sum) {
+                                                                OrdSummary *__restrict__ sum,
+                                                                const unsigned int *__restrict__ tie_count,
+                                                                const uint2 *__restrict__ tie_list) {
     constexpr int C = NChains<KIND>::C;
     constexpr int PER = OB / OB_THREADS;
     __shared__ Tri2 s_tri[OB_THREADS / 32][C];
     __shared__ int s_flag[C];
-    const int seg = blockIdx.y;
+  for (unsigned int item = blockIdx.x; item < *tie_count; item += gridDim.x) { // persistent CTAs over the work list
+    const int seg = (int)tie_list[item].x;
+    const uint32_t blk = tie_list[item].y;
     const PbSeg sg = segs[seg];
-    const uint32_t base = blockIdx.x * OB;
-    if (base >= sg.n) return;
+    const uint32_t base = blk * OB;
     const PbPlanes &P = sg.buf ? b1 : b0;
-    OrdSummary *out = sum + ((size_t)sg.bbase + blockIdx.x) * C;
-    {
-        bool todo = false;
-#pragma unroll
-        for (int c = 0; c < C; c++) todo |= out[c].flag == 2;
-        if (!todo) return; // uniform across the CTA
-    }
+    OrdSummary *out = sum + ((size_t)sg.bbase + blk) * C;
+    __syncthreads();
     double m0 = 0, m1 = 0, m2 = 0;
     if (KIND == KIND_CENTERED) { m0 = stats[seg].mean[0]; m1 = stats[seg].mean[1]; m2 = stats[seg].mean[2]; }
     double scale[C];
@@ -373,6 +378,7 @@ __global__ void __launch_bounds__(OB_THREADS) k_ord_summary_tie(PbPlanes b0, PbP
         out[threadIdx.x].t = v;
         out[threadIdx.x].flag = s_flag[threadIdx.x];
     }
+  }
 }
 
 // ---- S4: ordered resolve ---------------------------------------------------------------------------
@@ -658,10 +664,12 @@ void launch_pass(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t
                  PbStats *d_stats, void *d_scratch, size_t scratch_bytes, cudaStream_t st) {
     constexpr int C = NChains<KIND>::C;
     const uint32_t blk_cap = (max_n + OB - 1) / OB; // grid width; the tables are packed by PbSeg::bbase
-    const size_t need = (size_t)total_blocks * C * (sizeof(double) + sizeof(OrdSummary));
+    const size_t need = pb_ordered_scratch_bytes(total_blocks);
     const bool speculative = max_n >= 8 * OB && d_scratch && need <= scratch_bytes;
     double *psum = (double *)d_scratch;
-    OrdSummary *sum = (OrdSummary *)((char *)d_scratch + (size_t)total_blocks * C * sizeof(double));
+    OrdSummary *sum = (OrdSummary *)((char *)d_scratch + (size_t)total_blocks * 7 * sizeof(double));
+    uint2 *tie_list = (uint2 *)((char *)d_scratch + (size_t)total_blocks * 7 * (sizeof(double) + sizeof(OrdSummary)));
+    unsigned int *tie_count = (unsigned int *)(tie_list + total_blocks);
     const double bytes = 0; // set by the caller through pb_prof_next_bytes for the resolve kernel
     (void)bytes;
     if (speculative) {
@@ -670,10 +678,11 @@ void launch_pass(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t
           k_ord_blocksum<KIND, W><<<grid, OB_THREADS, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, blk_cap, psum); }
         { PbProfScope p("k_ord_prefix", st, false);
           k_ord_prefix<C><<<dim3(C, nseg), 32, 0, st>>>(d_segs, blk_cap, psum, sum); }
+        PB_CUDA_OK(cudaMemsetAsync(tie_count, 0, sizeof(unsigned int), st));
         { PbProfScope p(KIND == KIND_MEAN ? "k_ord_summary_mean" : "k_ord_summary_centered", st);
-          k_ord_summary<KIND, W><<<grid, OS_THREADS, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, blk_cap, sum); }
+          k_ord_summary<KIND, W><<<grid, OS_THREADS, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, blk_cap, sum, tie_count, tie_list); }
         { PbProfScope p("k_ord_summary_tie", st, false);
-          k_ord_summary_tie<KIND, W><<<grid, OB_THREADS, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, blk_cap, sum); }
+          k_ord_summary_tie<KIND, W><<<148 * 4, OB_THREADS, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, blk_cap, sum, tie_count, tie_list); }
     }
     { PbProfScope p(KIND == KIND_MEAN ? "k_ord_resolve_mean" : "k_ord_resolve_centered", st, !speculative);
       k_ord_resolve<KIND, W><<<nseg, 32 * C, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, blk_cap, sum, speculative); }
@@ -693,7 +702,7 @@ void pb_ordered_counts(unsigned long long out[8], bool reset) {
 uint32_t pb_ordered_blocks(uint32_t n) { return (n + OB - 1) / OB; }
 
 size_t pb_ordered_scratch_bytes(size_t total_blocks) {
-    return total_blocks * 7 * (sizeof(double) + sizeof(OrdSummary)) + 256;
+    return total_blocks * (7 * (sizeof(double) + sizeof(OrdSummary)) + sizeof(uint2)) + 256;
 }
 
 void pb_launch_pass_mean(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t max_n,
