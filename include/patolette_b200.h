@@ -97,6 +97,11 @@ PB200_API int patolette_b200_kmeans(const float *x, size_t n, size_t K, float *c
 PB200_API int patolette_b200_dither(const double *planar, size_t width, size_t height,
                           const double *palette_rm, size_t K, size_t *map);
 
+/* patolette() for colours stored N x 3 ROW-major (interleaved RGB - numpy's default layout); the
+ * transposition the reference's wrapper does on the host (patolette.pyx:388-391) happens on the GPU. */
+PB200_API void patolette_b200_interleaved(size_t width, size_t height, const double *rgb, const double *weights,
+                                          size_t palette_size, const patolette__QuantizationOptions *options,
+                                          double *palette, size_t *palette_map, int *exit_code);
 /* Same pipeline with DEVICE-resident I/O: d_data / d_weights / d_palette_map are CUDA device
  * pointers on the current device (layouts as for patolette()); palette stays a host pointer.
  * Inputs are copied device-to-device first (never written), as patolette.c:187-199 copies. */

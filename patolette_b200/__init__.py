@@ -56,7 +56,10 @@ def quantize(width, height, colors, palette_size, dither=True, palette_only=Fals
             "saliency weights (tile_size > 0) are not part of patolette_b200; pass tile_size=0 "
             "or supply weights=...")
     lib = _lib.load()
-    data = np.asfortranarray(colors, dtype=np.float64)
+    # The reference copies to Fortran order on the host (patolette.pyx:388-391).  A C-contiguous f64
+    # array is instead handed over as is and de-interleaved on the GPU (same values, no host pass).
+    interleaved = colors.dtype == np.float64 and colors.flags.c_contiguous and not colors.flags.f_contiguous
+    data = colors if interleaved else np.asfortranarray(colors, dtype=np.float64)
     palette = np.zeros((palette_size, 3), dtype=np.float64, order="F")
     pmap = None if palette_only else np.zeros(width * height, dtype=np.uintp)
     w = None
@@ -67,7 +70,8 @@ def quantize(width, height, colors, palette_size, dither=True, palette_only=Fals
     opts = _lib.QuantizationOptions(bool(dither), bool(palette_only), int(color_space), int(kmeans_niter),
                                     int(kmeans_max_samples), bool(verbose))
     code = C.c_int(0)
-    lib.patolette(width, height, data.ctypes.data if color_count else None,
+    entry = lib.patolette_b200_interleaved if interleaved else lib.patolette
+    entry(width, height, data.ctypes.data if color_count else None,
                   None if w is None else w.ctypes.data, palette_size, C.byref(opts),
                   palette.ctypes.data if palette_size else None,
                   None if pmap is None else pmap.ctypes.data, C.byref(code))

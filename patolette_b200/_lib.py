@@ -39,6 +39,8 @@ SYMBOLS = {
     "patolette_b200_kmeans": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
     "patolette_b200_dither": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
     "patolette_b200_last_timings": (C.c_int, [C.c_void_p]),
+    "patolette_b200_interleaved": (None, [C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t,
+                                          C.POINTER(QuantizationOptions), C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]),
     "patolette_b200_device": (None, [C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t,
                                      C.POINTER(QuantizationOptions), C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]),
     "patolette_b200_set_stream": (C.c_int, [C.c_void_p, C.c_int]),

@@ -203,6 +203,24 @@ __global__ void __launch_bounds__(256) k_color(const double *__restrict__ s0, co
     }
 }
 
+// N x 3 row-major (interleaved RGB, numpy's default layout) -> three planes.  The reference's Python
+// wrapper does this on the host with np.asfortranarray (patolette.pyx:388-391), ~0.2 s at 4096^2.
+__global__ void __launch_bounds__(256) k_deinterleave(const double *__restrict__ rgb, size_t n, double *__restrict__ d0,
+                                                      double *__restrict__ d1, double *__restrict__ d2) {
+    __shared__ double tile[256 * 3];
+    for (size_t base = (size_t)blockIdx.x * 256; base < n; base += (size_t)gridDim.x * 256) {
+        const size_t cnt = min((size_t)256, n - base);
+        for (size_t i = threadIdx.x; i < cnt * 3; i += 256) tile[i] = rgb[base * 3 + i]; // coalesced
+        __syncthreads();
+        if (threadIdx.x < cnt) {
+            d0[base + threadIdx.x] = tile[3 * threadIdx.x];
+            d1[base + threadIdx.x] = tile[3 * threadIdx.x + 1];
+            d2[base + threadIdx.x] = tile[3 * threadIdx.x + 2];
+        }
+        __syncthreads();
+    }
+}
+
 __global__ void k_pow(const double *x, double y, double *out, size_t n) {
     __shared__ uint64_t s_log[128 * 3];
     __shared__ uint64_t s_exp[256];
@@ -250,6 +268,13 @@ void pb_launch_color(int which, const double *const src[3], double *const dst[3]
     default: break;
     }
 #undef PB_CASE
+    PB_CUDA_OK(cudaGetLastError());
+}
+
+void pb_launch_deinterleave(const double *d_rgb, size_t n, double *const dst[3], int sm_count, cudaStream_t st) {
+    if (n == 0) return;
+    PbProfScope _prof("k_deinterleave", st);
+    k_deinterleave<<<grid_for(n, 256, sm_count), 256, 0, st>>>(d_rgb, n, dst[0], dst[1], dst[2]);
     PB_CUDA_OK(cudaGetLastError());
 }
 

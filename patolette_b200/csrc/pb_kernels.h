@@ -19,6 +19,7 @@ enum {
 void pb_launch_color(int which, const double *const src[3], double *const dst[3], size_t n,
                      int sm_count, cudaStream_t st);
 void pb_launch_pow(const double *x, double y, double *out, size_t n, int sm_count, cudaStream_t st);
+void pb_launch_deinterleave(const double *d_rgb, size_t n, double *const dst[3], int sm_count, cudaStream_t st);
 
 // ---- ordered-sum kernels, pb_ordered.cu / pb_chain.cu ----------------------------------
 // Every reference statistic is a left-to-right f64 sum in ascending pixel order; these

@@ -331,10 +331,12 @@ __global__ void __launch_bounds__(OB_THREADS) k_ord_summary_tie(PbPlanes b0, PbP
     double scale[C];
     Tri2 tri[C];
     int flag[C];
+    bool need[C]; // only the chains that actually hold a tie are redone (uniform across the CTA)
     bool any = false;
 #pragma unroll
     for (int c = 0; c < C; c++) {
         const int e = out[c].e;
+        need[c] = out[c].flag == 2;
         flag[c] = e == E_NOGUESS;
         scale[c] = flag[c] ? 0.0 : scalbn(1.0, 52 - e); // 1 / q
         tri[c].p[0] = tri[c].p[1] = Tri{0.0, 1e300, -1e300}; // empty run
@@ -349,13 +351,15 @@ __global__ void __launch_bounds__(OB_THREADS) k_ord_summary_tie(PbPlanes b0, PbP
             double t[C];
             terms_all<KIND, W>(W ? P.w[p] : 1.0, P.c[0][p], P.c[1][p], P.c[2][p], m0, m1, m2, t);
 #pragma unroll
-            for (int c = 0; c < C; c++) tri2_push(tri[c], __dmul_rn(t[c], scale[c]) /* a / q, exact */, flag[c], !any);
+            for (int c = 0; c < C; c++)
+                if (need[c]) tri2_push(tri[c], __dmul_rn(t[c], scale[c]) /* a / q, exact */, flag[c], !any);
             any = true;
         }
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int c = 0; c < C; c++) {
+        if (!need[c]) continue;
         if (flag[c]) atomicOr(&s_flag[c], 1);
         Tri2 v = tri[c];
 #pragma unroll
@@ -372,7 +376,7 @@ __global__ void __launch_bounds__(OB_THREADS) k_ord_summary_tie(PbPlanes b0, PbP
         if (lane == 0) s_tri[warp][c] = v;
     }
     __syncthreads();
-    if (threadIdx.x < C && out[threadIdx.x].flag == 2) {
+    if (threadIdx.x < C && out[threadIdx.x].flag == 2) { // == need[threadIdx.x]
         Tri2 v = s_tri[0][threadIdx.x];
         for (int w = 1; w < OB_THREADS / 32; w++) v = tri2_cat(v, s_tri[w][threadIdx.x]);
         out[threadIdx.x].t = v;

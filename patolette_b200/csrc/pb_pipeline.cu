@@ -22,6 +22,7 @@
 #include "pb_pipeline.h"
 #include "pb_pool.h"
 #include "pb_prof.h"
+#include "pb_xfer.h"
 
 namespace {
 
@@ -566,7 +567,7 @@ void colors_transform(Quantizer &qz, int which) {
 
 void run_patolette(size_t width, size_t height, const double *data, const double *weights, size_t K,
                    const patolette__QuantizationOptions *opt, double *palette, size_t *palette_map,
-                   int *exit_code, bool device_io) {
+                   int *exit_code, bool device_io, bool interleaved = false) {
     const size_t n = width * height;
     memset(g_timings, 0, sizeof g_timings);
     const long launches0 = pb_prof_launch_count();
@@ -577,9 +578,23 @@ void run_patolette(size_t width, size_t height, const double *data, const double
 
     stage.start(); // patolette.c:187-199: the library works on its own copy
     const cudaMemcpyKind in_kind = device_io ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-    for (int j = 0; j < 3; j++)
-        PB_CUDA_OK(cudaMemcpyAsync(qz.col[j].p, data + (size_t)j * n, n * sizeof(double), in_kind, qz.st));
-    if (weights) PB_CUDA_OK(cudaMemcpyAsync(qz.wgt.p, weights, n * sizeof(double), in_kind, qz.st));
+    if (interleaved) { // N x 3 row-major input: one copy, de-interleaved on the device
+        DevArr<double> rgb;
+        rgb.alloc(3 * n);
+        if (device_io) PB_CUDA_OK(cudaMemcpyAsync(rgb.p, data, 3 * n * sizeof(double), in_kind, qz.st));
+        else pb_copy_h2d(rgb.p, data, 3 * n * sizeof(double), qz.st);
+        double *dst[3] = {qz.col[0].p, qz.col[1].p, qz.col[2].p};
+        pb_launch_deinterleave(rgb.p, n, dst, qz.sm_count, qz.st);
+        qz.sync(); // rgb is released at the end of this scope
+    } else
+    for (int j = 0; j < 3; j++) {
+        if (device_io) PB_CUDA_OK(cudaMemcpyAsync(qz.col[j].p, data + (size_t)j * n, n * sizeof(double), in_kind, qz.st));
+        else pb_copy_h2d(qz.col[j].p, data + (size_t)j * n, n * sizeof(double), qz.st);
+    }
+    if (weights) {
+        if (device_io) PB_CUDA_OK(cudaMemcpyAsync(qz.wgt.p, weights, n * sizeof(double), in_kind, qz.st));
+        else pb_copy_h2d(qz.wgt.p, weights, n * sizeof(double), qz.st);
+    }
     set_timing(1, stage.stop());
 
     stage.start(); // patolette.c:201-207
@@ -652,8 +667,8 @@ void run_patolette(size_t width, size_t height, const double *data, const double
             set_timing(6, stage.stop());
         }
         stage.start();
-        PB_CUDA_OK(cudaMemcpyAsync(palette_map, dmap.p, n * sizeof(size_t),
-                                   device_io ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, qz.st));
+        if (device_io) PB_CUDA_OK(cudaMemcpyAsync(palette_map, dmap.p, n * sizeof(size_t), cudaMemcpyDeviceToDevice, qz.st));
+        else pb_copy_d2h(palette_map, dmap.p, n * sizeof(size_t), qz.st);
         set_timing(8, stage.stop());
     }
     for (size_t j = 0; j < K * 3; j++) palette[j] = -1.0; // patolette.c:328-330
@@ -697,6 +712,23 @@ void patolette_b200_device(size_t width, size_t height, const double *d_data, co
     if (width * height > (size_t)40000 * 40000) { *exit_code = -4; return; }
     try {
         run_patolette(width, height, d_data, d_weights, palette_size, options, palette, d_palette_map, exit_code, true);
+    } catch (const pb_cuda_error &) {
+        cudaGetLastError();
+        *exit_code = -5;
+    } catch (const std::bad_alloc &) {
+        *exit_code = -1;
+    }
+}
+
+void patolette_b200_interleaved(size_t width, size_t height, const double *rgb, const double *weights,
+                                size_t palette_size, const patolette__QuantizationOptions *options, double *palette,
+                                size_t *palette_map, int *exit_code) {
+    *exit_code = 0;
+    if (width * height == 0) { *exit_code = -2; return; }
+    if (palette_size < 1) { *exit_code = -3; return; }
+    if (width * height > (size_t)40000 * 40000) { *exit_code = -4; return; }
+    try {
+        run_patolette(width, height, rgb, weights, palette_size, options, palette, palette_map, exit_code, false, true);
     } catch (const pb_cuda_error &) {
         cudaGetLastError();
         *exit_code = -5;
