@@ -63,10 +63,13 @@ void pb_launch_split_select(const double *d_bucket_sums, const uint32_t *d_class
 // index list by an ascending scan: local.c:216-243, global.c:300-377).
 enum { PB_CLS_BUCKET = 0, PB_CLS_SPLIT = 1, PB_CLS_LUT = 2 };
 size_t pb_scatter_tiles(uint32_t n);
-// d_tile_hist: packed by PbSeg::tbase, (sum of tiles) * nclass u32 ; d_class_start: nseg * (nclass + 1) u32
+// d_tile_hist: pb_scatter_table_words(total_tiles, nseg, nclass) u32, packed by PbSeg::tbase (total_tiles
+// = capacity of the packed tile table, >= sum of the segments' tiles); d_class_start: nseg * (nclass + 1) u32
+size_t pb_scatter_table_words(size_t total_tiles, int nseg, int nclass);
+size_t pb_scatter_chunk_offset(size_t total_tiles, int nclass);
 void pb_launch_class_rank(int cls_mode, int nclass, const PbSeg *d_segs, int nseg, uint32_t max_n,
-                          const uint16_t *d_bucket, const PbSplit *d_split, const uint8_t *d_lut,
-                          uint32_t *d_tile_hist, uint32_t *d_class_start, cudaStream_t st);
+                          size_t total_tiles, const uint16_t *d_bucket, const PbSplit *d_split,
+                          const uint8_t *d_lut, uint32_t *d_tile_hist, uint32_t *d_class_start, cudaStream_t st);
 // ord[dst] = source position (the bucket sort feeding the ordered per-bucket sums)
 void pb_launch_scatter_ord(int cls_mode, int nclass, const PbSeg *d_segs, int nseg, uint32_t max_n,
                            const uint16_t *d_bucket, const PbSplit *d_split, const uint8_t *d_lut,

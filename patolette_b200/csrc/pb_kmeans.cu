@@ -248,7 +248,7 @@ void pb_kmeans_device(const float *d_x0, const float *d_x1, const float *d_x2, c
     uint16_t *d_assign = mem.alloc<uint16_t>(nx);
     uint32_t *d_ord = mem.alloc<uint32_t>(nx);
     const size_t tiles = pb_scatter_tiles((uint32_t)nx);
-    uint32_t *d_tile_hist = mem.alloc<uint32_t>(tiles * (size_t)K + 64);
+    uint32_t *d_tile_hist = mem.alloc<uint32_t>(pb_scatter_table_words(tiles, 1, K));
     uint32_t *d_cstart = mem.alloc<uint32_t>((size_t)K + 1);
     float *d_cen = mem.alloc<float>((size_t)K * 3);
     float *d_sums = mem.alloc<float>((size_t)K * 4);
@@ -272,7 +272,7 @@ void pb_kmeans_device(const float *d_x0, const float *d_x1, const float *d_x2, c
             { PbProfScope _prof("k_assign", st);
             k_assign<<<grid, 256, smem, st>>>(d_x0, d_x1, d_x2, nx, d_cen, K, nx < 20, d_assign, d_stop);
             }
-            pb_launch_class_rank(PB_CLS_BUCKET, K, d_seg, 1, (uint32_t)nx, d_assign, nullptr, nullptr, d_tile_hist,
+            pb_launch_class_rank(PB_CLS_BUCKET, K, d_seg, 1, (uint32_t)nx, tiles, d_assign, nullptr, nullptr, d_tile_hist,
                                  d_cstart, st);
             pb_launch_scatter_ord(PB_CLS_BUCKET, K, d_seg, 1, (uint32_t)nx, d_assign, nullptr, nullptr, d_tile_hist,
                                   d_cstart, d_ord, st);

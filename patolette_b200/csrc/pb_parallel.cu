@@ -194,31 +194,67 @@ __global__ void k_tile_hist(ClsCtx cc, int nclass, const PbSeg *__restrict__ seg
     for (int c = lane; c < nclass; c += 32) out[c] = cnt[c];
 }
 
-// One warp per (segment, class): lanes split the tile range into 32 chunks, scan their
-// chunk serially, warp-scan the chunk totals, then write exclusive per-tile offsets.
-__global__ void k_tile_scan(int nclass, const PbSeg *__restrict__ segs, uint32_t tiles_cap,
-                            uint32_t *__restrict__ tile_hist, uint32_t *__restrict__ class_tot) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+// Exclusive scan of the [tile][class] table down its columns (class-major order of the output), with
+// ROW-wise (coalesced) accesses: (a) column sums of every chunk of SC_CHUNK tiles, (b) scan of the
+// chunk totals (one thread per class), (c) exclusive offsets inside each chunk.
+constexpr int SC_CHUNK = 32;
+__device__ __forceinline__ uint32_t chunk_row0(const PbSeg &sg, int seg) { return sg.tbase / SC_CHUNK + (uint32_t)seg; }
+
+__global__ void __launch_bounds__(256) k_tile_scan_a(int nclass, const PbSeg *__restrict__ segs,
+                                                     const uint32_t *__restrict__ tile_hist,
+                                                     uint32_t *__restrict__ chunk_tot) {
     const int seg = blockIdx.y;
-    if (warp >= nclass) return;
-    const uint32_t ntiles = (segs[seg].n + SC_TILE - 1) / SC_TILE;
-    uint32_t *h = tile_hist + (size_t)segs[seg].tbase * nclass + warp;
-    const uint32_t per = (ntiles + 31) / 32;
-    const uint32_t t0 = min(lane * per, ntiles), t1 = min(t0 + per, ntiles);
-    uint32_t sum = 0;
-    for (uint32_t t = t0; t < t1; t++) sum += h[(size_t)t * nclass];
-    uint32_t incl = sum;
-    for (int o = 1; o < 32; o <<= 1) {
-        uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
+    const PbSeg sg = segs[seg];
+    const uint32_t ntiles = (sg.n + SC_TILE - 1) / SC_TILE;
+    const uint32_t t0 = blockIdx.x * SC_CHUNK;
+    if (t0 >= ntiles) return;
+    const uint32_t t1 = min(t0 + (uint32_t)SC_CHUNK, ntiles);
+    const uint32_t *h = tile_hist + (size_t)sg.tbase * nclass;
+    uint32_t *out = chunk_tot + (size_t)(chunk_row0(sg, seg) + blockIdx.x) * nclass;
+    for (int c = threadIdx.x; c < nclass; c += blockDim.x) {
+        uint32_t sum = 0;
+        for (uint32_t t = t0; t < t1; t++) sum += h[(size_t)t * nclass + c];
+        out[c] = sum;
     }
-    uint32_t run = incl - sum;
-    for (uint32_t t = t0; t < t1; t++) {
-        const uint32_t v = h[(size_t)t * nclass];
-        h[(size_t)t * nclass] = run;
-        run += v;
+}
+
+__global__ void __launch_bounds__(256) k_tile_scan_b(int nclass, const PbSeg *__restrict__ segs,
+                                                     uint32_t *__restrict__ chunk_tot,
+                                                     uint32_t *__restrict__ class_tot) {
+    const int seg = blockIdx.x;
+    const PbSeg sg = segs[seg];
+    const uint32_t ntiles = (sg.n + SC_TILE - 1) / SC_TILE, nchunks = (ntiles + SC_CHUNK - 1) / SC_CHUNK;
+    uint32_t *ct = chunk_tot + (size_t)chunk_row0(sg, seg) * nclass;
+    for (int c = threadIdx.x; c < nclass; c += blockDim.x) {
+        uint32_t run = 0;
+        for (uint32_t k = 0; k < nchunks; k++) {
+            const uint32_t v = ct[(size_t)k * nclass + c];
+            ct[(size_t)k * nclass + c] = run;
+            run += v;
+        }
+        class_tot[(size_t)seg * (nclass + 1) + c] = run;
     }
-    if (lane == 31) class_tot[(size_t)seg * (nclass + 1) + warp] = incl;
+}
+
+__global__ void __launch_bounds__(256) k_tile_scan_c(int nclass, const PbSeg *__restrict__ segs,
+                                                     uint32_t *__restrict__ tile_hist,
+                                                     const uint32_t *__restrict__ chunk_tot) {
+    const int seg = blockIdx.y;
+    const PbSeg sg = segs[seg];
+    const uint32_t ntiles = (sg.n + SC_TILE - 1) / SC_TILE;
+    const uint32_t t0 = blockIdx.x * SC_CHUNK;
+    if (t0 >= ntiles) return;
+    const uint32_t t1 = min(t0 + (uint32_t)SC_CHUNK, ntiles);
+    uint32_t *h = tile_hist + (size_t)sg.tbase * nclass;
+    const uint32_t *in = chunk_tot + (size_t)(chunk_row0(sg, seg) + blockIdx.x) * nclass;
+    for (int c = threadIdx.x; c < nclass; c += blockDim.x) {
+        uint32_t run = in[c];
+        for (uint32_t t = t0; t < t1; t++) {
+            const uint32_t v = h[(size_t)t * nclass + c];
+            h[(size_t)t * nclass + c] = run;
+            run += v;
+        }
+    }
 }
 
 // class_start[seg][c] = seg.lo + sum_{c' < c} tot[c']   (in place over class_tot)
@@ -372,9 +408,15 @@ size_t pb_scatter_tiles(uint32_t n) { return ((size_t)n + SC_TILE - 1) / SC_TILE
 
 static int scatter_warps(int nclass) { return nclass <= 16 ? 8 : (nclass <= 1024 ? 4 : (nclass <= 8192 ? 2 : 1)); }
 
+size_t pb_scatter_chunk_offset(size_t total_tiles, int nclass) { return total_tiles * (size_t)nclass; }
+
+size_t pb_scatter_table_words(size_t total_tiles, int nseg, int nclass) {
+    return (total_tiles + total_tiles / SC_CHUNK + (size_t)nseg + 2) * (size_t)nclass + 64;
+}
+
 void pb_launch_class_rank(int cls_mode, int nclass, const PbSeg *d_segs, int nseg, uint32_t max_n,
-                          const uint16_t *d_bucket, const PbSplit *d_split, const uint8_t *d_lut,
-                          uint32_t *d_tile_hist, uint32_t *d_class_start, cudaStream_t st) {
+                          size_t total_tiles, const uint16_t *d_bucket, const PbSplit *d_split,
+                          const uint8_t *d_lut, uint32_t *d_tile_hist, uint32_t *d_class_start, cudaStream_t st) {
     if (nseg <= 0) return;
     const uint32_t tiles_cap = (uint32_t)pb_scatter_tiles(max_n ? max_n : 1);
     const int warps = scatter_warps(nclass);
@@ -385,9 +427,17 @@ void pb_launch_class_rank(int cls_mode, int nclass, const PbSeg *d_segs, int nse
     { PbProfScope _prof("k_tile_hist", st, false);
     k_tile_hist<<<g1, warps * 32, (size_t)warps * nclass * 4, st>>>(cc, nclass, d_segs, tiles_cap, d_tile_hist);
     }
-    dim3 g2((nclass + 7) / 8, nseg);
+    // the chunk totals live behind the tile table (pb_scatter_table_words reserves the room)
+    uint32_t *d_chunk_tot = d_tile_hist + pb_scatter_chunk_offset(total_tiles, nclass);
+    dim3 g2((tiles_cap + SC_CHUNK - 1) / SC_CHUNK, nseg);
     { PbProfScope _prof("k_tile_scan", st, false);
-    k_tile_scan<<<g2, 256, 0, st>>>(nclass, d_segs, tiles_cap, d_tile_hist, d_class_start);
+    k_tile_scan_a<<<g2, 256, 0, st>>>(nclass, d_segs, d_tile_hist, d_chunk_tot);
+    }
+    { PbProfScope _prof("k_tile_scan", st, false);
+    k_tile_scan_b<<<nseg, 256, 0, st>>>(nclass, d_segs, d_chunk_tot, d_class_start);
+    }
+    { PbProfScope _prof("k_tile_scan", st, false);
+    k_tile_scan_c<<<g2, 256, 0, st>>>(nclass, d_segs, d_tile_hist, d_chunk_tot);
     }
     { PbProfScope _prof("k_class_start", st, false);
     k_class_start<<<nseg, 32, 0, st>>>(nclass, d_segs, d_class_start);

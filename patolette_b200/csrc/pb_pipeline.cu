@@ -228,6 +228,7 @@ struct Quantizer {
 
     static constexpr int MAXB = 64; // clusters evaluated per batch (their 2 * MAXB children get stats)
     size_t max_blocks = 0;         // capacity of the packed ordered-sum block table
+    size_t max_tiles = 0;          // capacity of the packed scatter tile table
 
     void init(size_t n, bool with_weights) {
         N = n;
@@ -254,7 +255,8 @@ struct Quantizer {
         }
         bucket.alloc(N);
         ord.alloc(N);
-        tile_hist.alloc((pb_scatter_tiles((uint32_t)N) + MAXB) * PB_BUCKETS + 64);
+        max_tiles = pb_scatter_tiles((uint32_t)N) + MAXB;
+        tile_hist.alloc(pb_scatter_table_words(max_tiles, MAXB, PB_BUCKETS));
         cstart_b.alloc(MAXB * (PB_BUCKETS + 1));
         cstart_s.alloc(MAXB * 17);
         bsums.alloc(MAXB * PB_BUCKETS * 10);
@@ -300,7 +302,7 @@ struct Quantizer {
         pb_launch_dots_minmax(gq, segs.p, 1, (uint32_t)N, axes.p, split.p, sm_count, st);
         pb_prof_next_bytes(26.0 * N);
         pb_launch_buckets(gq, segs.p, 1, (uint32_t)N, axes.p, split.p, bucket.p, sm_count, st);
-        pb_launch_class_rank(PB_CLS_BUCKET, PB_BUCKETS, segs.p, 1, (uint32_t)N, bucket.p, split.p, lut.p,
+        pb_launch_class_rank(PB_CLS_BUCKET, PB_BUCKETS, segs.p, 1, (uint32_t)N, max_tiles, bucket.p, split.p, lut.p,
                              tile_hist.p, cstart_b.p, st);
         pb_launch_scatter_ord(PB_CLS_BUCKET, PB_BUCKETS, segs.p, 1, (uint32_t)N, bucket.p, split.p, lut.p,
                               tile_hist.p, cstart_b.p, ord.p, st);
@@ -340,7 +342,7 @@ struct Quantizer {
         }
         h2d(lut.p, hl, PB_BUCKETS);
         // global.c:334-356: per-cell ascending index lists == stable scatter by cell
-        pb_launch_class_rank(PB_CLS_LUT, (int)cells, segs.p, 1, (uint32_t)N, bucket.p, split.p, lut.p,
+        pb_launch_class_rank(PB_CLS_LUT, (int)cells, segs.p, 1, (uint32_t)N, max_tiles, bucket.p, split.p, lut.p,
                              tile_hist.p, cstart_s.p, st);
         PbPlanes src = orig;
         src.w = weighted ? wgt.p : nullptr;
@@ -415,14 +417,14 @@ struct Quantizer {
         pb_launch_dots_minmax(bufs, segs.p, nb, max_n, axes.p, split.p, sm_count, st);
         pb_prof_next_bytes(26.0 * tot_n);
         pb_launch_buckets(bufs, segs.p, nb, max_n, axes.p, split.p, bucket.p, sm_count, st);
-        pb_launch_class_rank(PB_CLS_BUCKET, PB_BUCKETS, segs.p, nb, max_n, bucket.p, split.p, lut.p, tile_hist.p,
+        pb_launch_class_rank(PB_CLS_BUCKET, PB_BUCKETS, segs.p, nb, max_n, max_tiles, bucket.p, split.p, lut.p, tile_hist.p,
                              cstart_b.p, st);
         pb_launch_scatter_ord(PB_CLS_BUCKET, PB_BUCKETS, segs.p, nb, max_n, bucket.p, split.p, lut.p, tile_hist.p,
                               cstart_b.p, ord.p, st);
         pb_prof_next_bytes((bpp + 4.0) * tot_n);
         pb_launch_bucket_chains_lq(bufs, segs.p, nb, weighted, ord.p, cstart_b.p, bsums.p, st);
         pb_launch_split_select(bsums.p, cstart_b.p, nb, split.p, st);
-        pb_launch_class_rank(PB_CLS_SPLIT, 2, segs.p, nb, max_n, bucket.p, split.p, lut.p, tile_hist.p, cstart_s.p,
+        pb_launch_class_rank(PB_CLS_SPLIT, 2, segs.p, nb, max_n, max_tiles, bucket.p, split.p, lut.p, tile_hist.p, cstart_s.p,
                              st);
         const PbPlanes swapped[2] = {bufs[1], bufs[0]};
         pb_prof_next_bytes((2 * (bpp + 4.0) + 2.0) * tot_n);
