@@ -4,41 +4,30 @@
 // covariance (math/pca.c:84-97) and distortion (quantize/cluster.c:135-148) - are naive
 // sequential accumulations over up to N pixels in ascending pixel order.  The parity bar is
 // bit-exact, and fl(fl(a+b)+c) != fl(a+fl(b+c)), so a tree / shuffle / atomic reduction is
-// out.  A literal sequential chain costs one dependent DADD (~6 cycles) per pixel per pass:
-// seconds per image.  This file gets the SAME BITS in parallel.
+// out.  A literal sequential chain costs one dependent DADD (~8 cycles) per pixel per pass:
+// seconds per image.  This file gets the SAME BITS in parallel:
 //
-//   Observation.  fl(s + a) rounds the exact sum x = s + a to the grid of the binade that x lies in:
-//   with q = ulp(binade of x), fl(x) = q * rint(x / q).  s is itself a multiple of a quantum that
-//   divides... not necessarily q, but if every partial sum is expressed in ONE fine unit u = 2^(E-52)
-//   (E = the lowest binade met), s = S*u with S an integer, and the step becomes
-//       S' = S + (rint(a / q_i) << k_i),   q_i = 2^(e_i - 52),  k_i = e_i - E          (no tie)
-//   i.e. sequential floating-point accumulation is INTEGER accumulation of terms quantised to the grid
-//   of the binade the running sum is in at that step - and integer addition is associative.  The
-//   binades e_i are not known in advance, but an ordinary (unordered, approximate) prefix sum predicts
-//   them: it is within ~1e-12 of the true running sum, so it lands in the same binade unless the sum
-//   sits that close to a power of two.
+//   Observation.  While the running sum s stays inside one binade [2^e, 2^(e+1)), its ulp
+//   q = 2^(e-52) is constant and s = M*q with M an integer in [2^52, 2^53).  Then
+//       fl(s + a) = (M + rint(a/q)) * q            (exactly, unless a/q is a tie x.5)
+//   i.e. sequential floating-point accumulation degenerates into INTEGER accumulation of the
+//   terms quantised to q - and integer addition is associative.
 //
 //   Speculate, summarise, verify.
-//     S1  k_ord_blocksum : plain f64 sum of every block of OB elements, per chain.
-//     S2  k_ord_prefix   : approximate running total at each block start.
-//     S3  k_ord_summary  : per block and chain: approximate running sum at every ELEMENT -> predicted
-//                          binade e_i and sign; contribution c_i = rint(a_i / q_i) << k_i; and the
-//                          condition for the prediction to be right - the true partial sum after element
-//                          i must lie strictly inside binade e_i:  S_start + C_i in (2^(k_i+52), 2^(k_i+53))
-//                          (mirrored for negative sums).  Every element thus bounds S_start by an
-//                          interval; the block summary is  (sum of c_i, max of lower bounds, min of upper
-//                          bounds)  - an in-order monoid reduction over exact integers.
-//     S3b k_ord_summary_tie : a term that lands exactly half-way is rounded to the EVEN neighbour, which
-//                          depends on the parity of the state: blocks that hold ties (and stay in one
-//                          binade) get both parities (a two-state transducer, still associative).
-//     S4  k_ord_resolve  : one warp per chain walks the blocks in order with the exact state; a block is
-//                          accepted iff lo <= S <= hi, then S += sum.  Otherwise that block is REPLAYED:
-//                          the same idea with the exact binade at 16-element granularity, down to the
-//                          literal sequential loop for the sub-chunk where the prediction breaks.
-//   The prediction only decides SPEED: an accepted block is proven step by step to be what the
-//   sequential loop computes (every rounding used the right grid), everything else is the loop itself.
-//   Sums that hover around zero (off-diagonal covariances of uncorrelated channels change binade every
-//   few elements) validate like any other, as long as a block spans at most 8 binades.
+//     S1  k_ord_blocksum : plain (unordered) f64 sum of every block of OB elements, per chain.
+//     S2  k_ord_prefix   : approximate running total at each block start -> guessed binade e.
+//     S3  k_ord_summary  : per block and chain, with q = 2^(e-52): D = sum of rint(a/q) and the
+//                          min / max over the block's in-order prefix sums (exact integers; an
+//                          in-order monoid reduction), plus a flag if any term was a tie or too
+//                          large to quantise.
+//     S4  k_ord_resolve  : one lane per chain walks the BLOCKS in order holding the exact
+//                          state (M, e).  A block is accepted iff the guess was right, no flag
+//                          is set and 2^52 < M + min .. M + max < 2^53 (every intermediate value
+//                          provably stayed in the binade); then M += D.  Otherwise the lane
+//                          replays that one block element by element - the literal reference loop.
+//   The guess only decides SPEED: every accepted block is proven equal to the sequential
+//   result, every other block IS the sequential loop.  Binade crossings (~log2 n per chain),
+//   ties (~2 ln n) and the first block take the slow path; everything else is parallel.
 //
 // Small clusters skip S1-S3 and run S4 in replay-only mode (one launch).
 #include "pb_common.cuh"
@@ -48,38 +37,28 @@
 namespace {
 
 constexpr int OB = 512;         // elements per summary block
-constexpr int OB_THREADS = 128; // S1: 4 elements per thread
+constexpr int OB_THREADS = 128; // S1/S3: 4 elements per thread
 constexpr int E_NOGUESS = 0x7fffffff;
-constexpr double MAGIC = 6755399441055744.0; // 1.5 * 2^52: (t + MAGIC) - MAGIC == rint(t) for |t| < 2^51
+constexpr double MAGIC = 6755399441055744.0;      // 1.5 * 2^52: (t + MAGIC) - MAGIC == rint(t) for |t| < 2^51
 constexpr double TWO51 = 2251799813685248.0;
 constexpr long long TWO52 = 1LL << 52, TWO53 = 1LL << 53;
-constexpr int MAX_SPREAD = 8; // binades a block may span (states stay below 2^61 in the block's unit)
 
-// 0 accepted, 1 replayed, 2 flagged, 3 state outside the block's unit range, 4 interval, 5 replay rounds,
-// 6 element-wise sub-chunks
-__device__ unsigned long long g_ord_counts[8];
+// blocks accepted from their summary / blocks replayed sequentially (per chain), since last reset
+__device__ unsigned long long g_ord_counts[8]; // 0 accepted, 1 replayed, 2 flag, 3 binade guess, 4 bounds, 5 replay rounds, 6 element-wise sub-chunks
 
-// Effect of a run of terms on the integer state S (in units of 2^(eref-52)): the run is what the
-// sequential loop computes iff lo <= S_start <= hi; afterwards S = S_start + sum.
-struct Span { long long sum, lo, hi; };
-constexpr long long SPAN_INF = 1LL << 61;
-__device__ __forceinline__ Span span_empty() { return Span{0, -SPAN_INF, SPAN_INF}; }
-// in-order concatenation a ++ b: b's condition applies to S_start + a.sum
-__device__ __forceinline__ Span span_cat(const Span &a, const Span &b) {
-    return Span{a.sum + b.sum, max(a.lo, b.lo - a.sum), min(a.hi, b.hi - a.sum)};
-}
-struct Span2 { Span p[2]; }; // by parity of S_start (differs only when the run holds a tie)
-__device__ __forceinline__ Span2 span2_cat(const Span2 &a, const Span2 &b) {
-    Span2 r;
-#pragma unroll
-    for (int p = 0; p < 2; p++) r.p[p] = span_cat(a.p[p], b.p[(p + (int)(a.p[p].sum & 1LL)) & 1]);
-    return r;
-}
+// Quantised effect of a run of terms on the integer state M, for both parities of M at its start:
+// total, and min / max over the in-order prefixes.  The parity only matters through ties: a term
+// that lands exactly half-way (a/q = k + 0.5) is rounded to the EVEN neighbour, i.e. it adds k or
+// k + 1 depending on whether M + (everything before it) + k is even - a two-state transducer whose
+// composition is still associative.  After any element the parity of the state is
+// (p + prefix sum) mod 2, so no extra field is needed.
+struct Tri { double sum, mn, mx; };
+struct Tri2 { Tri p[2]; };
 
 struct OrdSummary {
-    Span2 t;
-    int eref; // binade whose ulp is the unit of t
-    int flag; // 0 usable; bit 0: replay; 2: tie inside a single-binade block -> k_ord_summary_tie
+    Tri2 t;   // quantised terms of the block (integers stored as doubles)
+    int e;    // guessed binade of the running sum across this block
+    int flag; // non-zero: replay the block
 };
 
 enum { KIND_MEAN = 0, KIND_CENTERED = 1 };
@@ -178,17 +157,18 @@ __global__ void __launch_bounds__(OB_THREADS) k_ord_blocksum(PbPlanes b0, PbPlan
     }
 }
 
-// ---- S2: approximate exclusive prefix per chain (in place over the block sums) ------------------
+// ---- S2: approximate exclusive prefix per chain -> guessed binade ------------------------------
 template <int C>
 __global__ void __launch_bounds__(32) k_ord_prefix(const PbSeg *__restrict__ segs, uint32_t blk_cap,
-                                                   double *__restrict__ psum) {
+                                                   const double *__restrict__ psum, OrdSummary *__restrict__ sum) {
     const int seg = blockIdx.y, c = blockIdx.x, lane = threadIdx.x;
     const uint32_t nblk = (segs[seg].n + OB - 1) / OB;
-    double *io = psum + (size_t)segs[seg].bbase * C + c;
+    const double *in = psum + (size_t)segs[seg].bbase * C + c;
+    OrdSummary *out = sum + (size_t)segs[seg].bbase * C + c;
     const uint32_t per = (nblk + 31) / 32;
     const uint32_t b0 = min(lane * per, nblk), b1 = min(b0 + per, nblk);
     double s = 0.0;
-    for (uint32_t b = b0; b < b1; b++) s += io[(size_t)b * C];
+    for (uint32_t b = b0; b < b1; b++) s += in[(size_t)b * C];
     double incl = s;
     for (int o = 1; o < 32; o <<= 1) {
         const double v = __shfl_up_sync(0xffffffffu, incl, o);
@@ -196,338 +176,227 @@ __global__ void __launch_bounds__(32) k_ord_prefix(const PbSeg *__restrict__ seg
     }
     double run = incl - s;
     for (uint32_t b = b0; b < b1; b++) {
-        const double v = io[(size_t)b * C];
-        io[(size_t)b * C] = run;
-        run += v;
+        int e = E_NOGUESS;
+        const double a = fabs(run);
+        if (a > 1e-280 && a < 1e280) e = ilogb(a);
+        out[(size_t)b * C].e = e;
+        run += in[(size_t)b * C];
     }
 }
 
-// ---- S3: block summaries with per-element binade prediction ------------------------------------
+// ---- S3: quantised block summaries --------------------------------------------------------------
+// (sum, min prefix, max prefix) of a sequence of integers is a monoid under in-order concatenation:
+//   (a ++ b).sum = a.sum + b.sum ; (a ++ b).mn = min(a.mn, a.sum + b.mn) ; likewise mx.
+// Each thread owns 4 CONSECUTIVE elements, warps reduce in lane order, warp 0..3 in warp order, so
+// mn / mx are the exact extremes of the running integer sum in element order.
+__device__ __forceinline__ int dparity(double v) { return (int)((long long)v & 1LL); }
+
+// in-order concatenation a ++ b
+__device__ __forceinline__ Tri2 tri2_cat(const Tri2 &a, const Tri2 &b) {
+    Tri2 r;
+#pragma unroll
+    for (int p = 0; p < 2; p++) {
+        const Tri &x = a.p[p];
+        const Tri &y = b.p[(p + dparity(x.sum)) & 1];
+        r.p[p] = Tri{x.sum + y.sum, fmin(x.mn, x.sum + y.mn), fmax(x.mx, x.sum + y.mx)};
+    }
+    return r;
+}
+
+// append one term u = a / q to the run
+__device__ __forceinline__ void tri2_push(Tri2 &t, double u, int &flag, bool first) {
+    const double d = __dsub_rn(__dadd_rn(u, MAGIC), MAGIC); // rint(u), ties to even of u itself
+    const double r = __dsub_rn(u, d);                       // exact remainder
+    flag |= !(fabs(u) < TWO51);                             // unquantisable (or NaN)
+    const bool tie = fabs(r) == 0.5;
+    const double lo = tie ? floor(u) : d;                   // k  (u = k + 0.5)
+#pragma unroll
+    for (int p = 0; p < 2; p++) {
+        Tri &x = t.p[p];
+        // ties go to the neighbour that makes the state even: parity before = p + x.sum
+        const double dd = (tie && (((p + dparity(x.sum) + dparity(lo)) & 1) != 0)) ? lo + 1.0 : lo;
+        const double ps = x.sum + dd;
+        x.mn = first ? ps : fmin(x.mn, ps);
+        x.mx = first ? ps : fmax(x.mx, ps);
+        x.sum = ps;
+    }
+}
+
+// ---- S3a: the common case - no tie anywhere in the block: one parity-independent summary ----------
 constexpr int OS_THREADS = 64; // 8 consecutive elements per thread, two warps per block
-constexpr int OS_PER = OB / OS_THREADS;
-
-__device__ __forceinline__ int exponent_of(double v) { return (int)((__double_as_longlong(v) >> 52) & 0x7ff) - 1023; }
-__device__ __forceinline__ double pow2(int e) { return __longlong_as_double((long long)(e + 1023) << 52); }
-
-// One element: predicted running sum `approx` (after the element) fixes the binade and sign; the term is
-// quantised on that binade's grid and expressed in units of binade eref.  C = thread-local running total.
-//   returns flags: bit 0 unusable, bit 1 tie
-__device__ __forceinline__ int span_push(Span &sp, long long &C, double term, double approx, int eref) {
-    const int e = exponent_of(approx), k = e - eref;
-    int bad = (k < 0) | (k > MAX_SPREAD);
-    const double u = __dmul_rn(term, pow2(52 - e)); // a / q_i, exact (power of two)
-    bad |= !(fabs(u) < 9007199254740992.0);         // beyond 2^53 the state bound is violated anyway (or NaN)
-    const long long d = __double2ll_rn(u);          // rint(u); exact remainder below
-    const int tie = fabs(__dsub_rn(u, (double)d)) == 0.5;
-    const int kk = bad ? 0 : k;
-    C += d << kk;
-    // true partial sum after this element strictly inside the predicted binade (mirrored if negative)
-    const long long A = 1LL << (kk + 52), B = 1LL << (kk + 53);
-    const bool neg = approx < 0;
-    const long long lo = (neg ? -B : A) + 1 - C, hi = (neg ? -A : B) - 1 - C;
-    sp.lo = max(sp.lo, lo);
-    sp.hi = min(sp.hi, hi);
-    sp.sum = C;
-    return bad | (tie << 1);
+struct TriPlain { double sum, mn, mx; };
+__device__ __forceinline__ TriPlain trip_cat(const TriPlain &a, const TriPlain &b) {
+    return TriPlain{a.sum + b.sum, fmin(a.mn, a.sum + b.mn), fmax(a.mx, a.sum + b.mx)};
 }
 
 template <int KIND, bool W>
 __global__ void __launch_bounds__(OS_THREADS) k_ord_summary(PbPlanes b0, PbPlanes b1, const PbSeg *__restrict__ segs,
                                                             const PbStats *__restrict__ stats, uint32_t blk_cap,
-                                                            const double *__restrict__ pstart,
                                                             OrdSummary *__restrict__ sum,
                                                             unsigned int *__restrict__ tie_count,
                                                             uint2 *__restrict__ tie_list) {
     constexpr int C = NChains<KIND>::C;
-    __shared__ double s_wsum[C];            // warp 0's total (approximate prefix hand-over)
-    __shared__ int s_emin[2][C], s_emax[2][C];
-    __shared__ Span s_span[C];              // warp 0's span
+    constexpr int PER = OB / OS_THREADS;
+    __shared__ TriPlain s_tri[OS_THREADS / 32][C];
     __shared__ int s_flag[C];
     const int seg = blockIdx.y;
     const PbSeg sg = segs[seg];
     const uint32_t base = blockIdx.x * OB;
     if (base >= sg.n) return;
     const PbPlanes &P = sg.buf ? b1 : b0;
-    const size_t row = ((size_t)sg.bbase + blockIdx.x) * C;
-    OrdSummary *out = sum + row;
+    OrdSummary *out = sum + ((size_t)sg.bbase + blockIdx.x) * C;
     double m0 = 0, m1 = 0, m2 = 0;
     if (KIND == KIND_CENTERED) { m0 = stats[seg].mean[0]; m1 = stats[seg].mean[1]; m2 = stats[seg].mean[2]; }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t i0 = base + threadIdx.x * OS_PER; // this thread's consecutive elements
-    if (threadIdx.x < C) s_flag[threadIdx.x] = 0;
-
-    // ---- phase 1: approximate running sum at the start of this thread's elements -----------------
-    double tstart[C];
-    {
-        double tl[C];
-#pragma unroll
-        for (int c = 0; c < C; c++) tl[c] = 0.0;
-#pragma unroll
-        for (int k = 0; k < OS_PER; k++) {
-            if (i0 + k < sg.n) {
-                const size_t p = (size_t)sg.lo + i0 + k;
-                double t[C];
-                terms_all<KIND, W>(W ? P.w[p] : 1.0, P.c[0][p], P.c[1][p], P.c[2][p], m0, m1, m2, t);
-#pragma unroll
-                for (int c = 0; c < C; c++) tl[c] += t[c];
-            }
-        }
-#pragma unroll
-        for (int c = 0; c < C; c++) {
-            double incl = tl[c];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const double v = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += v;
-            }
-            if (warp == 0 && lane == 31) s_wsum[c] = incl;
-            tstart[c] = incl - tl[c];
-        }
-        __syncthreads();
-#pragma unroll
-        for (int c = 0; c < C; c++) tstart[c] += pstart[row + c] + (warp ? s_wsum[c] : 0.0);
-    }
-    // binade range of the predicted running sums over the block
-    {
-        int emin[C], emax[C];
-        double run[C];
-#pragma unroll
-        for (int c = 0; c < C; c++) { emin[c] = 1 << 20; emax[c] = -(1 << 20); run[c] = tstart[c]; }
-#pragma unroll
-        for (int k = 0; k < OS_PER; k++) {
-            if (i0 + k < sg.n) {
-                const size_t p = (size_t)sg.lo + i0 + k;
-                double t[C];
-                terms_all<KIND, W>(W ? P.w[p] : 1.0, P.c[0][p], P.c[1][p], P.c[2][p], m0, m1, m2, t);
-#pragma unroll
-                for (int c = 0; c < C; c++) {
-                    run[c] += t[c];
-                    const int e = exponent_of(run[c]);
-                    emin[c] = min(emin[c], e);
-                    emax[c] = max(emax[c], e);
-                }
-            }
-        }
-#pragma unroll
-        for (int c = 0; c < C; c++) {
-#pragma unroll
-            for (int o = 16; o; o >>= 1) {
-                emin[c] = min(emin[c], __shfl_xor_sync(0xffffffffu, emin[c], o));
-                emax[c] = max(emax[c], __shfl_xor_sync(0xffffffffu, emax[c], o));
-            }
-            if (lane == 0) { s_emin[warp][c] = emin[c]; s_emax[warp][c] = emax[c]; }
-        }
-        __syncthreads();
-    }
-    // ---- phase 2: quantise on the predicted grids, in units of the lowest binade ------------------
-    int eref[C], flag[C];
-    bool uniform[C]; // the whole block is predicted to stay in one binade
-    Span sp[C];
+    double scale[C];
+    TriPlain tri[C];
+    int flag[C]; // bit 0: unusable (no guess / unquantisable term), bit 1: a tie -> needs the tie-aware pass
 #pragma unroll
     for (int c = 0; c < C; c++) {
-        const int lo = min(s_emin[0][c], s_emin[1][c]), hi = max(s_emax[0][c], s_emax[1][c]);
-        eref[c] = lo;
-        uniform[c] = lo == hi;
-        // zero / subnormal / non-finite predictions, or too wide a range: replay
-        flag[c] = (lo < -1000) | (hi > 1000) | (hi - lo > MAX_SPREAD);
-        if (flag[c]) eref[c] = 0;
-        sp[c] = span_empty();
+        const int e = out[c].e;
+        flag[c] = e == E_NOGUESS;
+        scale[c] = flag[c] ? 0.0 : scalbn(1.0, 52 - e); // 1 / q
+        tri[c] = TriPlain{0.0, 1e300, -1e300};          // empty run
     }
-    {
-        double run[C];
-        long long Cacc[C];
+    if (threadIdx.x < C) s_flag[threadIdx.x] = 0;
+    __syncthreads();
 #pragma unroll
-        for (int c = 0; c < C; c++) { run[c] = tstart[c]; Cacc[c] = 0; }
+    for (int k = 0; k < PER; k++) {
+        const uint32_t i = base + threadIdx.x * PER + k; // consecutive elements per thread
+        if (i < sg.n) {
+            const size_t p = (size_t)sg.lo + i;
+            double t[C];
+            terms_all<KIND, W>(W ? P.w[p] : 1.0, P.c[0][p], P.c[1][p], P.c[2][p], m0, m1, m2, t);
 #pragma unroll
-        for (int k = 0; k < OS_PER; k++) {
-            if (i0 + k < sg.n) {
-                const size_t p = (size_t)sg.lo + i0 + k;
-                double t[C];
-                terms_all<KIND, W>(W ? P.w[p] : 1.0, P.c[0][p], P.c[1][p], P.c[2][p], m0, m1, m2, t);
-#pragma unroll
-                for (int c = 0; c < C; c++) {
-                    run[c] += t[c]; // same operations as phase 1: same predictions
-                    const int f = span_push(sp[c], Cacc[c], t[c], run[c], eref[c]);
-                    // a tie can be resolved by the parity transducer only when the block stays in one binade
-                    flag[c] |= (f & 1) | ((f & 2) ? (uniform[c] ? 2 : 1) : 0);
-                }
+            for (int c = 0; c < C; c++) {
+                const double u = __dmul_rn(t[c], scale[c]);             // a / q, exact (power of two)
+                const double d = __dsub_rn(__dadd_rn(u, MAGIC), MAGIC); // rint(u)
+                flag[c] |= (!(fabs(u) < TWO51) ? 1 : 0) | (fabs(__dsub_rn(u, d)) == 0.5 ? 2 : 0);
+                const double ps = tri[c].sum + d;
+                tri[c] = TriPlain{ps, fmin(tri[c].mn, ps), fmax(tri[c].mx, ps)};
             }
         }
     }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int c = 0; c < C; c++) {
         if (flag[c]) atomicOr(&s_flag[c], flag[c]);
-        Span v = sp[c];
+        TriPlain v = tri[c];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { // in-order tree: lane i absorbs lane i + o
-            Span r;
+            TriPlain r;
             r.sum = __shfl_down_sync(0xffffffffu, v.sum, o);
-            r.lo = __shfl_down_sync(0xffffffffu, v.lo, o);
-            r.hi = __shfl_down_sync(0xffffffffu, v.hi, o);
-            if ((lane & (2 * o - 1)) == 0) v = span_cat(v, r);
+            r.mn = __shfl_down_sync(0xffffffffu, v.mn, o);
+            r.mx = __shfl_down_sync(0xffffffffu, v.mx, o);
+            if ((lane & (2 * o - 1)) == 0) v = trip_cat(v, r);
         }
-        if (warp == 0 && lane == 0) s_span[c] = v;
-        sp[c] = v;
+        if (lane == 0) s_tri[warp][c] = v;
     }
     __syncthreads();
-    if (warp == 1 && lane == 0) {
+    if (threadIdx.x < C) {
+        TriPlain v = s_tri[0][threadIdx.x];
+        for (int w = 1; w < OS_THREADS / 32; w++) v = trip_cat(v, s_tri[w][threadIdx.x]);
+        const Tri tt{v.sum, v.mn, v.mx};
+        out[threadIdx.x].t.p[0] = tt;
+        out[threadIdx.x].t.p[1] = tt;
+        out[threadIdx.x].flag = s_flag[threadIdx.x]; // 0 ok, odd: replay, 2: redo with k_ord_summary_tie
+    }
+    if (threadIdx.x == 0) { // blocks holding a tie go on the work list of the tie-aware pass
         bool tie = false;
-#pragma unroll
-        for (int c = 0; c < C; c++) {
-            const Span v = span_cat(s_span[c], sp[c]);
-            out[c].t.p[0] = v;
-            out[c].t.p[1] = v;
-            out[c].eref = eref[c];
-            out[c].flag = s_flag[c];
-            tie |= s_flag[c] == 2;
-        }
+        for (int c = 0; c < C; c++) tie |= s_flag[c] == 2;
         if (tie) tie_list[atomicAdd(tie_count, 1u)] = make_uint2((unsigned)seg, blockIdx.x);
     }
-    // blocks shorter than one warp's share have no warp-1 elements: warp 1 spans are empty, fine
 }
 
-// ---- S3b: single-binade blocks that hold a tie: both start parities ------------------------------
-// (the parity of the state decides which neighbour a half-way term is rounded to)
-__device__ __forceinline__ int span2_push(Span2 &sp, long long C[2], double term, double approx, int eref) {
-    const int e = exponent_of(approx);
-    int bad = e != eref;
-    const double u = __dmul_rn(term, pow2(52 - eref));
-    bad |= !(fabs(u) < 9007199254740992.0);
-    const long long d = __double2ll_rn(u);
-    const bool tie = fabs(__dsub_rn(u, (double)d)) == 0.5;
-    const long long lo_int = tie ? (long long)floor(u) : d; // k of u = k + 0.5
-    const bool neg = approx < 0;
-#pragma unroll
-    for (int p = 0; p < 2; p++) {
-        // state before this element has parity p + C[p]; a tie goes to the neighbour that makes it even
-        const long long dd = (tie && (((p + C[p] + lo_int) & 1LL) != 0)) ? lo_int + 1 : lo_int;
-        C[p] += dd;
-        const long long lo = (neg ? -TWO53 : TWO52) + 1 - C[p], hi = (neg ? -TWO52 : TWO53) - 1 - C[p];
-        sp.p[p].lo = max(sp.p[p].lo, lo);
-        sp.p[p].hi = min(sp.p[p].hi, hi);
-        sp.p[p].sum = C[p];
-    }
-    return bad;
-}
-
+// ---- S3b: blocks that contain a tie: both start parities (the two-state transducer) --------------
 template <int KIND, bool W>
-__global__ void __launch_bounds__(OS_THREADS) k_ord_summary_tie(PbPlanes b0, PbPlanes b1, const PbSeg *__restrict__ segs,
+__global__ void __launch_bounds__(OB_THREADS) k_ord_summary_tie(PbPlanes b0, PbPlanes b1, const PbSeg *__restrict__ segs,
                                                                 const PbStats *__restrict__ stats, uint32_t blk_cap,
-                                                                const double *__restrict__ pstart,
                                                                 OrdSummary *__restrict__ sum,
                                                                 const unsigned int *__restrict__ tie_count,
                                                                 const uint2 *__restrict__ tie_list) {
     constexpr int C = NChains<KIND>::C;
-    __shared__ double s_wsum[C];
-    __shared__ Span2 s_span[C];
+    constexpr int PER = OB / OB_THREADS;
+    __shared__ Tri2 s_tri[OB_THREADS / 32][C];
     __shared__ int s_flag[C];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (unsigned int item = blockIdx.x; item < *tie_count; item += gridDim.x) { // persistent CTAs over the work list
-        const int seg = (int)tie_list[item].x;
-        const uint32_t blk = tie_list[item].y;
-        const PbSeg sg = segs[seg];
-        const uint32_t base = blk * OB;
-        const PbPlanes &P = sg.buf ? b1 : b0;
-        const size_t row = ((size_t)sg.bbase + blk) * C;
-        OrdSummary *out = sum + row;
-        double m0 = 0, m1 = 0, m2 = 0;
-        if (KIND == KIND_CENTERED) { m0 = stats[seg].mean[0]; m1 = stats[seg].mean[1]; m2 = stats[seg].mean[2]; }
-        const uint32_t i0 = base + threadIdx.x * OS_PER;
-        __syncthreads();
-        if (threadIdx.x < C) s_flag[threadIdx.x] = 0;
-        bool need[C]; // only the chains that actually hold a tie are redone (uniform across the CTA)
-        int eref[C];
+  for (unsigned int item = blockIdx.x; item < *tie_count; item += gridDim.x) { // persistent CTAs over the work list
+    const int seg = (int)tie_list[item].x;
+    const uint32_t blk = tie_list[item].y;
+    const PbSeg sg = segs[seg];
+    const uint32_t base = blk * OB;
+    const PbPlanes &P = sg.buf ? b1 : b0;
+    OrdSummary *out = sum + ((size_t)sg.bbase + blk) * C;
+    __syncthreads();
+    double m0 = 0, m1 = 0, m2 = 0;
+    if (KIND == KIND_CENTERED) { m0 = stats[seg].mean[0]; m1 = stats[seg].mean[1]; m2 = stats[seg].mean[2]; }
+    double scale[C];
+    Tri2 tri[C];
+    int flag[C];
+    bool need[C]; // only the chains that actually hold a tie are redone (uniform across the CTA)
+    bool any = false;
 #pragma unroll
-        for (int c = 0; c < C; c++) { need[c] = out[c].flag == 2; eref[c] = out[c].eref; }
-        // the same approximate running sum as k_ord_summary (same operations, same order)
-        double tstart[C];
-        {
-            double tl[C];
+    for (int c = 0; c < C; c++) {
+        const int e = out[c].e;
+        need[c] = out[c].flag == 2;
+        flag[c] = e == E_NOGUESS;
+        scale[c] = flag[c] ? 0.0 : scalbn(1.0, 52 - e); // 1 / q
+        tri[c].p[0] = tri[c].p[1] = Tri{0.0, 1e300, -1e300}; // empty run
+    }
+    if (threadIdx.x < C) s_flag[threadIdx.x] = 0;
+    __syncthreads();
 #pragma unroll
-            for (int c = 0; c < C; c++) tl[c] = 0.0;
+    for (int k = 0; k < PER; k++) {
+        const uint32_t i = base + threadIdx.x * PER + k; // consecutive elements per thread
+        if (i < sg.n) {
+            const size_t p = (size_t)sg.lo + i;
+            double t[C];
+            terms_all<KIND, W>(W ? P.w[p] : 1.0, P.c[0][p], P.c[1][p], P.c[2][p], m0, m1, m2, t);
 #pragma unroll
-            for (int k = 0; k < OS_PER; k++) {
-                if (i0 + k < sg.n) {
-                    const size_t p = (size_t)sg.lo + i0 + k;
-                    double t[C];
-                    terms_all<KIND, W>(W ? P.w[p] : 1.0, P.c[0][p], P.c[1][p], P.c[2][p], m0, m1, m2, t);
-#pragma unroll
-                    for (int c = 0; c < C; c++) tl[c] += t[c];
-                }
-            }
-#pragma unroll
-            for (int c = 0; c < C; c++) {
-                double incl = tl[c];
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const double v = __shfl_up_sync(0xffffffffu, incl, o);
-                    if (lane >= o) incl += v;
-                }
-                if (warp == 0 && lane == 31) s_wsum[c] = incl;
-                tstart[c] = incl - tl[c];
-            }
-            __syncthreads();
-#pragma unroll
-            for (int c = 0; c < C; c++) tstart[c] += pstart[row + c] + (warp ? s_wsum[c] : 0.0);
-        }
-        Span2 sp[C];
-        int flag[C];
-        {
-            double run[C];
-            long long Cacc[C][2];
-#pragma unroll
-            for (int c = 0; c < C; c++) {
-                run[c] = tstart[c]; Cacc[c][0] = Cacc[c][1] = 0; flag[c] = 0;
-                sp[c].p[0] = sp[c].p[1] = span_empty();
-            }
-#pragma unroll
-            for (int k = 0; k < OS_PER; k++) {
-                if (i0 + k < sg.n) {
-                    const size_t p = (size_t)sg.lo + i0 + k;
-                    double t[C];
-                    terms_all<KIND, W>(W ? P.w[p] : 1.0, P.c[0][p], P.c[1][p], P.c[2][p], m0, m1, m2, t);
-#pragma unroll
-                    for (int c = 0; c < C; c++) {
-                        run[c] += t[c];
-                        if (need[c]) flag[c] |= span2_push(sp[c], Cacc[c], t[c], run[c], eref[c]);
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int c = 0; c < C; c++) {
-            if (!need[c]) continue;
-            if (flag[c]) atomicOr(&s_flag[c], 1);
-            Span2 v = sp[c];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                Span2 r;
-#pragma unroll
-                for (int p = 0; p < 2; p++) {
-                    r.p[p].sum = __shfl_down_sync(0xffffffffu, v.p[p].sum, o);
-                    r.p[p].lo = __shfl_down_sync(0xffffffffu, v.p[p].lo, o);
-                    r.p[p].hi = __shfl_down_sync(0xffffffffu, v.p[p].hi, o);
-                }
-                if ((lane & (2 * o - 1)) == 0) v = span2_cat(v, r);
-            }
-            if (warp == 0 && lane == 0) s_span[c] = v;
-            sp[c] = v;
-        }
-        __syncthreads();
-        if (warp == 1 && lane == 0) {
-#pragma unroll
-            for (int c = 0; c < C; c++) {
-                if (!need[c]) continue;
-                out[c].t = span2_cat(s_span[c], sp[c]);
-                out[c].flag = s_flag[c];
-            }
+            for (int c = 0; c < C; c++)
+                if (need[c]) tri2_push(tri[c], __dmul_rn(t[c], scale[c]) /* a / q, exact */, flag[c], !any);
+            any = true;
         }
     }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+        if (!need[c]) continue;
+        if (flag[c]) atomicOr(&s_flag[c], 1);
+        Tri2 v = tri[c];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { // in-order tree: lane i absorbs lane i + o
+            Tri2 r;
+#pragma unroll
+            for (int p = 0; p < 2; p++) {
+                r.p[p].sum = __shfl_down_sync(0xffffffffu, v.p[p].sum, o);
+                r.p[p].mn = __shfl_down_sync(0xffffffffu, v.p[p].mn, o);
+                r.p[p].mx = __shfl_down_sync(0xffffffffu, v.p[p].mx, o);
+            }
+            if ((lane & (2 * o - 1)) == 0) v = tri2_cat(v, r);
+        }
+        if (lane == 0) s_tri[warp][c] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < C && out[threadIdx.x].flag == 2) { // == need[threadIdx.x]
+        Tri2 v = s_tri[0][threadIdx.x];
+        for (int w = 1; w < OB_THREADS / 32; w++) v = tri2_cat(v, s_tri[w][threadIdx.x]);
+        out[threadIdx.x].t = v;
+        out[threadIdx.x].flag = s_flag[threadIdx.x];
+    }
+  }
 }
 
 // ---- S4: ordered resolve ---------------------------------------------------------------------------
-// One CTA per cluster, one WARP per chain; the warp's state is the exact running sum s (uniform across
-// lanes).  Summaries are fetched 32 blocks at a time (lane b holds block b) and applied in order.
+// One CTA per cluster, one WARP per chain.  The warp's state is the exact running sum s (uniform
+// across lanes).  Blocks are taken 32 at a time, lane b holding the summary of block b: an in-order
+// warp scan of the block totals gives every lane the exact state its block would start from IF all
+// earlier blocks are accepted, each lane validates its own block against that state, and a ballot
+// finds the first block that cannot be accepted.  Everything before it is applied in one step; that
+// block is replayed; the walk resumes behind it.
+//
+// Replaying a block uses the same idea one level down, now with the EXACT binade (s is known):
+// each lane quantises its 16 consecutive elements, the warp scans / validates / ballots, accepted
+// sub-chunks are applied at once and only the sub-chunk where the binade changes (or a tie sits) is
+// added element by element - the literal reference loop, 16 elements long.
 constexpr int SUB = OB / 32; // elements per lane in a replay
 
 __device__ __forceinline__ long long warp_incl_scan(long long v, int lane) {
@@ -537,6 +406,77 @@ __device__ __forceinline__ long long warp_incl_scan(long long v, int lane) {
         if (lane >= o) v += u;
     }
     return v;
+}
+
+// Applies the items [next, limit) held one per lane (usable iff ok) to the state s as far as they
+// validate.  Returns the first index that does not (limit if all do) and updates s.  Item l checks
+// its own prefix extremes against the exact state it would start from if everything before it is
+// accepted; that state comes from an in-order warp scan of the monoid.  `validate` turns the scanned
+// run of a lane into (usable, total).
+__device__ __forceinline__ uint32_t finish_run(double &s, long long bits, long long M, bool negs, bool mine, bool ok,
+                                              long long tot, double rmn, double rmx, uint32_t next, uint32_t limit) {
+    const long long lo = rmn > 9e299 ? 0 : (long long)rmn, hi = rmx < -9e299 ? 0 : (long long)rmx;
+    const long long vmin = negs ? M - hi : M + lo, vmax = negs ? M - lo : M + hi;
+    // every prefix up to and including this item strictly inside (2^52, 2^53): the unrounded value
+    // must itself stay inside the binade
+    const bool valid = ok && vmin > TWO52 && vmax < TWO53;
+    const unsigned fails = __ballot_sync(0xffffffffu, mine && !valid);
+    const uint32_t f = fails ? (uint32_t)(__ffs(fails) - 1) : limit;
+    if (f > next) {
+        const long long acc = __shfl_sync(0xffffffffu, tot, (int)f - 1); // inclusive total of lane f - 1
+        const long long M2 = negs ? M - acc : M + acc;
+        s = __longlong_as_double((bits & 0xfff0000000000000LL) | (M2 & 0x000fffffffffffffLL));
+    }
+    return f;
+}
+
+// items whose effect does not depend on the start parity (no tie inside): a 3-double scan
+__device__ __forceinline__ uint32_t apply_run_plain(double &s, int lane, uint32_t next, uint32_t limit, bool ok,
+                                                   const TriPlain &item) {
+    const long long bits = __double_as_longlong(s);
+    const long long M = (bits & 0x000fffffffffffffLL) | TWO52; // |s| / q
+    const bool mine = lane >= (int)next && lane < (int)limit;
+    TriPlain run = (mine && ok) ? item : TriPlain{0.0, 1e300, -1e300};
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        TriPlain up;
+        up.sum = __shfl_up_sync(0xffffffffu, run.sum, o);
+        up.mn = __shfl_up_sync(0xffffffffu, run.mn, o);
+        up.mx = __shfl_up_sync(0xffffffffu, run.mx, o);
+        if (lane >= o) run = trip_cat(up, run);
+    }
+    return finish_run(s, bits, M, bits < 0, mine, ok, (long long)run.sum, run.mn, run.mx, next, limit);
+}
+
+// general items: the parity each one starts from depends on the items before it, so the warp scans
+// the two-parity monoid
+__device__ __forceinline__ uint32_t apply_run(double &s, int lane, uint32_t next, uint32_t limit, bool ok,
+                                             const Tri2 &item) {
+    const long long bits = __double_as_longlong(s);
+    const long long M = (bits & 0x000fffffffffffffLL) | TWO52; // |s| / q
+    const int p0 = (int)(M & 1LL);
+    const bool mine = lane >= (int)next && lane < (int)limit;
+    const bool parity_matters = mine && ok && (item.p[0].sum != item.p[1].sum || item.p[0].mn != item.p[1].mn ||
+                                               item.p[0].mx != item.p[1].mx);
+    if (!__any_sync(0xffffffffu, parity_matters))
+        return apply_run_plain(s, lane, next, limit, ok, TriPlain{item.p[0].sum, item.p[0].mn, item.p[0].mx});
+    Tri2 inc;
+    if (mine && ok) inc = item;
+    else inc.p[0] = inc.p[1] = Tri{0.0, 1e300, -1e300};
+    Tri2 run = inc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        Tri2 up;
+#pragma unroll
+        for (int p = 0; p < 2; p++) {
+            up.p[p].sum = __shfl_up_sync(0xffffffffu, run.p[p].sum, o);
+            up.p[p].mn = __shfl_up_sync(0xffffffffu, run.p[p].mn, o);
+            up.p[p].mx = __shfl_up_sync(0xffffffffu, run.p[p].mx, o);
+        }
+        if (lane >= o) run = tri2_cat(up, run);
+    }
+    // run.p[p0] = items next..lane applied to a state of parity p0: prefix extremes included
+    return finish_run(s, bits, M, bits < 0, mine, ok, (long long)run.p[p0].sum, run.p[p0].mn, run.p[p0].mx, next, limit);
 }
 
 // One lane's 16 elements quantised against binade e: total, prefix extremes, exclusive prefix of the
@@ -650,17 +590,6 @@ __device__ __forceinline__ double replay_block(const PbPlanes &P, size_t first, 
     return s;
 }
 
-// exact state -> integer in units of 2^(eref-52); false if it is not representable there
-__device__ __forceinline__ bool state_to_units(double s, int eref, long long &S) {
-    const long long bits = __double_as_longlong(s);
-    if ((bits << 1) == 0) { S = 0; return true; }
-    const int es = (int)((bits >> 52) & 0x7ff) - 1023, k0 = es - eref;
-    if (es < -1000 || es > 1000 || k0 < 0 || k0 > MAX_SPREAD + 1) return false;
-    const long long M = ((bits & 0x000fffffffffffffLL) | TWO52) << k0;
-    S = bits < 0 ? -M : M;
-    return true;
-}
-
 template <int KIND, bool W>
 __global__ void __launch_bounds__(32 * NChains<KIND>::C) k_ord_resolve(PbPlanes b0, PbPlanes b1,
                                                                        const PbSeg *__restrict__ segs,
@@ -682,36 +611,32 @@ __global__ void __launch_bounds__(32 * NChains<KIND>::C) k_ord_resolve(PbPlanes 
     for (uint32_t g0 = 0; g0 < nblk; g0 += 32) {
         const uint32_t gcnt = min(32u, nblk - g0);
         OrdSummary sm;
-        sm.t.p[0] = sm.t.p[1] = span_empty();
-        sm.eref = 0;
+        sm.t.p[0] = sm.t.p[1] = Tri{0.0, 0.0, 0.0};
+        sm.e = E_NOGUESS;
         sm.flag = 1;
         if (use_summaries && lane < (int)gcnt) sm = srow[(size_t)(g0 + lane) * C];
-        for (uint32_t b = 0; b < gcnt; b++) {
-            bool accept = false;
-            if (use_summaries) {
-                const int flag = __shfl_sync(0xffffffffu, sm.flag, (int)b), eref = __shfl_sync(0xffffffffu, sm.eref, (int)b);
-                long long S = 0;
-                int why = 0;
-                if (flag == 0) {
-                    if (state_to_units(s, eref, S)) {
-                        const int p = (int)(S & 1LL);
-                        const long long lo = __shfl_sync(0xffffffffu, p ? sm.t.p[1].lo : sm.t.p[0].lo, (int)b);
-                        const long long hi = __shfl_sync(0xffffffffu, p ? sm.t.p[1].hi : sm.t.p[0].hi, (int)b);
-                        if (S >= lo && S <= hi) {
-                            const long long d = __shfl_sync(0xffffffffu, p ? sm.t.p[1].sum : sm.t.p[0].sum, (int)b);
-                            s = __dmul_rn((double)(S + d), pow2(eref - 52)); // exact: a valid double by construction
-                            accept = true;
-                        } else why = 2;
-                    } else why = 1;
+        uint32_t next = 0;
+        while (next < gcnt) {
+            const long long bits = __double_as_longlong(s);
+            const int es = (int)((bits >> 52) & 0x7ff) - 1023;
+            const bool ok = use_summaries && sm.flag == 0 && sm.e == es && es > -1000 && es < 1000;
+            const uint32_t f = apply_run(s, lane, next, gcnt, ok, sm.t);
+            n_acc += f - next;
+            if (f < gcnt && use_summaries) {
+                const int fl = __shfl_sync(0xffffffffu, sm.flag, (int)f), fe = __shfl_sync(0xffffffffu, sm.e, (int)f);
+                if (lane == 0) {
+                    if (fl) n_why[0]++;
+                    else if (fe != es) n_why[1]++;
+                    else n_why[2]++;
                 }
-                if (!accept) n_why[why]++;
             }
-            if (accept) {
-                n_acc++;
-            } else {
-                const uint32_t base = (g0 + b) * OB;
+            if (f < gcnt) {
+                const uint32_t base = (g0 + f) * OB;
                 s = replay_block<KIND, W>(P, (size_t)sg.lo + base, min((uint32_t)OB, n - base), chain, m0, m1, m2, s, lane, hover);
                 n_rep++;
+                next = f + 1;
+            } else {
+                next = gcnt;
             }
         }
     }
@@ -749,17 +674,19 @@ void launch_pass(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t
     OrdSummary *sum = (OrdSummary *)((char *)d_scratch + (size_t)total_blocks * 7 * sizeof(double));
     uint2 *tie_list = (uint2 *)((char *)d_scratch + (size_t)total_blocks * 7 * (sizeof(double) + sizeof(OrdSummary)));
     unsigned int *tie_count = (unsigned int *)(tie_list + total_blocks);
+    const double bytes = 0; // set by the caller through pb_prof_next_bytes for the resolve kernel
+    (void)bytes;
     if (speculative) {
         dim3 grid(blk_cap, nseg);
         { PbProfScope p(KIND == KIND_MEAN ? "k_ord_blocksum_mean" : "k_ord_blocksum_centered", st, false);
           k_ord_blocksum<KIND, W><<<grid, OB_THREADS, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, blk_cap, psum); }
         { PbProfScope p("k_ord_prefix", st, false);
-          k_ord_prefix<C><<<dim3(C, nseg), 32, 0, st>>>(d_segs, blk_cap, psum); }
+          k_ord_prefix<C><<<dim3(C, nseg), 32, 0, st>>>(d_segs, blk_cap, psum, sum); }
         PB_CUDA_OK(cudaMemsetAsync(tie_count, 0, sizeof(unsigned int), st));
         { PbProfScope p(KIND == KIND_MEAN ? "k_ord_summary_mean" : "k_ord_summary_centered", st);
-          k_ord_summary<KIND, W><<<grid, OS_THREADS, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, blk_cap, psum, sum, tie_count, tie_list); }
+          k_ord_summary<KIND, W><<<grid, OS_THREADS, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, blk_cap, sum, tie_count, tie_list); }
         { PbProfScope p("k_ord_summary_tie", st, false);
-          k_ord_summary_tie<KIND, W><<<148 * 4, OS_THREADS, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, blk_cap, psum, sum, tie_count, tie_list); }
+          k_ord_summary_tie<KIND, W><<<148 * 4, OB_THREADS, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, blk_cap, sum, tie_count, tie_list); }
     }
     { PbProfScope p(KIND == KIND_MEAN ? "k_ord_resolve_mean" : "k_ord_resolve_centered", st, !speculative);
       k_ord_resolve<KIND, W><<<nseg, 32 * C, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, blk_cap, sum, speculative); }
