@@ -5,64 +5,64 @@
 // sequential accumulations over up to N pixels in ascending pixel order.  The parity bar is
 // bit-exact, and fl(fl(a+b)+c) != fl(a+fl(b+c)), so a tree / shuffle / atomic reduction is
 // out.  A literal sequential chain costs one dependent DADD (~8 cycles) per pixel per pass:
-// seconds per image.  This file gets the SAME BITS in parallel:
-//
-//   Observation.  While the running sum s stays inside one binade [2^e, 2^(e+1)), its ulp
-//   q = 2^(e-52) is constant and s = M*q with M an integer in [2^52, 2^53).  Then
-//       fl(s + a) = (M + rint(a/q)) * q            (exactly, unless a/q is a tie x.5)
-//   i.e. sequential floating-point accumulation degenerates into INTEGER accumulation of the
-//   terms quantised to q - and integer addition is associative.
+// seconds per image.  This file gets the SAME BITS in parallel.  The arithmetic (and the proof
+// obligations) live in pb_span.h, which also compiles on the host: tests/native/test_span.cpp
+// checks it against the literal loop on adversarial data.
 //
 //   Speculate, summarise, verify.
 //     S1  k_ord_blocksum : plain (unordered) f64 sum of every block of OB elements, per chain.
-//     S2  k_ord_prefix   : approximate running total at each block start -> guessed binade e.
-//     S3  k_ord_summary  : per block and chain, with q = 2^(e-52): D = sum of rint(a/q) and the
-//                          min / max over the block's in-order prefix sums (exact integers; an
-//                          in-order monoid reduction), plus a flag if any term was a tie or too
-//                          large to quantise.
-//     S4  k_ord_resolve  : one lane per chain walks the BLOCKS in order holding the exact
-//                          state (M, e).  A block is accepted iff the guess was right, no flag
-//                          is set and 2^52 < M + min .. M + max < 2^53 (every intermediate value
-//                          provably stayed in the binade); then M += D.  Otherwise the lane
-//                          replays that one block element by element - the literal reference loop.
-//   The guess only decides SPEED: every accepted block is proven equal to the sequential
-//   result, every other block IS the sequential loop.  Binade crossings (~log2 n per chain),
-//   ties (~2 ln n) and the first block take the slow path; everything else is parallel.
+//     S2  k_ord_prefix   : approximate running total at each block start.
+//     S3  k_ord_summary  : approximate running sum at every ELEMENT -> predicted binade of every
+//                          partial sum; the block's unit is the ulp of the lowest one.  Each thread
+//                          turns its 8 consecutive elements into a span (integer translation +
+//                          interval of start states for which every prediction is right), spans are
+//                          concatenated in element order (an associative monoid): one record per block.
+//     S3b k_ord_summary2 : blocks in which a step depends on the parity of the state (a tie, or a step
+//                          up from the lowest binade) are redone for both parities (work list).
+//     S4  k_ord_resolve  : one warp per chain walks the blocks in order with the exact state: 32 block
+//                          records at a time, in-order warp scan of the spans, ballot -> the first block
+//                          whose interval does not hold; everything before it is applied in one step,
+//                          that block is REPLAYED: the same idea with the exact binade at 16-element
+//                          granularity, down to the literal sequential loop for the sub-chunk where a
+//                          prediction breaks.
+//   The predictions only decide SPEED: an accepted block is proven step by step to be what the
+//   sequential loop computes (every rounding used the right grid), everything else is the loop itself.
 //
 // Small clusters skip S1-S3 and run S4 in replay-only mode (one launch).
 #include "pb_common.cuh"
 #include "pb_kernels.h"
 #include "pb_prof.h"
+#include "pb_span.h"
 
 namespace {
 
 constexpr int OB = 512;         // elements per summary block
-constexpr int OB_THREADS = 128; // S1/S3: 4 elements per thread
+constexpr int OB_THREADS = 128; // S1: 4 elements per thread
 constexpr int E_NOGUESS = 0x7fffffff;
-constexpr double MAGIC = 6755399441055744.0;      // 1.5 * 2^52: (t + MAGIC) - MAGIC == rint(t) for |t| < 2^51
+constexpr double MAGIC = 6755399441055744.0; // 1.5 * 2^52: (t + MAGIC) - MAGIC == rint(t) for |t| < 2^51
 constexpr double TWO51 = 2251799813685248.0;
 constexpr long long TWO52 = 1LL << 52, TWO53 = 1LL << 53;
 
-// blocks accepted from their summary / blocks replayed sequentially (per chain), since last reset
-__device__ unsigned long long g_ord_counts[8]; // 0 accepted, 1 replayed, 2 flag, 3 binade guess, 4 bounds, 5 replay rounds, 6 element-wise sub-chunks
+// 0 accepted, 1 replayed, 2 unusable record, 3 state not expressible in the block's unit, 4 interval,
+// 5 replay rounds, 6 element-wise sub-chunks, 7 blocks accepted through the two-parity record
+__device__ unsigned long long g_ord_counts[8];
 
-// Quantised effect of a run of terms on the integer state M, for both parities of M at its start:
-// total, and min / max over the in-order prefixes.  The parity only matters through ties: a term
-// that lands exactly half-way (a/q = k + 0.5) is rounded to the EVEN neighbour, i.e. it adds k or
-// k + 1 depending on whether M + (everything before it) + k is even - a two-state transducer whose
-// composition is still associative.  After any element the parity of the state is
-// (p + prefix sum) mod 2, so no extra field is needed.
-struct Tri { double sum, mn, mx; };
-struct Tri2 { Tri p[2]; };
-
-struct OrdSummary {
-    Tri2 t;   // quantised terms of the block (integers stored as doubles)
-    int e;    // guessed binade of the running sum across this block
-    int flag; // non-zero: replay the block
+// One block of one chain.  flag: see F_*.
+struct OrdRec {
+    long long sum, lo, hi;
+    int eref; // binade whose ulp is the unit
+    int flag;
 };
+enum { F_OK = 0, F_REPLAY = 1, F_PENDING = 2, F_SENSITIVE = 3 };
 
 enum { KIND_MEAN = 0, KIND_CENTERED = 1 };
 template <int KIND> struct NChains { static constexpr int C = KIND == KIND_MEAN ? 4 : 7; };
+
+// record of (chain, block) of a segment: chain-major inside the segment's region of the packed table, so
+// that the 32 lanes of a resolving warp read 32 consecutive records
+__device__ __forceinline__ size_t rec_row(const PbSeg &sg, int C, int chain, uint32_t nblk, uint32_t blk) {
+    return (size_t)sg.bbase * C + (size_t)chain * nblk + blk;
+}
 
 // All chain terms of one element (S1 / S3).
 //   MEAN:     t0 = w, t1..3 = c_j * w                                  (matrix2D.c:222-228, vector.c:97-109)
@@ -124,7 +124,7 @@ __device__ __forceinline__ double block_reduce_sum(double v, double *sm /* [OB_T
 // ---- S1: unordered block sums -----------------------------------------------------------------
 template <int KIND, bool W>
 __global__ void __launch_bounds__(OB_THREADS) k_ord_blocksum(PbPlanes b0, PbPlanes b1, const PbSeg *__restrict__ segs,
-                                                             const PbStats *__restrict__ stats, uint32_t blk_cap,
+                                                             const PbStats *__restrict__ stats,
                                                              double *__restrict__ psum) {
     constexpr int C = NChains<KIND>::C;
     __shared__ double red[OB_THREADS / 32];
@@ -157,18 +157,16 @@ __global__ void __launch_bounds__(OB_THREADS) k_ord_blocksum(PbPlanes b0, PbPlan
     }
 }
 
-// ---- S2: approximate exclusive prefix per chain -> guessed binade ------------------------------
+// ---- S2: approximate exclusive prefix per chain (in place over the block sums) ------------------
 template <int C>
-__global__ void __launch_bounds__(32) k_ord_prefix(const PbSeg *__restrict__ segs, uint32_t blk_cap,
-                                                   const double *__restrict__ psum, OrdSummary *__restrict__ sum) {
+__global__ void __launch_bounds__(32) k_ord_prefix(const PbSeg *__restrict__ segs, double *__restrict__ psum) {
     const int seg = blockIdx.y, c = blockIdx.x, lane = threadIdx.x;
     const uint32_t nblk = (segs[seg].n + OB - 1) / OB;
-    const double *in = psum + (size_t)segs[seg].bbase * C + c;
-    OrdSummary *out = sum + (size_t)segs[seg].bbase * C + c;
+    double *io = psum + (size_t)segs[seg].bbase * C + c;
     const uint32_t per = (nblk + 31) / 32;
     const uint32_t b0 = min(lane * per, nblk), b1 = min(b0 + per, nblk);
     double s = 0.0;
-    for (uint32_t b = b0; b < b1; b++) s += in[(size_t)b * C];
+    for (uint32_t b = b0; b < b1; b++) s += io[(size_t)b * C];
     double incl = s;
     for (int o = 1; o < 32; o <<= 1) {
         const double v = __shfl_up_sync(0xffffffffu, incl, o);
@@ -176,227 +174,251 @@ __global__ void __launch_bounds__(32) k_ord_prefix(const PbSeg *__restrict__ seg
     }
     double run = incl - s;
     for (uint32_t b = b0; b < b1; b++) {
-        int e = E_NOGUESS;
-        const double a = fabs(run);
-        if (a > 1e-280 && a < 1e280) e = ilogb(a);
-        out[(size_t)b * C].e = e;
-        run += in[(size_t)b * C];
+        const double v = io[(size_t)b * C];
+        io[(size_t)b * C] = run;
+        run += v;
     }
 }
 
-// ---- S3: quantised block summaries --------------------------------------------------------------
-// (sum, min prefix, max prefix) of a sequence of integers is a monoid under in-order concatenation:
-//   (a ++ b).sum = a.sum + b.sum ; (a ++ b).mn = min(a.mn, a.sum + b.mn) ; likewise mx.
-// Each thread owns 4 CONSECUTIVE elements, warps reduce in lane order, warp 0..3 in warp order, so
-// mn / mx are the exact extremes of the running integer sum in element order.
-__device__ __forceinline__ int dparity(double v) { return (int)((long long)v & 1LL); }
+// ---- S3: block summaries with per-element binade prediction ------------------------------------
+constexpr int OS_THREADS = 64; // 8 consecutive elements per thread, two warps per block
+constexpr int OS_PER = OB / OS_THREADS;
 
-// in-order concatenation a ++ b
-__device__ __forceinline__ Tri2 tri2_cat(const Tri2 &a, const Tri2 &b) {
-    Tri2 r;
-#pragma unroll
-    for (int p = 0; p < 2; p++) {
-        const Tri &x = a.p[p];
-        const Tri &y = b.p[(p + dparity(x.sum)) & 1];
-        r.p[p] = Tri{x.sum + y.sum, fmin(x.mn, x.sum + y.mn), fmax(x.mx, x.sum + y.mx)};
-    }
+__device__ __forceinline__ PbSpan shfl_down_span(const PbSpan &v, int o) {
+    PbSpan r;
+    r.sum = __shfl_down_sync(0xffffffffu, v.sum, o);
+    r.lo = __shfl_down_sync(0xffffffffu, v.lo, o);
+    r.hi = __shfl_down_sync(0xffffffffu, v.hi, o);
+    return r;
+}
+__device__ __forceinline__ PbSpan shfl_up_span(const PbSpan &v, int o) {
+    PbSpan r;
+    r.sum = __shfl_up_sync(0xffffffffu, v.sum, o);
+    r.lo = __shfl_up_sync(0xffffffffu, v.lo, o);
+    r.hi = __shfl_up_sync(0xffffffffu, v.hi, o);
     return r;
 }
 
-// append one term u = a / q to the run
-__device__ __forceinline__ void tri2_push(Tri2 &t, double u, int &flag, bool first) {
-    const double d = __dsub_rn(__dadd_rn(u, MAGIC), MAGIC); // rint(u), ties to even of u itself
-    const double r = __dsub_rn(u, d);                       // exact remainder
-    flag |= !(fabs(u) < TWO51);                             // unquantisable (or NaN)
-    const bool tie = fabs(r) == 0.5;
-    const double lo = tie ? floor(u) : d;                   // k  (u = k + 0.5)
-#pragma unroll
-    for (int p = 0; p < 2; p++) {
-        Tri &x = t.p[p];
-        // ties go to the neighbour that makes the state even: parity before = p + x.sum
-        const double dd = (tie && (((p + dparity(x.sum) + dparity(lo)) & 1) != 0)) ? lo + 1.0 : lo;
-        const double ps = x.sum + dd;
-        x.mn = first ? ps : fmin(x.mn, ps);
-        x.mx = first ? ps : fmax(x.mx, ps);
-        x.sum = ps;
-    }
-}
+struct SumShared {
+    double wsum[7];          // warp 0's total (approximate prefix hand-over)
+    int emin[2][7], emax[2][7];
+    PbSpan2 span[7];         // warp 0's span
+    int flag[7];
+};
 
-// ---- S3a: the common case - no tie anywhere in the block: one parity-independent summary ----------
-constexpr int OS_THREADS = 64; // 8 consecutive elements per thread, two warps per block
-struct TriPlain { double sum, mn, mx; };
-__device__ __forceinline__ TriPlain trip_cat(const TriPlain &a, const TriPlain &b) {
-    return TriPlain{a.sum + b.sum, fmin(a.mn, a.sum + b.mn), fmax(a.mx, a.sum + b.mx)};
+// Summarises block `blk` of segment `sg` for every chain with need[c] (NV = 1: one record, parity-dependent
+// blocks are left F_PENDING; NV = 2: both parities).  All threads of the CTA take part.
+template <int KIND, bool W, int NV>
+__device__ __forceinline__ bool summarise_block(const PbPlanes &P, const PbSeg &sg, uint32_t blk, double m0, double m1,
+                                                double m2, const double *__restrict__ pstart, OrdRec *__restrict__ rec0,
+                                                OrdRec *__restrict__ rec1, const bool *need, SumShared &sh) {
+    constexpr int C = NChains<KIND>::C;
+    const uint32_t nblk = (sg.n + OB - 1) / OB;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t i0 = blk * OB + threadIdx.x * OS_PER; // this thread's consecutive elements
+    const bool have = i0 < sg.n;
+    if (threadIdx.x < C) sh.flag[threadIdx.x] = 0;
+
+    // ---- phase 1: approximate running sum at the start of this thread's elements ------------------
+    double tstart[C];
+    {
+        double tl[C];
+#pragma unroll
+        for (int c = 0; c < C; c++) tl[c] = 0.0;
+#pragma unroll
+        for (int k = 0; k < OS_PER; k++) {
+            if (i0 + k < sg.n) {
+                const size_t p = (size_t)sg.lo + i0 + k;
+                double t[C];
+                terms_all<KIND, W>(W ? P.w[p] : 1.0, P.c[0][p], P.c[1][p], P.c[2][p], m0, m1, m2, t);
+#pragma unroll
+                for (int c = 0; c < C; c++) tl[c] += t[c];
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+            double incl = tl[c];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            if (warp == 0 && lane == 31) sh.wsum[c] = incl;
+            tstart[c] = incl - tl[c];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < C; c++) tstart[c] += pstart[c] + (warp ? sh.wsum[c] : 0.0);
+    }
+    // ---- phase 2: binade range of the predicted partial sums (start states included) --------------
+    {
+        int emin[C], emax[C];
+        double run[C];
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+            run[c] = tstart[c];
+            const int e = pb_exponent_of(run[c]);
+            emin[c] = have ? e : (1 << 20);
+            emax[c] = have ? e : -(1 << 20);
+        }
+#pragma unroll
+        for (int k = 0; k < OS_PER; k++) {
+            if (i0 + k < sg.n) {
+                const size_t p = (size_t)sg.lo + i0 + k;
+                double t[C];
+                terms_all<KIND, W>(W ? P.w[p] : 1.0, P.c[0][p], P.c[1][p], P.c[2][p], m0, m1, m2, t);
+#pragma unroll
+                for (int c = 0; c < C; c++) {
+                    run[c] += t[c];
+                    const int e = pb_exponent_of(run[c]);
+                    emin[c] = min(emin[c], e);
+                    emax[c] = max(emax[c], e);
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                emin[c] = min(emin[c], __shfl_xor_sync(0xffffffffu, emin[c], o));
+                emax[c] = max(emax[c], __shfl_xor_sync(0xffffffffu, emax[c], o));
+            }
+            if (lane == 0) { sh.emin[warp][c] = emin[c]; sh.emax[warp][c] = emax[c]; }
+        }
+        __syncthreads();
+    }
+    // ---- phase 3: spans on the predicted grids, in units of the lowest binade ----------------------
+    int eref[C];
+    bool usable[C];
+    PbRun run_st[C];
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+        const int lo = min(sh.emin[0][c], sh.emin[1][c]), hi = max(sh.emax[0][c], sh.emax[1][c]);
+        eref[c] = lo;
+        // zero / subnormal / non-finite predictions, or too wide a range: replay
+        usable[c] = need[c] && pb_eref_ok(lo) && pb_eref_ok(hi) && hi - lo <= PB_SPAN_MAX_LEVEL;
+        if (!usable[c]) eref[c] = 0;
+        pb_run_begin(run_st[c], tstart[c], eref[c]);
+    }
+    if (have) {
+        double run[C];
+#pragma unroll
+        for (int c = 0; c < C; c++) run[c] = tstart[c];
+#pragma unroll
+        for (int k = 0; k < OS_PER; k++) {
+            if (i0 + k < sg.n) {
+                const size_t p = (size_t)sg.lo + i0 + k;
+                double t[C];
+                terms_all<KIND, W>(W ? P.w[p] : 1.0, P.c[0][p], P.c[1][p], P.c[2][p], m0, m1, m2, t);
+#pragma unroll
+                for (int c = 0; c < C; c++) {
+                    run[c] += t[c]; // same operations as phase 2: same predictions
+                    if (usable[c] && !run_st[c].bad) pb_run_push<NV>(run_st[c], t[c], run[c], eref[c]);
+                }
+            }
+        }
+    }
+    bool pending = false;
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+        if (!need[c]) continue; // CTA-uniform
+        PbSpan2 v = pb_span2_identity();
+        if (usable[c] && have) {
+            v = pb_run_span<NV>(run_st[c]);
+            const int f = (run_st[c].bad ? 1 : 0) | (run_st[c].sensitive ? 2 : 0);
+            if (f) atomicOr(&sh.flag[c], f);
+        }
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { // in-order tree: lane i absorbs lane i + o
+            PbSpan2 r;
+            r.p[0] = shfl_down_span(v.p[0], o);
+            if (NV == 2) r.p[1] = shfl_down_span(v.p[1], o);
+            else r.p[1] = r.p[0];
+            if ((lane & (2 * o - 1)) == 0) {
+                if (NV == 2) v = pb_span2_cat(v, r);
+                else { v.p[0] = pb_span_cat(v.p[0], r.p[0]); v.p[1] = v.p[0]; }
+            }
+        }
+        if (warp == 0 && lane == 0) sh.span[c] = v;
+        __syncthreads();
+        if (warp == 1 && lane == 0) {
+            PbSpan2 w;
+            if (NV == 2) w = pb_span2_cat(sh.span[c], v);
+            else { w.p[0] = pb_span_cat(sh.span[c].p[0], v.p[0]); w.p[1] = w.p[0]; }
+            const int f = sh.flag[c];
+            int flag;
+            if (!usable[c] || (f & 1)) flag = F_REPLAY;
+            else if (NV == 1) flag = (f & 2) ? F_PENDING : F_OK;
+            else flag = F_SENSITIVE;
+            // contradictory predictions (empty interval): never applicable.  A two-parity record stays
+            // usable if one parity is valid; the resolve checks the interval of the parity it needs.
+            if (flag == F_OK && !pb_span_valid(w.p[0])) flag = F_REPLAY;
+            if (flag == F_SENSITIVE && !pb_span_valid(w.p[0]) && !pb_span_valid(w.p[1])) flag = F_REPLAY;
+            const size_t row = rec_row(sg, C, c, nblk, blk);
+            OrdRec o0;
+            o0.sum = w.p[0].sum; o0.lo = w.p[0].lo; o0.hi = w.p[0].hi; o0.eref = eref[c]; o0.flag = flag;
+            rec0[row] = o0;
+            if (NV == 2) {
+                OrdRec o1;
+                o1.sum = w.p[1].sum; o1.lo = w.p[1].lo; o1.hi = w.p[1].hi; o1.eref = eref[c]; o1.flag = flag;
+                rec1[row] = o1;
+            }
+            pending |= flag == F_PENDING;
+        }
+    }
+    return pending; // meaningful on (warp 1, lane 0)
 }
 
 template <int KIND, bool W>
 __global__ void __launch_bounds__(OS_THREADS) k_ord_summary(PbPlanes b0, PbPlanes b1, const PbSeg *__restrict__ segs,
-                                                            const PbStats *__restrict__ stats, uint32_t blk_cap,
-                                                            OrdSummary *__restrict__ sum,
-                                                            unsigned int *__restrict__ tie_count,
-                                                            uint2 *__restrict__ tie_list) {
+                                                            const PbStats *__restrict__ stats,
+                                                            const double *__restrict__ psum, OrdRec *__restrict__ rec0,
+                                                            unsigned int *__restrict__ list_count,
+                                                            uint2 *__restrict__ list) {
     constexpr int C = NChains<KIND>::C;
-    constexpr int PER = OB / OS_THREADS;
-    __shared__ TriPlain s_tri[OS_THREADS / 32][C];
-    __shared__ int s_flag[C];
+    __shared__ SumShared sh;
     const int seg = blockIdx.y;
     const PbSeg sg = segs[seg];
-    const uint32_t base = blockIdx.x * OB;
-    if (base >= sg.n) return;
+    if (blockIdx.x * OB >= sg.n) return;
     const PbPlanes &P = sg.buf ? b1 : b0;
-    OrdSummary *out = sum + ((size_t)sg.bbase + blockIdx.x) * C;
     double m0 = 0, m1 = 0, m2 = 0;
     if (KIND == KIND_CENTERED) { m0 = stats[seg].mean[0]; m1 = stats[seg].mean[1]; m2 = stats[seg].mean[2]; }
-    double scale[C];
-    TriPlain tri[C];
-    int flag[C]; // bit 0: unusable (no guess / unquantisable term), bit 1: a tie -> needs the tie-aware pass
+    bool need[C];
 #pragma unroll
-    for (int c = 0; c < C; c++) {
-        const int e = out[c].e;
-        flag[c] = e == E_NOGUESS;
-        scale[c] = flag[c] ? 0.0 : scalbn(1.0, 52 - e); // 1 / q
-        tri[c] = TriPlain{0.0, 1e300, -1e300};          // empty run
-    }
-    if (threadIdx.x < C) s_flag[threadIdx.x] = 0;
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < PER; k++) {
-        const uint32_t i = base + threadIdx.x * PER + k; // consecutive elements per thread
-        if (i < sg.n) {
-            const size_t p = (size_t)sg.lo + i;
-            double t[C];
-            terms_all<KIND, W>(W ? P.w[p] : 1.0, P.c[0][p], P.c[1][p], P.c[2][p], m0, m1, m2, t);
-#pragma unroll
-            for (int c = 0; c < C; c++) {
-                const double u = __dmul_rn(t[c], scale[c]);             // a / q, exact (power of two)
-                const double d = __dsub_rn(__dadd_rn(u, MAGIC), MAGIC); // rint(u)
-                flag[c] |= (!(fabs(u) < TWO51) ? 1 : 0) | (fabs(__dsub_rn(u, d)) == 0.5 ? 2 : 0);
-                const double ps = tri[c].sum + d;
-                tri[c] = TriPlain{ps, fmin(tri[c].mn, ps), fmax(tri[c].mx, ps)};
-            }
-        }
-    }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int c = 0; c < C; c++) {
-        if (flag[c]) atomicOr(&s_flag[c], flag[c]);
-        TriPlain v = tri[c];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { // in-order tree: lane i absorbs lane i + o
-            TriPlain r;
-            r.sum = __shfl_down_sync(0xffffffffu, v.sum, o);
-            r.mn = __shfl_down_sync(0xffffffffu, v.mn, o);
-            r.mx = __shfl_down_sync(0xffffffffu, v.mx, o);
-            if ((lane & (2 * o - 1)) == 0) v = trip_cat(v, r);
-        }
-        if (lane == 0) s_tri[warp][c] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x < C) {
-        TriPlain v = s_tri[0][threadIdx.x];
-        for (int w = 1; w < OS_THREADS / 32; w++) v = trip_cat(v, s_tri[w][threadIdx.x]);
-        const Tri tt{v.sum, v.mn, v.mx};
-        out[threadIdx.x].t.p[0] = tt;
-        out[threadIdx.x].t.p[1] = tt;
-        out[threadIdx.x].flag = s_flag[threadIdx.x]; // 0 ok, odd: replay, 2: redo with k_ord_summary_tie
-    }
-    if (threadIdx.x == 0) { // blocks holding a tie go on the work list of the tie-aware pass
-        bool tie = false;
-        for (int c = 0; c < C; c++) tie |= s_flag[c] == 2;
-        if (tie) tie_list[atomicAdd(tie_count, 1u)] = make_uint2((unsigned)seg, blockIdx.x);
-    }
+    for (int c = 0; c < C; c++) need[c] = true;
+    const bool pending = summarise_block<KIND, W, 1>(P, sg, blockIdx.x, m0, m1, m2,
+                                                     psum + ((size_t)sg.bbase + blockIdx.x) * C, rec0, nullptr, need, sh);
+    if (threadIdx.x == 32 && pending) list[atomicAdd(list_count, 1u)] = make_uint2((unsigned)seg, blockIdx.x);
 }
 
-// ---- S3b: blocks that contain a tie: both start parities (the two-state transducer) --------------
+// ---- S3b: blocks with a parity-dependent step: both start parities ---------------------------------
 template <int KIND, bool W>
-__global__ void __launch_bounds__(OB_THREADS) k_ord_summary_tie(PbPlanes b0, PbPlanes b1, const PbSeg *__restrict__ segs,
-                                                                const PbStats *__restrict__ stats, uint32_t blk_cap,
-                                                                OrdSummary *__restrict__ sum,
-                                                                const unsigned int *__restrict__ tie_count,
-                                                                const uint2 *__restrict__ tie_list) {
+__global__ void __launch_bounds__(OS_THREADS) k_ord_summary2(PbPlanes b0, PbPlanes b1, const PbSeg *__restrict__ segs,
+                                                             const PbStats *__restrict__ stats,
+                                                             const double *__restrict__ psum, OrdRec *__restrict__ rec0,
+                                                             OrdRec *__restrict__ rec1,
+                                                             const unsigned int *__restrict__ list_count,
+                                                             const uint2 *__restrict__ list) {
     constexpr int C = NChains<KIND>::C;
-    constexpr int PER = OB / OB_THREADS;
-    __shared__ Tri2 s_tri[OB_THREADS / 32][C];
-    __shared__ int s_flag[C];
-  for (unsigned int item = blockIdx.x; item < *tie_count; item += gridDim.x) { // persistent CTAs over the work list
-    const int seg = (int)tie_list[item].x;
-    const uint32_t blk = tie_list[item].y;
-    const PbSeg sg = segs[seg];
-    const uint32_t base = blk * OB;
-    const PbPlanes &P = sg.buf ? b1 : b0;
-    OrdSummary *out = sum + ((size_t)sg.bbase + blk) * C;
-    __syncthreads();
-    double m0 = 0, m1 = 0, m2 = 0;
-    if (KIND == KIND_CENTERED) { m0 = stats[seg].mean[0]; m1 = stats[seg].mean[1]; m2 = stats[seg].mean[2]; }
-    double scale[C];
-    Tri2 tri[C];
-    int flag[C];
-    bool need[C]; // only the chains that actually hold a tie are redone (uniform across the CTA)
-    bool any = false;
+    __shared__ SumShared sh;
+    for (unsigned int item = blockIdx.x; item < *list_count; item += gridDim.x) { // persistent CTAs over the work list
+        const int seg = (int)list[item].x;
+        const uint32_t blk = list[item].y;
+        const PbSeg sg = segs[seg];
+        const PbPlanes &P = sg.buf ? b1 : b0;
+        const uint32_t nblk = (sg.n + OB - 1) / OB;
+        double m0 = 0, m1 = 0, m2 = 0;
+        if (KIND == KIND_CENTERED) { m0 = stats[seg].mean[0]; m1 = stats[seg].mean[1]; m2 = stats[seg].mean[2]; }
+        __syncthreads(); // sh is reused across items
+        bool need[C]; // only the chains that asked for it are redone (uniform across the CTA)
 #pragma unroll
-    for (int c = 0; c < C; c++) {
-        const int e = out[c].e;
-        need[c] = out[c].flag == 2;
-        flag[c] = e == E_NOGUESS;
-        scale[c] = flag[c] ? 0.0 : scalbn(1.0, 52 - e); // 1 / q
-        tri[c].p[0] = tri[c].p[1] = Tri{0.0, 1e300, -1e300}; // empty run
+        for (int c = 0; c < C; c++) need[c] = rec0[rec_row(sg, C, c, nblk, blk)].flag == F_PENDING;
+        __syncthreads(); // every thread has read the flags before (warp 1, lane 0) rewrites the records
+        summarise_block<KIND, W, 2>(P, sg, blk, m0, m1, m2, psum + ((size_t)sg.bbase + blk) * C, rec0, rec1, need, sh);
     }
-    if (threadIdx.x < C) s_flag[threadIdx.x] = 0;
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < PER; k++) {
-        const uint32_t i = base + threadIdx.x * PER + k; // consecutive elements per thread
-        if (i < sg.n) {
-            const size_t p = (size_t)sg.lo + i;
-            double t[C];
-            terms_all<KIND, W>(W ? P.w[p] : 1.0, P.c[0][p], P.c[1][p], P.c[2][p], m0, m1, m2, t);
-#pragma unroll
-            for (int c = 0; c < C; c++)
-                if (need[c]) tri2_push(tri[c], __dmul_rn(t[c], scale[c]) /* a / q, exact */, flag[c], !any);
-            any = true;
-        }
-    }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int c = 0; c < C; c++) {
-        if (!need[c]) continue;
-        if (flag[c]) atomicOr(&s_flag[c], 1);
-        Tri2 v = tri[c];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { // in-order tree: lane i absorbs lane i + o
-            Tri2 r;
-#pragma unroll
-            for (int p = 0; p < 2; p++) {
-                r.p[p].sum = __shfl_down_sync(0xffffffffu, v.p[p].sum, o);
-                r.p[p].mn = __shfl_down_sync(0xffffffffu, v.p[p].mn, o);
-                r.p[p].mx = __shfl_down_sync(0xffffffffu, v.p[p].mx, o);
-            }
-            if ((lane & (2 * o - 1)) == 0) v = tri2_cat(v, r);
-        }
-        if (lane == 0) s_tri[warp][c] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x < C && out[threadIdx.x].flag == 2) { // == need[threadIdx.x]
-        Tri2 v = s_tri[0][threadIdx.x];
-        for (int w = 1; w < OB_THREADS / 32; w++) v = tri2_cat(v, s_tri[w][threadIdx.x]);
-        out[threadIdx.x].t = v;
-        out[threadIdx.x].flag = s_flag[threadIdx.x];
-    }
-  }
 }
 
 // ---- S4: ordered resolve ---------------------------------------------------------------------------
-// One CTA per cluster, one WARP per chain.  The warp's state is the exact running sum s (uniform
-// across lanes).  Blocks are taken 32 at a time, lane b holding the summary of block b: an in-order
-// warp scan of the block totals gives every lane the exact state its block would start from IF all
-// earlier blocks are accepted, each lane validates its own block against that state, and a ballot
-// finds the first block that cannot be accepted.  Everything before it is applied in one step; that
-// block is replayed; the walk resumes behind it.
-//
-// Replaying a block uses the same idea one level down, now with the EXACT binade (s is known):
-// each lane quantises its 16 consecutive elements, the warp scans / validates / ballots, accepted
-// sub-chunks are applied at once and only the sub-chunk where the binade changes (or a tie sits) is
-// added element by element - the literal reference loop, 16 elements long.
 constexpr int SUB = OB / 32; // elements per lane in a replay
 
 __device__ __forceinline__ long long warp_incl_scan(long long v, int lane) {
@@ -408,80 +430,11 @@ __device__ __forceinline__ long long warp_incl_scan(long long v, int lane) {
     return v;
 }
 
-// Applies the items [next, limit) held one per lane (usable iff ok) to the state s as far as they
-// validate.  Returns the first index that does not (limit if all do) and updates s.  Item l checks
-// its own prefix extremes against the exact state it would start from if everything before it is
-// accepted; that state comes from an in-order warp scan of the monoid.  `validate` turns the scanned
-// run of a lane into (usable, total).
-__device__ __forceinline__ uint32_t finish_run(double &s, long long bits, long long M, bool negs, bool mine, bool ok,
-                                              long long tot, double rmn, double rmx, uint32_t next, uint32_t limit) {
-    const long long lo = rmn > 9e299 ? 0 : (long long)rmn, hi = rmx < -9e299 ? 0 : (long long)rmx;
-    const long long vmin = negs ? M - hi : M + lo, vmax = negs ? M - lo : M + hi;
-    // every prefix up to and including this item strictly inside (2^52, 2^53): the unrounded value
-    // must itself stay inside the binade
-    const bool valid = ok && vmin > TWO52 && vmax < TWO53;
-    const unsigned fails = __ballot_sync(0xffffffffu, mine && !valid);
-    const uint32_t f = fails ? (uint32_t)(__ffs(fails) - 1) : limit;
-    if (f > next) {
-        const long long acc = __shfl_sync(0xffffffffu, tot, (int)f - 1); // inclusive total of lane f - 1
-        const long long M2 = negs ? M - acc : M + acc;
-        s = __longlong_as_double((bits & 0xfff0000000000000LL) | (M2 & 0x000fffffffffffffLL));
-    }
-    return f;
-}
-
-// items whose effect does not depend on the start parity (no tie inside): a 3-double scan
-__device__ __forceinline__ uint32_t apply_run_plain(double &s, int lane, uint32_t next, uint32_t limit, bool ok,
-                                                   const TriPlain &item) {
-    const long long bits = __double_as_longlong(s);
-    const long long M = (bits & 0x000fffffffffffffLL) | TWO52; // |s| / q
-    const bool mine = lane >= (int)next && lane < (int)limit;
-    TriPlain run = (mine && ok) ? item : TriPlain{0.0, 1e300, -1e300};
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        TriPlain up;
-        up.sum = __shfl_up_sync(0xffffffffu, run.sum, o);
-        up.mn = __shfl_up_sync(0xffffffffu, run.mn, o);
-        up.mx = __shfl_up_sync(0xffffffffu, run.mx, o);
-        if (lane >= o) run = trip_cat(up, run);
-    }
-    return finish_run(s, bits, M, bits < 0, mine, ok, (long long)run.sum, run.mn, run.mx, next, limit);
-}
-
-// general items: the parity each one starts from depends on the items before it, so the warp scans
-// the two-parity monoid
-__device__ __forceinline__ uint32_t apply_run(double &s, int lane, uint32_t next, uint32_t limit, bool ok,
-                                             const Tri2 &item) {
-    const long long bits = __double_as_longlong(s);
-    const long long M = (bits & 0x000fffffffffffffLL) | TWO52; // |s| / q
-    const int p0 = (int)(M & 1LL);
-    const bool mine = lane >= (int)next && lane < (int)limit;
-    const bool parity_matters = mine && ok && (item.p[0].sum != item.p[1].sum || item.p[0].mn != item.p[1].mn ||
-                                               item.p[0].mx != item.p[1].mx);
-    if (!__any_sync(0xffffffffu, parity_matters))
-        return apply_run_plain(s, lane, next, limit, ok, TriPlain{item.p[0].sum, item.p[0].mn, item.p[0].mx});
-    Tri2 inc;
-    if (mine && ok) inc = item;
-    else inc.p[0] = inc.p[1] = Tri{0.0, 1e300, -1e300};
-    Tri2 run = inc;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        Tri2 up;
-#pragma unroll
-        for (int p = 0; p < 2; p++) {
-            up.p[p].sum = __shfl_up_sync(0xffffffffu, run.p[p].sum, o);
-            up.p[p].mn = __shfl_up_sync(0xffffffffu, run.p[p].mn, o);
-            up.p[p].mx = __shfl_up_sync(0xffffffffu, run.p[p].mx, o);
-        }
-        if (lane >= o) run = tri2_cat(up, run);
-    }
-    // run.p[p0] = items next..lane applied to a state of parity p0: prefix extremes included
-    return finish_run(s, bits, M, bits < 0, mine, ok, (long long)run.p[p0].sum, run.p[p0].mn, run.p[p0].mx, next, limit);
-}
-
 // One lane's 16 elements quantised against binade e: total, prefix extremes, exclusive prefix of the
 // totals over the lanes before it, and whether the sub-chunk is unusable (unquantisable term, or a tie,
 // whose rounding depends on the parity of the state - such a sub-chunk is simply added element-wise).
+// The state provably stays inside binade e (prefix extremes checked against (2^52, 2^53)), so every
+// step is the translation rint(a / q).
 struct SubVer {
     int e;
     int bad;
@@ -523,8 +476,7 @@ __device__ __forceinline__ SubVer quantise_sub(const double *t, int my, int e, i
 // quantisations are kept.
 template <int KIND, bool W>
 __device__ __forceinline__ double replay_block(const PbPlanes &P, size_t first, uint32_t cnt, int chain, double m0,
-                                               double m1, double m2, double s, int lane, int &hover) {
-    (void)hover;
+                                               double m1, double m2, double s, int lane) {
     double t[SUB];
     const int my = max(0, min(SUB, (int)cnt - lane * SUB));
 #pragma unroll
@@ -593,8 +545,9 @@ __device__ __forceinline__ double replay_block(const PbPlanes &P, size_t first, 
 template <int KIND, bool W>
 __global__ void __launch_bounds__(32 * NChains<KIND>::C) k_ord_resolve(PbPlanes b0, PbPlanes b1,
                                                                        const PbSeg *__restrict__ segs,
-                                                                       PbStats *__restrict__ stats, uint32_t blk_cap,
-                                                                       const OrdSummary *__restrict__ sum,
+                                                                       PbStats *__restrict__ stats,
+                                                                       const OrdRec *__restrict__ rec0,
+                                                                       const OrdRec *__restrict__ rec1,
                                                                        bool use_summaries) {
     constexpr int C = NChains<KIND>::C;
     __shared__ double s_res[C];
@@ -605,38 +558,76 @@ __global__ void __launch_bounds__(32 * NChains<KIND>::C) k_ord_resolve(PbPlanes 
     double m0 = 0, m1 = 0, m2 = 0;
     if (KIND == KIND_CENTERED) { m0 = stats[seg].mean[0]; m1 = stats[seg].mean[1]; m2 = stats[seg].mean[2]; }
     double s = 0.0; // exact running sum of this warp's chain
-    unsigned int n_acc = 0, n_rep = 0, n_why[3] = {0, 0, 0};
-    int hover = 0;
-    const OrdSummary *srow = sum + (size_t)sg.bbase * C + chain;
+    unsigned int n_acc = 0, n_rep = 0, n_acc2 = 0, n_why[3] = {0, 0, 0};
+    const size_t row0 = rec_row(sg, C, chain, nblk, 0);
     for (uint32_t g0 = 0; g0 < nblk; g0 += 32) {
         const uint32_t gcnt = min(32u, nblk - g0);
-        OrdSummary sm;
-        sm.t.p[0] = sm.t.p[1] = Tri{0.0, 0.0, 0.0};
-        sm.e = E_NOGUESS;
-        sm.flag = 1;
-        if (use_summaries && lane < (int)gcnt) sm = srow[(size_t)(g0 + lane) * C];
+        OrdRec r, r1;
+        r.sum = 0; r.lo = 1; r.hi = 0; r.eref = 0; r.flag = F_REPLAY;
+        if (use_summaries && lane < (int)gcnt) r = rec0[row0 + g0 + lane];
+        r1 = r;
+        if (r.flag == F_SENSITIVE) r1 = rec1[row0 + g0 + lane];
         uint32_t next = 0;
         while (next < gcnt) {
-            const long long bits = __double_as_longlong(s);
-            const int es = (int)((bits >> 52) & 0x7ff) - 1023;
-            const bool ok = use_summaries && sm.flag == 0 && sm.e == es && es > -1000 && es < 1000;
-            const uint32_t f = apply_run(s, lane, next, gcnt, ok, sm.t);
-            n_acc += f - next;
-            if (f < gcnt && use_summaries) {
-                const int fl = __shfl_sync(0xffffffffu, sm.flag, (int)f), fe = __shfl_sync(0xffffffffu, sm.e, (int)f);
-                if (lane == 0) {
-                    if (fl) n_why[0]++;
-                    else if (fe != es) n_why[1]++;
-                    else n_why[2]++;
+            const int fl0 = __shfl_sync(0xffffffffu, r.flag, (int)next), e0 = __shfl_sync(0xffffffffu, r.eref, (int)next);
+            bool handled = false;
+            int why = 0;
+            if (fl0 == F_OK) {
+                long long S = 0;
+                if (pb_eref_ok(e0) && pb_state_to_units(s, e0, S)) {
+                    // maximal run of plain records with the same unit starting at `next`
+                    const bool okl = lane >= (int)next && r.flag == F_OK && r.eref == e0; // lanes >= gcnt hold F_REPLAY
+                    const unsigned notok = __ballot_sync(0xffffffffu, lane >= (int)next && !okl);
+                    const uint32_t runend = notok ? (uint32_t)(__ffs(notok) - 1) : 32u;
+                    PbSpan v = pb_span_identity();
+                    if (lane >= (int)next && lane < (int)runend) { v.sum = r.sum; v.lo = r.lo; v.hi = r.hi; }
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { // in-order inclusive scan of the monoid
+                        const PbSpan up = shfl_up_span(v, o);
+                        if (lane >= o) v = pb_span_cat(up, v);
+                    }
+                    const bool mine = lane >= (int)next && lane < (int)runend;
+                    const bool valid = pb_span_valid(v) && S >= v.lo && S <= v.hi;
+                    const unsigned fails = __ballot_sync(0xffffffffu, mine && !valid);
+                    const uint32_t f = fails ? (uint32_t)(__ffs(fails) - 1) : runend;
+                    if (f > next) {
+                        const long long acc = __shfl_sync(0xffffffffu, v.sum, (int)f - 1);
+                        s = pb_units_to_state(S + acc, e0); // exact: at most 53 significant bits by the last constraint
+                        n_acc += f - next;
+                        next = f;
+                        handled = true;
+                    } else {
+                        why = 2; // the very first record's interval does not hold
+                    }
+                } else {
+                    why = 1;
+                }
+            } else if (fl0 == F_SENSITIVE) {
+                double s2 = s;
+                int ok = 0;
+                if (lane == (int)next) {
+                    PbSpan2 sp;
+                    sp.p[0].sum = r.sum; sp.p[0].lo = r.lo; sp.p[0].hi = r.hi;
+                    sp.p[1].sum = r1.sum; sp.p[1].lo = r1.lo; sp.p[1].hi = r1.hi;
+                    ok = pb_span2_apply(sp, r.eref, s2) ? 1 : 0;
+                }
+                ok = __shfl_sync(0xffffffffu, ok, (int)next);
+                if (ok) {
+                    s = __shfl_sync(0xffffffffu, s2, (int)next);
+                    n_acc++;
+                    n_acc2++;
+                    next++;
+                    handled = true;
+                } else {
+                    why = 2;
                 }
             }
-            if (f < gcnt) {
-                const uint32_t base = (g0 + f) * OB;
-                s = replay_block<KIND, W>(P, (size_t)sg.lo + base, min((uint32_t)OB, n - base), chain, m0, m1, m2, s, lane, hover);
+            if (!handled) {
+                const uint32_t base = (g0 + next) * OB;
+                s = replay_block<KIND, W>(P, (size_t)sg.lo + base, min((uint32_t)OB, n - base), chain, m0, m1, m2, s, lane);
                 n_rep++;
-                next = f + 1;
-            } else {
-                next = gcnt;
+                n_why[why]++;
+                next++;
             }
         }
     }
@@ -645,7 +636,8 @@ __global__ void __launch_bounds__(32 * NChains<KIND>::C) k_ord_resolve(PbPlanes 
         if (use_summaries) {
             atomicAdd(&g_ord_counts[0], (unsigned long long)n_acc);
             atomicAdd(&g_ord_counts[1], (unsigned long long)n_rep);
-            for (int r = 0; r < 3; r++) atomicAdd(&g_ord_counts[2 + r], (unsigned long long)n_why[r]);
+            for (int q = 0; q < 3; q++) atomicAdd(&g_ord_counts[2 + q], (unsigned long long)n_why[q]);
+            atomicAdd(&g_ord_counts[7], (unsigned long long)n_acc2);
         }
     }
     __syncthreads();
@@ -663,6 +655,23 @@ __global__ void __launch_bounds__(32 * NChains<KIND>::C) k_ord_resolve(PbPlanes 
     }
 }
 
+struct Scratch {
+    double *psum;
+    OrdRec *rec0, *rec1;
+    uint2 *list;
+    unsigned int *list_count;
+};
+Scratch carve(void *d_scratch, size_t total_blocks) {
+    Scratch s;
+    char *p = (char *)d_scratch;
+    s.psum = (double *)p; p += total_blocks * 7 * sizeof(double);
+    s.rec0 = (OrdRec *)p; p += total_blocks * 7 * sizeof(OrdRec);
+    s.rec1 = (OrdRec *)p; p += total_blocks * 7 * sizeof(OrdRec);
+    s.list = (uint2 *)p; p += total_blocks * sizeof(uint2);
+    s.list_count = (unsigned int *)p;
+    return s;
+}
+
 template <int KIND, bool W>
 void launch_pass(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t max_n, uint32_t total_blocks,
                  PbStats *d_stats, void *d_scratch, size_t scratch_bytes, cudaStream_t st) {
@@ -670,26 +679,22 @@ void launch_pass(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t
     const uint32_t blk_cap = (max_n + OB - 1) / OB; // grid width; the tables are packed by PbSeg::bbase
     const size_t need = pb_ordered_scratch_bytes(total_blocks);
     const bool speculative = max_n >= 8 * OB && d_scratch && need <= scratch_bytes;
-    double *psum = (double *)d_scratch;
-    OrdSummary *sum = (OrdSummary *)((char *)d_scratch + (size_t)total_blocks * 7 * sizeof(double));
-    uint2 *tie_list = (uint2 *)((char *)d_scratch + (size_t)total_blocks * 7 * (sizeof(double) + sizeof(OrdSummary)));
-    unsigned int *tie_count = (unsigned int *)(tie_list + total_blocks);
-    const double bytes = 0; // set by the caller through pb_prof_next_bytes for the resolve kernel
-    (void)bytes;
+    Scratch sc{};
     if (speculative) {
+        sc = carve(d_scratch, total_blocks);
         dim3 grid(blk_cap, nseg);
         { PbProfScope p(KIND == KIND_MEAN ? "k_ord_blocksum_mean" : "k_ord_blocksum_centered", st, false);
-          k_ord_blocksum<KIND, W><<<grid, OB_THREADS, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, blk_cap, psum); }
+          k_ord_blocksum<KIND, W><<<grid, OB_THREADS, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, sc.psum); }
         { PbProfScope p("k_ord_prefix", st, false);
-          k_ord_prefix<C><<<dim3(C, nseg), 32, 0, st>>>(d_segs, blk_cap, psum, sum); }
-        PB_CUDA_OK(cudaMemsetAsync(tie_count, 0, sizeof(unsigned int), st));
+          k_ord_prefix<C><<<dim3(C, nseg), 32, 0, st>>>(d_segs, sc.psum); }
+        PB_CUDA_OK(cudaMemsetAsync(sc.list_count, 0, sizeof(unsigned int), st));
         { PbProfScope p(KIND == KIND_MEAN ? "k_ord_summary_mean" : "k_ord_summary_centered", st);
-          k_ord_summary<KIND, W><<<grid, OS_THREADS, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, blk_cap, sum, tie_count, tie_list); }
-        { PbProfScope p("k_ord_summary_tie", st, false);
-          k_ord_summary_tie<KIND, W><<<148 * 4, OB_THREADS, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, blk_cap, sum, tie_count, tie_list); }
+          k_ord_summary<KIND, W><<<grid, OS_THREADS, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, sc.psum, sc.rec0, sc.list_count, sc.list); }
+        { PbProfScope p("k_ord_summary2", st, false);
+          k_ord_summary2<KIND, W><<<148 * 4, OS_THREADS, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, sc.psum, sc.rec0, sc.rec1, sc.list_count, sc.list); }
     }
     { PbProfScope p(KIND == KIND_MEAN ? "k_ord_resolve_mean" : "k_ord_resolve_centered", st, !speculative);
-      k_ord_resolve<KIND, W><<<nseg, 32 * C, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, blk_cap, sum, speculative); }
+      k_ord_resolve<KIND, W><<<nseg, 32 * C, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, sc.rec0, sc.rec1, speculative); }
     PB_CUDA_OK(cudaGetLastError());
 }
 
@@ -706,7 +711,7 @@ void pb_ordered_counts(unsigned long long out[8], bool reset) {
 uint32_t pb_ordered_blocks(uint32_t n) { return (n + OB - 1) / OB; }
 
 size_t pb_ordered_scratch_bytes(size_t total_blocks) {
-    return total_blocks * (7 * (sizeof(double) + sizeof(OrdSummary)) + sizeof(uint2)) + 256;
+    return total_blocks * (7 * (sizeof(double) + 2 * sizeof(OrdRec)) + sizeof(uint2)) + 256;
 }
 
 void pb_launch_pass_mean(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t max_n,

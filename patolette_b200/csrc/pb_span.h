@@ -1,0 +1,237 @@
+// pb_span.h - the arithmetic core of the bit-exact ordered sums (pb_ordered.cu), host + device.
+//
+// A left-to-right f64 accumulation s_i = fl(s_{i-1} + a_i) (matrix2D.c:222-228, pca.c:88-93,
+// cluster.c:135-148 in the reference) is modelled on integers.  Fix a unit u = 2^(eref-52), the ulp of
+// the LOWEST binade the running sum visits inside a run of elements, and write s = S * u.  A step whose
+// exact result x = s_{i-1} + a_i lies in binade eref + k rounds x to a multiple of g = 2^k units:
+//
+//     S_i = RN_g(S_{i-1} + a_i / u)                  (ties to the even multiple)
+//
+// S_{i-1} is a multiple of 2^k' (k' = level of the previous result).  If k <= k' it is also a multiple of
+// g and the step is a TRANSLATION, S_i = S_{i-1} + RN_g(a_i / u): sequential floating-point accumulation
+// degenerates into integer accumulation of quantised terms, and integer addition is associative.  Two
+// things make a step depend on the state itself:
+//   * a tie (the discarded part is exactly g/2): the winner is the neighbour that leaves S_i / g even;
+//   * an upward step k > k': S_{i-1} has set bits below g that take part in the rounding.
+// Both need ONE bit of the state when they happen on the lowest level (a tie at k = 0, a step 0 -> 1),
+// and that bit is bit 0 of (S_start + everything added so far).  A run is therefore summarised for both
+// parities of its start state (a two-state transducer; composition stays associative).  Anything that
+// would need a higher bit (ties at k >= 1, steps from k' >= 1, steps of two or more levels) marks the run
+// unusable: it is replayed sequentially.
+//
+// The levels k_i are PREDICTED from an approximate (unordered) running sum.  The prediction is verified,
+// not trusted: every element contributes the constraint "S_start + C_i lies strictly inside binade k_i"
+// (C_i = contributions so far), i.e. an interval for S_start, and so does the predicted level of the
+// start state.  A run is the translation `sum` iff lo <= S_start <= hi; spans concatenate like
+//     (a ++ b) = { a.sum + b.sum, max(a.lo, b.lo - a.sum), min(a.hi, b.hi - a.sum) }.
+// If the exact state satisfies the interval, every rounding above used the grid the FPU uses, so the
+// result is bit-identical to the sequential loop; if not, the caller falls back to the loop itself.
+#pragma once
+#include <stdint.h>
+#include <string.h>
+
+#if defined(__CUDACC__)
+#define PB_HD __host__ __device__ __forceinline__
+#else
+#define PB_HD static inline
+#endif
+
+#define PB_SPAN_MAX_LEVEL 8 /* levels 0..8 above the unit: |S| < 2^61 */
+
+struct PbSpan { long long sum, lo, hi; };
+struct PbSpan2 { PbSpan p[2]; }; // by bit 0 of the start state
+
+#define PB_SPAN_INF (1LL << 61)
+
+PB_HD long long pb_ll_max(long long a, long long b) { return a > b ? a : b; }
+PB_HD long long pb_ll_min(long long a, long long b) { return a < b ? a : b; }
+
+PB_HD PbSpan pb_span_identity() { PbSpan s; s.sum = 0; s.lo = -PB_SPAN_INF; s.hi = PB_SPAN_INF; return s; }
+PB_HD PbSpan pb_span_invalid() { PbSpan s; s.sum = 0; s.lo = PB_SPAN_INF; s.hi = -PB_SPAN_INF; return s; }
+PB_HD bool pb_span_valid(const PbSpan &s) { return s.lo <= s.hi; }
+
+// a ++ b (b's constraint applies to S_start + a.sum); an empty interval is absorbing
+PB_HD PbSpan pb_span_cat(const PbSpan &a, const PbSpan &b) {
+    if (!pb_span_valid(a) || !pb_span_valid(b)) return pb_span_invalid();
+    PbSpan r;
+    r.sum = a.sum + b.sum;
+    r.lo = pb_ll_max(a.lo, b.lo - a.sum);
+    r.hi = pb_ll_min(a.hi, b.hi - a.sum);
+    if (r.lo > r.hi) return pb_span_invalid();
+    return r;
+}
+
+PB_HD PbSpan2 pb_span2_identity() { PbSpan2 r; r.p[0] = r.p[1] = pb_span_identity(); return r; }
+
+PB_HD PbSpan2 pb_span2_cat(const PbSpan2 &a, const PbSpan2 &b) {
+    PbSpan2 r;
+    for (int p = 0; p < 2; p++) r.p[p] = pb_span_cat(a.p[p], b.p[(p + (int)(a.p[p].sum & 1LL)) & 1]);
+    return r;
+}
+
+PB_HD long long pb_double_bits(double d) {
+#if defined(__CUDA_ARCH__)
+    return __double_as_longlong(d);
+#else
+    long long b;
+    memcpy(&b, &d, 8);
+    return b;
+#endif
+}
+PB_HD double pb_bits_double(long long b) {
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double(b);
+#else
+    double d;
+    memcpy(&d, &b, 8);
+    return d;
+#endif
+}
+PB_HD int pb_exponent_of(double v) { return (int)((pb_double_bits(v) >> 52) & 0x7ff) - 1023; }
+PB_HD double pb_pow2(int e) { return pb_bits_double((long long)(e + 1023) << 52); } // -1022 <= e <= 1023
+
+// usable exponent range of a unit: scaling by 2^(52 - eref) must stay a normal power of two
+PB_HD bool pb_eref_ok(int eref) { return eref > -900 && eref < 900; }
+
+// a_i / u split into sign, integer part and fraction of the magnitude (all exact)
+struct PbQuant {
+    long long si; // signed integer part (truncated towards zero)
+    double f2;    // 2 * signed fraction, |f2| < 2
+    int bad;      // too large for the integer state (or NaN / Inf)
+};
+PB_HD PbQuant pb_quantise(double term, int eref) {
+    PbQuant q;
+    const double u = term * pb_pow2(52 - eref); // exact: power-of-two scaling (underflow only rounds
+                                                // magnitudes below 2^-1022 units, far below any tie)
+    const double au = u < 0 ? -u : u;
+    q.bad = !(au < 1152921504606846976.0); // 2^60
+    const long long ai = q.bad ? 0 : (long long)au;
+    const double af = q.bad ? 0.0 : au - (double)ai; // exact, in [0, 1)
+    q.si = u < 0 ? -ai : ai;
+    q.f2 = u < 0 ? -2.0 * af : 2.0 * af;
+    return q;
+}
+
+// One step on level k (g = 2^k units) from a state whose residue modulo g is Ls (0 unless this is the
+// upward step 0 -> 1, where Ls = bit 0 of the state).  Returns d = S_i - S_{i-1}; *tie is set when the
+// discarded part is exactly g / 2 (then d is the LOWER candidate and the caller decides).
+PB_HD long long pb_round_step(const PbQuant &q, int k, long long Ls, int *tie) {
+    const long long g = 1LL << k;
+    const long long t = Ls + q.si;
+    const long long low = t & (g - 1); // floor-mod: two's complement AND
+    const double D = (double)(g - 2 * low);
+    long long r;
+    *tie = 0;
+    if (k == 0) { // low == 0, D == 1: x = f in (-1, 1), candidates -1, 0, 1
+        if (q.f2 > 1.0) r = 1;
+        else if (q.f2 == 1.0) { r = 0; *tie = 1; }   // candidates 0 (lower), 1
+        else if (q.f2 > -1.0) r = 0;
+        else if (q.f2 == -1.0) { r = -1; *tie = 1; } // candidates -1 (lower), 0
+        else r = -1;
+    } else { // x = low + f in (-1, g + 1): candidates 0 and g
+        if (q.f2 > D) r = g;
+        else if (q.f2 == D) { r = 0; *tie = 1; }
+        else r = 0;
+    }
+    return q.si - low + r; // S_i = (S_{i-1} - Ls) + (t - low) + r
+}
+
+// Running state of a run being summarised (one per start parity when PARITY2).
+struct PbRun {
+    long long C[2]; // contributions so far, by start parity
+    long long lo[2], hi[2];
+    int kprev;      // level of the previous result (of the start state before the first element)
+    int bad;        // the run cannot be summarised
+    int sensitive;  // some step depended on the parity of the state
+};
+
+// constraint "S_start + C strictly inside binade level k on the side of sign(approx)"
+PB_HD void pb_run_constrain(PbRun &r, int p, int k, bool neg) {
+    const long long A = 1LL << (k + 52), B = 1LL << (k + 53);
+    const long long lo = (neg ? -B : A) + 1 - r.C[p], hi = (neg ? -A : B) - 1 - r.C[p];
+    r.lo[p] = pb_ll_max(r.lo[p], lo);
+    r.hi[p] = pb_ll_min(r.hi[p], hi);
+}
+
+// start a run: approx0 = predicted state before the first element.  Every run (a thread's share of a
+// block included) constrains its own start state, so neighbouring runs need not agree on the prediction:
+// if they do not, the concatenated interval is empty and the block is replayed.
+PB_HD void pb_run_begin(PbRun &r, double approx0, int eref) {
+    r.C[0] = r.C[1] = 0;
+    r.lo[0] = r.lo[1] = -PB_SPAN_INF;
+    r.hi[0] = r.hi[1] = PB_SPAN_INF;
+    r.bad = 0;
+    r.sensitive = 0;
+    const int k = pb_exponent_of(approx0) - eref;
+    if (k < 0 || k > PB_SPAN_MAX_LEVEL) { r.bad = 1; r.kprev = 0; return; }
+    r.kprev = k;
+    pb_run_constrain(r, 0, k, approx0 < 0);
+    pb_run_constrain(r, 1, k, approx0 < 0);
+}
+
+// one element; approx = predicted state AFTER it.  NV = 1: only the parity-0 variant is maintained and a
+// parity-dependent step just sets `sensitive` (the run is then redone with NV = 2).
+template <int NV>
+PB_HD void pb_run_push(PbRun &r, double term, double approx, int eref) {
+    const int k = pb_exponent_of(approx) - eref;
+    if (k < 0 || k > PB_SPAN_MAX_LEVEL) { r.bad = 1; return; }
+    const PbQuant q = pb_quantise(term, eref);
+    if (q.bad) { r.bad = 1; return; }
+    const bool up = k > r.kprev;
+    if (up && !(r.kprev == 0 && k == 1)) { r.bad = 1; return; } // needs bits above bit 0 of the state
+    const bool neg = approx < 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int p = 0; p < NV; p++) {
+        const long long bit0 = (p + r.C[p]) & 1LL; // bit 0 of S_{i-1}
+        int tie;
+        long long d = pb_round_step(q, k, up ? bit0 : 0, &tie);
+        if (up) r.sensitive = 1;
+        if (tie) {
+            if (k != 0 || up) { r.bad = 1; return; }
+            r.sensitive = 1;
+            // candidates d (lower) and d + 1: the one that leaves S_i even
+            if ((bit0 + d) & 1LL) d += 1;
+        }
+        r.C[p] += d;
+        pb_run_constrain(r, p, k, neg);
+    }
+    r.kprev = k;
+}
+
+template <int NV>
+PB_HD PbSpan2 pb_run_span(const PbRun &r) {
+    PbSpan2 s;
+    for (int p = 0; p < 2; p++) {
+        const int v = NV == 2 ? p : 0;
+        s.p[p].sum = r.C[v];
+        s.p[p].lo = r.lo[v];
+        s.p[p].hi = r.hi[v];
+        if (r.bad || s.p[p].lo > s.p[p].hi) s.p[p] = pb_span_invalid();
+    }
+    return s;
+}
+
+// exact state <-> integer in units of 2^(eref-52)
+PB_HD bool pb_state_to_units(double s, int eref, long long &S) {
+    const long long bits = pb_double_bits(s);
+    if ((bits << 1) == 0) { S = 0; return true; }
+    const int es = (int)((bits >> 52) & 0x7ff) - 1023, k0 = es - eref;
+    if (es < -1000 || es > 1000 || k0 < 0 || k0 > PB_SPAN_MAX_LEVEL) return false;
+    const long long M = ((bits & 0x000fffffffffffffLL) | (1LL << 52)) << k0;
+    S = bits < 0 ? -M : M;
+    return true;
+}
+// valid for states that passed a span's interval check (at most 53 significant bits)
+PB_HD double pb_units_to_state(long long S, int eref) { return (double)S * pb_pow2(eref - 52); }
+
+// apply a summarised run to the exact state; false = not applicable (replay it)
+PB_HD bool pb_span2_apply(const PbSpan2 &sp, int eref, double &s) {
+    long long S;
+    if (!pb_eref_ok(eref) || !pb_state_to_units(s, eref, S)) return false;
+    const PbSpan &v = sp.p[(int)(S & 1LL)];
+    if (!(S >= v.lo && S <= v.hi)) return false;
+    s = pb_units_to_state(S + v.sum, eref);
+    return true;
+}

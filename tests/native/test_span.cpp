@@ -1,0 +1,205 @@
+// CPU check of patolette_b200/csrc/pb_span.h: the block-summary arithmetic of the ordered sums,
+// emulated with the kernel's tiling (blocks of 512 elements, 8 consecutive elements per thread,
+// in-order tree composition), against the literal sequential loop.
+//
+//   g++ -O2 -ffp-contract=off -std=c++17 -I patolette_b200/csrc tests/native/test_span.cpp -o /tmp/test_span
+//
+// For every chain and block: if the summary accepts the exact start state, the state it produces must
+// be bit-identical to the sequential loop's.  Prints acceptance statistics per data family; exits 1 on
+// any mismatch.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <random>
+#include <string>
+#include <vector>
+
+#include "pb_span.h"
+
+static const int OB = 512, PER = 8, THREADS = OB / PER;
+
+struct Stats {
+    long blocks = 0, accepted = 0, wrong = 0, sensitive = 0, bad = 0, assoc_fail = 0;
+};
+
+static double tree_sum(const double *a, int n) {
+    if (n <= 0) return 0.0;
+    if (n == 1) return a[0];
+    return tree_sum(a, n / 2) + tree_sum(a + n / 2, n - n / 2);
+}
+
+static void summarise_block(const double *a, int cnt, double pstart, PbSpan2 &out, int &eref, bool &usable,
+                            bool &sensitive, Stats &st) {
+    // approximate running sums exactly as the kernel predicts them
+    double tl[THREADS], tstart[THREADS];
+    for (int t = 0; t < THREADS; t++) {
+        double s = 0;
+        for (int k = 0; k < PER; k++)
+            if (t * PER + k < cnt) s += a[t * PER + k];
+        tl[t] = s;
+    }
+    {
+        double run = 0;
+        for (int t = 0; t < THREADS; t++) { tstart[t] = pstart + run; run += tl[t]; }
+    }
+    int emin = 1 << 20, emax = -(1 << 20);
+    for (int t = 0; t < THREADS; t++) {
+        if (t * PER >= cnt) break;
+        double run = tstart[t];
+        int e = pb_exponent_of(run);
+        emin = e < emin ? e : emin; emax = e > emax ? e : emax;
+        for (int k = 0; k < PER; k++)
+            if (t * PER + k < cnt) {
+                run += a[t * PER + k];
+                e = pb_exponent_of(run);
+                emin = e < emin ? e : emin; emax = e > emax ? e : emax;
+            }
+    }
+    eref = emin;
+    usable = pb_eref_ok(emin) && pb_eref_ok(emax) && emax - emin <= PB_SPAN_MAX_LEVEL;
+    sensitive = false;
+    out = pb_span2_identity();
+    if (!usable) { st.bad++; return; }
+    std::vector<PbSpan2> spans;
+    for (int pass = 0; pass < 2; pass++) { // pass 0: single variant; pass 1: both parities if sensitive
+        spans.clear();
+        bool sens = false, bad = false;
+        for (int t = 0; t < THREADS; t++) {
+            if (t * PER >= cnt) break;
+            PbRun r;
+            pb_run_begin(r, tstart[t], eref);
+            double run = tstart[t];
+            for (int k = 0; k < PER; k++)
+                if (t * PER + k < cnt) {
+                    run += a[t * PER + k];
+                    if (pass == 0) pb_run_push<1>(r, a[t * PER + k], run, eref);
+                    else pb_run_push<2>(r, a[t * PER + k], run, eref);
+                }
+            sens |= r.sensitive != 0;
+            bad |= r.bad != 0;
+            spans.push_back(pass == 0 ? pb_run_span<1>(r) : pb_run_span<2>(r));
+        }
+        if (bad) { usable = false; st.bad++; return; }
+        if (pass == 0 && !sens) break;
+        sensitive = true;
+        if (pass == 0) continue;
+    }
+    // in-order composition: left fold and a balanced tree must agree (associativity)
+    PbSpan2 fold = spans[0];
+    for (size_t i = 1; i < spans.size(); i++) fold = pb_span2_cat(fold, spans[i]);
+    std::vector<PbSpan2> lvl = spans;
+    while (lvl.size() > 1) {
+        std::vector<PbSpan2> nx;
+        for (size_t i = 0; i < lvl.size(); i += 2)
+            nx.push_back(i + 1 < lvl.size() ? pb_span2_cat(lvl[i], lvl[i + 1]) : lvl[i]);
+        lvl.swap(nx);
+    }
+    for (int p = 0; p < 2; p++) {
+        const PbSpan &x = fold.p[p], &y = lvl[0].p[p];
+        const bool vx = pb_span_valid(x), vy = pb_span_valid(y);
+        if (vx != vy || (vx && (x.sum != y.sum || x.lo != y.lo || x.hi != y.hi))) st.assoc_fail++;
+    }
+    out = fold;
+    if (sensitive) st.sensitive++;
+}
+
+static void run_chain(const std::vector<double> &a, Stats &st) {
+    const size_t n = a.size();
+    const size_t nblk = (n + OB - 1) / OB;
+    std::vector<double> bsum(nblk), pstart(nblk);
+    for (size_t b = 0; b < nblk; b++) bsum[b] = tree_sum(&a[b * OB], (int)std::min<size_t>(OB, n - b * OB));
+    {
+        double run = 0;
+        for (size_t b = 0; b < nblk; b++) { pstart[b] = run; run += bsum[b]; }
+    }
+    double s = 0.0;
+    for (size_t b = 0; b < nblk; b++) {
+        const int cnt = (int)std::min<size_t>(OB, n - b * OB);
+        double truth = s;
+        for (int i = 0; i < cnt; i++) truth = truth + a[b * OB + i];
+        PbSpan2 sp;
+        int eref;
+        bool usable, sens;
+        summarise_block(&a[b * OB], cnt, pstart[b], sp, eref, usable, sens, st);
+        st.blocks++;
+        if (usable) {
+            double got = s;
+            if (pb_span2_apply(sp, eref, got)) {
+                st.accepted++;
+                if (pb_double_bits(got) != pb_double_bits(truth)) {
+                    st.wrong++;
+                    if (st.wrong < 5)
+                        fprintf(stderr, "  MISMATCH block %zu: start %a truth %a got %a eref %d sens %d\n", b, s, truth, got,
+                                eref, (int)sens);
+                }
+            }
+        }
+        s = truth;
+    }
+}
+
+int main(int argc, char **argv) {
+    const int reps = argc > 1 ? atoi(argv[1]) : 6;
+    std::mt19937_64 rng(12345);
+    std::uniform_real_distribution<double> U(0.0, 1.0);
+    std::normal_distribution<double> G(0.0, 1.0);
+    struct Family { std::string name; int kind; };
+    const Family fams[] = {
+        {"uniform positive", 0},      {"weighted positive (w in 1..1025)", 1}, {"centred products (hovering)", 2},
+        {"centred squares", 3},       {"dyadic 2^-8 (ties)", 4},               {"dyadic products hovering", 5},
+        {"tiny cancellation", 6},     {"sign-changing drift", 7},              {"spikes", 8},
+        {"sorted ascending", 9},      {"integers (exact)", 10},                {"wide dynamic range", 11},
+        {"alternating near power of two", 12},     {"mean-centred products (zero-drift walk)", 13},
+        {"mean-centred, weakly correlated", 14},
+    };
+    long total_wrong = 0, total_assoc = 0;
+    for (const Family &f : fams) {
+        Stats st;
+        for (int rep = 0; rep < reps; rep++) {
+            const size_t n = (size_t)(1000 + (rng() % 400000));
+            std::vector<double> a(n);
+            const double mu = U(rng), mu2 = U(rng);
+            for (size_t i = 0; i < n; i++) {
+                double v = 0;
+                switch (f.kind) {
+                case 0: v = U(rng); break;
+                case 1: v = U(rng) * (double)(1 + rng() % 1025); break;
+                case 2: v = (U(rng) - mu) * (U(rng) - mu2); break;
+                case 3: { double d = U(rng) - mu; v = d * d; break; }
+                case 4: v = (double)(rng() % 257) / 256.0; break;
+                case 5: v = ((double)(rng() % 257) / 256.0 - 0.5) * ((double)(rng() % 257) / 256.0 - 0.5); break;
+                case 6: v = (i & 1) ? 1.0 + 1e-9 * U(rng) : -1.0 + 1e-9 * U(rng); break;
+                case 7: v = G(rng) + 0.01 * sin((double)i * 1e-4); break;
+                case 8: v = (rng() % 5000 == 0) ? 1e6 * U(rng) : U(rng) * 1e-3; break;
+                case 9: v = (double)i / (double)n; break;
+                case 10: v = (double)(long)(rng() % 2001) - 1000.0; break;
+                case 11: v = ldexp(G(rng), (int)(rng() % 60) - 30); break;
+                case 12: v = ((i & 1) ? -1.0 : 1.0) * (0.25 + 1e-3 * U(rng)) + ((i % 64 == 0) ? 1.0 / 64 : 0.0); break;
+                }
+                a[i] = v;
+            }
+            if (f.kind == 13 || f.kind == 14) { // off-diagonal covariance terms of (nearly) independent channels
+                std::vector<double> x(n), y(n);
+                double mx = 0, my = 0;
+                for (size_t i = 0; i < n; i++) {
+                    x[i] = U(rng);
+                    y[i] = f.kind == 14 ? 0.02 * x[i] + U(rng) : U(rng);
+                    mx += x[i]; my += y[i];
+                }
+                mx *= 1.0 / (double)n; my *= 1.0 / (double)n;
+                for (size_t i = 0; i < n; i++) a[i] = (x[i] - mx) * (y[i] - my);
+            }
+            if (f.kind == 12) a[0] = 1.0; // start right at a power of two and wobble around it
+            run_chain(a, st);
+        }
+        printf("%-36s blocks %7ld accepted %6.2f%% sensitive %5.2f%% unusable %5.2f%% wrong %ld assoc %ld\n", f.name.c_str(),
+               st.blocks, 100.0 * st.accepted / st.blocks, 100.0 * st.sensitive / st.blocks, 100.0 * st.bad / st.blocks,
+               st.wrong, st.assoc_fail);
+        total_wrong += st.wrong;
+        total_assoc += st.assoc_fail;
+    }
+    if (total_wrong || total_assoc) { printf("FAIL\n"); return 1; }
+    printf("OK\n");
+    return 0;
+}
