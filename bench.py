@@ -246,7 +246,7 @@ def run_ours(args):
 
     # ---------------- per-kernel profile (untimed extra step) -> roofline ----------------
     lib.patolette_b200_set_stream(C.c_void_p(stream.cuda_stream), 1)
-    cnt = (C.c_ulonglong * 8)()
+    cnt = (C.c_ulonglong * 16)()
     lib.patolette_b200_ordered_counts(cnt, 1)
     lib.patolette_b200_profile_enable(1)
     step_resident()
@@ -298,7 +298,11 @@ def run_ours(args):
         "ordered_sums": {"blocks_accepted": ord_acc, "blocks_replayed": ord_rep,
                          "replay_frac": ord_rep / max(ord_acc + ord_rep, 1),
                          "replay_reasons": {"flag": int(cnt[2]), "binade_guess": int(cnt[3]), "bounds": int(cnt[4])},
-                         "replay_rounds": int(cnt[5]), "elementwise_subchunks": int(cnt[6])},
+                         "replay_rounds": int(cnt[5]), "elementwise_subchunks": int(cnt[6]),
+                         "accepted_two_parity": int(cnt[7]),
+                         "resolve_warp_Mcycles": {"scan_walk": round(int(cnt[8]) / 1e6, 2), "two_parity": round(int(cnt[9]) / 1e6, 2),
+                                                  "replay": round(int(cnt[10]) / 1e6, 2), "slowest_warp": round(int(cnt[12]) / 1e6, 3)},
+                         "record_groups": int(cnt[11])},
     }
     if cpu_baseline is not None:
         line["cpu_baseline"] = cpu_baseline

@@ -119,10 +119,15 @@ PB200_API int patolette_b200_set_stream(void *cuda_stream, int enable);
 PB200_API int patolette_b200_profile_enable(int on);
 PB200_API size_t patolette_b200_profile_json(char *buf, size_t cap);
 
-/* Ordered-sum statistics since the last reset (pb_ordered.cu), 8 counters: (chain, block) pairs
- * accepted from their quantised summary, pairs replayed, replay reasons {tie/unquantisable flag,
- * wrong binade guess, binade bounds}, replay rounds, element-wise 16-element sub-chunks, spare. */
-PB200_API int patolette_b200_ordered_counts(unsigned long long *out8, int reset);
+/* Ordered-sum statistics since the last reset (pb_ordered.cu), 16 counters: (chain, block) pairs
+ * accepted from their summary record, pairs replayed, replay reasons {unusable record, state not
+ * expressible in the block's unit, interval}, replay rounds, element-wise sub-chunks, pairs accepted
+ * through a two-parity record, SM cycles of the resolving warps in {scan walk, two-parity records,
+ * replays}, record groups loaded, cycles of the slowest resolving warp, 3 spare. */
+PB200_API int patolette_b200_ordered_counts(unsigned long long *out16, int reset);
+/* Debug: per chain of the centred pass {cycles scan walk, cycles record walk, cycles replays, replays,
+ * records walked one by one}, 7 x 5 counters. */
+PB200_API int patolette_b200_ordered_chain_debug(unsigned long long *out35, int reset);
 
 /* Timings of the last patolette() call on this process, milliseconds (CUDA events
  * on the library's stream; h2d/d2h include the host copies).  Keys in order:

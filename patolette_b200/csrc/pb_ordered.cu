@@ -38,14 +38,14 @@ namespace {
 
 constexpr int OB = 512;         // elements per summary block
 constexpr int OB_THREADS = 128; // S1: 4 elements per thread
-constexpr int E_NOGUESS = 0x7fffffff;
-constexpr double MAGIC = 6755399441055744.0; // 1.5 * 2^52: (t + MAGIC) - MAGIC == rint(t) for |t| < 2^51
-constexpr double TWO51 = 2251799813685248.0;
-constexpr long long TWO52 = 1LL << 52, TWO53 = 1LL << 53;
 
 // 0 accepted, 1 replayed, 2 unusable record, 3 state not expressible in the block's unit, 4 interval,
 // 5 replay rounds, 6 element-wise sub-chunks, 7 blocks accepted through the two-parity record
-__device__ unsigned long long g_ord_counts[8];
+// 8 cycles in scan-walk, 9 cycles in two-parity records, 10 cycles in replays, 11 record-group loads,
+// 12 cycles of the slowest resolving warp seen
+__device__ unsigned long long g_ord_counts[16];
+// per chain of the centred pass (debug): cycles in {scan walk, record walk, replays}, replays, general-path records
+__device__ unsigned long long g_ord_chain[7][5];
 
 // One block of one chain.  flag: see F_*.
 struct OrdRec {
@@ -206,6 +206,13 @@ struct SumShared {
     int flag[7];
 };
 
+// The general element step, out of line: it is the rare path (threads whose predictions change level or
+// sign) and keeping it out of the main body keeps the common path's register footprint small.
+template <int NV>
+__device__ __noinline__ void run_push_slow(PbRun *r, double term, double approx, int eref) {
+    pb_run_push<NV>(*r, term, approx, eref);
+}
+
 // Summarises block `blk` of segment `sg` for every chain with need[c] (NV = 1: one record, parity-dependent
 // blocks are left F_PENDING; NV = 2: both parities).  All threads of the CTA take part.
 template <int KIND, bool W, int NV>
@@ -213,10 +220,12 @@ __device__ __forceinline__ bool summarise_block(const PbPlanes &P, const PbSeg &
                                                 double m2, const double *__restrict__ pstart, OrdRec *__restrict__ rec0,
                                                 OrdRec *__restrict__ rec1, const bool *need, SumShared &sh) {
     constexpr int C = NChains<KIND>::C;
+    constexpr int NOLEVEL = -(1 << 20);
     const uint32_t nblk = (sg.n + OB - 1) / OB;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t i0 = blk * OB + threadIdx.x * OS_PER; // this thread's consecutive elements
     const bool have = i0 < sg.n;
+    const int mycnt = have ? min(OS_PER, (int)(sg.n - i0)) : 0;
     if (threadIdx.x < C) sh.flag[threadIdx.x] = 0;
 
     // ---- phase 1: approximate running sum at the start of this thread's elements ------------------
@@ -227,7 +236,7 @@ __device__ __forceinline__ bool summarise_block(const PbPlanes &P, const PbSeg &
         for (int c = 0; c < C; c++) tl[c] = 0.0;
 #pragma unroll
         for (int k = 0; k < OS_PER; k++) {
-            if (i0 + k < sg.n) {
+            if (k < mycnt) {
                 const size_t p = (size_t)sg.lo + i0 + k;
                 double t[C];
                 terms_all<KIND, W>(W ? P.w[p] : 1.0, P.c[0][p], P.c[1][p], P.c[2][p], m0, m1, m2, t);
@@ -237,6 +246,8 @@ __device__ __forceinline__ bool summarise_block(const PbPlanes &P, const PbSeg &
         }
 #pragma unroll
         for (int c = 0; c < C; c++) {
+            tstart[c] = 0.0;
+            if (!need[c]) continue; // CTA-uniform
             double incl = tl[c];
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -248,22 +259,31 @@ __device__ __forceinline__ bool summarise_block(const PbPlanes &P, const PbSeg &
         }
         __syncthreads();
 #pragma unroll
-        for (int c = 0; c < C; c++) tstart[c] += pstart[c] + (warp ? sh.wsum[c] : 0.0);
+        for (int c = 0; c < C; c++)
+            if (need[c]) tstart[c] += pstart[c] + (warp ? sh.wsum[c] : 0.0);
     }
-    // ---- phase 2: binade range of the predicted partial sums (start states included) --------------
+    // ---- phase 2: predicted binade of every partial sum (start states included) -> range over the block;
+    //      at the same time the cheap summary, valid if this thread's predictions all sit on one level:
+    //      it works in the ulp of the thread's own level, the block's unit is not needed yet ----------------
+    int tlevel[C]; // the thread's (absolute) level if uniform in binade and sign, else NOLEVEL
+    PbUni uni[C];
     {
         int emin[C], emax[C];
-        double run[C];
+        double run[C], uscale[C];
+        bool flip[C];
 #pragma unroll
         for (int c = 0; c < C; c++) {
             run[c] = tstart[c];
             const int e = pb_exponent_of(run[c]);
             emin[c] = have ? e : (1 << 20);
-            emax[c] = have ? e : -(1 << 20);
+            emax[c] = have ? e : NOLEVEL;
+            flip[c] = false;
+            pb_uni_begin(uni[c]);
+            uscale[c] = (NV == 1 && pb_eref_ok(e)) ? pb_pow2(52 - e) : 0.0;
         }
 #pragma unroll
         for (int k = 0; k < OS_PER; k++) {
-            if (i0 + k < sg.n) {
+            if (k < mycnt) {
                 const size_t p = (size_t)sg.lo + i0 + k;
                 double t[C];
                 terms_all<KIND, W>(W ? P.w[p] : 1.0, P.c[0][p], P.c[1][p], P.c[2][p], m0, m1, m2, t);
@@ -273,11 +293,15 @@ __device__ __forceinline__ bool summarise_block(const PbPlanes &P, const PbSeg &
                     const int e = pb_exponent_of(run[c]);
                     emin[c] = min(emin[c], e);
                     emax[c] = max(emax[c], e);
+                    flip[c] |= (run[c] < 0) != (tstart[c] < 0);
+                    if (NV == 1) pb_uni_push(uni[c], t[c], uscale[c]);
                 }
             }
         }
 #pragma unroll
         for (int c = 0; c < C; c++) {
+            tlevel[c] = (have && emin[c] == emax[c] && !flip[c]) ? emin[c] : NOLEVEL;
+            if (!need[c]) continue; // CTA-uniform
 #pragma unroll
             for (int o = 16; o; o >>= 1) {
                 emin[c] = min(emin[c], __shfl_xor_sync(0xffffffffu, emin[c], o));
@@ -287,10 +311,11 @@ __device__ __forceinline__ bool summarise_block(const PbPlanes &P, const PbSeg &
         }
         __syncthreads();
     }
-    // ---- phase 3: spans on the predicted grids, in units of the lowest binade ----------------------
+    // ---- phase 3: spans in units of the block's lowest binade -----------------------------------------
     int eref[C];
-    bool usable[C];
+    bool usable[C], slow[C];
     PbRun run_st[C];
+    bool any_slow = false;
 #pragma unroll
     for (int c = 0; c < C; c++) {
         const int lo = min(sh.emin[0][c], sh.emin[1][c]), hi = max(sh.emax[0][c], sh.emax[1][c]);
@@ -298,58 +323,68 @@ __device__ __forceinline__ bool summarise_block(const PbPlanes &P, const PbSeg &
         // zero / subnormal / non-finite predictions, or too wide a range: replay
         usable[c] = need[c] && pb_eref_ok(lo) && pb_eref_ok(hi) && hi - lo <= PB_SPAN_MAX_LEVEL;
         if (!usable[c]) eref[c] = 0;
-        pb_run_begin(run_st[c], tstart[c], eref[c]);
+        const bool fast = NV == 1 && usable[c] && tlevel[c] != NOLEVEL;
+        slow[c] = usable[c] && have && !fast;
+        any_slow |= slow[c];
+        if (fast) pb_uni_end(uni[c], run_st[c], tlevel[c] - eref[c], tstart[c] < 0);
+        else pb_run_begin(run_st[c], tstart[c], eref[c]);
     }
-    if (have) {
+    if (any_slow) { // the general path, element by element, for the chains of this thread that need it
         double run[C];
 #pragma unroll
         for (int c = 0; c < C; c++) run[c] = tstart[c];
+#pragma unroll 1
+        for (int k = 0; k < mycnt; k++) {
+            const size_t p = (size_t)sg.lo + i0 + k;
+            double t[C];
+            terms_all<KIND, W>(W ? P.w[p] : 1.0, P.c[0][p], P.c[1][p], P.c[2][p], m0, m1, m2, t);
 #pragma unroll
-        for (int k = 0; k < OS_PER; k++) {
-            if (i0 + k < sg.n) {
-                const size_t p = (size_t)sg.lo + i0 + k;
-                double t[C];
-                terms_all<KIND, W>(W ? P.w[p] : 1.0, P.c[0][p], P.c[1][p], P.c[2][p], m0, m1, m2, t);
-#pragma unroll
-                for (int c = 0; c < C; c++) {
-                    run[c] += t[c]; // same operations as phase 2: same predictions
-                    if (usable[c] && !run_st[c].bad) pb_run_push<NV>(run_st[c], t[c], run[c], eref[c]);
-                }
+            for (int c = 0; c < C; c++) {
+                run[c] += t[c]; // same operations as phase 2: same predictions
+                if (slow[c] && !run_st[c].bad) run_push_slow<NV>(&run_st[c], t[c], run[c], eref[c]);
             }
         }
     }
-    bool pending = false;
+    // in-order composition over the warp (lane i absorbs lane i + o), all chains interleaved
+    PbSpan2 v[C];
 #pragma unroll
     for (int c = 0; c < C; c++) {
+        v[c] = pb_span2_identity();
         if (!need[c]) continue; // CTA-uniform
-        PbSpan2 v = pb_span2_identity();
         if (usable[c] && have) {
-            v = pb_run_span<NV>(run_st[c]);
+            v[c] = pb_run_span<NV>(run_st[c]);
             const int f = (run_st[c].bad ? 1 : 0) | (run_st[c].sensitive ? 2 : 0);
             if (f) atomicOr(&sh.flag[c], f);
         }
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { // in-order tree: lane i absorbs lane i + o
+        for (int o = 1; o < 32; o <<= 1) {
             PbSpan2 r;
-            r.p[0] = shfl_down_span(v.p[0], o);
-            if (NV == 2) r.p[1] = shfl_down_span(v.p[1], o);
+            r.p[0] = shfl_down_span(v[c].p[0], o);
+            if (NV == 2) r.p[1] = shfl_down_span(v[c].p[1], o);
             else r.p[1] = r.p[0];
             if ((lane & (2 * o - 1)) == 0) {
-                if (NV == 2) v = pb_span2_cat(v, r);
-                else { v.p[0] = pb_span_cat(v.p[0], r.p[0]); v.p[1] = v.p[0]; }
+                if (NV == 2) v[c] = pb_span2_cat(v[c], r);
+                else { v[c].p[0] = pb_span_cat(v[c].p[0], r.p[0]); v[c].p[1] = v[c].p[0]; }
             }
         }
-        if (warp == 0 && lane == 0) sh.span[c] = v;
-        __syncthreads();
-        if (warp == 1 && lane == 0) {
+        if (warp == 0 && lane == 0) sh.span[c] = v[c];
+    }
+    __syncthreads();
+    bool pending = false;
+    if (warp == 1 && lane == 0) {
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+            if (!need[c]) continue;
             PbSpan2 w;
-            if (NV == 2) w = pb_span2_cat(sh.span[c], v);
-            else { w.p[0] = pb_span_cat(sh.span[c].p[0], v.p[0]); w.p[1] = w.p[0]; }
+            if (NV == 2) w = pb_span2_cat(sh.span[c], v[c]);
+            else { w.p[0] = pb_span_cat(sh.span[c].p[0], v[c].p[0]); w.p[1] = w.p[0]; }
             const int f = sh.flag[c];
             int flag;
             if (!usable[c] || (f & 1)) flag = F_REPLAY;
             else if (NV == 1) flag = (f & 2) ? F_PENDING : F_OK;
-            else flag = F_SENSITIVE;
+            // a parity-dependent block whose start state sits above its lowest binade (enforced by its own
+            // start constraint) only ever sees parity 0: variant 0 of the two-parity composition is a plain record
+            else flag = pb_exponent_of(pstart[c]) - eref[c] < 1 ? F_SENSITIVE : F_OK;
             // contradictory predictions (empty interval): never applicable.  A two-parity record stays
             // usable if one parity is valid; the resolve checks the interval of the parity it needs.
             if (flag == F_OK && !pb_span_valid(w.p[0])) flag = F_REPLAY;
@@ -419,126 +454,39 @@ __global__ void __launch_bounds__(OS_THREADS) k_ord_summary2(PbPlanes b0, PbPlan
 }
 
 // ---- S4: ordered resolve ---------------------------------------------------------------------------
-constexpr int SUB = OB / 32; // elements per lane in a replay
-
-__device__ __forceinline__ long long warp_incl_scan(long long v, int lane) {
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const long long u = __shfl_up_sync(0xffffffffu, v, o);
-        if (lane >= o) v += u;
-    }
-    return v;
-}
-
-// One lane's 16 elements quantised against binade e: total, prefix extremes, exclusive prefix of the
-// totals over the lanes before it, and whether the sub-chunk is unusable (unquantisable term, or a tie,
-// whose rounding depends on the parity of the state - such a sub-chunk is simply added element-wise).
-// The state provably stays inside binade e (prefix extremes checked against (2^52, 2^53)), so every
-// step is the translation rint(a / q).
-struct SubVer {
-    int e;
-    int bad;
-    long long sum, mn, mx, pre;
+// One CTA per cluster, one WARP per chain; the warp carries the exact running sum, as an integer in the
+// unit of the records it is walking (pb_span.h: PbState).  Records are fetched 32 at a time, one group
+// ahead.  A group of plain records that share their unit is applied with one in-order warp scan of the
+// span monoid + a ballot for the first record whose interval does not hold.  Any other group (parity-
+// dependent records, unit changes, unusable records) is staged in shared memory and walked record by
+// record - a dozen integer operations each.  A record that cannot be applied means its block is REPLAYED:
+// the block's terms are staged in shared memory (coalesced) and added one by one - the reference loop.
+struct ResolveShared {
+    double terms[7][OB];
+    long long sum[7][2][32], lo[7][2][32], hi[7][2][32];
+    int eref[7][32], flag[7][32];
+    double res[7];
 };
 
-__device__ __forceinline__ SubVer quantise_sub(const double *t, int my, int e, int lane) {
-    SubVer v;
-    v.e = e;
-    const double scale = scalbn(1.0, 52 - e);
-    double sum = 0.0, mn = 1e300, mx = -1e300;
-    int bad = my == 0;
-#pragma unroll
-    for (int k = 0; k < SUB; k++) {
-        if (k < my) {
-            const double u = __dmul_rn(t[k], scale);
-            const double d = __dsub_rn(__dadd_rn(u, MAGIC), MAGIC);
-            bad |= !(fabs(u) < TWO51) | (fabs(__dsub_rn(u, d)) == 0.5);
-            sum += d;
-            mn = fmin(mn, sum);
-            mx = fmax(mx, sum);
-        }
-    }
-    v.bad = bad;
-    v.sum = bad ? 0 : (long long)sum;
-    v.mn = bad ? 0 : (long long)mn;
-    v.mx = bad ? 0 : (long long)mx;
-    v.pre = warp_incl_scan(v.sum, lane) - v.sum;
-    return v;
-}
-
-// Replays one block exactly.  The exact state s is known, so each lane quantises its 16 consecutive
-// elements against the TRUE binade; prefix totals are scanned once per binade, after which finding the
-// first sub-chunk that cannot be applied is one ballot: lane l checks its own prefix extremes against
-// the state it would start from if every lane before it is applied.  Accepted sub-chunks are applied in
-// one step, the failing one (where the binade changes, or a tie sits) is added element by element - the
-// literal reference loop - and the walk resumes behind it with the quantisation of the new binade.
-// Sums that wander around a power of two bounce between adjacent binades, so the last three
-// quantisations are kept.
 template <int KIND, bool W>
 __device__ __forceinline__ double replay_block(const PbPlanes &P, size_t first, uint32_t cnt, int chain, double m0,
-                                               double m1, double m2, double s, int lane) {
-    double t[SUB];
-    const int my = max(0, min(SUB, (int)cnt - lane * SUB));
+                                               double m1, double m2, double s, int lane, double *sm) {
+    double t[OB / 32];
 #pragma unroll
-    for (int k = 0; k < SUB; k++) {
-        t[k] = 0.0;
-        if (k < my) {
-            const size_t p = first + (size_t)lane * SUB + k;
-            t[k] = term_one<KIND, W>(chain, W ? P.w[p] : 1.0, P.c[0][p], P.c[1][p], P.c[2][p], m0, m1, m2);
+    for (int q = 0; q < OB / 32; q++) { // all loads in flight at once: nothing is stored until every term is in a register
+        const uint32_t k = q * 32 + lane;
+        t[q] = 0.0;
+        if (k < cnt) {
+            const size_t p = first + k;
+            t[q] = term_one<KIND, W>(chain, W ? P.w[p] : 1.0, P.c[0][p], P.c[1][p], P.c[2][p], m0, m1, m2);
         }
     }
-    const uint32_t nl = (cnt + SUB - 1) / SUB; // lanes that hold elements
-    uint32_t next = 0;
-    unsigned int rounds = 0, elementwise = 0;
-    SubVer v0, v1, v2;
-    v0.e = v1.e = v2.e = E_NOGUESS;
-    int victim = 0;
-    while (next < nl) {
-        rounds++;
-        const long long bits = __double_as_longlong(s);
-        const int ef = (int)((bits >> 52) & 0x7ff);
-        uint32_t f = next;
-        if (ef > 24 && ef < 2000) { // a normal, finite state
-            const int es = ef - 1023;
-            if (v0.e != es && v1.e != es && v2.e != es) {
-                const SubVer nv = quantise_sub(t, my, es, lane);
-                if (victim == 0) v0 = nv; else if (victim == 1) v1 = nv; else v2 = nv;
-                victim = victim == 2 ? 0 : victim + 1;
-            }
-            const SubVer &v = v0.e == es ? v0 : (v1.e == es ? v1 : v2);
-            const long long M = (bits & 0x000fffffffffffffLL) | TWO52; // |s| / q
-            const bool negs = bits < 0;
-            const long long p = v.pre - __shfl_sync(0xffffffffu, v.pre, (int)next); // lanes [next, lane)
-            const long long cur = negs ? M - p : M + p;
-            const long long vmin = negs ? cur - v.mx : cur + v.mn, vmax = negs ? cur - v.mn : cur + v.mx;
-            const bool mine = lane >= (int)next && lane < (int)nl;
-            const bool valid = !v.bad && vmin > TWO52 && vmax < TWO53;
-            const unsigned fails = __ballot_sync(0xffffffffu, mine && !valid);
-            f = fails ? (uint32_t)(__ffs(fails) - 1) : nl;
-            if (f > next) {
-                const long long acc = __shfl_sync(0xffffffffu, p + v.sum, (int)f - 1); // total of lanes [next, f)
-                const long long M2 = negs ? M - acc : M + acc;
-                s = __longlong_as_double((bits & 0xfff0000000000000LL) | (M2 & 0x000fffffffffffffLL));
-            }
-        }
-        if (f < nl) { // sub-chunk f: element by element (binade change, tie, or a zero / subnormal state)
-            double v = s;
-            if (lane == (int)f) {
 #pragma unroll
-                for (int k = 0; k < SUB; k++)
-                    if (k < my) v = __dadd_rn(v, t[k]);
-            }
-            s = __shfl_sync(0xffffffffu, v, (int)f);
-            next = f + 1;
-            elementwise++;
-        } else {
-            next = nl;
-        }
-    }
-    if (lane == 0) {
-        atomicAdd(&g_ord_counts[5], (unsigned long long)rounds);
-        atomicAdd(&g_ord_counts[6], (unsigned long long)elementwise);
-    }
+    for (int q = 0; q < OB / 32; q++) sm[q * 32 + lane] = t[q];
+    __syncwarp();
+#pragma unroll 16
+    for (uint32_t i = 0; i < cnt; i++) s = __dadd_rn(s, sm[i]); // every lane runs the same chain (broadcast reads)
+    __syncwarp();
     return s;
 }
 
@@ -550,107 +498,138 @@ __global__ void __launch_bounds__(32 * NChains<KIND>::C) k_ord_resolve(PbPlanes 
                                                                        const OrdRec *__restrict__ rec1,
                                                                        bool use_summaries) {
     constexpr int C = NChains<KIND>::C;
-    __shared__ double s_res[C];
+    __shared__ ResolveShared sh;
     const int seg = blockIdx.x, chain = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const PbSeg sg = segs[seg];
     const PbPlanes &P = sg.buf ? b1 : b0;
     const uint32_t n = sg.n, nblk = (n + OB - 1) / OB;
     double m0 = 0, m1 = 0, m2 = 0;
     if (KIND == KIND_CENTERED) { m0 = stats[seg].mean[0]; m1 = stats[seg].mean[1]; m2 = stats[seg].mean[2]; }
-    double s = 0.0; // exact running sum of this warp's chain
-    unsigned int n_acc = 0, n_rep = 0, n_acc2 = 0, n_why[3] = {0, 0, 0};
+    double sd = 0.0;                          // the exact running sum, authoritative while !st.ok
+    PbState st = pb_state_from_double(sd);    // ... and as integer * unit while st.ok
+    unsigned int n_acc = 0, n_rep = 0, n_acc2 = 0, n_gen = 0, n_why[3] = {0, 0, 0};
+    long long cyc[3] = {0, 0, 0}, t_begin = clock64();
     const size_t row0 = rec_row(sg, C, chain, nblk, 0);
+    OrdRec dummy;
+    dummy.sum = 0; dummy.lo = 1; dummy.hi = 0; dummy.eref = 0; dummy.flag = F_REPLAY;
+    OrdRec nr = dummy, nr1 = dummy; // records of the next group, loaded one group ahead
+    if (use_summaries && lane < (int)nblk) { nr = rec0[row0 + lane]; nr1 = rec1[row0 + lane]; }
     for (uint32_t g0 = 0; g0 < nblk; g0 += 32) {
         const uint32_t gcnt = min(32u, nblk - g0);
-        OrdRec r, r1;
-        r.sum = 0; r.lo = 1; r.hi = 0; r.eref = 0; r.flag = F_REPLAY;
-        if (use_summaries && lane < (int)gcnt) r = rec0[row0 + g0 + lane];
-        r1 = r;
-        if (r.flag == F_SENSITIVE) r1 = rec1[row0 + g0 + lane];
+        const OrdRec r = nr, r1 = nr1; // r1 is only meaningful where r.flag == F_SENSITIVE
+        nr = dummy;
+        nr1 = dummy;
+        if (use_summaries && g0 + 32 + lane < nblk) { nr = rec0[row0 + g0 + 32 + lane]; nr1 = rec1[row0 + g0 + 32 + lane]; }
+        if (use_summaries && g0 + 32 * 5 + lane < nblk) { // pull the records of the group four further ahead into L1
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(rec0 + row0 + g0 + 32 * 5 + lane));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(rec1 + row0 + g0 + 32 * 5 + lane));
+        }
         uint32_t next = 0;
-        while (next < gcnt) {
-            const int fl0 = __shfl_sync(0xffffffffu, r.flag, (int)next), e0 = __shfl_sync(0xffffffffu, r.eref, (int)next);
-            bool handled = false;
-            int why = 0;
-            if (fl0 == F_OK) {
-                long long S = 0;
-                if (pb_eref_ok(e0) && pb_state_to_units(s, e0, S)) {
-                    // maximal run of plain records with the same unit starting at `next`
-                    const bool okl = lane >= (int)next && r.flag == F_OK && r.eref == e0; // lanes >= gcnt hold F_REPLAY
-                    const unsigned notok = __ballot_sync(0xffffffffu, lane >= (int)next && !okl);
-                    const uint32_t runend = notok ? (uint32_t)(__ffs(notok) - 1) : 32u;
-                    PbSpan v = pb_span_identity();
-                    if (lane >= (int)next && lane < (int)runend) { v.sum = r.sum; v.lo = r.lo; v.hi = r.hi; }
+        // ---- fast path: the whole group is plain and shares its unit ------------------------------------
+        long long t0 = clock64();
+        const int e0 = __shfl_sync(0xffffffffu, r.eref, 0);
+        const bool uniform = __all_sync(0xffffffffu, lane >= (int)gcnt || (r.flag == F_OK && r.eref == e0));
+        if (uniform && pb_state_rebase(st, e0)) {
+            PbSpan v = pb_span_identity();
+            if (lane < (int)gcnt) { v.sum = r.sum; v.lo = r.lo; v.hi = r.hi; }
 #pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) { // in-order inclusive scan of the monoid
-                        const PbSpan up = shfl_up_span(v, o);
-                        if (lane >= o) v = pb_span_cat(up, v);
-                    }
-                    const bool mine = lane >= (int)next && lane < (int)runend;
-                    const bool valid = pb_span_valid(v) && S >= v.lo && S <= v.hi;
-                    const unsigned fails = __ballot_sync(0xffffffffu, mine && !valid);
-                    const uint32_t f = fails ? (uint32_t)(__ffs(fails) - 1) : runend;
-                    if (f > next) {
-                        const long long acc = __shfl_sync(0xffffffffu, v.sum, (int)f - 1);
-                        s = pb_units_to_state(S + acc, e0); // exact: at most 53 significant bits by the last constraint
-                        n_acc += f - next;
-                        next = f;
-                        handled = true;
-                    } else {
-                        why = 2; // the very first record's interval does not hold
-                    }
-                } else {
-                    why = 1;
-                }
-            } else if (fl0 == F_SENSITIVE) {
-                double s2 = s;
-                int ok = 0;
-                if (lane == (int)next) {
-                    PbSpan2 sp;
-                    sp.p[0].sum = r.sum; sp.p[0].lo = r.lo; sp.p[0].hi = r.hi;
-                    sp.p[1].sum = r1.sum; sp.p[1].lo = r1.lo; sp.p[1].hi = r1.hi;
-                    ok = pb_span2_apply(sp, r.eref, s2) ? 1 : 0;
-                }
-                ok = __shfl_sync(0xffffffffu, ok, (int)next);
-                if (ok) {
-                    s = __shfl_sync(0xffffffffu, s2, (int)next);
-                    n_acc++;
-                    n_acc2++;
-                    next++;
-                    handled = true;
-                } else {
-                    why = 2;
-                }
+            for (int o = 1; o < 32; o <<= 1) { // in-order inclusive scan of the monoid
+                const PbSpan up = shfl_up_span(v, o);
+                if (lane >= o) v = pb_span_cat(up, v);
             }
-            if (!handled) {
-                const uint32_t base = (g0 + next) * OB;
-                s = replay_block<KIND, W>(P, (size_t)sg.lo + base, min((uint32_t)OB, n - base), chain, m0, m1, m2, s, lane);
-                n_rep++;
-                n_why[why]++;
-                next++;
+            const bool valid = pb_span_valid(v) && st.S >= v.lo && st.S <= v.hi;
+            const unsigned fails = __ballot_sync(0xffffffffu, lane < (int)gcnt && !valid);
+            const uint32_t f = fails ? (uint32_t)(__ffs(fails) - 1) : gcnt;
+            if (f > 0) {
+                st.S += __shfl_sync(0xffffffffu, v.sum, (int)f - 1);
+                n_acc += f;
+                next = f;
             }
         }
+        cyc[0] += clock64() - t0;
+        if (next >= gcnt) continue;
+        // ---- general path: stage the records, walk them one by one -------------------------------------
+        t0 = clock64();
+        sh.sum[chain][0][lane] = r.sum; sh.lo[chain][0][lane] = r.lo; sh.hi[chain][0][lane] = r.hi;
+        sh.sum[chain][1][lane] = r1.sum; sh.lo[chain][1][lane] = r1.lo; sh.hi[chain][1][lane] = r1.hi;
+        sh.eref[chain][lane] = r.eref;
+        sh.flag[chain][lane] = r.flag;
+        __syncwarp();
+        // software-pipelined: record b + 1 is fetched from shared memory while record b is applied, so the
+        // loop-carried dependency is just the integer state
+        struct Staged { PbSpan a0, a1; int eref, flag; };
+        auto fetch = [&](uint32_t b) {
+            Staged g;
+            g.flag = sh.flag[chain][b];
+            g.eref = sh.eref[chain][b];
+            g.a0.sum = sh.sum[chain][0][b]; g.a0.lo = sh.lo[chain][0][b]; g.a0.hi = sh.hi[chain][0][b];
+            g.a1.sum = sh.sum[chain][1][b]; g.a1.lo = sh.lo[chain][1][b]; g.a1.hi = sh.hi[chain][1][b];
+            return g;
+        };
+        Staged cur = fetch(next);
+        n_gen += gcnt - next;
+        for (uint32_t b = next; b < gcnt; b++) {
+            const Staged g = cur;
+            if (b + 1 < gcnt) cur = fetch(b + 1);
+            bool ok = false;
+            int why = 0;
+            if (g.flag == F_OK || g.flag == F_SENSITIVE) {
+                if (pb_state_rebase(st, g.eref)) {
+                    const bool odd = (st.S & 1LL) && g.flag == F_SENSITIVE;
+                    const long long vsum = odd ? g.a1.sum : g.a0.sum, vlo = odd ? g.a1.lo : g.a0.lo, vhi = odd ? g.a1.hi : g.a0.hi;
+                    if (st.S >= vlo && st.S <= vhi) {
+                        st.S += vsum;
+                        ok = true;
+                        n_acc++;
+                        n_acc2 += g.flag == F_SENSITIVE;
+                    } else why = 2;
+                } else why = 1;
+            }
+            if (!ok) {
+                const long long t1 = clock64();
+                const double s = st.ok ? pb_state_to_double(st) : sd;
+                const uint32_t base = (g0 + b) * OB;
+                sd = replay_block<KIND, W>(P, (size_t)sg.lo + base, min((uint32_t)OB, n - base), chain, m0, m1, m2, s, lane,
+                                           sh.terms[chain]);
+                st = pb_state_from_double(sd);
+                n_rep++;
+                n_why[why]++;
+                const long long dt = clock64() - t1;
+                cyc[2] += dt;
+                cyc[1] -= dt;
+            }
+        }
+        __syncwarp();
+        cyc[1] += clock64() - t0;
     }
     if (lane == 0) {
-        s_res[chain] = s;
+        sh.res[chain] = st.ok ? pb_state_to_double(st) : sd;
         if (use_summaries) {
             atomicAdd(&g_ord_counts[0], (unsigned long long)n_acc);
             atomicAdd(&g_ord_counts[1], (unsigned long long)n_rep);
             for (int q = 0; q < 3; q++) atomicAdd(&g_ord_counts[2 + q], (unsigned long long)n_why[q]);
             atomicAdd(&g_ord_counts[7], (unsigned long long)n_acc2);
+            for (int q = 0; q < 3; q++) atomicAdd(&g_ord_counts[8 + q], (unsigned long long)cyc[q]);
+            atomicAdd(&g_ord_counts[11], (unsigned long long)((nblk + 31) / 32));
+            atomicMax(&g_ord_counts[12], (unsigned long long)(clock64() - t_begin));
+            if (KIND == KIND_CENTERED) {
+                for (int q = 0; q < 3; q++) atomicAdd(&g_ord_chain[chain][q], (unsigned long long)cyc[q]);
+                atomicAdd(&g_ord_chain[chain][3], (unsigned long long)n_rep);
+                atomicAdd(&g_ord_chain[chain][4], (unsigned long long)n_gen);
+            }
         }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         if (KIND == KIND_MEAN) {
             // matrix2D.c:230-231: scale = 1 / wsum (1 / rows when unweighted); mean *= scale
-            const double wsum = W ? s_res[0] : (double)n;
+            const double wsum = W ? sh.res[0] : (double)n;
             const double inv = 1.0 / wsum;
             stats[seg].wsum = wsum;
-            for (int j = 0; j < 3; j++) stats[seg].mean[j] = __dmul_rn(s_res[1 + j], inv);
+            for (int j = 0; j < 3; j++) stats[seg].mean[j] = __dmul_rn(sh.res[1 + j], inv);
         } else {
-            for (int j = 0; j < 6; j++) stats[seg].cov[j] = s_res[j];
-            stats[seg].dist = s_res[6];
+            for (int j = 0; j < 6; j++) stats[seg].cov[j] = sh.res[j];
+            stats[seg].dist = sh.res[6];
         }
     }
 }
@@ -700,11 +679,19 @@ void launch_pass(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t
 
 } // namespace
 
-void pb_ordered_counts(unsigned long long out[8], bool reset) {
-    PB_CUDA_OK(cudaMemcpyFromSymbol(out, g_ord_counts, sizeof(unsigned long long) * 8));
+void pb_ordered_counts(unsigned long long out[16], bool reset) {
+    PB_CUDA_OK(cudaMemcpyFromSymbol(out, g_ord_counts, sizeof(unsigned long long) * 16));
     if (reset) {
-        unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        unsigned long long z[16] = {0};
         PB_CUDA_OK(cudaMemcpyToSymbol(g_ord_counts, z, sizeof z));
+    }
+}
+
+void pb_ordered_chain_debug(unsigned long long out[35], bool reset) {
+    PB_CUDA_OK(cudaMemcpyFromSymbol(out, g_ord_chain, sizeof(unsigned long long) * 35));
+    if (reset) {
+        unsigned long long z[35] = {0};
+        PB_CUDA_OK(cudaMemcpyToSymbol(g_ord_chain, z, sizeof z));
     }
 }
 

@@ -746,6 +746,13 @@ int patolette_b200_ordered_counts(unsigned long long *out2, int reset) {
     } catch (const pb_cuda_error &e) { return -(int)e.code; }
 }
 
+int patolette_b200_ordered_chain_debug(unsigned long long *out35, int reset) {
+    try {
+        pb_ordered_chain_debug(out35, reset != 0);
+        return 0;
+    } catch (const pb_cuda_error &e) { return -(int)e.code; }
+}
+
 size_t patolette_b200_release_cache(void) {
     const size_t held = pb_pool_cached_bytes();
     pb_pool_release_all();

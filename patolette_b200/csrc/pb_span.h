@@ -136,6 +136,12 @@ PB_HD long long pb_round_step(const PbQuant &q, int k, long long Ls, int *tie) {
     return q.si - low + r; // S_i = (S_{i-1} - Ls) + (t - low) + r
 }
 
+#ifdef PB_SPAN_REASONS
+#define PB_WHY(r, v) ((r).why = (v))
+#else
+#define PB_WHY(r, v) ((void)0)
+#endif
+
 // Running state of a run being summarised (one per start parity when PARITY2).
 struct PbRun {
     long long C[2]; // contributions so far, by start parity
@@ -143,6 +149,9 @@ struct PbRun {
     int kprev;      // level of the previous result (of the start state before the first element)
     int bad;        // the run cannot be summarised
     int sensitive;  // some step depended on the parity of the state
+#ifdef PB_SPAN_REASONS
+    int why;        // analysis builds only: 1 level out of range, 2 term too large, 3 upward step, 4 tie
+#endif
 };
 
 // constraint "S_start + C strictly inside binade level k on the side of sign(approx)"
@@ -174,11 +183,11 @@ PB_HD void pb_run_begin(PbRun &r, double approx0, int eref) {
 template <int NV>
 PB_HD void pb_run_push(PbRun &r, double term, double approx, int eref) {
     const int k = pb_exponent_of(approx) - eref;
-    if (k < 0 || k > PB_SPAN_MAX_LEVEL) { r.bad = 1; return; }
+    if (k < 0 || k > PB_SPAN_MAX_LEVEL) { r.bad = 1; PB_WHY(r, 1); return; }
     const PbQuant q = pb_quantise(term, eref);
-    if (q.bad) { r.bad = 1; return; }
+    if (q.bad) { r.bad = 1; PB_WHY(r, 2); return; }
     const bool up = k > r.kprev;
-    if (up && !(r.kprev == 0 && k == 1)) { r.bad = 1; return; } // needs bits above bit 0 of the state
+    if (up && !(r.kprev == 0 && k == 1)) { r.bad = 1; PB_WHY(r, 3); return; } // needs bits above bit 0 of the state
     const bool neg = approx < 0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -189,7 +198,7 @@ PB_HD void pb_run_push(PbRun &r, double term, double approx, int eref) {
         long long d = pb_round_step(q, k, up ? bit0 : 0, &tie);
         if (up) r.sensitive = 1;
         if (tie) {
-            if (k != 0 || up) { r.bad = 1; return; }
+            if (k != 0 || up) { r.bad = 1; PB_WHY(r, 4); return; }
             r.sensitive = 1;
             // candidates d (lower) and d + 1: the one that leaves S_i even
             if ((bit0 + d) & 1LL) d += 1;
@@ -198,6 +207,48 @@ PB_HD void pb_run_push(PbRun &r, double term, double approx, int eref) {
         pb_run_constrain(r, p, k, neg);
     }
     r.kprev = k;
+}
+
+// The common case, cheaply: every predicted level of a thread's run (start state included) is the same
+// level k and the sign never changes.  Then every step is the translation rint(a / 2^k units) and the
+// constraints collapse to the extremes of the prefix sums.  Equivalent to pb_run_begin + pb_run_push<1>
+// element by element (tests/native/test_span.cpp checks that); a tie marks the run sensitive (k = 0) or
+// unusable (k > 0) exactly like the general path, and a sensitive run is redone by the two-parity pass.
+struct PbUni {
+    double ps, mn, mx; // prefix sum of the quantised terms and its extremes (0 = the start state included)
+    int bad, tie;
+};
+PB_HD void pb_uni_begin(PbUni &u) { u.ps = u.mn = u.mx = 0.0; u.bad = u.tie = 0; }
+PB_HD double pb_uni_scale(int k, int eref) { return pb_pow2(52 - eref - k); }
+PB_HD void pb_uni_push(PbUni &q, double term, double scale) {
+    const double MAGIC = 6755399441055744.0; // 1.5 * 2^52: (u + MAGIC) - MAGIC == rint(u) for |u| < 2^51
+    const double u = term * scale;           // exact
+    const double au = u < 0 ? -u : u;
+    const double d = (u + MAGIC) - MAGIC;
+    const double rem = u - d;
+    q.bad |= !(au < 2251799813685248.0); // 2^51 (or NaN)
+    q.tie |= (rem == 0.5) | (rem == -0.5);
+    q.ps += d;
+    q.mn = q.ps < q.mn ? q.ps : q.mn;
+    q.mx = q.ps > q.mx ? q.ps : q.mx;
+}
+PB_HD void pb_uni_end(const PbUni &q, PbRun &r, int k, bool neg) {
+    r.kprev = k;
+    r.bad = q.bad | (q.tie && k != 0);
+    r.sensitive = q.tie && k == 0;
+    if (r.bad) { r.C[0] = r.C[1] = 0; return; }
+    const long long A = 1LL << (k + 52), B = 1LL << (k + 53);
+    const long long lmn = ((long long)q.mn) * (1LL << k), lmx = ((long long)q.mx) * (1LL << k);
+    r.C[0] = r.C[1] = ((long long)q.ps) * (1LL << k);
+    r.lo[0] = r.lo[1] = (neg ? -B : A) + 1 - lmn;
+    r.hi[0] = r.hi[1] = (neg ? -A : B) - 1 - lmx;
+}
+PB_HD void pb_run_uniform(PbRun &r, const double *t, int cnt, int k, bool neg, int eref) {
+    PbUni q;
+    pb_uni_begin(q);
+    const double scale = pb_uni_scale(k, eref);
+    for (int i = 0; i < cnt; i++) pb_uni_push(q, t[i], scale);
+    pb_uni_end(q, r, k, neg);
 }
 
 template <int NV>
@@ -233,5 +284,45 @@ PB_HD bool pb_span2_apply(const PbSpan2 &sp, int eref, double &s) {
     const PbSpan &v = sp.p[(int)(S & 1LL)];
     if (!(S >= v.lo && S <= v.hi)) return false;
     s = pb_units_to_state(S + v.sum, eref);
+    return true;
+}
+
+// ---- the resolving walker's state: an exact double kept as integer * unit ---------------------------
+// value = S * 2^(e - 52).  Between records of the same unit the walk is pure integer arithmetic; the
+// double is only rebuilt where the unit changes or a block has to be replayed.
+struct PbState {
+    long long S;
+    int e;
+    int ok; // 0: the value is zero, subnormal, huge or non-finite - records cannot be applied to it
+};
+PB_HD PbState pb_state_from_double(double s) {
+    PbState st;
+    const long long bits = pb_double_bits(s);
+    const int ef = (int)((bits >> 52) & 0x7ff);
+    st.e = ef - 1023;
+    st.ok = ef > 123 && ef < 1923; // |e| < 900
+    const long long M = (bits & 0x000fffffffffffffLL) | (1LL << 52);
+    st.S = bits < 0 ? -M : M;
+    return st;
+}
+PB_HD double pb_state_to_double(const PbState &st) { return (double)st.S * pb_pow2(st.e - 52); }
+// re-express in unit eref (exact) - false if the value has bits below it or would overflow the level range
+PB_HD bool pb_state_rebase(PbState &st, int eref) {
+    if (!st.ok) return false;
+    if (st.e == eref) return true;
+    // normalise through the double: S has at most 53 significant bits
+    long long S;
+    const double v = pb_state_to_double(st);
+    if (!pb_eref_ok(eref) || !pb_state_to_units(v, eref, S)) return false;
+    st.S = S;
+    st.e = eref;
+    return true;
+}
+// one record (both parities) applied to the state; false = replay the block
+PB_HD bool pb_state_apply(PbState &st, const PbSpan &v0, const PbSpan &v1, int eref) {
+    if (!pb_state_rebase(st, eref)) return false;
+    const PbSpan &v = (st.S & 1LL) ? v1 : v0;
+    if (!(st.S >= v.lo && st.S <= v.hi)) return false; // an invalid span has lo > hi
+    st.S += v.sum;
     return true;
 }
