@@ -57,6 +57,8 @@ enum { F_OK = 0, F_REPLAY = 1, F_PENDING = 2, F_SENSITIVE = 3 };
 
 enum { KIND_MEAN = 0, KIND_CENTERED = 1 };
 template <int KIND> struct NChains { static constexpr int C = KIND == KIND_MEAN ? 4 : 7; };
+// chain 0 of the mean pass is the weight sum; unweighted it is the row count (matrix2D.c:230) - not summed
+template <int KIND, bool W> __host__ __device__ constexpr bool chain_live(int c) { return !(KIND == KIND_MEAN && !W && c == 0); }
 
 // record of (chain, block) of a segment: chain-major inside the segment's region of the packed table, so
 // that the 32 lanes of a resolving warp read 32 consecutive records
@@ -152,6 +154,7 @@ __global__ void __launch_bounds__(OB_THREADS) k_ord_blocksum(PbPlanes b0, PbPlan
     double *out = psum + ((size_t)sg.bbase + blockIdx.x) * C;
 #pragma unroll
     for (int c = 0; c < C; c++) {
+        if (!chain_live<KIND, W>(c)) continue;
         const double r = block_reduce_sum(acc[c], red);
         if (threadIdx.x == 0) out[c] = r;
     }
@@ -159,8 +162,8 @@ __global__ void __launch_bounds__(OB_THREADS) k_ord_blocksum(PbPlanes b0, PbPlan
 
 // ---- S2: approximate exclusive prefix per chain (in place over the block sums) ------------------
 template <int C>
-__global__ void __launch_bounds__(32) k_ord_prefix(const PbSeg *__restrict__ segs, double *__restrict__ psum) {
-    const int seg = blockIdx.y, c = blockIdx.x, lane = threadIdx.x;
+__global__ void __launch_bounds__(32) k_ord_prefix(const PbSeg *__restrict__ segs, double *__restrict__ psum, int first_chain) {
+    const int seg = blockIdx.y, c = blockIdx.x + first_chain, lane = threadIdx.x;
     const uint32_t nblk = (segs[seg].n + OB - 1) / OB;
     double *io = psum + (size_t)segs[seg].bbase * C + c;
     const uint32_t per = (nblk + 31) / 32;
@@ -241,7 +244,8 @@ __device__ __forceinline__ bool summarise_block(const PbPlanes &P, const PbSeg &
                 double t[C];
                 terms_all<KIND, W>(W ? P.w[p] : 1.0, P.c[0][p], P.c[1][p], P.c[2][p], m0, m1, m2, t);
 #pragma unroll
-                for (int c = 0; c < C; c++) tl[c] += t[c];
+                for (int c = 0; c < C; c++)
+                    if (chain_live<KIND, W>(c)) tl[c] += t[c];
             }
         }
 #pragma unroll
@@ -289,6 +293,7 @@ __device__ __forceinline__ bool summarise_block(const PbPlanes &P, const PbSeg &
                 terms_all<KIND, W>(W ? P.w[p] : 1.0, P.c[0][p], P.c[1][p], P.c[2][p], m0, m1, m2, t);
 #pragma unroll
                 for (int c = 0; c < C; c++) {
+                    if (!chain_live<KIND, W>(c)) continue;
                     run[c] += t[c];
                     const int e = pb_exponent_of(run[c]);
                     emin[c] = min(emin[c], e);
@@ -340,6 +345,7 @@ __device__ __forceinline__ bool summarise_block(const PbPlanes &P, const PbSeg &
             terms_all<KIND, W>(W ? P.w[p] : 1.0, P.c[0][p], P.c[1][p], P.c[2][p], m0, m1, m2, t);
 #pragma unroll
             for (int c = 0; c < C; c++) {
+                if (!chain_live<KIND, W>(c)) continue;
                 run[c] += t[c]; // same operations as phase 2: same predictions
                 if (slow[c] && !run_st[c].bad) run_push_slow<NV>(&run_st[c], t[c], run[c], eref[c]);
             }
@@ -420,7 +426,7 @@ __global__ void __launch_bounds__(OS_THREADS) k_ord_summary(PbPlanes b0, PbPlane
     if (KIND == KIND_CENTERED) { m0 = stats[seg].mean[0]; m1 = stats[seg].mean[1]; m2 = stats[seg].mean[2]; }
     bool need[C];
 #pragma unroll
-    for (int c = 0; c < C; c++) need[c] = true;
+    for (int c = 0; c < C; c++) need[c] = chain_live<KIND, W>(c);
     const bool pending = summarise_block<KIND, W, 1>(P, sg, blockIdx.x, m0, m1, m2,
                                                      psum + ((size_t)sg.bbase + blockIdx.x) * C, rec0, nullptr, need, sh);
     if (threadIdx.x == 32 && pending) list[atomicAdd(list_count, 1u)] = make_uint2((unsigned)seg, blockIdx.x);
@@ -447,7 +453,8 @@ __global__ void __launch_bounds__(OS_THREADS) k_ord_summary2(PbPlanes b0, PbPlan
         __syncthreads(); // sh is reused across items
         bool need[C]; // only the chains that asked for it are redone (uniform across the CTA)
 #pragma unroll
-        for (int c = 0; c < C; c++) need[c] = rec0[rec_row(sg, C, c, nblk, blk)].flag == F_PENDING;
+        for (int c = 0; c < C; c++)
+            need[c] = chain_live<KIND, W>(c) && rec0[rec_row(sg, C, c, nblk, blk)].flag == F_PENDING;
         __syncthreads(); // every thread has read the flags before (warp 1, lane 0) rewrites the records
         summarise_block<KIND, W, 2>(P, sg, blk, m0, m1, m2, psum + ((size_t)sg.bbase + blk) * C, rec0, rec1, need, sh);
     }
@@ -502,7 +509,7 @@ __global__ void __launch_bounds__(32 * NChains<KIND>::C) k_ord_resolve(PbPlanes 
     const int seg = blockIdx.x, chain = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const PbSeg sg = segs[seg];
     const PbPlanes &P = sg.buf ? b1 : b0;
-    const uint32_t n = sg.n, nblk = (n + OB - 1) / OB;
+    const uint32_t n = sg.n, nblk = chain_live<KIND, W>(chain) ? (n + OB - 1) / OB : 0u;
     double m0 = 0, m1 = 0, m2 = 0;
     if (KIND == KIND_CENTERED) { m0 = stats[seg].mean[0]; m1 = stats[seg].mean[1]; m2 = stats[seg].mean[2]; }
     double sd = 0.0;                          // the exact running sum, authoritative while !st.ok
@@ -665,7 +672,7 @@ void launch_pass(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t
         { PbProfScope p(KIND == KIND_MEAN ? "k_ord_blocksum_mean" : "k_ord_blocksum_centered", st, false);
           k_ord_blocksum<KIND, W><<<grid, OB_THREADS, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, sc.psum); }
         { PbProfScope p("k_ord_prefix", st, false);
-          k_ord_prefix<C><<<dim3(C, nseg), 32, 0, st>>>(d_segs, sc.psum); }
+          k_ord_prefix<C><<<dim3(chain_live<KIND, W>(0) ? C : C - 1, nseg), 32, 0, st>>>(d_segs, sc.psum, chain_live<KIND, W>(0) ? 0 : 1); }
         PB_CUDA_OK(cudaMemsetAsync(sc.list_count, 0, sizeof(unsigned int), st));
         { PbProfScope p(KIND == KIND_MEAN ? "k_ord_summary_mean" : "k_ord_summary_centered", st);
           k_ord_summary<KIND, W><<<grid, OS_THREADS, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, sc.psum, sc.rec0, sc.list_count, sc.list); }
