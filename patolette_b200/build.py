@@ -61,7 +61,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for src in sources():
         obj = os.path.join(BUILD, os.path.basename(src) + ".o")
         objs.append(obj)
-        extra = ["-Xptxas", "-v"] if verbose else []
+        extra = (["-Xptxas", "-v"] if verbose else []) + os.environ.get("PB200_NVCC_EXTRA", "").split()
         jobs.append([cc] + NVCC_FLAGS + extra + ["-c", src, "-o", obj])
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 4)) as ex:
         logs = list(ex.map(_run, jobs))

@@ -32,17 +32,27 @@ namespace {
 // order, are ord[class_start[b] .. class_start[b+1]) (stable bucket sort, pb_scatter.cu).
 // One warp per (cluster, bucket): lanes gather a tile of members, chain lanes add.
 // ------------------------------------------------------------------------------------
-constexpr int BK_TILE = 64;
+constexpr int BK_TILE = 128;           // members staged per step (4 per lane)
 constexpr int BK_STRIDE = BK_TILE + 2;
 constexpr int BK_WARPS = 4;
+constexpr int BK_PER = BK_TILE / 32;
 
+// The chain lanes run ONE uniform loop `acc = acc + term[lane][e]`: every per-element term is formed by the
+// gathering lanes (in parallel) before it is staged, so the critical path per element is a shared-memory
+// broadcast read + one dependent DADD.  The gather of tile t+1 is issued into registers before the chain
+// over tile t starts, so its latency hides behind the chain.
+//   LQ (local.c:124-134): term 0 = w (bucket "size"), terms 1..3 = c_j * w.
+//     The reference accumulates the size as size_t += double (local.c:133), i.e.
+//     size = trunc((double)size + w) at every step.  Unweighted that is the member count (exact), and
+//     c_j * 1.0 == c_j: three plain chains.  Weighted, every chain lane runs the trunc-select stream.
 template <bool WEIGHTED>
 __global__ void __launch_bounds__(BK_WARPS * 32) k_bucket_chains_lq(PbPlanes b0, PbPlanes b1,
                                                                    const PbSeg *__restrict__ segs, int nseg,
                                                                    const uint32_t *__restrict__ ord,
                                                                    const uint32_t *__restrict__ class_start,
                                                                    double *__restrict__ out) {
-    __shared__ double sm_all[BK_WARPS][4][BK_STRIDE];
+    constexpr int NT = WEIGHTED ? 4 : 3;
+    __shared__ double sm_all[BK_WARPS][NT][BK_STRIDE];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int gw = blockIdx.x * BK_WARPS + warp;
     if (gw >= nseg * PB_BUCKETS) return;
@@ -52,82 +62,116 @@ __global__ void __launch_bounds__(BK_WARPS * 32) k_bucket_chains_lq(PbPlanes b0,
     const PbPlanes &P = sg.buf ? b1 : b0;
     const uint32_t *cs = class_start + (size_t)seg * (PB_BUCKETS + 1);
     const uint32_t beg = cs[b], end = cs[b + 1];
-    // lane 0: bucket "size" - the reference accumulates a size_t with += double
-    // (local.c:133), i.e. size = trunc((double)size + w) at every step; kept here as an
-    // integer-valued double so all four chain lanes run the same instruction stream.
-    // lanes 1..3: sum c_j * w (local.c:130-132).
     double acc = 0.0;
+    double g[BK_PER][NT];
+    auto gather = [&](uint32_t i0) {
+#pragma unroll
+        for (int q = 0; q < BK_PER; q++) {
+            const uint32_t i = i0 + q * 32 + lane;
+#pragma unroll
+            for (int t = 0; t < NT; t++) g[q][t] = 0.0;
+            if (i < end) {
+                const uint32_t p = ord[i];
+                if (WEIGHTED) {
+                    const double w = P.w[p];
+                    g[q][0] = w;
+                    g[q][1] = __dmul_rn(P.c[0][p], w);
+                    g[q][2] = __dmul_rn(P.c[1][p], w);
+                    g[q][3] = __dmul_rn(P.c[2][p], w);
+                } else {
+                    g[q][0] = P.c[0][p];
+                    g[q][1] = P.c[1][p];
+                    g[q][2] = P.c[2][p];
+                }
+            }
+        }
+    };
+    if (beg < end) gather(beg);
     for (uint32_t i0 = beg; i0 < end; i0 += BK_TILE) {
         const uint32_t cnt = min((uint32_t)BK_TILE, end - i0);
 #pragma unroll
-        for (int q = 0; q < BK_TILE / 32; q++) {
-            const uint32_t e = q * 32 + lane;
-            if (e < cnt) {
-                const uint32_t p = ord[i0 + e];
-                sm[0][e] = WEIGHTED ? P.w[p] : 1.0;
-                sm[1][e] = P.c[0][p];
-                sm[2][e] = P.c[1][p];
-                sm[3][e] = P.c[2][p];
-            }
-        }
+        for (int q = 0; q < BK_PER; q++)
+#pragma unroll
+            for (int t = 0; t < NT; t++) sm[t][q * 32 + lane] = g[q][t];
         __syncwarp();
-        if (lane < 4) {
+        if (i0 + BK_TILE < end) gather(i0 + BK_TILE); // in flight during the chain below
+        if (lane < NT) {
             const double *vp = sm[lane];
+            if (WEIGHTED) {
 #pragma unroll 8
-            for (uint32_t e = 0; e < cnt; e++) {
-                const double w = sm[0][e];
-                const double t = __dadd_rn(acc, lane == 0 ? w : __dmul_rn(vp[e], w));
-                acc = lane == 0 ? trunc(t) : t;
+                for (uint32_t e = 0; e < cnt; e++) {
+                    const double t = __dadd_rn(acc, vp[e]);
+                    acc = lane == 0 ? trunc(t) : t;
+                }
+            } else {
+#pragma unroll 16
+                for (uint32_t e = 0; e < cnt; e++) acc = __dadd_rn(acc, vp[e]);
             }
         }
         __syncwarp();
     }
     double *o = out + ((size_t)seg * PB_BUCKETS + b) * 4;
-    if (lane == 0) o[0] = __longlong_as_double((long long)(unsigned long long)acc);
-    else if (lane < 4) o[lane] = acc;
+    if (WEIGHTED) {
+        if (lane == 0) o[0] = __longlong_as_double((long long)(unsigned long long)acc);
+        else if (lane < 4) o[lane] = acc;
+    } else {
+        if (lane == 0) o[0] = __longlong_as_double((long long)(unsigned long long)(end - beg));
+        if (lane < 3) o[1 + lane] = acc;
+    }
 }
 
-// GQ cell moments (cells.c:78-116), unweighted, over the whole image.
+// GQ cell moments (cells.c:78-116), unweighted, over the whole image:
+// terms 0..2 = c_j ; 3 = (cx^2 + cy^2) + cz^2 ; 4..9 = c_r * c_s for (r,s) = (0,0)(0,1)(1,1)(0,2)(1,2)(2,2).
 __global__ void __launch_bounds__(BK_WARPS * 32) k_bucket_chains_gq(PbPlanes src, const uint32_t *__restrict__ ord,
                                                                    const uint32_t *__restrict__ class_start,
                                                                    double *__restrict__ out) {
-    __shared__ double sm_all[BK_WARPS][3][BK_STRIDE];
+    constexpr int NT = 10;
+    constexpr int GT = 64, GPER = GT / 32, GSTRIDE = GT + 2; // smaller tile: 10 term rows per warp
+    __shared__ double sm_all[BK_WARPS][NT][GSTRIDE];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * BK_WARPS + warp;
     if (b >= PB_BUCKETS) return;
-    double(*sm)[BK_STRIDE] = sm_all[warp];
+    double(*sm)[GSTRIDE] = sm_all[warp];
     const uint32_t beg = class_start[b], end = class_start[b + 1];
-    // lanes 0..2: sum c_j ; lane 3: sum (cx^2 + cy^2) + cz^2 ; lanes 4..9: sum c_r * c_s
-    const int r = (lane == 4 || lane == 5 || lane == 7) ? 0 : ((lane == 6 || lane == 8) ? 1 : 2);
-    const int s = lane == 4 ? 0 : ((lane == 5 || lane == 6) ? 1 : 2);
     double acc = 0.0;
-    for (uint32_t i0 = beg; i0 < end; i0 += BK_TILE) {
-        const uint32_t cnt = min((uint32_t)BK_TILE, end - i0);
+    double g[GPER][3];
+    auto gather = [&](uint32_t i0) {
 #pragma unroll
-        for (int q = 0; q < BK_TILE / 32; q++) {
-            const uint32_t e = q * 32 + lane;
-            if (e < cnt) {
-                const uint32_t p = ord[i0 + e];
-                sm[0][e] = src.c[0][p];
-                sm[1][e] = src.c[1][p];
-                sm[2][e] = src.c[2][p];
+        for (int q = 0; q < GPER; q++) {
+            const uint32_t i = i0 + q * 32 + lane;
+            g[q][0] = g[q][1] = g[q][2] = 0.0;
+            if (i < end) {
+                const uint32_t p = ord[i];
+                g[q][0] = src.c[0][p];
+                g[q][1] = src.c[1][p];
+                g[q][2] = src.c[2][p];
             }
         }
+    };
+    if (beg < end) gather(beg);
+    for (uint32_t i0 = beg; i0 < end; i0 += GT) {
+        const uint32_t cnt = min((uint32_t)GT, end - i0);
+#pragma unroll
+        for (int q = 0; q < GPER; q++) {
+            const int e = q * 32 + lane;
+            const double x = g[q][0], y = g[q][1], z = g[q][2];
+            sm[0][e] = x;
+            sm[1][e] = y;
+            sm[2][e] = z;
+            sm[3][e] = __dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z));
+            sm[4][e] = __dmul_rn(x, x);
+            sm[5][e] = __dmul_rn(x, y);
+            sm[6][e] = __dmul_rn(y, y);
+            sm[7][e] = __dmul_rn(x, z);
+            sm[8][e] = __dmul_rn(y, z);
+            sm[9][e] = __dmul_rn(z, z);
+        }
         __syncwarp();
-        if (lane < 3) {
+        if (i0 + GT < end) gather(i0 + GT);
+        if (lane < NT) {
             const double *vp = sm[lane];
-#pragma unroll 8
+#pragma unroll 16
             for (uint32_t e = 0; e < cnt; e++) acc = __dadd_rn(acc, vp[e]);
-        } else if (lane == 3) {
-#pragma unroll 4
-            for (uint32_t e = 0; e < cnt; e++) {
-                const double x = sm[0][e], y = sm[1][e], z = sm[2][e];
-                acc = __dadd_rn(acc, __dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z)));
-            }
-        } else if (lane < 10) {
-            const double *rp = sm[r], *sp = sm[s];
-#pragma unroll 8
-            for (uint32_t e = 0; e < cnt; e++) acc = __dadd_rn(acc, __dmul_rn(rp[e], sp[e]));
         }
         __syncwarp();
     }

@@ -185,6 +185,9 @@ __global__ void __launch_bounds__(32) k_ord_prefix(const PbSeg *__restrict__ seg
 
 // ---- S3: block summaries with per-element binade prediction ------------------------------------
 constexpr int OS_THREADS = 64; // 8 consecutive elements per thread, two warps per block
+#ifndef PB_OS_MINB
+#define PB_OS_MINB 8 // minimum resident CTAs per SM asked of ptxas for the summary kernels (register cap)
+#endif
 constexpr int OS_PER = OB / OS_THREADS;
 
 __device__ __forceinline__ PbSpan shfl_down_span(const PbSpan &v, int o) {
@@ -207,6 +210,16 @@ struct SumShared {
     int emin[2][7], emax[2][7];
     PbSpan2 span[7];         // warp 0's span
     int flag[7];
+    int slot[7];             // term-dump slot of a chain whose record is F_REPLAY (-1: none)
+};
+
+// Blocks whose record is F_REPLAY are known before the resolve runs: their terms are written out here, in
+// parallel, so that the sequential replay is a coalesced 4 KB read + the dependent adds (no loads of the
+// pixel planes, no term arithmetic on the resolving warp's critical path).
+struct Dump {
+    double *terms;          // [cap][OB]
+    unsigned int *count;    // slots handed out (may run past cap: those blocks are replayed from the planes)
+    unsigned int cap;
 };
 
 // The general element step, out of line: it is the rare path (threads whose predictions change level or
@@ -221,7 +234,7 @@ __device__ __noinline__ void run_push_slow(PbRun *r, double term, double approx,
 template <int KIND, bool W, int NV>
 __device__ __forceinline__ bool summarise_block(const PbPlanes &P, const PbSeg &sg, uint32_t blk, double m0, double m1,
                                                 double m2, const double *__restrict__ pstart, OrdRec *__restrict__ rec0,
-                                                OrdRec *__restrict__ rec1, const bool *need, SumShared &sh) {
+                                                OrdRec *__restrict__ rec1, const bool *need, SumShared &sh, const Dump &dump) {
     constexpr int C = NChains<KIND>::C;
     constexpr int NOLEVEL = -(1 << 20);
     const uint32_t nblk = (sg.n + OB - 1) / OB;
@@ -229,7 +242,7 @@ __device__ __forceinline__ bool summarise_block(const PbPlanes &P, const PbSeg &
     const uint32_t i0 = blk * OB + threadIdx.x * OS_PER; // this thread's consecutive elements
     const bool have = i0 < sg.n;
     const int mycnt = have ? min(OS_PER, (int)(sg.n - i0)) : 0;
-    if (threadIdx.x < C) sh.flag[threadIdx.x] = 0;
+    if (threadIdx.x < C) { sh.flag[threadIdx.x] = 0; sh.slot[threadIdx.x] = -1; }
 
     // ---- phase 1: approximate running sum at the start of this thread's elements ------------------
     double tstart[C];
@@ -398,6 +411,11 @@ __device__ __forceinline__ bool summarise_block(const PbPlanes &P, const PbSeg &
             const size_t row = rec_row(sg, C, c, nblk, blk);
             OrdRec o0;
             o0.sum = w.p[0].sum; o0.lo = w.p[0].lo; o0.hi = w.p[0].hi; o0.eref = eref[c]; o0.flag = flag;
+            if (flag == F_REPLAY) { // the record carries the dump slot instead of a translation
+                const unsigned int slot = atomicAdd(dump.count, 1u);
+                o0.sum = slot < dump.cap ? (long long)slot : -1LL;
+                sh.slot[c] = (int)o0.sum;
+            }
             rec0[row] = o0;
             if (NV == 2) {
                 OrdRec o1;
@@ -407,15 +425,32 @@ __device__ __forceinline__ bool summarise_block(const PbPlanes &P, const PbSeg &
             pending |= flag == F_PENDING;
         }
     }
+    __syncthreads();
+    {
+        bool any = false;
+#pragma unroll
+        for (int c = 0; c < C; c++) any |= sh.slot[c] >= 0;
+        if (any && have) { // CTA-uniform `any`: write this thread's terms of the dumped chains
+#pragma unroll 1
+            for (int k = 0; k < mycnt; k++) {
+                const size_t p = (size_t)sg.lo + i0 + k;
+                double t[C];
+                terms_all<KIND, W>(W ? P.w[p] : 1.0, P.c[0][p], P.c[1][p], P.c[2][p], m0, m1, m2, t);
+#pragma unroll
+                for (int c = 0; c < C; c++)
+                    if (sh.slot[c] >= 0) dump.terms[(size_t)sh.slot[c] * OB + threadIdx.x * OS_PER + k] = t[c];
+            }
+        }
+    }
     return pending; // meaningful on (warp 1, lane 0)
 }
 
 template <int KIND, bool W>
-__global__ void __launch_bounds__(OS_THREADS) k_ord_summary(PbPlanes b0, PbPlanes b1, const PbSeg *__restrict__ segs,
+__global__ void __launch_bounds__(OS_THREADS, PB_OS_MINB) k_ord_summary(PbPlanes b0, PbPlanes b1, const PbSeg *__restrict__ segs,
                                                             const PbStats *__restrict__ stats,
                                                             const double *__restrict__ psum, OrdRec *__restrict__ rec0,
                                                             unsigned int *__restrict__ list_count,
-                                                            uint2 *__restrict__ list) {
+                                                            uint2 *__restrict__ list, Dump dump) {
     constexpr int C = NChains<KIND>::C;
     __shared__ SumShared sh;
     const int seg = blockIdx.y;
@@ -428,18 +463,18 @@ __global__ void __launch_bounds__(OS_THREADS) k_ord_summary(PbPlanes b0, PbPlane
 #pragma unroll
     for (int c = 0; c < C; c++) need[c] = chain_live<KIND, W>(c);
     const bool pending = summarise_block<KIND, W, 1>(P, sg, blockIdx.x, m0, m1, m2,
-                                                     psum + ((size_t)sg.bbase + blockIdx.x) * C, rec0, nullptr, need, sh);
+                                                     psum + ((size_t)sg.bbase + blockIdx.x) * C, rec0, nullptr, need, sh, dump);
     if (threadIdx.x == 32 && pending) list[atomicAdd(list_count, 1u)] = make_uint2((unsigned)seg, blockIdx.x);
 }
 
 // ---- S3b: blocks with a parity-dependent step: both start parities ---------------------------------
 template <int KIND, bool W>
-__global__ void __launch_bounds__(OS_THREADS) k_ord_summary2(PbPlanes b0, PbPlanes b1, const PbSeg *__restrict__ segs,
+__global__ void __launch_bounds__(OS_THREADS, PB_OS_MINB) k_ord_summary2(PbPlanes b0, PbPlanes b1, const PbSeg *__restrict__ segs,
                                                              const PbStats *__restrict__ stats,
                                                              const double *__restrict__ psum, OrdRec *__restrict__ rec0,
                                                              OrdRec *__restrict__ rec1,
                                                              const unsigned int *__restrict__ list_count,
-                                                             const uint2 *__restrict__ list) {
+                                                             const uint2 *__restrict__ list, Dump dump) {
     constexpr int C = NChains<KIND>::C;
     __shared__ SumShared sh;
     for (unsigned int item = blockIdx.x; item < *list_count; item += gridDim.x) { // persistent CTAs over the work list
@@ -456,7 +491,7 @@ __global__ void __launch_bounds__(OS_THREADS) k_ord_summary2(PbPlanes b0, PbPlan
         for (int c = 0; c < C; c++)
             need[c] = chain_live<KIND, W>(c) && rec0[rec_row(sg, C, c, nblk, blk)].flag == F_PENDING;
         __syncthreads(); // every thread has read the flags before (warp 1, lane 0) rewrites the records
-        summarise_block<KIND, W, 2>(P, sg, blk, m0, m1, m2, psum + ((size_t)sg.bbase + blk) * C, rec0, rec1, need, sh);
+        summarise_block<KIND, W, 2>(P, sg, blk, m0, m1, m2, psum + ((size_t)sg.bbase + blk) * C, rec0, rec1, need, sh, dump);
     }
 }
 
@@ -475,6 +510,20 @@ struct ResolveShared {
     double res[7];
 };
 
+// the sequential loop over terms staged in shared memory: every lane runs the same chain (broadcast reads)
+__device__ __forceinline__ double chain_terms(const double *sm, uint32_t cnt, double s) {
+    const double2 *sm2 = reinterpret_cast<const double2 *>(sm);
+    uint32_t i = 0;
+#pragma unroll 8
+    for (; i + 2 <= cnt; i += 2) {
+        const double2 v = sm2[i >> 1];
+        s = __dadd_rn(s, v.x);
+        s = __dadd_rn(s, v.y);
+    }
+    if (i < cnt) s = __dadd_rn(s, sm[i]);
+    return s;
+}
+
 template <int KIND, bool W>
 __device__ __forceinline__ double replay_block(const PbPlanes &P, size_t first, uint32_t cnt, int chain, double m0,
                                                double m1, double m2, double s, int lane, double *sm) {
@@ -491,8 +540,26 @@ __device__ __forceinline__ double replay_block(const PbPlanes &P, size_t first, 
 #pragma unroll
     for (int q = 0; q < OB / 32; q++) sm[q * 32 + lane] = t[q];
     __syncwarp();
-#pragma unroll 16
-    for (uint32_t i = 0; i < cnt; i++) s = __dadd_rn(s, sm[i]); // every lane runs the same chain (broadcast reads)
+    s = chain_terms(sm, cnt, s);
+    __syncwarp();
+    return s;
+}
+
+// replay of a block whose terms were written out by the summary kernels
+__device__ __forceinline__ double replay_dump(const double *__restrict__ terms, uint32_t cnt, double s, int lane, double *sm) {
+    const double2 *src = reinterpret_cast<const double2 *>(terms);
+    double2 *dst = reinterpret_cast<double2 *>(sm);
+    double2 t[OB / 64];
+#pragma unroll
+    for (int q = 0; q < OB / 64; q++) {
+        const uint32_t k = q * 32 + lane;
+        t[q] = make_double2(0.0, 0.0);
+        if (2 * k < cnt) t[q] = src[k];
+    }
+#pragma unroll
+    for (int q = 0; q < OB / 64; q++) dst[q * 32 + lane] = t[q];
+    __syncwarp();
+    s = chain_terms(sm, cnt, s);
     __syncwarp();
     return s;
 }
@@ -503,6 +570,7 @@ __global__ void __launch_bounds__(32 * NChains<KIND>::C) k_ord_resolve(PbPlanes 
                                                                        PbStats *__restrict__ stats,
                                                                        const OrdRec *__restrict__ rec0,
                                                                        const OrdRec *__restrict__ rec1,
+                                                                       const double *__restrict__ dump_terms,
                                                                        bool use_summaries) {
     constexpr int C = NChains<KIND>::C;
     __shared__ ResolveShared sh;
@@ -518,7 +586,7 @@ __global__ void __launch_bounds__(32 * NChains<KIND>::C) k_ord_resolve(PbPlanes 
     long long cyc[3] = {0, 0, 0}, t_begin = clock64();
     const size_t row0 = rec_row(sg, C, chain, nblk, 0);
     OrdRec dummy;
-    dummy.sum = 0; dummy.lo = 1; dummy.hi = 0; dummy.eref = 0; dummy.flag = F_REPLAY;
+    dummy.sum = -1; dummy.lo = 1; dummy.hi = 0; dummy.eref = 0; dummy.flag = F_REPLAY;
     OrdRec nr = dummy, nr1 = dummy; // records of the next group, loaded one group ahead
     if (use_summaries && lane < (int)nblk) { nr = rec0[row0 + lane]; nr1 = rec1[row0 + lane]; }
     for (uint32_t g0 = 0; g0 < nblk; g0 += 32) {
@@ -596,8 +664,11 @@ __global__ void __launch_bounds__(32 * NChains<KIND>::C) k_ord_resolve(PbPlanes 
                 const long long t1 = clock64();
                 const double s = st.ok ? pb_state_to_double(st) : sd;
                 const uint32_t base = (g0 + b) * OB;
-                sd = replay_block<KIND, W>(P, (size_t)sg.lo + base, min((uint32_t)OB, n - base), chain, m0, m1, m2, s, lane,
-                                           sh.terms[chain]);
+                const uint32_t cnt = min((uint32_t)OB, n - base);
+                if (g.flag == F_REPLAY && g.a0.sum >= 0) // warp-uniform: the record names a dump slot
+                    sd = replay_dump(dump_terms + (size_t)g.a0.sum * OB, cnt, s, lane, sh.terms[chain]);
+                else
+                    sd = replay_block<KIND, W>(P, (size_t)sg.lo + base, cnt, chain, m0, m1, m2, s, lane, sh.terms[chain]);
                 st = pb_state_from_double(sd);
                 n_rep++;
                 n_why[why]++;
@@ -645,16 +716,21 @@ struct Scratch {
     double *psum;
     OrdRec *rec0, *rec1;
     uint2 *list;
-    unsigned int *list_count;
+    unsigned int *list_count; // [0] work list of summary2, [1] dump slots
+    Dump dump;
 };
+size_t dump_slots(size_t total_blocks) { return total_blocks / 4 + 1024; }
 Scratch carve(void *d_scratch, size_t total_blocks) {
     Scratch s;
     char *p = (char *)d_scratch;
+    s.dump.terms = (double *)p; p += dump_slots(total_blocks) * OB * sizeof(double); // 4 KB slots: keeps 16 B alignment
     s.psum = (double *)p; p += total_blocks * 7 * sizeof(double);
     s.rec0 = (OrdRec *)p; p += total_blocks * 7 * sizeof(OrdRec);
     s.rec1 = (OrdRec *)p; p += total_blocks * 7 * sizeof(OrdRec);
     s.list = (uint2 *)p; p += total_blocks * sizeof(uint2);
     s.list_count = (unsigned int *)p;
+    s.dump.count = s.list_count + 1;
+    s.dump.cap = (unsigned int)dump_slots(total_blocks);
     return s;
 }
 
@@ -673,14 +749,14 @@ void launch_pass(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t
           k_ord_blocksum<KIND, W><<<grid, OB_THREADS, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, sc.psum); }
         { PbProfScope p("k_ord_prefix", st, false);
           k_ord_prefix<C><<<dim3(chain_live<KIND, W>(0) ? C : C - 1, nseg), 32, 0, st>>>(d_segs, sc.psum, chain_live<KIND, W>(0) ? 0 : 1); }
-        PB_CUDA_OK(cudaMemsetAsync(sc.list_count, 0, sizeof(unsigned int), st));
+        PB_CUDA_OK(cudaMemsetAsync(sc.list_count, 0, 2 * sizeof(unsigned int), st));
         { PbProfScope p(KIND == KIND_MEAN ? "k_ord_summary_mean" : "k_ord_summary_centered", st);
-          k_ord_summary<KIND, W><<<grid, OS_THREADS, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, sc.psum, sc.rec0, sc.list_count, sc.list); }
+          k_ord_summary<KIND, W><<<grid, OS_THREADS, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, sc.psum, sc.rec0, sc.list_count, sc.list, sc.dump); }
         { PbProfScope p("k_ord_summary2", st, false);
-          k_ord_summary2<KIND, W><<<148 * 4, OS_THREADS, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, sc.psum, sc.rec0, sc.rec1, sc.list_count, sc.list); }
+          k_ord_summary2<KIND, W><<<148 * 4, OS_THREADS, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, sc.psum, sc.rec0, sc.rec1, sc.list_count, sc.list, sc.dump); }
     }
     { PbProfScope p(KIND == KIND_MEAN ? "k_ord_resolve_mean" : "k_ord_resolve_centered", st, !speculative);
-      k_ord_resolve<KIND, W><<<nseg, 32 * C, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, sc.rec0, sc.rec1, speculative); }
+      k_ord_resolve<KIND, W><<<nseg, 32 * C, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, sc.rec0, sc.rec1, sc.dump.terms, speculative); }
     PB_CUDA_OK(cudaGetLastError());
 }
 
@@ -705,7 +781,8 @@ void pb_ordered_chain_debug(unsigned long long out[35], bool reset) {
 uint32_t pb_ordered_blocks(uint32_t n) { return (n + OB - 1) / OB; }
 
 size_t pb_ordered_scratch_bytes(size_t total_blocks) {
-    return total_blocks * (7 * (sizeof(double) + 2 * sizeof(OrdRec)) + sizeof(uint2)) + 256;
+    return dump_slots(total_blocks) * OB * sizeof(double) +
+           total_blocks * (7 * (sizeof(double) + 2 * sizeof(OrdRec)) + sizeof(uint2)) + 256;
 }
 
 void pb_launch_pass_mean(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t max_n,

@@ -306,11 +306,33 @@ PB_HD PbState pb_state_from_double(double s) {
     return st;
 }
 PB_HD double pb_state_to_double(const PbState &st) { return (double)st.S * pb_pow2(st.e - 52); }
-// re-express in unit eref (exact) - false if the value has bits below it or would overflow the level range
+// re-express in unit eref (exact) - false if the value has bits below it or would overflow the level range.
+// Integer-only (this sits on the resolving warp's critical path): the value's binade is e - 52 + (index of
+// the top set bit of |S|); a valid state has at most 53 significant bits, so the shift is exact whenever
+// that binade is not below eref.
 PB_HD bool pb_state_rebase(PbState &st, int eref) {
     if (!st.ok) return false;
     if (st.e == eref) return true;
-    // normalise through the double: S has at most 53 significant bits
+    if (!pb_eref_ok(eref)) return false;
+    if (st.S == 0) { st.e = eref; return true; }
+    const unsigned long long a = (unsigned long long)(st.S < 0 ? -st.S : st.S);
+#if defined(__CUDA_ARCH__)
+    const int msb = 63 - __clzll((long long)a);
+#else
+    const int msb = 63 - __builtin_clzll(a);
+#endif
+    const int es = st.e - 52 + msb, k0 = es - eref;
+    if (es < -1000 || es > 1000 || k0 < 0 || k0 > PB_SPAN_MAX_LEVEL) return false;
+    const int d = st.e - eref; // k0 - (msb - 52): the result has msb + d = k0 + 52 <= 60
+    const unsigned long long r = d >= 0 ? a << d : a >> -d;
+    st.S = st.S < 0 ? -(long long)r : (long long)r;
+    st.e = eref;
+    return true;
+}
+// the previous formulation, through the double (kept for the self-test)
+PB_HD bool pb_state_rebase_ref(PbState &st, int eref) {
+    if (!st.ok) return false;
+    if (st.e == eref) return true;
     long long S;
     const double v = pb_state_to_double(st);
     if (!pb_eref_ok(eref) || !pb_state_to_units(v, eref, S)) return false;

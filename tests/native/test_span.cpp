@@ -171,9 +171,34 @@ static void run_chain(const std::vector<double> &a, Stats &st) {
     }
 }
 
+// pb_state_rebase (integer shifts) must agree with the formulation through the double for every valid
+// state (at most 53 significant bits, any trailing-zero count up to the level range) and every unit.
+static long check_rebase(std::mt19937_64 &rng) {
+    long wrong = 0;
+    for (int it = 0; it < 4000000; it++) {
+        PbState a;
+        const int tz = (int)(rng() % 10), bits = 1 + (int)(rng() % 53);
+        unsigned long long m = rng() >> (64 - bits);
+        m |= 1ULL << (bits - 1);
+        if (bits + tz > 61) continue;
+        a.S = (long long)(m << tz);
+        if (rng() & 1) a.S = -a.S;
+        if (rng() % 64 == 0) a.S = 0;
+        a.e = (int)(rng() % 1900) - 950;
+        a.ok = (rng() % 32) != 0;
+        const int eref = a.e + (int)(rng() % 25) - 12 + ((rng() % 16 == 0) ? 900 : 0);
+        PbState b = a;
+        const bool ra = pb_state_rebase(a, eref), rb = pb_state_rebase_ref(b, eref);
+        if (ra != rb || (ra && (a.S != b.S || a.e != b.e))) wrong++;
+    }
+    printf("rebase self-test: %ld mismatches\n", wrong);
+    return wrong;
+}
+
 int main(int argc, char **argv) {
     const int reps = argc > 1 ? atoi(argv[1]) : 6;
     std::mt19937_64 rng(12345);
+    if (check_rebase(rng)) { printf("FAILED\n"); return 1; }
     std::uniform_real_distribution<double> U(0.0, 1.0);
     std::normal_distribution<double> G(0.0, 1.0);
     struct Family { std::string name; int kind; };
