@@ -229,42 +229,50 @@ __device__ __noinline__ void run_push_slow(PbRun *r, double term, double approx,
     pb_run_push<NV>(*r, term, approx, eref);
 }
 
-// Summarises block `blk` of segment `sg` for every chain with need[c] (NV = 1: one record, parity-dependent
-// blocks are left F_PENDING; NV = 2: both parities).  All threads of the CTA take part.
-template <int KIND, bool W, int NV>
-__device__ __forceinline__ bool summarise_block(const PbPlanes &P, const PbSeg &sg, uint32_t blk, double m0, double m1,
-                                                double m2, const double *__restrict__ pstart, OrdRec *__restrict__ rec0,
-                                                OrdRec *__restrict__ rec1, const bool *need, SumShared &sh, const Dump &dump) {
+// Summarises block `blk` of segment `sg`.  NC = C: every live chain, one record each (NV = 1; blocks with a
+// parity-dependent step are left F_PENDING and returned as a bit mask).  NC = 1: the single chain `ch0`, for
+// both start parities (NV = 2, the work-list pass).  All threads of the CTA take part.
+template <int KIND, bool W, int NV, int NC>
+__device__ __forceinline__ unsigned summarise_block(const PbPlanes &P, const PbSeg &sg, uint32_t blk, int ch0, double m0,
+                                                    double m1, double m2, const double *__restrict__ pstart,
+                                                    OrdRec *__restrict__ rec0, OrdRec *__restrict__ rec1, SumShared &sh,
+                                                    const Dump &dump) {
     constexpr int C = NChains<KIND>::C;
     constexpr int NOLEVEL = -(1 << 20);
+    static_assert(NC == 1 || NC == C, "all chains or one");
+    auto chain_of = [&](int slot) { return NC == 1 ? ch0 : slot; };
+    auto live = [&](int slot) { return NC == 1 ? true : chain_live<KIND, W>(slot); };
+    auto terms = [&](size_t p, double *t) {
+        if (NC == 1) t[0] = term_one<KIND, W>(ch0, W ? P.w[p] : 1.0, P.c[0][p], P.c[1][p], P.c[2][p], m0, m1, m2);
+        else terms_all<KIND, W>(W ? P.w[p] : 1.0, P.c[0][p], P.c[1][p], P.c[2][p], m0, m1, m2, t);
+    };
     const uint32_t nblk = (sg.n + OB - 1) / OB;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t i0 = blk * OB + threadIdx.x * OS_PER; // this thread's consecutive elements
     const bool have = i0 < sg.n;
     const int mycnt = have ? min(OS_PER, (int)(sg.n - i0)) : 0;
-    if (threadIdx.x < C) { sh.flag[threadIdx.x] = 0; sh.slot[threadIdx.x] = -1; }
+    if (threadIdx.x < NC) { sh.flag[threadIdx.x] = 0; sh.slot[threadIdx.x] = -1; }
 
     // ---- phase 1: approximate running sum at the start of this thread's elements ------------------
-    double tstart[C];
+    double tstart[NC];
     {
-        double tl[C];
+        double tl[NC];
 #pragma unroll
-        for (int c = 0; c < C; c++) tl[c] = 0.0;
+        for (int c = 0; c < NC; c++) tl[c] = 0.0;
 #pragma unroll
         for (int k = 0; k < OS_PER; k++) {
             if (k < mycnt) {
-                const size_t p = (size_t)sg.lo + i0 + k;
                 double t[C];
-                terms_all<KIND, W>(W ? P.w[p] : 1.0, P.c[0][p], P.c[1][p], P.c[2][p], m0, m1, m2, t);
+                terms((size_t)sg.lo + i0 + k, t);
 #pragma unroll
-                for (int c = 0; c < C; c++)
-                    if (chain_live<KIND, W>(c)) tl[c] += t[c];
+                for (int c = 0; c < NC; c++)
+                    if (live(c)) tl[c] += t[c];
             }
         }
 #pragma unroll
-        for (int c = 0; c < C; c++) {
+        for (int c = 0; c < NC; c++) {
             tstart[c] = 0.0;
-            if (!need[c]) continue; // CTA-uniform
+            if (!live(c)) continue;
             double incl = tl[c];
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -276,50 +284,49 @@ __device__ __forceinline__ bool summarise_block(const PbPlanes &P, const PbSeg &
         }
         __syncthreads();
 #pragma unroll
-        for (int c = 0; c < C; c++)
-            if (need[c]) tstart[c] += pstart[c] + (warp ? sh.wsum[c] : 0.0);
+        for (int c = 0; c < NC; c++)
+            if (live(c)) tstart[c] += pstart[chain_of(c)] + (warp ? sh.wsum[c] : 0.0);
     }
     // ---- phase 2: predicted binade of every partial sum (start states included) -> range over the block;
     //      at the same time the cheap summary, valid if this thread's predictions all sit on one level:
     //      it works in the ulp of the thread's own level, the block's unit is not needed yet ----------------
-    int tlevel[C]; // the thread's (absolute) level if uniform in binade and sign, else NOLEVEL
-    PbUni uni[C];
+    int tlevel[NC]; // the thread's (absolute) level if uniform in binade and sign, else NOLEVEL
+    PbUni uni[NC];
     {
-        int emin[C], emax[C];
-        double run[C], uscale[C];
-        bool flip[C];
+        int emin[NC], emax[NC];
+        double run[NC], uscale[NC];
+        bool flip[NC];
 #pragma unroll
-        for (int c = 0; c < C; c++) {
+        for (int c = 0; c < NC; c++) {
             run[c] = tstart[c];
             const int e = pb_exponent_of(run[c]);
             emin[c] = have ? e : (1 << 20);
             emax[c] = have ? e : NOLEVEL;
             flip[c] = false;
             pb_uni_begin(uni[c]);
-            uscale[c] = (NV == 1 && pb_eref_ok(e)) ? pb_pow2(52 - e) : 0.0;
+            uscale[c] = pb_eref_ok(e) ? pb_pow2(52 - e) : 0.0;
         }
 #pragma unroll
         for (int k = 0; k < OS_PER; k++) {
             if (k < mycnt) {
-                const size_t p = (size_t)sg.lo + i0 + k;
                 double t[C];
-                terms_all<KIND, W>(W ? P.w[p] : 1.0, P.c[0][p], P.c[1][p], P.c[2][p], m0, m1, m2, t);
+                terms((size_t)sg.lo + i0 + k, t);
 #pragma unroll
-                for (int c = 0; c < C; c++) {
-                    if (!chain_live<KIND, W>(c)) continue;
+                for (int c = 0; c < NC; c++) {
+                    if (!live(c)) continue;
                     run[c] += t[c];
                     const int e = pb_exponent_of(run[c]);
                     emin[c] = min(emin[c], e);
                     emax[c] = max(emax[c], e);
                     flip[c] |= (run[c] < 0) != (tstart[c] < 0);
-                    if (NV == 1) pb_uni_push(uni[c], t[c], uscale[c]);
+                    pb_uni_push(uni[c], t[c], uscale[c]);
                 }
             }
         }
 #pragma unroll
-        for (int c = 0; c < C; c++) {
+        for (int c = 0; c < NC; c++) {
             tlevel[c] = (have && emin[c] == emax[c] && !flip[c]) ? emin[c] : NOLEVEL;
-            if (!need[c]) continue; // CTA-uniform
+            if (!live(c)) continue;
 #pragma unroll
             for (int o = 16; o; o >>= 1) {
                 emin[c] = min(emin[c], __shfl_xor_sync(0xffffffffu, emin[c], o));
@@ -330,46 +337,50 @@ __device__ __forceinline__ bool summarise_block(const PbPlanes &P, const PbSeg &
         __syncthreads();
     }
     // ---- phase 3: spans in units of the block's lowest binade -----------------------------------------
-    int eref[C];
-    bool usable[C], slow[C];
-    PbRun run_st[C];
+    int eref[NC];
+    bool usable[NC], slow[NC];
+    PbRun run_st[NC];
     bool any_slow = false;
 #pragma unroll
-    for (int c = 0; c < C; c++) {
-        const int lo = min(sh.emin[0][c], sh.emin[1][c]), hi = max(sh.emax[0][c], sh.emax[1][c]);
+    for (int c = 0; c < NC; c++) {
+        const int lo = live(c) ? min(sh.emin[0][c], sh.emin[1][c]) : 0, hi = live(c) ? max(sh.emax[0][c], sh.emax[1][c]) : 0;
         eref[c] = lo;
         // zero / subnormal / non-finite predictions, or too wide a range: replay
-        usable[c] = need[c] && pb_eref_ok(lo) && pb_eref_ok(hi) && hi - lo <= PB_SPAN_MAX_LEVEL;
+        usable[c] = live(c) && pb_eref_ok(lo) && pb_eref_ok(hi) && hi - lo <= PB_SPAN_MAX_LEVEL;
         if (!usable[c]) eref[c] = 0;
-        const bool fast = NV == 1 && usable[c] && tlevel[c] != NOLEVEL;
+        // a thread whose predictions sit on one level is a plain translation for BOTH start parities unless
+        // it holds a tie on the lowest level; only then (NV = 2) it is redone by the general path
+        bool fast = usable[c] && tlevel[c] != NOLEVEL;
+        if (fast) {
+            pb_uni_end(uni[c], run_st[c], tlevel[c] - eref[c], tstart[c] < 0);
+            if (NV == 2 && run_st[c].sensitive) fast = false;
+        }
+        if (!fast) pb_run_begin(run_st[c], tstart[c], eref[c]);
         slow[c] = usable[c] && have && !fast;
         any_slow |= slow[c];
-        if (fast) pb_uni_end(uni[c], run_st[c], tlevel[c] - eref[c], tstart[c] < 0);
-        else pb_run_begin(run_st[c], tstart[c], eref[c]);
     }
     if (any_slow) { // the general path, element by element, for the chains of this thread that need it
-        double run[C];
+        double run[NC];
 #pragma unroll
-        for (int c = 0; c < C; c++) run[c] = tstart[c];
+        for (int c = 0; c < NC; c++) run[c] = tstart[c];
 #pragma unroll 1
         for (int k = 0; k < mycnt; k++) {
-            const size_t p = (size_t)sg.lo + i0 + k;
             double t[C];
-            terms_all<KIND, W>(W ? P.w[p] : 1.0, P.c[0][p], P.c[1][p], P.c[2][p], m0, m1, m2, t);
+            terms((size_t)sg.lo + i0 + k, t);
 #pragma unroll
-            for (int c = 0; c < C; c++) {
-                if (!chain_live<KIND, W>(c)) continue;
+            for (int c = 0; c < NC; c++) {
+                if (!live(c)) continue;
                 run[c] += t[c]; // same operations as phase 2: same predictions
                 if (slow[c] && !run_st[c].bad) run_push_slow<NV>(&run_st[c], t[c], run[c], eref[c]);
             }
         }
     }
     // in-order composition over the warp (lane i absorbs lane i + o), all chains interleaved
-    PbSpan2 v[C];
+    PbSpan2 v[NC];
 #pragma unroll
-    for (int c = 0; c < C; c++) {
+    for (int c = 0; c < NC; c++) {
         v[c] = pb_span2_identity();
-        if (!need[c]) continue; // CTA-uniform
+        if (!live(c)) continue;
         if (usable[c] && have) {
             v[c] = pb_run_span<NV>(run_st[c]);
             const int f = (run_st[c].bad ? 1 : 0) | (run_st[c].sensitive ? 2 : 0);
@@ -389,11 +400,11 @@ __device__ __forceinline__ bool summarise_block(const PbPlanes &P, const PbSeg &
         if (warp == 0 && lane == 0) sh.span[c] = v[c];
     }
     __syncthreads();
-    bool pending = false;
+    unsigned pending = 0;
     if (warp == 1 && lane == 0) {
 #pragma unroll
-        for (int c = 0; c < C; c++) {
-            if (!need[c]) continue;
+        for (int c = 0; c < NC; c++) {
+            if (!live(c)) continue;
             PbSpan2 w;
             if (NV == 2) w = pb_span2_cat(sh.span[c], v[c]);
             else { w.p[0] = pb_span_cat(sh.span[c].p[0], v[c].p[0]); w.p[1] = w.p[0]; }
@@ -403,12 +414,12 @@ __device__ __forceinline__ bool summarise_block(const PbPlanes &P, const PbSeg &
             else if (NV == 1) flag = (f & 2) ? F_PENDING : F_OK;
             // a parity-dependent block whose start state sits above its lowest binade (enforced by its own
             // start constraint) only ever sees parity 0: variant 0 of the two-parity composition is a plain record
-            else flag = pb_exponent_of(pstart[c]) - eref[c] < 1 ? F_SENSITIVE : F_OK;
+            else flag = pb_exponent_of(pstart[chain_of(c)]) - eref[c] < 1 ? F_SENSITIVE : F_OK;
             // contradictory predictions (empty interval): never applicable.  A two-parity record stays
             // usable if one parity is valid; the resolve checks the interval of the parity it needs.
             if (flag == F_OK && !pb_span_valid(w.p[0])) flag = F_REPLAY;
             if (flag == F_SENSITIVE && !pb_span_valid(w.p[0]) && !pb_span_valid(w.p[1])) flag = F_REPLAY;
-            const size_t row = rec_row(sg, C, c, nblk, blk);
+            const size_t row = rec_row(sg, C, chain_of(c), nblk, blk);
             OrdRec o0;
             o0.sum = w.p[0].sum; o0.lo = w.p[0].lo; o0.hi = w.p[0].hi; o0.eref = eref[c]; o0.flag = flag;
             if (flag == F_REPLAY) { // the record carries the dump slot instead of a translation
@@ -422,27 +433,26 @@ __device__ __forceinline__ bool summarise_block(const PbPlanes &P, const PbSeg &
                 o1.sum = w.p[1].sum; o1.lo = w.p[1].lo; o1.hi = w.p[1].hi; o1.eref = eref[c]; o1.flag = flag;
                 rec1[row] = o1;
             }
-            pending |= flag == F_PENDING;
+            if (flag == F_PENDING) pending |= 1u << c;
         }
     }
     __syncthreads();
     {
         bool any = false;
 #pragma unroll
-        for (int c = 0; c < C; c++) any |= sh.slot[c] >= 0;
+        for (int c = 0; c < NC; c++) any |= sh.slot[c] >= 0;
         if (any && have) { // CTA-uniform `any`: write this thread's terms of the dumped chains
 #pragma unroll 1
             for (int k = 0; k < mycnt; k++) {
-                const size_t p = (size_t)sg.lo + i0 + k;
                 double t[C];
-                terms_all<KIND, W>(W ? P.w[p] : 1.0, P.c[0][p], P.c[1][p], P.c[2][p], m0, m1, m2, t);
+                terms((size_t)sg.lo + i0 + k, t);
 #pragma unroll
-                for (int c = 0; c < C; c++)
+                for (int c = 0; c < NC; c++)
                     if (sh.slot[c] >= 0) dump.terms[(size_t)sh.slot[c] * OB + threadIdx.x * OS_PER + k] = t[c];
             }
         }
     }
-    return pending; // meaningful on (warp 1, lane 0)
+    return pending; // meaningful on (warp 1, lane 0): chains left F_PENDING
 }
 
 template <int KIND, bool W>
@@ -459,17 +469,19 @@ __global__ void __launch_bounds__(OS_THREADS, PB_OS_MINB) k_ord_summary(PbPlanes
     const PbPlanes &P = sg.buf ? b1 : b0;
     double m0 = 0, m1 = 0, m2 = 0;
     if (KIND == KIND_CENTERED) { m0 = stats[seg].mean[0]; m1 = stats[seg].mean[1]; m2 = stats[seg].mean[2]; }
-    bool need[C];
-#pragma unroll
-    for (int c = 0; c < C; c++) need[c] = chain_live<KIND, W>(c);
-    const bool pending = summarise_block<KIND, W, 1>(P, sg, blockIdx.x, m0, m1, m2,
-                                                     psum + ((size_t)sg.bbase + blockIdx.x) * C, rec0, nullptr, need, sh, dump);
-    if (threadIdx.x == 32 && pending) list[atomicAdd(list_count, 1u)] = make_uint2((unsigned)seg, blockIdx.x);
+    const unsigned pending = summarise_block<KIND, W, 1, C>(P, sg, blockIdx.x, 0, m0, m1, m2,
+                                                            psum + ((size_t)sg.bbase + blockIdx.x) * C, rec0, nullptr, sh, dump);
+    if (threadIdx.x == 32 && pending) { // one work item per (block, chain): block index < 2^28
+        const unsigned int at = atomicAdd(list_count, (unsigned)__popc(pending));
+        unsigned int k = 0;
+        for (int c = 0; c < C; c++)
+            if (pending >> c & 1u) list[at + k++] = make_uint2((unsigned)seg, blockIdx.x | ((unsigned)c << 28));
+    }
 }
 
-// ---- S3b: blocks with a parity-dependent step: both start parities ---------------------------------
+// ---- S3b: (block, chain) pairs with a parity-dependent step: both start parities ---------------------
 template <int KIND, bool W>
-__global__ void __launch_bounds__(OS_THREADS, PB_OS_MINB) k_ord_summary2(PbPlanes b0, PbPlanes b1, const PbSeg *__restrict__ segs,
+__global__ void __launch_bounds__(OS_THREADS) k_ord_summary2(PbPlanes b0, PbPlanes b1, const PbSeg *__restrict__ segs,
                                                              const PbStats *__restrict__ stats,
                                                              const double *__restrict__ psum, OrdRec *__restrict__ rec0,
                                                              OrdRec *__restrict__ rec1,
@@ -479,36 +491,97 @@ __global__ void __launch_bounds__(OS_THREADS, PB_OS_MINB) k_ord_summary2(PbPlane
     __shared__ SumShared sh;
     for (unsigned int item = blockIdx.x; item < *list_count; item += gridDim.x) { // persistent CTAs over the work list
         const int seg = (int)list[item].x;
-        const uint32_t blk = list[item].y;
+        const uint32_t blk = list[item].y & 0x0fffffffu;
+        const int chain = (int)(list[item].y >> 28);
         const PbSeg sg = segs[seg];
         const PbPlanes &P = sg.buf ? b1 : b0;
-        const uint32_t nblk = (sg.n + OB - 1) / OB;
         double m0 = 0, m1 = 0, m2 = 0;
         if (KIND == KIND_CENTERED) { m0 = stats[seg].mean[0]; m1 = stats[seg].mean[1]; m2 = stats[seg].mean[2]; }
         __syncthreads(); // sh is reused across items
-        bool need[C]; // only the chains that asked for it are redone (uniform across the CTA)
+        summarise_block<KIND, W, 2, 1>(P, sg, blk, chain, m0, m1, m2, psum + ((size_t)sg.bbase + blk) * C, rec0, rec1, sh, dump);
+    }
+}
+
+// ---- S3c: group records ------------------------------------------------------------------------------
+// 32 consecutive block records of a chain composed into one (same monoid), in parallel over all groups, so
+// that the sequential walk below moves 1024 blocks per step where nothing special happens.  A group that
+// holds anything but plain records of one unit is marked F_REPLAY ("walk its records").
+__device__ __forceinline__ size_t group_row(const PbSeg &sg, int C, int seg, int chain, uint32_t nblk) {
+    // disjoint ranges of ceil(nblk / 32) rows per (segment, chain) in a table of total_blocks * C / 32 + nseg * (C + 1) rows
+    return ((size_t)sg.bbase * C + (size_t)chain * nblk) / 32 + (size_t)chain + (size_t)seg * (C + 1);
+}
+
+template <int KIND, bool W>
+__global__ void __launch_bounds__(32 * NChains<KIND>::C) k_ord_group(const PbSeg *__restrict__ segs,
+                                                                     const OrdRec *__restrict__ rec0,
+                                                                     OrdRec *__restrict__ grec) {
+    constexpr int C = NChains<KIND>::C;
+    const int seg = blockIdx.y, chain = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const PbSeg sg = segs[seg];
+    const uint32_t nblk = (sg.n + OB - 1) / OB, g0 = blockIdx.x * 32;
+    if (g0 >= nblk || !chain_live<KIND, W>(chain)) return;
+    const uint32_t gcnt = min(32u, nblk - g0);
+    PbSpan v = pb_span_identity();
+    int eref = 0, flag = F_OK;
+    if (lane < (int)gcnt) {
+        const OrdRec r = rec0[rec_row(sg, C, chain, nblk, g0 + lane)];
+        v.sum = r.sum; v.lo = r.lo; v.hi = r.hi;
+        eref = r.eref;
+        flag = r.flag;
+    }
+    const int e0 = __shfl_sync(0xffffffffu, eref, 0);
+    const bool plain = __all_sync(0xffffffffu, lane >= (int)gcnt || (flag == F_OK && eref == e0));
 #pragma unroll
-        for (int c = 0; c < C; c++)
-            need[c] = chain_live<KIND, W>(c) && rec0[rec_row(sg, C, c, nblk, blk)].flag == F_PENDING;
-        __syncthreads(); // every thread has read the flags before (warp 1, lane 0) rewrites the records
-        summarise_block<KIND, W, 2>(P, sg, blk, m0, m1, m2, psum + ((size_t)sg.bbase + blk) * C, rec0, rec1, need, sh, dump);
+    for (int o = 1; o < 32; o <<= 1) { // in-order composition: lane i absorbs lane i + o
+        const PbSpan r = shfl_down_span(v, o);
+        if ((lane & (2 * o - 1)) == 0) v = pb_span_cat(v, r);
+    }
+    if (lane == 0) {
+        OrdRec o;
+        o.sum = v.sum; o.lo = v.lo; o.hi = v.hi; o.eref = e0;
+        o.flag = (plain && pb_span_valid(v)) ? F_OK : F_REPLAY;
+        grec[group_row(sg, C, seg, chain, nblk) + blockIdx.x] = o;
     }
 }
 
 // ---- S4: ordered resolve ---------------------------------------------------------------------------
-// One CTA per cluster, one WARP per chain; the warp carries the exact running sum, as an integer in the
-// unit of the records it is walking (pb_span.h: PbState).  Records are fetched 32 at a time, one group
-// ahead.  A group of plain records that share their unit is applied with one in-order warp scan of the
-// span monoid + a ballot for the first record whose interval does not hold.  Any other group (parity-
-// dependent records, unit changes, unusable records) is staged in shared memory and walked record by
-// record - a dozen integer operations each.  A record that cannot be applied means its block is REPLAYED:
-// the block's terms are staged in shared memory (coalesced) and added one by one - the reference loop.
+// One CTA per cluster, one WARP per chain; the warp carries the exact running sum as an integer in the
+// unit of the records it is walking (pb_span.h: PbState; every lane holds the same state).
+//   level 2: 32 group records at a time - in-order warp scan of the span monoid + a ballot for the first
+//            group whose interval does not hold (or that is not plain); everything before it is applied
+//            in one step;
+//   level 1: the records of that group, the same way: scan over the plain run that starts at the current
+//            record, then the record the scan stopped at on its own (two-parity record, unit change,
+//            interval failure, unusable record), then scan again;
+//   a record that cannot be applied means its block is REPLAYED: the block's terms (written out by the
+//   summary kernels for the blocks they flagged, recomputed from the planes otherwise) are staged in
+//   shared memory and added one by one - the reference loop.
 struct ResolveShared {
     double terms[7][OB];
-    long long sum[7][2][32], lo[7][2][32], hi[7][2][32];
-    int eref[7][32], flag[7][32];
     double res[7];
 };
+
+// Applies the longest acceptable prefix of the plain records held by lanes [first, cnt) (one record per
+// lane, in order) to the state; returns how many were applied.
+__device__ __forceinline__ uint32_t scan_apply(const OrdRec &r, uint32_t cnt, uint32_t first, PbState &st, int lane) {
+    const int e0 = __shfl_sync(0xffffffffu, r.eref, (int)first);
+    if (!pb_state_rebase(st, e0)) return 0; // warp-uniform
+    PbSpan v = pb_span_identity(); // lanes before `first`
+    if (lane >= (int)first) {
+        if (lane < (int)cnt && r.flag == F_OK && r.eref == e0) { v.sum = r.sum; v.lo = r.lo; v.hi = r.hi; }
+        else v = pb_span_invalid(); // absorbing: nothing from here on is accepted
+    }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { // in-order inclusive scan of the monoid
+        const PbSpan up = shfl_up_span(v, o);
+        if (lane >= o) v = pb_span_cat(up, v);
+    }
+    const bool valid = pb_span_valid(v) && st.S >= v.lo && st.S <= v.hi;
+    const unsigned fails = __ballot_sync(0xffffffffu, lane >= (int)first && !valid);
+    const uint32_t f = fails ? (uint32_t)(__ffs(fails) - 1) : 32u; // lanes >= cnt always fail: f <= cnt when cnt < 32
+    if (f > first) st.S += __shfl_sync(0xffffffffu, v.sum, (int)f - 1);
+    return f - first;
+}
 
 // the sequential loop over terms staged in shared memory: every lane runs the same chain (broadcast reads)
 __device__ __forceinline__ double chain_terms(const double *sm, uint32_t cnt, double s) {
@@ -570,103 +643,88 @@ __global__ void __launch_bounds__(32 * NChains<KIND>::C) k_ord_resolve(PbPlanes 
                                                                        PbStats *__restrict__ stats,
                                                                        const OrdRec *__restrict__ rec0,
                                                                        const OrdRec *__restrict__ rec1,
+                                                                       const OrdRec *__restrict__ grec,
                                                                        const double *__restrict__ dump_terms,
                                                                        bool use_summaries) {
     constexpr int C = NChains<KIND>::C;
-    __shared__ ResolveShared sh;
+    __shared__ __align__(16) ResolveShared sh;
     const int seg = blockIdx.x, chain = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const PbSeg sg = segs[seg];
     const PbPlanes &P = sg.buf ? b1 : b0;
-    const uint32_t n = sg.n, nblk = chain_live<KIND, W>(chain) ? (n + OB - 1) / OB : 0u;
+    const uint32_t n = sg.n, nblk_all = (n + OB - 1) / OB, nblk = chain_live<KIND, W>(chain) ? nblk_all : 0u;
     double m0 = 0, m1 = 0, m2 = 0;
     if (KIND == KIND_CENTERED) { m0 = stats[seg].mean[0]; m1 = stats[seg].mean[1]; m2 = stats[seg].mean[2]; }
     double sd = 0.0;                          // the exact running sum, authoritative while !st.ok
     PbState st = pb_state_from_double(sd);    // ... and as integer * unit while st.ok
     unsigned int n_acc = 0, n_rep = 0, n_acc2 = 0, n_gen = 0, n_why[3] = {0, 0, 0};
     long long cyc[3] = {0, 0, 0}, t_begin = clock64();
-    const size_t row0 = rec_row(sg, C, chain, nblk, 0);
+    const size_t row0 = rec_row(sg, C, chain, nblk_all, 0);
+    const size_t grow0 = group_row(sg, C, seg, chain, nblk_all);
+    const uint32_t ngrp = (nblk + 31) / 32;
     OrdRec dummy;
     dummy.sum = -1; dummy.lo = 1; dummy.hi = 0; dummy.eref = 0; dummy.flag = F_REPLAY;
-    OrdRec nr = dummy, nr1 = dummy; // records of the next group, loaded one group ahead
-    if (use_summaries && lane < (int)nblk) { nr = rec0[row0 + lane]; nr1 = rec1[row0 + lane]; }
-    for (uint32_t g0 = 0; g0 < nblk; g0 += 32) {
+    uint32_t g0 = 0; // next block; a multiple of 32 at the top of the loop
+    while (g0 < nblk) {
+        // ---- level 2: up to 32 groups in one step ------------------------------------------------------
+        if (use_summaries && nblk - g0 > 64) {
+            const long long t0 = clock64();
+            const uint32_t G = g0 >> 5, gc = min(32u, ngrp - G);
+            OrdRec q = dummy;
+            if (lane < (int)gc) q = grec[grow0 + G + lane];
+            const uint32_t a = scan_apply(q, gc, 0, st, lane);
+            const uint32_t blocks = min(32u * a, nblk - g0);
+            n_acc += blocks;
+            g0 += blocks;
+            cyc[0] += clock64() - t0;
+            if (a == gc || g0 >= nblk) continue;
+        }
+        // ---- level 1: the records of one group --------------------------------------------------------
         const uint32_t gcnt = min(32u, nblk - g0);
-        const OrdRec r = nr, r1 = nr1; // r1 is only meaningful where r.flag == F_SENSITIVE
-        nr = dummy;
-        nr1 = dummy;
-        if (use_summaries && g0 + 32 + lane < nblk) { nr = rec0[row0 + g0 + 32 + lane]; nr1 = rec1[row0 + g0 + 32 + lane]; }
-        if (use_summaries && g0 + 32 * 5 + lane < nblk) { // pull the records of the group four further ahead into L1
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(rec0 + row0 + g0 + 32 * 5 + lane));
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(rec1 + row0 + g0 + 32 * 5 + lane));
+        OrdRec r = dummy, r1 = dummy; // r1 is only meaningful where r.flag == F_SENSITIVE
+        if (use_summaries && lane < (int)gcnt) {
+            r = rec0[row0 + g0 + lane];
+            if (r.flag == F_SENSITIVE) r1 = rec1[row0 + g0 + lane];
         }
         uint32_t next = 0;
-        // ---- fast path: the whole group is plain and shares its unit ------------------------------------
-        long long t0 = clock64();
-        const int e0 = __shfl_sync(0xffffffffu, r.eref, 0);
-        const bool uniform = __all_sync(0xffffffffu, lane >= (int)gcnt || (r.flag == F_OK && r.eref == e0));
-        if (uniform && pb_state_rebase(st, e0)) {
-            PbSpan v = pb_span_identity();
-            if (lane < (int)gcnt) { v.sum = r.sum; v.lo = r.lo; v.hi = r.hi; }
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { // in-order inclusive scan of the monoid
-                const PbSpan up = shfl_up_span(v, o);
-                if (lane >= o) v = pb_span_cat(up, v);
+        while (next < gcnt) {
+            long long t0 = clock64();
+            const int fl = __shfl_sync(0xffffffffu, r.flag, (int)next);
+            if (fl == F_OK) { // the plain run that starts here
+                const uint32_t a = scan_apply(r, gcnt, next, st, lane);
+                n_acc += a;
+                next += a;
+                cyc[0] += clock64() - t0;
+                if (next >= gcnt) break;
+                t0 = clock64();
             }
-            const bool valid = pb_span_valid(v) && st.S >= v.lo && st.S <= v.hi;
-            const unsigned fails = __ballot_sync(0xffffffffu, lane < (int)gcnt && !valid);
-            const uint32_t f = fails ? (uint32_t)(__ffs(fails) - 1) : gcnt;
-            if (f > 0) {
-                st.S += __shfl_sync(0xffffffffu, v.sum, (int)f - 1);
-                n_acc += f;
-                next = f;
-            }
-        }
-        cyc[0] += clock64() - t0;
-        if (next >= gcnt) continue;
-        // ---- general path: stage the records, walk them one by one -------------------------------------
-        t0 = clock64();
-        sh.sum[chain][0][lane] = r.sum; sh.lo[chain][0][lane] = r.lo; sh.hi[chain][0][lane] = r.hi;
-        sh.sum[chain][1][lane] = r1.sum; sh.lo[chain][1][lane] = r1.lo; sh.hi[chain][1][lane] = r1.hi;
-        sh.eref[chain][lane] = r.eref;
-        sh.flag[chain][lane] = r.flag;
-        __syncwarp();
-        // software-pipelined: record b + 1 is fetched from shared memory while record b is applied, so the
-        // loop-carried dependency is just the integer state
-        struct Staged { PbSpan a0, a1; int eref, flag; };
-        auto fetch = [&](uint32_t b) {
-            Staged g;
-            g.flag = sh.flag[chain][b];
-            g.eref = sh.eref[chain][b];
-            g.a0.sum = sh.sum[chain][0][b]; g.a0.lo = sh.lo[chain][0][b]; g.a0.hi = sh.hi[chain][0][b];
-            g.a1.sum = sh.sum[chain][1][b]; g.a1.lo = sh.lo[chain][1][b]; g.a1.hi = sh.hi[chain][1][b];
-            return g;
-        };
-        Staged cur = fetch(next);
-        n_gen += gcnt - next;
-        for (uint32_t b = next; b < gcnt; b++) {
-            const Staged g = cur;
-            if (b + 1 < gcnt) cur = fetch(b + 1);
+            // record `next` on its own (warp-uniform)
+            const int src = (int)next;
+            const int fl1 = __shfl_sync(0xffffffffu, r.flag, src), er = __shfl_sync(0xffffffffu, r.eref, src);
+            const long long s0 = __shfl_sync(0xffffffffu, r.sum, src);
             bool ok = false;
             int why = 0;
-            if (g.flag == F_OK || g.flag == F_SENSITIVE) {
-                if (pb_state_rebase(st, g.eref)) {
-                    const bool odd = (st.S & 1LL) && g.flag == F_SENSITIVE;
-                    const long long vsum = odd ? g.a1.sum : g.a0.sum, vlo = odd ? g.a1.lo : g.a0.lo, vhi = odd ? g.a1.hi : g.a0.hi;
+            n_gen++;
+            if (fl1 == F_OK || fl1 == F_SENSITIVE) {
+                if (pb_state_rebase(st, er)) {
+                    const bool odd = (st.S & 1LL) && fl1 == F_SENSITIVE;
+                    const OrdRec &pick = odd ? r1 : r;
+                    const long long vsum = odd ? __shfl_sync(0xffffffffu, pick.sum, src) : s0;
+                    const long long vlo = __shfl_sync(0xffffffffu, pick.lo, src), vhi = __shfl_sync(0xffffffffu, pick.hi, src);
                     if (st.S >= vlo && st.S <= vhi) {
                         st.S += vsum;
                         ok = true;
                         n_acc++;
-                        n_acc2 += g.flag == F_SENSITIVE;
+                        n_acc2 += fl1 == F_SENSITIVE;
                     } else why = 2;
                 } else why = 1;
             }
             if (!ok) {
                 const long long t1 = clock64();
                 const double s = st.ok ? pb_state_to_double(st) : sd;
-                const uint32_t base = (g0 + b) * OB;
+                const uint32_t base = (g0 + next) * OB;
                 const uint32_t cnt = min((uint32_t)OB, n - base);
-                if (g.flag == F_REPLAY && g.a0.sum >= 0) // warp-uniform: the record names a dump slot
-                    sd = replay_dump(dump_terms + (size_t)g.a0.sum * OB, cnt, s, lane, sh.terms[chain]);
+                if (fl1 == F_REPLAY && s0 >= 0) // the record names a dump slot
+                    sd = replay_dump(dump_terms + (size_t)s0 * OB, cnt, s, lane, sh.terms[chain]);
                 else
                     sd = replay_block<KIND, W>(P, (size_t)sg.lo + base, cnt, chain, m0, m1, m2, s, lane, sh.terms[chain]);
                 st = pb_state_from_double(sd);
@@ -676,9 +734,10 @@ __global__ void __launch_bounds__(32 * NChains<KIND>::C) k_ord_resolve(PbPlanes 
                 cyc[2] += dt;
                 cyc[1] -= dt;
             }
+            next++;
+            cyc[1] += clock64() - t0;
         }
-        __syncwarp();
-        cyc[1] += clock64() - t0;
+        g0 += 32;
     }
     if (lane == 0) {
         sh.res[chain] = st.ok ? pb_state_to_double(st) : sd;
@@ -688,7 +747,7 @@ __global__ void __launch_bounds__(32 * NChains<KIND>::C) k_ord_resolve(PbPlanes 
             for (int q = 0; q < 3; q++) atomicAdd(&g_ord_counts[2 + q], (unsigned long long)n_why[q]);
             atomicAdd(&g_ord_counts[7], (unsigned long long)n_acc2);
             for (int q = 0; q < 3; q++) atomicAdd(&g_ord_counts[8 + q], (unsigned long long)cyc[q]);
-            atomicAdd(&g_ord_counts[11], (unsigned long long)((nblk + 31) / 32));
+            atomicAdd(&g_ord_counts[11], (unsigned long long)n_gen);
             atomicMax(&g_ord_counts[12], (unsigned long long)(clock64() - t_begin));
             if (KIND == KIND_CENTERED) {
                 for (int q = 0; q < 3; q++) atomicAdd(&g_ord_chain[chain][q], (unsigned long long)cyc[q]);
@@ -717,8 +776,10 @@ struct Scratch {
     OrdRec *rec0, *rec1;
     uint2 *list;
     unsigned int *list_count; // [0] work list of summary2, [1] dump slots
+    OrdRec *grec;
     Dump dump;
 };
+size_t group_rows(size_t total_blocks) { return total_blocks * 7 / 32 + 4096; } // + nseg * (C + 1), nseg <= 2 * 64
 size_t dump_slots(size_t total_blocks) { return total_blocks / 4 + 1024; }
 Scratch carve(void *d_scratch, size_t total_blocks) {
     Scratch s;
@@ -727,7 +788,8 @@ Scratch carve(void *d_scratch, size_t total_blocks) {
     s.psum = (double *)p; p += total_blocks * 7 * sizeof(double);
     s.rec0 = (OrdRec *)p; p += total_blocks * 7 * sizeof(OrdRec);
     s.rec1 = (OrdRec *)p; p += total_blocks * 7 * sizeof(OrdRec);
-    s.list = (uint2 *)p; p += total_blocks * sizeof(uint2);
+    s.grec = (OrdRec *)p; p += group_rows(total_blocks) * sizeof(OrdRec);
+    s.list = (uint2 *)p; p += total_blocks * 7 * sizeof(uint2);
     s.list_count = (unsigned int *)p;
     s.dump.count = s.list_count + 1;
     s.dump.cap = (unsigned int)dump_slots(total_blocks);
@@ -754,9 +816,11 @@ void launch_pass(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t
           k_ord_summary<KIND, W><<<grid, OS_THREADS, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, sc.psum, sc.rec0, sc.list_count, sc.list, sc.dump); }
         { PbProfScope p("k_ord_summary2", st, false);
           k_ord_summary2<KIND, W><<<148 * 4, OS_THREADS, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, sc.psum, sc.rec0, sc.rec1, sc.list_count, sc.list, sc.dump); }
+        { PbProfScope p("k_ord_group", st, false);
+          k_ord_group<KIND, W><<<dim3((blk_cap + 31) / 32, nseg), 32 * C, 0, st>>>(d_segs, sc.rec0, sc.grec); }
     }
     { PbProfScope p(KIND == KIND_MEAN ? "k_ord_resolve_mean" : "k_ord_resolve_centered", st, !speculative);
-      k_ord_resolve<KIND, W><<<nseg, 32 * C, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, sc.rec0, sc.rec1, sc.dump.terms, speculative); }
+      k_ord_resolve<KIND, W><<<nseg, 32 * C, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, sc.rec0, sc.rec1, sc.grec, sc.dump.terms, speculative); }
     PB_CUDA_OK(cudaGetLastError());
 }
 
@@ -781,8 +845,8 @@ void pb_ordered_chain_debug(unsigned long long out[35], bool reset) {
 uint32_t pb_ordered_blocks(uint32_t n) { return (n + OB - 1) / OB; }
 
 size_t pb_ordered_scratch_bytes(size_t total_blocks) {
-    return dump_slots(total_blocks) * OB * sizeof(double) +
-           total_blocks * (7 * (sizeof(double) + 2 * sizeof(OrdRec)) + sizeof(uint2)) + 256;
+    return dump_slots(total_blocks) * OB * sizeof(double) + group_rows(total_blocks) * sizeof(OrdRec) +
+           total_blocks * 7 * (sizeof(double) + 2 * sizeof(OrdRec) + sizeof(uint2)) + 256;
 }
 
 void pb_launch_pass_mean(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t max_n,
