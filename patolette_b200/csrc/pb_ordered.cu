@@ -29,6 +29,8 @@
 //   sequential loop computes (every rounding used the right grid), everything else is the loop itself.
 //
 // Small clusters skip S1-S3 and run S4 in replay-only mode (one launch).
+#include <stdlib.h>
+
 #include "pb_common.cuh"
 #include "pb_kernels.h"
 #include "pb_prof.h"
@@ -184,11 +186,26 @@ __global__ void __launch_bounds__(32) k_ord_prefix(const PbSeg *__restrict__ seg
 }
 
 // ---- S3: block summaries with per-element binade prediction ------------------------------------
-constexpr int OS_THREADS = 64; // 8 consecutive elements per thread, two warps per block
-#ifndef PB_OS_MINB
-#define PB_OS_MINB 8 // minimum resident CTAs per SM asked of ptxas for the summary kernels (register cap)
+// One WARP per block: 16 consecutive elements per lane.  (ncu on the first version - 64 threads x 8 elements,
+// everything unrolled - showed two thirds of the instructions in the per-thread fixed part (span set-up and
+// the in-order composition) and 30 % of the stall samples on instruction fetch: longer per-lane runs halve
+// the fixed share, rolled element loops keep the body inside the instruction cache, and a warp needs no
+// shared memory or CTA barrier to compose its block.)
+constexpr int OS_WARPS = 2;                 // blocks per CTA
+constexpr int OS_THREADS = 32 * OS_WARPS;
+constexpr int OS_PER = OB / 32;             // consecutive elements per lane
+constexpr int OS_STRIDE = OS_PER + 1;       // padded lane stride of the staged planes (doubles)
+constexpr int OS_PLANE = 32 * OS_STRIDE;
+template <int KIND, int NC> __host__ __device__ constexpr bool summary_staged() { return KIND == 0 /* KIND_MEAN */ && NC != 1; }
+#ifndef PB_OS_UNROLL_MEAN
+#define PB_OS_UNROLL_MEAN 4 // small loop body: unrolled for load-level parallelism
 #endif
-constexpr int OS_PER = OB / OS_THREADS;
+#ifndef PB_OS_UNROLL_CEN
+#define PB_OS_UNROLL_CEN 1  // large loop body: rolled, it has to stay inside the instruction cache
+#endif
+#ifndef PB_OS_MINB
+#define PB_OS_MINB 8 // minimum resident CTAs per SM asked of ptxas for the summary kernel (register cap)
+#endif
 
 __device__ __forceinline__ PbSpan shfl_down_span(const PbSpan &v, int o) {
     PbSpan r;
@@ -205,14 +222,6 @@ __device__ __forceinline__ PbSpan shfl_up_span(const PbSpan &v, int o) {
     return r;
 }
 
-struct SumShared {
-    double wsum[7];          // warp 0's total (approximate prefix hand-over)
-    int emin[2][7], emax[2][7];
-    PbSpan2 span[7];         // warp 0's span
-    int flag[7];
-    int slot[7];             // term-dump slot of a chain whose record is F_REPLAY (-1: none)
-};
-
 // Blocks whose record is F_REPLAY are known before the resolve runs: their terms are written out here, in
 // parallel, so that the sequential replay is a coalesced 4 KB read + the dependent adds (no loads of the
 // pixel planes, no term arithmetic on the resolving warp's critical path).
@@ -222,52 +231,78 @@ struct Dump {
     unsigned int cap;
 };
 
-// The general element step, out of line: it is the rare path (threads whose predictions change level or
+// The general element step, out of line: it is the rare path (lanes whose predictions change level or
 // sign) and keeping it out of the main body keeps the common path's register footprint small.
 template <int NV>
 __device__ __noinline__ void run_push_slow(PbRun *r, double term, double approx, int eref) {
     pb_run_push<NV>(*r, term, approx, eref);
 }
 
-// Summarises block `blk` of segment `sg`.  NC = C: every live chain, one record each (NV = 1; blocks with a
-// parity-dependent step are left F_PENDING and returned as a bit mask).  NC = 1: the single chain `ch0`, for
-// both start parities (NV = 2, the work-list pass).  All threads of the CTA take part.
+// Summarises block `blk` of segment `sg`; called by a whole warp.  NC = C: every live chain, one record each
+// (NV = 1; chains with a parity-dependent step are left F_PENDING and returned as a bit mask).  NC = 1: the
+// single chain `ch0`, for both start parities (NV = 2, the work-list pass).
 template <int KIND, bool W, int NV, int NC>
 __device__ __forceinline__ unsigned summarise_block(const PbPlanes &P, const PbSeg &sg, uint32_t blk, int ch0, double m0,
                                                     double m1, double m2, const double *__restrict__ pstart,
-                                                    OrdRec *__restrict__ rec0, OrdRec *__restrict__ rec1, SumShared &sh,
-                                                    const Dump &dump) {
+                                                    OrdRec *__restrict__ rec0, OrdRec *__restrict__ rec1, const Dump &dump,
+                                                    double *stage /* this warp's [3 or 4][OS_PLANE] */) {
     constexpr int C = NChains<KIND>::C;
     constexpr int NOLEVEL = -(1 << 20);
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int OS_UNROLL = NC == 1 ? 4 : (KIND == KIND_MEAN ? PB_OS_UNROLL_MEAN : PB_OS_UNROLL_CEN);
     static_assert(NC == 1 || NC == C, "all chains or one");
     auto chain_of = [&](int slot) { return NC == 1 ? ch0 : slot; };
     auto live = [&](int slot) { return NC == 1 ? true : chain_live<KIND, W>(slot); };
-    auto terms = [&](size_t p, double *t) {
-        if (NC == 1) t[0] = term_one<KIND, W>(ch0, W ? P.w[p] : 1.0, P.c[0][p], P.c[1][p], P.c[2][p], m0, m1, m2);
-        else terms_all<KIND, W>(W ? P.w[p] : 1.0, P.c[0][p], P.c[1][p], P.c[2][p], m0, m1, m2, t);
-    };
     const uint32_t nblk = (sg.n + OB - 1) / OB;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t i0 = blk * OB + threadIdx.x * OS_PER; // this thread's consecutive elements
+    const int lane = threadIdx.x & 31;
+    const uint32_t i0 = blk * OB + lane * OS_PER; // this lane's consecutive elements
     const bool have = i0 < sg.n;
     const int mycnt = have ? min(OS_PER, (int)(sg.n - i0)) : 0;
-    if (threadIdx.x < NC) { sh.flag[threadIdx.x] = 0; sh.slot[threadIdx.x] = -1; }
-
-    // ---- phase 1: approximate running sum at the start of this thread's elements ------------------
+    // Mean pass (few operations per element): the block's planes go through shared memory - coalesced
+    // 256-byte reads (two L1 wavefronts per instruction), then every lane reads ITS 16 consecutive elements
+    // at stride 17 (conflict-free).  Straight from global memory every load instruction costs 32 wavefronts
+    // (one 128-byte line per lane) and the load/store unit becomes the bottleneck.  The centred pass hides
+    // that behind its arithmetic and measured slower with the extra staging step, so it reads directly.
+    constexpr bool STAGED = summary_staged<KIND, NC>();
+    const size_t p0 = (size_t)sg.lo + i0;
+    if (STAGED) {
+        const size_t b0 = (size_t)sg.lo + (size_t)blk * OB;
+        const uint32_t bcnt = min((uint32_t)OB, sg.n - blk * OB);
+        __syncwarp();
+#pragma unroll 4
+        for (int q = 0; q < OB / 32; q++) {
+            const uint32_t idx = q * 32 + lane;
+            if (idx < bcnt) {
+                const int at = (int)(idx >> 4) * OS_STRIDE + (int)(idx & 15);
+                stage[0 * OS_PLANE + at] = P.c[0][b0 + idx];
+                stage[1 * OS_PLANE + at] = P.c[1][b0 + idx];
+                stage[2 * OS_PLANE + at] = P.c[2][b0 + idx];
+                if (W) stage[3 * OS_PLANE + at] = P.w[b0 + idx];
+            }
+        }
+        __syncwarp();
+    }
+    const double *mine = stage + lane * OS_STRIDE;
+    auto terms = [&](int k, double *t) {
+        double w, c0, c1, c2;
+        if (STAGED) { w = W ? mine[3 * OS_PLANE + k] : 1.0; c0 = mine[k]; c1 = mine[OS_PLANE + k]; c2 = mine[2 * OS_PLANE + k]; }
+        else { const size_t p = p0 + k; w = W ? P.w[p] : 1.0; c0 = P.c[0][p]; c1 = P.c[1][p]; c2 = P.c[2][p]; }
+        if (NC == 1) t[0] = term_one<KIND, W>(ch0, w, c0, c1, c2, m0, m1, m2);
+        else terms_all<KIND, W>(w, c0, c1, c2, m0, m1, m2, t);
+    };
+    // ---- phase 1: approximate running sum at the start of this lane's elements ---------------------
     double tstart[NC];
     {
         double tl[NC];
 #pragma unroll
         for (int c = 0; c < NC; c++) tl[c] = 0.0;
+#pragma unroll OS_UNROLL
+        for (int k = 0; k < mycnt; k++) {
+            double t[C];
+            terms(k, t);
 #pragma unroll
-        for (int k = 0; k < OS_PER; k++) {
-            if (k < mycnt) {
-                double t[C];
-                terms((size_t)sg.lo + i0 + k, t);
-#pragma unroll
-                for (int c = 0; c < NC; c++)
-                    if (live(c)) tl[c] += t[c];
-            }
+            for (int c = 0; c < NC; c++)
+                if (live(c)) tl[c] += t[c];
         }
 #pragma unroll
         for (int c = 0; c < NC; c++) {
@@ -276,21 +311,18 @@ __device__ __forceinline__ unsigned summarise_block(const PbPlanes &P, const PbS
             double incl = tl[c];
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                const double v = __shfl_up_sync(0xffffffffu, incl, o);
+                const double v = __shfl_up_sync(FULL, incl, o);
                 if (lane >= o) incl += v;
             }
-            if (warp == 0 && lane == 31) sh.wsum[c] = incl;
-            tstart[c] = incl - tl[c];
+            tstart[c] = pstart[chain_of(c)] + (incl - tl[c]);
         }
-        __syncthreads();
-#pragma unroll
-        for (int c = 0; c < NC; c++)
-            if (live(c)) tstart[c] += pstart[chain_of(c)] + (warp ? sh.wsum[c] : 0.0);
     }
     // ---- phase 2: predicted binade of every partial sum (start states included) -> range over the block;
-    //      at the same time the cheap summary, valid if this thread's predictions all sit on one level:
-    //      it works in the ulp of the thread's own level, the block's unit is not needed yet ----------------
-    int tlevel[NC]; // the thread's (absolute) level if uniform in binade and sign, else NOLEVEL
+    //      at the same time the cheap summary, valid if this lane's predictions all sit on one level:
+    //      it works in the ulp of the lane's own level, the block's unit is not needed yet ------------------
+    int tlevel[NC]; // the lane's (absolute) level if uniform in binade and sign, else NOLEVEL
+    int eref[NC];   // lowest predicted binade of the block
+    bool usable[NC];
     PbUni uni[NC];
     {
         int emin[NC], emax[NC];
@@ -306,49 +338,40 @@ __device__ __forceinline__ unsigned summarise_block(const PbPlanes &P, const PbS
             pb_uni_begin(uni[c]);
             uscale[c] = pb_eref_ok(e) ? pb_pow2(52 - e) : 0.0;
         }
+#pragma unroll OS_UNROLL
+        for (int k = 0; k < mycnt; k++) {
+            double t[C];
+            terms(k, t);
 #pragma unroll
-        for (int k = 0; k < OS_PER; k++) {
-            if (k < mycnt) {
-                double t[C];
-                terms((size_t)sg.lo + i0 + k, t);
-#pragma unroll
-                for (int c = 0; c < NC; c++) {
-                    if (!live(c)) continue;
-                    run[c] += t[c];
-                    const int e = pb_exponent_of(run[c]);
-                    emin[c] = min(emin[c], e);
-                    emax[c] = max(emax[c], e);
-                    flip[c] |= (run[c] < 0) != (tstart[c] < 0);
-                    pb_uni_push(uni[c], t[c], uscale[c]);
-                }
+            for (int c = 0; c < NC; c++) {
+                if (!live(c)) continue;
+                run[c] += t[c];
+                const int e = pb_exponent_of(run[c]);
+                emin[c] = min(emin[c], e);
+                emax[c] = max(emax[c], e);
+                flip[c] |= (run[c] < 0) != (tstart[c] < 0);
+                pb_uni_push(uni[c], t[c], uscale[c]);
             }
         }
 #pragma unroll
         for (int c = 0; c < NC; c++) {
             tlevel[c] = (have && emin[c] == emax[c] && !flip[c]) ? emin[c] : NOLEVEL;
+            eref[c] = 0;
+            usable[c] = false;
             if (!live(c)) continue;
-#pragma unroll
-            for (int o = 16; o; o >>= 1) {
-                emin[c] = min(emin[c], __shfl_xor_sync(0xffffffffu, emin[c], o));
-                emax[c] = max(emax[c], __shfl_xor_sync(0xffffffffu, emax[c], o));
-            }
-            if (lane == 0) { sh.emin[warp][c] = emin[c]; sh.emax[warp][c] = emax[c]; }
+            const int lo = __reduce_min_sync(FULL, emin[c]), hi = __reduce_max_sync(FULL, emax[c]);
+            // zero / subnormal / non-finite predictions, or too wide a range: replay
+            usable[c] = pb_eref_ok(lo) && pb_eref_ok(hi) && hi - lo <= PB_SPAN_MAX_LEVEL;
+            if (usable[c]) eref[c] = lo;
         }
-        __syncthreads();
     }
     // ---- phase 3: spans in units of the block's lowest binade -----------------------------------------
-    int eref[NC];
-    bool usable[NC], slow[NC];
+    bool slow[NC];
     PbRun run_st[NC];
     bool any_slow = false;
 #pragma unroll
     for (int c = 0; c < NC; c++) {
-        const int lo = live(c) ? min(sh.emin[0][c], sh.emin[1][c]) : 0, hi = live(c) ? max(sh.emax[0][c], sh.emax[1][c]) : 0;
-        eref[c] = lo;
-        // zero / subnormal / non-finite predictions, or too wide a range: replay
-        usable[c] = live(c) && pb_eref_ok(lo) && pb_eref_ok(hi) && hi - lo <= PB_SPAN_MAX_LEVEL;
-        if (!usable[c]) eref[c] = 0;
-        // a thread whose predictions sit on one level is a plain translation for BOTH start parities unless
+        // a lane whose predictions sit on one level is a plain translation for BOTH start parities unless
         // it holds a tie on the lowest level; only then (NV = 2) it is redone by the general path
         bool fast = usable[c] && tlevel[c] != NOLEVEL;
         if (fast) {
@@ -359,14 +382,14 @@ __device__ __forceinline__ unsigned summarise_block(const PbPlanes &P, const PbS
         slow[c] = usable[c] && have && !fast;
         any_slow |= slow[c];
     }
-    if (any_slow) { // the general path, element by element, for the chains of this thread that need it
+    if (any_slow) { // the general path, element by element, for the chains of this lane that need it
         double run[NC];
 #pragma unroll
         for (int c = 0; c < NC; c++) run[c] = tstart[c];
 #pragma unroll 1
         for (int k = 0; k < mycnt; k++) {
             double t[C];
-            terms((size_t)sg.lo + i0 + k, t);
+            terms(k, t);
 #pragma unroll
             for (int c = 0; c < NC; c++) {
                 if (!live(c)) continue;
@@ -375,84 +398,78 @@ __device__ __forceinline__ unsigned summarise_block(const PbPlanes &P, const PbS
             }
         }
     }
-    // in-order composition over the warp (lane i absorbs lane i + o), all chains interleaved
-    PbSpan2 v[NC];
+    __syncwarp();
+    // in-order composition over the warp (lane i absorbs lane i + o); lane 0 ends up with the block
+    unsigned pending = 0;
+    int slot[NC];
 #pragma unroll
     for (int c = 0; c < NC; c++) {
-        v[c] = pb_span2_identity();
+        slot[c] = -1;
         if (!live(c)) continue;
+        PbSpan2 v = pb_span2_identity();
+        unsigned f = 0;
         if (usable[c] && have) {
-            v[c] = pb_run_span<NV>(run_st[c]);
-            const int f = (run_st[c].bad ? 1 : 0) | (run_st[c].sensitive ? 2 : 0);
-            if (f) atomicOr(&sh.flag[c], f);
+            v = pb_run_span<NV>(run_st[c]);
+            f = (run_st[c].bad ? 1u : 0u) | (run_st[c].sensitive ? 2u : 0u);
         }
+        f = __reduce_or_sync(FULL, f);
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             PbSpan2 r;
-            r.p[0] = shfl_down_span(v[c].p[0], o);
-            if (NV == 2) r.p[1] = shfl_down_span(v[c].p[1], o);
+            r.p[0] = shfl_down_span(v.p[0], o);
+            if (NV == 2) r.p[1] = shfl_down_span(v.p[1], o);
             else r.p[1] = r.p[0];
             if ((lane & (2 * o - 1)) == 0) {
-                if (NV == 2) v[c] = pb_span2_cat(v[c], r);
-                else { v[c].p[0] = pb_span_cat(v[c].p[0], r.p[0]); v[c].p[1] = v[c].p[0]; }
+                if (NV == 2) v = pb_span2_cat(v, r);
+                else { v.p[0] = pb_span_cat(v.p[0], r.p[0]); v.p[1] = v.p[0]; }
             }
         }
-        if (warp == 0 && lane == 0) sh.span[c] = v[c];
-    }
-    __syncthreads();
-    unsigned pending = 0;
-    if (warp == 1 && lane == 0) {
-#pragma unroll
-        for (int c = 0; c < NC; c++) {
-            if (!live(c)) continue;
-            PbSpan2 w;
-            if (NV == 2) w = pb_span2_cat(sh.span[c], v[c]);
-            else { w.p[0] = pb_span_cat(sh.span[c].p[0], v[c].p[0]); w.p[1] = w.p[0]; }
-            const int f = sh.flag[c];
-            int flag;
-            if (!usable[c] || (f & 1)) flag = F_REPLAY;
-            else if (NV == 1) flag = (f & 2) ? F_PENDING : F_OK;
-            // a parity-dependent block whose start state sits above its lowest binade (enforced by its own
-            // start constraint) only ever sees parity 0: variant 0 of the two-parity composition is a plain record
-            else flag = pb_exponent_of(pstart[chain_of(c)]) - eref[c] < 1 ? F_SENSITIVE : F_OK;
+        int flag;
+        if (!usable[c] || (f & 1u)) flag = F_REPLAY;
+        else if (NV == 1) flag = (f & 2u) ? F_PENDING : F_OK;
+        // a parity-dependent block whose start state sits above its lowest binade (enforced by its own
+        // start constraint) only ever sees parity 0: variant 0 of the two-parity composition is a plain record
+        else flag = pb_exponent_of(pstart[chain_of(c)]) - eref[c] < 1 ? F_SENSITIVE : F_OK;
+        if (lane == 0) {
             // contradictory predictions (empty interval): never applicable.  A two-parity record stays
             // usable if one parity is valid; the resolve checks the interval of the parity it needs.
-            if (flag == F_OK && !pb_span_valid(w.p[0])) flag = F_REPLAY;
-            if (flag == F_SENSITIVE && !pb_span_valid(w.p[0]) && !pb_span_valid(w.p[1])) flag = F_REPLAY;
+            if (flag == F_OK && !pb_span_valid(v.p[0])) flag = F_REPLAY;
+            if (flag == F_SENSITIVE && !pb_span_valid(v.p[0]) && !pb_span_valid(v.p[1])) flag = F_REPLAY;
             const size_t row = rec_row(sg, C, chain_of(c), nblk, blk);
             OrdRec o0;
-            o0.sum = w.p[0].sum; o0.lo = w.p[0].lo; o0.hi = w.p[0].hi; o0.eref = eref[c]; o0.flag = flag;
+            o0.sum = v.p[0].sum; o0.lo = v.p[0].lo; o0.hi = v.p[0].hi; o0.eref = eref[c]; o0.flag = flag;
             if (flag == F_REPLAY) { // the record carries the dump slot instead of a translation
-                const unsigned int slot = atomicAdd(dump.count, 1u);
-                o0.sum = slot < dump.cap ? (long long)slot : -1LL;
-                sh.slot[c] = (int)o0.sum;
+                const unsigned int sl = atomicAdd(dump.count, 1u);
+                o0.sum = sl < dump.cap ? (long long)sl : -1LL;
+                slot[c] = (int)o0.sum;
             }
             rec0[row] = o0;
             if (NV == 2) {
                 OrdRec o1;
-                o1.sum = w.p[1].sum; o1.lo = w.p[1].lo; o1.hi = w.p[1].hi; o1.eref = eref[c]; o1.flag = flag;
+                o1.sum = v.p[1].sum; o1.lo = v.p[1].lo; o1.hi = v.p[1].hi; o1.eref = eref[c]; o1.flag = flag;
                 rec1[row] = o1;
             }
-            if (flag == F_PENDING) pending |= 1u << c;
         }
+        flag = __shfl_sync(FULL, flag, 0);
+        slot[c] = __shfl_sync(FULL, slot[c], 0);
+        if (flag == F_PENDING) pending |= 1u << c;
     }
-    __syncthreads();
     {
         bool any = false;
 #pragma unroll
-        for (int c = 0; c < NC; c++) any |= sh.slot[c] >= 0;
-        if (any && have) { // CTA-uniform `any`: write this thread's terms of the dumped chains
+        for (int c = 0; c < NC; c++) any |= slot[c] >= 0;
+        if (any) { // warp-uniform: write this lane's terms of the dumped chains
 #pragma unroll 1
             for (int k = 0; k < mycnt; k++) {
                 double t[C];
-                terms((size_t)sg.lo + i0 + k, t);
+                terms(k, t);
 #pragma unroll
                 for (int c = 0; c < NC; c++)
-                    if (sh.slot[c] >= 0) dump.terms[(size_t)sh.slot[c] * OB + threadIdx.x * OS_PER + k] = t[c];
+                    if (slot[c] >= 0) dump.terms[(size_t)slot[c] * OB + lane * OS_PER + k] = t[c];
             }
         }
     }
-    return pending; // meaningful on (warp 1, lane 0): chains left F_PENDING
+    return pending; // warp-uniform: chains left F_PENDING
 }
 
 template <int KIND, bool W>
@@ -462,20 +479,21 @@ __global__ void __launch_bounds__(OS_THREADS, PB_OS_MINB) k_ord_summary(PbPlanes
                                                             unsigned int *__restrict__ list_count,
                                                             uint2 *__restrict__ list, Dump dump) {
     constexpr int C = NChains<KIND>::C;
-    __shared__ SumShared sh;
+    __shared__ double stage[OS_WARPS][summary_staged<KIND, C>() ? (W ? 4 : 3) * OS_PLANE : 1];
     const int seg = blockIdx.y;
     const PbSeg sg = segs[seg];
-    if (blockIdx.x * OB >= sg.n) return;
+    const uint32_t blk = blockIdx.x * OS_WARPS + (threadIdx.x >> 5);
+    if ((size_t)blk * OB >= sg.n) return; // warp-uniform
     const PbPlanes &P = sg.buf ? b1 : b0;
     double m0 = 0, m1 = 0, m2 = 0;
     if (KIND == KIND_CENTERED) { m0 = stats[seg].mean[0]; m1 = stats[seg].mean[1]; m2 = stats[seg].mean[2]; }
-    const unsigned pending = summarise_block<KIND, W, 1, C>(P, sg, blockIdx.x, 0, m0, m1, m2,
-                                                            psum + ((size_t)sg.bbase + blockIdx.x) * C, rec0, nullptr, sh, dump);
-    if (threadIdx.x == 32 && pending) { // one work item per (block, chain): block index < 2^28
+    const unsigned pending = summarise_block<KIND, W, 1, C>(P, sg, blk, 0, m0, m1, m2, psum + ((size_t)sg.bbase + blk) * C,
+                                                            rec0, nullptr, dump, stage[threadIdx.x >> 5]);
+    if ((threadIdx.x & 31) == 0 && pending) { // one work item per (block, chain): block index < 2^28
         const unsigned int at = atomicAdd(list_count, (unsigned)__popc(pending));
         unsigned int k = 0;
         for (int c = 0; c < C; c++)
-            if (pending >> c & 1u) list[at + k++] = make_uint2((unsigned)seg, blockIdx.x | ((unsigned)c << 28));
+            if (pending >> c & 1u) list[at + k++] = make_uint2((unsigned)seg, blk | ((unsigned)c << 28));
     }
 }
 
@@ -488,8 +506,9 @@ __global__ void __launch_bounds__(OS_THREADS) k_ord_summary2(PbPlanes b0, PbPlan
                                                              const unsigned int *__restrict__ list_count,
                                                              const uint2 *__restrict__ list, Dump dump) {
     constexpr int C = NChains<KIND>::C;
-    __shared__ SumShared sh;
-    for (unsigned int item = blockIdx.x; item < *list_count; item += gridDim.x) { // persistent CTAs over the work list
+    __shared__ double stage[OS_WARPS][summary_staged<KIND, 1>() ? (W ? 4 : 3) * OS_PLANE : 1];
+    const unsigned int nitem = *list_count, stride = gridDim.x * OS_WARPS;
+    for (unsigned int item = blockIdx.x * OS_WARPS + (threadIdx.x >> 5); item < nitem; item += stride) { // persistent warps
         const int seg = (int)list[item].x;
         const uint32_t blk = list[item].y & 0x0fffffffu;
         const int chain = (int)(list[item].y >> 28);
@@ -497,8 +516,8 @@ __global__ void __launch_bounds__(OS_THREADS) k_ord_summary2(PbPlanes b0, PbPlan
         const PbPlanes &P = sg.buf ? b1 : b0;
         double m0 = 0, m1 = 0, m2 = 0;
         if (KIND == KIND_CENTERED) { m0 = stats[seg].mean[0]; m1 = stats[seg].mean[1]; m2 = stats[seg].mean[2]; }
-        __syncthreads(); // sh is reused across items
-        summarise_block<KIND, W, 2, 1>(P, sg, blk, chain, m0, m1, m2, psum + ((size_t)sg.bbase + blk) * C, rec0, rec1, sh, dump);
+        summarise_block<KIND, W, 2, 1>(P, sg, blk, chain, m0, m1, m2, psum + ((size_t)sg.bbase + blk) * C, rec0, rec1, dump,
+                                       stage[threadIdx.x >> 5]);
     }
 }
 
@@ -796,6 +815,18 @@ Scratch carve(void *d_scratch, size_t total_blocks) {
     return s;
 }
 
+// Unused dynamic shared memory that caps the resident CTAs of the summary kernel: every lane streams its
+// own 128-byte line per plane, so the L1 working set is 12-16 KB per warp and more resident warps than L1
+// can hold turn the second sweep over the block into L2 traffic.
+size_t summary_pad_smem(int kind) {
+    static int pad[2] = {-1, -1};
+    if (pad[kind] < 0) {
+        const char *e = getenv(kind == KIND_MEAN ? "PB200_SUMMARY_PAD_MEAN" : "PB200_SUMMARY_PAD_CENTERED");
+        pad[kind] = e ? atoi(e) : 0;
+    }
+    return (size_t)pad[kind];
+}
+
 template <int KIND, bool W>
 void launch_pass(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t max_n, uint32_t total_blocks,
                  PbStats *d_stats, void *d_scratch, size_t scratch_bytes, cudaStream_t st) {
@@ -806,14 +837,14 @@ void launch_pass(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t
     Scratch sc{};
     if (speculative) {
         sc = carve(d_scratch, total_blocks);
-        dim3 grid(blk_cap, nseg);
+        dim3 grid(blk_cap, nseg), sgrid((blk_cap + OS_WARPS - 1) / OS_WARPS, nseg);
         { PbProfScope p(KIND == KIND_MEAN ? "k_ord_blocksum_mean" : "k_ord_blocksum_centered", st, false);
           k_ord_blocksum<KIND, W><<<grid, OB_THREADS, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, sc.psum); }
         { PbProfScope p("k_ord_prefix", st, false);
           k_ord_prefix<C><<<dim3(chain_live<KIND, W>(0) ? C : C - 1, nseg), 32, 0, st>>>(d_segs, sc.psum, chain_live<KIND, W>(0) ? 0 : 1); }
         PB_CUDA_OK(cudaMemsetAsync(sc.list_count, 0, 2 * sizeof(unsigned int), st));
         { PbProfScope p(KIND == KIND_MEAN ? "k_ord_summary_mean" : "k_ord_summary_centered", st);
-          k_ord_summary<KIND, W><<<grid, OS_THREADS, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, sc.psum, sc.rec0, sc.list_count, sc.list, sc.dump); }
+          k_ord_summary<KIND, W><<<sgrid, OS_THREADS, summary_pad_smem(KIND), st>>>(bufs[0], bufs[1], d_segs, d_stats, sc.psum, sc.rec0, sc.list_count, sc.list, sc.dump); }
         { PbProfScope p("k_ord_summary2", st, false);
           k_ord_summary2<KIND, W><<<148 * 4, OS_THREADS, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, sc.psum, sc.rec0, sc.rec1, sc.list_count, sc.list, sc.dump); }
         { PbProfScope p("k_ord_group", st, false);

@@ -1,5 +1,5 @@
 // CPU check of patolette_b200/csrc/pb_span.h: the block-summary arithmetic of the ordered sums,
-// emulated with the kernel's tiling (blocks of 512 elements, 8 consecutive elements per thread,
+// emulated with the kernel's tiling (blocks of 512 elements, 16 consecutive elements per lane,
 // in-order tree composition), against the literal sequential loop.
 //
 //   g++ -O2 -ffp-contract=off -std=c++17 -I patolette_b200/csrc tests/native/test_span.cpp -o /tmp/test_span
@@ -17,7 +17,7 @@
 
 #include "pb_span.h"
 
-static const int OB = 512, PER = 8, THREADS = OB / PER;
+static const int OB = 512, PER = 16, THREADS = OB / PER;
 
 struct Stats {
     long blocks = 0, accepted = 0, wrong = 0, sensitive = 0, bad = 0, assoc_fail = 0, fast = 0, fast_mismatch = 0;
