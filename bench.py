@@ -261,16 +261,47 @@ def run_ours(args):
     peak, peak_src = measured_peaks()
     kernels = sorted(prof.items(), key=lambda kv: -kv[1]["ms"])
     top_name, top = kernels[0]
+    # Algorithmic bytes of the resolve kernels = what the sequential walk must read: one 32-byte record per
+    # (block, chain) it walks + the 4 KB of terms of every block it replays.  The pixel
+    # planes are attributed to the summary kernels, which are the ones that stream them.
+    resolve_bytes = (ord_acc + ord_rep) * 32.0 + ord_rep * 4096.0
+    resolve_ms = sum(v["ms"] for k, v in prof.items() if k.startswith("k_ord_resolve"))
+    for k, v in prof.items():
+        if k.startswith("k_ord_resolve") and resolve_ms > 0:
+            v["bytes"] = resolve_bytes * v["ms"] / resolve_ms
     gbs = top["bytes"] / (top["ms"] * 1e-3) / 1e9 if top["ms"] > 0 else 0.0
+    ncu = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_summary.json")) as f:
+            ncu = json.load(f)
+    except Exception:
+        pass
+
+    def stage_roofline(names, bytes_per_step):
+        ms = sum(v["ms"] for k, v in prof.items() if any(k.startswith(nm) for nm in names))
+        g = bytes_per_step / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        return {"kernels": names, "ms_per_step": round(ms, 3), "algorithmic_bytes_per_step": bytes_per_step,
+                "achieved": round(g, 1), "unit": "GB/s", "frac": round(g / peak, 4)}
+
+    pass_bytes = sum(v["bytes"] for k, v in prof.items() if k.startswith("k_ord_summary_"))  # 24|32 B per pixel-visit per pass
     roofline = {"bound": "hbm", "kernel": top_name, "achieved": gbs, "peak": peak, "unit": "GB/s",
-                "frac": gbs / peak, "traffic": None, "peak_source": peak_src,
+                "frac": gbs / peak, "traffic": ncu.get(top_name, {}).get("dram_bytes_per_launch"),
+                "peak_source": peak_src,
                 "launches_per_step": top["launches"], "ms_per_step_in_kernel": top["ms"],
                 "algorithmic_bytes_per_step": top["bytes"],
-                "note": "ordered (bit-exact sequential) sums: latency-bound by design in round 1, see DESIGN.md",
+                "note": "the step has no single dominant HBM kernel: bit-exact ordered sums are instruction-/latency-bound "
+                        "(DESIGN.md sections 3-4); per-stage rooflines in `stages`",
                 "top_kernel_launch_ms": [round(x, 3) for x in top.get("each", [])],
+                "stages": {
+                    "covariance (ordered mean + centred passes: k_ord_*)": stage_roofline(["k_ord_"], pass_bytes),
+                    "assignment (k_nearest, f64 brute force: FP64-ALU bound, 9*K flop/px)": stage_roofline(["k_nearest"], 32.0 * n),
+                    "projection + bucket sort + partition (k_dots_minmax, k_buckets, k_tile_*, k_scatter)":
+                        stage_roofline(["k_dots_minmax", "k_buckets", "k_tile_", "k_scatter", "k_class_start"],
+                              sum(v["bytes"] for k, v in prof.items() if k in ("k_dots_minmax", "k_buckets", "k_scatter"))),
+                },
                 "kernels": {k: {"ms": round(v["ms"], 3), "launches": v["launches"],
                                 "GB/s": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] > 0 and v["bytes"] else None}
-                            for k, v in kernels[:12]}}
+                            for k, v in kernels[:14]}}
 
     if rank != 0:
         if dist is not None:
@@ -302,7 +333,7 @@ def run_ours(args):
                          "accepted_two_parity": int(cnt[7]),
                          "resolve_warp_Mcycles": {"scan_walk": round(int(cnt[8]) / 1e6, 2), "two_parity": round(int(cnt[9]) / 1e6, 2),
                                                   "replay": round(int(cnt[10]) / 1e6, 2), "slowest_warp": round(int(cnt[12]) / 1e6, 3)},
-                         "record_groups": int(cnt[11])},
+                         "records_walked_singly": int(cnt[11])},
     }
     if cpu_baseline is not None:
         line["cpu_baseline"] = cpu_baseline

@@ -32,15 +32,79 @@ namespace {
 // order, are ord[class_start[b] .. class_start[b+1]) (stable bucket sort, pb_scatter.cu).
 // One warp per (cluster, bucket): lanes gather a tile of members, chain lanes add.
 // ------------------------------------------------------------------------------------
-constexpr int BK_TILE = 128;           // members staged per step (4 per lane)
+constexpr int BK_TILE = 64;            // members per stage (2 per lane)
 constexpr int BK_STRIDE = BK_TILE + 2;
 constexpr int BK_WARPS = 4;
 constexpr int BK_PER = BK_TILE / 32;
+constexpr int BK_DEPTH = 4;            // stages in flight per warp
 
-// The chain lanes run ONE uniform loop `acc = acc + term[lane][e]`: every per-element term is formed by the
-// gathering lanes (in parallel) before it is staged, so the critical path per element is a shared-memory
-// broadcast read + one dependent DADD.  The gather of tile t+1 is issued into registers before the chain
-// over tile t starts, so its latency hides behind the chain.
+// The members of a bucket are gathered (random 8-byte reads of the planes, measured 135-157 cycles per
+// element when only one tile was in flight) through a ring of BK_DEPTH stages filled with cp.async: the
+// gathers of tile t + BK_DEPTH - 1 are issued before the chain over tile t starts, and the positions (`ord`)
+// they need were loaded one iteration earlier, so the only latency left on the warp's critical path is the
+// chain itself: a shared-memory broadcast read + one dependent DADD per element, ONE uniform loop
+// `acc += term[lane][e]` for all chain lanes (every term is formed by the gathering lanes, in parallel).
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+// Generic driver: NP planes gathered per member, `emit(e, raw)` turns the staged values of element e into
+// the NT term rows, chain lanes accumulate with `step(acc, term, lane)`.
+template <int NP, int NT, typename Planes, typename Emit, typename Step>
+__device__ __forceinline__ double bucket_chain(const uint32_t *__restrict__ ord, uint32_t beg, uint32_t end, Planes plane,
+                                               double (*raw)[NP][BK_TILE], double (*term)[BK_STRIDE], Emit emit, Step step,
+                                               int lane) {
+    double acc = 0.0;
+    if (beg >= end) return acc;
+    const uint32_t ntile = (end - beg + BK_TILE - 1) / BK_TILE;
+    uint32_t ordv[BK_PER]; // positions of the tile whose gathers are issued next
+    auto load_ord = [&](uint32_t t) {
+#pragma unroll
+        for (int q = 0; q < BK_PER; q++) {
+            const uint32_t i = beg + t * BK_TILE + q * 32 + lane;
+            ordv[q] = (t < ntile && i < end) ? ord[i] : 0xffffffffu;
+        }
+    };
+    auto issue = [&](uint32_t t) { // gathers of tile t into stage t % BK_DEPTH (always one commit per call)
+#pragma unroll
+        for (int q = 0; q < BK_PER; q++) {
+            if (ordv[q] != 0xffffffffu) {
+#pragma unroll
+                for (int j = 0; j < NP; j++) cp_async8(&raw[t % BK_DEPTH][j][q * 32 + lane], plane(j) + ordv[q]);
+            }
+        }
+        cp_async_commit();
+    };
+    for (uint32_t t = 0; t + 1 < BK_DEPTH; t++) { load_ord(t); issue(t); }
+    load_ord(BK_DEPTH - 1);
+    for (uint32_t t = 0; t < ntile; t++) {
+        const uint32_t cnt = min((uint32_t)BK_TILE, end - (beg + t * BK_TILE));
+        cp_async_wait<BK_DEPTH - 2>(); // tile t has landed (this lane's copies)
+        __syncwarp();                  // ... and everybody else's
+#pragma unroll
+        for (int q = 0; q < BK_PER; q++) {
+            const int e = q * 32 + lane;
+            double v[NP];
+#pragma unroll
+            for (int j = 0; j < NP; j++) v[j] = raw[t % BK_DEPTH][j][e];
+            emit(e, v, term);
+        }
+        __syncwarp();
+        issue(t + BK_DEPTH - 1);      // refills the stage consumed at iteration t - 1
+        load_ord(t + BK_DEPTH);
+        if (lane < NT) {
+            const double *vp = term[lane];
+#pragma unroll 8
+            for (uint32_t e = 0; e < cnt; e++) acc = step(acc, vp[e]);
+        }
+        __syncwarp();
+    }
+    cp_async_wait<0>();
+    return acc;
+}
+
 //   LQ (local.c:124-134): term 0 = w (bucket "size"), terms 1..3 = c_j * w.
 //     The reference accumulates the size as size_t += double (local.c:133), i.e.
 //     size = trunc((double)size + w) at every step.  Unweighted that is the member count (exact), and
@@ -52,64 +116,34 @@ __global__ void __launch_bounds__(BK_WARPS * 32) k_bucket_chains_lq(PbPlanes b0,
                                                                    const uint32_t *__restrict__ class_start,
                                                                    double *__restrict__ out) {
     constexpr int NT = WEIGHTED ? 4 : 3;
-    __shared__ double sm_all[BK_WARPS][NT][BK_STRIDE];
+    __shared__ double raw_all[BK_WARPS][BK_DEPTH][NT][BK_TILE];
+    __shared__ double term_all[BK_WARPS][NT][BK_STRIDE];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int gw = blockIdx.x * BK_WARPS + warp;
     if (gw >= nseg * PB_BUCKETS) return;
     const int seg = gw / PB_BUCKETS, b = gw % PB_BUCKETS;
-    double(*sm)[BK_STRIDE] = sm_all[warp];
     const PbSeg sg = segs[seg];
     const PbPlanes &P = sg.buf ? b1 : b0;
     const uint32_t *cs = class_start + (size_t)seg * (PB_BUCKETS + 1);
     const uint32_t beg = cs[b], end = cs[b + 1];
-    double acc = 0.0;
-    double g[BK_PER][NT];
-    auto gather = [&](uint32_t i0) {
-#pragma unroll
-        for (int q = 0; q < BK_PER; q++) {
-            const uint32_t i = i0 + q * 32 + lane;
-#pragma unroll
-            for (int t = 0; t < NT; t++) g[q][t] = 0.0;
-            if (i < end) {
-                const uint32_t p = ord[i];
-                if (WEIGHTED) {
-                    const double w = P.w[p];
-                    g[q][0] = w;
-                    g[q][1] = __dmul_rn(P.c[0][p], w);
-                    g[q][2] = __dmul_rn(P.c[1][p], w);
-                    g[q][3] = __dmul_rn(P.c[2][p], w);
-                } else {
-                    g[q][0] = P.c[0][p];
-                    g[q][1] = P.c[1][p];
-                    g[q][2] = P.c[2][p];
-                }
-            }
+    auto plane = [&](int j) -> const double * { return j < 3 ? P.c[j] : P.w; };
+    auto emit = [&](int e, const double *v, double (*term)[BK_STRIDE]) {
+        if (WEIGHTED) {
+            term[0][e] = v[3];
+            term[1][e] = __dmul_rn(v[0], v[3]);
+            term[2][e] = __dmul_rn(v[1], v[3]);
+            term[3][e] = __dmul_rn(v[2], v[3]);
+        } else {
+            term[0][e] = v[0];
+            term[1][e] = v[1];
+            term[2][e] = v[2];
         }
     };
-    if (beg < end) gather(beg);
-    for (uint32_t i0 = beg; i0 < end; i0 += BK_TILE) {
-        const uint32_t cnt = min((uint32_t)BK_TILE, end - i0);
-#pragma unroll
-        for (int q = 0; q < BK_PER; q++)
-#pragma unroll
-            for (int t = 0; t < NT; t++) sm[t][q * 32 + lane] = g[q][t];
-        __syncwarp();
-        if (i0 + BK_TILE < end) gather(i0 + BK_TILE); // in flight during the chain below
-        if (lane < NT) {
-            const double *vp = sm[lane];
-            if (WEIGHTED) {
-#pragma unroll 8
-                for (uint32_t e = 0; e < cnt; e++) {
-                    const double t = __dadd_rn(acc, vp[e]);
-                    acc = lane == 0 ? trunc(t) : t;
-                }
-            } else {
-#pragma unroll 16
-                for (uint32_t e = 0; e < cnt; e++) acc = __dadd_rn(acc, vp[e]);
-            }
-        }
-        __syncwarp();
-    }
+    auto step = [&](double acc, double t) {
+        const double r = __dadd_rn(acc, t);
+        return (WEIGHTED && lane == 0) ? trunc(r) : r;
+    };
+    const double acc = bucket_chain<NT, NT>(ord, beg, end, plane, raw_all[warp], term_all[warp], emit, step, lane);
     double *o = out + ((size_t)seg * PB_BUCKETS + b) * 4;
     if (WEIGHTED) {
         if (lane == 0) o[0] = __longlong_as_double((long long)(unsigned long long)acc);
@@ -126,55 +160,28 @@ __global__ void __launch_bounds__(BK_WARPS * 32) k_bucket_chains_gq(PbPlanes src
                                                                    const uint32_t *__restrict__ class_start,
                                                                    double *__restrict__ out) {
     constexpr int NT = 10;
-    constexpr int GT = 64, GPER = GT / 32, GSTRIDE = GT + 2; // smaller tile: 10 term rows per warp
-    __shared__ double sm_all[BK_WARPS][NT][GSTRIDE];
+    __shared__ double raw_all[BK_WARPS][BK_DEPTH][3][BK_TILE];
+    __shared__ double term_all[BK_WARPS][NT][BK_STRIDE];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * BK_WARPS + warp;
     if (b >= PB_BUCKETS) return;
-    double(*sm)[GSTRIDE] = sm_all[warp];
     const uint32_t beg = class_start[b], end = class_start[b + 1];
-    double acc = 0.0;
-    double g[GPER][3];
-    auto gather = [&](uint32_t i0) {
-#pragma unroll
-        for (int q = 0; q < GPER; q++) {
-            const uint32_t i = i0 + q * 32 + lane;
-            g[q][0] = g[q][1] = g[q][2] = 0.0;
-            if (i < end) {
-                const uint32_t p = ord[i];
-                g[q][0] = src.c[0][p];
-                g[q][1] = src.c[1][p];
-                g[q][2] = src.c[2][p];
-            }
-        }
+    auto plane = [&](int j) -> const double * { return src.c[j]; };
+    auto emit = [&](int e, const double *v, double (*term)[BK_STRIDE]) {
+        const double x = v[0], y = v[1], z = v[2];
+        term[0][e] = x;
+        term[1][e] = y;
+        term[2][e] = z;
+        term[3][e] = __dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z));
+        term[4][e] = __dmul_rn(x, x);
+        term[5][e] = __dmul_rn(x, y);
+        term[6][e] = __dmul_rn(y, y);
+        term[7][e] = __dmul_rn(x, z);
+        term[8][e] = __dmul_rn(y, z);
+        term[9][e] = __dmul_rn(z, z);
     };
-    if (beg < end) gather(beg);
-    for (uint32_t i0 = beg; i0 < end; i0 += GT) {
-        const uint32_t cnt = min((uint32_t)GT, end - i0);
-#pragma unroll
-        for (int q = 0; q < GPER; q++) {
-            const int e = q * 32 + lane;
-            const double x = g[q][0], y = g[q][1], z = g[q][2];
-            sm[0][e] = x;
-            sm[1][e] = y;
-            sm[2][e] = z;
-            sm[3][e] = __dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z));
-            sm[4][e] = __dmul_rn(x, x);
-            sm[5][e] = __dmul_rn(x, y);
-            sm[6][e] = __dmul_rn(y, y);
-            sm[7][e] = __dmul_rn(x, z);
-            sm[8][e] = __dmul_rn(y, z);
-            sm[9][e] = __dmul_rn(z, z);
-        }
-        __syncwarp();
-        if (i0 + GT < end) gather(i0 + GT);
-        if (lane < NT) {
-            const double *vp = sm[lane];
-#pragma unroll 16
-            for (uint32_t e = 0; e < cnt; e++) acc = __dadd_rn(acc, vp[e]);
-        }
-        __syncwarp();
-    }
+    auto step = [&](double acc, double t) { return __dadd_rn(acc, t); };
+    const double acc = bucket_chain<3, NT>(ord, beg, end, plane, raw_all[warp], term_all[warp], emit, step, lane);
     if (lane < 10) out[(size_t)b * 10 + lane] = acc;
 }
 

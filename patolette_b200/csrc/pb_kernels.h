@@ -33,6 +33,8 @@ size_t pb_ordered_scratch_bytes(size_t total_blocks);
 // {blocks accepted from summaries, blocks replayed sequentially} per chain since the last reset
 void pb_ordered_counts(unsigned long long out[16], bool reset);
 void pb_ordered_chain_debug(unsigned long long out[35], bool reset);
+// test knob: cap on the term-dump slots of a pass (-1 = default); blocks beyond it are replayed from the planes
+void pb_ordered_set_dump_cap(long long slots);
 void pb_launch_pass_mean(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t max_n,
                          uint32_t total_blocks, bool weighted, PbStats *d_stats, void *d_scratch,
                          size_t scratch_bytes, cudaStream_t st);

@@ -799,7 +799,12 @@ struct Scratch {
     Dump dump;
 };
 size_t group_rows(size_t total_blocks) { return total_blocks * 7 / 32 + 4096; } // + nseg * (C + 1), nseg <= 2 * 64
+long long g_dump_cap_override = -1; // debug/test knob (patolette_b200_set_option "dump_cap")
 size_t dump_slots(size_t total_blocks) { return total_blocks / 4 + 1024; }
+unsigned int dump_cap(size_t total_blocks) {
+    const size_t n = dump_slots(total_blocks);
+    return (unsigned int)(g_dump_cap_override >= 0 && (size_t)g_dump_cap_override < n ? (size_t)g_dump_cap_override : n);
+}
 Scratch carve(void *d_scratch, size_t total_blocks) {
     Scratch s;
     char *p = (char *)d_scratch;
@@ -811,7 +816,7 @@ Scratch carve(void *d_scratch, size_t total_blocks) {
     s.list = (uint2 *)p; p += total_blocks * 7 * sizeof(uint2);
     s.list_count = (unsigned int *)p;
     s.dump.count = s.list_count + 1;
-    s.dump.cap = (unsigned int)dump_slots(total_blocks);
+    s.dump.cap = dump_cap(total_blocks);
     return s;
 }
 
@@ -872,6 +877,8 @@ void pb_ordered_chain_debug(unsigned long long out[35], bool reset) {
         PB_CUDA_OK(cudaMemcpyToSymbol(g_ord_chain, z, sizeof z));
     }
 }
+
+void pb_ordered_set_dump_cap(long long slots) { g_dump_cap_override = slots; }
 
 uint32_t pb_ordered_blocks(uint32_t n) { return (n + OB - 1) / OB; }
 

@@ -27,6 +27,7 @@
 namespace {
 
 int g_device = 0;
+int g_overlap_override = -1; // patolette_b200_set_option "overlap": -1 default, 0 off, 1 on
 cudaStream_t g_user_stream = nullptr;
 bool g_use_user_stream = false;
 double g_timings[10] = {0};
@@ -226,6 +227,22 @@ struct Quantizer {
     DevArr<char> oscratch; // block sums + summaries of the speculative ordered sums
     PbPlanes orig{}, bufs[2]{};
 
+    // Second half-batch context.  The ordered-sum resolve of a batch is latency-bound (one warp per chain,
+    // a few dozen busy SMs) while the summaries, scatters and bucket chains are throughput work: a batch is
+    // therefore split into two halves on two streams, so that one half's resolve overlaps the other half's
+    // streaming kernels.  Half 0 uses the members above and `st`.
+    struct Half {
+        DevArr<uint32_t> tile_hist, cstart_b, cstart_s;
+        DevArr<double> bsums, axes;
+        DevArr<PbSeg> segs, children;
+        DevArr<PbStats> stats;
+        DevArr<PbSplit> split;
+        DevArr<char> oscratch;
+        cudaStream_t st = nullptr;
+        cudaEvent_t fork = nullptr;
+    } hx;
+    bool overlap = true;
+
     static constexpr int MAXB = 64; // clusters evaluated per batch (their 2 * MAXB children get stats)
     size_t max_blocks = 0;         // capacity of the packed ordered-sum block table
     size_t max_tiles = 0;          // capacity of the packed scatter tile table
@@ -268,8 +285,31 @@ struct Quantizer {
         lut.alloc(PB_BUCKETS);
         max_blocks = 2 * ((size_t)pb_ordered_blocks((uint32_t)N) + 2 * MAXB) + 64;
         oscratch.alloc(pb_ordered_scratch_bytes(max_blocks));
+        const char *e = getenv("PB200_OVERLAP");
+        overlap = !(e && e[0] == '0') && N >= (size_t)1 << 16;
+        if (g_overlap_override >= 0) overlap = g_overlap_override != 0;
+        if (overlap) {
+            hx.tile_hist.alloc(pb_scatter_table_words(max_tiles, MAXB, PB_BUCKETS));
+            hx.cstart_b.alloc(MAXB * (PB_BUCKETS + 1));
+            hx.cstart_s.alloc(MAXB * 17);
+            hx.bsums.alloc(MAXB * PB_BUCKETS * 10);
+            hx.axes.alloc(MAXB * 3);
+            hx.segs.alloc(MAXB);
+            hx.children.alloc(2 * MAXB);
+            hx.stats.alloc(2 * MAXB);
+            hx.split.alloc(MAXB);
+            hx.oscratch.alloc(pb_ordered_scratch_bytes(max_blocks));
+            // higher priority than the first half's stream: its CTAs are placed first, which staggers the two
+            // halves (one streams at full speed while the other is inside its latency-bound resolve)
+            int prio_least = 0, prio_greatest = 0;
+            PB_CUDA_OK(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+            PB_CUDA_OK(cudaStreamCreateWithPriority(&hx.st, cudaStreamNonBlocking, prio_greatest));
+            PB_CUDA_OK(cudaEventCreateWithFlags(&hx.fork, cudaEventDisableTiming));
+        }
     }
     ~Quantizer() {
+        if (hx.st) cudaStreamDestroy(hx.st);
+        if (hx.fork) cudaEventDestroy(hx.fork);
         if (st && own_stream) cudaStreamDestroy(st);
     }
     void sync() { PB_CUDA_OK(cudaStreamSynchronize(st)); }
@@ -388,66 +428,121 @@ struct Quantizer {
     // per-bucket sums, optimal cut, stable partition into the other ping-pong buffer, and the
     // mean / covariance / distortion of both children.  One host synchronisation per batch.
     void eval_split(HNode *const nodes[], HPair *const outs[], int count) {
-        PbSeg hsegs[MAXB];
-        double haxes[3 * MAXB];
-        int map[MAXB], nb = 0;
-        uint32_t max_n = 0, tb = 0, bb = 0;
-        double tot_n = 0;
+        struct Cand { int i; double axis[3]; };
+        Cand cand[MAXB];
+        int nc = 0;
         for (int i = 0; i < count; i++) {
             outs[i]->valid = false;
             if (nodes[i]->seg.n <= 1) continue; // local.c:187
-            double v[9], axis[3];
+            double v[9];
             fill_vcov(nodes[i]->st, v);
-            if (!pca_axis_from_vcov(v, axis)) continue; // local.c:193-196
-            hsegs[nb] = nodes[i]->seg;
-            hsegs[nb].tbase = tb;
-            hsegs[nb].bbase = bb;
-            tb += (uint32_t)pb_scatter_tiles(hsegs[nb].n);
-            bb += pb_ordered_blocks(hsegs[nb].n) + 1;
-            memcpy(&haxes[3 * nb], axis, sizeof axis);
-            max_n = std::max(max_n, nodes[i]->seg.n);
-            tot_n += nodes[i]->seg.n;
-            map[nb++] = i;
+            if (!pca_axis_from_vcov(v, cand[nc].axis)) continue; // local.c:193-196
+            cand[nc++].i = i;
         }
-        if (nb == 0) return;
-        h2d(segs.p, hsegs, nb);
-        h2d(axes.p, haxes, 3 * nb);
+        if (nc == 0) return;
+        // two half-batches (largest first, each to the lighter half); one when profiling per kernel
+        const int nhalf = (overlap && nc >= 2 && !pb_prof_enabled()) ? 2 : 1;
+        std::sort(cand, cand + nc, [&](const Cand &a, const Cand &b) { return nodes[a.i]->seg.n > nodes[b.i]->seg.n; });
+        struct HalfBatch {
+            PbSeg hsegs[MAXB];
+            double haxes[3 * MAXB];
+            int map[MAXB], nb = 0;
+            uint32_t max_n = 0, tb = 0, bb = 0;
+            double tot_n = 0;
+            PbSeg hch[2 * MAXB];
+            PbStats hst[2 * MAXB];
+        };
+        static thread_local HalfBatch hb[2];
+        for (int h = 0; h < 2; h++) { hb[h].nb = 0; hb[h].max_n = hb[h].tb = hb[h].bb = 0; hb[h].tot_n = 0; }
+        for (int c = 0; c < nc; c++) {
+            HalfBatch &B = hb[(nhalf == 2 && hb[1].tot_n < hb[0].tot_n) ? 1 : 0];
+            const HNode &nd = *nodes[cand[c].i];
+            PbSeg &sg = B.hsegs[B.nb];
+            sg = nd.seg;
+            sg.tbase = B.tb;
+            sg.bbase = B.bb;
+            B.tb += (uint32_t)pb_scatter_tiles(sg.n);
+            B.bb += pb_ordered_blocks(sg.n) + 1;
+            memcpy(&B.haxes[3 * B.nb], cand[c].axis, sizeof cand[c].axis);
+            B.max_n = std::max(B.max_n, sg.n);
+            B.tot_n += sg.n;
+            B.map[B.nb++] = cand[c].i;
+        }
+        struct Dev { // device scratch of a half
+            PbSeg *segs, *children; double *axes, *bsums; PbSplit *split; PbStats *stats;
+            uint32_t *tile_hist, *cstart_b, *cstart_s; char *oscratch; size_t oscratch_n; cudaStream_t st;
+        };
+        const Dev dev[2] = {
+            {segs.p, children.p, axes.p, bsums.p, split.p, stats.p, tile_hist.p, cstart_b.p, cstart_s.p, oscratch.p, oscratch.n, st},
+            {hx.segs.p, hx.children.p, hx.axes.p, hx.bsums.p, hx.split.p, hx.stats.p, hx.tile_hist.p, hx.cstart_b.p, hx.cstart_s.p,
+             hx.oscratch.p, hx.oscratch.n, hx.st}};
+        if (nhalf == 2) { // the second stream starts after everything already queued on the first
+            PB_CUDA_OK(cudaEventRecord(hx.fork, st));
+            PB_CUDA_OK(cudaStreamWaitEvent(hx.st, hx.fork, 0));
+        }
         const double bpp = weighted ? 32.0 : 24.0; // planar f64 payload per pixel
-        pb_prof_next_bytes(24.0 * tot_n);
-        pb_launch_dots_minmax(bufs, segs.p, nb, max_n, axes.p, split.p, sm_count, st);
-        pb_prof_next_bytes(26.0 * tot_n);
-        pb_launch_buckets(bufs, segs.p, nb, max_n, axes.p, split.p, bucket.p, sm_count, st);
-        pb_launch_class_rank(PB_CLS_BUCKET, PB_BUCKETS, segs.p, nb, max_n, max_tiles, bucket.p, split.p, lut.p, tile_hist.p,
-                             cstart_b.p, st);
-        pb_launch_scatter_ord(PB_CLS_BUCKET, PB_BUCKETS, segs.p, nb, max_n, bucket.p, split.p, lut.p, tile_hist.p,
-                              cstart_b.p, ord.p, st);
-        pb_prof_next_bytes((bpp + 4.0) * tot_n);
-        pb_launch_bucket_chains_lq(bufs, segs.p, nb, weighted, ord.p, cstart_b.p, bsums.p, st);
-        pb_launch_split_select(bsums.p, cstart_b.p, nb, split.p, st);
-        pb_launch_class_rank(PB_CLS_SPLIT, 2, segs.p, nb, max_n, max_tiles, bucket.p, split.p, lut.p, tile_hist.p, cstart_s.p,
-                             st);
         const PbPlanes swapped[2] = {bufs[1], bufs[0]};
-        pb_prof_next_bytes((2 * (bpp + 4.0) + 2.0) * tot_n);
-        pb_launch_scatter_payload(PB_CLS_SPLIT, 2, bufs, swapped, false, segs.p, nb, max_n, bucket.p, split.p,
-                                  lut.p, tile_hist.p, cstart_s.p, st);
-        pb_launch_make_children(segs.p, nb, split.p, children.p, st);
-        pb_prof_next_bytes(bpp * tot_n);
-        pb_launch_pass_mean(bufs, children.p, 2 * nb, max_n, (uint32_t)max_blocks, weighted, stats.p, oscratch.p,
-                            oscratch.n, st);
-        pb_prof_next_bytes(bpp * tot_n);
-        pb_launch_pass_centered(bufs, children.p, 2 * nb, max_n, (uint32_t)max_blocks, weighted, stats.p,
-                                oscratch.p, oscratch.n, st);
-        PbSeg hch[2 * MAXB];
-        PbStats hst[2 * MAXB];
-        d2h(hch, children.p, 2 * nb);
-        d2h(hst, stats.p, 2 * nb);
-        sync();
-        for (int b = 0; b < nb; b++) {
-            HPair *o = outs[map[b]];
-            o->valid = true;
-            o->l = HNode{hch[2 * b], hst[2 * b]};
-            o->r = HNode{hch[2 * b + 1], hst[2 * b + 1]};
+        // the launch sequence of split_cluster, step by step and alternating between the halves
+        auto step = [&](int k, const HalfBatch &B, const Dev &d) {
+            const int nb = B.nb;
+            const uint32_t max_n = B.max_n;
+            switch (k) {
+            case 0:
+                PB_CUDA_OK(cudaMemcpyAsync(d.segs, B.hsegs, nb * sizeof(PbSeg), cudaMemcpyHostToDevice, d.st));
+                PB_CUDA_OK(cudaMemcpyAsync(d.axes, B.haxes, 3 * nb * sizeof(double), cudaMemcpyHostToDevice, d.st));
+                pb_prof_next_bytes(24.0 * B.tot_n);
+                pb_launch_dots_minmax(bufs, d.segs, nb, max_n, d.axes, d.split, sm_count, d.st);
+                pb_prof_next_bytes(26.0 * B.tot_n);
+                pb_launch_buckets(bufs, d.segs, nb, max_n, d.axes, d.split, bucket.p, sm_count, d.st);
+                break;
+            case 1:
+                pb_launch_class_rank(PB_CLS_BUCKET, PB_BUCKETS, d.segs, nb, max_n, max_tiles, bucket.p, d.split, lut.p,
+                                     d.tile_hist, d.cstart_b, d.st);
+                pb_launch_scatter_ord(PB_CLS_BUCKET, PB_BUCKETS, d.segs, nb, max_n, bucket.p, d.split, lut.p, d.tile_hist,
+                                      d.cstart_b, ord.p, d.st);
+                break;
+            case 2:
+                pb_prof_next_bytes((bpp + 4.0) * B.tot_n);
+                pb_launch_bucket_chains_lq(bufs, d.segs, nb, weighted, ord.p, d.cstart_b, d.bsums, d.st);
+                pb_launch_split_select(d.bsums, d.cstart_b, nb, d.split, d.st);
+                break;
+            case 3:
+                pb_launch_class_rank(PB_CLS_SPLIT, 2, d.segs, nb, max_n, max_tiles, bucket.p, d.split, lut.p, d.tile_hist,
+                                     d.cstart_s, d.st);
+                pb_prof_next_bytes((2 * (bpp + 4.0) + 2.0) * B.tot_n);
+                pb_launch_scatter_payload(PB_CLS_SPLIT, 2, bufs, swapped, false, d.segs, nb, max_n, bucket.p, d.split,
+                                          lut.p, d.tile_hist, d.cstart_s, d.st);
+                pb_launch_make_children(d.segs, nb, d.split, d.children, d.st);
+                break;
+            case 4:
+                pb_prof_next_bytes(bpp * B.tot_n);
+                pb_launch_pass_mean(bufs, d.children, 2 * nb, max_n, (uint32_t)max_blocks, weighted, d.stats, d.oscratch,
+                                    d.oscratch_n, d.st);
+                break;
+            case 5:
+                pb_prof_next_bytes(bpp * B.tot_n);
+                pb_launch_pass_centered(bufs, d.children, 2 * nb, max_n, (uint32_t)max_blocks, weighted, d.stats,
+                                        d.oscratch, d.oscratch_n, d.st);
+                break;
+            }
+        };
+        for (int k = 0; k < 6; k++)
+            for (int h = 0; h < nhalf; h++)
+                if (hb[h].nb) step(k, hb[h], dev[h]);
+        for (int h = 0; h < nhalf; h++) { // pageable destinations: each copy returns when its stream got there
+            if (!hb[h].nb) continue;
+            PB_CUDA_OK(cudaMemcpyAsync(hb[h].hch, dev[h].children, 2 * hb[h].nb * sizeof(PbSeg), cudaMemcpyDeviceToHost, dev[h].st));
+            PB_CUDA_OK(cudaMemcpyAsync(hb[h].hst, dev[h].stats, 2 * hb[h].nb * sizeof(PbStats), cudaMemcpyDeviceToHost, dev[h].st));
         }
+        for (int h = 0; h < nhalf; h++)
+            if (hb[h].nb) PB_CUDA_OK(cudaStreamSynchronize(dev[h].st));
+        for (int h = 0; h < nhalf; h++)
+            for (int b = 0; b < hb[h].nb; b++) {
+                HPair *o = outs[hb[h].map[b]];
+                o->valid = true;
+                o->l = HNode{hb[h].hch[2 * b], hb[h].hst[2 * b]};
+                o->r = HNode{hb[h].hch[2 * b + 1], hb[h].hst[2 * b + 1]};
+            }
     }
 
     static double benefit_of(const HNode &c, const HPair &ch) { // local.c:256-275
@@ -744,6 +839,13 @@ int patolette_b200_ordered_counts(unsigned long long *out2, int reset) {
         pb_ordered_counts(out2, reset != 0);
         return 0;
     } catch (const pb_cuda_error &e) { return -(int)e.code; }
+}
+
+int patolette_b200_set_option(const char *name, long long value) {
+    if (!name) return -1;
+    if (!strcmp(name, "dump_cap")) { pb_ordered_set_dump_cap(value); return 0; }
+    if (!strcmp(name, "overlap")) { g_overlap_override = (int)value; return 0; }
+    return -1;
 }
 
 int patolette_b200_ordered_chain_debug(unsigned long long *out35, int reset) {

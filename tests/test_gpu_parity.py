@@ -223,6 +223,40 @@ def test_unused_palette_rows_are_minus_one(cuda_lib):
     assert code == 0 and (pal[15:] == -1).all() and (pal[:15] != -1).any() and pmap.max() < 15
 
 
+def _cluster_tree(lib, fn, planar, n, K, wts=None):
+    labels = np.zeros(n, dtype=np.uint32); centers = np.zeros((K, 3)); cnt = C.c_size_t(0); gq = C.c_size_t(0)
+    f = getattr(lib, fn)
+    f.restype = C.c_int
+    f.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
+    assert f(planar.ctypes.data, n, None if wts is None else wts.ctypes.data, K, labels.ctypes.data, centers.ctypes.data,
+             C.byref(cnt), C.byref(gq)) == 0
+    return labels, centers[:cnt.value].copy(), cnt.value, gq.value
+
+
+@pytest.mark.parametrize("route", ["default", "no_term_dump", "one_slot", "no_overlap", "overlap"])
+def test_cluster_tree_1p5M_every_route_matches_oracle(cuda_lib, oracle, route):
+    """1.5 M pixels, K=48 (clusters long enough for the group records and the two-level resolve, hovering
+    off-diagonal sums, two-parity records): the ordered-sum machinery has several routes to the same bits -
+    replays from the term dump or from the planes (dump exhausted), half-batches on two streams or one.
+    Every route must give the oracle's partition and centres bit for bit."""
+    n, K = 1_500_000, 48
+    side = int(np.ceil(np.sqrt(n)))
+    planar = np.asfortranarray(image_like_colors(side, side, 17)[:n] * 0.5 + 0.5 * uniform_colors(side, side, 18)[:n])
+    want = _cluster_tree(oracle.lib, "orc_quantize_clusters", planar, n, K)
+    opts = {"default": [], "no_term_dump": [(b"dump_cap", 0)], "one_slot": [(b"dump_cap", 1)],
+            "no_overlap": [(b"overlap", 0)], "overlap": [(b"overlap", 1)]}[route]
+    try:
+        for k, v in opts:
+            assert cuda_lib.patolette_b200_set_option(k, v) == 0
+        got = _cluster_tree(cuda_lib, "patolette_b200_quantize_clusters", planar, n, K)
+    finally:
+        cuda_lib.patolette_b200_set_option(b"dump_cap", -1)
+        cuda_lib.patolette_b200_set_option(b"overlap", -1)
+    assert got[2:] == want[2:], "cluster counts differ"
+    assert np.array_equal(got[0], want[0]), "cluster membership differs"
+    assert_same_floats(got[1], want[1], "cluster centres")
+
+
 # ---------------------------------------------------------------------------------- large-size properties
 def test_config2_scale_properties(cuda_lib):
     """2048 x 2048, K=256, ICtCp, dither off (BASELINE config 2 at a quarter of the pixels): size-independent

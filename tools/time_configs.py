@@ -23,8 +23,8 @@ CONFIGS = [
     ("C4 4096^2 K=256 ICtCp kmeans10 full-N", dict(side=4096, K=256, cs=2, dither=False, km=10, full=True)),
     ("C5 4096^2 K=1024 ICtCp weighted kmeans10 full-N", dict(side=4096, K=1024, cs=2, dither=False, km=10, full=True, w=True)),
     ("C4 16384^2 K=256 ICtCp no-dither", dict(side=16384, K=256, cs=2, dither=False, km=0)),
-    ("FULL C3 8192^2 K=256 CIELuv dither", dict(side=8192, K=256, cs=1, dither=True, km=0, reps=1)),
-    ("FULL C4 16384^2 K=256 ICtCp kmeans10 dither", dict(side=16384, K=256, cs=2, dither=True, km=10, reps=1)),
+    ("FULL C3 8192^2 K=256 CIELuv dither", dict(side=8192, K=256, cs=1, dither=True, km=0, reps=2)),
+    ("FULL C4 16384^2 K=256 ICtCp kmeans10 dither", dict(side=16384, K=256, cs=2, dither=True, km=10, reps=2)),
 ]
 PROFILE = "--profile" in sys.argv
 if PROFILE:
