@@ -29,121 +29,93 @@ namespace {
 
 // ------------------------------------------------------------------------------------
 // Per-bucket ordered sums.  The members of bucket b of a cluster, in ascending pixel
-// order, are ord[class_start[b] .. class_start[b+1]) (stable bucket sort, pb_scatter.cu).
+// order, are ord[class_start[b] .. class_start[b+1]) (stable bucket sort, pb_parallel.cu).
 // One warp per (cluster, bucket): lanes gather a tile of members, chain lanes add.
+//
+// The gathers are what bounds these kernels (measured: 2.2 TB/s of 32-byte sector traffic with the planar
+// layout, i.e. the random-access limit of HBM, not the DADD chain).  k_buckets therefore leaves an
+// interleaved copy (c0, c1, c2, w) of every pixel behind: one sector per member instead of three.
+// The chain lanes run ONE uniform loop `acc += term[lane][e]`: every per-element term is formed by the
+// gathering lanes (in parallel) before it is staged, so the critical path per element is a shared-memory
+// broadcast read + one dependent DADD.
 // ------------------------------------------------------------------------------------
-constexpr int BK_TILE = 64;            // members per stage (2 per lane)
-constexpr int BK_STRIDE = BK_TILE + 2;
 constexpr int BK_WARPS = 4;
-constexpr int BK_PER = BK_TILE / 32;
-constexpr int BK_DEPTH = 4;            // stages in flight per warp
 
-// The members of a bucket are gathered (random 8-byte reads of the planes, measured 135-157 cycles per
-// element when only one tile was in flight) through a ring of BK_DEPTH stages filled with cp.async: the
-// gathers of tile t + BK_DEPTH - 1 are issued before the chain over tile t starts, and the positions (`ord`)
-// they need were loaded one iteration earlier, so the only latency left on the warp's critical path is the
-// chain itself: a shared-memory broadcast read + one dependent DADD per element, ONE uniform loop
-// `acc += term[lane][e]` for all chain lanes (every term is formed by the gathering lanes, in parallel).
-__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
-
-// Generic driver: NP planes gathered per member, `emit(e, raw)` turns the staged values of element e into
-// the NT term rows, chain lanes accumulate with `step(acc, term, lane)`.
-template <int NP, int NT, typename Planes, typename Emit, typename Step>
-__device__ __forceinline__ double bucket_chain(const uint32_t *__restrict__ ord, uint32_t beg, uint32_t end, Planes plane,
-                                               double (*raw)[NP][BK_TILE], double (*term)[BK_STRIDE], Emit emit, Step step,
-                                               int lane) {
-    double acc = 0.0;
-    if (beg >= end) return acc;
-    const uint32_t ntile = (end - beg + BK_TILE - 1) / BK_TILE;
-    uint32_t ordv[BK_PER]; // positions of the tile whose gathers are issued next
-    auto load_ord = [&](uint32_t t) {
-#pragma unroll
-        for (int q = 0; q < BK_PER; q++) {
-            const uint32_t i = beg + t * BK_TILE + q * 32 + lane;
-            ordv[q] = (t < ntile && i < end) ? ord[i] : 0xffffffffu;
-        }
-    };
-    auto issue = [&](uint32_t t) { // gathers of tile t into stage t % BK_DEPTH (always one commit per call)
-#pragma unroll
-        for (int q = 0; q < BK_PER; q++) {
-            if (ordv[q] != 0xffffffffu) {
-#pragma unroll
-                for (int j = 0; j < NP; j++) cp_async8(&raw[t % BK_DEPTH][j][q * 32 + lane], plane(j) + ordv[q]);
-            }
-        }
-        cp_async_commit();
-    };
-    for (uint32_t t = 0; t + 1 < BK_DEPTH; t++) { load_ord(t); issue(t); }
-    load_ord(BK_DEPTH - 1);
-    for (uint32_t t = 0; t < ntile; t++) {
-        const uint32_t cnt = min((uint32_t)BK_TILE, end - (beg + t * BK_TILE));
-        cp_async_wait<BK_DEPTH - 2>(); // tile t has landed (this lane's copies)
-        __syncwarp();                  // ... and everybody else's
-#pragma unroll
-        for (int q = 0; q < BK_PER; q++) {
-            const int e = q * 32 + lane;
-            double v[NP];
-#pragma unroll
-            for (int j = 0; j < NP; j++) v[j] = raw[t % BK_DEPTH][j][e];
-            emit(e, v, term);
-        }
-        __syncwarp();
-        issue(t + BK_DEPTH - 1);      // refills the stage consumed at iteration t - 1
-        load_ord(t + BK_DEPTH);
-        if (lane < NT) {
-            const double *vp = term[lane];
-#pragma unroll 8
-            for (uint32_t e = 0; e < cnt; e++) acc = step(acc, vp[e]);
-        }
-        __syncwarp();
-    }
-    cp_async_wait<0>();
-    return acc;
+struct Px { double c0, c1, c2, w; };
+__device__ __forceinline__ Px load_px(const double *__restrict__ aos, uint32_t p) {
+    const double2 *a = reinterpret_cast<const double2 *>(aos) + 2 * (size_t)p;
+    const double2 u = a[0], v = a[1];
+    return Px{u.x, u.y, v.x, v.y};
 }
 
 //   LQ (local.c:124-134): term 0 = w (bucket "size"), terms 1..3 = c_j * w.
 //     The reference accumulates the size as size_t += double (local.c:133), i.e.
 //     size = trunc((double)size + w) at every step.  Unweighted that is the member count (exact), and
 //     c_j * 1.0 == c_j: three plain chains.  Weighted, every chain lane runs the trunc-select stream.
+//   The gather of tile t+1 sits in registers during the chain over tile t.
+constexpr int BS_TILE = 128, BS_STRIDE = BS_TILE + 2, BS_PER = BS_TILE / 32;
 template <bool WEIGHTED>
-__global__ void __launch_bounds__(BK_WARPS * 32) k_bucket_chains_lq(PbPlanes b0, PbPlanes b1,
+__global__ void __launch_bounds__(BK_WARPS * 32) k_bucket_chains_lq(const double *__restrict__ aos,
                                                                    const PbSeg *__restrict__ segs, int nseg,
                                                                    const uint32_t *__restrict__ ord,
                                                                    const uint32_t *__restrict__ class_start,
                                                                    double *__restrict__ out) {
     constexpr int NT = WEIGHTED ? 4 : 3;
-    __shared__ double raw_all[BK_WARPS][BK_DEPTH][NT][BK_TILE];
-    __shared__ double term_all[BK_WARPS][NT][BK_STRIDE];
+    __shared__ double sm_all[BK_WARPS][NT][BS_STRIDE];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int gw = blockIdx.x * BK_WARPS + warp;
     if (gw >= nseg * PB_BUCKETS) return;
     const int seg = gw / PB_BUCKETS, b = gw % PB_BUCKETS;
-    const PbSeg sg = segs[seg];
-    const PbPlanes &P = sg.buf ? b1 : b0;
+    double(*sm)[BS_STRIDE] = sm_all[warp];
     const uint32_t *cs = class_start + (size_t)seg * (PB_BUCKETS + 1);
     const uint32_t beg = cs[b], end = cs[b + 1];
-    auto plane = [&](int j) -> const double * { return j < 3 ? P.c[j] : P.w; };
-    auto emit = [&](int e, const double *v, double (*term)[BK_STRIDE]) {
-        if (WEIGHTED) {
-            term[0][e] = v[3];
-            term[1][e] = __dmul_rn(v[0], v[3]);
-            term[2][e] = __dmul_rn(v[1], v[3]);
-            term[3][e] = __dmul_rn(v[2], v[3]);
-        } else {
-            term[0][e] = v[0];
-            term[1][e] = v[1];
-            term[2][e] = v[2];
+    double acc = 0.0;
+    double g[BS_PER][NT];
+    auto gather = [&](uint32_t i0) {
+#pragma unroll
+        for (int q = 0; q < BS_PER; q++) {
+            const uint32_t i = i0 + q * 32 + lane;
+#pragma unroll
+            for (int t = 0; t < NT; t++) g[q][t] = 0.0;
+            if (i < end) {
+                const Px x = load_px(aos, ord[i]);
+                if (WEIGHTED) {
+                    g[q][0] = x.w;
+                    g[q][1] = __dmul_rn(x.c0, x.w);
+                    g[q][2] = __dmul_rn(x.c1, x.w);
+                    g[q][3] = __dmul_rn(x.c2, x.w);
+                } else {
+                    g[q][0] = x.c0;
+                    g[q][1] = x.c1;
+                    g[q][2] = x.c2;
+                }
+            }
         }
     };
-    auto step = [&](double acc, double t) {
-        const double r = __dadd_rn(acc, t);
-        return (WEIGHTED && lane == 0) ? trunc(r) : r;
-    };
-    const double acc = bucket_chain<NT, NT>(ord, beg, end, plane, raw_all[warp], term_all[warp], emit, step, lane);
+    if (beg < end) gather(beg);
+    for (uint32_t i0 = beg; i0 < end; i0 += BS_TILE) {
+        const uint32_t cnt = min((uint32_t)BS_TILE, end - i0);
+#pragma unroll
+        for (int q = 0; q < BS_PER; q++)
+#pragma unroll
+            for (int t = 0; t < NT; t++) sm[t][q * 32 + lane] = g[q][t];
+        __syncwarp();
+        if (i0 + BS_TILE < end) gather(i0 + BS_TILE); // in flight during the chain below
+        if (lane < NT) {
+            const double *vp = sm[lane];
+            if (WEIGHTED) {
+#pragma unroll 8
+                for (uint32_t e = 0; e < cnt; e++) {
+                    const double t = __dadd_rn(acc, vp[e]);
+                    acc = lane == 0 ? trunc(t) : t;
+                }
+            } else {
+#pragma unroll 16
+                for (uint32_t e = 0; e < cnt; e++) acc = __dadd_rn(acc, vp[e]);
+            }
+        }
+        __syncwarp();
+    }
     double *o = out + ((size_t)seg * PB_BUCKETS + b) * 4;
     if (WEIGHTED) {
         if (lane == 0) o[0] = __longlong_as_double((long long)(unsigned long long)acc);
@@ -154,59 +126,118 @@ __global__ void __launch_bounds__(BK_WARPS * 32) k_bucket_chains_lq(PbPlanes b0,
     }
 }
 
-// GQ cell moments (cells.c:78-116), unweighted, over the whole image:
+// GQ cell moments (cells.c:78-116), unweighted, over the whole image: only 512 warps, each with a long
+// bucket, so the gathers go through a ring of BK_DEPTH stages filled with cp.async (16-byte copies of the
+// interleaved pixels): the gathers of tile t + BK_DEPTH - 1 are issued before the chain over tile t starts,
+// and the positions (`ord`) they need were loaded one iteration earlier.
 // terms 0..2 = c_j ; 3 = (cx^2 + cy^2) + cz^2 ; 4..9 = c_r * c_s for (r,s) = (0,0)(0,1)(1,1)(0,2)(1,2)(2,2).
-__global__ void __launch_bounds__(BK_WARPS * 32) k_bucket_chains_gq(PbPlanes src, const uint32_t *__restrict__ ord,
+constexpr int BK_TILE = 64;            // members per stage (2 per lane)
+constexpr int BK_STRIDE = BK_TILE + 2;
+constexpr int BK_PER = BK_TILE / 32;
+constexpr int BK_DEPTH = 3;            // stages in flight per warp (static shared memory: 45 KB per CTA)
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+__global__ void __launch_bounds__(BK_WARPS * 32) k_bucket_chains_gq(const double *__restrict__ aos,
+                                                                   const uint32_t *__restrict__ ord,
                                                                    const uint32_t *__restrict__ class_start,
                                                                    double *__restrict__ out) {
     constexpr int NT = 10;
-    __shared__ double raw_all[BK_WARPS][BK_DEPTH][3][BK_TILE];
+    __shared__ __align__(16) double raw_all[BK_WARPS][BK_DEPTH][BK_TILE][4];
     __shared__ double term_all[BK_WARPS][NT][BK_STRIDE];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = blockIdx.x * BK_WARPS + warp;
     if (b >= PB_BUCKETS) return;
+    double(*raw)[BK_TILE][4] = raw_all[warp];
+    double(*term)[BK_STRIDE] = term_all[warp];
     const uint32_t beg = class_start[b], end = class_start[b + 1];
-    auto plane = [&](int j) -> const double * { return src.c[j]; };
-    auto emit = [&](int e, const double *v, double (*term)[BK_STRIDE]) {
-        const double x = v[0], y = v[1], z = v[2];
-        term[0][e] = x;
-        term[1][e] = y;
-        term[2][e] = z;
-        term[3][e] = __dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z));
-        term[4][e] = __dmul_rn(x, x);
-        term[5][e] = __dmul_rn(x, y);
-        term[6][e] = __dmul_rn(y, y);
-        term[7][e] = __dmul_rn(x, z);
-        term[8][e] = __dmul_rn(y, z);
-        term[9][e] = __dmul_rn(z, z);
-    };
-    auto step = [&](double acc, double t) { return __dadd_rn(acc, t); };
-    const double acc = bucket_chain<3, NT>(ord, beg, end, plane, raw_all[warp], term_all[warp], emit, step, lane);
+    double acc = 0.0;
+    if (beg < end) {
+        const uint32_t ntile = (end - beg + BK_TILE - 1) / BK_TILE;
+        auto load_ord = [&](uint32_t t, uint32_t *o) {
+#pragma unroll
+            for (int q = 0; q < BK_PER; q++) {
+                const uint32_t i = beg + t * BK_TILE + q * 32 + lane;
+                o[q] = (t < ntile && i < end) ? ord[i] : 0xffffffffu;
+            }
+        };
+        auto issue = [&](uint32_t t, const uint32_t *o) { // gathers of tile t into stage t % BK_DEPTH (one commit per call)
+#pragma unroll
+            for (int q = 0; q < BK_PER; q++) {
+                if (o[q] != 0xffffffffu) {
+                    const double *src = aos + 4 * (size_t)o[q];
+                    double *dst = raw[t % BK_DEPTH][q * 32 + lane];
+                    cp_async16(dst, src);
+                    cp_async16(dst + 2, src + 2);
+                }
+            }
+            cp_async_commit();
+        };
+        uint32_t ordv[BK_PER]; // positions of the tile whose gathers are issued next
+        {   // prologue: the positions of the first BK_DEPTH tiles in flight together, then their gathers
+            uint32_t o[BK_DEPTH][BK_PER];
+#pragma unroll
+            for (int t = 0; t < BK_DEPTH; t++) load_ord(t, o[t]);
+#pragma unroll
+            for (int t = 0; t + 1 < BK_DEPTH; t++) issue(t, o[t]);
+#pragma unroll
+            for (int q = 0; q < BK_PER; q++) ordv[q] = o[BK_DEPTH - 1][q];
+        }
+        for (uint32_t t = 0; t < ntile; t++) {
+            const uint32_t cnt = min((uint32_t)BK_TILE, end - (beg + t * BK_TILE));
+            cp_async_wait<BK_DEPTH - 2>(); // tile t has landed (this lane's copies)
+            __syncwarp();                  // ... and everybody else's
+#pragma unroll
+            for (int q = 0; q < BK_PER; q++) {
+                const int e = q * 32 + lane;
+                const double x = raw[t % BK_DEPTH][e][0], y = raw[t % BK_DEPTH][e][1], z = raw[t % BK_DEPTH][e][2];
+                term[0][e] = x;
+                term[1][e] = y;
+                term[2][e] = z;
+                term[3][e] = __dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z));
+                term[4][e] = __dmul_rn(x, x);
+                term[5][e] = __dmul_rn(x, y);
+                term[6][e] = __dmul_rn(y, y);
+                term[7][e] = __dmul_rn(x, z);
+                term[8][e] = __dmul_rn(y, z);
+                term[9][e] = __dmul_rn(z, z);
+            }
+            __syncwarp();
+            issue(t + BK_DEPTH - 1, ordv); // refills the stage consumed at iteration t - 1
+            load_ord(t + BK_DEPTH, ordv);
+            if (lane < NT) {
+                const double *vp = term[lane];
+#pragma unroll 16
+                for (uint32_t e = 0; e < cnt; e++) acc = __dadd_rn(acc, vp[e]);
+            }
+            __syncwarp();
+        }
+        cp_async_wait<0>();
+    }
     if (lane < 10) out[(size_t)b * 10 + lane] = acc;
 }
 
 } // namespace
 
-void pb_launch_bucket_chains_lq(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, bool weighted,
+void pb_launch_bucket_chains_lq(const double *d_aos, const PbSeg *d_segs, int nseg, bool weighted,
                                 const uint32_t *d_ord, const uint32_t *d_class_start, double *d_out,
                                 cudaStream_t st) {
     if (nseg <= 0) return;
     const int grid = (nseg * PB_BUCKETS + BK_WARPS - 1) / BK_WARPS;
-    if (weighted)
-        { PbProfScope _prof("k_bucket_chains_lq", st);
-        k_bucket_chains_lq<true><<<grid, BK_WARPS * 32, 0, st>>>(bufs[0], bufs[1], d_segs, nseg, d_ord, d_class_start, d_out);
-        }
-    else
-        { PbProfScope _prof("k_bucket_chains_lq", st);
-        k_bucket_chains_lq<false><<<grid, BK_WARPS * 32, 0, st>>>(bufs[0], bufs[1], d_segs, nseg, d_ord, d_class_start, d_out);
-        }
+    PbProfScope _prof("k_bucket_chains_lq", st);
+    if (weighted) k_bucket_chains_lq<true><<<grid, BK_WARPS * 32, 0, st>>>(d_aos, d_segs, nseg, d_ord, d_class_start, d_out);
+    else k_bucket_chains_lq<false><<<grid, BK_WARPS * 32, 0, st>>>(d_aos, d_segs, nseg, d_ord, d_class_start, d_out);
     PB_CUDA_OK(cudaGetLastError());
 }
 
-void pb_launch_bucket_chains_gq(const PbPlanes &src, const uint32_t *d_ord, const uint32_t *d_class_start,
+void pb_launch_bucket_chains_gq(const double *d_aos, const uint32_t *d_ord, const uint32_t *d_class_start,
                                 double *d_out, cudaStream_t st) {
     { PbProfScope _prof("k_bucket_chains_gq", st);
-    k_bucket_chains_gq<<<PB_BUCKETS / BK_WARPS, BK_WARPS * 32, 0, st>>>(src, d_ord, d_class_start, d_out);
+    k_bucket_chains_gq<<<PB_BUCKETS / BK_WARPS, BK_WARPS * 32, 0, st>>>(d_aos, d_ord, d_class_start, d_out);
     }
     PB_CUDA_OK(cudaGetLastError());
 }

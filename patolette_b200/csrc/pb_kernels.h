@@ -44,10 +44,10 @@ void pb_launch_pass_centered(const PbPlanes bufs[2], const PbSeg *d_segs, int ns
 // Per-bucket ordered sums over bucket-sorted position lists.
 //   LQ (local.c:102-146): out[seg][b] = {size (as double bits of u64), sum c0*w, sum c1*w, sum c2*w}
 //   GQ (cells.c:53-116):  out[b] = {sum c0, c1, c2, sum |c|^2, sums c_r*c_s (r<=s: 00,01,11,02,12,22)}
-void pb_launch_bucket_chains_lq(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, bool weighted,
+void pb_launch_bucket_chains_lq(const double *d_aos, const PbSeg *d_segs, int nseg, bool weighted,
                                 const uint32_t *d_ord, const uint32_t *d_class_start,
                                 double *d_out /* nseg x 512 x 4 */, cudaStream_t st);
-void pb_launch_bucket_chains_gq(const PbPlanes &src, const uint32_t *d_ord,
+void pb_launch_bucket_chains_gq(const double *d_aos, const uint32_t *d_ord,
                                 const uint32_t *d_class_start, double *d_out /* 512 x 10 */,
                                 cudaStream_t st);
 
@@ -56,7 +56,7 @@ void pb_launch_dots_minmax(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg
                            const double *d_axes /* nseg x 3 */, PbSplit *d_split, int sm_count,
                            cudaStream_t st);
 void pb_launch_buckets(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t max_n,
-                       const double *d_axes, PbSplit *d_split, uint16_t *d_bucket, int sm_count,
+                       const double *d_axes, PbSplit *d_split, uint16_t *d_bucket, double *d_aos, int sm_count,
                        cudaStream_t st);
 void pb_launch_split_select(const double *d_bucket_sums, const uint32_t *d_class_start, int nseg,
                             PbSplit *d_split, cudaStream_t st);

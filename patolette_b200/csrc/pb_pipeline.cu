@@ -218,6 +218,7 @@ struct Quantizer {
     DevArr<double> pc[2][3], pw[2];            // ping-pong permuted planes
     DevArr<uint32_t> pidx[2];
     DevArr<uint16_t> bucket;
+    DevArr<double> aos; // interleaved (c0, c1, c2, w) copy written by k_buckets for the gathering bucket sums
     DevArr<uint32_t> ord, tile_hist, cstart_b, cstart_s;
     DevArr<double> bsums, axes;
     DevArr<PbSeg> segs, children;
@@ -271,6 +272,7 @@ struct Quantizer {
             bufs[b] = PbPlanes{{pc[b][0].p, pc[b][1].p, pc[b][2].p}, weighted ? pw[b].p : nullptr, pidx[b].p};
         }
         bucket.alloc(N);
+        aos.alloc(4 * N);
         ord.alloc(N);
         max_tiles = pb_scatter_tiles((uint32_t)N) + MAXB;
         tile_hist.alloc(pb_scatter_table_words(max_tiles, MAXB, PB_BUCKETS));
@@ -341,12 +343,12 @@ struct Quantizer {
         pb_prof_next_bytes(24.0 * N);
         pb_launch_dots_minmax(gq, segs.p, 1, (uint32_t)N, axes.p, split.p, sm_count, st);
         pb_prof_next_bytes(26.0 * N);
-        pb_launch_buckets(gq, segs.p, 1, (uint32_t)N, axes.p, split.p, bucket.p, sm_count, st);
+        pb_launch_buckets(gq, segs.p, 1, (uint32_t)N, axes.p, split.p, bucket.p, aos.p, sm_count, st);
         pb_launch_class_rank(PB_CLS_BUCKET, PB_BUCKETS, segs.p, 1, (uint32_t)N, max_tiles, bucket.p, split.p, lut.p,
                              tile_hist.p, cstart_b.p, st);
         pb_launch_scatter_ord(PB_CLS_BUCKET, PB_BUCKETS, segs.p, 1, (uint32_t)N, bucket.p, split.p, lut.p,
                               tile_hist.p, cstart_b.p, ord.p, st);
-        pb_launch_bucket_chains_gq(orig, ord.p, cstart_b.p, bsums.p, st);
+        pb_launch_bucket_chains_gq(aos.p, ord.p, cstart_b.p, bsums.p, st);
         std::vector<double> hs(PB_BUCKETS * 10);
         std::vector<uint32_t> hcs(PB_BUCKETS + 1);
         d2h(hs.data(), bsums.p, hs.size());
@@ -492,8 +494,8 @@ struct Quantizer {
                 PB_CUDA_OK(cudaMemcpyAsync(d.axes, B.haxes, 3 * nb * sizeof(double), cudaMemcpyHostToDevice, d.st));
                 pb_prof_next_bytes(24.0 * B.tot_n);
                 pb_launch_dots_minmax(bufs, d.segs, nb, max_n, d.axes, d.split, sm_count, d.st);
-                pb_prof_next_bytes(26.0 * B.tot_n);
-                pb_launch_buckets(bufs, d.segs, nb, max_n, d.axes, d.split, bucket.p, sm_count, d.st);
+                pb_prof_next_bytes((26.0 + 32.0) * B.tot_n);
+                pb_launch_buckets(bufs, d.segs, nb, max_n, d.axes, d.split, bucket.p, aos.p, sm_count, d.st);
                 break;
             case 1:
                 pb_launch_class_rank(PB_CLS_BUCKET, PB_BUCKETS, d.segs, nb, max_n, max_tiles, bucket.p, d.split, lut.p,
@@ -503,7 +505,7 @@ struct Quantizer {
                 break;
             case 2:
                 pb_prof_next_bytes((bpp + 4.0) * B.tot_n);
-                pb_launch_bucket_chains_lq(bufs, d.segs, nb, weighted, ord.p, d.cstart_b, d.bsums, d.st);
+                pb_launch_bucket_chains_lq(aos.p, d.segs, nb, weighted, ord.p, d.cstart_b, d.bsums, d.st);
                 pb_launch_split_select(d.bsums, d.cstart_b, nb, d.split, d.st);
                 break;
             case 3:
