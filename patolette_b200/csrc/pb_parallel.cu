@@ -320,6 +320,65 @@ __global__ void k_scatter(ClsCtx cc, int nclass, const PbSeg *__restrict__ segs,
     }
 }
 
+// Two-class payload scatter (the split partition, local.c:219-245): ranks come from two ballots per row of
+// 32 positions and two warp-uniform running offsets in registers - no shared-memory counters, no
+// __match_any, no __syncwarp - and four rows are loaded before any is stored (memory-level parallelism).
+constexpr int SC2_UNROLL = 4;
+__global__ void __launch_bounds__(256) k_scatter2(const uint16_t *__restrict__ bucket, const PbSplit *__restrict__ sp,
+                                                  const PbSeg *__restrict__ segs, const uint32_t *__restrict__ tile_hist,
+                                                  const uint32_t *__restrict__ class_start, PbPlanes src0, PbPlanes src1,
+                                                  PbPlanes dst0, PbPlanes dst1, bool src_is_identity) {
+    const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int seg = blockIdx.y;
+    const PbSeg sg = segs[seg];
+    const uint32_t tile = blockIdx.x * warps + warp;
+    if ((size_t)tile * SC_TILE >= sg.n) return;
+    const uint32_t *hist = tile_hist + ((size_t)sg.tbase + tile) * 2;
+    const uint32_t *cst = class_start + (size_t)seg * 3;
+    uint32_t base0 = hist[0] + cst[0], base1 = hist[1] + cst[1];
+    const uint32_t split = sp[seg].split;
+    const PbPlanes &S = sg.buf ? src1 : src0;
+    const PbPlanes &D = sg.buf ? dst1 : dst0;
+    const bool has_w = S.w != nullptr, has_idx = D.idx != nullptr;
+    const uint32_t beg = tile * SC_TILE, end = min(beg + (uint32_t)SC_TILE, sg.n);
+    const uint32_t below = (1u << lane) - 1u;
+    for (uint32_t row = beg; row < end; row += 32 * SC2_UNROLL) {
+        bool valid[SC2_UNROLL], right[SC2_UNROLL];
+        double v0[SC2_UNROLL], v1[SC2_UNROLL], v2[SC2_UNROLL], vw[SC2_UNROLL];
+        uint32_t vi[SC2_UNROLL];
+#pragma unroll
+        for (int u = 0; u < SC2_UNROLL; u++) {
+            const uint32_t i = row + u * 32 + lane;
+            valid[u] = i < end;
+            const uint32_t pos = sg.lo + i;
+            right[u] = false; v0[u] = v1[u] = v2[u] = vw[u] = 0.0; vi[u] = 0;
+            if (valid[u]) {
+                right[u] = bucket[pos] > split;
+                v0[u] = S.c[0][pos];
+                v1[u] = S.c[1][pos];
+                v2[u] = S.c[2][pos];
+                if (has_w) vw[u] = S.w[pos];
+                if (has_idx) vi[u] = src_is_identity ? pos : S.idx[pos];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < SC2_UNROLL; u++) {
+            const uint32_t m1 = __ballot_sync(0xffffffffu, valid[u] && right[u]);
+            const uint32_t m0 = __ballot_sync(0xffffffffu, valid[u] && !right[u]);
+            if (valid[u]) {
+                const uint32_t dst = right[u] ? base1 + __popc(m1 & below) : base0 + __popc(m0 & below);
+                D.c[0][dst] = v0[u];
+                D.c[1][dst] = v1[u];
+                D.c[2][dst] = v2[u];
+                if (has_w) D.w[dst] = vw[u];
+                if (has_idx) D.idx[dst] = vi[u];
+            }
+            base0 += __popc(m0);
+            base1 += __popc(m1);
+        }
+    }
+}
+
 __global__ void k_make_children(const PbSeg *__restrict__ segs, int nseg, const PbSplit *__restrict__ sp,
                                 PbSeg *__restrict__ children) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -481,10 +540,16 @@ void pb_launch_scatter_payload(int cls_mode, int nclass, const PbPlanes src[2], 
     const int warps = scatter_warps(nclass);
     ClsCtx cc{cls_mode, d_bucket, d_split, d_lut};
     dim3 g((tiles_cap + warps - 1) / warps, nseg);
-    { PbProfScope _prof("k_scatter", st);
-    k_scatter<true><<<g, warps * 32, (size_t)warps * (nclass + 1) * 4, st>>>(
-        cc, nclass, d_segs, tiles_cap, d_tile_hist, d_class_start, nullptr, src[0], src[1], dst[0], dst[1],
-        src_is_identity);
+    if (cls_mode == PB_CLS_SPLIT && nclass == 2) {
+        PbProfScope _prof("k_scatter", st);
+        dim3 g2((tiles_cap + 7) / 8, nseg);
+        k_scatter2<<<g2, 256, 0, st>>>(d_bucket, d_split, d_segs, d_tile_hist, d_class_start, src[0], src[1], dst[0], dst[1],
+                                      src_is_identity);
+    } else {
+        PbProfScope _prof("k_scatter", st);
+        k_scatter<true><<<g, warps * 32, (size_t)warps * (nclass + 1) * 4, st>>>(
+            cc, nclass, d_segs, tiles_cap, d_tile_hist, d_class_start, nullptr, src[0], src[1], dst[0], dst[1],
+            src_is_identity);
     }
     PB_CUDA_OK(cudaGetLastError());
 }

@@ -244,7 +244,10 @@ struct Quantizer {
     } hx;
     bool overlap = true;
 
-    static constexpr int MAXB = 64; // clusters evaluated per batch (their 2 * MAXB children get stats)
+#ifndef PB_MAXB
+#define PB_MAXB 64
+#endif
+    static constexpr int MAXB = PB_MAXB; // clusters evaluated per batch (their 2 * MAXB children get stats)
     size_t max_blocks = 0;         // capacity of the packed ordered-sum block table
     size_t max_tiles = 0;          // capacity of the packed scatter tile table
 
