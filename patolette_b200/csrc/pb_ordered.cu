@@ -283,13 +283,18 @@ __device__ __forceinline__ unsigned summarise_block(const PbPlanes &P, const PbS
         __syncwarp();
     }
     const double *mine = stage + lane * OS_STRIDE;
-    auto terms = [&](int k, double *t) {
-        double w, c0, c1, c2;
-        if (STAGED) { w = W ? mine[3 * OS_PLANE + k] : 1.0; c0 = mine[k]; c1 = mine[OS_PLANE + k]; c2 = mine[2 * OS_PLANE + k]; }
-        else { const size_t p = p0 + k; w = W ? P.w[p] : 1.0; c0 = P.c[0][p]; c1 = P.c[1][p]; c2 = P.c[2][p]; }
-        if (NC == 1) t[0] = term_one<KIND, W>(ch0, w, c0, c1, c2, m0, m1, m2);
-        else terms_all<KIND, W>(w, c0, c1, c2, m0, m1, m2, t);
+    struct Px { double w, c0, c1, c2; };
+    auto fetch = [&](int k) {
+        Px x;
+        if (STAGED) { x.w = W ? mine[3 * OS_PLANE + k] : 1.0; x.c0 = mine[k]; x.c1 = mine[OS_PLANE + k]; x.c2 = mine[2 * OS_PLANE + k]; }
+        else { const size_t p = p0 + k; x.w = W ? P.w[p] : 1.0; x.c0 = P.c[0][p]; x.c1 = P.c[1][p]; x.c2 = P.c[2][p]; }
+        return x;
     };
+    auto terms_of = [&](const Px &x, double *t) {
+        if (NC == 1) t[0] = term_one<KIND, W>(ch0, x.w, x.c0, x.c1, x.c2, m0, m1, m2);
+        else terms_all<KIND, W>(x.w, x.c0, x.c1, x.c2, m0, m1, m2, t);
+    };
+    auto terms = [&](int k, double *t) { terms_of(fetch(k), t); };
     // ---- phase 1: approximate running sum at the start of this lane's elements ---------------------
     double tstart[NC];
     {
@@ -297,7 +302,7 @@ __device__ __forceinline__ unsigned summarise_block(const PbPlanes &P, const PbS
 #pragma unroll
         for (int c = 0; c < NC; c++) tl[c] = 0.0;
 #pragma unroll OS_UNROLL
-        for (int k = 0; k < mycnt; k++) {
+        for (int k = 0; k < mycnt; k++) { // (a register prefetch of element k + 1 measured slower: 128-register cap)
             double t[C];
             terms(k, t);
 #pragma unroll
@@ -742,6 +747,14 @@ __global__ void __launch_bounds__(32 * NChains<KIND>::C) k_ord_resolve(PbPlanes 
                 const double s = st.ok ? pb_state_to_double(st) : sd;
                 const uint32_t base = (g0 + next) * OB;
                 const uint32_t cnt = min((uint32_t)OB, n - base);
+                {   // the next block of this group that will be replayed from the dump: pull its 4 KB towards L1 now,
+                    // one 128-byte line per lane, so that its load does not start cold after this chain
+                    const unsigned nx = __ballot_sync(0xffffffffu, lane > src && r.flag == F_REPLAY && r.sum >= 0);
+                    if (nx) {
+                        const long long sl = __shfl_sync(0xffffffffu, r.sum, __ffs(nx) - 1);
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(dump_terms + (size_t)sl * OB + lane * 16));
+                    }
+                }
                 if (fl1 == F_REPLAY && s0 >= 0) // the record names a dump slot
                     sd = replay_dump(dump_terms + (size_t)s0 * OB, cnt, s, lane, sh.terms[chain]);
                 else
