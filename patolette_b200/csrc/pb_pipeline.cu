@@ -677,6 +677,15 @@ void run_patolette(size_t width, size_t height, const double *data, const double
     qz.init(n, weights != nullptr);
     Timer total(qz.st), stage(qz.st);
     total.start();
+    struct SideStream { // copies that overlap kernels of the compute stream (pinned host buffers only)
+        cudaStream_t s = nullptr;
+        cudaStream_t get() {
+            if (!s) PB_CUDA_OK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+            return s;
+        }
+        ~SideStream() { if (s) cudaStreamDestroy(s); }
+    } copy_stream;
+    bool piped_color = false;
 
     stage.start(); // patolette.c:187-199: the library works on its own copy
     const cudaMemcpyKind in_kind = device_io ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
@@ -688,6 +697,30 @@ void run_patolette(size_t width, size_t height, const double *data, const double
         double *dst[3] = {qz.col[0].p, qz.col[1].p, qz.col[2].p};
         pb_launch_deinterleave(rgb.p, n, dst, qz.sm_count, qz.st);
         qz.sync(); // rgb is released at the end of this scope
+    } else if (!device_io && n >= ((size_t)1 << 20) && pb_host_is_pinned(data)) {
+        // pinned host planes: the copy is pipelined with the colour transform (patolette.c:201-207) in
+        // chunks - chunk c is transformed on the compute stream while chunk c + 1 crosses PCIe
+        piped_color = true;
+        const int which = opt->color_space == patolette__CIELuv ? PB_T_SRGB_TO_CIELUV
+                          : opt->color_space == patolette__ICtCp ? PB_T_SRGB_TO_ICTCP : -1;
+        constexpr int NCH = 8;
+        const size_t per = ((n + NCH - 1) / NCH + 1023) & ~(size_t)1023;
+        cudaEvent_t ev[NCH];
+        for (size_t off = 0, c = 0; off < n; off += per, c++) {
+            const size_t len = std::min(per, n - off);
+            for (int j = 0; j < 3; j++)
+                PB_CUDA_OK(cudaMemcpyAsync(qz.col[j].p + off, data + (size_t)j * n + off, len * sizeof(double), in_kind, copy_stream.get()));
+            PB_CUDA_OK(cudaEventCreateWithFlags(&ev[c], cudaEventDisableTiming));
+            PB_CUDA_OK(cudaEventRecord(ev[c], copy_stream.get()));
+            PB_CUDA_OK(cudaStreamWaitEvent(qz.st, ev[c], 0));
+            if (which >= 0) {
+                const double *src[3] = {qz.col[0].p + off, qz.col[1].p + off, qz.col[2].p + off};
+                double *dst[3] = {qz.col[0].p + off, qz.col[1].p + off, qz.col[2].p + off};
+                pb_prof_next_bytes(48.0 * len);
+                pb_launch_color(which, src, dst, len, qz.sm_count, qz.st);
+            }
+            PB_CUDA_OK(cudaEventDestroy(ev[c])); // released by the runtime once it has completed
+        }
     } else
     for (int j = 0; j < 3; j++) {
         if (device_io) PB_CUDA_OK(cudaMemcpyAsync(qz.col[j].p, data + (size_t)j * n, n * sizeof(double), in_kind, qz.st));
@@ -700,8 +733,10 @@ void run_patolette(size_t width, size_t height, const double *data, const double
     set_timing(1, stage.stop());
 
     stage.start(); // patolette.c:201-207
-    if (opt->color_space == patolette__CIELuv) colors_transform(qz, PB_T_SRGB_TO_CIELUV);
-    else if (opt->color_space == patolette__ICtCp) colors_transform(qz, PB_T_SRGB_TO_ICTCP);
+    if (!piped_color) {
+        if (opt->color_space == patolette__CIELuv) colors_transform(qz, PB_T_SRGB_TO_CIELUV);
+        else if (opt->color_space == patolette__ICtCp) colors_transform(qz, PB_T_SRGB_TO_ICTCP);
+    }
     set_timing(2, stage.stop());
     if (opt->verbose) printf("patolette ======== Palette generation \n");
 
@@ -734,6 +769,7 @@ void run_patolette(size_t width, size_t height, const double *data, const double
     if (!opt->palette_only) {
         DevArr<unsigned long long> dmap;
         dmap.alloc(n);
+        bool map_sent = false;
         if (opt->dither) { // patolette.c:268-299
             if (opt->verbose) printf("patolette ======== Dithering\n");
             stage.start();
@@ -760,8 +796,27 @@ void run_patolette(size_t width, size_t height, const double *data, const double
             dpal.alloc(3 * count);
             qz.h2d(dpal.p, pal.data(), 3 * count);
             const double *planes[3] = {qz.col[0].p, qz.col[1].p, qz.col[2].p};
-            pb_prof_next_bytes(32.0 * n);
-            pb_launch_nearest(planes, n, dpal.p, (int)count, dmap.p, qz.sm_count, qz.st);
+            if (!device_io && n >= ((size_t)1 << 20) && pb_host_is_pinned(palette_map)) {
+                // pinned destination: the map goes home chunk by chunk while the next chunk is assigned
+                constexpr int NCH = 4;
+                const size_t per = ((n + NCH - 1) / NCH + 1023) & ~(size_t)1023;
+                for (size_t off = 0; off < n; off += per) {
+                    const size_t len = std::min(per, n - off);
+                    const double *pl[3] = {planes[0] + off, planes[1] + off, planes[2] + off};
+                    pb_prof_next_bytes(32.0 * len);
+                    pb_launch_nearest(pl, len, dpal.p, (int)count, dmap.p + off, qz.sm_count, qz.st);
+                    cudaEvent_t ev;
+                    PB_CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                    PB_CUDA_OK(cudaEventRecord(ev, qz.st));
+                    PB_CUDA_OK(cudaStreamWaitEvent(copy_stream.get(), ev, 0));
+                    PB_CUDA_OK(cudaEventDestroy(ev));
+                    PB_CUDA_OK(cudaMemcpyAsync(palette_map + off, dmap.p + off, len * sizeof(size_t), cudaMemcpyDeviceToHost, copy_stream.get()));
+                }
+                map_sent = true;
+            } else {
+                pb_prof_next_bytes(32.0 * n);
+                pb_launch_nearest(planes, n, dpal.p, (int)count, dmap.p, qz.sm_count, qz.st);
+            }
             qz.sync();
             // patolette.c:322-323, applied whatever the colour space was (reference bug B1)
             palette_transform(qz, PB_T_ICTCP_TO_REC2020, pal);
@@ -769,7 +824,8 @@ void run_patolette(size_t width, size_t height, const double *data, const double
             set_timing(6, stage.stop());
         }
         stage.start();
-        if (device_io) PB_CUDA_OK(cudaMemcpyAsync(palette_map, dmap.p, n * sizeof(size_t), cudaMemcpyDeviceToDevice, qz.st));
+        if (map_sent) PB_CUDA_OK(cudaStreamSynchronize(copy_stream.get())); // the tail of the chunked copy
+        else if (device_io) PB_CUDA_OK(cudaMemcpyAsync(palette_map, dmap.p, n * sizeof(size_t), cudaMemcpyDeviceToDevice, qz.st));
         else pb_copy_d2h(palette_map, dmap.p, n * sizeof(size_t), qz.st);
         set_timing(8, stage.stop());
     }
@@ -1050,6 +1106,7 @@ int patolette_b200_dither(const double *planar, size_t width, size_t height, con
         for (int j = 0; j < 3; j++) qz.h2d(qz.col[j].p, planar + (size_t)j * n, n);
         DevArr<unsigned long long> dmap;
         dmap.alloc(n);
+        bool map_sent = false;
         qz.h2d(dmap.p, (const unsigned long long *)map, n);
         std::vector<double> pal(palette_rm, palette_rm + 3 * K);
         const double *planes[3] = {qz.col[0].p, qz.col[1].p, qz.col[2].p};

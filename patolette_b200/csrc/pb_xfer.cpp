@@ -44,7 +44,7 @@ bool is_pinned(const void *p) {
 
 int worker_count() {
     unsigned hc = std::thread::hardware_concurrency();
-    int n = hc >= 16 ? 6 : (hc >= 8 ? 4 : 2);
+    int n = hc >= 16 ? 8 : (hc >= 8 ? 4 : 2);
     return std::min(n, MAX_LANES);
 }
 
@@ -100,6 +100,8 @@ void striped(char *dev, char *host, size_t bytes) {
 }
 
 } // namespace
+
+bool pb_host_is_pinned(const void *p) { return is_pinned(p); }
 
 void pb_copy_h2d(void *dst_dev, const void *src_host, size_t bytes, cudaStream_t st) {
     if (!bytes) return;

@@ -11,3 +11,5 @@
 
 void pb_copy_h2d(void *dst_dev, const void *src_host, size_t bytes, cudaStream_t st);
 void pb_copy_d2h(void *dst_host, const void *src_dev, size_t bytes, cudaStream_t st);
+// true for pinned / registered / managed host memory (DMA straight from the caller's buffer)
+bool pb_host_is_pinned(const void *p);
