@@ -90,5 +90,11 @@ void pb_launch_make_children(const PbSeg *d_segs, int nseg, const PbSplit *d_spl
 // Nearest palette entry + cluster labels.
 void pb_launch_nearest(const double *const planes[3], size_t n, const double *d_palette_rm, int K,
                        unsigned long long *d_map, int sm_count, cudaStream_t st);
+// exact 1-NN through per-cell candidate lists (pb_nngrid.cu): same map as pb_launch_nearest
+size_t pb_nngrid_scratch_bytes(int K);
+void pb_launch_nngrid_build(const double *const planes[3], size_t n, const double *d_palette_rm, int K, void *d_scratch,
+                            int sm_count, cudaStream_t st);
+void pb_launch_nearest_grid(const double *const planes[3], size_t n, const double *d_palette_rm, int K, const void *d_scratch,
+                            unsigned long long *d_map, int sm_count, cudaStream_t st);
 void pb_launch_labels(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t max_n,
                       uint32_t *d_labels, int sm_count, cudaStream_t st);

@@ -28,6 +28,7 @@ namespace {
 
 int g_device = 0;
 int g_overlap_override = -1; // patolette_b200_set_option "overlap": -1 default, 0 off, 1 on
+bool g_nn_grid = true;       // patolette_b200_set_option "nn_grid": candidate-list 1-NN (pb_nngrid.cu) vs brute force
 cudaStream_t g_user_stream = nullptr;
 bool g_use_user_stream = false;
 double g_timings[10] = {0};
@@ -796,6 +797,18 @@ void run_patolette(size_t width, size_t height, const double *data, const double
             dpal.alloc(3 * count);
             qz.h2d(dpal.p, pal.data(), 3 * count);
             const double *planes[3] = {qz.col[0].p, qz.col[1].p, qz.col[2].p};
+            // exact 1-NN through per-cell candidate lists when the brute force would be FP64-bound (pb_nngrid.cu)
+            DevArr<char> nngrid;
+            const bool use_grid = g_nn_grid && count >= 32 && count <= 4096 && n >= ((size_t)1 << 18);
+            if (use_grid) {
+                nngrid.alloc(pb_nngrid_scratch_bytes((int)count));
+                pb_launch_nngrid_build(planes, n, dpal.p, (int)count, nngrid.p, qz.sm_count, qz.st);
+            }
+            auto assign = [&](const double *const pl[3], size_t len, unsigned long long *out) {
+                pb_prof_next_bytes(32.0 * len);
+                if (use_grid) pb_launch_nearest_grid(pl, len, dpal.p, (int)count, nngrid.p, out, qz.sm_count, qz.st);
+                else pb_launch_nearest(pl, len, dpal.p, (int)count, out, qz.sm_count, qz.st);
+            };
             if (!device_io && n >= ((size_t)1 << 20) && pb_host_is_pinned(palette_map)) {
                 // pinned destination: the map goes home chunk by chunk while the next chunk is assigned
                 constexpr int NCH = 4;
@@ -803,8 +816,7 @@ void run_patolette(size_t width, size_t height, const double *data, const double
                 for (size_t off = 0; off < n; off += per) {
                     const size_t len = std::min(per, n - off);
                     const double *pl[3] = {planes[0] + off, planes[1] + off, planes[2] + off};
-                    pb_prof_next_bytes(32.0 * len);
-                    pb_launch_nearest(pl, len, dpal.p, (int)count, dmap.p + off, qz.sm_count, qz.st);
+                    assign(pl, len, dmap.p + off);
                     cudaEvent_t ev;
                     PB_CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
                     PB_CUDA_OK(cudaEventRecord(ev, qz.st));
@@ -814,8 +826,7 @@ void run_patolette(size_t width, size_t height, const double *data, const double
                 }
                 map_sent = true;
             } else {
-                pb_prof_next_bytes(32.0 * n);
-                pb_launch_nearest(planes, n, dpal.p, (int)count, dmap.p, qz.sm_count, qz.st);
+                assign(planes, n, dmap.p);
             }
             qz.sync();
             // patolette.c:322-323, applied whatever the colour space was (reference bug B1)
@@ -906,6 +917,7 @@ int patolette_b200_set_option(const char *name, long long value) {
     if (!name) return -1;
     if (!strcmp(name, "dump_cap")) { pb_ordered_set_dump_cap(value); return 0; }
     if (!strcmp(name, "overlap")) { g_overlap_override = (int)value; return 0; }
+    if (!strcmp(name, "nn_grid")) { g_nn_grid = value != 0; return 0; }
     return -1;
 }
 
@@ -1061,7 +1073,14 @@ int patolette_b200_nearest(const double *planar, size_t n, const double *palette
         dmap.alloc(n);
         qz.h2d(dpal.p, palette_rm, 3 * K);
         const double *planes[3] = {qz.col[0].p, qz.col[1].p, qz.col[2].p};
-        pb_launch_nearest(planes, n, dpal.p, (int)K, dmap.p, qz.sm_count, qz.st);
+        DevArr<char> nngrid;
+        if (g_nn_grid && K >= 32 && K <= 4096 && n >= ((size_t)1 << 18)) { // same route selection as run_patolette
+            nngrid.alloc(pb_nngrid_scratch_bytes((int)K));
+            pb_launch_nngrid_build(planes, n, dpal.p, (int)K, nngrid.p, qz.sm_count, qz.st);
+            pb_launch_nearest_grid(planes, n, dpal.p, (int)K, nngrid.p, dmap.p, qz.sm_count, qz.st);
+        } else {
+            pb_launch_nearest(planes, n, dpal.p, (int)K, dmap.p, qz.sm_count, qz.st);
+        }
         qz.d2h((unsigned long long *)map, dmap.p, n);
         qz.sync();
         return 0;

@@ -151,6 +151,44 @@ def test_nearest_map_matches_oracle(cuda_lib, oracle):
     assert 17 not in b
 
 
+@pytest.mark.parametrize("kind", ["uniform", "narrow", "lattice_ties", "clustered_far", "degenerate_axis", "outliers_nan"])
+def test_nearest_candidate_lists_equal_brute_force(cuda_lib, oracle, kind):
+    """The candidate-list 1-NN (pb_nngrid.cu) against the CUDA brute force and the oracle on inputs chosen to
+    break a careless pruning rule: a pixel range tiny next to the coordinates, exact ties on a lattice
+    (lowest index must win), palette entries far outside the pixels' box, a constant channel, non-finite values."""
+    n, K = 400_003, 256
+    rng = np.random.default_rng(len(kind))
+    if kind == "uniform":
+        px = rng.random((n, 3)); pal = rng.random((K, 3))
+    elif kind == "narrow":
+        px = 0.5 + (rng.random((n, 3)) - 0.5) * 1e-9; pal = 0.5 + (rng.random((K, 3)) - 0.5) * 1e-9
+    elif kind == "lattice_ties":
+        px = rng.integers(0, 64, (n, 3)) / 64.0          # every pixel sits on the half-way planes of the palette lattice
+        pal = (rng.integers(0, 8, (K, 3)) * 8 + 4) / 64.0  # many duplicates and equidistant entries
+    elif kind == "clustered_far":
+        px = rng.random((n, 3)) * 0.1 + 0.45
+        pal = np.concatenate([rng.random((K // 2, 3)) * 50 - 25, rng.random((K - K // 2, 3)) * 0.1 + 0.45])
+    elif kind == "degenerate_axis":
+        px = rng.random((n, 3)); px[:, 1] = 0.25; pal = rng.random((K, 3))
+    else:
+        px = rng.random((n, 3)); pal = rng.random((K, 3))
+        px[::50_000] = 1e12; px[7] = np.nan; px[8, 2] = -3.0; pal[5] = 1e9
+    planar = np.asfortranarray(px)
+    got = np.zeros(n, dtype=np.uintp); brute = np.zeros(n, dtype=np.uintp)
+    assert cuda_lib.patolette_b200_nearest(planar.ctypes.data, n, pal.ctypes.data, K, got.ctypes.data) == 0
+    try:
+        assert cuda_lib.patolette_b200_set_option(b"nn_grid", 0) == 0
+        assert cuda_lib.patolette_b200_nearest(planar.ctypes.data, n, pal.ctypes.data, K, brute.ctypes.data) == 0
+    finally:
+        cuda_lib.patolette_b200_set_option(b"nn_grid", 1)
+    assert np.array_equal(got, brute), f"{int((got != brute).sum())} pixels differ from the brute force"
+    if kind != "outliers_nan":  # NaN ordering is the brute force's own convention; the oracle is compared on finite data
+        want = np.zeros(n, dtype=np.uintp)
+        oracle.lib.orc_fill_palette_map_nearest(planar.ctypes.data_as(C.c_void_p), C.c_size_t(n), pal.ctypes.data_as(C.c_void_p),
+                                                C.c_size_t(K), want.ctypes.data_as(C.c_void_p))
+        assert np.array_equal(got, want)
+
+
 @pytest.mark.parametrize("n,K,weighted,mppc", [(40_000, 64, False, 10_000), (300_000, 32, True, 1024), (16, 8, False, 8192),
                                                  (8, 8, False, 100), (5, 8, False, 100)])
 def test_kmeans_matches_oracle(cuda_lib, oracle, n, K, weighted, mppc):
