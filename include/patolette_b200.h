@@ -127,8 +127,9 @@ PB200_API size_t patolette_b200_profile_json(char *buf, size_t cap);
 PB200_API int patolette_b200_ordered_counts(unsigned long long *out16, int reset);
 /* Test / tuning knobs (never change results, only the route taken): "dump_cap" = cap on the term-dump slots
  * of an ordered-sum pass (-1 default; 0 = every replay recomputes its terms from the planes), "overlap" =
- * two-stream half-batch evaluation of the split loop (-1 default, 0 off, 1 on), "nn_grid" = nearest map through
- * per-cell candidate lists (1, default) or brute force (0).  Returns 0, -1 if unknown. */
+ * two-stream half-batch evaluation of the split loop (-1 default, 0 off, 1 on), "nn_grid" / "dither_grid" = nearest
+ * map / the dither's per-step search through per-cell candidate lists (1, default) or brute force (0).
+ * Returns 0, -1 if unknown. */
 PB200_API int patolette_b200_set_option(const char *name, long long value);
 /* Debug: per chain of the centred pass {cycles scan walk, cycles record walk, cycles replays, replays,
  * records walked one by one}, 7 x 5 counters. */

@@ -23,6 +23,7 @@
 
 #include "pb_common.cuh"
 #include "pb_kernels.h"
+#include "pb_nngrid.cuh"
 #include "pb_prof.h"
 #include "pb_pipeline.h"
 #include "pb_pool.h"
@@ -116,9 +117,17 @@ struct DitherLane {
     int ch;
 };
 
+// Candidate lists of the exact nearest-neighbour search (pb_nngrid.cu), built over the weighted query space:
+// a query inside the grid looks at the ~10-20 entries of its cell instead of all K.  geom = {lo[3], inv[3]}
+// in shared memory; cnt == nullptr: brute force.
+struct DitherGrid {
+    const double *geom;
+    const unsigned short *cnt, *list;
+};
+
 // One pixel: returns the chosen palette index (uniform across the warp) and updates the queue.
 __device__ __forceinline__ int dither_step(DitherLane &L, double P, const double *__restrict__ s_pal,
-                                           const double *__restrict__ s_palw, int K, int lane) {
+                                           const double *__restrict__ s_palw, int K, int lane, const DitherGrid &G) {
     // riemersma.c:292-297: error = sum_i queue[i] * weight[i], i ascending
     double err = 0.0;
 #pragma unroll
@@ -129,11 +138,25 @@ __device__ __forceinline__ int dither_step(DitherLane &L, double P, const double
                  z = __shfl_sync(0xffffffffu, Cw, 2);
     double bd = 0.0;
     int best = 0x7fffffff;
-    for (int j = lane; j < K; j += 32) {
-        const double dx = __dsub_rn(x, s_palw[3 * j]), dy = __dsub_rn(y, s_palw[3 * j + 1]),
-                     dz = __dsub_rn(z, s_palw[3 * j + 2]);
-        const double dd = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
-        if (best == 0x7fffffff || dd < bd) { bd = dd; best = j; }
+    const int cell = G.cnt ? pb_grid_cell(true, G.geom, G.geom + 3, x, y, z) : -1; // warp-uniform
+    if (cell >= 0) {
+        const unsigned short *Lst = G.list + (size_t)cell * K;
+        const int j0 = Lst[lane]; // K >= 64: in bounds; issued together with the count
+        const int m = G.cnt[cell];
+        for (int t = lane; t < m; t += 32) {
+            const int j = t == lane ? j0 : (int)Lst[t];
+            const double dx = __dsub_rn(x, s_palw[3 * j]), dy = __dsub_rn(y, s_palw[3 * j + 1]),
+                         dz = __dsub_rn(z, s_palw[3 * j + 2]);
+            const double dd = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+            if (best == 0x7fffffff || dd < bd) { bd = dd; best = j; }
+        }
+    } else {
+        for (int j = lane; j < K; j += 32) {
+            const double dx = __dsub_rn(x, s_palw[3 * j]), dy = __dsub_rn(y, s_palw[3 * j + 1]),
+                         dz = __dsub_rn(z, s_palw[3 * j + 2]);
+            const double dd = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+            if (best == 0x7fffffff || dd < bd) { bd = dd; best = j; }
+        }
     }
     // exact warp argmin, lowest index on ties, via integer reductions: squared distances are
     // non-negative doubles, whose bit patterns order like unsigned integers
@@ -166,7 +189,7 @@ template <typename Emit>
 __device__ __forceinline__ void dither_run(DitherLane &L, const double *__restrict__ h0, const double *__restrict__ h1,
                                            const double *__restrict__ h2, size_t from, size_t to,
                                            const double *__restrict__ s_pal, const double *__restrict__ s_palw, int K,
-                                           int lane, Emit emit) {
+                                           int lane, const DitherGrid &G, Emit emit) {
     for (size_t base = from; base < to; base += 32) {
         const size_t i = base + lane;
         double a = 0, b = 0, c = 0;
@@ -177,7 +200,7 @@ __device__ __forceinline__ void dither_run(DitherLane &L, const double *__restri
             const double pa = __shfl_sync(0xffffffffu, a, e), pb = __shfl_sync(0xffffffffu, b, e),
                          pc = __shfl_sync(0xffffffffu, c, e);
             const double P = L.ch == 0 ? pa : (L.ch == 1 ? pb : pc);
-            const int best = dither_step(L, P, s_pal, s_palw, K, lane);
+            const int best = dither_step(L, P, s_pal, s_palw, K, lane, G);
             if (lane == e) mine = best;
         }
         if (lane < cnt) emit(i, mine);
@@ -189,11 +212,27 @@ __global__ void __launch_bounds__(DT_WARPS * 32) k_riemersma_spec(const double *
                                                                  size_t warm, const double *__restrict__ pal,
                                                                  const double *__restrict__ palw, int K,
                                                                  const double *__restrict__ qweights,
-                                                                 uint32_t *__restrict__ hidx, uint32_t *__restrict__ overlap) {
+                                                                 uint32_t *__restrict__ hidx, uint32_t *__restrict__ overlap,
+                                                                 const void *__restrict__ nngrid) {
     extern __shared__ double s_mem[];
     double *s_pal = s_mem, *s_palw = s_mem + (size_t)K * 3;
+    __shared__ double s_geom[6];
+    __shared__ int s_grid_ok;
     for (int i = threadIdx.x; i < K * 3; i += blockDim.x) { s_pal[i] = pal[i]; s_palw[i] = palw[i]; }
+    if (threadIdx.x == 0) {
+        s_grid_ok = 0;
+        if (nngrid) {
+            const PbGridGeom g = pb_grid_geom((const PbGridHdr *)nngrid);
+            for (int d = 0; d < 3; d++) { s_geom[d] = g.lo[d]; s_geom[3 + d] = g.inv[d]; }
+            s_grid_ok = g.ok;
+        }
+    }
     __syncthreads();
+    DitherGrid G{s_geom, nullptr, nullptr};
+    if (s_grid_ok) {
+        G.cnt = (const unsigned short *)((const char *)nngrid + 256);
+        G.list = G.cnt + PB_NCELL;
+    }
     const int lane = threadIdx.x & 31;
     const size_t g = (size_t)blockIdx.x * DT_WARPS + (threadIdx.x >> 5);
     const size_t a = g * seg;
@@ -202,7 +241,7 @@ __global__ void __launch_bounds__(DT_WARPS * 32) k_riemersma_spec(const double *
     DitherLane L;
     dither_lane_init(L, qweights, lane);
     uint32_t *ov = overlap + g * 16;
-    dither_run(L, h0, h1, h2, start, end, s_pal, s_palw, K, lane, [&](size_t pos, int idx) {
+    dither_run(L, h0, h1, h2, start, end, s_pal, s_palw, K, lane, G, [&](size_t pos, int idx) {
         if (pos >= a) hidx[pos] = (uint32_t)idx;
         else if (pos + 16 >= a) ov[pos + 16 - a] = (uint32_t)idx;
     });
@@ -213,12 +252,28 @@ __global__ void __launch_bounds__(32) k_riemersma_repair(const double *__restric
                                                          const double *__restrict__ pal, const double *__restrict__ palw,
                                                          int K, const double *__restrict__ qweights,
                                                          uint32_t *__restrict__ hidx, const uint32_t *__restrict__ overlap,
-                                                         unsigned long long *__restrict__ stats) {
+                                                         unsigned long long *__restrict__ stats,
+                                                         const void *__restrict__ nngrid) {
     extern __shared__ double s_mem[];
     double *s_pal = s_mem, *s_palw = s_mem + (size_t)K * 3;
+    __shared__ double s_geom[6];
+    __shared__ int s_grid_ok;
     const int lane = threadIdx.x;
     for (int i = lane; i < K * 3; i += 32) { s_pal[i] = pal[i]; s_palw[i] = palw[i]; }
+    if (lane == 0) {
+        s_grid_ok = 0;
+        if (nngrid) {
+            const PbGridGeom g = pb_grid_geom((const PbGridHdr *)nngrid);
+            for (int d = 0; d < 3; d++) { s_geom[d] = g.lo[d]; s_geom[3 + d] = g.inv[d]; }
+            s_grid_ok = g.ok;
+        }
+    }
     __syncwarp();
+    DitherGrid G{s_geom, nullptr, nullptr};
+    if (s_grid_ok) {
+        G.cnt = (const unsigned short *)((const char *)nngrid + 256);
+        G.list = G.cnt + PB_NCELL;
+    }
     const size_t nseg = (n + seg - 1) / seg;
     DitherLane L;
     dither_lane_init(L, qweights, lane);
@@ -241,7 +296,7 @@ __global__ void __launch_bounds__(32) k_riemersma_repair(const double *__restric
         while (pos < n && agree < 16) {
             if (pos % seg == 0) agree = 0;
             const double P = hp[pos];
-            const int best = dither_step(L, P, s_pal, s_palw, K, lane);
+            const int best = dither_step(L, P, s_pal, s_palw, K, lane, G);
             const uint32_t old = hidx[pos];
             if ((uint32_t)best == old) agree++;
             else { agree = 0; if (lane == 0) hidx[pos] = (uint32_t)best; }
@@ -255,6 +310,9 @@ __global__ void __launch_bounds__(32) k_riemersma_repair(const double *__restric
 }
 
 } // namespace
+
+static bool g_dither_grid = true; // patolette_b200_set_option "dither_grid"
+void pb_dither_set_grid(bool on) { g_dither_grid = on; }
 
 void pb_dither_riemersma(const double *const planes[3], size_t width, size_t height,
                          const std::vector<double> &pal_rm, unsigned long long *d_map, int sm_count,
@@ -283,11 +341,12 @@ void pb_dither_riemersma(const double *const planes[3], size_t width, size_t hei
         palw[3 * j + 2] = pal_rm[3 * j + 2] * fz;
     }
     double *d_h[3] = {nullptr, nullptr, nullptr}, *d_pal = nullptr, *d_palw = nullptr, *d_qw = nullptr;
+    void *d_grid = nullptr;
     uint32_t *d_rank = nullptr, *d_hidx = nullptr, *d_overlap = nullptr;
     unsigned long long *d_stats = nullptr;
     auto cleanup = [&]() {
         for (int j = 0; j < 3; j++) pb_pool_free(d_h[j]);
-        pb_pool_free(d_pal); pb_pool_free(d_palw); pb_pool_free(d_qw); pb_pool_free(d_rank); pb_pool_free(d_hidx); pb_pool_free(d_overlap); pb_pool_free(d_stats);
+        pb_pool_free(d_pal); pb_pool_free(d_palw); pb_pool_free(d_qw); pb_pool_free(d_rank); pb_pool_free(d_hidx); pb_pool_free(d_overlap); pb_pool_free(d_stats); pb_pool_free(d_grid);
     };
     try {
         for (int j = 0; j < 3; j++) d_h[j] = (double *)pb_pool_alloc(n * sizeof(double));
@@ -321,13 +380,22 @@ void pb_dither_riemersma(const double *const planes[3], size_t width, size_t hei
             PB_CUDA_OK(cudaFuncSetAttribute(k_riemersma_spec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             PB_CUDA_OK(cudaFuncSetAttribute(k_riemersma_repair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         }
+        // candidate lists over the weighted query space: the pixels' box scaled by the sqrt-luma weights and
+        // widened by a quarter of its range on every side (queries = pixel + diffused error; a query that
+        // still falls outside searches all K entries)
+        if (g_dither_grid && K >= 64 && K <= 4096 && n >= 16384) {
+            d_grid = pb_pool_alloc(pb_nngrid_scratch_bytes(K));
+            const double cw[3] = {0.51254268114958, 0.8234075540095561, 0.2435159132377184};
+            const double *hp[3] = {d_h[0], d_h[1], d_h[2]};
+            pb_launch_nngrid_build(hp, n, d_palw, K, d_grid, sm_count, st, cw, 0.25);
+        }
         { PbProfScope _prof("k_riemersma_spec", st);
         k_riemersma_spec<<<(unsigned)((nseg + DT_WARPS - 1) / DT_WARPS), DT_WARPS * 32, smem, st>>>(
-            d_h[0], d_h[1], d_h[2], n, seg, warm, d_pal, d_palw, K, d_qw, d_hidx, d_overlap);
+            d_h[0], d_h[1], d_h[2], n, seg, warm, d_pal, d_palw, K, d_qw, d_hidx, d_overlap, d_grid);
         }
         { PbProfScope _prof("k_riemersma_repair", st);
         k_riemersma_repair<<<1, 32, smem, st>>>(d_h[0], d_h[1], d_h[2], n, seg, d_pal, d_palw, K, d_qw, d_hidx,
-                                                d_overlap, d_stats);
+                                                d_overlap, d_stats, d_grid);
         }
         { PbProfScope _prof("k_unpermute", st);
         k_unpermute<<<grid, 256, 0, st>>>(d_rank, d_hidx, n, d_map);

@@ -92,8 +92,10 @@ void pb_launch_nearest(const double *const planes[3], size_t n, const double *d_
                        unsigned long long *d_map, int sm_count, cudaStream_t st);
 // exact 1-NN through per-cell candidate lists (pb_nngrid.cu): same map as pb_launch_nearest
 size_t pb_nngrid_scratch_bytes(int K);
+// scratch layout: PbGridHdr (256 B) | u16 count[4096] | u16 list[4096][K].  `scale` (nullptr = 1) maps pixel space to
+// query space, `expand` widens the pixels' box by that fraction of its range on every side.
 void pb_launch_nngrid_build(const double *const planes[3], size_t n, const double *d_palette_rm, int K, void *d_scratch,
-                            int sm_count, cudaStream_t st);
+                            int sm_count, cudaStream_t st, const double *scale = nullptr, double expand = 0.0);
 void pb_launch_nearest_grid(const double *const planes[3], size_t n, const double *d_palette_rm, int K, const void *d_scratch,
                             unsigned long long *d_map, int sm_count, cudaStream_t st);
 void pb_launch_labels(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t max_n,

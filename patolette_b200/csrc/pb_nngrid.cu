@@ -22,19 +22,20 @@
 // the box by rounding) take the brute-force loop.
 #include "pb_common.cuh"
 #include "pb_kernels.h"
+#include "pb_nngrid.cuh"
 #include "pb_prof.h"
 
 namespace {
 
-constexpr int NG = 16;               // cells per dimension
-constexpr int NCELL = NG * NG * NG;
+constexpr int NG = PB_NG;
+constexpr int NCELL = PB_NCELL;
+using GridHdr = PbGridHdr;
+using GridGeom = PbGridGeom;
+__device__ __forceinline__ GridGeom grid_geom(const GridHdr *h) { return pb_grid_geom(h); }
 
-struct GridHdr {
-    unsigned long long mn[3], mx[3]; // order-encoded extrema of the pixel planes (k_nn_bbox)
-};
-
-__global__ void k_nn_bbox_init(GridHdr *h) {
+__global__ void k_nn_bbox_init(GridHdr *h, double s0, double s1, double s2, double expand) {
     if (threadIdx.x < 3) { h->mn[threadIdx.x] = ~0ULL; h->mx[threadIdx.x] = 0ULL; }
+    if (threadIdx.x == 0) { h->scale[0] = s0; h->scale[1] = s1; h->scale[2] = s2; h->expand = expand; }
 }
 
 __global__ void __launch_bounds__(256) k_nn_bbox(const double *__restrict__ c0, const double *__restrict__ c1,
@@ -60,28 +61,6 @@ __global__ void __launch_bounds__(256) k_nn_bbox(const double *__restrict__ c0, 
         }
         if ((threadIdx.x & 31) == 0) { atomicMin(&h->mn[d], mn[d]); atomicMax(&h->mx[d], mx[d]); }
     }
-}
-
-struct GridGeom {
-    double lo[3], w[3], inv[3]; // cell c of dimension d covers [lo + c*w, lo + (c+1)*w]
-    double cmax[3];             // largest |coordinate| of the pixels
-    bool ok;
-};
-__device__ __forceinline__ GridGeom grid_geom(const GridHdr *h) {
-    GridGeom g;
-    g.ok = true;
-    for (int d = 0; d < 3; d++) {
-        if (h->mn[d] > h->mx[d]) { g.ok = false; g.lo[d] = g.w[d] = g.inv[d] = g.cmax[d] = 0; continue; } // no finite pixel
-        const double a = pb_ord_decode(h->mn[d]), b = pb_ord_decode(h->mx[d]);
-        double range = b - a;
-        if (!(range > 1e-300)) range = 1e-300; // one colour along this axis
-        if (!(range < 1e300) || !(a > -1e300) || !(b < 1e300)) g.ok = false;
-        g.lo[d] = a;
-        g.cmax[d] = fabs(a) > fabs(b) ? fabs(a) : fabs(b);
-        g.w[d] = range / NG;
-        g.inv[d] = NG / range;
-    }
-    return g;
 }
 
 // one CTA per cell: candidate list in ascending palette index
@@ -157,13 +136,10 @@ __global__ void __launch_bounds__(256) k_nearest_grid(const double *__restrict__
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const double x = c0[i], y = c1[i], z = c2[i];
-        const double fx = (x - g.lo[0]) * g.inv[0], fy = (y - g.lo[1]) * g.inv[1], fz = (z - g.lo[2]) * g.inv[2];
         double bd = 0.0;
         int best = 0;
-        // inside the grid (the comparisons are false for NaN)?
-        if (g.ok && fx >= 0.0 && fy >= 0.0 && fz >= 0.0 && fx <= (double)NG && fy <= (double)NG && fz <= (double)NG) {
-            const int ix = min((int)fx, NG - 1), iy = min((int)fy, NG - 1), iz = min((int)fz, NG - 1);
-            const int cell = (ix * NG + iy) * NG + iz;
+        const int cell = pb_grid_cell(g.ok, g.lo, g.inv, x, y, z);
+        if (cell >= 0) {
             const int m = cnt[cell];
             const unsigned short *L = list + (size_t)cell * K;
             for (int t = 0; t < m; t++) {
@@ -192,12 +168,12 @@ size_t pb_nngrid_scratch_bytes(int K) { return 256 + (size_t)NCELL * 2 + (size_t
 
 // pixels -> bounding box -> per-cell candidate lists (d_scratch: pb_nngrid_scratch_bytes(K))
 void pb_launch_nngrid_build(const double *const planes[3], size_t n, const double *d_palette_rm, int K, void *d_scratch,
-                            int sm_count, cudaStream_t st) {
+                            int sm_count, cudaStream_t st, const double *scale, double expand) {
     GridHdr *hdr = (GridHdr *)d_scratch;
     unsigned short *cnt = (unsigned short *)((char *)d_scratch + 256);
     unsigned short *list = cnt + NCELL;
     { PbProfScope _prof("k_nn_bbox", st, false);
-      k_nn_bbox_init<<<1, 32, 0, st>>>(hdr);
+      k_nn_bbox_init<<<1, 32, 0, st>>>(hdr, scale ? scale[0] : 1.0, scale ? scale[1] : 1.0, scale ? scale[2] : 1.0, expand);
       size_t want = (n + 256 * 8 - 1) / (256 * 8), cap = (size_t)sm_count * 8;
       k_nn_bbox<<<(int)(want < cap ? (want ? want : 1) : cap), 256, 0, st>>>(planes[0], planes[1], planes[2], n, hdr); }
     { PbProfScope _prof("k_nn_cells", st, false);

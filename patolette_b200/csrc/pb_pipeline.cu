@@ -918,6 +918,7 @@ int patolette_b200_set_option(const char *name, long long value) {
     if (!strcmp(name, "dump_cap")) { pb_ordered_set_dump_cap(value); return 0; }
     if (!strcmp(name, "overlap")) { g_overlap_override = (int)value; return 0; }
     if (!strcmp(name, "nn_grid")) { g_nn_grid = value != 0; return 0; }
+    if (!strcmp(name, "dither_grid")) { pb_dither_set_grid(value != 0); return 0; }
     return -1;
 }
 

@@ -16,3 +16,5 @@ void pb_kmeans_device(const float *d_x0, const float *d_x1, const float *d_x2, c
 void pb_dither_riemersma(const double *const planes[3], size_t width, size_t height,
                          const std::vector<double> &pal_rm, unsigned long long *d_map, int sm_count,
                          cudaStream_t st, long *launches);
+// test knob: candidate-list nearest-neighbour search inside the dither (default on)
+void pb_dither_set_grid(bool on);

@@ -220,6 +220,34 @@ def test_dither_matches_oracle(cuda_lib, oracle, W, H, K):
     assert np.array_equal(a, b), f"{int((a != b).sum())} of {n} indices differ, first at {int(np.argmax(a != b))}"
 
 
+@pytest.mark.parametrize("kind", ["in_gamut", "palette_off_to_one_side", "narrow"])
+def test_dither_candidate_lists_equal_brute_force(cuda_lib, oracle, kind):
+    """The dither's per-step exact search through the per-cell candidate lists against its own brute force and
+    the oracle: a palette that covers the pixels, one that sits off to one side (errors accumulate and the
+    queries leave the grid: fallback path), and a pixel range tiny next to the coordinates."""
+    W, H, K = 320, 200, 128
+    n = W * H
+    rng = np.random.default_rng(len(kind) + 40)
+    if kind == "in_gamut":
+        px = rng.random((n, 3)); pal = rng.random((K, 3))
+    elif kind == "palette_off_to_one_side":
+        px = rng.random((n, 3)); pal = rng.random((K, 3)) * 0.3
+    else:
+        px = 0.4 + 1e-7 * rng.random((n, 3)); pal = 0.4 + 1e-7 * rng.random((K, 3))
+    planar = np.asfortranarray(px)
+    got = np.full(n, 7, dtype=np.uintp); brute = np.full(n, 7, dtype=np.uintp); want = np.full(n, 7, dtype=np.uintp)
+    assert cuda_lib.patolette_b200_dither(planar.ctypes.data, W, H, pal.ctypes.data, K, got.ctypes.data) == 0
+    try:
+        assert cuda_lib.patolette_b200_set_option(b"dither_grid", 0) == 0
+        assert cuda_lib.patolette_b200_dither(planar.ctypes.data, W, H, pal.ctypes.data, K, brute.ctypes.data) == 0
+    finally:
+        cuda_lib.patolette_b200_set_option(b"dither_grid", 1)
+    oracle.lib.orc_dither_riemersma(planar.ctypes.data_as(C.c_void_p), C.c_size_t(W), C.c_size_t(H), pal.ctypes.data_as(C.c_void_p),
+                                    C.c_size_t(K), want.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(got, brute), f"{int((got != brute).sum())} indices differ from the brute-force search"
+    assert np.array_equal(got, want), f"{int((got != want).sum())} indices differ from the oracle"
+
+
 # ---------------------------------------------------------------------------------- end to end
 @pytest.mark.parametrize("name", sorted(GOLDEN_CASES))
 def test_pipeline_matches_golden_and_oracle(cuda_lib, oracle, golden, name):
