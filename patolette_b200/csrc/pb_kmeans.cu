@@ -158,12 +158,23 @@ __global__ void __launch_bounds__(256) k_assign(const float *__restrict__ x0, co
     }
 }
 
-constexpr int KM_TILE = 64;
+constexpr int KM_TILE = 128;
+constexpr int KM_PER = KM_TILE / 32;
 constexpr int KM_WARPS = 4;
+
+// (x0, x1, x2, w) of every sample interleaved: the centroid chains GATHER the members of a cluster, and one
+// 16-byte sector access per member replaces four 4-byte ones (same idea as the f64 bucket sums, pb_chain.cu)
+__global__ void k_pack_samples(const float *__restrict__ x0, const float *__restrict__ x1, const float *__restrict__ x2,
+                               const float *__restrict__ wf, size_t nx, float4 *__restrict__ aos) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nx; i += (size_t)gridDim.x * blockDim.x)
+        aos[i] = make_float4(x0[i], x1[i], x2[i], wf ? wf[i] : 1.0f);
+}
+
 // One warp per centroid: lanes 0..3 chain {hassign, c0, c1, c2} in sample order (Clustering.cpp:178-187).
+// Every term is formed by the gathering lanes; the gather of tile t+1 sits in registers during the chain
+// over tile t.
 template <bool WEIGHTED>
-__global__ void __launch_bounds__(KM_WARPS * 32) k_centroid_chains(const float *__restrict__ x0, const float *__restrict__ x1,
-                                                                   const float *__restrict__ x2, const float *__restrict__ wf,
+__global__ void __launch_bounds__(KM_WARPS * 32) k_centroid_chains(const float4 *__restrict__ aos,
                                                                    const uint32_t *__restrict__ ord,
                                                                    const uint32_t *__restrict__ class_start, int K,
                                                                    float *__restrict__ out /* K x 4 */,
@@ -176,27 +187,34 @@ __global__ void __launch_bounds__(KM_WARPS * 32) k_centroid_chains(const float *
     float(*sm)[KM_TILE + 1] = sm_all[warp];
     const uint32_t beg = class_start[c], end = class_start[c + 1];
     float acc = 0.f;
+    float4 g[KM_PER];
+    auto gather = [&](uint32_t i0) {
+#pragma unroll
+        for (int q = 0; q < KM_PER; q++) {
+            const uint32_t i = i0 + q * 32 + lane;
+            g[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < end) g[q] = aos[ord[i]];
+        }
+    };
+    if (beg < end) gather(beg);
     for (uint32_t i0 = beg; i0 < end; i0 += KM_TILE) {
         const uint32_t cnt = min((uint32_t)KM_TILE, end - i0);
 #pragma unroll
-        for (int q = 0; q < KM_TILE / 32; q++) {
-            const uint32_t e = q * 32 + lane;
-            if (e < cnt) {
-                const uint32_t p = ord[i0 + e];
-                sm[0][e] = WEIGHTED ? wf[p] : 1.0f;
-                sm[1][e] = x0[p]; sm[2][e] = x1[p]; sm[3][e] = x2[p];
-            }
+        for (int q = 0; q < KM_PER; q++) {
+            const int e = q * 32 + lane;
+            const float w = g[q].w;
+            // hassign += w ; c[j] += x[j] * w   (unweighted: += 1.0 ; += x[j])
+            sm[0][e] = WEIGHTED ? w : 1.0f;
+            sm[1][e] = WEIGHTED ? __fmul_rn(g[q].x, w) : g[q].x;
+            sm[2][e] = WEIGHTED ? __fmul_rn(g[q].y, w) : g[q].y;
+            sm[3][e] = WEIGHTED ? __fmul_rn(g[q].z, w) : g[q].z;
         }
         __syncwarp();
+        if (i0 + KM_TILE < end) gather(i0 + KM_TILE);
         if (lane < 4) {
             const float *vp = sm[lane];
-#pragma unroll 8
-            for (uint32_t e = 0; e < cnt; e++) {
-                const float w = sm[0][e];
-                // hassign += w ; c[j] += x[j] * w   (unweighted: += 1.0 ; += x[j])
-                const float term = lane == 0 ? w : (WEIGHTED ? __fmul_rn(vp[e], w) : vp[e]);
-                acc = __fadd_rn(acc, term);
-            }
+#pragma unroll 16
+            for (uint32_t e = 0; e < cnt; e++) acc = __fadd_rn(acc, vp[e]);
         }
         __syncwarp();
     }
@@ -252,6 +270,7 @@ void pb_kmeans_device(const float *d_x0, const float *d_x1, const float *d_x2, c
     uint32_t *d_cstart = mem.alloc<uint32_t>((size_t)K + 1);
     float *d_cen = mem.alloc<float>((size_t)K * 3);
     float *d_sums = mem.alloc<float>((size_t)K * 4);
+    float4 *d_aos = mem.alloc<float4>(nx);
     PbSeg *d_seg = mem.alloc<PbSeg>(1);
     PbSeg whole{0u, (uint32_t)nx, 0u, 0u};
     PB_CUDA_OK(cudaMemcpyAsync(d_seg, &whole, sizeof whole, cudaMemcpyHostToDevice, st));
@@ -261,6 +280,8 @@ void pb_kmeans_device(const float *d_x0, const float *d_x1, const float *d_x2, c
     if (smem > 48 * 1024)
         PB_CUDA_OK(cudaFuncSetAttribute(k_assign, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int *d_stop = mem.alloc<int>(1);
+    { PbProfScope _prof("k_pack_samples", st, false);
+      k_pack_samples<<<grid, 256, 0, st>>>(d_x0, d_x1, d_x2, d_wf, nx, d_aos); }
     std::vector<float> sums((size_t)K * 4);
     // All iterations are enqueued back to back (Clustering.cpp:442-530); the centroid epilogue runs on the
     // device.  Only an empty cluster (rare) hands control back to the host for faiss' split protocol.
@@ -278,8 +299,8 @@ void pb_kmeans_device(const float *d_x0, const float *d_x1, const float *d_x2, c
                                   d_cstart, d_ord, st);
             const int cg = (K + KM_WARPS - 1) / KM_WARPS;
             { PbProfScope _prof("k_centroid_chains", st);
-            if (d_wf) k_centroid_chains<true><<<cg, KM_WARPS * 32, 0, st>>>(d_x0, d_x1, d_x2, d_wf, d_ord, d_cstart, K, d_sums, d_stop);
-            else k_centroid_chains<false><<<cg, KM_WARPS * 32, 0, st>>>(d_x0, d_x1, d_x2, d_wf, d_ord, d_cstart, K, d_sums, d_stop);
+            if (d_wf) k_centroid_chains<true><<<cg, KM_WARPS * 32, 0, st>>>(d_aos, d_ord, d_cstart, K, d_sums, d_stop);
+            else k_centroid_chains<false><<<cg, KM_WARPS * 32, 0, st>>>(d_aos, d_ord, d_cstart, K, d_sums, d_stop);
             }
             { PbProfScope _prof("k_finalize_centroids", st, false);
             k_finalize_centroids<<<1, 256, 0, st>>>(d_sums, K, i, d_cen, d_stop);
