@@ -13,8 +13,10 @@ K=256, ICtCp, dither off, kmeans off.
   e2e    : same metric through the reference-facing C ABI patolette() with HOST buffers (pinned),
            host->device and device->host copies inside the timed region.
   roofline: the dominant kernel of the step (by accumulated CUDA-event time from the library's
-           per-kernel profiler, measured in a separate untimed profiling step), algorithmic bytes
-           / duration against MEASURED_PEAKS.json.
+           per-kernel profiler, measured in a separate untimed profiling step on one stream), algorithmic
+           bytes / duration against MEASURED_PEAKS.json; `roofline.stages` gives the same for the covariance
+           stage as a whole (all k_ord_* kernels), the assignment kernel and the projection/sort/partition
+           group; `traffic` is the ncu DRAM byte count per launch of that kernel (profiles/r01_ncu_summary.json).
   cpu_baseline: the reference's own code (oracle/_ref) - or the oracle port when the prebuilt
            .so is absent - timed on this box's host cores on a bounded sample (rank 0, N=1).
 

@@ -15,3 +15,4 @@ print(round(d['value'],1),'Mpx/s', round(d['ms_per_step'],2),'ms  e2e', round(d[
 print({n:k[n]['ms'] for n in k}); print(d['roofline']['stages'])
 for l in open('gpurun_out/${tag}_full_configs.jsonl'): print(l[:1200])
 PY
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${tag}_smoke.log 2>&1; tail -2 gpurun_out/${tag}_smoke.log
