@@ -535,37 +535,54 @@ __device__ __forceinline__ size_t group_row(const PbSeg &sg, int C, int seg, int
     return ((size_t)sg.bbase * C + (size_t)chain * nblk) / 32 + (size_t)chain + (size_t)seg * (C + 1);
 }
 
-// Besides the group record, every record i gets a RUN record: the composition of the maximal run of plain
-// records of one unit that starts at i (inside its group) and its length - a backward segmented scan, done
-// here in parallel for all groups.  The sequential walk then crosses a whole run with one interval check.
+// Besides the group record, every record i gets a RUN record: the composition of the maximal run of usable
+// records (plain or two-parity) of one unit that starts at i (inside its group) and its length - a backward
+// segmented scan of the two-state transducer, done here in parallel for all groups.  The sequential walk
+// then crosses a whole run with one interval check on the variant its state's parity selects.
+__device__ __forceinline__ PbSpan2 shfl_down_span2(const PbSpan2 &v, int o) {
+    PbSpan2 r;
+    r.p[0] = shfl_down_span(v.p[0], o);
+    r.p[1] = shfl_down_span(v.p[1], o);
+    return r;
+}
+
 template <int KIND, bool W>
 __global__ void __launch_bounds__(32 * NChains<KIND>::C) k_ord_group(const PbSeg *__restrict__ segs,
                                                                      const OrdRec *__restrict__ rec0,
-                                                                     OrdRec *__restrict__ grec, OrdRec *__restrict__ rrec) {
+                                                                     const OrdRec *__restrict__ rec1,
+                                                                     OrdRec *__restrict__ grec, OrdRec *__restrict__ rrec0,
+                                                                     OrdRec *__restrict__ rrec1) {
     constexpr int C = NChains<KIND>::C;
     const int seg = blockIdx.y, chain = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const PbSeg sg = segs[seg];
     const uint32_t nblk = (sg.n + OB - 1) / OB, g0 = blockIdx.x * 32;
     if (g0 >= nblk || !chain_live<KIND, W>(chain)) return;
     const uint32_t gcnt = min(32u, nblk - g0);
-    PbSpan v = pb_span_identity();
-    int eref = 0, len = 0;
+    PbSpan2 v = pb_span2_identity();
+    int eref = 0, len = 0, flag = F_OK;
     const size_t row = rec_row(sg, C, chain, nblk, g0 + lane);
     if (lane < (int)gcnt) {
         const OrdRec r = rec0[row];
-        v.sum = r.sum; v.lo = r.lo; v.hi = r.hi;
+        v.p[0].sum = r.sum; v.p[0].lo = r.lo; v.p[0].hi = r.hi;
+        v.p[1] = v.p[0];
         eref = r.eref;
-        len = r.flag == F_OK ? 1 : 0;
+        flag = r.flag;
+        if (flag == F_SENSITIVE) {
+            const OrdRec q = rec1[row];
+            v.p[1].sum = q.sum; v.p[1].lo = q.lo; v.p[1].hi = q.hi;
+        }
+        len = (flag == F_OK || flag == F_SENSITIVE) ? 1 : 0;
     }
+    const bool all_plain = __all_sync(0xffffffffu, lane >= (int)gcnt || flag == F_OK);
     bool open = len > 0; // the run may still extend: then it covers exactly [lane, lane + o) at round o
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        const PbSpan pv = shfl_down_span(v, o);
+        const PbSpan2 pv = shfl_down_span2(v, o);
         const int plen = __shfl_down_sync(0xffffffffu, len, o), peref = __shfl_down_sync(0xffffffffu, eref, o);
         const bool popen = __shfl_down_sync(0xffffffffu, (int)open, o) != 0;
         if (open) {
             if (lane + o < 32 && plen > 0 && peref == eref) {
-                v = pb_span_cat(v, pv);
+                v = pb_span2_cat(v, pv);
                 len += plen;
                 open = popen;
             } else open = false;
@@ -573,14 +590,16 @@ __global__ void __launch_bounds__(32 * NChains<KIND>::C) k_ord_group(const PbSeg
     }
     if (lane < (int)gcnt) {
         OrdRec o;
-        o.sum = v.sum; o.lo = v.lo; o.hi = v.hi; o.eref = eref;
-        o.flag = len; // 0: record `lane` is not plain
-        rrec[row] = o;
+        o.sum = v.p[0].sum; o.lo = v.p[0].lo; o.hi = v.p[0].hi; o.eref = eref;
+        o.flag = len; // 0: record `lane` cannot be applied from its summary
+        rrec0[row] = o;
+        o.sum = v.p[1].sum; o.lo = v.p[1].lo; o.hi = v.p[1].hi;
+        rrec1[row] = o;
     }
-    if (lane == 0) {
+    if (lane == 0) { // the group record serves the plain level-2 scan: only groups without two-parity records
         OrdRec o;
-        o.sum = v.sum; o.lo = v.lo; o.hi = v.hi; o.eref = eref;
-        o.flag = (len == (int)gcnt && pb_span_valid(v)) ? F_OK : F_REPLAY;
+        o.sum = v.p[0].sum; o.lo = v.p[0].lo; o.hi = v.p[0].hi; o.eref = eref;
+        o.flag = (all_plain && len == (int)gcnt && pb_span_valid(v.p[0])) ? F_OK : F_REPLAY;
         grec[group_row(sg, C, seg, chain, nblk) + blockIdx.x] = o;
     }
 }
@@ -686,6 +705,7 @@ __global__ void __launch_bounds__(32 * NChains<KIND>::C) k_ord_resolve(PbPlanes 
                                                                        const OrdRec *__restrict__ rec1,
                                                                        const OrdRec *__restrict__ grec,
                                                                        const OrdRec *__restrict__ rrec,
+                                                                       const OrdRec *__restrict__ rrec1,
                                                                        const double *__restrict__ dump_terms,
                                                                        bool use_summaries) {
     constexpr int C = NChains<KIND>::C;
@@ -722,34 +742,42 @@ __global__ void __launch_bounds__(32 * NChains<KIND>::C) k_ord_resolve(PbPlanes 
         }
         // ---- level 1: the records of one group --------------------------------------------------------
         const uint32_t gcnt = min(32u, nblk - g0);
-        OrdRec r = dummy, r1 = dummy, rr = dummy; // r1 is only meaningful where r.flag == F_SENSITIVE
+        OrdRec r = dummy, r1 = dummy, rr = dummy, rq = dummy; // r1 is only meaningful where r.flag == F_SENSITIVE
         rr.flag = 0;
         if (use_summaries && lane < (int)gcnt) {
             r = rec0[row0 + g0 + lane];
             rr = rrec[row0 + g0 + lane];
+            rq = rrec1[row0 + g0 + lane];
             if (r.flag == F_SENSITIVE) r1 = rec1[row0 + g0 + lane];
         }
         uint32_t next = 0;
         while (next < gcnt) {
             long long t0 = clock64();
-            const int run = __shfl_sync(0xffffffffu, rr.flag, (int)next); // length of the plain run that starts here
+            const int run = __shfl_sync(0xffffffffu, rr.flag, (int)next); // length of the usable run that starts here
             if (run > 0) {
-                // the whole run with one interval check (its composition was prepared by k_ord_group) ...
+                // the whole run with one interval check on the variant the state's parity selects (its
+                // composition was prepared by k_ord_group) ...
                 const int er = __shfl_sync(0xffffffffu, rr.eref, (int)next);
-                const long long rsum = __shfl_sync(0xffffffffu, rr.sum, (int)next), rlo = __shfl_sync(0xffffffffu, rr.lo, (int)next),
-                                rhi = __shfl_sync(0xffffffffu, rr.hi, (int)next);
                 uint32_t a = 0;
-                if (pb_state_rebase(st, er) && st.S >= rlo && st.S <= rhi) { // (an empty interval has lo > hi)
-                    st.S += rsum;
-                    a = (uint32_t)run;
-                } else {
-                    a = scan_apply(r, gcnt, next, st, lane); // ... or as far as it goes, record by record
+                bool crossed = false;
+                if (pb_state_rebase(st, er)) {
+                    const OrdRec &pick = (st.S & 1LL) ? rq : rr; // warp-uniform choice
+                    const long long rsum = __shfl_sync(0xffffffffu, pick.sum, (int)next),
+                                    rlo = __shfl_sync(0xffffffffu, pick.lo, (int)next),
+                                    rhi = __shfl_sync(0xffffffffu, pick.hi, (int)next);
+                    if (st.S >= rlo && st.S <= rhi) { // (an empty interval has lo > hi)
+                        st.S += rsum;
+                        a = (uint32_t)run;
+                        crossed = true;
+                    }
                 }
+                if (!crossed && __shfl_sync(0xffffffffu, r.flag, (int)next) == F_OK)
+                    a = scan_apply(r, gcnt, next, st, lane); // ... or as far as the plain records go, one by one
                 n_acc += a;
                 next += a;
                 cyc[0] += clock64() - t0;
                 if (next >= gcnt) break;
-                if (a == (uint32_t)run) continue; // the next record starts another run or is special: look again
+                if (crossed) continue; // the next record starts another run or is unusable: look again
                 t0 = clock64();
             }
             // record `next` on its own (warp-uniform)
@@ -839,7 +867,7 @@ struct Scratch {
     OrdRec *rec0, *rec1;
     uint2 *list;
     unsigned int *list_count; // [0] work list of summary2, [1] dump slots
-    OrdRec *grec, *rrec;
+    OrdRec *grec, *rrec, *rrec1;
     Dump dump;
 };
 size_t group_rows(size_t total_blocks) { return total_blocks * 7 / 32 + 4096; } // + nseg * (C + 1), nseg <= 2 * 64
@@ -858,6 +886,7 @@ Scratch carve(void *d_scratch, size_t total_blocks) {
     s.rec1 = (OrdRec *)p; p += total_blocks * 7 * sizeof(OrdRec);
     s.grec = (OrdRec *)p; p += group_rows(total_blocks) * sizeof(OrdRec);
     s.rrec = (OrdRec *)p; p += total_blocks * 7 * sizeof(OrdRec);
+    s.rrec1 = (OrdRec *)p; p += total_blocks * 7 * sizeof(OrdRec);
     s.list = (uint2 *)p; p += total_blocks * 7 * sizeof(uint2);
     s.list_count = (unsigned int *)p;
     s.dump.count = s.list_count + 1;
@@ -898,10 +927,10 @@ void launch_pass(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t
         { PbProfScope p("k_ord_summary2", st, false);
           k_ord_summary2<KIND, W><<<148 * 16, OS_THREADS, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, sc.psum, sc.rec0, sc.rec1, sc.list_count, sc.list, sc.dump); }
         { PbProfScope p("k_ord_group", st, false);
-          k_ord_group<KIND, W><<<dim3((blk_cap + 31) / 32, nseg), 32 * C, 0, st>>>(d_segs, sc.rec0, sc.grec, sc.rrec); }
+          k_ord_group<KIND, W><<<dim3((blk_cap + 31) / 32, nseg), 32 * C, 0, st>>>(d_segs, sc.rec0, sc.rec1, sc.grec, sc.rrec, sc.rrec1); }
     }
     { PbProfScope p(KIND == KIND_MEAN ? "k_ord_resolve_mean" : "k_ord_resolve_centered", st, !speculative);
-      k_ord_resolve<KIND, W><<<nseg, 32 * C, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, sc.rec0, sc.rec1, sc.grec, sc.rrec, sc.dump.terms, speculative); }
+      k_ord_resolve<KIND, W><<<nseg, 32 * C, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, sc.rec0, sc.rec1, sc.grec, sc.rrec, sc.rrec1, sc.dump.terms, speculative); }
     PB_CUDA_OK(cudaGetLastError());
 }
 
@@ -929,7 +958,7 @@ uint32_t pb_ordered_blocks(uint32_t n) { return (n + OB - 1) / OB; }
 
 size_t pb_ordered_scratch_bytes(size_t total_blocks) {
     return dump_slots(total_blocks) * OB * sizeof(double) + group_rows(total_blocks) * sizeof(OrdRec) +
-           total_blocks * 7 * (sizeof(double) + 3 * sizeof(OrdRec) + sizeof(uint2)) + 256;
+           total_blocks * 7 * (sizeof(double) + 4 * sizeof(OrdRec) + sizeof(uint2)) + 256;
 }
 
 void pb_launch_pass_mean(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t max_n,
