@@ -12,19 +12,21 @@
 //   Speculate, summarise, verify.
 //     S1  k_ord_blocksum : plain (unordered) f64 sum of every block of OB elements, per chain.
 //     S2  k_ord_prefix   : approximate running total at each block start.
-//     S3  k_ord_summary  : approximate running sum at every ELEMENT -> predicted binade of every
-//                          partial sum; the block's unit is the ulp of the lowest one.  Each thread
-//                          turns its 8 consecutive elements into a span (integer translation +
+//     S3  k_ord_summary  : one warp per block, 16 consecutive elements per lane: approximate running sum at
+//                          every ELEMENT -> predicted binade of every partial sum; the block's unit is the ulp
+//                          of the lowest one.  Each lane turns its elements into a span (integer translation +
 //                          interval of start states for which every prediction is right), spans are
-//                          concatenated in element order (an associative monoid): one record per block.
-//     S3b k_ord_summary2 : blocks in which a step depends on the parity of the state (a tie, or a step
-//                          up from the lowest binade) are redone for both parities (work list).
-//     S4  k_ord_resolve  : one warp per chain walks the blocks in order with the exact state: 32 block
-//                          records at a time, in-order warp scan of the spans, ballot -> the first block
-//                          whose interval does not hold; everything before it is applied in one step,
-//                          that block is REPLAYED: the same idea with the exact binade at 16-element
-//                          granularity, down to the literal sequential loop for the sub-chunk where a
-//                          prediction breaks.
+//                          concatenated in element order (an associative monoid): one record per block and
+//                          chain.  Chains that cannot be summarised are flagged and their 512 terms written
+//                          to a dump slot for the replay.
+//     S3b k_ord_summary2 : (block, chain) pairs in which a step depends on the parity of the state (a tie, or
+//                          a step up from the lowest binade) are redone for both parities (work list).
+//     S3c k_ord_group    : 32 records -> one group record; for every record the composition of the run of
+//                          usable records that starts there (run record, both parities).
+//     S4  k_ord_resolve  : one warp per chain walks the blocks in order with the exact state (integer * unit):
+//                          32 group records at a time (scan + ballot), then inside a group run by run (one
+//                          interval check per run); a record that cannot be applied means its block is
+//                          REPLAYED: the literal sequential loop over its (dumped) terms.
 //   The predictions only decide SPEED: an accepted block is proven step by step to be what the
 //   sequential loop computes (every rounding used the right grid), everything else is the loop itself.
 //
@@ -191,7 +193,10 @@ __global__ void __launch_bounds__(32) k_ord_prefix(const PbSeg *__restrict__ seg
 // the in-order composition) and 30 % of the stall samples on instruction fetch: longer per-lane runs halve
 // the fixed share, rolled element loops keep the body inside the instruction cache, and a warp needs no
 // shared memory or CTA barrier to compose its block.)
-constexpr int OS_WARPS = 2;                 // blocks per CTA
+#ifndef PB_OS_WARPS
+#define PB_OS_WARPS 2
+#endif
+constexpr int OS_WARPS = PB_OS_WARPS;       // blocks per CTA
 constexpr int OS_THREADS = 32 * OS_WARPS;
 constexpr int OS_PER = OB / 32;             // consecutive elements per lane
 constexpr int OS_STRIDE = OS_PER + 1;       // padded lane stride of the staged planes (doubles)
