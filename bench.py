@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--side", type=int, default=0, help="override the image side (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard", action="store_true",
+                    help="N > 1: ONE image, ordered sums chain-sharded over the ranks (strong scaling) instead of replicas")
     return ap.parse_args()
 
 
@@ -183,7 +185,10 @@ def run_ours(args):
     w = h = side
     n = w * h
     K = WORKLOAD["K"]
-    colors = uniform_colors(w, h, WORKLOAD["seed"] + rank)          # every rank its own image (replicas)
+    shard = bool(args.shard and world > 1)
+    if shard:  # every rank the SAME image; moment rows exchanged over a gloo group (host bytes)
+        pb.set_sharding(rank, world, pb.torch_allgather(dist.new_group(backend="gloo")))
+    colors = uniform_colors(w, h, WORKLOAD["seed"] + (0 if shard else rank))  # replicas: every rank its own image
     planar = np.asfortranarray(colors)                               # [N,3] F-order == 3 planes
     opts = _lib.QuantizationOptions(False, False, WORKLOAD["color_space"], 0, 512 ** 2, False)
     code = C.c_int(0)
@@ -314,14 +319,16 @@ def run_ours(args):
         cpu_baseline, _ = time_reference(1536, 1, 0)
     line = {
         "metric": "Mpixels/s end-to-end quantize() at K=256",
-        "value": aggregate_throughput(n, world, ms_step), "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "value": aggregate_throughput(n, 1 if shard else world, ms_step), "unit": "Mpixels/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if shard else "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD["name"] if not args.side else f"{side}x{side} debug size", "K": K,
-                   "parallelism": "single GPU" if world == 1 else f"replicas x{world} (one image per rank, no collective)",
+                   "parallelism": "single GPU" if world == 1 else (
+                       f"chain-sharded x{world} (one image, ordered sums split by chain, moment rows all-gathered)" if shard
+                       else f"replicas x{world} (one image per rank, no collective)"),
                    "l2": "inputs (403 MB) larger than L2; no flush needed",
                    "mode": "exact (bit-identical to the reference CPU path)"},
-        "e2e": {"value": world * n / e2e_s / 1e6, "unit": "Mpixels/s", "h2d_bytes_per_step": 24 * n,
+        "e2e": {"value": (1 if shard else world) * n / e2e_s / 1e6, "unit": "Mpixels/s", "h2d_bytes_per_step": 24 * n,
                 "d2h_bytes_per_step": 8 * n + 24 * K, "ms_per_step": e2e_s * 1e3, "host_buffers": "pinned",
                 "stage_ms": {k: round(v, 3) for k, v in e2e_stage.items()}},
         "gpu_launches": launches * args.steps if launches else None,

@@ -125,6 +125,13 @@ PB200_API size_t patolette_b200_profile_json(char *buf, size_t cap);
  * through a two-parity record, SM cycles of the resolving warps in {scan walk, two-parity records,
  * replays}, record groups loaded, cycles of the slowest resolving warp, 3 spare. */
 PB200_API int patolette_b200_ordered_counts(unsigned long long *out16, int reset);
+/* Chain-sharded multi-GPU runs: every rank (process + GPU) is given the SAME image and calls
+ * patolette() at the same time; rank r computes the ordered sums of the chains it owns and the ranks exchange
+ * their per-cluster moment rows through `allgather`, which must gather `bytes` bytes from every rank into
+ * `recv` (world * bytes, rank-major) - host memory, any transport.  Results are identical for every world size.
+ * world = 1 (default) switches sharding off.  Returns 0, -1 on bad arguments. */
+typedef void (*patolette_b200_allgather_fn)(const void *send, void *recv, size_t bytes, void *user);
+PB200_API int patolette_b200_set_sharding(int rank, int world, patolette_b200_allgather_fn allgather, void *user);
 /* Test / tuning knobs (never change results, only the route taken): "dump_cap" = cap on the term-dump slots
  * of an ordered-sum pass (-1 default; 0 = every replay recomputes its terms from the planes), "overlap" =
  * two-stream half-batch evaluation of the split loop (-1 default, 0 off, 1 on), "nn_grid" / "dither_grid" = nearest

@@ -24,7 +24,8 @@ color_mismatch = "The number of colors doesn't match the supplied width and heig
 bad_channel_count = "Expected colors to be in sRGB[0, 1] space. Channel count mismatch: {} found."
 bad_tile_size = "tile_size parameter expected to be in the range [0, inf]"
 
-__all__ = ["__doc__", "__version__", "quantize", "ColorSpace_sRGB", "ColorSpace_CIELuv", "ColorSpace_ICtCp"]
+__all__ = ["__doc__", "__version__", "quantize", "ColorSpace_sRGB", "ColorSpace_CIELuv", "ColorSpace_ICtCp",
+           "set_sharding", "torch_allgather"]
 
 
 def quantize(width, height, colors, palette_size, dither=True, palette_only=False,
@@ -82,6 +83,52 @@ def quantize(width, height, colors, palette_size, dither=True, palette_only=Fals
     if palette_only:
         return (success, palette, None, message)
     return (success, palette, pmap, message)
+
+
+_shard_cb = None  # keeps the ctypes callback alive
+
+
+def set_sharding(rank: int, world: int, allgather=None) -> None:
+    """Chain-sharded multi-GPU runs (extension).  Every rank - one process per GPU - calls
+    ``quantize`` with the SAME image at the same time; the ordered sums are split over the ranks by chain and
+    the per-cluster moment rows are exchanged through ``allgather(send: bytes) -> bytes`` (the concatenation
+    of every rank's ``send``, rank-major; e.g. built on ``torch.distributed.all_gather``).  Results are
+    bit-identical for every world size.  ``world == 1`` switches sharding off."""
+    global _shard_cb
+    lib = _lib.load()
+    if world <= 1:
+        _shard_cb = None
+        if lib.patolette_b200_set_sharding(0, 1, None, None) != 0:
+            raise ValueError("bad sharding arguments")
+        return
+    if allgather is None:
+        raise ValueError("world > 1 needs an allgather callable")
+
+    @C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
+    def cb(send, recv, nbytes, _user):
+        out = allgather(C.string_at(send, nbytes))
+        if len(out) != nbytes * world:
+            raise RuntimeError("allgather returned %d bytes, expected %d" % (len(out), nbytes * world))
+        C.memmove(recv, out, len(out))
+
+    if lib.patolette_b200_set_sharding(int(rank), int(world), C.cast(cb, C.c_void_p), None) != 0:
+        raise ValueError("bad sharding arguments")
+    _shard_cb = cb
+
+
+def torch_allgather(group=None):
+    """An ``allgather`` for :func:`set_sharding` on top of torch.distributed (host tensors: use a gloo group, or
+    the default group when it is gloo)."""
+    import torch
+    import torch.distributed as dist
+
+    def allgather(send: bytes) -> bytes:
+        t = torch.frombuffer(bytearray(send), dtype=torch.uint8)
+        outs = [torch.empty_like(t) for _ in range(dist.get_world_size(group))]
+        dist.all_gather(outs, t, group=group)
+        return b"".join(o.numpy().tobytes() for o in outs)
+
+    return allgather
 
 
 def last_timings() -> dict:

@@ -35,12 +35,14 @@ void pb_ordered_counts(unsigned long long out[16], bool reset);
 void pb_ordered_chain_debug(unsigned long long out[35], bool reset);
 // test knob: cap on the term-dump slots of a pass (-1 = default); blocks beyond it are replayed from the planes
 void pb_ordered_set_dump_cap(long long slots);
+// cmask: bit c set = chain c is summed by this call (chain-sharded multi-GPU runs split the chains over the
+// ranks; the other fields of PbStats are left as they are).  raw_mean: leave sum(c_j * w) unscaled in mean[].
 void pb_launch_pass_mean(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t max_n,
                          uint32_t total_blocks, bool weighted, PbStats *d_stats, void *d_scratch,
-                         size_t scratch_bytes, cudaStream_t st);
+                         size_t scratch_bytes, cudaStream_t st, unsigned cmask = ~0u, bool raw_mean = false);
 void pb_launch_pass_centered(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t max_n,
                              uint32_t total_blocks, bool weighted, PbStats *d_stats, void *d_scratch,
-                             size_t scratch_bytes, cudaStream_t st);
+                             size_t scratch_bytes, cudaStream_t st, unsigned cmask = ~0u);
 // Per-bucket ordered sums over bucket-sorted position lists.
 //   LQ (local.c:102-146): out[seg][b] = {size (as double bits of u64), sum c0*w, sum c1*w, sum c2*w}
 //   GQ (cells.c:53-116):  out[b] = {sum c0, c1, c2, sum |c|^2, sums c_r*c_s (r<=s: 00,01,11,02,12,22)}

@@ -131,7 +131,7 @@ __device__ __forceinline__ double block_reduce_sum(double v, double *sm /* [OB_T
 template <int KIND, bool W>
 __global__ void __launch_bounds__(OB_THREADS) k_ord_blocksum(PbPlanes b0, PbPlanes b1, const PbSeg *__restrict__ segs,
                                                              const PbStats *__restrict__ stats,
-                                                             double *__restrict__ psum) {
+                                                             double *__restrict__ psum, unsigned cmask) {
     constexpr int C = NChains<KIND>::C;
     __shared__ double red[OB_THREADS / 32];
     const int seg = blockIdx.y;
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(OB_THREADS) k_ord_blocksum(PbPlanes b0, PbPlan
     double *out = psum + ((size_t)sg.bbase + blockIdx.x) * C;
 #pragma unroll
     for (int c = 0; c < C; c++) {
-        if (!chain_live<KIND, W>(c)) continue;
+        if (!chain_live<KIND, W>(c) || !(cmask >> c & 1u)) continue; // (cmask: chains this rank owns, CTA-uniform)
         const double r = block_reduce_sum(acc[c], red);
         if (threadIdx.x == 0) out[c] = r;
     }
@@ -166,8 +166,10 @@ __global__ void __launch_bounds__(OB_THREADS) k_ord_blocksum(PbPlanes b0, PbPlan
 
 // ---- S2: approximate exclusive prefix per chain (in place over the block sums) ------------------
 template <int C>
-__global__ void __launch_bounds__(32) k_ord_prefix(const PbSeg *__restrict__ segs, double *__restrict__ psum, int first_chain) {
+__global__ void __launch_bounds__(32) k_ord_prefix(const PbSeg *__restrict__ segs, double *__restrict__ psum, int first_chain,
+                                                   unsigned cmask) {
     const int seg = blockIdx.y, c = blockIdx.x + first_chain, lane = threadIdx.x;
+    if (!(cmask >> c & 1u)) return;
     const uint32_t nblk = (segs[seg].n + OB - 1) / OB;
     double *io = psum + (size_t)segs[seg].bbase * C + c;
     const uint32_t per = (nblk + 31) / 32;
@@ -250,14 +252,14 @@ template <int KIND, bool W, int NV, int NC>
 __device__ __forceinline__ unsigned summarise_block(const PbPlanes &P, const PbSeg &sg, uint32_t blk, int ch0, double m0,
                                                     double m1, double m2, const double *__restrict__ pstart,
                                                     OrdRec *__restrict__ rec0, OrdRec *__restrict__ rec1, const Dump &dump,
-                                                    double *stage /* this warp's [3 or 4][OS_PLANE] */) {
+                                                    double *stage /* this warp's [3 or 4][OS_PLANE] */, unsigned cmask) {
     constexpr int C = NChains<KIND>::C;
     constexpr int NOLEVEL = -(1 << 20);
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int OS_UNROLL = NC == 1 ? 4 : (KIND == KIND_MEAN ? PB_OS_UNROLL_MEAN : PB_OS_UNROLL_CEN);
     static_assert(NC == 1 || NC == C, "all chains or one");
     auto chain_of = [&](int slot) { return NC == 1 ? ch0 : slot; };
-    auto live = [&](int slot) { return NC == 1 ? true : chain_live<KIND, W>(slot); };
+    auto live = [&](int slot) { return NC == 1 ? true : (chain_live<KIND, W>(slot) && (cmask >> slot & 1u)); };
     const uint32_t nblk = (sg.n + OB - 1) / OB;
     const int lane = threadIdx.x & 31;
     const uint32_t i0 = blk * OB + lane * OS_PER; // this lane's consecutive elements
@@ -487,7 +489,7 @@ __global__ void __launch_bounds__(OS_THREADS, PB_OS_MINB) k_ord_summary(PbPlanes
                                                             const PbStats *__restrict__ stats,
                                                             const double *__restrict__ psum, OrdRec *__restrict__ rec0,
                                                             unsigned int *__restrict__ list_count,
-                                                            uint2 *__restrict__ list, Dump dump) {
+                                                            uint2 *__restrict__ list, Dump dump, unsigned cmask) {
     constexpr int C = NChains<KIND>::C;
     __shared__ double stage[OS_WARPS][summary_staged<KIND, C>() ? (W ? 4 : 3) * OS_PLANE : 1];
     const int seg = blockIdx.y;
@@ -498,7 +500,7 @@ __global__ void __launch_bounds__(OS_THREADS, PB_OS_MINB) k_ord_summary(PbPlanes
     double m0 = 0, m1 = 0, m2 = 0;
     if (KIND == KIND_CENTERED) { m0 = stats[seg].mean[0]; m1 = stats[seg].mean[1]; m2 = stats[seg].mean[2]; }
     const unsigned pending = summarise_block<KIND, W, 1, C>(P, sg, blk, 0, m0, m1, m2, psum + ((size_t)sg.bbase + blk) * C,
-                                                            rec0, nullptr, dump, stage[threadIdx.x >> 5]);
+                                                            rec0, nullptr, dump, stage[threadIdx.x >> 5], cmask);
     if ((threadIdx.x & 31) == 0 && pending) { // one work item per (block, chain): block index < 2^28
         const unsigned int at = atomicAdd(list_count, (unsigned)__popc(pending));
         unsigned int k = 0;
@@ -527,7 +529,7 @@ __global__ void __launch_bounds__(OS_THREADS) k_ord_summary2(PbPlanes b0, PbPlan
         double m0 = 0, m1 = 0, m2 = 0;
         if (KIND == KIND_CENTERED) { m0 = stats[seg].mean[0]; m1 = stats[seg].mean[1]; m2 = stats[seg].mean[2]; }
         summarise_block<KIND, W, 2, 1>(P, sg, blk, chain, m0, m1, m2, psum + ((size_t)sg.bbase + blk) * C, rec0, rec1, dump,
-                                       stage[threadIdx.x >> 5]);
+                                       stage[threadIdx.x >> 5], ~0u);
     }
 }
 
@@ -556,12 +558,12 @@ __global__ void __launch_bounds__(32 * NChains<KIND>::C) k_ord_group(const PbSeg
                                                                      const OrdRec *__restrict__ rec0,
                                                                      const OrdRec *__restrict__ rec1,
                                                                      OrdRec *__restrict__ grec, OrdRec *__restrict__ rrec0,
-                                                                     OrdRec *__restrict__ rrec1) {
+                                                                     OrdRec *__restrict__ rrec1, unsigned cmask) {
     constexpr int C = NChains<KIND>::C;
     const int seg = blockIdx.y, chain = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const PbSeg sg = segs[seg];
     const uint32_t nblk = (sg.n + OB - 1) / OB, g0 = blockIdx.x * 32;
-    if (g0 >= nblk || !chain_live<KIND, W>(chain)) return;
+    if (g0 >= nblk || !chain_live<KIND, W>(chain) || !(cmask >> chain & 1u)) return;
     const uint32_t gcnt = min(32u, nblk - g0);
     PbSpan2 v = pb_span2_identity();
     int eref = 0, len = 0, flag = F_OK;
@@ -712,13 +714,14 @@ __global__ void __launch_bounds__(32 * NChains<KIND>::C) k_ord_resolve(PbPlanes 
                                                                        const OrdRec *__restrict__ rrec,
                                                                        const OrdRec *__restrict__ rrec1,
                                                                        const double *__restrict__ dump_terms,
-                                                                       bool use_summaries) {
+                                                                       bool use_summaries, unsigned cmask, bool raw_mean) {
     constexpr int C = NChains<KIND>::C;
     __shared__ __align__(16) ResolveShared sh;
     const int seg = blockIdx.x, chain = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const PbSeg sg = segs[seg];
     const PbPlanes &P = sg.buf ? b1 : b0;
-    const uint32_t n = sg.n, nblk_all = (n + OB - 1) / OB, nblk = chain_live<KIND, W>(chain) ? nblk_all : 0u;
+    const uint32_t n = sg.n, nblk_all = (n + OB - 1) / OB,
+                   nblk = (chain_live<KIND, W>(chain) && (cmask >> chain & 1u)) ? nblk_all : 0u;
     double m0 = 0, m1 = 0, m2 = 0;
     if (KIND == KIND_CENTERED) { m0 = stats[seg].mean[0]; m1 = stats[seg].mean[1]; m2 = stats[seg].mean[2]; }
     double sd = 0.0;                          // the exact running sum, authoritative while !st.ok
@@ -859,7 +862,8 @@ __global__ void __launch_bounds__(32 * NChains<KIND>::C) k_ord_resolve(PbPlanes 
             const double wsum = W ? sh.res[0] : (double)n;
             const double inv = 1.0 / wsum;
             stats[seg].wsum = wsum;
-            for (int j = 0; j < 3; j++) stats[seg].mean[j] = __dmul_rn(sh.res[1 + j], inv);
+            // raw_mean (chain-sharded runs): the sums leave unscaled, the owner of the weight sum may be another rank
+            for (int j = 0; j < 3; j++) stats[seg].mean[j] = raw_mean ? sh.res[1 + j] : __dmul_rn(sh.res[1 + j], inv);
         } else {
             for (int j = 0; j < 6; j++) stats[seg].cov[j] = sh.res[j];
             stats[seg].dist = sh.res[6];
@@ -913,7 +917,7 @@ size_t summary_pad_smem(int kind) {
 
 template <int KIND, bool W>
 void launch_pass(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t max_n, uint32_t total_blocks,
-                 PbStats *d_stats, void *d_scratch, size_t scratch_bytes, cudaStream_t st) {
+                 PbStats *d_stats, void *d_scratch, size_t scratch_bytes, cudaStream_t st, unsigned cmask, bool raw_mean) {
     constexpr int C = NChains<KIND>::C;
     const uint32_t blk_cap = (max_n + OB - 1) / OB; // grid width; the tables are packed by PbSeg::bbase
     const size_t need = pb_ordered_scratch_bytes(total_blocks);
@@ -923,19 +927,19 @@ void launch_pass(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t
         sc = carve(d_scratch, total_blocks);
         dim3 grid(blk_cap, nseg), sgrid((blk_cap + OS_WARPS - 1) / OS_WARPS, nseg);
         { PbProfScope p(KIND == KIND_MEAN ? "k_ord_blocksum_mean" : "k_ord_blocksum_centered", st, false);
-          k_ord_blocksum<KIND, W><<<grid, OB_THREADS, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, sc.psum); }
+          k_ord_blocksum<KIND, W><<<grid, OB_THREADS, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, sc.psum, cmask); }
         { PbProfScope p("k_ord_prefix", st, false);
-          k_ord_prefix<C><<<dim3(chain_live<KIND, W>(0) ? C : C - 1, nseg), 32, 0, st>>>(d_segs, sc.psum, chain_live<KIND, W>(0) ? 0 : 1); }
+          k_ord_prefix<C><<<dim3(chain_live<KIND, W>(0) ? C : C - 1, nseg), 32, 0, st>>>(d_segs, sc.psum, chain_live<KIND, W>(0) ? 0 : 1, cmask); }
         PB_CUDA_OK(cudaMemsetAsync(sc.list_count, 0, 2 * sizeof(unsigned int), st));
         { PbProfScope p(KIND == KIND_MEAN ? "k_ord_summary_mean" : "k_ord_summary_centered", st);
-          k_ord_summary<KIND, W><<<sgrid, OS_THREADS, summary_pad_smem(KIND), st>>>(bufs[0], bufs[1], d_segs, d_stats, sc.psum, sc.rec0, sc.list_count, sc.list, sc.dump); }
+          k_ord_summary<KIND, W><<<sgrid, OS_THREADS, summary_pad_smem(KIND), st>>>(bufs[0], bufs[1], d_segs, d_stats, sc.psum, sc.rec0, sc.list_count, sc.list, sc.dump, cmask); }
         { PbProfScope p("k_ord_summary2", st, false);
           k_ord_summary2<KIND, W><<<148 * 16, OS_THREADS, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, sc.psum, sc.rec0, sc.rec1, sc.list_count, sc.list, sc.dump); }
         { PbProfScope p("k_ord_group", st, false);
-          k_ord_group<KIND, W><<<dim3((blk_cap + 31) / 32, nseg), 32 * C, 0, st>>>(d_segs, sc.rec0, sc.rec1, sc.grec, sc.rrec, sc.rrec1); }
+          k_ord_group<KIND, W><<<dim3((blk_cap + 31) / 32, nseg), 32 * C, 0, st>>>(d_segs, sc.rec0, sc.rec1, sc.grec, sc.rrec, sc.rrec1, cmask); }
     }
     { PbProfScope p(KIND == KIND_MEAN ? "k_ord_resolve_mean" : "k_ord_resolve_centered", st, !speculative);
-      k_ord_resolve<KIND, W><<<nseg, 32 * C, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, sc.rec0, sc.rec1, sc.grec, sc.rrec, sc.rrec1, sc.dump.terms, speculative); }
+      k_ord_resolve<KIND, W><<<nseg, 32 * C, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, sc.rec0, sc.rec1, sc.grec, sc.rrec, sc.rrec1, sc.dump.terms, speculative, cmask, raw_mean); }
     PB_CUDA_OK(cudaGetLastError());
 }
 
@@ -968,16 +972,16 @@ size_t pb_ordered_scratch_bytes(size_t total_blocks) {
 
 void pb_launch_pass_mean(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t max_n,
                          uint32_t total_blocks, bool weighted, PbStats *d_stats, void *d_scratch,
-                         size_t scratch_bytes, cudaStream_t st) {
+                         size_t scratch_bytes, cudaStream_t st, unsigned cmask, bool raw_mean) {
     if (nseg <= 0) return;
-    if (weighted) launch_pass<KIND_MEAN, true>(bufs, d_segs, nseg, max_n, total_blocks, d_stats, d_scratch, scratch_bytes, st);
-    else launch_pass<KIND_MEAN, false>(bufs, d_segs, nseg, max_n, total_blocks, d_stats, d_scratch, scratch_bytes, st);
+    if (weighted) launch_pass<KIND_MEAN, true>(bufs, d_segs, nseg, max_n, total_blocks, d_stats, d_scratch, scratch_bytes, st, cmask, raw_mean);
+    else launch_pass<KIND_MEAN, false>(bufs, d_segs, nseg, max_n, total_blocks, d_stats, d_scratch, scratch_bytes, st, cmask, raw_mean);
 }
 
 void pb_launch_pass_centered(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t max_n,
                              uint32_t total_blocks, bool weighted, PbStats *d_stats, void *d_scratch,
-                             size_t scratch_bytes, cudaStream_t st) {
+                             size_t scratch_bytes, cudaStream_t st, unsigned cmask) {
     if (nseg <= 0) return;
-    if (weighted) launch_pass<KIND_CENTERED, true>(bufs, d_segs, nseg, max_n, total_blocks, d_stats, d_scratch, scratch_bytes, st);
-    else launch_pass<KIND_CENTERED, false>(bufs, d_segs, nseg, max_n, total_blocks, d_stats, d_scratch, scratch_bytes, st);
+    if (weighted) launch_pass<KIND_CENTERED, true>(bufs, d_segs, nseg, max_n, total_blocks, d_stats, d_scratch, scratch_bytes, st, cmask, false);
+    else launch_pass<KIND_CENTERED, false>(bufs, d_segs, nseg, max_n, total_blocks, d_stats, d_scratch, scratch_bytes, st, cmask, false);
 }

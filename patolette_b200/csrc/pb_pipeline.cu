@@ -29,6 +29,53 @@ namespace {
 int g_device = 0;
 int g_overlap_override = -1; // patolette_b200_set_option "overlap": -1 default, 0 off, 1 on
 bool g_nn_grid = true;       // patolette_b200_set_option "nn_grid": candidate-list 1-NN (pb_nngrid.cu) vs brute force
+
+// ---- chain sharding (patolette_b200_set_sharding) --------------------------------------------------
+// Every rank holds the whole image and runs the same host logic; the ordered sums - the bulk of the step -
+// are split by CHAIN: rank r sums the chains it owns for every segment, and the ranks' PbStats rows are
+// all-gathered through the caller's callback (torch.distributed / MPI / anything that can all-gather host
+// bytes) and merged field by field.  Every field is still the reference's sequential sum, so the result
+// does not depend on the number of ranks.
+int g_shard_rank = 0, g_shard_world = 1;
+patolette_b200_allgather_fn g_shard_allgather = nullptr;
+void *g_shard_user = nullptr;
+bool sharded() { return g_shard_world > 1 && g_shard_allgather; }
+// chains of the mean pass: {w, c0*w, c1*w, c2*w} (w only when weighted), of the centred pass: 6 covariances + distortion
+int mean_owner(int chain, bool weighted) { return (weighted ? chain : chain - 1) % g_shard_world; }
+int cent_owner(int chain) { return chain % g_shard_world; }
+unsigned mean_mask(bool weighted) {
+    if (!sharded()) return ~0u;
+    unsigned m = 0;
+    for (int c = weighted ? 0 : 1; c < 4; c++)
+        if (mean_owner(c, weighted) == g_shard_rank) m |= 1u << c;
+    return m;
+}
+unsigned cent_mask() {
+    if (!sharded()) return ~0u;
+    unsigned m = 0;
+    for (int c = 0; c < 7; c++)
+        if (cent_owner(c) == g_shard_rank) m |= 1u << c;
+    return m;
+}
+// all-gather `count` rows and keep, for every field, the owner's value.  Mean pass: the raw sums are scaled
+// here (matrix2D.c:230-231: mean = sum * (1 / wsum)) - the same two IEEE operations the kernel performs.
+void shard_merge(PbStats *rows, int count, bool mean_pass, bool weighted) {
+    if (!sharded() || count <= 0) return;
+    static thread_local std::vector<PbStats> all;
+    all.resize((size_t)count * g_shard_world);
+    g_shard_allgather(rows, all.data(), (size_t)count * sizeof(PbStats), g_shard_user);
+    for (int i = 0; i < count; i++) {
+        auto from = [&](int rank) -> const PbStats & { return all[(size_t)rank * count + i]; };
+        if (mean_pass) {
+            if (weighted) rows[i].wsum = from(mean_owner(0, true)).wsum;
+            const double inv = 1.0 / rows[i].wsum;
+            for (int j = 0; j < 3; j++) rows[i].mean[j] = from(mean_owner(1 + j, weighted)).mean[j] * inv;
+        } else {
+            for (int t = 0; t < 6; t++) rows[i].cov[t] = from(cent_owner(t)).cov[t];
+            rows[i].dist = from(cent_owner(6)).dist;
+        }
+    }
+}
 cudaStream_t g_user_stream = nullptr;
 bool g_use_user_stream = false;
 double g_timings[10] = {0};
@@ -335,11 +382,20 @@ struct Quantizer {
         const PbPlanes gq[2] = {orig, orig};
         h2d(segs.p, &whole, 1);
         pb_prof_next_bytes(24.0 * N);
-        pb_launch_pass_mean(gq, segs.p, 1, (uint32_t)N, (uint32_t)max_blocks, false, stats.p, oscratch.p, oscratch.n, st);     // global.c:407: UNWEIGHTED PCA
+        pb_launch_pass_mean(gq, segs.p, 1, (uint32_t)N, (uint32_t)max_blocks, false, stats.p, oscratch.p, oscratch.n, st,
+                            mean_mask(false), sharded());     // global.c:407: UNWEIGHTED PCA
+        if (sharded()) { // the centred pass needs the complete mean on every rank
+            d2h(&hst, stats.p, 1);
+            sync();
+            shard_merge(&hst, 1, true, false);
+            h2d(stats.p, &hst, 1);
+        }
         pb_prof_next_bytes(24.0 * N);
-        pb_launch_pass_centered(gq, segs.p, 1, (uint32_t)N, (uint32_t)max_blocks, false, stats.p, oscratch.p, oscratch.n, st);
+        pb_launch_pass_centered(gq, segs.p, 1, (uint32_t)N, (uint32_t)max_blocks, false, stats.p, oscratch.p, oscratch.n, st,
+                                cent_mask());
         d2h(&hst, stats.p, 1);
         sync();
+        shard_merge(&hst, 1, false, false);
         double v[9], axis[3];
         fill_vcov(hst, v);
         if (!pca_axis_from_vcov(v, axis)) return 0;
@@ -409,12 +465,21 @@ struct Quantizer {
         uint32_t cmax = 0;
         for (size_t j = 0; j < cells; j++) cmax = std::max(cmax, hsegs[j].n);
         pb_prof_next_bytes((weighted ? 32.0 : 24.0) * N);
-        pb_launch_pass_mean(bufs, segs.p, (int)cells, cmax, (uint32_t)max_blocks, weighted, stats.p, oscratch.p, oscratch.n, st);
-        pb_prof_next_bytes((weighted ? 32.0 : 24.0) * N);
-        pb_launch_pass_centered(bufs, segs.p, (int)cells, cmax, (uint32_t)max_blocks, weighted, stats.p, oscratch.p, oscratch.n, st);
         std::vector<PbStats> hstats(cells);
+        pb_launch_pass_mean(bufs, segs.p, (int)cells, cmax, (uint32_t)max_blocks, weighted, stats.p, oscratch.p, oscratch.n, st,
+                            mean_mask(weighted), sharded());
+        if (sharded()) {
+            d2h(hstats.data(), stats.p, cells);
+            sync();
+            shard_merge(hstats.data(), (int)cells, true, weighted);
+            h2d(stats.p, hstats.data(), cells);
+        }
+        pb_prof_next_bytes((weighted ? 32.0 : 24.0) * N);
+        pb_launch_pass_centered(bufs, segs.p, (int)cells, cmax, (uint32_t)max_blocks, weighted, stats.p, oscratch.p, oscratch.n, st,
+                                cent_mask());
         d2h(hstats.data(), stats.p, cells);
         sync();
+        shard_merge(hstats.data(), (int)cells, false, weighted);
         for (size_t j = 0; j < cells; j++) out[j] = HNode{hsegs[j], hstats[j]};
         return cells;
     }
@@ -523,18 +588,30 @@ struct Quantizer {
             case 4:
                 pb_prof_next_bytes(bpp * B.tot_n);
                 pb_launch_pass_mean(bufs, d.children, 2 * nb, max_n, (uint32_t)max_blocks, weighted, d.stats, d.oscratch,
-                                    d.oscratch_n, d.st);
+                                    d.oscratch_n, d.st, mean_mask(weighted), sharded());
                 break;
             case 5:
                 pb_prof_next_bytes(bpp * B.tot_n);
                 pb_launch_pass_centered(bufs, d.children, 2 * nb, max_n, (uint32_t)max_blocks, weighted, d.stats,
-                                        d.oscratch, d.oscratch_n, d.st);
+                                        d.oscratch, d.oscratch_n, d.st, cent_mask());
                 break;
             }
         };
-        for (int k = 0; k < 6; k++)
+        for (int k = 0; k < 6; k++) {
+            if (k == 5 && sharded()) { // between the mean and the centred pass: complete means on every rank
+                for (int h = 0; h < nhalf; h++)
+                    if (hb[h].nb)
+                        PB_CUDA_OK(cudaMemcpyAsync(hb[h].hst, dev[h].stats, 2 * hb[h].nb * sizeof(PbStats), cudaMemcpyDeviceToHost, dev[h].st));
+                for (int h = 0; h < nhalf; h++) {
+                    if (!hb[h].nb) continue;
+                    PB_CUDA_OK(cudaStreamSynchronize(dev[h].st));
+                    shard_merge(hb[h].hst, 2 * hb[h].nb, true, weighted);
+                    PB_CUDA_OK(cudaMemcpyAsync(dev[h].stats, hb[h].hst, 2 * hb[h].nb * sizeof(PbStats), cudaMemcpyHostToDevice, dev[h].st));
+                }
+            }
             for (int h = 0; h < nhalf; h++)
                 if (hb[h].nb) step(k, hb[h], dev[h]);
+        }
         for (int h = 0; h < nhalf; h++) { // pageable destinations: each copy returns when its stream got there
             if (!hb[h].nb) continue;
             PB_CUDA_OK(cudaMemcpyAsync(hb[h].hch, dev[h].children, 2 * hb[h].nb * sizeof(PbSeg), cudaMemcpyDeviceToHost, dev[h].st));
@@ -542,6 +619,8 @@ struct Quantizer {
         }
         for (int h = 0; h < nhalf; h++)
             if (hb[h].nb) PB_CUDA_OK(cudaStreamSynchronize(dev[h].st));
+        for (int h = 0; h < nhalf; h++)
+            if (hb[h].nb) shard_merge(hb[h].hst, 2 * hb[h].nb, false, weighted);
         for (int h = 0; h < nhalf; h++)
             for (int b = 0; b < hb[h].nb; b++) {
                 HPair *o = outs[hb[h].map[b]];
@@ -911,6 +990,15 @@ int patolette_b200_ordered_counts(unsigned long long *out2, int reset) {
         pb_ordered_counts(out2, reset != 0);
         return 0;
     } catch (const pb_cuda_error &e) { return -(int)e.code; }
+}
+
+int patolette_b200_set_sharding(int rank, int world, patolette_b200_allgather_fn allgather, void *user) {
+    if (world < 1 || rank < 0 || rank >= world || (world > 1 && !allgather)) return -1;
+    g_shard_rank = rank;
+    g_shard_world = world;
+    g_shard_allgather = world > 1 ? allgather : nullptr;
+    g_shard_user = user;
+    return 0;
 }
 
 int patolette_b200_set_option(const char *name, long long value) {
