@@ -171,6 +171,82 @@ static void run_chain(const std::vector<double> &a, Stats &st) {
     }
 }
 
+// The run records of k_ord_group / k_ord_resolve (pb_ordered.cu), emulated lane by lane: a backward
+// segmented doubling scan composes, for every record of a group of 32, the maximal run of usable records of
+// one unit that starts there (both start parities); the walk crosses a whole run with one interval check on
+// the variant its state's parity selects.  Whatever it accepts must be the sequential loop's state.
+struct RunStats { long runs = 0, run_blocks = 0, singles = 0, replays = 0, wrong = 0; };
+static void run_chain_with_run_records(const std::vector<double> &a, RunStats &rs) {
+    const size_t n = a.size(), nblk = (n + OB - 1) / OB;
+    std::vector<double> pstart(nblk), truth(nblk);
+    {
+        double run = 0, s = 0;
+        for (size_t b = 0; b < nblk; b++) {
+            const int cnt = (int)std::min<size_t>(OB, n - b * OB);
+            pstart[b] = run;
+            run += tree_sum(&a[b * OB], cnt);
+            for (int i = 0; i < cnt; i++) s = s + a[b * OB + i];
+            truth[b] = s;
+        }
+    }
+    enum { OK = 0, SENS = 1, REPLAY = 2 };
+    std::vector<PbSpan2> rec(nblk);
+    std::vector<int> eref(nblk), kind(nblk);
+    Stats dummy;
+    for (size_t b = 0; b < nblk; b++) {
+        const int cnt = (int)std::min<size_t>(OB, n - b * OB);
+        bool usable, sens;
+        summarise_block(&a[b * OB], cnt, pstart[b], rec[b], eref[b], usable, sens, dummy);
+        kind[b] = !usable ? REPLAY : (sens ? SENS : OK);
+        if (kind[b] == OK) { rec[b].p[1] = rec[b].p[0]; if (!pb_span_valid(rec[b].p[0])) kind[b] = REPLAY; }
+        if (kind[b] == SENS && !pb_span_valid(rec[b].p[0]) && !pb_span_valid(rec[b].p[1])) kind[b] = REPLAY;
+    }
+    PbState st = pb_state_from_double(0.0);
+    auto check = [&](size_t b) {
+        if (pb_double_bits(pb_state_to_double(st)) != pb_double_bits(truth[b])) { rs.wrong++; st = pb_state_from_double(truth[b]); }
+    };
+    for (size_t g0 = 0; g0 < nblk; g0 += 32) {
+        const int gcnt = (int)std::min<size_t>(32, nblk - g0);
+        PbSpan2 v[32], nv[32];
+        int len[32], nlen[32], er[32];
+        bool open[32], nopen[32];
+        for (int l = 0; l < 32; l++) {
+            v[l] = pb_span2_identity(); len[l] = 0; er[l] = 0;
+            if (l < gcnt) { v[l] = rec[g0 + l]; er[l] = eref[g0 + l]; len[l] = kind[g0 + l] != REPLAY ? 1 : 0; }
+            open[l] = len[l] > 0;
+        }
+        for (int o = 1; o < 32; o <<= 1) { // every lane reads its partner's values of the previous round
+            for (int l = 0; l < 32; l++) {
+                nv[l] = v[l]; nlen[l] = len[l]; nopen[l] = open[l];
+                if (!open[l]) continue;
+                const int p = l + o;
+                if (p < 32 && len[p] > 0 && er[p] == er[l]) { nv[l] = pb_span2_cat(v[l], v[p]); nlen[l] = len[l] + len[p]; nopen[l] = open[p]; }
+                else nopen[l] = false;
+            }
+            for (int l = 0; l < 32; l++) { v[l] = nv[l]; len[l] = nlen[l]; open[l] = nopen[l]; }
+        }
+        int next = 0;
+        while (next < gcnt) {
+            if (len[next] > 0 && pb_state_rebase(st, er[next])) {
+                const PbSpan &pick = v[next].p[(int)(st.S & 1LL)];
+                if (st.S >= pick.lo && st.S <= pick.hi) {
+                    st.S += pick.sum;
+                    rs.runs++; rs.run_blocks += len[next];
+                    next += len[next];
+                    check(g0 + next - 1);
+                    continue;
+                }
+            }
+            const size_t b = g0 + next;
+            bool applied = false;
+            if (kind[b] != REPLAY) applied = pb_state_apply(st, rec[b].p[0], rec[b].p[1], eref[b]);
+            if (applied) { rs.singles++; check(b); }
+            else { rs.replays++; st = pb_state_from_double(truth[b]); }
+            next++;
+        }
+    }
+}
+
 // pb_state_rebase (integer shifts) must agree with the formulation through the double for every valid
 // state (at most 53 significant bits, any trailing-zero count up to the level range) and every unit.
 static long check_rebase(std::mt19937_64 &rng) {
@@ -211,6 +287,7 @@ int main(int argc, char **argv) {
         {"mean-centred, weakly correlated", 14},
     };
     long total_wrong = 0, total_assoc = 0;
+    RunStats rr;
     for (const Family &f : fams) {
         Stats st;
         for (int rep = 0; rep < reps; rep++) {
@@ -249,6 +326,7 @@ int main(int argc, char **argv) {
             }
             if (f.kind == 12) a[0] = 1.0; // start right at a power of two and wobble around it
             run_chain(a, st);
+            run_chain_with_run_records(a, rr);
         }
         printf("%-40s blocks %7ld accepted %6.2f%% sensitive %5.2f%% unusable %5.2f%% fast-threads %5.1f%% wrong %ld assoc %ld fastmis %ld\n",
                f.name.c_str(), st.blocks, 100.0 * st.accepted / st.blocks, 100.0 * st.sensitive / st.blocks,
@@ -256,6 +334,9 @@ int main(int argc, char **argv) {
         total_wrong += st.wrong + st.fast_mismatch;
         total_assoc += st.assoc_fail;
     }
+    printf("run records: %ld runs crossing %ld blocks, %ld single records, %ld replays, wrong %ld\n", rr.runs, rr.run_blocks,
+           rr.singles, rr.replays, rr.wrong);
+    total_wrong += rr.wrong;
     if (total_wrong || total_assoc) { printf("FAIL\n"); return 1; }
     printf("OK\n");
     return 0;

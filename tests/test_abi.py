@@ -103,3 +103,24 @@ def test_pow_restatement_matches_libm_on_host(tmp_path):
     r = subprocess.run([str(exe), "1000000"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-2000:]
     assert "mismatches=0" in r.stdout
+
+
+def test_route_and_sharding_knobs_validate_their_arguments():
+    """patolette_b200_set_option / patolette_b200_set_sharding are pure host state: usable without a GPU."""
+    import ctypes as C
+    from patolette_b200 import _lib
+    import patolette_b200 as pb
+    lib = _lib.load()
+    assert lib.patolette_b200_set_option(b"no_such_option", 1) == -1
+    for name in (b"dump_cap", b"overlap", b"nn_grid", b"dither_grid"):
+        assert lib.patolette_b200_set_option(name, 1) == 0
+    lib.patolette_b200_set_option(b"dump_cap", -1)
+    lib.patolette_b200_set_option(b"overlap", -1)
+    assert lib.patolette_b200_set_sharding(0, 0, None, None) == -1      # world < 1
+    assert lib.patolette_b200_set_sharding(2, 2, None, None) == -1      # rank out of range
+    assert lib.patolette_b200_set_sharding(0, 2, None, None) == -1      # world > 1 needs a callback
+    assert lib.patolette_b200_set_sharding(0, 1, None, None) == 0
+    with pytest.raises(ValueError):
+        pb.set_sharding(0, 2)                                           # no allgather given
+    pb.set_sharding(1, 2, lambda send: send * 2)
+    pb.set_sharding(0, 1)                                               # back to a single rank
