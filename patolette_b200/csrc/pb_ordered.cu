@@ -248,7 +248,7 @@ __device__ __noinline__ void run_push_slow(PbRun *r, double term, double approx,
 // Summarises block `blk` of segment `sg`; called by a whole warp.  NC = C: every live chain, one record each
 // (NV = 1; chains with a parity-dependent step are left F_PENDING and returned as a bit mask).  NC = 1: the
 // single chain `ch0`, for both start parities (NV = 2, the work-list pass).
-template <int KIND, bool W, int NV, int NC>
+template <int KIND, bool W, int NV, int NC, bool MASKED = false>
 __device__ __forceinline__ unsigned summarise_block(const PbPlanes &P, const PbSeg &sg, uint32_t blk, int ch0, double m0,
                                                     double m1, double m2, const double *__restrict__ pstart,
                                                     OrdRec *__restrict__ rec0, OrdRec *__restrict__ rec1, const Dump &dump,
@@ -259,7 +259,8 @@ __device__ __forceinline__ unsigned summarise_block(const PbPlanes &P, const PbS
     constexpr int OS_UNROLL = NC == 1 ? 4 : (KIND == KIND_MEAN ? PB_OS_UNROLL_MEAN : PB_OS_UNROLL_CEN);
     static_assert(NC == 1 || NC == C, "all chains or one");
     auto chain_of = [&](int slot) { return NC == 1 ? ch0 : slot; };
-    auto live = [&](int slot) { return NC == 1 ? true : (chain_live<KIND, W>(slot) && (cmask >> slot & 1u)); };
+    // MASKED (chain-sharded runs only): the chains this rank owns; otherwise a compile-time predicate
+    auto live = [&](int slot) { return NC == 1 ? true : (chain_live<KIND, W>(slot) && (!MASKED || (cmask >> slot & 1u))); };
     const uint32_t nblk = (sg.n + OB - 1) / OB;
     const int lane = threadIdx.x & 31;
     const uint32_t i0 = blk * OB + lane * OS_PER; // this lane's consecutive elements
@@ -484,7 +485,7 @@ __device__ __forceinline__ unsigned summarise_block(const PbPlanes &P, const PbS
     return pending; // warp-uniform: chains left F_PENDING
 }
 
-template <int KIND, bool W>
+template <int KIND, bool W, bool MASKED>
 __global__ void __launch_bounds__(OS_THREADS, PB_OS_MINB) k_ord_summary(PbPlanes b0, PbPlanes b1, const PbSeg *__restrict__ segs,
                                                             const PbStats *__restrict__ stats,
                                                             const double *__restrict__ psum, OrdRec *__restrict__ rec0,
@@ -499,7 +500,7 @@ __global__ void __launch_bounds__(OS_THREADS, PB_OS_MINB) k_ord_summary(PbPlanes
     const PbPlanes &P = sg.buf ? b1 : b0;
     double m0 = 0, m1 = 0, m2 = 0;
     if (KIND == KIND_CENTERED) { m0 = stats[seg].mean[0]; m1 = stats[seg].mean[1]; m2 = stats[seg].mean[2]; }
-    const unsigned pending = summarise_block<KIND, W, 1, C>(P, sg, blk, 0, m0, m1, m2, psum + ((size_t)sg.bbase + blk) * C,
+    const unsigned pending = summarise_block<KIND, W, 1, C, MASKED>(P, sg, blk, 0, m0, m1, m2, psum + ((size_t)sg.bbase + blk) * C,
                                                             rec0, nullptr, dump, stage[threadIdx.x >> 5], cmask);
     if ((threadIdx.x & 31) == 0 && pending) { // one work item per (block, chain): block index < 2^28
         const unsigned int at = atomicAdd(list_count, (unsigned)__popc(pending));
@@ -932,7 +933,10 @@ void launch_pass(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t
           k_ord_prefix<C><<<dim3(chain_live<KIND, W>(0) ? C : C - 1, nseg), 32, 0, st>>>(d_segs, sc.psum, chain_live<KIND, W>(0) ? 0 : 1, cmask); }
         PB_CUDA_OK(cudaMemsetAsync(sc.list_count, 0, 2 * sizeof(unsigned int), st));
         { PbProfScope p(KIND == KIND_MEAN ? "k_ord_summary_mean" : "k_ord_summary_centered", st);
-          k_ord_summary<KIND, W><<<sgrid, OS_THREADS, summary_pad_smem(KIND), st>>>(bufs[0], bufs[1], d_segs, d_stats, sc.psum, sc.rec0, sc.list_count, sc.list, sc.dump, cmask); }
+          if (cmask == ~0u) // every chain: the single-GPU instantiation, chain liveness known at compile time
+              k_ord_summary<KIND, W, false><<<sgrid, OS_THREADS, summary_pad_smem(KIND), st>>>(bufs[0], bufs[1], d_segs, d_stats, sc.psum, sc.rec0, sc.list_count, sc.list, sc.dump, cmask);
+          else
+              k_ord_summary<KIND, W, true><<<sgrid, OS_THREADS, summary_pad_smem(KIND), st>>>(bufs[0], bufs[1], d_segs, d_stats, sc.psum, sc.rec0, sc.list_count, sc.list, sc.dump, cmask); }
         { PbProfScope p("k_ord_summary2", st, false);
           k_ord_summary2<KIND, W><<<148 * 16, OS_THREADS, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, sc.psum, sc.rec0, sc.rec1, sc.list_count, sc.list, sc.dump); }
         { PbProfScope p("k_ord_group", st, false);
