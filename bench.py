@@ -146,13 +146,31 @@ def time_reference(side: int, steps: int, warmup: int):
                        f"{dt:.2f} s; FLANN absent -> exact brute-force NN stand-in (OpenMP); OpenBLAS 1 thread"), dt
 
 
+class QuietStdout:
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner at
+    communicator creation, for one): while the bench runs, file descriptor 1 points at stderr."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     total = args.steps + args.warmup
     side = 1536 if total <= 8 else (1024 if total <= 20 else 768)
-    cb, dt = time_reference(side, args.steps, args.warmup)
+    with QuietStdout():
+        cb, dt = time_reference(side, args.steps, args.warmup)
     line = {"metric": "Mpixels/s end-to-end quantize() at K=256", "value": cb["value"], "unit": "Mpixels/s",
             "impl": "reference", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -165,6 +183,13 @@ def run_reference(args):
 
 
 def run_ours(args):
+    with QuietStdout():
+        line = measure_ours(args)
+    if line is not None:
+        print(json.dumps(line))
+
+
+def measure_ours(args):
     import numpy as np
     import torch
     import patolette_b200 as pb
@@ -313,7 +338,7 @@ def run_ours(args):
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
-        return
+        return None
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         cpu_baseline, _ = time_reference(1536, 1, 0)
@@ -346,9 +371,9 @@ def run_ours(args):
     }
     if cpu_baseline is not None:
         line["cpu_baseline"] = cpu_baseline
-    print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
+    return line
 
 
 if __name__ == "__main__":
