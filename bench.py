@@ -326,7 +326,7 @@ def measure_ours(args):
                 "top_kernel_launch_ms": [round(x, 3) for x in top.get("each", [])],
                 "stages": {
                     "covariance (ordered mean + centred passes: k_ord_*)": stage_roofline(["k_ord_"], pass_bytes),
-                    "assignment (k_nearest, f64 brute force: FP64-ALU bound, 9*K flop/px)": stage_roofline(["k_nearest"], 32.0 * n),
+                    "assignment (k_nearest: exact f64 1-NN over per-cell candidate lists)": stage_roofline(["k_nearest"], 32.0 * n),
                     "projection + bucket sort + partition (k_dots_minmax, k_buckets, k_tile_*, k_scatter)":
                         stage_roofline(["k_dots_minmax", "k_buckets", "k_tile_", "k_scatter", "k_class_start"],
                               sum(v["bytes"] for k, v in prof.items() if k in ("k_dots_minmax", "k_buckets", "k_scatter"))),
