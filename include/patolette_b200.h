@@ -125,6 +125,11 @@ PB200_API size_t patolette_b200_profile_json(char *buf, size_t cap);
  * through a two-parity record, SM cycles of the resolving warps in {scan walk, two-parity records,
  * replays}, record groups loaded, cycles of the slowest resolving warp, 3 spare. */
 PB200_API int patolette_b200_ordered_counts(unsigned long long *out16, int reset);
+/* Host-only stage entry (no GPU needed): the GQ dynamic programme (quantize/global.c:189-298) on 512 x 10
+ * per-bucket sums {sum c[3], sum |c|^2, sum c_r*c_s (0,0)(0,1)(1,1)(0,2)(1,2)(2,2)} and 513 class starts.
+ * Writes the cut list q[0..cells] into cuts16, returns the cell count (0 on failure). */
+PB200_API int patolette_b200_gq_cuts(const double *bucket_sums, const unsigned int *class_start, size_t palette_size,
+                                     size_t *cuts16);
 /* Chain-sharded multi-GPU runs: every rank (process + GPU) is given the SAME image and calls
  * patolette() at the same time; rank r computes the ordered sums of the chains it owns and the ranks exchange
  * their per-cluster moment rows through `allgather`, which must gather `bytes` bytes from every rank into
@@ -134,7 +139,8 @@ typedef void (*patolette_b200_allgather_fn)(const void *send, void *recv, size_t
 PB200_API int patolette_b200_set_sharding(int rank, int world, patolette_b200_allgather_fn allgather, void *user);
 /* Test / tuning knobs (never change results, only the route taken): "dump_cap" = cap on the term-dump slots
  * of an ordered-sum pass (-1 default; 0 = every replay recomputes its terms from the planes), "overlap" =
- * two-stream half-batch evaluation of the split loop (-1 default, 0 off, 1 on), "nn_grid" / "dither_grid" = nearest
+ * two-stream half-batch evaluation of the split loop (-1 default, 0 off, 1 on), "gq_threads" = host threads of the GQ
+ * dynamic programme (0 default), "nn_grid" / "dither_grid" = nearest
  * map / the dither's per-step search through per-cell candidate lists (1, default) or brute force (0).
  * Returns 0, -1 if unknown. */
 PB200_API int patolette_b200_set_option(const char *name, long long value);

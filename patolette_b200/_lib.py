@@ -49,6 +49,7 @@ SYMBOLS = {
     "patolette_b200_ordered_chain_debug": (C.c_int, [C.c_void_p, C.c_int]),
     "patolette_b200_set_option": (C.c_int, [C.c_char_p, C.c_longlong]),
     "patolette_b200_set_sharding": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "patolette_b200_gq_cuts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "patolette_b200_profile_enable": (C.c_int, [C.c_int]),
     "patolette_b200_profile_json": (C.c_size_t, [C.c_char_p, C.c_size_t]),
 }

@@ -18,6 +18,7 @@
 #include "../../include/patolette_b200.h"
 #include "pb_common.cuh"
 #include "pb_host.h"
+#include "pb_hostpool.h"
 #include "pb_kernels.h"
 #include "pb_pipeline.h"
 #include "pb_pool.h"
@@ -208,34 +209,62 @@ void l_chain(const std::vector<double> &L, size_t ld, size_t k, size_t N, size_t
     chain[k] = N;
 }
 
-size_t principal_quantizer(size_t K, const CellMoments &m, size_t *q) { // global.c:189-298
+// cells.c:53-139: bucket b lives in 1-based slot b + 1; then prefix sums.  hs: 512 x {sum c[3], sum |c|^2,
+// sum c_r*c_s for (r,s) = (0,0)(0,1)(1,1)(0,2)(1,2)(2,2)}, hcs: 513 class starts.
+void build_cell_moments(const double *hs, const uint32_t *hcs, CellMoments &m) {
+    memset(&m, 0, sizeof m);
+    for (int b = 0; b < PB_BUCKETS; b++) {
+        const double *s = &hs[(size_t)b * 10];
+        m.w0[b + 1] = hcs[b + 1] - hcs[b];
+        m.w1[0][b + 1] = s[0]; m.w1[1][b + 1] = s[1]; m.w1[2][b + 1] = s[2];
+        m.w2[b + 1] = s[3];
+        m.wrs[0][0][b + 1] = s[4]; m.wrs[0][1][b + 1] = s[5]; m.wrs[1][1][b + 1] = s[6];
+        m.wrs[0][2][b + 1] = s[7]; m.wrs[1][2][b + 1] = s[8]; m.wrs[2][2][b + 1] = s[9];
+    }
+    for (int i = 1; i < CELLS; i++) {
+        m.w0[i] += m.w0[i - 1];
+        m.w2[i] += m.w2[i - 1];
+        for (int j = 0; j < 3; j++) m.w1[j][i] += m.w1[j][i - 1];
+        for (int s = 0; s < 3; s++)
+            for (int r = 0; r <= s; r++) m.wrs[r][s][i] += m.wrs[r][s][i - 1];
+    }
+}
+
+int g_gq_threads = 0; // 0: pb_hostpool_default_threads(); patolette_b200_set_option "gq_threads"
+
+// Wu's dynamic programme over the 512 buckets (global.c:189-298).  E_k[n] = min_t E_{k-1}[t] + D(t, n) is
+// independent for every n, so the n loop of an iteration is spread over a few host threads (each n keeps
+// its own descending scan over t, i.e. exactly the reference's comparisons and tie-breaks): 8.8 ms -> ~1.5 ms
+// for the full 11 iterations an image with structure goes through.  The reference's L table is
+// (max(K, 512) + 1)^2 doubles of which only the first 13 columns are ever read; here it has those.
+size_t principal_quantizer(size_t K, const CellMoments &m, size_t *q) {
     const size_t N = CELLS - 1, max_k = 12;
     double axis[3];
     if (!cell_pca(0, N, m, axis)) return 0;
     std::vector<double> E(N + 1, 0.0), E2(N + 1, 0.0);
-    size_t ls = std::max(K, N) + 1;
-    std::vector<double> L;
-    try {
-        L.assign(ls * ls, 0.0);
-    } catch (...) { return 0; }
+    const size_t ls = max_k + 1;
+    std::vector<double> L((N + 1) * ls, 0.0);
     for (size_t i = 1; i <= N; i++) E[i] = cell_distortion(0, i, m);
     for (size_t i = 1; i <= K && i < ls; i++) L[i * ls + i] = (double)i;
     size_t k_out = 1;
     l_chain(L, ls, 1, N, q);
-    size_t kmax = std::min(max_k, K);
+    const size_t kmax = std::min(max_k, K);
+    const int threads = g_gq_threads > 0 ? g_gq_threads : pb_hostpool_default_threads();
     for (size_t k = 2; k <= kmax; k++) {
         if (gq_should_terminate(q, k_out + 1, axis, m)) break;
         E2 = E;
-        for (size_t n = k + 1; n <= N; n++) {
-            double cut = (double)(n - 1);
-            double e = E2[n - 1];
-            for (size_t t = n - 2; t >= k - 1; t--) {
-                double c = E2[t] + cell_distortion(t, n, m);
-                if (c < e) { cut = (double)t; e = c; }
+        pb_hostpool_run(threads, [&](int tid) {
+            for (size_t n = k + 1 + (size_t)tid; n <= N; n += (size_t)threads) { // interleaved: the work grows with n
+                double cut = (double)(n - 1);
+                double e = E2[n - 1];
+                for (size_t t = n - 2; t >= k - 1; t--) {
+                    double c = E2[t] + cell_distortion(t, n, m);
+                    if (c < e) { cut = (double)t; e = c; }
+                }
+                L[n * ls + k] = cut;
+                E[n] = e;
             }
-            L[n * ls + k] = cut;
-            E[n] = e;
-        }
+        });
         l_chain(L, ls, k, N, q);
         k_out = k;
     }
@@ -414,24 +443,8 @@ struct Quantizer {
         d2h(hs.data(), bsums.p, hs.size());
         d2h(hcs.data(), cstart_b.p, hcs.size());
         sync();
-        // cells.c:53-139: bucket b lives in 1-based slot b + 1; then prefix sums
         static thread_local CellMoments m;
-        memset(&m, 0, sizeof m);
-        for (int b = 0; b < PB_BUCKETS; b++) {
-            const double *s = &hs[(size_t)b * 10];
-            m.w0[b + 1] = hcs[b + 1] - hcs[b];
-            m.w1[0][b + 1] = s[0]; m.w1[1][b + 1] = s[1]; m.w1[2][b + 1] = s[2];
-            m.w2[b + 1] = s[3];
-            m.wrs[0][0][b + 1] = s[4]; m.wrs[0][1][b + 1] = s[5]; m.wrs[1][1][b + 1] = s[6];
-            m.wrs[0][2][b + 1] = s[7]; m.wrs[1][2][b + 1] = s[8]; m.wrs[2][2][b + 1] = s[9];
-        }
-        for (int i = 1; i < CELLS; i++) {
-            m.w0[i] += m.w0[i - 1];
-            m.w2[i] += m.w2[i - 1];
-            for (int j = 0; j < 3; j++) m.w1[j][i] += m.w1[j][i - 1];
-            for (int s = 0; s < 3; s++)
-                for (int r = 0; r <= s; r++) m.wrs[r][s][i] += m.wrs[r][s][i - 1];
-        }
+        build_cell_moments(hs.data(), hcs.data(), m);
         size_t q[16];
         size_t cells = principal_quantizer(K, m, q);
         if (cells == 0) return 0;
@@ -992,6 +1005,16 @@ int patolette_b200_ordered_counts(unsigned long long *out2, int reset) {
     } catch (const pb_cuda_error &e) { return -(int)e.code; }
 }
 
+int patolette_b200_gq_cuts(const double *bucket_sums, const unsigned int *class_start, size_t palette_size, size_t *cuts16) {
+    // host only (no CUDA): the GQ dynamic programme on a table of per-bucket sums, for the CPU tests
+    static thread_local CellMoments m;
+    build_cell_moments(bucket_sums, class_start, m);
+    size_t q[16] = {0};
+    const size_t cells = principal_quantizer(palette_size, m, q);
+    for (int i = 0; i < 16; i++) cuts16[i] = q[i];
+    return (int)cells;
+}
+
 int patolette_b200_set_sharding(int rank, int world, patolette_b200_allgather_fn allgather, void *user) {
     if (world < 1 || rank < 0 || rank >= world || (world > 1 && !allgather)) return -1;
     g_shard_rank = rank;
@@ -1006,6 +1029,7 @@ int patolette_b200_set_option(const char *name, long long value) {
     if (!strcmp(name, "dump_cap")) { pb_ordered_set_dump_cap(value); return 0; }
     if (!strcmp(name, "overlap")) { g_overlap_override = (int)value; return 0; }
     if (!strcmp(name, "nn_grid")) { g_nn_grid = value != 0; return 0; }
+    if (!strcmp(name, "gq_threads")) { g_gq_threads = (int)value; return 0; }
     if (!strcmp(name, "dither_grid")) { pb_dither_set_grid(value != 0); return 0; }
     return -1;
 }
