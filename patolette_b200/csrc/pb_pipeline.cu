@@ -231,6 +231,7 @@ void build_cell_moments(const double *hs, const uint32_t *hcs, CellMoments &m) {
 }
 
 int g_gq_threads = 0; // 0: pb_hostpool_default_threads(); patolette_b200_set_option "gq_threads"
+bool g_gq_full_table = false; // "gq_full_table": the reference's (max(K, 512) + 1)^2 layout of L instead of 513 x 13
 
 // Wu's dynamic programme over the 512 buckets (global.c:189-298).  E_k[n] = min_t E_{k-1}[t] + D(t, n) is
 // independent for every n, so the n loop of an iteration is spread over a few host threads (each n keeps
@@ -242,8 +243,11 @@ size_t principal_quantizer(size_t K, const CellMoments &m, size_t *q) {
     double axis[3];
     if (!cell_pca(0, N, m, axis)) return 0;
     std::vector<double> E(N + 1, 0.0), E2(N + 1, 0.0);
-    const size_t ls = max_k + 1;
-    std::vector<double> L((N + 1) * ls, 0.0);
+    const size_t ls = g_gq_full_table ? std::max(K, N) + 1 : max_k + 1; // (the reference's layout, for the self-test)
+    std::vector<double> L;
+    try {
+        L.assign((g_gq_full_table ? ls : N + 1) * ls, 0.0);
+    } catch (...) { return 0; }
     for (size_t i = 1; i <= N; i++) E[i] = cell_distortion(0, i, m);
     for (size_t i = 1; i <= K && i < ls; i++) L[i * ls + i] = (double)i;
     size_t k_out = 1;
@@ -1030,6 +1034,7 @@ int patolette_b200_set_option(const char *name, long long value) {
     if (!strcmp(name, "overlap")) { g_overlap_override = (int)value; return 0; }
     if (!strcmp(name, "nn_grid")) { g_nn_grid = value != 0; return 0; }
     if (!strcmp(name, "gq_threads")) { g_gq_threads = (int)value; return 0; }
+    if (!strcmp(name, "gq_full_table")) { g_gq_full_table = value != 0; return 0; }
     if (!strcmp(name, "dither_grid")) { pb_dither_set_grid(value != 0); return 0; }
     return -1;
 }

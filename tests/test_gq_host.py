@@ -26,7 +26,8 @@ def bucket_table(colors):
     return np.ascontiguousarray(hs), cs
 
 
-@pytest.mark.parametrize("kind,K", [("image_like", 256), ("image_like", 7), ("uniform", 256), ("two_blobs", 64), ("gradient", 1024)])
+@pytest.mark.parametrize("kind,K", [("image_like", 256), ("image_like", 7), ("uniform", 256), ("two_blobs", 64), ("gradient", 1024),
+                                     ("gradient", 5), ("gradient", 12), ("gradient", 600)])
 def test_gq_cuts_do_not_depend_on_the_thread_count(kind, K):
     from patolette_b200 import _lib
     lib = _lib.load()
@@ -56,4 +57,13 @@ def test_gq_cuts_do_not_depend_on_the_thread_count(kind, K):
     assert all(np.diff(res[1][1][:res[1][0] + 1]) > 0), "cuts must ascend"
     for threads in (2, 3, 8):
         assert res[threads] == res[1], f"{threads} threads: {res[threads]} != {res[1]}"
+    try:  # the reference's full (max(K, 512) + 1)^2 table against the 513 x 13 one used by default
+        assert lib.patolette_b200_set_option(b"gq_full_table", 1) == 0
+        assert lib.patolette_b200_set_option(b"gq_threads", 1) == 0
+        q = np.zeros(16, dtype=np.uintp)
+        cells = lib.patolette_b200_gq_cuts(hs.ctypes.data, cs.ctypes.data, K, q.ctypes.data)
+        assert (cells, q.tolist()) == res[1]
+    finally:
+        lib.patolette_b200_set_option(b"gq_full_table", 0)
+        lib.patolette_b200_set_option(b"gq_threads", 0)
     print(f"{kind} K={K}: {res[1][0]} cells, ms by threads {ms}")
