@@ -67,3 +67,23 @@ def test_gq_cuts_do_not_depend_on_the_thread_count(kind, K):
         lib.patolette_b200_set_option(b"gq_full_table", 0)
         lib.patolette_b200_set_option(b"gq_threads", 0)
     print(f"{kind} K={K}: {res[1][0]} cells, ms by threads {ms}")
+
+
+def test_host_pool_survives_many_alternating_calls():
+    """The parked worker threads are reused across calls and thread counts (no lost wake-ups, no stale jobs)."""
+    from patolette_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(3)
+    t = np.linspace(0, 1, 60_000)[:, None]
+    hs, cs = bucket_table(t * np.array([[0.9, 0.5, 0.3]]) + 0.02 * rng.random((60_000, 3)))
+    want = None
+    try:
+        for it in range(300):
+            assert lib.patolette_b200_set_option(b"gq_threads", 1 + (it * 7) % 9) == 0
+            q = np.zeros(16, dtype=np.uintp)
+            cells = lib.patolette_b200_gq_cuts(hs.ctypes.data, cs.ctypes.data, 256, q.ctypes.data)
+            got = (cells, q.tolist())
+            want = want or got
+            assert got == want, it
+    finally:
+        lib.patolette_b200_set_option(b"gq_threads", 0)
