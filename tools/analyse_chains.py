@@ -19,7 +19,8 @@ from oracle.reflib import OracleLib  # noqa: E402
 from synth import uniform_colors  # noqa: E402
 
 NAMES = ["blocks", "accepted", "wrong", "unus_range", "unus_big", "unus_up", "unus_tie", "sensitive", "plainified",
-         "unit_changes", "interval_fail", "first_block", "replayed_elems"]
+         "unit_changes", "interval_fail", "first_block", "replayed_elems",
+         "groups", "groups_plain_one_unit", "groups_usable_one_unit", "groups_usable", "runs", "run_records"]
 
 
 def build():
@@ -56,7 +57,7 @@ def main():
     f = orc.orc_quantize_clusters
     f.restype = C.c_int
     f.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
-    for OB, PER in ((512, 8), (256, 8), (128, 4), (64, 4)):
+    for OB, PER in ((512, 16),):
         tot = {g: np.zeros(len(NAMES), dtype=np.int64) for g in ("mean", "diag", "offdiag")}
         elems = {g: 0 for g in tot}
         for K in (1, 4, 16, 64, 256):
@@ -87,6 +88,9 @@ def main():
             print(f"  {g:8s} blocks {o[0]:8d} accepted {100*o[1]/b:6.2f}% wrong {o[2]} | unusable: range {100*o[3]/b:5.2f}% (first blocks {100*o[11]/b:4.2f}%) "
                   f"big {100*o[4]/b:5.2f}% up {100*o[5]/b:5.2f}% tie {100*o[6]/b:5.2f}% | two-parity {100*o[7]/b:5.2f}% plainified {100*o[8]/b:5.2f}% "
                   f"unit changes {100*o[9]/b:5.2f}% interval fails {100*o[10]/b:5.2f}% | replayed elements {100*o[12]/max(elems[g],1):5.2f}%")
+            gr = max(o[13], 1)
+            print(f"           groups {o[13]:7d}: all plain, one unit {100*o[14]/gr:5.1f}% | all usable, one unit {100*o[15]/gr:5.1f}% | "
+                  f"all usable {100*o[16]/gr:5.1f}% | level-1 runs per group {o[17]/gr:4.2f}, records per run {o[18]/max(o[17],1):5.1f}")
 
 
 if __name__ == "__main__":

@@ -13,7 +13,10 @@ static double tree_sum(const double *a, int n) {
 
 // out: 0 blocks, 1 accepted, 2 wrong, 3 unusable: range/spread, 4 unusable: term too large, 5 unusable: upward step,
 //      6 unusable: tie above level 0, 7 sensitive (two-parity record), 8 plainified, 9 unit changes, 10 interval failures,
-//      11 first-block, 12 elements in replayed blocks
+//      11 first-block, 12 elements in replayed blocks,
+//      13 groups of 32 records, 14 groups that are all plain records of one unit (pass the level-2 scan today),
+//      15 groups whose records are all usable (plain or two-parity) with one unit, 16 the same ignoring the unit,
+//      17 level-1 runs (maximal runs of usable records of one unit inside a group), 18 records in those runs
 extern "C" void span_stats(const double *a, long n, int OB, int PER, long *out) {
     const long nblk = (n + OB - 1) / OB;
     std::vector<double> pstart(nblk);
@@ -24,6 +27,7 @@ extern "C" void span_stats(const double *a, long n, int OB, int PER, long *out) 
     double s = 0.0;
     PbState state = pb_state_from_double(s);
     int prev_e = 1 << 30;
+    std::vector<int> kind(nblk, 2), unit(nblk, 0); // 0 plain, 1 two-parity, 2 unusable
     for (long b = 0; b < nblk; b++) {
         const int cnt = (int)std::min<long>(OB, n - b * OB);
         const double *x = a + b * OB;
@@ -80,6 +84,8 @@ extern "C" void span_stats(const double *a, long n, int OB, int PER, long *out) 
                 out[why == 1 ? 3 : why == 2 ? 4 : why == 3 ? 5 : 6]++;
             } else {
                 const bool low = pb_exponent_of(pstart[b]) - eref < 1;
+                kind[b] = (sens && low) ? 1 : 0;
+                unit[b] = eref;
                 if (sens && low) out[7]++;
                 if (sens && !low) out[8]++;
                 if (prev_e != (1 << 30) && prev_e != eref) out[9]++;
@@ -95,5 +101,26 @@ extern "C" void span_stats(const double *a, long n, int OB, int PER, long *out) 
         }
         if (!applied) { state = pb_state_from_double(truth); out[12] += cnt; }
         s = truth;
+    }
+    for (long g0 = 0; g0 < nblk; g0 += 32) {
+        const long g1 = std::min<long>(g0 + 32, nblk);
+        bool plain = true, usable = true, one_unit = true;
+        for (long b = g0; b < g1; b++) {
+            plain &= kind[b] == 0;
+            usable &= kind[b] != 2;
+            one_unit &= unit[b] == unit[g0];
+        }
+        out[13]++;
+        out[14] += plain && one_unit;
+        out[15] += usable && one_unit;
+        out[16] += usable;
+        for (long b = g0; b < g1;) {
+            if (kind[b] == 2) { b++; continue; }
+            long e = b + 1;
+            while (e < g1 && kind[e] != 2 && unit[e] == unit[b]) e++;
+            out[17]++;
+            out[18] += e - b;
+            b = e;
+        }
     }
 }
