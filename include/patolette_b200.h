@@ -49,8 +49,11 @@ typedef struct patolette__QuantizationOptions {
  * palette: caller-allocated palette_size x 3 f64 column-major; unused rows = -1.
  * palette_map: caller-allocated width*height size_t (may be NULL iff palette_only).
  * exit_code: 0 ok, -1 internal, -2 bad dims, -3 bad palette size, -4 too big;
- * additionally -5 = CUDA failure (no GPU / out of memory), which the reference
- * cannot produce.  Synchronous; inputs are never written. */
+ * additionally -5 = CUDA failure (no GPU / out of memory) and -6 = palette_size above
+ * 50000 together with kmeans_niter > 0 (the reference accepts any size; the f32 KMeans
+ * slice here does not), which the reference cannot produce.  -1 also covers "no LAPACK
+ * dsyev_ found" (patolette_b200_set_lapack).  Synchronous; inputs are never written;
+ * calls from several threads are serialised. */
 PB200_API void patolette(size_t width, size_t height, const double *data, const double *weights,
                size_t palette_size, const patolette__QuantizationOptions *options,
                double *palette, size_t *palette_map, int *exit_code);
@@ -133,20 +136,27 @@ PB200_API int patolette_b200_gq_cuts(const double *bucket_sums, const unsigned i
 /* Chain-sharded multi-GPU runs: every rank (process + GPU) is given the SAME image and calls
  * patolette() at the same time; rank r computes the ordered sums of the chains it owns and the ranks exchange
  * their per-cluster moment rows through `allgather`, which must gather `bytes` bytes from every rank into
- * `recv` (world * bytes, rank-major) - host memory, any transport.  Results are identical for every world size.
+ * `recv` (world * bytes, rank-major) - host memory, any transport - and return 0; a non-zero return aborts the
+ * running patolette() call on this rank with exit code -1.  Results are identical for every world size.
  * world = 1 (default) switches sharding off.  Returns 0, -1 on bad arguments. */
-typedef void (*patolette_b200_allgather_fn)(const void *send, void *recv, size_t bytes, void *user);
+typedef int (*patolette_b200_allgather_fn)(const void *send, void *recv, size_t bytes, void *user);
 PB200_API int patolette_b200_set_sharding(int rank, int world, patolette_b200_allgather_fn allgather, void *user);
 /* Test / tuning knobs (never change results, only the route taken): "dump_cap" = cap on the term-dump slots
  * of an ordered-sum pass (-1 default; 0 = every replay recomputes its terms from the planes), "overlap" =
  * two-stream half-batch evaluation of the split loop (-1 default, 0 off, 1 on), "gq_threads" = host threads of the GQ
  * dynamic programme (0 default), "nn_grid" / "dither_grid" = nearest
  * map / the dither's per-step search through per-cell candidate lists (1, default) or brute force (0).
+ * "allow_jacobi" = 1 lets a built-in Jacobi solver stand in when no LAPACK dsyev_ can be resolved (default 0: such
+ * a call fails with exit code -1, because eigenvector signs - hence palette order - would differ from the reference).
  * Returns 0, -1 if unknown. */
 PB200_API int patolette_b200_set_option(const char *name, long long value);
 /* Debug: per chain of the centred pass {cycles scan walk, cycles record walk, cycles replays, replays,
  * records walked one by one}, 7 x 5 counters. */
 PB200_API int patolette_b200_ordered_chain_debug(unsigned long long *out35, int reset);
+
+/* FP64 FMA throughput of the current device, TFLOP/s (a register-resident DFMA kernel timed with CUDA events;
+ * the denominator of bench.py's FP64 fractions).  Negative cudaError on failure. */
+PB200_API double patolette_b200_fp64_peak(void);
 
 /* Timings of the last patolette() call on this process, milliseconds (CUDA events
  * on the library's stream; h2d/d2h include the host copies).  Keys in order:

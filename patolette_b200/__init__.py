@@ -76,6 +76,10 @@ def quantize(width, height, colors, palette_size, dither=True, palette_only=Fals
                   None if w is None else w.ctypes.data, palette_size, C.byref(opts),
                   palette.ctypes.data if palette_size else None,
                   None if pmap is None else pmap.ctypes.data, C.byref(code))
+    global _shard_error
+    if _shard_error is not None:  # the all-gather callback failed: surface it instead of exit code -1
+        err, _shard_error = _shard_error, None
+        raise err
     success = code.value == 0
     message = lib.get_patolette_exit_code_info_message(code.value).decode("utf-8")
     if not success:
@@ -86,6 +90,7 @@ def quantize(width, height, colors, palette_size, dither=True, palette_only=Fals
 
 
 _shard_cb = None  # keeps the ctypes callback alive
+_shard_error = None  # exception raised inside the all-gather callback of the running call
 
 
 def set_sharding(rank: int, world: int, allgather=None) -> None:
@@ -104,12 +109,20 @@ def set_sharding(rank: int, world: int, allgather=None) -> None:
     if allgather is None:
         raise ValueError("world > 1 needs an allgather callable")
 
-    @C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
+    @C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
     def cb(send, recv, nbytes, _user):
-        out = allgather(C.string_at(send, nbytes))
-        if len(out) != nbytes * world:
-            raise RuntimeError("allgather returned %d bytes, expected %d" % (len(out), nbytes * world))
-        C.memmove(recv, out, len(out))
+        # ctypes swallows exceptions raised inside a callback: catch, stash, and tell the C side to abort
+        # the call (exit code -1); quantize() re-raises the stashed exception
+        global _shard_error
+        try:
+            out = allgather(C.string_at(send, nbytes))
+            if len(out) != nbytes * world:
+                raise RuntimeError("allgather returned %d bytes, expected %d" % (len(out), nbytes * world))
+            C.memmove(recv, out, len(out))
+            return 0
+        except BaseException as e:  # noqa: BLE001 - must not propagate into C
+            _shard_error = e
+            return 1
 
     if lib.patolette_b200_set_sharding(int(rank), int(world), C.cast(cb, C.c_void_p), None) != 0:
         raise ValueError("bad sharding arguments")

@@ -213,12 +213,14 @@ __global__ void __launch_bounds__(DT_WARPS * 32) k_riemersma_spec(const double *
                                                                  const double *__restrict__ palw, int K,
                                                                  const double *__restrict__ qweights,
                                                                  uint32_t *__restrict__ hidx, uint32_t *__restrict__ overlap,
-                                                                 const void *__restrict__ nngrid) {
+                                                                 const void *__restrict__ nngrid, bool pal_in_smem) {
     extern __shared__ double s_mem[];
-    double *s_pal = s_mem, *s_palw = s_mem + (size_t)K * 3;
+    // palettes too large for shared memory (48 B x K) are read from global memory
+    const double *s_pal = pal_in_smem ? s_mem : pal, *s_palw = pal_in_smem ? s_mem + (size_t)K * 3 : palw;
     __shared__ double s_geom[6];
     __shared__ int s_grid_ok;
-    for (int i = threadIdx.x; i < K * 3; i += blockDim.x) { s_pal[i] = pal[i]; s_palw[i] = palw[i]; }
+    if (pal_in_smem)
+        for (int i = threadIdx.x; i < K * 3; i += blockDim.x) { s_mem[i] = pal[i]; s_mem[(size_t)K * 3 + i] = palw[i]; }
     if (threadIdx.x == 0) {
         s_grid_ok = 0;
         if (nngrid) {
@@ -253,13 +255,14 @@ __global__ void __launch_bounds__(32) k_riemersma_repair(const double *__restric
                                                          int K, const double *__restrict__ qweights,
                                                          uint32_t *__restrict__ hidx, const uint32_t *__restrict__ overlap,
                                                          unsigned long long *__restrict__ stats,
-                                                         const void *__restrict__ nngrid) {
+                                                         const void *__restrict__ nngrid, bool pal_in_smem) {
     extern __shared__ double s_mem[];
-    double *s_pal = s_mem, *s_palw = s_mem + (size_t)K * 3;
+    const double *s_pal = pal_in_smem ? s_mem : pal, *s_palw = pal_in_smem ? s_mem + (size_t)K * 3 : palw;
     __shared__ double s_geom[6];
     __shared__ int s_grid_ok;
     const int lane = threadIdx.x;
-    for (int i = lane; i < K * 3; i += 32) { s_pal[i] = pal[i]; s_palw[i] = palw[i]; }
+    if (pal_in_smem)
+        for (int i = lane; i < K * 3; i += 32) { s_mem[i] = pal[i]; s_mem[(size_t)K * 3 + i] = palw[i]; }
     if (lane == 0) {
         s_grid_ok = 0;
         if (nngrid) {
@@ -375,7 +378,8 @@ void pb_dither_riemersma(const double *const planes[3], size_t width, size_t hei
         const size_t nseg = (n + seg - 1) / seg;
         d_overlap = (uint32_t *)pb_pool_alloc((nseg + 1) * 16 * sizeof(uint32_t));
         d_stats = (unsigned long long *)pb_pool_alloc(2 * sizeof(unsigned long long));
-        const size_t smem = (size_t)K * 6 * sizeof(double);
+        const bool pal_in_smem = (size_t)K * 6 * sizeof(double) <= PB_SMEM_PALETTE_LIMIT;
+        const size_t smem = pal_in_smem ? (size_t)K * 6 * sizeof(double) : 0;
         if (smem > 48 * 1024) {
             PB_CUDA_OK(cudaFuncSetAttribute(k_riemersma_spec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             PB_CUDA_OK(cudaFuncSetAttribute(k_riemersma_repair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -391,11 +395,11 @@ void pb_dither_riemersma(const double *const planes[3], size_t width, size_t hei
         }
         { PbProfScope _prof("k_riemersma_spec", st);
         k_riemersma_spec<<<(unsigned)((nseg + DT_WARPS - 1) / DT_WARPS), DT_WARPS * 32, smem, st>>>(
-            d_h[0], d_h[1], d_h[2], n, seg, warm, d_pal, d_palw, K, d_qw, d_hidx, d_overlap, d_grid);
+            d_h[0], d_h[1], d_h[2], n, seg, warm, d_pal, d_palw, K, d_qw, d_hidx, d_overlap, d_grid, pal_in_smem);
         }
         { PbProfScope _prof("k_riemersma_repair", st);
         k_riemersma_repair<<<1, 32, smem, st>>>(d_h[0], d_h[1], d_h[2], n, seg, d_pal, d_palw, K, d_qw, d_hidx,
-                                                d_overlap, d_stats, d_grid);
+                                                d_overlap, d_stats, d_grid, pal_in_smem);
         }
         { PbProfScope _prof("k_unpermute", st);
         k_unpermute<<<grid, 256, 0, st>>>(d_rank, d_hidx, n, d_map);

@@ -5,4 +5,5 @@
 
 void pb_lapack_set_path(const char *path);
 const char *pb_lapack_source();
+void pb_lapack_allow_jacobi(bool on);
 bool pb_eigen_solve3(double a[9], double w[3]);

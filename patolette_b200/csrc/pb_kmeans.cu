@@ -123,33 +123,43 @@ __global__ void k_scan_finite(const double *__restrict__ c0, const double *__res
     if (bad) atomicOr(nonfinite, 1);
 }
 
+// (y0, y1, y2, |y|^2) per centroid; fvec_norms_L2sqr: ((y0^2 + y1^2) + y2^2), separately rounded
+__global__ void k_cen4(const float *__restrict__ cen, int K, float4 *__restrict__ cen4, const int *__restrict__ stop) {
+    if (*stop) return;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= K) return;
+    const float a = cen[3 * j], b = cen[3 * j + 1], c = cen[3 * j + 2];
+    cen4[j] = make_float4(a, b, c, __fadd_rn(__fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b)), __fmul_rn(c, c)));
+}
+
+// IN_SMEM: the centroid table sits in shared memory (16 B x K); palettes too large for that are read from
+// global memory - every lane asks for the same entry, so the loads are L1-served broadcasts.
+template <bool IN_SMEM>
 __global__ void __launch_bounds__(256) k_assign(const float *__restrict__ x0, const float *__restrict__ x1,
                                                 const float *__restrict__ x2, size_t nx,
-                                                const float *__restrict__ cen, int K, bool seq_path,
+                                                const float4 *__restrict__ cen4, int K, bool seq_path,
                                                 uint16_t *__restrict__ assign, const int *__restrict__ stop) {
-    extern __shared__ float s_cen[]; // K * 4: y0 y1 y2 |y|^2
+    extern __shared__ float4 s_cen[];
     if (*stop) return; // an earlier iteration produced an empty cluster: the host takes over from there
-    for (int j = threadIdx.x; j < K; j += blockDim.x) {
-        const float a = cen[3 * j], b = cen[3 * j + 1], c = cen[3 * j + 2];
-        s_cen[4 * j] = a; s_cen[4 * j + 1] = b; s_cen[4 * j + 2] = c;
-        // fvec_norms_L2sqr: ((y0^2 + y1^2) + y2^2), separately rounded
-        s_cen[4 * j + 3] = __fadd_rn(__fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b)), __fmul_rn(c, c));
+    if (IN_SMEM) {
+        for (int j = threadIdx.x; j < K; j += blockDim.x) s_cen[j] = cen4[j];
+        __syncthreads();
     }
-    __syncthreads();
+    const float4 *tab = IN_SMEM ? s_cen : cen4;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nx; i += (size_t)gridDim.x * blockDim.x) {
         const float a = x0[i], b = x1[i], c = x2[i];
         const float xn = __fadd_rn(__fadd_rn(__fmul_rn(a, a), __fmul_rn(b, b)), __fmul_rn(c, c));
         float bd = 0.f;
         int best = 0;
         for (int j = 0; j < K; j++) {
+            const float4 y = tab[j];
             float dd;
             if (seq_path) { // fewer than 20 queries: exhaustive_L2sqr_seq -> fvec_L2sqr
-                const float d0 = __fsub_rn(a, s_cen[4 * j]), d1 = __fsub_rn(b, s_cen[4 * j + 1]),
-                            d2 = __fsub_rn(c, s_cen[4 * j + 2]);
+                const float d0 = __fsub_rn(a, y.x), d1 = __fsub_rn(b, y.y), d2 = __fsub_rn(c, y.z);
                 dd = __fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2));
             } else { // distances.cpp:259-343: dis = x_norms + y_norms - 2 * ip, ip from sgemm_ (k = 3)
-                const float ip = __fmaf_rn(c, s_cen[4 * j + 2], __fmaf_rn(b, s_cen[4 * j + 1], __fmul_rn(a, s_cen[4 * j])));
-                dd = __fsub_rn(__fadd_rn(xn, s_cen[4 * j + 3]), __fmul_rn(2.f, ip));
+                const float ip = __fmaf_rn(c, y.z, __fmaf_rn(b, y.y, __fmul_rn(a, y.x)));
+                dd = __fsub_rn(__fadd_rn(xn, y.w), __fmul_rn(2.f, ip));
                 if (dd < 0) dd = 0;
             }
             if (j == 0 || dd < bd) { bd = dd; best = j; }
@@ -276,9 +286,12 @@ void pb_kmeans_device(const float *d_x0, const float *d_x1, const float *d_x2, c
     PB_CUDA_OK(cudaMemcpyAsync(d_seg, &whole, sizeof whole, cudaMemcpyHostToDevice, st));
     size_t want = (nx + 255) / 256, cap = (size_t)sm_count * 8;
     const int grid = (int)(want < cap ? (want ? want : 1) : cap);
-    const size_t smem = (size_t)K * 4 * sizeof(float);
+    const size_t smem_want = (size_t)K * sizeof(float4);
+    const bool cen_in_smem = smem_want <= PB_SMEM_PALETTE_LIMIT;
+    const size_t smem = cen_in_smem ? smem_want : 0;
     if (smem > 48 * 1024)
-        PB_CUDA_OK(cudaFuncSetAttribute(k_assign, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PB_CUDA_OK(cudaFuncSetAttribute(k_assign<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    float4 *d_cen4 = mem.alloc<float4>((size_t)K);
     int *d_stop = mem.alloc<int>(1);
     { PbProfScope _prof("k_pack_samples", st, false);
       k_pack_samples<<<grid, 256, 0, st>>>(d_x0, d_x1, d_x2, d_wf, nx, d_aos); }
@@ -290,8 +303,12 @@ void pb_kmeans_device(const float *d_x0, const float *d_x1, const float *d_x2, c
         PB_CUDA_OK(cudaMemcpyAsync(d_cen, cen.data(), cen.size() * sizeof(float), cudaMemcpyHostToDevice, st));
         PB_CUDA_OK(cudaMemsetAsync(d_stop, 0, sizeof(int), st));
         for (int i = it; i < niter; i++) {
+            { PbProfScope _prof("k_cen4", st, false);
+            k_cen4<<<(K + 255) / 256, 256, 0, st>>>(d_cen, K, d_cen4, d_stop);
+            }
             { PbProfScope _prof("k_assign", st);
-            k_assign<<<grid, 256, smem, st>>>(d_x0, d_x1, d_x2, nx, d_cen, K, nx < 20, d_assign, d_stop);
+            if (cen_in_smem) k_assign<true><<<grid, 256, smem, st>>>(d_x0, d_x1, d_x2, nx, d_cen4, K, nx < 20, d_assign, d_stop);
+            else k_assign<false><<<grid, 256, 0, st>>>(d_x0, d_x1, d_x2, nx, d_cen4, K, nx < 20, d_assign, d_stop);
             }
             pb_launch_class_rank(PB_CLS_BUCKET, K, d_seg, 1, (uint32_t)nx, tiles, d_assign, nullptr, nullptr, d_tile_hist,
                                  d_cstart, st);
@@ -351,7 +368,9 @@ void pb_kmeans_refine(const double *const planes[3], const double *d_w, size_t n
     auto finish = [&]() { // refine.c:202-212 runs whatever faiss did (error code ignored, bug B8)
         for (size_t j = 0; j < 3 * K; j++) pal_rm[j] = (double)cen[j];
     };
-    if (n < K || K > 65535) { finish(); return; } // Clustering.cpp:273-279 throws; K > 65535: not supported
+    // Clustering.cpp:273-279 throws for n < K.  K > PB_KMEANS_MAX_K with n >= K never gets here: patolette()
+    // rejects it with exit code -6 (16-bit assignments, per-warp class counters of the stable sort).
+    if (n < K || K > PB_KMEANS_MAX_K) { finish(); return; }
     DevMem mem;
     int *d_flag = mem.alloc<int>(1);
     PB_CUDA_OK(cudaMemsetAsync(d_flag, 0, sizeof(int), st));

@@ -10,9 +10,11 @@
 //      patolette_b200_set_lapack() by the Python wrapper (scipy's bundled OpenBLAS);
 //   2. the usual system sonames.
 // This is O(K) host work per image (one 3x3 solve per tree node), not a pixel path.
-// If no LAPACK can be found a cyclic-Jacobi solver keeps the library functional, with a
-// one-time warning: eigenvector signs - hence palette ORDER - may then differ from the
-// reference.
+// If no LAPACK can be found the library FAILS CLOSED: pb_eigen_solve3 returns false and
+// patolette() ends with exit code -1 (a drop-in must not silently return a permuted
+// palette).  A caller that accepts that divergence opts in with
+// patolette_b200_set_option("allow_jacobi", 1): a cyclic-Jacobi solver then stands in -
+// eigenvector signs, hence palette ORDER, may differ from the reference.
 #include <dlfcn.h>
 #include <math.h>
 #include <stdio.h>
@@ -34,6 +36,7 @@ dsyev_fn g_dsyev = nullptr;
 bool g_tried = false;
 std::string g_user_path;
 std::string g_source = "unresolved";
+bool g_allow_jacobi = false;
 
 dsyev_fn try_open(const char *path) {
     void *h = dlopen(path, RTLD_NOW | RTLD_LOCAL);
@@ -63,8 +66,11 @@ void resolve_locked() {
     if (!g_dsyev) {
         g_source = "builtin-jacobi";
         fprintf(stderr,
-                "patolette_b200: no LAPACK dsyev_ found (set PATOLETTE_B200_LAPACK); using the built-in "
-                "Jacobi solver - eigenvector signs and hence palette order may differ from the reference\n");
+                "patolette_b200: no LAPACK dsyev_ found (set PATOLETTE_B200_LAPACK or call patolette_b200_set_lapack); "
+                "%s\n", g_allow_jacobi ? "allow_jacobi is set: using the built-in Jacobi solver - eigenvector signs and "
+                                         "hence palette order may differ from the reference"
+                                       : "failing the call (exit code -1); patolette_b200_set_option(\"allow_jacobi\", 1) "
+                                         "accepts a built-in solver whose palette order may differ from the reference");
     }
 }
 
@@ -115,6 +121,13 @@ void pb_lapack_set_path(const char *path) {
     g_dsyev = nullptr;
 }
 
+void pb_lapack_allow_jacobi(bool on) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_allow_jacobi = on;
+    g_tried = false; // the warning text depends on it
+    g_dsyev = nullptr;
+}
+
 const char *pb_lapack_source() {
     std::lock_guard<std::mutex> lk(g_mu);
     resolve_locked();
@@ -126,12 +139,15 @@ const char *pb_lapack_source() {
 // (the only failure the reference observes, eigen.c:115-118).
 bool pb_eigen_solve3(double a[9], double w[3]) {
     dsyev_fn fn;
+    bool jacobi;
     {
         std::lock_guard<std::mutex> lk(g_mu);
         resolve_locked();
         fn = g_dsyev;
+        jacobi = g_allow_jacobi;
     }
     if (!fn) {
+        if (!jacobi) return false; // fail closed: the caller ends with exit code -1
         jacobi3(a, w);
         return true;
     }

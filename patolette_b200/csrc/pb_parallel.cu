@@ -3,6 +3,7 @@
 // nearest-palette assignment.  All are HBM-streaming kernels over planar f64.
 #include "pb_common.cuh"
 #include "pb_kernels.h"
+#include "pb_pipeline.h"
 #include "pb_prof.h"
 
 namespace {
@@ -398,13 +399,17 @@ __global__ void k_make_children(const PbSeg *__restrict__ segs, int nseg, const 
 // Palette in shared memory (broadcast reads); 24 B read + 8 B written per pixel but
 // 9*K FP64 operations, so FP64-pipe bound for K >= ~16.
 // ---------------------------------------------------------------------------------
+template <bool IN_SMEM> // palettes too large for shared memory are read from global memory (broadcast loads)
 __global__ void __launch_bounds__(256) k_nearest(const double *__restrict__ c0, const double *__restrict__ c1,
                                                  const double *__restrict__ c2, size_t n,
                                                  const double *__restrict__ pal, int K,
                                                  unsigned long long *__restrict__ map) {
-    extern __shared__ double s_pal[];
-    for (int i = threadIdx.x; i < K * 3; i += blockDim.x) s_pal[i] = pal[i];
-    __syncthreads();
+    extern __shared__ double s_pal_buf[];
+    if (IN_SMEM) {
+        for (int i = threadIdx.x; i < K * 3; i += blockDim.x) s_pal_buf[i] = pal[i];
+        __syncthreads();
+    }
+    const double *s_pal = IN_SMEM ? s_pal_buf : pal;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const double x = c0[i], y = c1[i], z = c2[i];
@@ -569,10 +574,12 @@ void pb_launch_nearest(const double *const planes[3], size_t n, const double *d_
     size_t want = (n + 255) / 256, cap = (size_t)sm_count * 8;
     const int grid = (int)(want < cap ? want : cap);
     const size_t smem = (size_t)K * 3 * sizeof(double);
-    if (smem > 48 * 1024)
-        PB_CUDA_OK(cudaFuncSetAttribute(k_nearest, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const bool in_smem = smem <= PB_SMEM_PALETTE_LIMIT;
+    if (in_smem && smem > 48 * 1024)
+        PB_CUDA_OK(cudaFuncSetAttribute(k_nearest<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     { PbProfScope _prof("k_nearest", st);
-    k_nearest<<<grid, 256, smem, st>>>(planes[0], planes[1], planes[2], n, d_palette_rm, K, d_map);
+    if (in_smem) k_nearest<true><<<grid, 256, smem, st>>>(planes[0], planes[1], planes[2], n, d_palette_rm, K, d_map);
+    else k_nearest<false><<<grid, 256, 0, st>>>(planes[0], planes[1], planes[2], n, d_palette_rm, K, d_map);
     }
     PB_CUDA_OK(cudaGetLastError());
 }

@@ -13,6 +13,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 #include <vector>
 
 #include "../../include/patolette_b200.h"
@@ -27,6 +28,9 @@
 
 namespace {
 
+// The library keeps per-process state (streams, pinned bounce lanes, timings, the buffer cache): calls are
+// serialised.  One call saturates the GPU anyway.
+std::mutex g_call_mu;
 int g_device = 0;
 int g_overlap_override = -1; // patolette_b200_set_option "overlap": -1 default, 0 off, 1 on
 bool g_nn_grid = true;       // patolette_b200_set_option "nn_grid": candidate-list 1-NN (pb_nngrid.cu) vs brute force
@@ -60,11 +64,12 @@ unsigned cent_mask() {
 }
 // all-gather `count` rows and keep, for every field, the owner's value.  Mean pass: the raw sums are scaled
 // here (matrix2D.c:230-231: mean = sum * (1 / wsum)) - the same two IEEE operations the kernel performs.
+struct pb_shard_error {}; // the caller's all-gather failed: the call ends with exit code -1 on this rank
 void shard_merge(PbStats *rows, int count, bool mean_pass, bool weighted) {
     if (!sharded() || count <= 0) return;
     static thread_local std::vector<PbStats> all;
-    all.resize((size_t)count * g_shard_world);
-    g_shard_allgather(rows, all.data(), (size_t)count * sizeof(PbStats), g_shard_user);
+    all.assign((size_t)count * g_shard_world, PbStats{});
+    if (g_shard_allgather(rows, all.data(), (size_t)count * sizeof(PbStats), g_shard_user) != 0) throw pb_shard_error{};
     for (int i = 0; i < count; i++) {
         auto from = [&](int rank) -> const PbStats & { return all[(size_t)rank * count + i]; };
         if (mean_pass) {
@@ -729,13 +734,29 @@ struct Quantizer {
 
 void set_timing(int slot, double ms) { g_timings[slot] = ms; }
 
-const char *k_messages[6] = {
+// FP64 throughput probe (the denominator of bench.py's FP64-ALU fractions): 8 independent DFMA chains per thread
+__global__ void __launch_bounds__(256) k_fp64_peak(double *out, int iters, double a, double b) {
+    double x[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) x[i] = (double)(threadIdx.x + i);
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) x[i] = __fma_rn(x[i], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += x[i];
+    if (s == 12345.678) out[0] = s; // never true: keeps the chains alive
+}
+
+const char *k_messages[7] = {
     "Quantization successful.",
     "Internal quantization error.",
     "Image dimensions should be greater than 0.",
     "Palette size should be greater than 0.",
     "Image dimensions are too big.",
     "CUDA error (no usable sm_100 device, or out of device memory).",
+    "Palette size above 50000 with KMeans refinement (kmeans_niter > 0) is not supported by patolette_b200.",
 };
 
 // Palette (K x 3 row-major, host) through one of the colour kernels.
@@ -768,6 +789,9 @@ void run_patolette(size_t width, size_t height, const double *data, const double
                    const patolette__QuantizationOptions *opt, double *palette, size_t *palette_map,
                    int *exit_code, bool device_io, bool interleaved = false) {
     const size_t n = width * height;
+    // the f32 KMeans slice sorts samples by a 16-bit assignment through per-warp class counters in shared
+    // memory: beyond PB_KMEANS_MAX_K the call fails with its own code instead of silently skipping refinement
+    if (opt->kmeans_niter > 0 && K > PB_KMEANS_MAX_K && n >= K) { *exit_code = -6; return; }
     memset(g_timings, 0, sizeof g_timings);
     const long launches0 = pb_prof_launch_count();
     Quantizer qz;
@@ -944,6 +968,45 @@ void run_patolette(size_t width, size_t height, const double *data, const double
     *exit_code = 0;
 }
 
+// Every entry point that runs the pipeline: one call at a time, and nothing but an exit code crosses the C ABI.
+// Before buffers go back to the cache on an error path the device is drained (kernels of the failed call may
+// still be running on the side streams).
+template <typename F>
+void guarded_run(int *exit_code, F &&body) {
+    std::lock_guard<std::mutex> lk(g_call_mu);
+    try {
+        body();
+    } catch (const pb_cuda_error &) {
+        cudaGetLastError();
+        cudaDeviceSynchronize();
+        cudaGetLastError();
+        *exit_code = -5;
+    } catch (const pb_shard_error &) {
+        cudaDeviceSynchronize();
+        *exit_code = -1;
+    } catch (...) { // std::bad_alloc, std::system_error from a host thread, std::length_error, ...
+        cudaDeviceSynchronize();
+        cudaGetLastError();
+        *exit_code = -1;
+    }
+}
+template <typename F>
+int guarded_stage(F &&body) {
+    std::lock_guard<std::mutex> lk(g_call_mu);
+    try {
+        return body();
+    } catch (const pb_cuda_error &e) {
+        cudaGetLastError();
+        cudaDeviceSynchronize();
+        cudaGetLastError();
+        return -(int)e.code;
+    } catch (...) {
+        cudaDeviceSynchronize();
+        cudaGetLastError();
+        return -1;
+    }
+}
+
 } // namespace
 
 // ======================================================================================
@@ -958,14 +1021,9 @@ void patolette(size_t width, size_t height, const double *data, const double *we
     if (width * height == 0) { *exit_code = -2; return; }
     if (palette_size < 1) { *exit_code = -3; return; }
     if (width * height > (size_t)40000 * 40000) { *exit_code = -4; return; }
-    try {
+    guarded_run(exit_code, [&] {
         run_patolette(width, height, data, weights, palette_size, options, palette, palette_map, exit_code, false);
-    } catch (const pb_cuda_error &) {
-        cudaGetLastError();
-        *exit_code = -5;
-    } catch (const std::bad_alloc &) {
-        *exit_code = -1;
-    }
+    });
 }
 
 void patolette_b200_device(size_t width, size_t height, const double *d_data, const double *d_weights,
@@ -975,14 +1033,9 @@ void patolette_b200_device(size_t width, size_t height, const double *d_data, co
     if (width * height == 0) { *exit_code = -2; return; }
     if (palette_size < 1) { *exit_code = -3; return; }
     if (width * height > (size_t)40000 * 40000) { *exit_code = -4; return; }
-    try {
+    guarded_run(exit_code, [&] {
         run_patolette(width, height, d_data, d_weights, palette_size, options, palette, d_palette_map, exit_code, true);
-    } catch (const pb_cuda_error &) {
-        cudaGetLastError();
-        *exit_code = -5;
-    } catch (const std::bad_alloc &) {
-        *exit_code = -1;
-    }
+    });
 }
 
 void patolette_b200_interleaved(size_t width, size_t height, const double *rgb, const double *weights,
@@ -992,21 +1045,16 @@ void patolette_b200_interleaved(size_t width, size_t height, const double *rgb, 
     if (width * height == 0) { *exit_code = -2; return; }
     if (palette_size < 1) { *exit_code = -3; return; }
     if (width * height > (size_t)40000 * 40000) { *exit_code = -4; return; }
-    try {
+    guarded_run(exit_code, [&] {
         run_patolette(width, height, rgb, weights, palette_size, options, palette, palette_map, exit_code, false, true);
-    } catch (const pb_cuda_error &) {
-        cudaGetLastError();
-        *exit_code = -5;
-    } catch (const std::bad_alloc &) {
-        *exit_code = -1;
-    }
+    });
 }
 
 int patolette_b200_ordered_counts(unsigned long long *out2, int reset) {
-    try {
+    return guarded_stage([&]() -> int {
         pb_ordered_counts(out2, reset != 0);
         return 0;
-    } catch (const pb_cuda_error &e) { return -(int)e.code; }
+    });
 }
 
 int patolette_b200_gq_cuts(const double *bucket_sums, const unsigned int *class_start, size_t palette_size, size_t *cuts16) {
@@ -1036,14 +1084,15 @@ int patolette_b200_set_option(const char *name, long long value) {
     if (!strcmp(name, "gq_threads")) { g_gq_threads = (int)value; return 0; }
     if (!strcmp(name, "gq_full_table")) { g_gq_full_table = value != 0; return 0; }
     if (!strcmp(name, "dither_grid")) { pb_dither_set_grid(value != 0); return 0; }
+    if (!strcmp(name, "allow_jacobi")) { pb_lapack_allow_jacobi(value != 0); return 0; }
     return -1;
 }
 
 int patolette_b200_ordered_chain_debug(unsigned long long *out35, int reset) {
-    try {
+    return guarded_stage([&]() -> int {
         pb_ordered_chain_debug(out35, reset != 0);
         return 0;
-    } catch (const pb_cuda_error &e) { return -(int)e.code; }
+    });
 }
 
 size_t patolette_b200_release_cache(void) {
@@ -1076,7 +1125,7 @@ size_t patolette_b200_profile_json(char *buf, size_t cap) {
 
 const char *get_patolette_exit_code_info_message(int exit_code) {
     int i = -exit_code;
-    if (i < 0 || i > 5) i = 1;
+    if (i < 0 || i > 6) i = 1;
     return k_messages[i];
 }
 
@@ -1107,13 +1156,45 @@ int patolette_b200_device_count(void) {
 void patolette_b200_set_lapack(const char *path) { pb_lapack_set_path(path); }
 const char *patolette_b200_lapack_source(void) { return pb_lapack_source(); }
 
+double patolette_b200_fp64_peak(void) {
+    std::lock_guard<std::mutex> lk(g_call_mu);
+    try {
+        PB_CUDA_OK(cudaSetDevice(g_device));
+        int sms = 0;
+        PB_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g_device));
+        double *d = (double *)pb_pool_alloc(64);
+        cudaEvent_t e0, e1;
+        PB_CUDA_OK(cudaEventCreate(&e0));
+        PB_CUDA_OK(cudaEventCreate(&e1));
+        const int iters = 1 << 14, grid = sms * 8;
+        double best = 0;
+        for (int rep = 0; rep < 4; rep++) { // the first repetition warms up
+            PB_CUDA_OK(cudaEventRecord(e0, 0));
+            k_fp64_peak<<<grid, 256>>>(d, iters, 1.0000001, 1e-9);
+            PB_CUDA_OK(cudaEventRecord(e1, 0));
+            PB_CUDA_OK(cudaEventSynchronize(e1));
+            float ms = 0;
+            PB_CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+            const double tf = 2.0 * 8 * iters * 256.0 * grid / (ms * 1e-3) / 1e12;
+            if (rep && tf > best) best = tf;
+        }
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        pb_pool_free(d);
+        return best;
+    } catch (const pb_cuda_error &e) {
+        cudaGetLastError();
+        return -(double)e.code;
+    }
+}
+
 int patolette_b200_last_timings(double *out10) {
     memcpy(out10, g_timings, sizeof g_timings);
     return 0;
 }
 
 int patolette_b200_color_transform(int which, double *planar, size_t n) {
-    try {
+    return guarded_stage([&]() -> int {
         Quantizer qz;
         qz.init(n, false);
         for (int j = 0; j < 3; j++) qz.h2d(qz.col[j].p, planar + (size_t)j * n, n);
@@ -1121,11 +1202,11 @@ int patolette_b200_color_transform(int which, double *planar, size_t n) {
         for (int j = 0; j < 3; j++) qz.d2h(planar + (size_t)j * n, qz.col[j].p, n);
         qz.sync();
         return 0;
-    } catch (const pb_cuda_error &e) { return -(int)e.code; }
+    });
 }
 
 int patolette_b200_pow(const double *x, double y, double *out, size_t n) {
-    try {
+    return guarded_stage([&]() -> int {
         Quantizer qz;
         qz.init(n, false);
         qz.h2d(qz.col[0].p, x, n);
@@ -1133,12 +1214,12 @@ int patolette_b200_pow(const double *x, double y, double *out, size_t n) {
         qz.d2h(out, qz.col[1].p, n);
         qz.sync();
         return 0;
-    } catch (const pb_cuda_error &e) { return -(int)e.code; }
+    });
 }
 
 int patolette_b200_quantize_clusters(const double *planar, size_t n, const double *weights, size_t palette_size,
                                      uint32_t *labels, double *centers, size_t *count, size_t *gq_count) {
-    try {
+    return guarded_stage([&]() -> int {
         Quantizer qz;
         qz.init(n, weights != nullptr);
         for (int j = 0; j < 3; j++) qz.h2d(qz.col[j].p, planar + (size_t)j * n, n);
@@ -1177,11 +1258,11 @@ int patolette_b200_quantize_clusters(const double *planar, size_t n, const doubl
             qz.sync();
         }
         return 0;
-    } catch (const pb_cuda_error &e) { return -(int)e.code; }
+    });
 }
 
 int patolette_b200_nearest(const double *planar, size_t n, const double *palette_rm, size_t K, size_t *map) {
-    try {
+    return guarded_stage([&]() -> int {
         Quantizer qz;
         qz.init(n, false);
         for (int j = 0; j < 3; j++) qz.h2d(qz.col[j].p, planar + (size_t)j * n, n);
@@ -1202,14 +1283,14 @@ int patolette_b200_nearest(const double *planar, size_t n, const double *palette
         qz.d2h((unsigned long long *)map, dmap.p, n);
         qz.sync();
         return 0;
-    } catch (const pb_cuda_error &e) { return -(int)e.code; }
+    });
 }
 
 int patolette_b200_kmeans(const float *x, size_t n, size_t K, float *centers, const float *w, int niter,
                           int max_points_per_centroid) {
     // Mirrors faiss kmeans_clustering (Clustering.cpp:587-603) on host-provided f32 samples by
     // widening them to the f64 planes the pipeline keeps on the device ((float)(double)f == f).
-    try {
+    return guarded_stage([&]() -> int {
         if (n < K) return -1;
         Quantizer qz;
         qz.init(n, w != nullptr);
@@ -1231,12 +1312,12 @@ int patolette_b200_kmeans(const float *x, size_t n, size_t K, float *centers, co
                          &qz.launches);
         for (size_t j = 0; j < 3 * K; j++) centers[j] = (float)pal[j];
         return 0;
-    } catch (const pb_cuda_error &e) { return -(int)e.code; }
+    });
 }
 
 int patolette_b200_dither(const double *planar, size_t width, size_t height, const double *palette_rm, size_t K,
                           size_t *map) {
-    try {
+    return guarded_stage([&]() -> int {
         const size_t n = width * height;
         Quantizer qz;
         qz.init(n, false);
@@ -1251,7 +1332,7 @@ int patolette_b200_dither(const double *planar, size_t width, size_t height, con
         qz.d2h((unsigned long long *)map, dmap.p, n);
         qz.sync();
         return 0;
-    } catch (const pb_cuda_error &e) { return -(int)e.code; }
+    });
 }
 
 } // extern "C"

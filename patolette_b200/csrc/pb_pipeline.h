@@ -18,3 +18,11 @@ void pb_dither_riemersma(const double *const planes[3], size_t width, size_t hei
                          cudaStream_t st, long *launches);
 // test knob: candidate-list nearest-neighbour search inside the dither (default on)
 void pb_dither_set_grid(bool on);
+
+// Largest palette the f32 KMeans slice supports (16-bit assignments; per-warp class counters of the stable
+// sort in shared memory, 4 B x K for one warp).  Above it patolette() returns exit code -6 when
+// kmeans_niter > 0 instead of silently skipping the refinement.
+#define PB_KMEANS_MAX_K 50000
+// Dynamic shared memory a kernel may ask for (227 KB opt-in limit minus static shared memory and slack):
+// palettes that do not fit are read from global memory instead (same arithmetic, L1/L2-served broadcasts).
+#define PB_SMEM_PALETTE_LIMIT (200 * 1024)

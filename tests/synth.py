@@ -53,6 +53,36 @@ GOLDEN_CASES = {
 }
 
 
+# Configurations beyond the goldens, small: restatement vs the reference's own code live on the CPU
+# (tests/test_oracle.py) and CUDA vs the oracle on the GPU (tests/test_gpu_big.py).
+WIDER = {
+    "k1024_weighted_kmeans_dither": dict(w=320, h=240, K=1024, seed=41, color_space=2, dither=True, kmeans_niter=4, weighted=True),
+    "gradient_many_gq_cells": dict(w=400, h=300, K=200, seed=42, color_space=1, dither=False, kmeans_niter=0, image_like=True),
+    "k_above_pixel_count": dict(w=9, h=7, K=100, seed=43, color_space=2, dither=True, kmeans_niter=2),
+    "srgb_kmeans_full_image": dict(w=200, h=150, K=37, seed=44, color_space=0, dither=True, kmeans_niter=6,
+                                   kmeans_max_samples=200 * 150),
+    "luv_weighted_palette_only": dict(w=256, h=128, K=64, seed=45, color_space=1, dither=False, kmeans_niter=3, weighted=True,
+                                      palette_only=True),
+    "single_row": dict(w=4096, h=1, K=16, seed=46, color_space=2, dither=True, kmeans_niter=0),
+    "k2": dict(w=300, h=300, K=2, seed=47, color_space=2, dither=True, kmeans_niter=1),
+}
+
+# BASELINE.json's own configurations (uniform sRGB, seed = config index) and their class at a
+# size the CPU reference finishes: frozen as hashes by tests/golden/make_golden_big.py (golden_big.json).
+BIG_CASES = {
+    "c2_4096_k256_ictcp": dict(w=4096, h=4096, K=256, seed=1, color_space=2, dither=False, kmeans_niter=0),
+    "c3_8192_k256_cieluv_dither": dict(w=8192, h=8192, K=256, seed=2, color_space=1, dither=True, kmeans_niter=0),
+    "c4_16384_k256_ictcp_kmeans10_dither": dict(w=16384, h=16384, K=256, seed=3, color_space=2, dither=True, kmeans_niter=10),
+    "c4_4096_k256_ictcp_kmeans10_dither": dict(w=4096, h=4096, K=256, seed=3, color_space=2, dither=True, kmeans_niter=10),
+    "c5_2048_k1024_weighted_fullkmeans_dither": dict(w=2048, h=2048, K=1024, seed=4, color_space=2, dither=True, kmeans_niter=10,
+                                                     kmeans_max_samples=2048 * 2048, weighted=True),
+    "imagelike_2048_k256_luv_weighted_dither": dict(w=2048, h=2048, K=256, seed=5, color_space=1, dither=True, kmeans_niter=4,
+                                                    image_like=True, weighted=True),
+    "k8192_1024": dict(w=1024, h=1024, K=8192, seed=6, color_space=2, dither=True, kmeans_niter=2),
+    "k70000_512": dict(w=512, h=512, K=70000, seed=7, color_space=2, dither=False, kmeans_niter=2),
+}
+
+
 def make_case(spec: dict):
     """-> (colors, weights | None, quantize kwargs)"""
     w, h = spec["w"], spec["h"]

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from conftest import sha
-from synth import GOLDEN_CASES, make_case
+from synth import GOLDEN_CASES, WIDER, make_case
 
 
 def _check_against_golden(entry, code, pal, pmap):
@@ -37,19 +37,6 @@ def test_oracle_matches_reference_build(oracle, reflib, name):
     assert a[0] == b[0]
     assert np.array_equal(a[1].view(np.uint64), b[1].view(np.uint64))
     assert np.array_equal(a[2], b[2])
-
-
-WIDER = {  # configurations beyond the goldens: restatement vs the reference's own code, live (CPU, seconds each)
-    "k1024_weighted_kmeans_dither": dict(w=320, h=240, K=1024, seed=41, color_space=2, dither=True, kmeans_niter=4, weighted=True),
-    "gradient_many_gq_cells": dict(w=400, h=300, K=200, seed=42, color_space=1, dither=False, kmeans_niter=0, image_like=True),
-    "k_above_pixel_count": dict(w=9, h=7, K=100, seed=43, color_space=2, dither=True, kmeans_niter=2),
-    "srgb_kmeans_full_image": dict(w=200, h=150, K=37, seed=44, color_space=0, dither=True, kmeans_niter=6,
-                                   kmeans_max_samples=200 * 150),
-    "luv_weighted_palette_only": dict(w=256, h=128, K=64, seed=45, color_space=1, dither=False, kmeans_niter=3, weighted=True,
-                                      palette_only=True),
-    "single_row": dict(w=4096, h=1, K=16, seed=46, color_space=2, dither=True, kmeans_niter=0),
-    "k2": dict(w=300, h=300, K=2, seed=47, color_space=2, dither=True, kmeans_niter=1),
-}
 
 
 @pytest.mark.parametrize("name", sorted(WIDER))
