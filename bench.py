@@ -540,7 +540,7 @@ def measure_ours(args):
         return None
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        cpu_baseline, _ = time_reference(2048 if not args.side else min(args.side, 2048), 1, 0, 60.0)
+        cpu_baseline, _ = time_reference(REFERENCE_SIDE if not args.side else min(args.side, REFERENCE_SIDE), 1, 0, 60.0)
     jobs = 1 if (shard or world == 1) else world
     line = {
         "metric": METRIC,

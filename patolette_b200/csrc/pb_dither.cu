@@ -363,9 +363,11 @@ void pb_dither_riemersma(const double *const planes[3], size_t width, size_t hei
         PB_CUDA_OK(cudaMemcpyAsync(d_qw, qw, sizeof qw, cudaMemcpyHostToDevice, st));
         size_t want = (n + 255) / 256, cap = (size_t)sm_count * 8;
         const int grid = (int)(want < cap ? want : cap);
+        pb_prof_next_bytes(4.0 * (double)n);
         { PbProfScope _prof("k_hilbert_rank", st);
         k_hilbert_rank<<<grid, 256, 0, st>>>((uint32_t)width, (uint32_t)height, level, d_rank);
         }
+        pb_prof_next_bytes(52.0 * (double)n); // 24 B read + 4 B rank + 24 B written
         { PbProfScope _prof("k_permute", st);
         k_permute<<<grid, 256, 0, st>>>(planes[0], planes[1], planes[2], d_rank, n, d_h[0], d_h[1], d_h[2]);
         }
@@ -380,7 +382,7 @@ void pb_dither_riemersma(const double *const planes[3], size_t width, size_t hei
         d_stats = (unsigned long long *)pb_pool_alloc(2 * sizeof(unsigned long long));
         const bool pal_in_smem = (size_t)K * 6 * sizeof(double) <= PB_SMEM_PALETTE_LIMIT;
         const size_t smem = pal_in_smem ? (size_t)K * 6 * sizeof(double) : 0;
-        if (smem > 48 * 1024) {
+        if (smem > 32 * 1024) {
             PB_CUDA_OK(cudaFuncSetAttribute(k_riemersma_spec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             PB_CUDA_OK(cudaFuncSetAttribute(k_riemersma_repair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         }
@@ -393,6 +395,7 @@ void pb_dither_riemersma(const double *const planes[3], size_t width, size_t hei
             const double *hp[3] = {d_h[0], d_h[1], d_h[2]};
             pb_launch_nngrid_build(hp, n, d_palw, K, d_grid, sm_count, st, cw, 0.25);
         }
+        pb_prof_next_bytes(28.0 * (double)n); // 24 B of colours read + 4 B index written per pixel of the walk
         { PbProfScope _prof("k_riemersma_spec", st);
         k_riemersma_spec<<<(unsigned)((nseg + DT_WARPS - 1) / DT_WARPS), DT_WARPS * 32, smem, st>>>(
             d_h[0], d_h[1], d_h[2], n, seg, warm, d_pal, d_palw, K, d_qw, d_hidx, d_overlap, d_grid, pal_in_smem);
@@ -401,6 +404,7 @@ void pb_dither_riemersma(const double *const planes[3], size_t width, size_t hei
         k_riemersma_repair<<<1, 32, smem, st>>>(d_h[0], d_h[1], d_h[2], n, seg, d_pal, d_palw, K, d_qw, d_hidx,
                                                 d_overlap, d_stats, d_grid, pal_in_smem);
         }
+        pb_prof_next_bytes(16.0 * (double)n);
         { PbProfScope _prof("k_unpermute", st);
         k_unpermute<<<grid, 256, 0, st>>>(d_rank, d_hidx, n, d_map);
         }

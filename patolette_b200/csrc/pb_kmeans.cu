@@ -289,7 +289,7 @@ void pb_kmeans_device(const float *d_x0, const float *d_x1, const float *d_x2, c
     const size_t smem_want = (size_t)K * sizeof(float4);
     const bool cen_in_smem = smem_want <= PB_SMEM_PALETTE_LIMIT;
     const size_t smem = cen_in_smem ? smem_want : 0;
-    if (smem > 48 * 1024)
+    if (smem > 32 * 1024)
         PB_CUDA_OK(cudaFuncSetAttribute(k_assign<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     float4 *d_cen4 = mem.alloc<float4>((size_t)K);
     int *d_stop = mem.alloc<int>(1);

@@ -178,7 +178,7 @@ void pb_launch_nngrid_build(const double *const planes[3], size_t n, const doubl
       k_nn_bbox<<<(int)(want < cap ? (want ? want : 1) : cap), 256, 0, st>>>(planes[0], planes[1], planes[2], n, hdr); }
     { PbProfScope _prof("k_nn_cells", st, false);
       const size_t smem = (size_t)K * sizeof(double);
-      if (smem > 48 * 1024) PB_CUDA_OK(cudaFuncSetAttribute(k_nn_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      if (smem > 32 * 1024) PB_CUDA_OK(cudaFuncSetAttribute(k_nn_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       k_nn_cells<<<NCELL, 128, smem, st>>>(hdr, d_palette_rm, K, cnt, list); }
     PB_CUDA_OK(cudaGetLastError());
 }
@@ -192,7 +192,7 @@ void pb_launch_nearest_grid(const double *const planes[3], size_t n, const doubl
     size_t want = (n + 255) / 256, cap = (size_t)sm_count * 8;
     const int grid = (int)(want < cap ? want : cap);
     const size_t smem = (size_t)K * 3 * sizeof(double);
-    if (smem > 48 * 1024)
+    if (smem > 32 * 1024)
         PB_CUDA_OK(cudaFuncSetAttribute(k_nearest_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     { PbProfScope _prof("k_nearest", st);
       k_nearest_grid<<<grid, 256, smem, st>>>(planes[0], planes[1], planes[2], n, d_palette_rm, K, hdr, cnt, list, d_map); }

@@ -510,6 +510,165 @@ __global__ void __launch_bounds__(OS_THREADS, PB_OS_MINB) k_ord_summary(PbPlanes
     }
 }
 
+
+// ---- S3-fast: block-uniform summaries ------------------------------------------------------------------
+// The common case by far: EVERY partial sum of a block of one chain lies in the binade of the block's start
+// state (a running sum of millions of terms moves by a fraction of itself inside 512 elements).  Then every
+// step is the translation S <- S + RN_u(a_i) on ONE grid u = ulp(start) (pb_span.h, "translation"), and
+//     RN_u(a) = (a + M) - M        with M = 1.5 * 2^e:  the FPU itself quantises onto the grid,
+// two dependent additions per element instead of the level bookkeeping of the general summary.  The sum of
+// quantised terms is exact in floating point (multiples of u below 2^53 u).  A tie (a_i exactly halfway
+// between grid points: its winner depends on the parity of the state) shows up as |a_i - RN_u(a_i)| = u / 2
+// and sends the (block, chain) pair to the general path; so does everything else that is not this case.
+// The claim "all partial sums stay inside binade e" is again an INTERVAL for the exact start state, built
+// from the exact extremes of the in-order prefix sums; the resolve checks it.  Soundness is pb_span.h's:
+// this is pb_run_uniform with k = 0 on a whole block (tests/native/test_span.cpp: `fast block` cases).
+//
+// One warp per block, 16 consecutive elements per lane (in-order prefixes inside the lane, span monoid
+// across lanes).  The block's planes are staged through shared memory: coalesced 256-byte global reads,
+// then every lane reads ITS run at stride 17 (conflict-free).
+#ifndef PB_OF_WARPS
+#define PB_OF_WARPS 2
+#endif
+constexpr int OF_WARPS = PB_OF_WARPS;
+constexpr int OF_THREADS = 32 * OF_WARPS;
+#ifndef PB_OF_MINB
+#define PB_OF_MINB 6
+#endif
+constexpr long long OF_MARGIN = 1LL << 20; // units between the predicted start state and the interval's ends
+
+// terms of chain c never negative (given non-negative weights): prefix extremes are 0 and the total
+template <int KIND> __host__ __device__ constexpr bool chain_monotone(int c) {
+    return KIND == KIND_MEAN ? c == 0 : (c == 0 || c == 2 || c == 5 || c == 6);
+}
+
+template <int KIND, bool W, bool MASKED>
+__global__ void __launch_bounds__(OF_THREADS, PB_OF_MINB) k_ord_fast(PbPlanes b0, PbPlanes b1, const PbSeg *__restrict__ segs,
+                                                                     const PbStats *__restrict__ stats,
+                                                                     const double *__restrict__ psum, OrdRec *__restrict__ rec0,
+                                                                     unsigned int *__restrict__ list_count,
+                                                                     uint2 *__restrict__ list, unsigned cmask) {
+    constexpr int C = NChains<KIND>::C;
+    constexpr unsigned FULL = 0xffffffffu;
+    __shared__ double stage_all[OF_WARPS][(W ? 4 : 3) * OS_PLANE];
+    const int seg = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const PbSeg sg = segs[seg];
+    const uint32_t blk = blockIdx.x * OF_WARPS + warp;
+    if ((size_t)blk * OB >= sg.n) return; // warp-uniform
+    const PbPlanes &P = sg.buf ? b1 : b0;
+    double *stage = stage_all[warp];
+    const uint32_t nblk = (sg.n + OB - 1) / OB;
+    const uint32_t bcnt = min((uint32_t)OB, sg.n - blk * OB);
+    const size_t g0 = (size_t)sg.lo + (size_t)blk * OB;
+    // ---- stage the block ------------------------------------------------------------------------------
+#pragma unroll 4
+    for (int q = 0; q < OB / 32; q++) {
+        const uint32_t idx = q * 32 + lane;
+        if (idx < bcnt) {
+            const int at = (int)(idx >> 4) * OS_STRIDE + (int)(idx & 15);
+            stage[0 * OS_PLANE + at] = P.c[0][g0 + idx];
+            stage[1 * OS_PLANE + at] = P.c[1][g0 + idx];
+            stage[2 * OS_PLANE + at] = P.c[2][g0 + idx];
+            if (W) stage[3 * OS_PLANE + at] = P.w[g0 + idx];
+        }
+    }
+    double m0 = 0, m1 = 0, m2 = 0;
+    if (KIND == KIND_CENTERED) { m0 = stats[seg].mean[0]; m1 = stats[seg].mean[1]; m2 = stats[seg].mean[2]; }
+    // ---- per chain: the grid of the predicted start state -------------------------------------------------
+    const double *pstart = psum + ((size_t)sg.bbase + blk) * C;
+    PbFastGrid grid[C];
+#pragma unroll
+    for (int c = 0; c < C; c++) grid[c] = pb_fast_grid(chain_live<KIND, W>(c) ? pstart[c] : 0.0);
+    __syncwarp();
+    // ---- this lane's 16 consecutive elements: quantised prefix sums and their extremes ---------------------
+    const int mycnt = min(OS_PER, max(0, (int)bcnt - lane * OS_PER));
+    const double *mine = stage + lane * OS_STRIDE;
+    double ps[C], mn[C], mx[C];
+    unsigned tie = 0;
+    bool wneg = false;
+#pragma unroll
+    for (int c = 0; c < C; c++) ps[c] = mn[c] = mx[c] = 0.0;
+#pragma unroll 2
+    for (int k = 0; k < mycnt; k++) {
+        const double w = W ? mine[3 * OS_PLANE + k] : 1.0;
+        double t[C];
+        terms_all<KIND, W>(w, mine[k], mine[OS_PLANE + k], mine[2 * OS_PLANE + k], m0, m1, m2, t);
+        if (W) wneg |= w < 0.0;
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+            if (!chain_live<KIND, W>(c)) continue;
+            bool tie_c;
+            ps[c] += pb_fast_quant(grid[c], t[c], &tie_c); // exact while below 2^53 u (checked at the end)
+            if (tie_c) tie |= 1u << c;
+            if (!chain_monotone<KIND>(c)) {
+                mn[c] = ps[c] < mn[c] ? ps[c] : mn[c];
+                mx[c] = ps[c] > mx[c] ? ps[c] : mx[c];
+            }
+        }
+    }
+    tie = __reduce_or_sync(FULL, tie);
+    const bool any_wneg = W && __any_sync(FULL, wneg);
+    // ---- compose the lanes in element order; lane c finishes chain c ----------------------------------------
+    double r_sum = 0.0, r_mn = 0.0, r_mx = 0.0; // of chain `lane`
+    PbFastGrid r_grid = grid[0];
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+        if (!chain_live<KIND, W>(c)) continue;
+        double tot, lo_ext, hi_ext;
+        if (chain_monotone<KIND>(c)) { // terms >= 0 (negative weights are checked): extremes are 0 and the total
+            tot = ps[c];
+#pragma unroll
+            for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(FULL, tot, o);
+            lo_ext = 0.0;
+            hi_ext = tot;
+        } else {
+            double incl = ps[c];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double v = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const double excl = incl - ps[c];
+            lo_ext = excl + mn[c];
+            hi_ext = excl + mx[c];
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                const double a = __shfl_xor_sync(FULL, lo_ext, o), b = __shfl_xor_sync(FULL, hi_ext, o);
+                lo_ext = a < lo_ext ? a : lo_ext;
+                hi_ext = b > hi_ext ? b : hi_ext;
+            }
+            tot = __shfl_sync(FULL, incl, 31);
+        }
+        if (lane == c) { r_sum = tot; r_mn = lo_ext; r_mx = hi_ext; r_grid = grid[c]; }
+    }
+    // ---- the record (lane c: chain c) -----------------------------------------------------------------------
+    bool general = false;
+    if (lane < C && chain_live<KIND, W>(lane) && (!MASKED || (cmask >> lane & 1u))) {
+        PbSpan sp;
+        const bool accept = !any_wneg && pb_fast_finish(r_grid, pstart[lane], r_sum, r_mn, r_mx, (tie >> lane & 1u) != 0, OF_MARGIN, sp);
+        if (accept) {
+            OrdRec o;
+            o.sum = sp.sum; o.lo = sp.lo; o.hi = sp.hi; o.eref = r_grid.e; o.flag = F_OK;
+            rec0[rec_row(sg, C, lane, nblk, blk)] = o;
+        }
+        general = !accept;
+    }
+    const unsigned gm = __ballot_sync(FULL, general);
+    if (gm) { // one work item per (block, chain) for the general two-parity pass: block index < 2^28
+        unsigned int at = 0;
+        if (lane == 0) at = atomicAdd(list_count, (unsigned)__popc(gm));
+        at = __shfl_sync(FULL, at, 0);
+        if (general) list[at + __popc(gm & ((1u << lane) - 1u))] = make_uint2((unsigned)seg, blk | ((unsigned)lane << 28));
+    }
+    if (lane == 0) {
+        int live = 0;
+#pragma unroll
+        for (int c = 0; c < C; c++) live += (chain_live<KIND, W>(c) && (!MASKED || (cmask >> c & 1u))) ? 1 : 0;
+        atomicAdd(&g_ord_counts[13], (unsigned long long)(live - __popc(gm)));
+        atomicAdd(&g_ord_counts[14], (unsigned long long)__popc(gm));
+    }
+}
+
 // ---- S3b: (block, chain) pairs with a parity-dependent step: both start parities ---------------------
 template <int KIND, bool W>
 __global__ void __launch_bounds__(OS_THREADS) k_ord_summary2(PbPlanes b0, PbPlanes b1, const PbSeg *__restrict__ segs,
@@ -882,6 +1041,7 @@ struct Scratch {
 };
 size_t group_rows(size_t total_blocks) { return total_blocks * 7 / 32 + 4096; } // + nseg * (C + 1), nseg <= 2 * 64
 long long g_dump_cap_override = -1; // debug/test knob (patolette_b200_set_option "dump_cap")
+bool g_fast_summary = true;         // "fast_summary": block-uniform summaries (k_ord_fast) + general work list; 0 = per-element summaries for every block
 size_t dump_slots(size_t total_blocks) { return total_blocks / 4 + 1024; }
 unsigned int dump_cap(size_t total_blocks) {
     const size_t n = dump_slots(total_blocks);
@@ -932,6 +1092,14 @@ void launch_pass(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t
         { PbProfScope p("k_ord_prefix", st, false);
           k_ord_prefix<C><<<dim3(chain_live<KIND, W>(0) ? C : C - 1, nseg), 32, 0, st>>>(d_segs, sc.psum, chain_live<KIND, W>(0) ? 0 : 1, cmask); }
         PB_CUDA_OK(cudaMemsetAsync(sc.list_count, 0, 2 * sizeof(unsigned int), st));
+        if (g_fast_summary) {
+            dim3 fgrid((blk_cap + OF_WARPS - 1) / OF_WARPS, nseg);
+            PbProfScope p(KIND == KIND_MEAN ? "k_ord_fast_mean" : "k_ord_fast_centered", st);
+            if (cmask == ~0u)
+                k_ord_fast<KIND, W, false><<<fgrid, OF_THREADS, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, sc.psum, sc.rec0, sc.list_count, sc.list, cmask);
+            else
+                k_ord_fast<KIND, W, true><<<fgrid, OF_THREADS, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, sc.psum, sc.rec0, sc.list_count, sc.list, cmask);
+        } else
         { PbProfScope p(KIND == KIND_MEAN ? "k_ord_summary_mean" : "k_ord_summary_centered", st);
           if (cmask == ~0u) // every chain: the single-GPU instantiation, chain liveness known at compile time
               k_ord_summary<KIND, W, false><<<sgrid, OS_THREADS, summary_pad_smem(KIND), st>>>(bufs[0], bufs[1], d_segs, d_stats, sc.psum, sc.rec0, sc.list_count, sc.list, sc.dump, cmask);
@@ -966,6 +1134,7 @@ void pb_ordered_chain_debug(unsigned long long out[35], bool reset) {
 }
 
 void pb_ordered_set_dump_cap(long long slots) { g_dump_cap_override = slots; }
+void pb_ordered_set_fast(bool on) { g_fast_summary = on; }
 
 uint32_t pb_ordered_blocks(uint32_t n) { return (n + OB - 1) / OB; }
 

@@ -493,7 +493,7 @@ void pb_launch_class_rank(int cls_mode, int nclass, const PbSeg *d_segs, int nse
     const int warps = scatter_warps(nclass);
     ClsCtx cc{cls_mode, d_bucket, d_split, d_lut};
     dim3 g1((tiles_cap + warps - 1) / warps, nseg);
-    if ((size_t)warps * nclass * 4 > 48 * 1024)
+    if ((size_t)warps * nclass * 4 > 32 * 1024)
         PB_CUDA_OK(cudaFuncSetAttribute(k_tile_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, warps * nclass * 4));
     { PbProfScope _prof("k_tile_hist", st, false);
     k_tile_hist<<<g1, warps * 32, (size_t)warps * nclass * 4, st>>>(cc, nclass, d_segs, tiles_cap, d_tile_hist);
@@ -526,7 +526,7 @@ void pb_launch_scatter_ord(int cls_mode, int nclass, const PbSeg *d_segs, int ns
     ClsCtx cc{cls_mode, d_bucket, d_split, d_lut};
     dim3 g((tiles_cap + warps - 1) / warps, nseg);
     PbPlanes none{};
-    if ((size_t)warps * (nclass + 1) * 4 > 48 * 1024)
+    if ((size_t)warps * (nclass + 1) * 4 > 32 * 1024)
         PB_CUDA_OK(cudaFuncSetAttribute(k_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         warps * (nclass + 1) * 4));
     { PbProfScope _prof("k_scatter", st);
@@ -575,7 +575,7 @@ void pb_launch_nearest(const double *const planes[3], size_t n, const double *d_
     const int grid = (int)(want < cap ? want : cap);
     const size_t smem = (size_t)K * 3 * sizeof(double);
     const bool in_smem = smem <= PB_SMEM_PALETTE_LIMIT;
-    if (in_smem && smem > 48 * 1024)
+    if (in_smem && smem > 32 * 1024)
         PB_CUDA_OK(cudaFuncSetAttribute(k_nearest<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     { PbProfScope _prof("k_nearest", st);
     if (in_smem) k_nearest<true><<<grid, 256, smem, st>>>(planes[0], planes[1], planes[2], n, d_palette_rm, K, d_map);

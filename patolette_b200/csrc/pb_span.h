@@ -264,6 +264,57 @@ PB_HD PbSpan2 pb_run_span(const PbRun &r) {
     return s;
 }
 
+// ---- block-uniform fast path (k_ord_fast in pb_ordered.cu) -------------------------------------------------
+// If every partial sum of a block lies in the binade e of the block's predicted start state, every step is a
+// translation on the ONE grid u = 2^(e-52), and the FPU quantises for us: RN_u(a) = (a + M) - M with
+// M = 1.5 * 2^e (valid while |a| < 2^(e-1); ulp(M) = u, M / u even).  The quantised terms are multiples of u,
+// so their sums are exact in floating point below 2^53 u.  A tie - |a - RN_u(a)| = u/2, its winner depends on
+// the parity of the state - and anything else that is not this case leaves the pair to the general path.  As
+// above the claim is an interval for the exact start state: S_start + (every in-order prefix) strictly inside
+// the binade.  This is pb_run_uniform with k = 0 stretched over a whole block.
+struct PbFastGrid {
+    double M, half; // 1.5 * 2^e, u / 2
+    int e, ok;
+};
+PB_HD PbFastGrid pb_fast_grid(double pstart) {
+    PbFastGrid g;
+    g.e = pb_exponent_of(pstart);
+    g.ok = pb_eref_ok(g.e) ? 1 : 0;
+    const int ee = g.ok ? g.e : 0;
+    g.M = 1.5 * pb_pow2(ee);
+    g.half = pb_pow2(ee - 53);
+    return g;
+}
+// one element: returns RN_u(t); sets *tie when t sits exactly halfway between two grid points
+PB_HD double pb_fast_quant(const PbFastGrid &g, double t, bool *tie) {
+    const double d = (t + g.M) - g.M; // a multiple of u
+    const double rem = t - d;         // exact
+    const double ar = rem < 0 ? -rem : rem;
+    *tie = ar == g.half;
+    return d;
+}
+#define PB_FAST_LIMIT 1125899906842624.0 /* 2^50 units */
+// sum / lo_ext / hi_ext: total and extremes (<= 0 <= ) of the in-order prefix sums of the quantised terms, in
+// the input's scale.  margin: distance (units) the PREDICTED start state must keep from the interval's ends -
+// a performance heuristic only (a record that will not apply costs a replay); soundness is the interval.
+PB_HD bool pb_fast_finish(const PbFastGrid &g, double pstart, double sum, double lo_ext, double hi_ext, bool tie,
+                          long long margin, PbSpan &out) {
+    if (!g.ok || tie) return false;
+    const double scale = pb_pow2(52 - g.e);
+    const double su = sum * scale, lu = lo_ext * scale, hu = hi_ext * scale; // exact power-of-two scalings
+    const double asu = su < 0 ? -su : su;
+    // below the limit every partial sum was exact and every |a_i| < 2^(e-1) (a larger term moves a prefix by
+    // at least 2^51 - 2 units); NaN fails every comparison
+    if (!(asu < PB_FAST_LIMIT) || !((hu - lu) < PB_FAST_LIMIT) || !(lu <= 0.0) || !(hu >= 0.0)) return false;
+    const long long A0 = 1LL << 52, B = 1LL << 53;
+    const bool neg = pstart < 0.0;
+    out.sum = (long long)su;
+    out.lo = (neg ? -B : A0) + 1 - (long long)lu;
+    out.hi = (neg ? -A0 : B) - 1 - (long long)hu;
+    const long long S0 = (long long)(pstart * scale); // an integer with |S0| in [2^52, 2^53)
+    return out.lo + margin <= S0 && S0 <= out.hi - margin;
+}
+
 // exact state <-> integer in units of 2^(eref-52)
 PB_HD bool pb_state_to_units(double s, int eref, long long &S) {
     const long long bits = pb_double_bits(s);

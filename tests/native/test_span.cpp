@@ -247,6 +247,66 @@ static void run_chain_with_run_records(const std::vector<double> &a, RunStats &r
     }
 }
 
+// k_ord_fast (pb_ordered.cu) emulated lane by lane: block-uniform quantisation on the grid of the predicted
+// start state, in-order prefixes inside a lane, span-style composition across lanes, pb_fast_finish.  Whatever
+// it accepts AND the exact state satisfies must be the sequential loop's result.
+struct FastStats { long blocks = 0, offered = 0, applied = 0, refused_by_state = 0, wrong = 0, mono_blocks = 0; };
+static void run_chain_fast(const std::vector<double> &a, FastStats &fs) {
+    const size_t n = a.size(), nblk = (n + OB - 1) / OB;
+    bool all_nonneg = true;
+    for (double v : a) all_nonneg &= v >= 0;
+    double run = 0, s = 0;
+    for (size_t b = 0; b < nblk; b++) {
+        const int cnt = (int)std::min<size_t>(OB, n - b * OB);
+        const double pstart = run;
+        run += tree_sum(&a[b * OB], cnt);
+        double truth = s;
+        for (int i = 0; i < cnt; i++) truth = truth + a[b * OB + i];
+        fs.blocks++;
+        const PbFastGrid g = pb_fast_grid(pstart);
+        double ps[THREADS], mn[THREADS], mx[THREADS];
+        bool tie = false;
+        for (int t = 0; t < THREADS; t++) {
+            ps[t] = mn[t] = mx[t] = 0.0;
+            for (int k = 0; k < PER; k++)
+                if (t * PER + k < cnt) {
+                    bool tc;
+                    ps[t] += pb_fast_quant(g, a[b * OB + t * PER + k], &tc);
+                    tie |= tc;
+                    mn[t] = ps[t] < mn[t] ? ps[t] : mn[t];
+                    mx[t] = ps[t] > mx[t] ? ps[t] : mx[t];
+                }
+        }
+        double tot = 0, lo = 0, hi = 0;
+        if (all_nonneg && (b & 1)) { // the kernel's shortcut for chains whose terms are never negative
+            for (int t = 0; t < THREADS; t++) tot += ps[t];
+            lo = 0; hi = tot;
+            fs.mono_blocks++;
+        } else {
+            double excl = 0;
+            for (int t = 0; t < THREADS; t++) {
+                lo = excl + mn[t] < lo ? excl + mn[t] : lo;
+                hi = excl + mx[t] > hi ? excl + mx[t] : hi;
+                excl += ps[t];
+            }
+            tot = excl;
+        }
+        PbSpan sp;
+        if (pb_fast_finish(g, pstart, tot, lo, hi, tie, 1LL << 20, sp)) {
+            fs.offered++;
+            PbState st = pb_state_from_double(s);
+            if (pb_state_apply(st, sp, sp, g.e)) {
+                fs.applied++;
+                if (pb_double_bits(pb_state_to_double(st)) != pb_double_bits(truth)) {
+                    fs.wrong++;
+                    if (fs.wrong < 5) fprintf(stderr, "  FAST MISMATCH block %zu: start %a truth %a got %a\n", b, s, truth, pb_state_to_double(st));
+                }
+            } else fs.refused_by_state++;
+        }
+        s = truth;
+    }
+}
+
 // pb_state_rebase (integer shifts) must agree with the formulation through the double for every valid
 // state (at most 53 significant bits, any trailing-zero count up to the level range) and every unit.
 static long check_rebase(std::mt19937_64 &rng) {
@@ -288,8 +348,10 @@ int main(int argc, char **argv) {
     };
     long total_wrong = 0, total_assoc = 0;
     RunStats rr;
+    long fast_wrong = 0;
     for (const Family &f : fams) {
         Stats st;
+        FastStats fs;
         for (int rep = 0; rep < reps; rep++) {
             const size_t n = (size_t)(1000 + (rng() % 400000));
             std::vector<double> a(n);
@@ -327,7 +389,16 @@ int main(int argc, char **argv) {
             if (f.kind == 12) a[0] = 1.0; // start right at a power of two and wobble around it
             run_chain(a, st);
             run_chain_with_run_records(a, rr);
+            run_chain_fast(a, fs);
+            if (rep == 0) { // the same data far along a chain (start state 2^20 times the terms) and behind a negative state
+                std::vector<double> b2(a);
+                b2.insert(b2.begin(), (f.kind % 2 ? -1.0 : 1.0) * 1048576.0 * (1.0 + U(rng)));
+                run_chain_fast(b2, fs);
+            }
         }
+        printf("    fast path: offered %6.2f%% of blocks, applied %6.2f%%, refused by the exact state %ld, wrong %ld\n",
+               100.0 * fs.offered / fs.blocks, 100.0 * fs.applied / fs.blocks, fs.refused_by_state, fs.wrong);
+        fast_wrong += fs.wrong;
         printf("%-40s blocks %7ld accepted %6.2f%% sensitive %5.2f%% unusable %5.2f%% fast-threads %5.1f%% wrong %ld assoc %ld fastmis %ld\n",
                f.name.c_str(), st.blocks, 100.0 * st.accepted / st.blocks, 100.0 * st.sensitive / st.blocks,
                100.0 * st.bad / st.blocks, 100.0 * st.fast / (st.blocks * (double)THREADS), st.wrong, st.assoc_fail, st.fast_mismatch);
@@ -336,7 +407,7 @@ int main(int argc, char **argv) {
     }
     printf("run records: %ld runs crossing %ld blocks, %ld single records, %ld replays, wrong %ld\n", rr.runs, rr.run_blocks,
            rr.singles, rr.replays, rr.wrong);
-    total_wrong += rr.wrong;
+    total_wrong += rr.wrong + fast_wrong;
     if (total_wrong || total_assoc) { printf("FAIL\n"); return 1; }
     printf("OK\n");
     return 0;
