@@ -249,13 +249,168 @@ __global__ void __launch_bounds__(DT_WARPS * 32) k_riemersma_spec(const double *
     });
 }
 
+// ---- sub-warp speculation: 4 lanes per chain, 8 chains per warp --------------------------------------------
+// In k_riemersma_spec a whole warp executes every instruction of ONE chain although only three lanes own an
+// error queue and a candidate list has ~15 entries: ~180 warp instructions per pixel, and the kernel is bound
+// by instruction issue, not by FP64 or memory.  Here a GROUP of four lanes runs a chain - lanes 0..2 own the
+// R/G/B queues (the 16-tap sum is the same dependent chain of separately rounded products, riemersma.c:292-297),
+// all four split the candidates of the exact search and reduce the argmin by two shuffles - so one warp
+// instruction advances eight chains.  The queue lives in registers and is never shifted: the walk is unrolled
+// sixteen pixels at a time and pixel k overwrites slot k (the oldest).  Pixels are staged through shared memory
+// in batches of 16 (each lane fetches 4 consecutive pixels of every channel: 128-byte coalesced per group) with
+// the next batch in registers; choices leave as one 64-byte store per group and batch.
+constexpr int DS_GROUP = 4;
+constexpr int DS_CHAINS = 32 / DS_GROUP;
+constexpr int DS_WARPS = 4;
+__constant__ double c_qw[16]; // queue weights (riemersma.c:360-373), oldest first
+
+__device__ __forceinline__ int dither_nn4(double x, double y, double z, const double *__restrict__ s_palw, int K, int gl,
+                                          const DitherGrid &G) {
+    double bd = 0.0;
+    int best = 0x7fffffff;
+    const int cell = G.cnt ? pb_grid_cell(true, G.geom, G.geom + 3, x, y, z) : -1; // uniform within the group
+    if (cell >= 0) {
+        const unsigned short *Lst = G.list + (size_t)cell * K;
+        const int m = G.cnt[cell];
+        for (int t = gl; t < m; t += DS_GROUP) {
+            const int j = Lst[t];
+            const double dx = __dsub_rn(x, s_palw[3 * j]), dy = __dsub_rn(y, s_palw[3 * j + 1]),
+                         dz = __dsub_rn(z, s_palw[3 * j + 2]);
+            const double dd = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+            if (best == 0x7fffffff || dd < bd) { bd = dd; best = j; }
+        }
+    } else {
+        for (int j = gl; j < K; j += DS_GROUP) {
+            const double dx = __dsub_rn(x, s_palw[3 * j]), dy = __dsub_rn(y, s_palw[3 * j + 1]),
+                         dz = __dsub_rn(z, s_palw[3 * j + 2]);
+            const double dd = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+            if (best == 0x7fffffff || dd < bd) { bd = dd; best = j; }
+        }
+    }
+    // exact argmin over the group, lowest index on ties: squared distances are non-negative doubles, whose bit
+    // patterns order like unsigned integers
+    unsigned long long key = best == 0x7fffffff ? ~0ULL : (unsigned long long)__double_as_longlong(bd);
+#pragma unroll
+    for (int o = 1; o < DS_GROUP; o <<= 1) {
+        const unsigned long long ok = __shfl_xor_sync(0xffffffffu, key, o);
+        const int oj = __shfl_xor_sync(0xffffffffu, best, o);
+        if (ok < key || (ok == key && oj < best)) { key = ok; best = oj; }
+    }
+    return best;
+}
+
+__global__ void __launch_bounds__(DS_WARPS * 32) k_riemersma_spec4(const double *__restrict__ h0, const double *__restrict__ h1,
+                                                                  const double *__restrict__ h2, size_t n, size_t seg,
+                                                                  size_t warm, const double *__restrict__ pal,
+                                                                  const double *__restrict__ palw, int K,
+                                                                  uint32_t *__restrict__ hidx, uint32_t *__restrict__ overlap,
+                                                                  const void *__restrict__ nngrid, bool pal_in_smem) {
+    extern __shared__ double s_mem[];
+    const double *s_pal = pal_in_smem ? s_mem : pal, *s_palw = pal_in_smem ? s_mem + (size_t)K * 3 : palw;
+    __shared__ double s_geom[6];
+    __shared__ int s_grid_ok;
+    __shared__ double s_px[DS_WARPS][DS_CHAINS][3][16];
+    __shared__ int s_choice[DS_WARPS][DS_CHAINS][16];
+    if (pal_in_smem)
+        for (int i = threadIdx.x; i < K * 3; i += blockDim.x) { s_mem[i] = pal[i]; s_mem[(size_t)K * 3 + i] = palw[i]; }
+    if (threadIdx.x == 0) {
+        s_grid_ok = 0;
+        if (nngrid) {
+            const PbGridGeom g = pb_grid_geom((const PbGridHdr *)nngrid);
+            for (int d = 0; d < 3; d++) { s_geom[d] = g.lo[d]; s_geom[3 + d] = g.inv[d]; }
+            s_grid_ok = g.ok;
+        }
+    }
+    __syncthreads();
+    DitherGrid G{s_geom, nullptr, nullptr};
+    if (s_grid_ok) {
+        G.cnt = (const unsigned short *)((const char *)nngrid + 256);
+        G.list = G.cnt + PB_NCELL;
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gl = lane & (DS_GROUP - 1), grp = lane / DS_GROUP;
+    const int ch = gl < 3 ? gl : 0;
+    const double cw = ch == 0 ? 0.51254268114958 : (ch == 1 ? 0.8234075540095561 : 0.2435159132377184);
+    const size_t g = ((size_t)blockIdx.x * DS_WARPS + warp) * DS_CHAINS + grp;
+    const size_t a = g * seg;                       // first pixel this chain owns
+    const bool live = a < n;
+    const size_t end = live ? min(n, a + seg) : 0;
+    size_t pos = live ? (a > warm ? a - warm : 0) : 0; // a - pos is a multiple of 16 (seg and warm are multiples of 128)
+    double(*px)[16] = s_px[warp][grp];
+    int *choice = s_choice[warp][grp];
+    uint32_t *ov = overlap + g * 16;
+    double q[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) q[i] = 0.0;
+    double nx[3][4]; // the next batch: pixels pos + 4 * gl + {0..3} of every channel
+    auto prefetch = [&](size_t at) {
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const size_t i = at + 4 * gl + e;
+            const bool in = i < end;
+            nx[0][e] = in ? h0[i] : 0.0;
+            nx[1][e] = in ? h1[i] : 0.0;
+            nx[2][e] = in ? h2[i] : 0.0;
+        }
+    };
+    prefetch(pos);
+    while (__any_sync(0xffffffffu, pos < end)) { // warp-uniform: finished groups idle through the rest
+        __syncwarp();
+#pragma unroll
+        for (int e = 0; e < 4; e++) { px[0][4 * gl + e] = nx[0][e]; px[1][4 * gl + e] = nx[1][e]; px[2][4 * gl + e] = nx[2][e]; }
+        __syncwarp();
+        prefetch(pos + 16);
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const double P = px[ch][k];
+            // riemersma.c:292-297: error = sum_i queue[i] * weight[i], oldest first; slot k holds the oldest entry
+            double err = 0.0;
+#pragma unroll
+            for (int t = 0; t < 16; t++) err = __dadd_rn(err, __dmul_rn(q[(k + t) & 15], c_qw[t]));
+            const double Cw = __dmul_rn(cw, __dadd_rn(P, err)); // :310-317, no clamping
+            const double x = __shfl_sync(0xffffffffu, Cw, 0, DS_GROUP), y = __shfl_sync(0xffffffffu, Cw, 1, DS_GROUP),
+                         z = __shfl_sync(0xffffffffu, Cw, 2, DS_GROUP);
+            const int best = dither_nn4(x, y, z, s_palw, K, gl, G);
+            q[k] = __dsub_rn(P, s_pal[3 * best + ch]); // :334-340: the newest entry takes the oldest one's slot
+            if (gl == 0) choice[k] = best;
+        }
+        __syncwarp();
+        if (pos < end) { // this lane's four choices of the batch
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const size_t i = pos + 4 * gl + e;
+                if (i < end) {
+                    if (i >= a) hidx[i] = (uint32_t)choice[4 * gl + e];
+                    else if (i + 16 >= a) ov[i + 16 - a] = (uint32_t)choice[4 * gl + e];
+                }
+            }
+        }
+        pos += 16;
+    }
+}
+
+// boundary g needs the sequential repair iff the 16 choices chain g made just before its segment differ from
+// what chain g - 1 produced there
+__global__ void k_riemersma_check(const uint32_t *__restrict__ hidx, const uint32_t *__restrict__ overlap, size_t nseg, size_t seg,
+                                  unsigned char *__restrict__ flags) {
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= nseg) return;
+    bool differ = false;
+    if (g >= 1) {
+        const size_t a = g * seg;
+#pragma unroll
+        for (int i = 0; i < 16; i++) differ |= overlap[g * 16 + i] != hidx[a - 16 + i];
+    }
+    flags[g] = differ ? 1 : 0;
+}
+
 __global__ void __launch_bounds__(32) k_riemersma_repair(const double *__restrict__ h0, const double *__restrict__ h1,
                                                          const double *__restrict__ h2, size_t n, size_t seg,
                                                          const double *__restrict__ pal, const double *__restrict__ palw,
                                                          int K, const double *__restrict__ qweights,
                                                          uint32_t *__restrict__ hidx, const uint32_t *__restrict__ overlap,
                                                          unsigned long long *__restrict__ stats,
-                                                         const void *__restrict__ nngrid, bool pal_in_smem) {
+                                                         const void *__restrict__ nngrid, bool pal_in_smem,
+                                                         const unsigned char *__restrict__ flags) {
     extern __shared__ double s_mem[];
     const double *s_pal = pal_in_smem ? s_mem : pal, *s_palw = pal_in_smem ? s_mem + (size_t)K * 3 : palw;
     __shared__ double s_geom[6];
@@ -284,6 +439,14 @@ __global__ void __launch_bounds__(32) k_riemersma_repair(const double *__restric
     unsigned long long repaired_segments = 0, repaired_pixels = 0;
     size_t g = 1;
     while (g < nseg) {
+        if (flags) {
+            // k_riemersma_check compared every boundary in parallel against the speculative choices.  A boundary it
+            // passed stays passed: its 16-pixel window only changes if an earlier repair runs across it, and then
+            // the walk below jumps past it anyway.  32 flags per step.
+            const unsigned m = __ballot_sync(0xffffffffu, g + lane < nseg && flags[g + lane]);
+            if (!m) { g += 32; continue; }
+            g += __ffs(m) - 1;
+        }
         const size_t a = g * seg;
         const bool differ = lane < 16 && overlap[g * 16 + lane] != hidx[a - 16 + lane];
         if (!__any_sync(0xffffffffu, differ)) { g++; continue; }
@@ -316,6 +479,8 @@ __global__ void __launch_bounds__(32) k_riemersma_repair(const double *__restric
 
 static bool g_dither_grid = true; // patolette_b200_set_option "dither_grid"
 void pb_dither_set_grid(bool on) { g_dither_grid = on; }
+static bool g_dither_subwarp = true; // "dither_subwarp": 4 lanes per chain (k_riemersma_spec4) or a warp per chain
+void pb_dither_set_subwarp(bool on) { g_dither_subwarp = on; }
 
 void pb_dither_riemersma(const double *const planes[3], size_t width, size_t height,
                          const std::vector<double> &pal_rm, unsigned long long *d_map, int sm_count,
@@ -347,7 +512,9 @@ void pb_dither_riemersma(const double *const planes[3], size_t width, size_t hei
     void *d_grid = nullptr;
     uint32_t *d_rank = nullptr, *d_hidx = nullptr, *d_overlap = nullptr;
     unsigned long long *d_stats = nullptr;
+    unsigned char *d_flags = nullptr;
     auto cleanup = [&]() {
+        pb_pool_free(d_flags);
         for (int j = 0; j < 3; j++) pb_pool_free(d_h[j]);
         pb_pool_free(d_pal); pb_pool_free(d_palw); pb_pool_free(d_qw); pb_pool_free(d_rank); pb_pool_free(d_hidx); pb_pool_free(d_overlap); pb_pool_free(d_stats); pb_pool_free(d_grid);
     };
@@ -396,13 +563,26 @@ void pb_dither_riemersma(const double *const planes[3], size_t width, size_t hei
             pb_launch_nngrid_build(hp, n, d_palw, K, d_grid, sm_count, st, cw, 0.25);
         }
         pb_prof_next_bytes(28.0 * (double)n); // 24 B of colours read + 4 B index written per pixel of the walk
+        if (g_dither_subwarp) {
+            PB_CUDA_OK(cudaMemcpyToSymbolAsync(c_qw, qw, sizeof qw, 0, cudaMemcpyHostToDevice, st)); // (per device; 128 B)
+            if (smem > 32 * 1024)
+                PB_CUDA_OK(cudaFuncSetAttribute(k_riemersma_spec4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const size_t per_cta = (size_t)DS_WARPS * DS_CHAINS;
+            PbProfScope _prof("k_riemersma_spec", st);
+            k_riemersma_spec4<<<(unsigned)((nseg + per_cta - 1) / per_cta), DS_WARPS * 32, smem, st>>>(
+                d_h[0], d_h[1], d_h[2], n, seg, warm, d_pal, d_palw, K, d_hidx, d_overlap, d_grid, pal_in_smem);
+        } else
         { PbProfScope _prof("k_riemersma_spec", st);
         k_riemersma_spec<<<(unsigned)((nseg + DT_WARPS - 1) / DT_WARPS), DT_WARPS * 32, smem, st>>>(
             d_h[0], d_h[1], d_h[2], n, seg, warm, d_pal, d_palw, K, d_qw, d_hidx, d_overlap, d_grid, pal_in_smem);
         }
+        d_flags = (unsigned char *)pb_pool_alloc(nseg + 64);
+        { PbProfScope _prof("k_riemersma_check", st, false);
+        k_riemersma_check<<<(unsigned)((nseg + 255) / 256), 256, 0, st>>>(d_hidx, d_overlap, nseg, seg, d_flags);
+        }
         { PbProfScope _prof("k_riemersma_repair", st);
         k_riemersma_repair<<<1, 32, smem, st>>>(d_h[0], d_h[1], d_h[2], n, seg, d_pal, d_palw, K, d_qw, d_hidx,
-                                                d_overlap, d_stats, d_grid, pal_in_smem);
+                                                d_overlap, d_stats, d_grid, pal_in_smem, d_flags);
         }
         pb_prof_next_bytes(16.0 * (double)n);
         { PbProfScope _prof("k_unpermute", st);

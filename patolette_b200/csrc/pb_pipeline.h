@@ -18,6 +18,8 @@ void pb_dither_riemersma(const double *const planes[3], size_t width, size_t hei
                          cudaStream_t st, long *launches);
 // test knob: candidate-list nearest-neighbour search inside the dither (default on)
 void pb_dither_set_grid(bool on);
+// test knob: 4 lanes per speculative chain (default) or one warp per chain
+void pb_dither_set_subwarp(bool on);
 
 // Largest palette the f32 KMeans slice supports (16-bit assignments; per-warp class counters of the stable
 // sort in shared memory, 4 B x K for one warp).  Above it patolette() returns exit code -6 when

@@ -206,7 +206,8 @@ def test_kmeans_matches_oracle(cuda_lib, oracle, n, K, weighted, mppc):
     assert np.array_equal(ca.view(np.uint32), cb.view(np.uint32)), f"max diff {np.abs(ca - cb).max()}"
 
 
-@pytest.mark.parametrize("W,H,K", [(64, 64, 16), (100, 37, 40), (1, 7, 4), (130, 257, 256), (1, 1, 3), (700, 500, 8), (512, 384, 2)])
+@pytest.mark.parametrize("W,H,K", [(64, 64, 16), (100, 37, 40), (1, 7, 4), (130, 257, 256), (1, 1, 3), (700, 500, 8), (512, 384, 2),
+                                   (1500, 1100, 64), (2048, 2048, 300)])
 def test_dither_matches_oracle(cuda_lib, oracle, W, H, K):
     n = W * H
     rng = np.random.default_rng(W * 1000 + H)
@@ -246,6 +247,14 @@ def test_dither_candidate_lists_equal_brute_force(cuda_lib, oracle, kind):
                                     C.c_size_t(K), want.ctypes.data_as(C.c_void_p))
     assert np.array_equal(got, brute), f"{int((got != brute).sum())} indices differ from the brute-force search"
     assert np.array_equal(got, want), f"{int((got != want).sum())} indices differ from the oracle"
+    # the other speculation kernel (one warp per chain instead of four lanes per chain): same map
+    warp = np.full(n, 7, dtype=np.uintp)
+    try:
+        assert cuda_lib.patolette_b200_set_option(b"dither_subwarp", 0) == 0
+        assert cuda_lib.patolette_b200_dither(planar.ctypes.data, W, H, pal.ctypes.data, K, warp.ctypes.data) == 0
+    finally:
+        cuda_lib.patolette_b200_set_option(b"dither_subwarp", 1)
+    assert np.array_equal(warp, want), f"{int((warp != want).sum())} indices of the warp-per-chain kernel differ from the oracle"
 
 
 # ---------------------------------------------------------------------------------- end to end
