@@ -477,6 +477,20 @@ __global__ void __launch_bounds__(32) k_riemersma_repair(const double *__restric
 
 } // namespace
 
+// The position of every pixel in the walk depends on (width, height) only: the table of the last image size is
+// kept between calls (4 B per pixel; patolette_b200_release_cache() drops it).
+namespace {
+struct RankCache {
+    int device = -1;
+    size_t width = 0, height = 0;
+    uint32_t *rank = nullptr;
+} g_rank_cache;
+} // namespace
+void pb_dither_release_cache() {
+    if (g_rank_cache.rank) pb_pool_free(g_rank_cache.rank);
+    g_rank_cache = RankCache{};
+}
+
 static bool g_dither_grid = true; // patolette_b200_set_option "dither_grid"
 void pb_dither_set_grid(bool on) { g_dither_grid = on; }
 static bool g_dither_subwarp = true; // "dither_subwarp": 4 lanes per chain (k_riemersma_spec4) or a warp per chain
@@ -516,14 +530,22 @@ void pb_dither_riemersma(const double *const planes[3], size_t width, size_t hei
     auto cleanup = [&]() {
         pb_pool_free(d_flags);
         for (int j = 0; j < 3; j++) pb_pool_free(d_h[j]);
-        pb_pool_free(d_pal); pb_pool_free(d_palw); pb_pool_free(d_qw); pb_pool_free(d_rank); pb_pool_free(d_hidx); pb_pool_free(d_overlap); pb_pool_free(d_stats); pb_pool_free(d_grid);
+        pb_pool_free(d_pal); pb_pool_free(d_palw); pb_pool_free(d_qw); pb_pool_free(d_hidx); pb_pool_free(d_overlap); pb_pool_free(d_stats); pb_pool_free(d_grid);
     };
     try {
         for (int j = 0; j < 3; j++) d_h[j] = (double *)pb_pool_alloc(n * sizeof(double));
         d_pal = (double *)pb_pool_alloc(pal_rm.size() * sizeof(double));
         d_palw = (double *)pb_pool_alloc(pal_rm.size() * sizeof(double));
         d_qw = (double *)pb_pool_alloc(sizeof qw);
-        d_rank = (uint32_t *)pb_pool_alloc(n * sizeof(uint32_t));
+        int dev = 0;
+        PB_CUDA_OK(cudaGetDevice(&dev));
+        const bool rank_cached = g_rank_cache.rank && g_rank_cache.device == dev && g_rank_cache.width == width && g_rank_cache.height == height;
+        if (!rank_cached) {
+            pb_dither_release_cache();
+            g_rank_cache.rank = (uint32_t *)pb_pool_alloc(n * sizeof(uint32_t));
+            g_rank_cache.device = dev; g_rank_cache.width = width; g_rank_cache.height = height;
+        }
+        d_rank = g_rank_cache.rank;
         d_hidx = (uint32_t *)pb_pool_alloc((n + 64) * sizeof(uint32_t));
         PB_CUDA_OK(cudaMemcpyAsync(d_pal, pal_rm.data(), pal_rm.size() * sizeof(double), cudaMemcpyHostToDevice, st));
         PB_CUDA_OK(cudaMemcpyAsync(d_palw, palw.data(), palw.size() * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -531,6 +553,7 @@ void pb_dither_riemersma(const double *const planes[3], size_t width, size_t hei
         size_t want = (n + 255) / 256, cap = (size_t)sm_count * 8;
         const int grid = (int)(want < cap ? want : cap);
         pb_prof_next_bytes(4.0 * (double)n);
+        if (!rank_cached)
         { PbProfScope _prof("k_hilbert_rank", st);
         k_hilbert_rank<<<grid, 256, 0, st>>>((uint32_t)width, (uint32_t)height, level, d_rank);
         }
@@ -592,6 +615,7 @@ void pb_dither_riemersma(const double *const planes[3], size_t width, size_t hei
         PB_CUDA_OK(cudaStreamSynchronize(st));
     } catch (...) {
         cleanup();
+        pb_dither_release_cache(); // the table may not have been filled
         throw;
     }
     cleanup();

@@ -165,23 +165,41 @@ __global__ void __launch_bounds__(OB_THREADS) k_ord_blocksum(PbPlanes b0, PbPlan
 }
 
 // ---- S2: approximate exclusive prefix per chain (in place over the block sums) ------------------
+// One CTA per (chain, segment): every thread sums a contiguous run of block sums (independent loads, several
+// in flight), the CTA scans the partials, the threads write the exclusive prefixes of their run.  (The first
+// version was one warp per chain: a 128 M pixel cluster has 262 144 blocks, i.e. 8192 dependent strided loads
+// per lane and pass - 8 ms of pure latency at 16384^2.)  Any summation order will do: these are predictions.
+constexpr int OP_THREADS = 1024;
 template <int C>
-__global__ void __launch_bounds__(32) k_ord_prefix(const PbSeg *__restrict__ segs, double *__restrict__ psum, int first_chain,
-                                                   unsigned cmask) {
-    const int seg = blockIdx.y, c = blockIdx.x + first_chain, lane = threadIdx.x;
+__global__ void __launch_bounds__(OP_THREADS) k_ord_prefix(const PbSeg *__restrict__ segs, double *__restrict__ psum, int first_chain,
+                                                           unsigned cmask) {
+    __shared__ double s_part[OP_THREADS / 32];
+    const int seg = blockIdx.y, c = blockIdx.x + first_chain, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (!(cmask >> c & 1u)) return;
     const uint32_t nblk = (segs[seg].n + OB - 1) / OB;
     double *io = psum + (size_t)segs[seg].bbase * C + c;
-    const uint32_t per = (nblk + 31) / 32;
-    const uint32_t b0 = min(lane * per, nblk), b1 = min(b0 + per, nblk);
+    const uint32_t per = (nblk + OP_THREADS - 1) / OP_THREADS;
+    const uint32_t b0 = min((uint32_t)tid * per, nblk), b1 = min(b0 + per, nblk);
     double s = 0.0;
+#pragma unroll 8
     for (uint32_t b = b0; b < b1; b++) s += io[(size_t)b * C];
     double incl = s;
     for (int o = 1; o < 32; o <<= 1) {
         const double v = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += v;
     }
-    double run = incl - s;
+    if (lane == 31) s_part[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        double w = s_part[lane];
+        for (int o = 1; o < 32; o <<= 1) {
+            const double v = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += v;
+        }
+        s_part[lane] = w; // inclusive over the warps
+    }
+    __syncthreads();
+    double run = (incl - s) + (warp ? s_part[warp - 1] : 0.0);
     for (uint32_t b = b0; b < b1; b++) {
         const double v = io[(size_t)b * C];
         io[(size_t)b * C] = run;
@@ -1090,7 +1108,7 @@ void launch_pass(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t
         { PbProfScope p(KIND == KIND_MEAN ? "k_ord_blocksum_mean" : "k_ord_blocksum_centered", st, false);
           k_ord_blocksum<KIND, W><<<grid, OB_THREADS, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, sc.psum, cmask); }
         { PbProfScope p("k_ord_prefix", st, false);
-          k_ord_prefix<C><<<dim3(chain_live<KIND, W>(0) ? C : C - 1, nseg), 32, 0, st>>>(d_segs, sc.psum, chain_live<KIND, W>(0) ? 0 : 1, cmask); }
+          k_ord_prefix<C><<<dim3(chain_live<KIND, W>(0) ? C : C - 1, nseg), OP_THREADS, 0, st>>>(d_segs, sc.psum, chain_live<KIND, W>(0) ? 0 : 1, cmask); }
         PB_CUDA_OK(cudaMemsetAsync(sc.list_count, 0, 2 * sizeof(unsigned int), st));
         if (g_fast_summary) {
             dim3 fgrid((blk_cap + OF_WARPS - 1) / OF_WARPS, nseg);

@@ -1098,6 +1098,8 @@ int patolette_b200_ordered_chain_debug(unsigned long long *out35, int reset) {
 }
 
 size_t patolette_b200_release_cache(void) {
+    std::lock_guard<std::mutex> lk(g_call_mu);
+    pb_dither_release_cache();
     const size_t held = pb_pool_cached_bytes();
     pb_pool_release_all();
     return held;

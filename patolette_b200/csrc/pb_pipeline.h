@@ -28,3 +28,5 @@ void pb_dither_set_subwarp(bool on);
 // Dynamic shared memory a kernel may ask for (227 KB opt-in limit minus static shared memory and slack):
 // palettes that do not fit are read from global memory instead (same arithmetic, L1/L2-served broadcasts).
 #define PB_SMEM_PALETTE_LIMIT (200 * 1024)
+// drops the cached walk-position table of the dither (pb_dither.cu)
+void pb_dither_release_cache();
