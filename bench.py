@@ -312,7 +312,13 @@ def measure_ours(args):
     shard = world > 1 and not args.replicas and hasattr(pb, "init_sharding")
     if shard:
         pb.init_sharding(dist)  # NCCL communicator of the library (unique id broadcast through torch.distributed)
-    colors = uniform_colors(w, h, wl["seed"] + (0 if (shard or world == 1) else rank))  # replicas: every rank its own image
+    # a sharded run: rank r brings pixels [first, first + count) of the ONE image (generated without the rest)
+    first, count = (pb.shard_range(n, rank, world) if shard else (0, n))
+    if shard:
+        from synth import uniform_colors_slice
+        colors = uniform_colors_slice(w, h, wl["seed"], first, count)
+    else:
+        colors = uniform_colors(w, h, wl["seed"] + (0 if world == 1 else rank))  # replicas: every rank its own image
     opts = _lib.QuantizationOptions(wl["dither"], False, wl["color_space"], wl["kmeans_niter"], 512 ** 2, False)
     code = C.c_int(0)
     palette = np.zeros((K, 3), order="F")
@@ -322,23 +328,41 @@ def measure_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # host buffers of the end-to-end arm: 3 x N planes (= the reference's column-major N x 3), pinned
-    h_in = torch.empty((3, n), dtype=torch.float64).pin_memory()
+    # host buffers of the end-to-end arm: 3 x count planes (= the reference's column-major layout), pinned
+    h_in = torch.empty((3, count), dtype=torch.float64).pin_memory()
     for j in range(3):
         h_in[j].numpy()[:] = colors[:, j]
-    h_map = torch.empty(n, dtype=torch.int64).pin_memory()
+    h_map = torch.empty(count, dtype=torch.int64).pin_memory()
 
     # ---------------- device-resident arm (value) ----------------
     d_in = h_in.cuda()
-    d_map = torch.empty(n, dtype=torch.int64, device="cuda")
+    d_map = torch.empty(count, dtype=torch.int64, device="cuda")
     stream = torch.cuda.Stream()  # a non-blocking stream: the legacy NULL stream serialises against everything
     torch.cuda.set_stream(stream)
     lib.patolette_b200_set_stream(C.c_void_p(stream.cuda_stream), 1)
 
-    def step_resident():
-        lib.patolette_b200_device(w, h, d_in.data_ptr(), None, K, C.byref(opts), palette.ctypes.data,
-                                  d_map.data_ptr(), C.byref(code))
+    def run_abi(in_ptr, map_ptr, device_io):
+        if shard:
+            lib.patolette_b200_sharded(w, h, in_ptr, None, K, C.byref(opts), palette.ctypes.data, map_ptr, device_io, C.byref(code))
+        elif device_io:
+            lib.patolette_b200_device(w, h, in_ptr, None, K, C.byref(opts), palette.ctypes.data, map_ptr, C.byref(code))
+        else:
+            lib.patolette(w, h, in_ptr, None, K, C.byref(opts), palette.ctypes.data, map_ptr, C.byref(code))
         assert code.value == 0, code.value
+
+    def step_resident():
+        run_abi(d_in.data_ptr(), d_map.data_ptr(), 1)
+
+    def whole_map_sha(t_dev):
+        """sha256 of the whole map on rank 0 (a sharded run gathers the slices over NCCL first)."""
+        if not shard:
+            return sha_map(t_dev.cpu()) if rank == 0 else None
+        S = pb.shard_range(n, 0, world)[1] if world > 1 else n
+        pad = torch.zeros(S, dtype=torch.int64, device="cuda")
+        pad[:count] = t_dev
+        allm = torch.empty(S * world, dtype=torch.int64, device="cuda")
+        dist.all_gather_into_tensor(allm, pad)
+        return sha_map(allm[:n].cpu()) if rank == 0 else None
 
     for _ in range(max(args.warmup, 3)):
         step_resident()
@@ -357,15 +381,13 @@ def measure_ours(args):
     ms_step = reduce_max_ms(ms_total, dist) / args.steps
     stage = pb.last_timings()
     pal_resident = palette.copy()
-    map_sha = sha_map(d_map.cpu()) if rank == 0 else None
+    map_sha = whole_map_sha(d_map)
 
     # ---------------- end-to-end arm: host buffers through the reference ABI ----------------
     lib.patolette_b200_set_stream(None, 0)
 
     def step_e2e():
-        lib.patolette(w, h, h_in.data_ptr(), None, K, C.byref(opts), palette.ctypes.data, h_map.data_ptr(),
-                      C.byref(code))
-        assert code.value == 0
+        run_abi(h_in.data_ptr(), h_map.data_ptr(), 0)
 
     for _ in range(min(max(args.warmup, 1), 2)):
         step_e2e()
@@ -377,8 +399,9 @@ def measure_ours(args):
     e2e_s = (time.perf_counter() - t0) / args.steps
     e2e_s = reduce_max_ms(e2e_s * 1e3, dist) / 1e3
     e2e_stage = pb.last_timings()
+    e2e_sha = whole_map_sha(h_map.cuda()) if shard else (sha_map(h_map) if rank == 0 else None)
     if rank == 0:
-        assert sha_map(h_map) == map_sha, "host and device arms disagree"
+        assert e2e_sha == map_sha, "host and device arms disagree"
         assert np.array_equal(palette.view(np.uint64), pal_resident.view(np.uint64)), "host and device arms disagree (palette)"
     parity = check_golden(wl, side, pal_resident, map_sha) if rank == 0 else None
 
@@ -554,9 +577,10 @@ def measure_ours(args):
                    "l2": f"inputs ({24 * n / 1e6:.0f} MB) larger than L2; no flush needed",
                    "mode": "exact (bit-identical to the reference CPU path)",
                    "parity": parity},
-        "e2e": {"value": jobs * n / e2e_s / 1e6, "unit": "Mpixels/s", "h2d_bytes_per_step": 24 * n,
-                "d2h_bytes_per_step": 8 * n + 24 * K, "ms_per_step": e2e_s * 1e3, "host_buffers": "pinned",
-                "api": "patolette() C ABI (lib/include/patolette.h:22-32), f64 planes in, size_t map out",
+        "e2e": {"value": jobs * n / e2e_s / 1e6, "unit": "Mpixels/s", "h2d_bytes_per_step": 24 * n * jobs,
+                "d2h_bytes_per_step": (8 * n + 24 * K) * jobs, "ms_per_step": e2e_s * 1e3, "host_buffers": "pinned",
+                "api": ("patolette_b200_sharded(): every rank passes its pixel slice (f64 planes) and receives the map of its slice; bytes are the job's totals"
+                        if shard else "patolette() C ABI (lib/include/patolette.h:22-32), f64 planes in, size_t map out"),
                 "stage_ms": {k: round(v, 3) for k, v in e2e_stage.items()}, **e2e_extra},
         "gpu_launches": launches * args.steps if launches else None,
         "gpu_launches_per_step": launches,

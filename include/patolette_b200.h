@@ -111,6 +111,33 @@ PB200_API void patolette_b200_interleaved(size_t width, size_t height, const dou
 PB200_API void patolette_b200_device(size_t width, size_t height, const double *d_data, const double *d_weights,
                                      size_t palette_size, const patolette__QuantizationOptions *options,
                                      double *palette, size_t *d_palette_map, int *exit_code);
+/* N1 (uint8 ingest): the workflow of README.md:150-158 starts from an 8-bit image, converts to f64 and divides by
+ * 255 on the host before calling quantize().  Here rgb is N x 3 row-major uint8 (PIL / numpy layout); value / 255
+ * is evaluated on the device in f64 (the same IEEE division), so palette and map equal what patolette() returns
+ * for the image `rgb / 255.0`.  palette_map element size: map_bytes = 1 (palette_size <= 256), 2 (<= 65536) or 8
+ * (size_t).  device_io != 0: rgb / weights / palette_map are device pointers.  Exit codes as patolette(); a
+ * map_bytes that cannot hold palette_size - 1 gives -3. */
+PB200_API void patolette_b200_u8(size_t width, size_t height, const uint8_t *rgb, const double *weights,
+                                 size_t palette_size, const patolette__QuantizationOptions *options, double *palette,
+                                 void *palette_map, int map_bytes, int device_io, int *exit_code);
+
+/* Image-sharded multi-GPU runs (one process per GPU).  The library owns an NCCL communicator:
+ * rank 0 calls patolette_b200_comm_unique_id() and hands the 128 bytes to every rank (any transport), then all
+ * ranks call patolette_b200_comm_init() (collective; after patolette_b200_set_device()).  world = 1 drops it.
+ * patolette_b200_sharded() is then a collective call: rank r passes pixels [first, first + count) of the image
+ * (patolette_b200_shard_range; planes of `count` doubles, column-major count x 3) and receives the map of the same
+ * pixels and the whole palette.  Colour planes are all-gathered over NVLink, the split loop is sharded by cluster
+ * with one device-side all-gather of 240 B per evaluated cluster and batch; results are bit-identical for every
+ * world size.  comm_info returns 1 when a communicator with world > 1 is active. */
+PB200_API int patolette_b200_comm_unique_id(char *id128);
+PB200_API int patolette_b200_comm_init(int rank, int world, const char *id128);
+PB200_API void patolette_b200_comm_destroy(void);
+PB200_API int patolette_b200_comm_info(int *rank, int *world, int *nccl_version);
+PB200_API int patolette_b200_shard_range(size_t n_pixels, int rank, int world, size_t *first, size_t *count);
+PB200_API void patolette_b200_sharded(size_t width, size_t height, const double *slice, const double *weights_slice,
+                                      size_t palette_size, const patolette__QuantizationOptions *options,
+                                      double *palette, size_t *map_slice, int device_io, int *exit_code);
+
 /* Working buffers (~100 B per pixel) are cached between calls; this returns them to the driver
  * (and reports how many bytes were held). */
 PB200_API size_t patolette_b200_release_cache(void);

@@ -25,6 +25,7 @@ bad_channel_count = "Expected colors to be in sRGB[0, 1] space. Channel count mi
 bad_tile_size = "tile_size parameter expected to be in the range [0, inf]"
 
 __all__ = ["__doc__", "__version__", "quantize", "ColorSpace_sRGB", "ColorSpace_CIELuv", "ColorSpace_ICtCp",
+           "quantize_u8", "init_sharding", "shard_range", "quantize_sharded", "sharding_description",
            "set_sharding", "torch_allgather"]
 
 
@@ -86,6 +87,114 @@ def quantize(width, height, colors, palette_size, dither=True, palette_only=Fals
         return (success, None, None, message)
     if palette_only:
         return (success, palette, None, message)
+    return (success, palette, pmap, message)
+
+
+def quantize_u8(width, height, rgb, palette_size, dither=True, palette_only=False, color_space=ColorSpace_ICtCp,
+                kmeans_niter=32, kmeans_max_samples=512 ** 2, verbose=False, *, weights=None):
+    """N1 (extension): quantise an 8-bit image without the host-side f64 conversion of README.md:150-158.
+
+    ``rgb``: uint8 array [N, 3] (or [H, W, 3]).  The division by 255 happens on the device in f64 (the same IEEE
+    operation), so the result equals ``quantize(width, height, rgb / 255.0, ..., tile_size=0)``; the map comes back
+    as uint8 (palette_size <= 256) or uint16 instead of uintp.  Returns (success, palette, palette_map, message)."""
+    rgb = np.ascontiguousarray(rgb, dtype=np.uint8).reshape(-1, 3)
+    if rgb.shape[0] != width * height:
+        return (False, None, None, color_mismatch)
+    if palette_size > 65536:
+        raise ValueError("quantize_u8 returns 8- or 16-bit indices: palette_size <= 65536")
+    lib = _lib.load()
+    map_dtype = np.uint8 if palette_size <= 256 else np.uint16
+    palette = np.zeros((palette_size, 3), dtype=np.float64, order="F")
+    pmap = None if palette_only else np.zeros(width * height, dtype=map_dtype)
+    w = None
+    if weights is not None:
+        w = np.ascontiguousarray(weights, dtype=np.float64)
+        if w.shape != (width * height,):
+            raise ValueError("weights must have one entry per pixel")
+    opts = _lib.QuantizationOptions(bool(dither), bool(palette_only), int(color_space), int(kmeans_niter),
+                                    int(kmeans_max_samples), bool(verbose))
+    code = C.c_int(0)
+    lib.patolette_b200_u8(width, height, rgb.ctypes.data if rgb.size else None, None if w is None else w.ctypes.data,
+                          palette_size, C.byref(opts), palette.ctypes.data if palette_size else None,
+                          None if pmap is None else pmap.ctypes.data, np.dtype(map_dtype).itemsize, 0, C.byref(code))
+    success = code.value == 0
+    message = lib.get_patolette_exit_code_info_message(code.value).decode("utf-8")
+    if not success:
+        return (success, None, None, message)
+    return (success, palette, None if palette_only else pmap, message)
+
+
+def init_sharding(dist=None, group=None) -> tuple[int, int]:
+    """Image-sharded multi-GPU runs (extension): create the library's NCCL communicator over the
+    ranks of a torch.distributed process group (one process per GPU; call after ``torch.cuda.set_device`` /
+    ``patolette_b200_set_device``).  The 128-byte NCCL unique id travels through ``dist.broadcast``; torch is
+    plumbing only.  Returns (rank, world)."""
+    import torch
+    if dist is None:
+        import torch.distributed as dist
+    lib = _lib.load()
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    ident = C.create_string_buffer(128)
+    if rank == 0 and lib.patolette_b200_comm_unique_id(ident) != 0:
+        raise RuntimeError("patolette_b200: NCCL is not available (libnccl.so.2)")
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    t = torch.frombuffer(bytearray(ident.raw), dtype=torch.uint8).to(dev)
+    dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    raw = bytes(t.cpu().numpy().tobytes())
+    if lib.patolette_b200_comm_init(rank, world, raw) != 0:
+        raise RuntimeError("patolette_b200: ncclCommInitRank failed")
+    return rank, world
+
+
+def shard_range(n_pixels: int, rank: int, world: int) -> tuple[int, int]:
+    """(first, count): the pixels rank ``rank`` of ``world`` brings to :func:`quantize_sharded`."""
+    first, count = C.c_size_t(0), C.c_size_t(0)
+    if _lib.load().patolette_b200_shard_range(n_pixels, rank, world, C.byref(first), C.byref(count)) != 0:
+        raise ValueError("bad rank / world")
+    return first.value, count.value
+
+
+def sharding_description() -> str:
+    lib = _lib.load()
+    r, w, v = C.c_int(0), C.c_int(1), C.c_int(0)
+    lib.patolette_b200_comm_info(C.byref(r), C.byref(w), C.byref(v))
+    return (f"image-sharded x{w.value}: one image, pixel slices in / map slices out; colour planes all-gathered over NVLink "
+            f"(NCCL {v.value}), split loop sharded by cluster with a device-side all-gather per batch, GQ / KMeans sample / "
+            f"dither walk replicated")
+
+
+def quantize_sharded(width, height, colors_slice, palette_size, dither=True, palette_only=False,
+                     color_space=ColorSpace_ICtCp, kmeans_niter=32, kmeans_max_samples=512 ** 2, verbose=False, *,
+                     weights_slice=None):
+    """Collective over the ranks of :func:`init_sharding`: every rank passes ITS pixels (``shard_range``) as an
+    [count, 3] f64 array and gets back ``(success, palette, palette_map_of_its_pixels, message)``.  Bit-identical to
+    ``quantize`` on the whole image for every world size."""
+    lib = _lib.load()
+    r, w = C.c_int(0), C.c_int(1)
+    if not lib.patolette_b200_comm_info(C.byref(r), C.byref(w), None):
+        raise RuntimeError("call init_sharding() first")
+    first, count = shard_range(width * height, r.value, w.value)
+    data = np.asfortranarray(colors_slice, dtype=np.float64)
+    if data.shape != (count, 3):
+        raise ValueError(f"rank {r.value} of {w.value} must pass pixels [{first}, {first + count}): shape ({count}, 3)")
+    ws = None
+    if weights_slice is not None:
+        ws = np.ascontiguousarray(weights_slice, dtype=np.float64)
+        if ws.shape != (count,):
+            raise ValueError("weights_slice must have one entry per pixel of the slice")
+    palette = np.zeros((palette_size, 3), dtype=np.float64, order="F")
+    pmap = None if palette_only else np.zeros(count, dtype=np.uintp)
+    opts = _lib.QuantizationOptions(bool(dither), bool(palette_only), int(color_space), int(kmeans_niter),
+                                    int(kmeans_max_samples), bool(verbose))
+    code = C.c_int(0)
+    lib.patolette_b200_sharded(width, height, data.ctypes.data if count else None, None if ws is None else ws.ctypes.data,
+                               palette_size, C.byref(opts), palette.ctypes.data,
+                               None if pmap is None or not count else pmap.ctypes.data, 0, C.byref(code))
+    success = code.value == 0
+    message = lib.get_patolette_exit_code_info_message(code.value).decode("utf-8")
+    if not success:
+        return (success, None, None, message)
     return (success, palette, pmap, message)
 
 

@@ -221,6 +221,31 @@ __global__ void __launch_bounds__(256) k_deinterleave(const double *__restrict__
     }
 }
 
+// N1: N x 3 interleaved uint8 RGB -> three f64 planes of value / 255 - the division the README's
+// workflow performs on the host (README.md:155-158: astype(float64), then /= 255), IEEE-exact, so the planes hold
+// the very doubles the f64 ABI would have been given.  24x fewer bytes cross PCIe.
+__global__ void __launch_bounds__(256) k_u8_to_planes(const uint8_t *__restrict__ rgb, size_t n, double *__restrict__ d0,
+                                                      double *__restrict__ d1, double *__restrict__ d2) {
+    __shared__ uint8_t tile[1024 * 3];
+    for (size_t base = (size_t)blockIdx.x * 1024; base < n; base += (size_t)gridDim.x * 1024) {
+        const size_t cnt = min((size_t)1024, n - base);
+        for (size_t i = threadIdx.x; i < cnt * 3; i += 256) tile[i] = rgb[base * 3 + i]; // coalesced bytes
+        __syncthreads();
+        for (size_t i = threadIdx.x; i < cnt; i += 256) {
+            d0[base + i] = __ddiv_rn((double)tile[3 * i], 255.0);
+            d1[base + i] = __ddiv_rn((double)tile[3 * i + 1], 255.0);
+            d2[base + i] = __ddiv_rn((double)tile[3 * i + 2], 255.0);
+        }
+        __syncthreads();
+    }
+}
+
+// palette_map as the index type a palette image stores: uint8 (K <= 256) or uint16 (K <= 65536) instead of size_t
+template <typename T>
+__global__ void __launch_bounds__(256) k_narrow_map(const unsigned long long *__restrict__ map, size_t n, T *__restrict__ out) {
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (size_t)gridDim.x * 256) out[i] = (T)map[i];
+}
+
 __global__ void k_pow(const double *x, double y, double *out, size_t n) {
     __shared__ uint64_t s_log[128 * 3];
     __shared__ uint64_t s_exp[256];
@@ -275,6 +300,21 @@ void pb_launch_deinterleave(const double *d_rgb, size_t n, double *const dst[3],
     if (n == 0) return;
     PbProfScope _prof("k_deinterleave", st);
     k_deinterleave<<<grid_for(n, 256, sm_count), 256, 0, st>>>(d_rgb, n, dst[0], dst[1], dst[2]);
+    PB_CUDA_OK(cudaGetLastError());
+}
+
+void pb_launch_u8_to_planes(const uint8_t *d_rgb, size_t n, double *const dst[3], int sm_count, cudaStream_t st) {
+    if (n == 0) return;
+    PbProfScope _prof("k_u8_to_planes", st);
+    k_u8_to_planes<<<grid_for(n, 1024, sm_count), 256, 0, st>>>(d_rgb, n, dst[0], dst[1], dst[2]);
+    PB_CUDA_OK(cudaGetLastError());
+}
+
+void pb_launch_narrow_map(const unsigned long long *d_map, size_t n, void *d_out, int bytes, int sm_count, cudaStream_t st) {
+    if (n == 0) return;
+    PbProfScope _prof("k_narrow_map", st, false);
+    if (bytes == 1) k_narrow_map<uint8_t><<<grid_for(n, 256, sm_count), 256, 0, st>>>(d_map, n, (uint8_t *)d_out);
+    else k_narrow_map<uint16_t><<<grid_for(n, 256, sm_count), 256, 0, st>>>(d_map, n, (uint16_t *)d_out);
     PB_CUDA_OK(cudaGetLastError());
 }
 

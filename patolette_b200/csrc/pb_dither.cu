@@ -271,8 +271,22 @@ __device__ __forceinline__ int dither_nn4(double x, double y, double z, const do
     const int cell = G.cnt ? pb_grid_cell(true, G.geom, G.geom + 3, x, y, z) : -1; // uniform within the group
     if (cell >= 0) {
         const unsigned short *Lst = G.list + (size_t)cell * K;
+        // the first four entries of this lane are requested together with the count (K >= 64: in bounds), so the
+        // step pays one memory round trip, not two
+        const int pre[4] = {Lst[gl], Lst[gl + DS_GROUP], Lst[gl + 2 * DS_GROUP], Lst[gl + 3 * DS_GROUP]};
         const int m = G.cnt[cell];
-        for (int t = gl; t < m; t += DS_GROUP) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int t = gl + u * DS_GROUP;
+            if (t < m) {
+                const int j = pre[u];
+                const double dx = __dsub_rn(x, s_palw[3 * j]), dy = __dsub_rn(y, s_palw[3 * j + 1]),
+                             dz = __dsub_rn(z, s_palw[3 * j + 2]);
+                const double dd = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                if (best == 0x7fffffff || dd < bd) { bd = dd; best = j; }
+            }
+        }
+        for (int t = gl + 4 * DS_GROUP; t < m; t += DS_GROUP) {
             const int j = Lst[t];
             const double dx = __dsub_rn(x, s_palw[3 * j]), dy = __dsub_rn(y, s_palw[3 * j + 1]),
                          dz = __dsub_rn(z, s_palw[3 * j + 2]);

@@ -20,6 +20,9 @@ void pb_launch_color(int which, const double *const src[3], double *const dst[3]
                      int sm_count, cudaStream_t st);
 void pb_launch_pow(const double *x, double y, double *out, size_t n, int sm_count, cudaStream_t st);
 void pb_launch_deinterleave(const double *d_rgb, size_t n, double *const dst[3], int sm_count, cudaStream_t st);
+// N x 3 interleaved uint8 -> planes of value / 255 (f64, IEEE division); size_t map -> uint8 / uint16 indices
+void pb_launch_u8_to_planes(const uint8_t *d_rgb, size_t n, double *const dst[3], int sm_count, cudaStream_t st);
+void pb_launch_narrow_map(const unsigned long long *d_map, size_t n, void *d_out, int bytes, int sm_count, cudaStream_t st);
 
 // ---- ordered-sum kernels, pb_ordered.cu / pb_chain.cu ----------------------------------
 // Every reference statistic is a left-to-right f64 sum in ascending pixel order; these

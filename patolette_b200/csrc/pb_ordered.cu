@@ -551,7 +551,7 @@ __global__ void __launch_bounds__(OS_THREADS, PB_OS_MINB) k_ord_summary(PbPlanes
 constexpr int OF_WARPS = PB_OF_WARPS;
 constexpr int OF_THREADS = 32 * OF_WARPS;
 #ifndef PB_OF_MINB
-#define PB_OF_MINB 6
+#define PB_OF_MINB 8 // resident CTAs per SM asked of ptxas: 16 warps at 128 registers; shared memory allows 8 (6 weighted)
 #endif
 constexpr long long OF_MARGIN = 1LL << 20; // units between the predicted start state and the interval's ends
 
@@ -579,15 +579,34 @@ __global__ void __launch_bounds__(OF_THREADS, PB_OF_MINB) k_ord_fast(PbPlanes b0
     const uint32_t bcnt = min((uint32_t)OB, sg.n - blk * OB);
     const size_t g0 = (size_t)sg.lo + (size_t)blk * OB;
     // ---- stage the block ------------------------------------------------------------------------------
+    // a full block: every load of the block is issued before the first store (48 - 64 independent 256-byte
+    // requests per warp in flight: one memory round trip per block instead of four; nothing else is live yet)
+    if (bcnt == OB) {
+        double v0[OB / 32], v1[OB / 32], v2[OB / 32], vw[W ? OB / 32 : 1];
+#pragma unroll
+        for (int q = 0; q < OB / 32; q++) {
+            const size_t g = g0 + q * 32 + lane;
+            v0[q] = P.c[0][g]; v1[q] = P.c[1][g]; v2[q] = P.c[2][g];
+            if (W) vw[q] = P.w[g];
+        }
+#pragma unroll
+        for (int q = 0; q < OB / 32; q++) {
+            const int idx = q * 32 + lane;
+            const int at = (idx >> 4) * OS_STRIDE + (idx & 15);
+            stage[0 * OS_PLANE + at] = v0[q]; stage[1 * OS_PLANE + at] = v1[q]; stage[2 * OS_PLANE + at] = v2[q];
+            if (W) stage[3 * OS_PLANE + at] = vw[q];
+        }
+    } else {
 #pragma unroll 4
-    for (int q = 0; q < OB / 32; q++) {
-        const uint32_t idx = q * 32 + lane;
-        if (idx < bcnt) {
-            const int at = (int)(idx >> 4) * OS_STRIDE + (int)(idx & 15);
-            stage[0 * OS_PLANE + at] = P.c[0][g0 + idx];
-            stage[1 * OS_PLANE + at] = P.c[1][g0 + idx];
-            stage[2 * OS_PLANE + at] = P.c[2][g0 + idx];
-            if (W) stage[3 * OS_PLANE + at] = P.w[g0 + idx];
+        for (int q = 0; q < OB / 32; q++) {
+            const uint32_t idx = q * 32 + lane;
+            if (idx < bcnt) {
+                const int at = (int)(idx >> 4) * OS_STRIDE + (int)(idx & 15);
+                stage[0 * OS_PLANE + at] = P.c[0][g0 + idx];
+                stage[1 * OS_PLANE + at] = P.c[1][g0 + idx];
+                stage[2 * OS_PLANE + at] = P.c[2][g0 + idx];
+                if (W) stage[3 * OS_PLANE + at] = P.w[g0 + idx];
+            }
         }
     }
     double m0 = 0, m1 = 0, m2 = 0;

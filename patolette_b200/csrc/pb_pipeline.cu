@@ -21,6 +21,7 @@
 #include "pb_host.h"
 #include "pb_hostpool.h"
 #include "pb_kernels.h"
+#include "pb_nccl.h"
 #include "pb_pipeline.h"
 #include "pb_pool.h"
 #include "pb_prof.h"
@@ -286,7 +287,53 @@ size_t principal_quantizer(size_t K, const CellMoments &m, size_t *q) {
 struct HNode {
     PbSeg seg;
     PbStats st;
+    int owner = -1; // image-sharded runs: the rank that holds this cluster's pixels, -1 = every rank does
 };
+
+// ---- image-sharded runs (patolette_b200_sharded, NCCL) ---------------------------------------------------
+// Rank r brings pixels [first, first + count) of the image.  After the colour transform the planes are
+// all-gathered, GQ runs replicated, and the split loop is sharded by CLUSTER: split_cluster(c) is a pure
+// function of c's pixels, so which GPU evaluates a cluster cannot change a bit of the result.  While the tree is
+// narrower than the machine every rank evaluates every cluster (the data stays replicated); from the first batch
+// with at least `world` replicated clusters on, clusters are dealt out (largest first, to the least loaded rank)
+// and a cluster's children stay with the rank that made them - that rank is the only one holding their pixels.
+// Per batch the ranks all-gather the children's segments and statistics (240 B per evaluated cluster) on the
+// device; the greedy selection runs replicated on every host, on identical numbers.
+struct ShardCtx {
+    bool on = false;
+    int rank = 0, world = 1;
+    size_t S = 0;     // slice stride: ceil(n / world) rounded up to 1024 pixels
+    size_t first = 0; // first pixel of this rank
+    size_t count = 0; // pixels of this rank
+};
+size_t shard_stride(size_t n, int world) {
+    const size_t per = (n + (size_t)world - 1) / (size_t)world;
+    return (per + 1023) & ~(size_t)1023;
+}
+ShardCtx make_shard_ctx(size_t n, bool on) {
+    ShardCtx c;
+    if (!on || !pb_nccl_active()) return c;
+    c.on = true;
+    c.rank = pb_nccl_rank();
+    c.world = pb_nccl_world();
+    c.S = shard_stride(n, c.world);
+    c.first = std::min(n, (size_t)c.rank * c.S);
+    c.count = std::min(c.S, n - c.first);
+    return c;
+}
+struct XRes { // what the evaluation of one cluster produces
+    PbSeg seg[2];
+    PbStats st[2];
+};
+__global__ void k_pack_results(const PbSeg *__restrict__ children, const PbStats *__restrict__ stats,
+                               const int *__restrict__ gidx, int nb, XRes *__restrict__ out) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nb) return;
+    XRes x;
+    x.seg[0] = children[2 * b]; x.seg[1] = children[2 * b + 1];
+    x.st[0] = stats[2 * b]; x.st[1] = stats[2 * b + 1];
+    out[gidx[b]] = x;
+}
 struct HPair {
     bool valid = false;
     HNode l, r;
@@ -313,6 +360,9 @@ struct Quantizer {
     DevArr<uint8_t> lut;
     DevArr<char> oscratch; // block sums + summaries of the speculative ordered sums
     PbPlanes orig{}, bufs[2]{};
+    ShardCtx sh;                       // image-sharded run (NCCL) or not
+    DevArr<XRes> xres, xall;           // this rank's batch results by global batch position; all ranks' (all-gathered)
+    DevArr<int> gidx[2];               // per half-batch: global batch position of every local cluster
 
     // Second half-batch context.  The ordered-sum resolve of a batch is latency-bound (one warp per chain,
     // a few dozen busy SMs) while the summaries, scatters and bucket chains are throughput work: a batch is
@@ -337,7 +387,8 @@ struct Quantizer {
     size_t max_blocks = 0;         // capacity of the packed ordered-sum block table
     size_t max_tiles = 0;          // capacity of the packed scatter tile table
 
-    void init(size_t n, bool with_weights) {
+    void init(size_t n, bool with_weights, size_t n_alloc = 0) {
+        if (n_alloc < n) n_alloc = n;
         N = n;
         weighted = with_weights;
         PB_CUDA_OK(cudaSetDevice(g_device));
@@ -349,8 +400,8 @@ struct Quantizer {
         sm_count = cached_sms;
         if (g_use_user_stream) { st = g_user_stream; own_stream = false; }
         else PB_CUDA_OK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-        for (int j = 0; j < 3; j++) col[j].alloc(n);
-        if (weighted) wgt.alloc(n);
+        for (int j = 0; j < 3; j++) col[j].alloc(n_alloc);
+        if (weighted) wgt.alloc(n_alloc);
         orig = PbPlanes{{col[0].p, col[1].p, col[2].p}, nullptr, nullptr};
     }
     void init_tree() {
@@ -374,6 +425,12 @@ struct Quantizer {
         stats.alloc(2 * MAXB);
         split.alloc(MAXB);
         lut.alloc(PB_BUCKETS);
+        if (sh.on) {
+            xres.alloc(MAXB);
+            xall.alloc((size_t)MAXB * sh.world);
+            gidx[0].alloc(MAXB);
+            gidx[1].alloc(MAXB);
+        }
         max_blocks = 2 * ((size_t)pb_ordered_blocks((uint32_t)N) + 2 * MAXB) + 64;
         oscratch.alloc(pb_ordered_scratch_bytes(max_blocks));
         const char *e = getenv("PB200_OVERLAP");
@@ -533,12 +590,40 @@ struct Quantizer {
             cand[nc++].i = i;
         }
         if (nc == 0) return;
-        // two half-batches (largest first, each to the lighter half); one when profiling per kernel
-        const int nhalf = (overlap && nc >= 2 && !pb_prof_enabled()) ? 2 : 1;
         std::sort(cand, cand + nc, [&](const Cand &a, const Cand &b) { return nodes[a.i]->seg.n > nodes[b.i]->seg.n; });
+        // image-sharded runs: the rank that evaluates every candidate (-1: all of them, the result stays replicated).
+        // Every rank runs this on identical inputs, so all agree.  Replicated clusters are dealt out as soon as there
+        // are enough of them for every rank (or the batch mixes them with clusters that already have an owner).
+        int exec[MAXB];
+        for (int c = 0; c < nc; c++) exec[c] = -1;
+        if (sh.on) {
+            double load[256] = {0};
+            int n_rep = 0;
+            bool any_owned = false;
+            for (int c = 0; c < nc; c++) {
+                const HNode &nd = *nodes[cand[c].i];
+                if (nd.owner >= 0) { exec[c] = nd.owner; load[nd.owner] += nd.seg.n; any_owned = true; }
+                else n_rep++;
+            }
+            if (n_rep >= sh.world || any_owned)
+                for (int c = 0; c < nc; c++) { // largest first (cand is sorted), each to the least loaded rank
+                    if (exec[c] >= 0) continue;
+                    int best = 0;
+                    for (int r = 1; r < sh.world; r++)
+                        if (load[r] < load[best]) best = r;
+                    exec[c] = best;
+                    load[best] += nodes[cand[c].i]->seg.n;
+                }
+        }
+        auto mine = [&](int c) { return exec[c] < 0 || exec[c] == sh.rank; };
+        int nlocal = 0;
+        for (int c = 0; c < nc; c++) nlocal += mine(c) ? 1 : 0;
+        // two half-batches (largest first, each to the lighter half); one when profiling per kernel
+        const int nhalf = (overlap && nlocal >= 2 && !pb_prof_enabled()) ? 2 : 1;
         struct HalfBatch {
             PbSeg hsegs[MAXB];
             double haxes[3 * MAXB];
+            int gidx[MAXB]; // position of the cluster in the (rank-independent) sorted candidate list
             int map[MAXB], nb = 0;
             uint32_t max_n = 0, tb = 0, bb = 0;
             double tot_n = 0;
@@ -548,6 +633,7 @@ struct Quantizer {
         static thread_local HalfBatch hb[2];
         for (int h = 0; h < 2; h++) { hb[h].nb = 0; hb[h].max_n = hb[h].tb = hb[h].bb = 0; hb[h].tot_n = 0; }
         for (int c = 0; c < nc; c++) {
+            if (!mine(c)) continue;
             HalfBatch &B = hb[(nhalf == 2 && hb[1].tot_n < hb[0].tot_n) ? 1 : 0];
             const HNode &nd = *nodes[cand[c].i];
             PbSeg &sg = B.hsegs[B.nb];
@@ -559,6 +645,7 @@ struct Quantizer {
             memcpy(&B.haxes[3 * B.nb], cand[c].axis, sizeof cand[c].axis);
             B.max_n = std::max(B.max_n, sg.n);
             B.tot_n += sg.n;
+            B.gidx[B.nb] = c;
             B.map[B.nb++] = cand[c].i;
         }
         struct Dev { // device scratch of a half
@@ -633,6 +720,34 @@ struct Quantizer {
             }
             for (int h = 0; h < nhalf; h++)
                 if (hb[h].nb) step(k, hb[h], dev[h]);
+        }
+        if (sh.on) {
+            // every rank packs what it evaluated into the batch-position slots, the slots are all-gathered on the
+            // device, and one copy brings every rank's results home
+            for (int h = 0; h < nhalf; h++) {
+                if (!hb[h].nb) continue;
+                PB_CUDA_OK(cudaMemcpyAsync(gidx[h].p, hb[h].gidx, hb[h].nb * sizeof(int), cudaMemcpyHostToDevice, dev[h].st));
+                { PbProfScope _prof("k_pack_results", dev[h].st, false);
+                  k_pack_results<<<(hb[h].nb + 63) / 64, 64, 0, dev[h].st>>>(dev[h].children, dev[h].stats, gidx[h].p, hb[h].nb, xres.p); }
+            }
+            if (nhalf == 2 && hb[1].nb) { // join: the exchange runs on the first stream
+                PB_CUDA_OK(cudaEventRecord(hx.fork, hx.st));
+                PB_CUDA_OK(cudaStreamWaitEvent(st, hx.fork, 0));
+            }
+            pb_nccl_allgather(xres.p, xall.p, (size_t)nc * sizeof(XRes), st);
+            static thread_local std::vector<XRes> hall;
+            hall.resize((size_t)nc * sh.world);
+            PB_CUDA_OK(cudaMemcpyAsync(hall.data(), xall.p, hall.size() * sizeof(XRes), cudaMemcpyDeviceToHost, st));
+            PB_CUDA_OK(cudaStreamSynchronize(st));
+            for (int c = 0; c < nc; c++) {
+                const XRes &x = hall[(size_t)(exec[c] < 0 ? sh.rank : exec[c]) * nc + c];
+                HPair *o = outs[cand[c].i];
+                o->valid = true;
+                o->l = HNode{x.seg[0], x.st[0]};
+                o->r = HNode{x.seg[1], x.st[1]};
+                o->l.owner = o->r.owner = exec[c];
+            }
+            return;
         }
         for (int h = 0; h < nhalf; h++) { // pageable destinations: each copy returns when its stream got there
             if (!hb[h].nb) continue;
@@ -778,24 +893,41 @@ void palette_transform(Quantizer &qz, int which, std::vector<double> &pal_rm) {
         for (int c = 0; c < 3; c++) pal_rm[3 * j + c] = planar[c * K + j];
 }
 
-void colors_transform(Quantizer &qz, int which) {
-    const double *src[3] = {qz.col[0].p, qz.col[1].p, qz.col[2].p};
-    double *dst[3] = {qz.col[0].p, qz.col[1].p, qz.col[2].p};
-    pb_prof_next_bytes(48.0 * qz.N);
-    pb_launch_color(which, src, dst, qz.N, qz.sm_count, qz.st);
+void colors_transform(Quantizer &qz, int which, size_t off = 0, size_t len = (size_t)-1) {
+    if (len == (size_t)-1) len = qz.N - off;
+    if (!len) return;
+    const double *src[3] = {qz.col[0].p + off, qz.col[1].p + off, qz.col[2].p + off};
+    double *dst[3] = {qz.col[0].p + off, qz.col[1].p + off, qz.col[2].p + off};
+    pb_prof_next_bytes(48.0 * len);
+    pb_launch_color(which, src, dst, len, qz.sm_count, qz.st);
 }
 
-void run_patolette(size_t width, size_t height, const double *data, const double *weights, size_t K,
-                   const patolette__QuantizationOptions *opt, double *palette, size_t *palette_map,
-                   int *exit_code, bool device_io, bool interleaved = false) {
+// How the caller's buffers look.  The reference ABI is {host, planar f64, size_t map}.
+struct IoSpec {
+    bool device_io = false; // data / weights / map are device pointers
+    int in_fmt = 0;         // 0: three f64 planes (column-major N x 3), 1: N x 3 row-major f64, 2: N x 3 row-major uint8 (/ 255 on the device)
+    int map_bytes = 8;      // palette_map element: 8 (size_t), 1 or 2
+    bool sharded = false;   // data / weights / map hold this rank's pixel slice only (NCCL communicator required)
+};
+enum { IN_PLANAR = 0, IN_INTERLEAVED = 1, IN_U8 = 2 };
+
+void run_patolette(size_t width, size_t height, const void *data_v, const double *weights, size_t K,
+                   const patolette__QuantizationOptions *opt, double *palette, void *palette_map,
+                   int *exit_code, const IoSpec &io) {
     const size_t n = width * height;
+    const bool device_io = io.device_io;
     // the f32 KMeans slice sorts samples by a 16-bit assignment through per-warp class counters in shared
     // memory: beyond PB_KMEANS_MAX_K the call fails with its own code instead of silently skipping refinement
     if (opt->kmeans_niter > 0 && K > PB_KMEANS_MAX_K && n >= K) { *exit_code = -6; return; }
+    if (io.sharded && !pb_nccl_active()) { *exit_code = -1; return; }
     memset(g_timings, 0, sizeof g_timings);
     const long launches0 = pb_prof_launch_count();
     Quantizer qz;
-    qz.init(n, weights != nullptr);
+    qz.sh = make_shard_ctx(n, io.sharded);
+    const ShardCtx &sh = qz.sh;
+    // the caller's buffers cover pixels [in_off, in_off + in_n) of the image
+    const size_t in_n = sh.on ? sh.count : n, in_off = sh.on ? sh.first : 0;
+    qz.init(n, weights != nullptr, sh.on ? sh.S * (size_t)sh.world : n);
     Timer total(qz.st), stage(qz.st);
     total.start();
     struct SideStream { // copies that overlap kernels of the compute stream (pinned host buffers only)
@@ -807,56 +939,89 @@ void run_patolette(size_t width, size_t height, const double *data, const double
         ~SideStream() { if (s) cudaStreamDestroy(s); }
     } copy_stream;
     bool piped_color = false;
+    const int to_space = opt->color_space == patolette__CIELuv ? PB_T_SRGB_TO_CIELUV
+                         : opt->color_space == patolette__ICtCp ? PB_T_SRGB_TO_ICTCP : -1;
 
     stage.start(); // patolette.c:187-199: the library works on its own copy
     const cudaMemcpyKind in_kind = device_io ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-    if (interleaved) { // N x 3 row-major input: one copy, de-interleaved on the device
-        DevArr<double> rgb;
-        rgb.alloc(3 * n);
-        if (device_io) PB_CUDA_OK(cudaMemcpyAsync(rgb.p, data, 3 * n * sizeof(double), in_kind, qz.st));
-        else pb_copy_h2d(rgb.p, data, 3 * n * sizeof(double), qz.st);
-        double *dst[3] = {qz.col[0].p, qz.col[1].p, qz.col[2].p};
-        pb_launch_deinterleave(rgb.p, n, dst, qz.sm_count, qz.st);
-        qz.sync(); // rgb is released at the end of this scope
-    } else if (!device_io && n >= ((size_t)1 << 20) && pb_host_is_pinned(data)) {
-        // pinned host planes: the copy is pipelined with the colour transform (patolette.c:201-207) in
-        // chunks - chunk c is transformed on the compute stream while chunk c + 1 crosses PCIe
-        piped_color = true;
-        const int which = opt->color_space == patolette__CIELuv ? PB_T_SRGB_TO_CIELUV
-                          : opt->color_space == patolette__ICtCp ? PB_T_SRGB_TO_ICTCP : -1;
+    double *const cdst[3] = {qz.col[0].p + in_off, qz.col[1].p + in_off, qz.col[2].p + in_off};
+    // chunked delivery from pinned host memory: chunk c is converted / colour-transformed on the compute stream
+    // while chunk c + 1 crosses PCIe.  copy(off, len) enqueues the chunk's copies on the copy stream, then
+    // land(off, len) its kernels on the compute stream.
+    auto piped = [&](auto copy, auto land) {
         constexpr int NCH = 8;
-        const size_t per = ((n + NCH - 1) / NCH + 1023) & ~(size_t)1023;
-        cudaEvent_t ev[NCH];
-        for (size_t off = 0, c = 0; off < n; off += per, c++) {
-            const size_t len = std::min(per, n - off);
-            for (int j = 0; j < 3; j++)
-                PB_CUDA_OK(cudaMemcpyAsync(qz.col[j].p + off, data + (size_t)j * n + off, len * sizeof(double), in_kind, copy_stream.get()));
-            PB_CUDA_OK(cudaEventCreateWithFlags(&ev[c], cudaEventDisableTiming));
-            PB_CUDA_OK(cudaEventRecord(ev[c], copy_stream.get()));
-            PB_CUDA_OK(cudaStreamWaitEvent(qz.st, ev[c], 0));
-            if (which >= 0) {
-                const double *src[3] = {qz.col[0].p + off, qz.col[1].p + off, qz.col[2].p + off};
-                double *dst[3] = {qz.col[0].p + off, qz.col[1].p + off, qz.col[2].p + off};
-                pb_prof_next_bytes(48.0 * len);
-                pb_launch_color(which, src, dst, len, qz.sm_count, qz.st);
-            }
-            PB_CUDA_OK(cudaEventDestroy(ev[c])); // released by the runtime once it has completed
+        const size_t per = ((in_n + NCH - 1) / NCH + 1023) & ~(size_t)1023;
+        for (size_t off = 0; off < in_n; off += per) {
+            const size_t len = std::min(per, in_n - off);
+            copy(off, len);
+            cudaEvent_t ev;
+            PB_CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            PB_CUDA_OK(cudaEventRecord(ev, copy_stream.get()));
+            PB_CUDA_OK(cudaStreamWaitEvent(qz.st, ev, 0));
+            PB_CUDA_OK(cudaEventDestroy(ev)); // released by the runtime once it has completed
+            land(off, len);
         }
-    } else
-    for (int j = 0; j < 3; j++) {
-        if (device_io) PB_CUDA_OK(cudaMemcpyAsync(qz.col[j].p, data + (size_t)j * n, n * sizeof(double), in_kind, qz.st));
-        else pb_copy_h2d(qz.col[j].p, data + (size_t)j * n, n * sizeof(double), qz.st);
+    };
+    const bool pinned_in = !device_io && in_n >= ((size_t)1 << 20) && pb_host_is_pinned(data_v);
+    DevArr<uint8_t> rgb8;
+    if (io.in_fmt == IN_U8) { // N1: uint8 RGB in, / 255 on the device
+        const uint8_t *src = (const uint8_t *)data_v;
+        rgb8.alloc(3 * in_n + 16);
+        if (pinned_in) {
+            piped_color = true;
+            piped([&](size_t off, size_t len) {
+                      PB_CUDA_OK(cudaMemcpyAsync(rgb8.p + 3 * off, src + 3 * off, 3 * len, in_kind, copy_stream.get()));
+                  },
+                  [&](size_t off, size_t len) {
+                      double *const d[3] = {cdst[0] + off, cdst[1] + off, cdst[2] + off};
+                      pb_prof_next_bytes(27.0 * len);
+                      pb_launch_u8_to_planes(rgb8.p + 3 * off, len, d, qz.sm_count, qz.st);
+                      if (to_space >= 0) colors_transform(qz, to_space, in_off + off, len);
+                  });
+        } else {
+            if (device_io) PB_CUDA_OK(cudaMemcpyAsync(rgb8.p, src, 3 * in_n, in_kind, qz.st));
+            else pb_copy_h2d(rgb8.p, src, 3 * in_n, qz.st);
+            pb_prof_next_bytes(27.0 * in_n);
+            pb_launch_u8_to_planes(rgb8.p, in_n, cdst, qz.sm_count, qz.st);
+        }
+    } else if (io.in_fmt == IN_INTERLEAVED) { // N x 3 row-major input: one copy, de-interleaved on the device
+        const double *data = (const double *)data_v;
+        DevArr<double> rgb;
+        rgb.alloc(3 * in_n);
+        if (device_io) PB_CUDA_OK(cudaMemcpyAsync(rgb.p, data, 3 * in_n * sizeof(double), in_kind, qz.st));
+        else pb_copy_h2d(rgb.p, data, 3 * in_n * sizeof(double), qz.st);
+        pb_launch_deinterleave(rgb.p, in_n, cdst, qz.sm_count, qz.st);
+        qz.sync(); // rgb is released at the end of this scope
+    } else if (pinned_in) {
+        // pinned host planes: the copy is pipelined with the colour transform (patolette.c:201-207)
+        const double *data = (const double *)data_v;
+        piped_color = true;
+        piped([&](size_t off, size_t len) {
+                  for (int j = 0; j < 3; j++)
+                      PB_CUDA_OK(cudaMemcpyAsync(cdst[j] + off, data + (size_t)j * in_n + off, len * sizeof(double), in_kind, copy_stream.get()));
+              },
+              [&](size_t off, size_t len) {
+                  if (to_space >= 0) colors_transform(qz, to_space, in_off + off, len);
+              });
+    } else {
+        const double *data = (const double *)data_v;
+        for (int j = 0; j < 3 && in_n; j++) {
+            if (device_io) PB_CUDA_OK(cudaMemcpyAsync(cdst[j], data + (size_t)j * in_n, in_n * sizeof(double), in_kind, qz.st));
+            else pb_copy_h2d(cdst[j], data + (size_t)j * in_n, in_n * sizeof(double), qz.st);
+        }
     }
-    if (weights) {
-        if (device_io) PB_CUDA_OK(cudaMemcpyAsync(qz.wgt.p, weights, n * sizeof(double), in_kind, qz.st));
-        else pb_copy_h2d(qz.wgt.p, weights, n * sizeof(double), qz.st);
+    if (weights && in_n) {
+        if (device_io) PB_CUDA_OK(cudaMemcpyAsync(qz.wgt.p + in_off, weights, in_n * sizeof(double), in_kind, qz.st));
+        else pb_copy_h2d(qz.wgt.p + in_off, weights, in_n * sizeof(double), qz.st);
     }
     set_timing(1, stage.stop());
 
     stage.start(); // patolette.c:201-207
-    if (!piped_color) {
-        if (opt->color_space == patolette__CIELuv) colors_transform(qz, PB_T_SRGB_TO_CIELUV);
-        else if (opt->color_space == patolette__ICtCp) colors_transform(qz, PB_T_SRGB_TO_ICTCP);
+    if (!piped_color && to_space >= 0) colors_transform(qz, to_space, in_off, in_n);
+    if (sh.on) { // every rank transformed its slice: all-gather the planes over NVLink (in place)
+        const size_t sbytes = sh.S * sizeof(double);
+        for (int j = 0; j < 3; j++) pb_nccl_allgather(qz.col[j].p + (size_t)sh.rank * sh.S, qz.col[j].p, sbytes, qz.st);
+        if (weights) pb_nccl_allgather(qz.wgt.p + (size_t)sh.rank * sh.S, qz.wgt.p, sbytes, qz.st);
     }
     set_timing(2, stage.stop());
     if (opt->verbose) printf("patolette ======== Palette generation \n");
@@ -888,8 +1053,13 @@ void run_patolette(size_t width, size_t height, const double *data, const double
     }
 
     if (!opt->palette_only) {
+        // the caller's map covers the same pixels as its input; the device map is always whole-image size_t
+        const size_t out_n = in_n, out_off = in_off;
+        const size_t mb = (size_t)io.map_bytes;
         DevArr<unsigned long long> dmap;
         dmap.alloc(n);
+        DevArr<uint8_t> narrow; // uint8 / uint16 indices of the caller's pixels
+        if (mb != 8) narrow.alloc(out_n * mb + 16);
         bool map_sent = false;
         if (opt->dither) { // patolette.c:268-299
             if (opt->verbose) printf("patolette ======== Dithering\n");
@@ -901,8 +1071,11 @@ void run_patolette(size_t width, size_t height, const double *data, const double
             palette_transform(qz, t, pal);
             const double *planes[3] = {qz.col[0].p, qz.col[1].p, qz.col[2].p};
             // riemersma.c:452-456: a 1x1 image is never dithered; the map keeps the caller's bytes
-            if (palette_map && n == 1)
-                PB_CUDA_OK(cudaMemcpyAsync(dmap.p, palette_map, sizeof(size_t), in_kind, qz.st));
+            if (palette_map && n == 1 && out_n == 1) {
+                PB_CUDA_OK(cudaMemsetAsync(dmap.p, 0, sizeof(size_t), qz.st));
+                PB_CUDA_OK(cudaMemcpyAsync(dmap.p, palette_map, mb, in_kind, qz.st)); // (little endian)
+            }
+            // (an image-sharded run dithers the whole image on every rank: the walk is one recurrence)
             pb_dither_riemersma(planes, width, height, pal, dmap.p, qz.sm_count, qz.st, &qz.launches);
             palette_transform(qz, PB_T_REC2020_TO_SRGB, pal);
             set_timing(7, stage.stop());
@@ -910,43 +1083,49 @@ void run_patolette(size_t width, size_t height, const double *data, const double
             if (opt->verbose) printf("patolette ======== NN mapping\n");
             stage.start();
             if (opt->color_space == patolette__CIELuv) {
-                colors_transform(qz, PB_T_CIELUV_TO_ICTCP);
+                colors_transform(qz, PB_T_CIELUV_TO_ICTCP, out_off, out_n); // (a sharded run maps its own pixels only)
                 palette_transform(qz, PB_T_CIELUV_TO_ICTCP, pal);
             }
             DevArr<double> dpal;
             dpal.alloc(3 * count);
             qz.h2d(dpal.p, pal.data(), 3 * count);
-            const double *planes[3] = {qz.col[0].p, qz.col[1].p, qz.col[2].p};
+            const double *planes[3] = {qz.col[0].p + out_off, qz.col[1].p + out_off, qz.col[2].p + out_off};
             // exact 1-NN through per-cell candidate lists when the brute force would be FP64-bound (pb_nngrid.cu)
             DevArr<char> nngrid;
-            const bool use_grid = g_nn_grid && count >= 32 && count <= 4096 && n >= ((size_t)1 << 18);
+            const bool use_grid = g_nn_grid && count >= 32 && count <= 4096 && out_n >= ((size_t)1 << 18);
             if (use_grid) {
                 nngrid.alloc(pb_nngrid_scratch_bytes((int)count));
-                pb_launch_nngrid_build(planes, n, dpal.p, (int)count, nngrid.p, qz.sm_count, qz.st);
+                pb_launch_nngrid_build(planes, out_n, dpal.p, (int)count, nngrid.p, qz.sm_count, qz.st);
             }
             auto assign = [&](const double *const pl[3], size_t len, unsigned long long *out) {
+                if (!len) return;
                 pb_prof_next_bytes(32.0 * len);
                 if (use_grid) pb_launch_nearest_grid(pl, len, dpal.p, (int)count, nngrid.p, out, qz.sm_count, qz.st);
                 else pb_launch_nearest(pl, len, dpal.p, (int)count, out, qz.sm_count, qz.st);
             };
-            if (!device_io && n >= ((size_t)1 << 20) && pb_host_is_pinned(palette_map)) {
+            if (!device_io && out_n >= ((size_t)1 << 20) && pb_host_is_pinned(palette_map)) {
                 // pinned destination: the map goes home chunk by chunk while the next chunk is assigned
                 constexpr int NCH = 4;
-                const size_t per = ((n + NCH - 1) / NCH + 1023) & ~(size_t)1023;
-                for (size_t off = 0; off < n; off += per) {
-                    const size_t len = std::min(per, n - off);
+                const size_t per = ((out_n + NCH - 1) / NCH + 1023) & ~(size_t)1023;
+                for (size_t off = 0; off < out_n; off += per) {
+                    const size_t len = std::min(per, out_n - off);
                     const double *pl[3] = {planes[0] + off, planes[1] + off, planes[2] + off};
-                    assign(pl, len, dmap.p + off);
+                    assign(pl, len, dmap.p + out_off + off);
+                    const void *from = dmap.p + out_off + off;
+                    if (mb != 8) {
+                        pb_launch_narrow_map(dmap.p + out_off + off, len, narrow.p + off * mb, (int)mb, qz.sm_count, qz.st);
+                        from = narrow.p + off * mb;
+                    }
                     cudaEvent_t ev;
                     PB_CUDA_OK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
                     PB_CUDA_OK(cudaEventRecord(ev, qz.st));
                     PB_CUDA_OK(cudaStreamWaitEvent(copy_stream.get(), ev, 0));
                     PB_CUDA_OK(cudaEventDestroy(ev));
-                    PB_CUDA_OK(cudaMemcpyAsync(palette_map + off, dmap.p + off, len * sizeof(size_t), cudaMemcpyDeviceToHost, copy_stream.get()));
+                    PB_CUDA_OK(cudaMemcpyAsync((char *)palette_map + off * mb, from, len * mb, cudaMemcpyDeviceToHost, copy_stream.get()));
                 }
                 map_sent = true;
             } else {
-                assign(planes, n, dmap.p);
+                assign(planes, out_n, dmap.p + out_off);
             }
             qz.sync();
             // patolette.c:322-323, applied whatever the colour space was (reference bug B1)
@@ -956,8 +1135,16 @@ void run_patolette(size_t width, size_t height, const double *data, const double
         }
         stage.start();
         if (map_sent) PB_CUDA_OK(cudaStreamSynchronize(copy_stream.get())); // the tail of the chunked copy
-        else if (device_io) PB_CUDA_OK(cudaMemcpyAsync(palette_map, dmap.p, n * sizeof(size_t), cudaMemcpyDeviceToDevice, qz.st));
-        else pb_copy_d2h(palette_map, dmap.p, n * sizeof(size_t), qz.st);
+        else if (out_n) {
+            const void *from = dmap.p + out_off;
+            if (mb != 8) {
+                pb_launch_narrow_map(dmap.p + out_off, out_n, narrow.p, (int)mb, qz.sm_count, qz.st);
+                from = narrow.p;
+            }
+            if (device_io) PB_CUDA_OK(cudaMemcpyAsync(palette_map, from, out_n * mb, cudaMemcpyDeviceToDevice, qz.st));
+            else pb_copy_d2h(palette_map, from, out_n * mb, qz.st);
+        }
+        qz.sync();
         set_timing(8, stage.stop());
     }
     for (size_t j = 0; j < K * 3; j++) palette[j] = -1.0; // patolette.c:328-330
@@ -1022,7 +1209,7 @@ void patolette(size_t width, size_t height, const double *data, const double *we
     if (palette_size < 1) { *exit_code = -3; return; }
     if (width * height > (size_t)40000 * 40000) { *exit_code = -4; return; }
     guarded_run(exit_code, [&] {
-        run_patolette(width, height, data, weights, palette_size, options, palette, palette_map, exit_code, false);
+        run_patolette(width, height, data, weights, palette_size, options, palette, palette_map, exit_code, IoSpec{});
     });
 }
 
@@ -1034,7 +1221,9 @@ void patolette_b200_device(size_t width, size_t height, const double *d_data, co
     if (palette_size < 1) { *exit_code = -3; return; }
     if (width * height > (size_t)40000 * 40000) { *exit_code = -4; return; }
     guarded_run(exit_code, [&] {
-        run_patolette(width, height, d_data, d_weights, palette_size, options, palette, d_palette_map, exit_code, true);
+        IoSpec io;
+        io.device_io = true;
+        run_patolette(width, height, d_data, d_weights, palette_size, options, palette, d_palette_map, exit_code, io);
     });
 }
 
@@ -1046,8 +1235,73 @@ void patolette_b200_interleaved(size_t width, size_t height, const double *rgb, 
     if (palette_size < 1) { *exit_code = -3; return; }
     if (width * height > (size_t)40000 * 40000) { *exit_code = -4; return; }
     guarded_run(exit_code, [&] {
-        run_patolette(width, height, rgb, weights, palette_size, options, palette, palette_map, exit_code, false, true);
+        IoSpec io;
+        io.in_fmt = IN_INTERLEAVED;
+        run_patolette(width, height, rgb, weights, palette_size, options, palette, palette_map, exit_code, io);
     });
+}
+
+void patolette_b200_u8(size_t width, size_t height, const uint8_t *rgb, const double *weights, size_t palette_size,
+                       const patolette__QuantizationOptions *options, double *palette, void *palette_map,
+                       int map_bytes, int device_io, int *exit_code) {
+    *exit_code = 0;
+    if (width * height == 0) { *exit_code = -2; return; }
+    if (palette_size < 1) { *exit_code = -3; return; }
+    if (width * height > (size_t)40000 * 40000) { *exit_code = -4; return; }
+    // the index type must hold palette_size - 1 (no silent truncation)
+    if (!(map_bytes == 1 || map_bytes == 2 || map_bytes == 8) || (map_bytes == 1 && palette_size > 256) ||
+        (map_bytes == 2 && palette_size > 65536)) { *exit_code = -3; return; }
+    guarded_run(exit_code, [&] {
+        IoSpec io;
+        io.in_fmt = IN_U8;
+        io.map_bytes = map_bytes;
+        io.device_io = device_io != 0;
+        run_patolette(width, height, rgb, weights, palette_size, options, palette, palette_map, exit_code, io);
+    });
+}
+
+void patolette_b200_sharded(size_t width, size_t height, const double *slice, const double *weights_slice,
+                            size_t palette_size, const patolette__QuantizationOptions *options, double *palette,
+                            size_t *map_slice, int device_io, int *exit_code) {
+    *exit_code = 0;
+    if (width * height == 0) { *exit_code = -2; return; }
+    if (palette_size < 1) { *exit_code = -3; return; }
+    if (width * height > (size_t)40000 * 40000) { *exit_code = -4; return; }
+    guarded_run(exit_code, [&] {
+        IoSpec io;
+        io.sharded = true;
+        io.device_io = device_io != 0;
+        run_patolette(width, height, slice, weights_slice, palette_size, options, palette, map_slice, exit_code, io);
+    });
+}
+
+int patolette_b200_shard_range(size_t n_pixels, int rank, int world, size_t *first, size_t *count) {
+    if (world < 1 || rank < 0 || rank >= world) return -1;
+    const size_t S = shard_stride(n_pixels, world);
+    const size_t f = std::min(n_pixels, (size_t)rank * S);
+    if (first) *first = f;
+    if (count) *count = std::min(S, n_pixels - f);
+    return 0;
+}
+
+int patolette_b200_comm_unique_id(char *id128) { return id128 ? pb_nccl_unique_id(id128) : -1; }
+
+int patolette_b200_comm_init(int rank, int world, const char *id128) {
+    std::lock_guard<std::mutex> lk(g_call_mu);
+    if (cudaSetDevice(g_device) != cudaSuccess) return -5;
+    return pb_nccl_init(rank, world, id128);
+}
+
+void patolette_b200_comm_destroy(void) {
+    std::lock_guard<std::mutex> lk(g_call_mu);
+    pb_nccl_destroy();
+}
+
+int patolette_b200_comm_info(int *rank, int *world, int *nccl_version) {
+    if (rank) *rank = pb_nccl_rank();
+    if (world) *world = pb_nccl_world();
+    if (nccl_version) *nccl_version = pb_nccl_version();
+    return pb_nccl_active() ? 1 : 0;
 }
 
 int patolette_b200_ordered_counts(unsigned long long *out2, int reset) {

@@ -9,6 +9,14 @@ def uniform_colors(width: int, height: int, seed: int) -> np.ndarray:
     return np.random.default_rng(seed).random((width * height, 3))
 
 
+def uniform_colors_slice(width: int, height: int, seed: int, first: int, count: int) -> np.ndarray:
+    """Rows [first, first + count) of uniform_colors(width, height, seed) without generating the rest: every f64
+    draw consumes one 64-bit output of PCG64, and the bit generator can jump."""
+    rng = np.random.default_rng(seed)
+    rng.bit_generator.advance(3 * first)
+    return rng.random((count, 3))
+
+
 def image_like_colors(width: int, height: int, seed: int) -> np.ndarray:
     """Smooth gradients + noise, quantised to 8 bits (/255): many duplicate colours and exact ties,
     which uniform noise never produces."""

@@ -175,3 +175,38 @@ def test_k20000_kmeans_dither_matches_oracle(cuda_lib, oracle):
     assert a[0] == b[0] == 0
     assert np.array_equal(bits(a[1]), bits(b[1])), "palette bits differ"
     assert np.array_equal(a[2], b[2]), f"{int((a[2] != b[2]).sum())} map entries differ"
+
+
+@pytest.mark.parametrize("spec", [
+    dict(w=512, h=512, K=16, color_space=2, dither=False, kmeans_niter=0),
+    dict(w=640, h=400, K=256, color_space=2, dither=True, kmeans_niter=4),
+    dict(w=333, h=222, K=300, color_space=1, dither=True, kmeans_niter=0),          # 16-bit map
+    dict(w=1600, h=1200, K=64, color_space=0, dither=False, kmeans_niter=2, weighted=True),
+])
+def test_u8_ingest_equals_f64_abi(cuda_lib, spec):
+    """N1: uint8 RGB in, / 255 on the device, narrow map out == the f64 ABI fed rgb / 255.0 (README.md:155-158)."""
+    import patolette_b200 as pb
+    from synth import saliency_like_weights
+    w, h, K = spec["w"], spec["h"], spec["K"]
+    rng = np.random.default_rng(w + h)
+    yy, xx = np.mgrid[0:h, 0:w]
+    rgb = np.stack([(xx * 255 // w), (yy * 255 // h), ((xx + yy) * 255 // (w + h))], -1).reshape(-1, 3)
+    rgb = np.clip(rgb + rng.integers(-40, 41, rgb.shape), 0, 255).astype(np.uint8)
+    weights = saliency_like_weights(w, h, 3) if spec.get("weighted") else None
+    kw = dict(dither=spec["dither"], color_space=spec["color_space"], kmeans_niter=spec["kmeans_niter"])
+    colors = rgb.astype(np.float64)
+    colors /= 255
+    ok, pal, pmap, msg = pb.quantize(w, h, colors, K, tile_size=0, weights=weights, **kw)
+    ok8, pal8, map8, msg8 = pb.quantize_u8(w, h, rgb, K, weights=weights, **kw)
+    assert ok and ok8, (msg, msg8)
+    assert map8.dtype == (np.uint8 if K <= 256 else np.uint16)
+    assert np.array_equal(bits(pal), bits(pal8)), "palette bits differ"
+    assert np.array_equal(pmap, map8.astype(np.uintp))
+    # a map type that cannot hold the indices is refused
+    from patolette_b200 import _lib
+    code = C.c_int(0)
+    opts = _lib.QuantizationOptions(False, False, 2, 0, 512 ** 2, False)
+    palbuf = np.zeros((300, 3), order="F")
+    small = np.zeros(w * h, dtype=np.uint8)
+    cuda_lib.patolette_b200_u8(w, h, rgb.ctypes.data, None, 300, C.byref(opts), palbuf.ctypes.data, small.ctypes.data, 1, 0, C.byref(code))
+    assert code.value == -3
