@@ -706,6 +706,289 @@ __global__ void __launch_bounds__(OF_THREADS, PB_OF_MINB) k_ord_fast(PbPlanes b0
     }
 }
 
+
+// ---- S1+S2+S3 fused: single-pass summaries with a decoupled look-back ----------------------------------------
+// k_ord_fast needs the approximate running sum at every block start, which cost a whole extra sweep over the
+// planes (k_ord_blocksum) plus a scan (k_ord_prefix).  Here ONE kernel reads every pixel once:
+//   * a warp takes a TILE of two consecutive blocks of a segment (a ticket per segment hands tiles out in launch
+//     order, so every predecessor of a tile is already running - the look-back below cannot deadlock);
+//   * both blocks are fetched into shared memory with asynchronous copies (cp.async, 8 bytes per lane and request,
+//     256 coalesced bytes per warp request; the second block lands while the first is being summed);
+//   * sweep A: unordered f64 sums of the tile's terms per chain -> the tile's AGGREGATE is published;
+//   * look-back (Merrill & Garland's single-pass scan): the warp reads the status of the 32 tiles before it, adds
+//     aggregates back to the nearest tile that already knows its inclusive prefix, publishes its own;
+//   * sweep B: the block-uniform summary of k_ord_fast on the data still sitting in shared memory.
+// The running sums only steer predictions (which grid a block is summarised on, whether it is offered at all):
+// their summation order - which depends on timing here - cannot change a bit of the result.
+constexpr int OT_BLOCKS = 2;              // blocks per tile
+constexpr int OT_WARPS = 2;               // tiles per CTA
+constexpr int OT_THREADS = 32 * OT_WARPS;
+struct TileStat {
+    double agg[8];  // chain sums of the tile (7 used)
+    double incl[8]; // running sums up to and including the tile
+};
+enum { TS_NONE = 0, TS_AGG = 1, TS_INCL = 2 };
+
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <bool W>
+__device__ __forceinline__ void stage_block_async(const PbPlanes &P, size_t g0, uint32_t bcnt, double *stage, int lane) {
+#pragma unroll
+    for (int q = 0; q < OB / 32; q++) {
+        const uint32_t idx = q * 32 + lane;
+        if (idx < bcnt) {
+            const int at = (int)(idx >> 4) * OS_STRIDE + (int)(idx & 15);
+            cp_async8(&stage[0 * OS_PLANE + at], &P.c[0][g0 + idx]);
+            cp_async8(&stage[1 * OS_PLANE + at], &P.c[1][g0 + idx]);
+            cp_async8(&stage[2 * OS_PLANE + at], &P.c[2][g0 + idx]);
+            if (W) cp_async8(&stage[3 * OS_PLANE + at], &P.w[g0 + idx]);
+        }
+    }
+    cp_async_commit();
+}
+
+// sweep A over one staged block: per chain the warp's unordered sum of the terms (every lane ends up with it)
+template <int KIND, bool W>
+__device__ __forceinline__ void block_sums(const double *stage, uint32_t bcnt, int lane, double m0, double m1, double m2,
+                                           double *out /* [C] */) {
+    constexpr int C = NChains<KIND>::C;
+    const int mycnt = min(OS_PER, max(0, (int)bcnt - lane * OS_PER));
+    const double *mine = stage + lane * OS_STRIDE;
+    double acc[C];
+#pragma unroll
+    for (int c = 0; c < C; c++) acc[c] = 0.0;
+#pragma unroll 4
+    for (int k = 0; k < mycnt; k++) {
+        double t[C];
+        terms_all<KIND, W>(W ? mine[3 * OS_PLANE + k] : 1.0, mine[k], mine[OS_PLANE + k], mine[2 * OS_PLANE + k], m0, m1, m2, t);
+#pragma unroll
+        for (int c = 0; c < C; c++)
+            if (chain_live<KIND, W>(c)) acc[c] += t[c];
+    }
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+        out[c] = 0.0;
+        if (!chain_live<KIND, W>(c)) continue;
+        double v = acc[c];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        out[c] = v;
+    }
+}
+
+// sweep B over one staged block: the block-uniform summary (see k_ord_fast) given the predicted start states
+template <int KIND, bool W, bool MASKED>
+__device__ __forceinline__ void fast_block(const double *stage, const PbSeg &sg, int seg, uint32_t blk, uint32_t bcnt, uint32_t nblk,
+                                           int lane, double m0, double m1, double m2, const double *pstart /* [C], registers */,
+                                           OrdRec *__restrict__ rec0, unsigned int *__restrict__ list_count,
+                                           uint2 *__restrict__ list, unsigned cmask) {
+    constexpr int C = NChains<KIND>::C;
+    constexpr unsigned FULL = 0xffffffffu;
+    PbFastGrid grid[C];
+#pragma unroll
+    for (int c = 0; c < C; c++) grid[c] = pb_fast_grid(chain_live<KIND, W>(c) ? pstart[c] : 0.0);
+    const int mycnt = min(OS_PER, max(0, (int)bcnt - lane * OS_PER));
+    const double *mine = stage + lane * OS_STRIDE;
+    double ps[C], mn[C], mx[C];
+    unsigned tie = 0;
+    bool wneg = false;
+#pragma unroll
+    for (int c = 0; c < C; c++) ps[c] = mn[c] = mx[c] = 0.0;
+#pragma unroll 2
+    for (int k = 0; k < mycnt; k++) {
+        const double w = W ? mine[3 * OS_PLANE + k] : 1.0;
+        double t[C];
+        terms_all<KIND, W>(w, mine[k], mine[OS_PLANE + k], mine[2 * OS_PLANE + k], m0, m1, m2, t);
+        if (W) wneg |= w < 0.0;
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+            if (!chain_live<KIND, W>(c)) continue;
+            bool tie_c;
+            ps[c] += pb_fast_quant(grid[c], t[c], &tie_c);
+            if (tie_c) tie |= 1u << c;
+            if (!chain_monotone<KIND>(c)) {
+                mn[c] = ps[c] < mn[c] ? ps[c] : mn[c];
+                mx[c] = ps[c] > mx[c] ? ps[c] : mx[c];
+            }
+        }
+    }
+    tie = __reduce_or_sync(FULL, tie);
+    const bool any_wneg = W && __any_sync(FULL, wneg);
+    double r_sum = 0.0, r_mn = 0.0, r_mx = 0.0, r_start = 0.0;
+    PbFastGrid r_grid = grid[0];
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+        if (!chain_live<KIND, W>(c)) continue;
+        double tot, lo_ext, hi_ext;
+        if (chain_monotone<KIND>(c)) {
+            tot = ps[c];
+#pragma unroll
+            for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(FULL, tot, o);
+            lo_ext = 0.0;
+            hi_ext = tot;
+        } else {
+            double incl = ps[c];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double v = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const double excl = incl - ps[c];
+            lo_ext = excl + mn[c];
+            hi_ext = excl + mx[c];
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                const double a = __shfl_xor_sync(FULL, lo_ext, o), b = __shfl_xor_sync(FULL, hi_ext, o);
+                lo_ext = a < lo_ext ? a : lo_ext;
+                hi_ext = b > hi_ext ? b : hi_ext;
+            }
+            tot = __shfl_sync(FULL, incl, 31);
+        }
+        if (lane == c) { r_sum = tot; r_mn = lo_ext; r_mx = hi_ext; r_grid = grid[c]; r_start = pstart[c]; }
+    }
+    bool general = false;
+    if (lane < C && chain_live<KIND, W>(lane) && (!MASKED || (cmask >> lane & 1u))) {
+        PbSpan sp;
+        const bool accept = !any_wneg && pb_fast_finish(r_grid, r_start, r_sum, r_mn, r_mx, (tie >> lane & 1u) != 0, OF_MARGIN, sp);
+        if (accept) {
+            OrdRec o;
+            o.sum = sp.sum; o.lo = sp.lo; o.hi = sp.hi; o.eref = r_grid.e; o.flag = F_OK;
+            rec0[rec_row(sg, C, lane, nblk, blk)] = o;
+        }
+        general = !accept;
+    }
+    const unsigned gm = __ballot_sync(FULL, general);
+    if (gm) {
+        unsigned int at = 0;
+        if (lane == 0) at = atomicAdd(list_count, (unsigned)__popc(gm));
+        at = __shfl_sync(FULL, at, 0);
+        if (general) list[at + __popc(gm & ((1u << lane) - 1u))] = make_uint2((unsigned)seg, blk | ((unsigned)lane << 28));
+    }
+    if (lane == 0) {
+        int live = 0;
+#pragma unroll
+        for (int c = 0; c < C; c++) live += (chain_live<KIND, W>(c) && (!MASKED || (cmask >> c & 1u))) ? 1 : 0;
+        atomicAdd(&g_ord_counts[13], (unsigned long long)(live - __popc(gm)));
+        atomicAdd(&g_ord_counts[14], (unsigned long long)__popc(gm));
+    }
+}
+
+template <int KIND, bool W, bool MASKED>
+__global__ void __launch_bounds__(OT_THREADS) k_ord_fused(PbPlanes b0, PbPlanes b1, const PbSeg *__restrict__ segs,
+                                                          const PbStats *__restrict__ stats, double *__restrict__ psum,
+                                                          OrdRec *__restrict__ rec0, unsigned int *__restrict__ list_count,
+                                                          uint2 *__restrict__ list, unsigned int *__restrict__ tickets,
+                                                          int *__restrict__ tflag, TileStat *__restrict__ tstat, unsigned cmask) {
+    constexpr int C = NChains<KIND>::C;
+    constexpr unsigned FULL = 0xffffffffu;
+    constexpr int PLANES = W ? 4 : 3;
+    extern __shared__ __align__(16) double ot_smem[]; // [OT_WARPS][OT_BLOCKS][PLANES * OS_PLANE]
+    const int seg = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const PbSeg sg = segs[seg];
+    const uint32_t nblk = (sg.n + OB - 1) / OB, ntile = (nblk + OT_BLOCKS - 1) / OT_BLOCKS;
+    if ((uint32_t)blockIdx.x * OT_WARPS >= ntile) return; // no tile left for this CTA's first warp: none for any
+    // the ticket: tiles of a segment are handed out in the order warps start running
+    unsigned int tile = 0;
+    if (lane == 0) tile = atomicAdd(&tickets[seg], 1u);
+    tile = __shfl_sync(FULL, tile, 0);
+    if (tile >= ntile) return;
+    const PbPlanes &P = sg.buf ? b1 : b0;
+    double *stage0 = ot_smem + (size_t)(warp * OT_BLOCKS) * PLANES * OS_PLANE, *stage1 = stage0 + PLANES * OS_PLANE;
+    const uint32_t blk0 = tile * OT_BLOCKS, blk1 = blk0 + 1;
+    const uint32_t cnt0 = min((uint32_t)OB, sg.n - blk0 * OB);
+    const uint32_t cnt1 = blk1 < nblk ? min((uint32_t)OB, sg.n - blk1 * OB) : 0u;
+    stage_block_async<W>(P, (size_t)sg.lo + (size_t)blk0 * OB, cnt0, stage0, lane);
+    stage_block_async<W>(P, (size_t)sg.lo + (size_t)blk1 * OB, cnt1, stage1, lane); // (an empty group when there is no second block)
+    double m0 = 0, m1 = 0, m2 = 0;
+    if (KIND == KIND_CENTERED) { m0 = stats[seg].mean[0]; m1 = stats[seg].mean[1]; m2 = stats[seg].mean[2]; }
+    // ---- sweep A -----------------------------------------------------------------------------------------
+    double s0[C], s1[C];
+    cp_async_wait<1>();
+    __syncwarp();
+    block_sums<KIND, W>(stage0, cnt0, lane, m0, m1, m2, s0);
+    cp_async_wait<0>();
+    __syncwarp();
+    block_sums<KIND, W>(stage1, cnt1, lane, m0, m1, m2, s1);
+    // ---- publish the aggregate, look back, publish the inclusive prefix ---------------------------------------
+    const size_t trow = (size_t)sg.bbase + tile; // one row per tile; tiles <= blocks, so the block table's packing serves
+    double mine_agg = 0.0; // lane c: chain c
+#pragma unroll
+    for (int c = 0; c < C; c++) if (lane == c) mine_agg = s0[c] + s1[c];
+    if (lane < C) tstat[trow].agg[lane] = mine_agg;
+    __threadfence();
+    __syncwarp();
+    if (lane == 0 && tile + 1 < ntile) atomicExch(&tflag[trow], TS_AGG); // (the last tile has no reader)
+    double ex[C]; // running sums before this tile (every lane)
+#pragma unroll
+    for (int c = 0; c < C; c++) ex[c] = 0.0;
+    {
+        long long look = (long long)tile - 1; // nearest tile not yet accounted for
+        while (look >= 0) {
+            const long long t = look - lane; // lane 0: the nearest predecessor
+            int f = TS_INCL;                 // tiles before the segment: an inclusive prefix of zero
+            if (t >= 0) {
+                const volatile int *fp = &tflag[(size_t)sg.bbase + (size_t)t];
+                f = *fp;
+            }
+            const unsigned has_incl = __ballot_sync(FULL, f == TS_INCL);
+            const int p = has_incl ? __ffs(has_incl) - 1 : 32;                  // nearest tile with an inclusive prefix
+            const unsigned need = p >= 32 ? FULL : ((2u << p) - 1u);           // lanes 0..p
+            const unsigned missing = __ballot_sync(FULL, f == TS_NONE) & need;
+            if (missing) { __nanosleep(40); continue; }                         // a predecessor has not published yet
+            __threadfence();
+            // lanes < p add their tile's aggregate, lane p its inclusive prefix
+            double v[C];
+#pragma unroll
+            for (int c = 0; c < C; c++) v[c] = 0.0;
+            if (t >= 0 && lane <= p) {
+                const volatile double *src = lane == p ? tstat[(size_t)sg.bbase + (size_t)t].incl : tstat[(size_t)sg.bbase + (size_t)t].agg;
+#pragma unroll
+                for (int c = 0; c < C; c++)
+                    if (chain_live<KIND, W>(c)) v[c] = src[c];
+            }
+#pragma unroll
+            for (int c = 0; c < C; c++) {
+                if (!chain_live<KIND, W>(c)) continue;
+                double x = v[c];
+#pragma unroll
+                for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
+                ex[c] += x;
+            }
+            if (p < 32) break;
+            look -= 32;
+        }
+    }
+    {
+        double mine_incl = 0.0;
+#pragma unroll
+        for (int c = 0; c < C; c++) if (lane == c) mine_incl = ex[c] + (s0[c] + s1[c]);
+        if (lane < C) tstat[trow].incl[lane] = mine_incl;
+        __threadfence();
+        __syncwarp();
+        if (lane == 0 && tile + 1 < ntile) atomicExch(&tflag[trow], TS_INCL);
+    }
+    // the predicted start states of both blocks (the general pass reads them from the table)
+    double ps1[C];
+#pragma unroll
+    for (int c = 0; c < C; c++) ps1[c] = ex[c] + s0[c];
+    {
+        double a = 0.0, b = 0.0;
+#pragma unroll
+        for (int c = 0; c < C; c++) if (lane == c) { a = ex[c]; b = ps1[c]; }
+        if (lane < C) {
+            psum[((size_t)sg.bbase + blk0) * C + lane] = a;
+            if (cnt1) psum[((size_t)sg.bbase + blk1) * C + lane] = b;
+        }
+    }
+    // ---- sweep B --------------------------------------------------------------------------------------------
+    fast_block<KIND, W, MASKED>(stage0, sg, seg, blk0, cnt0, nblk, lane, m0, m1, m2, ex, rec0, list_count, list, cmask);
+    if (cnt1) fast_block<KIND, W, MASKED>(stage1, sg, seg, blk1, cnt1, nblk, lane, m0, m1, m2, ps1, rec0, list_count, list, cmask);
+}
+
 // ---- S3b: (block, chain) pairs with a parity-dependent step: both start parities ---------------------
 template <int KIND, bool W>
 __global__ void __launch_bounds__(OS_THREADS) k_ord_summary2(PbPlanes b0, PbPlanes b1, const PbSeg *__restrict__ segs,
@@ -1075,9 +1358,14 @@ struct Scratch {
     unsigned int *list_count; // [0] work list of summary2, [1] dump slots
     OrdRec *grec, *rrec, *rrec1;
     Dump dump;
+    unsigned int *tickets; // fused pass: next tile of every segment
+    int *tflag;            // ... status of every tile
+    TileStat *tstat;       // ... its aggregate / inclusive prefix
 };
+constexpr size_t OT_MAX_SEGS = 256;
 size_t group_rows(size_t total_blocks) { return total_blocks * 7 / 32 + 4096; } // + nseg * (C + 1), nseg <= 2 * 64
 long long g_dump_cap_override = -1; // debug/test knob (patolette_b200_set_option "dump_cap")
+bool g_fused_pass = true;           // "fused_pass": single-pass summaries with a decoupled look-back (k_ord_fused); 0 = blocksum + prefix + k_ord_fast
 bool g_fast_summary = true;         // "fast_summary": block-uniform summaries (k_ord_fast) + general work list; 0 = per-element summaries for every block
 size_t dump_slots(size_t total_blocks) { return total_blocks / 4 + 1024; }
 unsigned int dump_cap(size_t total_blocks) {
@@ -1095,9 +1383,12 @@ Scratch carve(void *d_scratch, size_t total_blocks) {
     s.rrec = (OrdRec *)p; p += total_blocks * 7 * sizeof(OrdRec);
     s.rrec1 = (OrdRec *)p; p += total_blocks * 7 * sizeof(OrdRec);
     s.list = (uint2 *)p; p += total_blocks * 7 * sizeof(uint2);
-    s.list_count = (unsigned int *)p;
+    s.list_count = (unsigned int *)p; p += 64;
     s.dump.count = s.list_count + 1;
     s.dump.cap = dump_cap(total_blocks);
+    s.tstat = (TileStat *)p; p += total_blocks * sizeof(TileStat);
+    s.tflag = (int *)p; p += total_blocks * sizeof(int);
+    s.tickets = (unsigned int *)p; // [OT_MAX_SEGS], directly behind the flags: one memset clears both
     return s;
 }
 
@@ -1124,6 +1415,21 @@ void launch_pass(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t
     if (speculative) {
         sc = carve(d_scratch, total_blocks);
         dim3 grid(blk_cap, nseg), sgrid((blk_cap + OS_WARPS - 1) / OS_WARPS, nseg);
+        const bool fused = g_fast_summary && g_fused_pass && (size_t)nseg <= OT_MAX_SEGS;
+        if (fused) {
+            PB_CUDA_OK(cudaMemsetAsync(sc.list_count, 0, 2 * sizeof(unsigned int), st));
+            PB_CUDA_OK(cudaMemsetAsync(sc.tflag, 0, (size_t)total_blocks * sizeof(int) + OT_MAX_SEGS * sizeof(unsigned int), st));
+            const uint32_t tile_cap = (blk_cap + OT_BLOCKS - 1) / OT_BLOCKS;
+            dim3 tgrid((tile_cap + OT_WARPS - 1) / OT_WARPS, nseg);
+            const size_t smem = (size_t)OT_WARPS * OT_BLOCKS * (W ? 4 : 3) * OS_PLANE * sizeof(double);
+            if (cmask == ~0u) PB_CUDA_OK(cudaFuncSetAttribute(k_ord_fused<KIND, W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            else PB_CUDA_OK(cudaFuncSetAttribute(k_ord_fused<KIND, W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            PbProfScope p(KIND == KIND_MEAN ? "k_ord_fused_mean" : "k_ord_fused_centered", st);
+            if (cmask == ~0u)
+                k_ord_fused<KIND, W, false><<<tgrid, OT_THREADS, smem, st>>>(bufs[0], bufs[1], d_segs, d_stats, sc.psum, sc.rec0, sc.list_count, sc.list, sc.tickets, sc.tflag, sc.tstat, cmask);
+            else
+                k_ord_fused<KIND, W, true><<<tgrid, OT_THREADS, smem, st>>>(bufs[0], bufs[1], d_segs, d_stats, sc.psum, sc.rec0, sc.list_count, sc.list, sc.tickets, sc.tflag, sc.tstat, cmask);
+        } else {
         { PbProfScope p(KIND == KIND_MEAN ? "k_ord_blocksum_mean" : "k_ord_blocksum_centered", st, false);
           k_ord_blocksum<KIND, W><<<grid, OB_THREADS, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, sc.psum, cmask); }
         { PbProfScope p("k_ord_prefix", st, false);
@@ -1142,6 +1448,7 @@ void launch_pass(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t
               k_ord_summary<KIND, W, false><<<sgrid, OS_THREADS, summary_pad_smem(KIND), st>>>(bufs[0], bufs[1], d_segs, d_stats, sc.psum, sc.rec0, sc.list_count, sc.list, sc.dump, cmask);
           else
               k_ord_summary<KIND, W, true><<<sgrid, OS_THREADS, summary_pad_smem(KIND), st>>>(bufs[0], bufs[1], d_segs, d_stats, sc.psum, sc.rec0, sc.list_count, sc.list, sc.dump, cmask); }
+        }
         { PbProfScope p("k_ord_summary2", st, false);
           k_ord_summary2<KIND, W><<<148 * 16, OS_THREADS, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, sc.psum, sc.rec0, sc.rec1, sc.list_count, sc.list, sc.dump); }
         { PbProfScope p("k_ord_group", st, false);
@@ -1172,12 +1479,14 @@ void pb_ordered_chain_debug(unsigned long long out[35], bool reset) {
 
 void pb_ordered_set_dump_cap(long long slots) { g_dump_cap_override = slots; }
 void pb_ordered_set_fast(bool on) { g_fast_summary = on; }
+void pb_ordered_set_fused(bool on) { g_fused_pass = on; }
 
 uint32_t pb_ordered_blocks(uint32_t n) { return (n + OB - 1) / OB; }
 
 size_t pb_ordered_scratch_bytes(size_t total_blocks) {
     return dump_slots(total_blocks) * OB * sizeof(double) + group_rows(total_blocks) * sizeof(OrdRec) +
-           total_blocks * 7 * (sizeof(double) + 4 * sizeof(OrdRec) + sizeof(uint2)) + 256;
+           total_blocks * 7 * (sizeof(double) + 4 * sizeof(OrdRec) + sizeof(uint2)) + 256 +
+           total_blocks * (sizeof(TileStat) + sizeof(int)) + OT_MAX_SEGS * sizeof(unsigned int);
 }
 
 void pb_launch_pass_mean(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t max_n,
