@@ -497,7 +497,7 @@ def measure_ours(args):
                     "covariance (ordered mean + centred passes: k_ord_*)": stage_roofline(["k_ord_"], pass_bytes),
                     "projection + bucket sort + partition (k_dots_minmax, k_buckets, k_tile_*, k_scatter)":
                         stage_roofline(["k_dots_minmax", "k_buckets", "k_tile_", "k_scatter", "k_class_start"],
-                              sum(v["bytes"] for k, v in prof.items() if k in ("k_dots_minmax", "k_buckets", "k_scatter"))),
+                              sum(v["bytes"] for k, v in prof.items() if k in ("k_dots_minmax", "k_buckets") or k.startswith("k_scatter"))),
                     "per-bucket ordered sums (k_bucket_chains_*)": stage_roofline(["k_bucket_chains"], sum(v["bytes"] for k, v in prof.items() if k.startswith("k_bucket_chains"))),
                     "colour transforms (k_color)": stage_roofline(["k_color"], sum(v["bytes"] for k, v in prof.items() if k == "k_color")),
                     "dither (hilbert rank, permute, k_riemersma_*, unpermute)": stage_roofline(["k_hilbert", "k_permute", "k_riemersma", "k_unpermute"], (2 * (24 + 8) + 32.0) * n),

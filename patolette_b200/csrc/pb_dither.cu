@@ -23,6 +23,7 @@
 
 #include "pb_common.cuh"
 #include "pb_kernels.h"
+#include "pb_nccl.h"
 #include "pb_nngrid.cuh"
 #include "pb_prof.h"
 #include "pb_pipeline.h"
@@ -86,9 +87,9 @@ __global__ void k_permute(const double *__restrict__ c0, const double *__restric
     }
 }
 
-__global__ void k_unpermute(const uint32_t *__restrict__ rank, const uint32_t *__restrict__ hidx, size_t n,
+__global__ void k_unpermute(const uint32_t *__restrict__ rank, const uint32_t *__restrict__ hidx, size_t first, size_t n,
                             unsigned long long *__restrict__ map) {
-    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (size_t)gridDim.x * blockDim.x)
+    for (size_t p = first + (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < first + n; p += (size_t)gridDim.x * blockDim.x)
         map[p] = hidx[rank[p]];
 }
 
@@ -318,7 +319,8 @@ __global__ void __launch_bounds__(DS_WARPS * 32) k_riemersma_spec4(const double 
                                                                   size_t warm, const double *__restrict__ pal,
                                                                   const double *__restrict__ palw, int K,
                                                                   uint32_t *__restrict__ hidx, uint32_t *__restrict__ overlap,
-                                                                  const void *__restrict__ nngrid, bool pal_in_smem) {
+                                                                  const void *__restrict__ nngrid, bool pal_in_smem,
+                                                                  size_t g_first, size_t g_end) {
     extern __shared__ double s_mem[];
     const double *s_pal = pal_in_smem ? s_mem : pal, *s_palw = pal_in_smem ? s_mem + (size_t)K * 3 : palw;
     __shared__ double s_geom[6];
@@ -344,9 +346,9 @@ __global__ void __launch_bounds__(DS_WARPS * 32) k_riemersma_spec4(const double 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gl = lane & (DS_GROUP - 1), grp = lane / DS_GROUP;
     const int ch = gl < 3 ? gl : 0;
     const double cw = ch == 0 ? 0.51254268114958 : (ch == 1 ? 0.8234075540095561 : 0.2435159132377184);
-    const size_t g = ((size_t)blockIdx.x * DS_WARPS + warp) * DS_CHAINS + grp;
+    const size_t g = g_first + ((size_t)blockIdx.x * DS_WARPS + warp) * DS_CHAINS + grp; // (an image-sharded run: this rank's chains)
     const size_t a = g * seg;                       // first pixel this chain owns
-    const bool live = a < n;
+    const bool live = g < g_end && a < n;
     const size_t end = live ? min(n, a + seg) : 0;
     size_t pos = live ? (a > warm ? a - warm : 0) : 0; // a - pos is a multiple of 16 (seg and warm are multiples of 128)
     double(*px)[16] = s_px[warp][grp];
@@ -512,8 +514,13 @@ void pb_dither_set_subwarp(bool on) { g_dither_subwarp = on; }
 
 void pb_dither_riemersma(const double *const planes[3], size_t width, size_t height,
                          const std::vector<double> &pal_rm, unsigned long long *d_map, int sm_count,
-                         cudaStream_t st, long *launches) {
+                         cudaStream_t st, long *launches, const PbDitherShard *shard) {
     const size_t n = width * height;
+    // image-sharded runs: the speculative chains are dealt out over the ranks (contiguous ranges of segments), the
+    // choices and warm-up records all-gathered over NVLink; the boundary check / repair is replicated (it needs
+    // every rank's choices and is sequential anyway) and every rank un-permutes the pixels it has to return
+    const int world = shard && shard->world > 1 && g_dither_subwarp ? shard->world : 1, srank = world > 1 ? shard->rank : 0;
+    const size_t out_first = shard ? shard->out_first : 0, out_count = shard ? shard->out_count : n;
     const int K = (int)(pal_rm.size() / 3);
     // riemersma.c:124-144
     int level = 0;
@@ -560,7 +567,12 @@ void pb_dither_riemersma(const double *const planes[3], size_t width, size_t hei
             g_rank_cache.device = dev; g_rank_cache.width = width; g_rank_cache.height = height;
         }
         d_rank = g_rank_cache.rank;
-        d_hidx = (uint32_t *)pb_pool_alloc((n + 64) * sizeof(uint32_t));
+        size_t seg = ((n / 2048 + 127) / 128) * 128;
+        seg = seg < 1024 ? 1024 : (seg > 8192 ? 8192 : seg);
+        const size_t warm = seg < 2048 ? seg : 2048;
+        const size_t nseg = (n + seg - 1) / seg;
+        const size_t per_rank = (nseg + (size_t)world - 1) / (size_t)world; // chains per rank
+        d_hidx = (uint32_t *)pb_pool_alloc((per_rank * (size_t)world * seg + 64) * sizeof(uint32_t));
         PB_CUDA_OK(cudaMemcpyAsync(d_pal, pal_rm.data(), pal_rm.size() * sizeof(double), cudaMemcpyHostToDevice, st));
         PB_CUDA_OK(cudaMemcpyAsync(d_palw, palw.data(), palw.size() * sizeof(double), cudaMemcpyHostToDevice, st));
         PB_CUDA_OK(cudaMemcpyAsync(d_qw, qw, sizeof qw, cudaMemcpyHostToDevice, st));
@@ -578,11 +590,7 @@ void pb_dither_riemersma(const double *const planes[3], size_t width, size_t hei
         // segment / warm-up lengths: enough segments to occupy the chip, warm-up long enough that
         // almost every segment locks on before it starts (cold starts converge in ~150 pixels on
         // average, ~1600 worst observed)
-        size_t seg = ((n / 2048 + 127) / 128) * 128;
-        seg = seg < 1024 ? 1024 : (seg > 8192 ? 8192 : seg);
-        const size_t warm = seg < 2048 ? seg : 2048;
-        const size_t nseg = (n + seg - 1) / seg;
-        d_overlap = (uint32_t *)pb_pool_alloc((nseg + 1) * 16 * sizeof(uint32_t));
+        d_overlap = (uint32_t *)pb_pool_alloc((per_rank * (size_t)world + 1) * 16 * sizeof(uint32_t));
         d_stats = (unsigned long long *)pb_pool_alloc(2 * sizeof(unsigned long long));
         const bool pal_in_smem = (size_t)K * 6 * sizeof(double) <= PB_SMEM_PALETTE_LIMIT;
         const size_t smem = pal_in_smem ? (size_t)K * 6 * sizeof(double) : 0;
@@ -605,9 +613,17 @@ void pb_dither_riemersma(const double *const planes[3], size_t width, size_t hei
             if (smem > 32 * 1024)
                 PB_CUDA_OK(cudaFuncSetAttribute(k_riemersma_spec4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             const size_t per_cta = (size_t)DS_WARPS * DS_CHAINS;
-            PbProfScope _prof("k_riemersma_spec", st);
-            k_riemersma_spec4<<<(unsigned)((nseg + per_cta - 1) / per_cta), DS_WARPS * 32, smem, st>>>(
-                d_h[0], d_h[1], d_h[2], n, seg, warm, d_pal, d_palw, K, d_hidx, d_overlap, d_grid, pal_in_smem);
+            const size_t g_first = (size_t)srank * per_rank, g_end = g_first + per_rank < nseg ? g_first + per_rank : nseg;
+            const size_t mine = g_end > g_first ? g_end - g_first : 0;
+            if (mine) {
+                PbProfScope _prof("k_riemersma_spec", st);
+                k_riemersma_spec4<<<(unsigned)((mine + per_cta - 1) / per_cta), DS_WARPS * 32, smem, st>>>(
+                    d_h[0], d_h[1], d_h[2], n, seg, warm, d_pal, d_palw, K, d_hidx, d_overlap, d_grid, pal_in_smem, g_first, g_end);
+            }
+            if (world > 1) { // every rank's choices and warm-up records, in place
+                pb_nccl_allgather(d_hidx + g_first * seg, d_hidx, per_rank * seg * sizeof(uint32_t), st);
+                pb_nccl_allgather(d_overlap + g_first * 16, d_overlap, per_rank * 16 * sizeof(uint32_t), st);
+            }
         } else
         { PbProfScope _prof("k_riemersma_spec", st);
         k_riemersma_spec<<<(unsigned)((nseg + DT_WARPS - 1) / DT_WARPS), DT_WARPS * 32, smem, st>>>(
@@ -621,9 +637,10 @@ void pb_dither_riemersma(const double *const planes[3], size_t width, size_t hei
         k_riemersma_repair<<<1, 32, smem, st>>>(d_h[0], d_h[1], d_h[2], n, seg, d_pal, d_palw, K, d_qw, d_hidx,
                                                 d_overlap, d_stats, d_grid, pal_in_smem, d_flags);
         }
-        pb_prof_next_bytes(16.0 * (double)n);
+        pb_prof_next_bytes(16.0 * (double)out_count);
+        if (out_count)
         { PbProfScope _prof("k_unpermute", st);
-        k_unpermute<<<grid, 256, 0, st>>>(d_rank, d_hidx, n, d_map);
+        k_unpermute<<<grid, 256, 0, st>>>(d_rank, d_hidx, out_first, out_count, d_map);
         }
         PB_CUDA_OK(cudaGetLastError());
         PB_CUDA_OK(cudaStreamSynchronize(st));

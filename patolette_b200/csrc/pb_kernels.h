@@ -42,6 +42,8 @@ void pb_ordered_set_dump_cap(long long slots);
 void pb_ordered_set_fast(bool on);
 // test knob: single-pass fused summaries (default) or the separate blocksum + prefix + summary kernels
 void pb_ordered_set_fused(bool on);
+// test knob: centred-pass block sums derived from the mean pass's raw moments (default) or summed from the pixels
+void pb_ordered_set_raw_moments(bool on);
 // cmask: bit c set = chain c is summed by this call (chain-sharded multi-GPU runs split the chains over the
 // ranks; the other fields of PbStats are left as they are).  raw_mean: leave sum(c_j * w) unscaled in mean[].
 void pb_launch_pass_mean(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t max_n,

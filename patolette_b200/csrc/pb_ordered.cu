@@ -164,6 +164,81 @@ __global__ void __launch_bounds__(OB_THREADS) k_ord_blocksum(PbPlanes b0, PbPlan
     }
 }
 
+// ---- S1': one warp per block, every load of the block in flight at once; the MEAN pass also leaves the block's
+// raw second moments behind, from which the centred pass derives ITS block sums without reading a pixel:
+//     sum w (c_j - m_j)(c_k - m_k) = Q_jk - m_j S_k - m_k S_j + m_j m_k S_w        (Q_jk = sum w c_j c_k)
+// The cancellation costs digits (|c|^2 / sigma^2 of them), which is fine: these sums only steer predictions.
+constexpr int OBW_WARPS = 4;
+constexpr int RAW_N = 10; // S_w, S_0, S_1, S_2, Q_00, Q_10, Q_11, Q_20, Q_21, Q_22
+template <bool W>
+__global__ void __launch_bounds__(32 * OBW_WARPS) k_ord_blocksum_raw(PbPlanes b0, PbPlanes b1, const PbSeg *__restrict__ segs,
+                                                                     double *__restrict__ psum /* [block][4] */,
+                                                                     double *__restrict__ raw /* [block][RAW_N] */) {
+    const int seg = blockIdx.y, lane = threadIdx.x & 31;
+    const PbSeg sg = segs[seg];
+    const uint32_t blk = blockIdx.x * OBW_WARPS + (threadIdx.x >> 5);
+    if ((size_t)blk * OB >= sg.n) return; // warp-uniform
+    const PbPlanes &P = sg.buf ? b1 : b0;
+    const uint32_t bcnt = min((uint32_t)OB, sg.n - blk * OB);
+    const size_t g0 = (size_t)sg.lo + (size_t)blk * OB;
+    double a[RAW_N];
+#pragma unroll
+    for (int i = 0; i < RAW_N; i++) a[i] = 0.0;
+    auto add = [&](double w, double c0, double c1, double c2) {
+        const double w0 = W ? c0 * w : c0, w1 = W ? c1 * w : c1, w2 = W ? c2 * w : c2;
+        a[0] += W ? w : 1.0; a[1] += w0; a[2] += w1; a[3] += w2;
+        a[4] = __fma_rn(w0, c0, a[4]); a[5] = __fma_rn(w1, c0, a[5]); a[6] = __fma_rn(w1, c1, a[6]);
+        a[7] = __fma_rn(w2, c0, a[7]); a[8] = __fma_rn(w2, c1, a[8]); a[9] = __fma_rn(w2, c2, a[9]);
+    };
+    if (bcnt == OB) {
+#pragma unroll
+        for (int h = 0; h < 2; h++) { // two rounds of 8 rows: 24 - 32 loads in flight per lane
+            double v0[8], v1[8], v2[8], vw[W ? 8 : 1];
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const size_t g = g0 + (h * 8 + q) * 32 + lane;
+                v0[q] = P.c[0][g]; v1[q] = P.c[1][g]; v2[q] = P.c[2][g];
+                if (W) vw[q] = P.w[g];
+            }
+#pragma unroll
+            for (int q = 0; q < 8; q++) add(W ? vw[q] : 1.0, v0[q], v1[q], v2[q]);
+        }
+    } else {
+        for (uint32_t i = lane; i < bcnt; i += 32) add(W ? P.w[g0 + i] : 1.0, P.c[0][g0 + i], P.c[1][g0 + i], P.c[2][g0 + i]);
+    }
+#pragma unroll
+    for (int i = 0; i < RAW_N; i++)
+#pragma unroll
+        for (int o = 16; o; o >>= 1) a[i] += __shfl_xor_sync(0xffffffffu, a[i], o);
+    const size_t row = (size_t)sg.bbase + blk;
+    double mine = 0.0;
+#pragma unroll
+    for (int i = 0; i < RAW_N; i++) if (lane == i) mine = a[i];
+    if (lane < RAW_N) raw[row * RAW_N + lane] = mine;
+    if (lane < 4) psum[row * 4 + lane] = mine; // chains of the mean pass: w, c0 w, c1 w, c2 w
+}
+
+// block sums of the centred pass from the raw moments and the (now exact) mean
+__global__ void __launch_bounds__(256) k_ord_derive_centered(const PbSeg *__restrict__ segs, const PbStats *__restrict__ stats,
+                                                             const double *__restrict__ raw, double *__restrict__ psum /* [block][7] */) {
+    const int seg = blockIdx.y;
+    const PbSeg sg = segs[seg];
+    const uint32_t nblk = (sg.n + OB - 1) / OB;
+    const double m0 = stats[seg].mean[0], m1 = stats[seg].mean[1], m2 = stats[seg].mean[2];
+    for (uint32_t blk = blockIdx.x * blockDim.x + threadIdx.x; blk < nblk; blk += gridDim.x * blockDim.x) {
+        const double *r = raw + ((size_t)sg.bbase + blk) * RAW_N;
+        const double Sw = r[0], S0 = r[1], S1 = r[2], S2 = r[3];
+        const double t00 = r[4] - 2.0 * m0 * S0 + m0 * m0 * Sw;
+        const double t10 = r[5] - m1 * S0 - m0 * S1 + m1 * m0 * Sw;
+        const double t11 = r[6] - 2.0 * m1 * S1 + m1 * m1 * Sw;
+        const double t20 = r[7] - m2 * S0 - m0 * S2 + m2 * m0 * Sw;
+        const double t21 = r[8] - m2 * S1 - m1 * S2 + m2 * m1 * Sw;
+        const double t22 = r[9] - 2.0 * m2 * S2 + m2 * m2 * Sw;
+        double *o = psum + ((size_t)sg.bbase + blk) * 7;
+        o[0] = t00; o[1] = t10; o[2] = t11; o[3] = t20; o[4] = t21; o[5] = t22; o[6] = (t00 + t11) + t22;
+    }
+}
+
 // ---- S2: approximate exclusive prefix per chain (in place over the block sums) ------------------
 // One CTA per (chain, segment): every thread sums a contiguous run of block sums (independent loads, several
 // in flight), the CTA scans the partials, the threads write the exclusive prefixes of their run.  (The first
@@ -621,12 +696,11 @@ __global__ void __launch_bounds__(OF_THREADS, PB_OF_MINB) k_ord_fast(PbPlanes b0
     const int mycnt = min(OS_PER, max(0, (int)bcnt - lane * OS_PER));
     const double *mine = stage + lane * OS_STRIDE;
     double ps[C], mn[C], mx[C];
-    unsigned tie = 0;
+    bool tie_any = false; // a tie in ANY chain sends all chains of the block to the general pass (ties are rare)
     bool wneg = false;
 #pragma unroll
     for (int c = 0; c < C; c++) ps[c] = mn[c] = mx[c] = 0.0;
-#pragma unroll 2
-    for (int k = 0; k < mycnt; k++) {
+    auto element = [&](int k) {
         const double w = W ? mine[3 * OS_PLANE + k] : 1.0;
         double t[C];
         terms_all<KIND, W>(w, mine[k], mine[OS_PLANE + k], mine[2 * OS_PLANE + k], m0, m1, m2, t);
@@ -636,14 +710,20 @@ __global__ void __launch_bounds__(OF_THREADS, PB_OF_MINB) k_ord_fast(PbPlanes b0
             if (!chain_live<KIND, W>(c)) continue;
             bool tie_c;
             ps[c] += pb_fast_quant(grid[c], t[c], &tie_c); // exact while below 2^53 u (checked at the end)
-            if (tie_c) tie |= 1u << c;
+            tie_any |= tie_c;
             if (!chain_monotone<KIND>(c)) {
                 mn[c] = ps[c] < mn[c] ? ps[c] : mn[c];
                 mx[c] = ps[c] > mx[c] ? ps[c] : mx[c];
             }
         }
+    };
+    if (mycnt == OS_PER) { // (every lane of a whole block) straight-line code: constant shared-memory offsets
+#pragma unroll
+        for (int k = 0; k < OS_PER; k++) element(k);
+    } else {
+        for (int k = 0; k < mycnt; k++) element(k);
     }
-    tie = __reduce_or_sync(FULL, tie);
+    const unsigned tie = __any_sync(FULL, tie_any) ? ~0u : 0u;
     const bool any_wneg = W && __any_sync(FULL, wneg);
     // ---- compose the lanes in element order; lane c finishes chain c ----------------------------------------
     double r_sum = 0.0, r_mn = 0.0, r_mx = 0.0; // of chain `lane`
@@ -1358,6 +1438,7 @@ struct Scratch {
     unsigned int *list_count; // [0] work list of summary2, [1] dump slots
     OrdRec *grec, *rrec, *rrec1;
     Dump dump;
+    double *raw;           // raw second moments of every block (written by the mean pass, read by the centred pass)
     unsigned int *tickets; // fused pass: next tile of every segment
     int *tflag;            // ... status of every tile
     TileStat *tstat;       // ... its aggregate / inclusive prefix
@@ -1365,7 +1446,31 @@ struct Scratch {
 constexpr size_t OT_MAX_SEGS = 256;
 size_t group_rows(size_t total_blocks) { return total_blocks * 7 / 32 + 4096; } // + nseg * (C + 1), nseg <= 2 * 64
 long long g_dump_cap_override = -1; // debug/test knob (patolette_b200_set_option "dump_cap")
-bool g_fused_pass = true;           // "fused_pass": single-pass summaries with a decoupled look-back (k_ord_fused); 0 = blocksum + prefix + k_ord_fast
+// "fused_pass": single-pass summaries with a decoupled look-back (k_ord_fused) instead of blocksum + prefix + k_ord_fast.
+// Measured SLOWER at 16384^2 (107 vs 85 ms for the two sweeps): the summaries are bound by instruction issue, not by HBM,
+// and the fused kernel's 52 KB of staging per CTA halves the resident warps.  Kept as a tested route, off by default.
+bool g_fused_pass = false;
+bool g_raw_moments = true;          // "raw_moments": the centred pass derives its block sums from the mean pass's raw moments
+struct RawTag {
+    const void *segs = nullptr;
+    int nseg = 0;
+    uint32_t max_n = 0, total_blocks = 0;
+    bool weighted = false;
+    bool operator==(const RawTag &o) const {
+        return segs && segs == o.segs && nseg == o.nseg && max_n == o.max_n && total_blocks == o.total_blocks && weighted == o.weighted;
+    }
+};
+RawTag &raw_tag(const void *scratch) { // which mean pass last filled the raw table of this scratch (two scratches per image)
+    static const void *key[4] = {nullptr, nullptr, nullptr, nullptr};
+    static RawTag tags[4];
+    for (int i = 0; i < 4; i++)
+        if (key[i] == scratch) return tags[i];
+    static int next = 0;
+    const int i = next++ & 3;
+    key[i] = scratch;
+    tags[i] = RawTag{};
+    return tags[i];
+}
 bool g_fast_summary = true;         // "fast_summary": block-uniform summaries (k_ord_fast) + general work list; 0 = per-element summaries for every block
 size_t dump_slots(size_t total_blocks) { return total_blocks / 4 + 1024; }
 unsigned int dump_cap(size_t total_blocks) {
@@ -1386,6 +1491,7 @@ Scratch carve(void *d_scratch, size_t total_blocks) {
     s.list_count = (unsigned int *)p; p += 64;
     s.dump.count = s.list_count + 1;
     s.dump.cap = dump_cap(total_blocks);
+    s.raw = (double *)p; p += total_blocks * RAW_N * sizeof(double);
     s.tstat = (TileStat *)p; p += total_blocks * sizeof(TileStat);
     s.tflag = (int *)p; p += total_blocks * sizeof(int);
     s.tickets = (unsigned int *)p; // [OT_MAX_SEGS], directly behind the flags: one memset clears both
@@ -1430,8 +1536,24 @@ void launch_pass(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t
             else
                 k_ord_fused<KIND, W, true><<<tgrid, OT_THREADS, smem, st>>>(bufs[0], bufs[1], d_segs, d_stats, sc.psum, sc.rec0, sc.list_count, sc.list, sc.tickets, sc.tflag, sc.tstat, cmask);
         } else {
-        { PbProfScope p(KIND == KIND_MEAN ? "k_ord_blocksum_mean" : "k_ord_blocksum_centered", st, false);
-          k_ord_blocksum<KIND, W><<<grid, OB_THREADS, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, sc.psum, cmask); }
+        // the mean pass leaves the raw second moments of every block in the scratch; the centred pass over the SAME
+        // segments and scratch (the pipeline always runs them back to back) derives its block sums from them
+        RawTag &tag = raw_tag(d_scratch);
+        const RawTag now{d_segs, nseg, max_n, total_blocks, W};
+        if (KIND == KIND_MEAN && g_raw_moments) {
+            PbProfScope p("k_ord_blocksum_mean", st, false);
+            k_ord_blocksum_raw<W><<<dim3((blk_cap + OBW_WARPS - 1) / OBW_WARPS, nseg), 32 * OBW_WARPS, 0, st>>>(bufs[0], bufs[1], d_segs, sc.psum, sc.raw);
+            tag = now;
+        } else if (KIND == KIND_CENTERED && g_raw_moments && tag == now) {
+            PbProfScope p("k_ord_derive_centered", st, false);
+            const uint32_t gx = (blk_cap + 255) / 256;
+            k_ord_derive_centered<<<dim3(gx < 64 ? gx : 64, nseg), 256, 0, st>>>(d_segs, d_stats, sc.raw, sc.psum);
+            tag = RawTag{};
+        } else {
+            PbProfScope p(KIND == KIND_MEAN ? "k_ord_blocksum_mean" : "k_ord_blocksum_centered", st, false);
+            k_ord_blocksum<KIND, W><<<grid, OB_THREADS, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, sc.psum, cmask);
+            tag = RawTag{};
+        }
         { PbProfScope p("k_ord_prefix", st, false);
           k_ord_prefix<C><<<dim3(chain_live<KIND, W>(0) ? C : C - 1, nseg), OP_THREADS, 0, st>>>(d_segs, sc.psum, chain_live<KIND, W>(0) ? 0 : 1, cmask); }
         PB_CUDA_OK(cudaMemsetAsync(sc.list_count, 0, 2 * sizeof(unsigned int), st));
@@ -1480,13 +1602,14 @@ void pb_ordered_chain_debug(unsigned long long out[35], bool reset) {
 void pb_ordered_set_dump_cap(long long slots) { g_dump_cap_override = slots; }
 void pb_ordered_set_fast(bool on) { g_fast_summary = on; }
 void pb_ordered_set_fused(bool on) { g_fused_pass = on; }
+void pb_ordered_set_raw_moments(bool on) { g_raw_moments = on; }
 
 uint32_t pb_ordered_blocks(uint32_t n) { return (n + OB - 1) / OB; }
 
 size_t pb_ordered_scratch_bytes(size_t total_blocks) {
     return dump_slots(total_blocks) * OB * sizeof(double) + group_rows(total_blocks) * sizeof(OrdRec) +
            total_blocks * 7 * (sizeof(double) + 4 * sizeof(OrdRec) + sizeof(uint2)) + 256 +
-           total_blocks * (sizeof(TileStat) + sizeof(int)) + OT_MAX_SEGS * sizeof(unsigned int);
+           total_blocks * (sizeof(TileStat) + sizeof(int) + RAW_N * sizeof(double)) + OT_MAX_SEGS * sizeof(unsigned int);
 }
 
 void pb_launch_pass_mean(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t max_n,

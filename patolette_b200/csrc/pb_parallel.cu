@@ -529,7 +529,7 @@ void pb_launch_scatter_ord(int cls_mode, int nclass, const PbSeg *d_segs, int ns
     if ((size_t)warps * (nclass + 1) * 4 > 32 * 1024)
         PB_CUDA_OK(cudaFuncSetAttribute(k_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         warps * (nclass + 1) * 4));
-    { PbProfScope _prof("k_scatter", st);
+    { PbProfScope _prof("k_scatter_ord", st);
     k_scatter<false><<<g, warps * 32, (size_t)warps * (nclass + 1) * 4, st>>>(
         cc, nclass, d_segs, tiles_cap, d_tile_hist, d_class_start, d_ord, none, none, none, none, false);
     }
@@ -546,12 +546,12 @@ void pb_launch_scatter_payload(int cls_mode, int nclass, const PbPlanes src[2], 
     ClsCtx cc{cls_mode, d_bucket, d_split, d_lut};
     dim3 g((tiles_cap + warps - 1) / warps, nseg);
     if (cls_mode == PB_CLS_SPLIT && nclass == 2) {
-        PbProfScope _prof("k_scatter", st);
+        PbProfScope _prof("k_scatter2", st);
         dim3 g2((tiles_cap + 7) / 8, nseg);
         k_scatter2<<<g2, 256, 0, st>>>(d_bucket, d_split, d_segs, d_tile_hist, d_class_start, src[0], src[1], dst[0], dst[1],
                                       src_is_identity);
     } else {
-        PbProfScope _prof("k_scatter", st);
+        PbProfScope _prof("k_scatter_payload", st);
         k_scatter<true><<<g, warps * 32, (size_t)warps * (nclass + 1) * 4, st>>>(
             cc, nclass, d_segs, tiles_cap, d_tile_hist, d_class_start, nullptr, src[0], src[1], dst[0], dst[1],
             src_is_identity);

@@ -1075,8 +1075,10 @@ void run_patolette(size_t width, size_t height, const void *data_v, const double
                 PB_CUDA_OK(cudaMemsetAsync(dmap.p, 0, sizeof(size_t), qz.st));
                 PB_CUDA_OK(cudaMemcpyAsync(dmap.p, palette_map, mb, in_kind, qz.st)); // (little endian)
             }
-            // (an image-sharded run dithers the whole image on every rank: the walk is one recurrence)
-            pb_dither_riemersma(planes, width, height, pal, dmap.p, qz.sm_count, qz.st, &qz.launches);
+            // (an image-sharded run splits the speculative chains of the walk over the ranks; the recurrence's
+            //  boundary repair stays replicated)
+            const PbDitherShard ds{sh.rank, sh.world, out_off, out_n};
+            pb_dither_riemersma(planes, width, height, pal, dmap.p, qz.sm_count, qz.st, &qz.launches, sh.on ? &ds : nullptr);
             palette_transform(qz, PB_T_REC2020_TO_SRGB, pal);
             set_timing(7, stage.stop());
         } else { // patolette.c:300-324
@@ -1333,6 +1335,7 @@ int patolette_b200_set_sharding(int rank, int world, patolette_b200_allgather_fn
 int patolette_b200_set_option(const char *name, long long value) {
     if (!name) return -1;
     if (!strcmp(name, "dump_cap")) { pb_ordered_set_dump_cap(value); return 0; }
+    if (!strcmp(name, "raw_moments")) { pb_ordered_set_raw_moments(value != 0); return 0; }
     if (!strcmp(name, "fused_pass")) { pb_ordered_set_fused(value != 0); return 0; }
     if (!strcmp(name, "fast_summary")) { pb_ordered_set_fast(value != 0); return 0; }
     if (!strcmp(name, "overlap")) { g_overlap_override = (int)value; return 0; }

@@ -13,9 +13,15 @@ void pb_kmeans_refine(const double *const planes[3], const double *d_w, size_t n
 void pb_kmeans_device(const float *d_x0, const float *d_x1, const float *d_x2, const float *d_wf, size_t nx,
                       std::vector<float> &cen, int K, int niter, int sm_count, cudaStream_t st, long *launches);
 // Riemersma dither (pb_dither.cu).  planes: device f64 linear-Rec2020 colours; writes d_map.
+// shard (image-sharded runs, optional): this rank runs its share of the speculative chains, the choices are
+// all-gathered, and only map[out_first, out_first + out_count) is written.
+struct PbDitherShard {
+    int rank, world;
+    size_t out_first, out_count;
+};
 void pb_dither_riemersma(const double *const planes[3], size_t width, size_t height,
                          const std::vector<double> &pal_rm, unsigned long long *d_map, int sm_count,
-                         cudaStream_t st, long *launches);
+                         cudaStream_t st, long *launches, const PbDitherShard *shard = nullptr);
 // test knob: candidate-list nearest-neighbour search inside the dither (default on)
 void pb_dither_set_grid(bool on);
 // test knob: 4 lanes per speculative chain (default) or one warp per chain
