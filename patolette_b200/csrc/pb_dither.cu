@@ -124,6 +124,7 @@ struct DitherLane {
 struct DitherGrid {
     const double *geom;
     const unsigned short *cnt, *list;
+    int ng;
 };
 
 // One pixel: returns the chosen palette index (uniform across the warp) and updates the queue.
@@ -139,7 +140,7 @@ __device__ __forceinline__ int dither_step(DitherLane &L, double P, const double
                  z = __shfl_sync(0xffffffffu, Cw, 2);
     double bd = 0.0;
     int best = 0x7fffffff;
-    const int cell = G.cnt ? pb_grid_cell(true, G.geom, G.geom + 3, x, y, z) : -1; // warp-uniform
+    const int cell = G.cnt ? pb_grid_cell(true, G.geom, G.geom + 3, G.ng, x, y, z) : -1; // warp-uniform
     if (cell >= 0) {
         const unsigned short *Lst = G.list + (size_t)cell * K;
         const int j0 = Lst[lane]; // K >= 64: in bounds; issued together with the count
@@ -219,7 +220,7 @@ __global__ void __launch_bounds__(DT_WARPS * 32) k_riemersma_spec(const double *
     // palettes too large for shared memory (48 B x K) are read from global memory
     const double *s_pal = pal_in_smem ? s_mem : pal, *s_palw = pal_in_smem ? s_mem + (size_t)K * 3 : palw;
     __shared__ double s_geom[6];
-    __shared__ int s_grid_ok;
+    __shared__ int s_grid_ok, s_grid_ng;
     if (pal_in_smem)
         for (int i = threadIdx.x; i < K * 3; i += blockDim.x) { s_mem[i] = pal[i]; s_mem[(size_t)K * 3 + i] = palw[i]; }
     if (threadIdx.x == 0) {
@@ -228,13 +229,15 @@ __global__ void __launch_bounds__(DT_WARPS * 32) k_riemersma_spec(const double *
             const PbGridGeom g = pb_grid_geom((const PbGridHdr *)nngrid);
             for (int d = 0; d < 3; d++) { s_geom[d] = g.lo[d]; s_geom[3 + d] = g.inv[d]; }
             s_grid_ok = g.ok;
+            s_grid_ng = g.ng;
         }
     }
     __syncthreads();
-    DitherGrid G{s_geom, nullptr, nullptr};
+    DitherGrid G{s_geom, nullptr, nullptr, 0};
     if (s_grid_ok) {
+        G.ng = s_grid_ng;
         G.cnt = (const unsigned short *)((const char *)nngrid + 256);
-        G.list = G.cnt + PB_NCELL;
+        G.list = G.cnt + G.ng * G.ng * G.ng;
     }
     const int lane = threadIdx.x & 31;
     const size_t g = (size_t)blockIdx.x * DT_WARPS + (threadIdx.x >> 5);
@@ -265,11 +268,18 @@ constexpr int DS_CHAINS = 32 / DS_GROUP;
 constexpr int DS_WARPS = 4;
 __constant__ double c_qw[16]; // queue weights (riemersma.c:360-373), oldest first
 
+// squared distance to palette entry j (weighted palette stored x, y, z, pad: two 16-byte loads)
+__device__ __forceinline__ double dither_dist4(const double *__restrict__ palw4, int j, double x, double y, double z) {
+    const double2 a = *reinterpret_cast<const double2 *>(palw4 + 4 * j), b = *reinterpret_cast<const double2 *>(palw4 + 4 * j + 2);
+    const double dx = __dsub_rn(x, a.x), dy = __dsub_rn(y, a.y), dz = __dsub_rn(z, b.x);
+    return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+}
+
 __device__ __forceinline__ int dither_nn4(double x, double y, double z, const double *__restrict__ s_palw, int K, int gl,
                                           const DitherGrid &G) {
     double bd = 0.0;
     int best = 0x7fffffff;
-    const int cell = G.cnt ? pb_grid_cell(true, G.geom, G.geom + 3, x, y, z) : -1; // uniform within the group
+    const int cell = G.cnt ? pb_grid_cell(true, G.geom, G.geom + 3, G.ng, x, y, z) : -1; // uniform within the group
     if (cell >= 0) {
         const unsigned short *Lst = G.list + (size_t)cell * K;
         // the first four entries of this lane are requested together with the count (K >= 64: in bounds), so the
@@ -281,24 +291,18 @@ __device__ __forceinline__ int dither_nn4(double x, double y, double z, const do
             const int t = gl + u * DS_GROUP;
             if (t < m) {
                 const int j = pre[u];
-                const double dx = __dsub_rn(x, s_palw[3 * j]), dy = __dsub_rn(y, s_palw[3 * j + 1]),
-                             dz = __dsub_rn(z, s_palw[3 * j + 2]);
-                const double dd = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                const double dd = dither_dist4(s_palw, j, x, y, z);
                 if (best == 0x7fffffff || dd < bd) { bd = dd; best = j; }
             }
         }
         for (int t = gl + 4 * DS_GROUP; t < m; t += DS_GROUP) {
             const int j = Lst[t];
-            const double dx = __dsub_rn(x, s_palw[3 * j]), dy = __dsub_rn(y, s_palw[3 * j + 1]),
-                         dz = __dsub_rn(z, s_palw[3 * j + 2]);
-            const double dd = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+            const double dd = dither_dist4(s_palw, j, x, y, z);
             if (best == 0x7fffffff || dd < bd) { bd = dd; best = j; }
         }
     } else {
         for (int j = gl; j < K; j += DS_GROUP) {
-            const double dx = __dsub_rn(x, s_palw[3 * j]), dy = __dsub_rn(y, s_palw[3 * j + 1]),
-                         dz = __dsub_rn(z, s_palw[3 * j + 2]);
-            const double dd = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+            const double dd = dither_dist4(s_palw, j, x, y, z);
             if (best == 0x7fffffff || dd < bd) { bd = dd; best = j; }
         }
     }
@@ -314,34 +318,39 @@ __device__ __forceinline__ int dither_nn4(double x, double y, double z, const do
     return best;
 }
 
+template <bool PAL_SMEM> // palette in shared memory (LDS) or - too large - in global memory
 __global__ void __launch_bounds__(DS_WARPS * 32) k_riemersma_spec4(const double *__restrict__ h0, const double *__restrict__ h1,
                                                                   const double *__restrict__ h2, size_t n, size_t seg,
                                                                   size_t warm, const double *__restrict__ pal,
                                                                   const double *__restrict__ palw, int K,
                                                                   uint32_t *__restrict__ hidx, uint32_t *__restrict__ overlap,
-                                                                  const void *__restrict__ nngrid, bool pal_in_smem,
+                                                                  const void *__restrict__ nngrid,
                                                                   size_t g_first, size_t g_end) {
-    extern __shared__ double s_mem[];
-    const double *s_pal = pal_in_smem ? s_mem : pal, *s_palw = pal_in_smem ? s_mem + (size_t)K * 3 : palw;
+    extern __shared__ __align__(16) double s_mem[]; // [K][4] weighted palette, then [K][3] palette
+    const double *s_palw = PAL_SMEM ? s_mem : palw, *s_pal = PAL_SMEM ? s_mem + (size_t)K * 4 : pal;
     __shared__ double s_geom[6];
-    __shared__ int s_grid_ok;
+    __shared__ int s_grid_ok, s_grid_ng;
     __shared__ double s_px[DS_WARPS][DS_CHAINS][3][16];
     __shared__ int s_choice[DS_WARPS][DS_CHAINS][16];
-    if (pal_in_smem)
-        for (int i = threadIdx.x; i < K * 3; i += blockDim.x) { s_mem[i] = pal[i]; s_mem[(size_t)K * 3 + i] = palw[i]; }
+    if (PAL_SMEM) {
+        for (int i = threadIdx.x; i < K * 4; i += blockDim.x) s_mem[i] = palw[i];
+        for (int i = threadIdx.x; i < K * 3; i += blockDim.x) s_mem[(size_t)K * 4 + i] = pal[i];
+    }
     if (threadIdx.x == 0) {
         s_grid_ok = 0;
         if (nngrid) {
             const PbGridGeom g = pb_grid_geom((const PbGridHdr *)nngrid);
             for (int d = 0; d < 3; d++) { s_geom[d] = g.lo[d]; s_geom[3 + d] = g.inv[d]; }
             s_grid_ok = g.ok;
+            s_grid_ng = g.ng;
         }
     }
     __syncthreads();
-    DitherGrid G{s_geom, nullptr, nullptr};
+    DitherGrid G{s_geom, nullptr, nullptr, 0};
     if (s_grid_ok) {
+        G.ng = s_grid_ng;
         G.cnt = (const unsigned short *)((const char *)nngrid + 256);
-        G.list = G.cnt + PB_NCELL;
+        G.list = G.cnt + G.ng * G.ng * G.ng;
     }
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gl = lane & (DS_GROUP - 1), grp = lane / DS_GROUP;
     const int ch = gl < 3 ? gl : 0;
@@ -430,7 +439,7 @@ __global__ void __launch_bounds__(32) k_riemersma_repair(const double *__restric
     extern __shared__ double s_mem[];
     const double *s_pal = pal_in_smem ? s_mem : pal, *s_palw = pal_in_smem ? s_mem + (size_t)K * 3 : palw;
     __shared__ double s_geom[6];
-    __shared__ int s_grid_ok;
+    __shared__ int s_grid_ok, s_grid_ng;
     const int lane = threadIdx.x;
     if (pal_in_smem)
         for (int i = lane; i < K * 3; i += 32) { s_mem[i] = pal[i]; s_mem[(size_t)K * 3 + i] = palw[i]; }
@@ -440,13 +449,15 @@ __global__ void __launch_bounds__(32) k_riemersma_repair(const double *__restric
             const PbGridGeom g = pb_grid_geom((const PbGridHdr *)nngrid);
             for (int d = 0; d < 3; d++) { s_geom[d] = g.lo[d]; s_geom[3 + d] = g.inv[d]; }
             s_grid_ok = g.ok;
+            s_grid_ng = g.ng;
         }
     }
     __syncwarp();
-    DitherGrid G{s_geom, nullptr, nullptr};
+    DitherGrid G{s_geom, nullptr, nullptr, 0};
     if (s_grid_ok) {
+        G.ng = s_grid_ng;
         G.cnt = (const unsigned short *)((const char *)nngrid + 256);
-        G.list = G.cnt + PB_NCELL;
+        G.list = G.cnt + G.ng * G.ng * G.ng;
     }
     const size_t nseg = (n + seg - 1) / seg;
     DitherLane L;
@@ -543,13 +554,14 @@ void pb_dither_riemersma(const double *const planes[3], size_t width, size_t hei
         palw[3 * j + 1] = pal_rm[3 * j + 1] * fy;
         palw[3 * j + 2] = pal_rm[3 * j + 2] * fz;
     }
-    double *d_h[3] = {nullptr, nullptr, nullptr}, *d_pal = nullptr, *d_palw = nullptr, *d_qw = nullptr;
+    double *d_h[3] = {nullptr, nullptr, nullptr}, *d_pal = nullptr, *d_palw = nullptr, *d_qw = nullptr, *d_palw4 = nullptr;
     void *d_grid = nullptr;
     uint32_t *d_rank = nullptr, *d_hidx = nullptr, *d_overlap = nullptr;
     unsigned long long *d_stats = nullptr;
     unsigned char *d_flags = nullptr;
     auto cleanup = [&]() {
         pb_pool_free(d_flags);
+        pb_pool_free(d_palw4);
         for (int j = 0; j < 3; j++) pb_pool_free(d_h[j]);
         pb_pool_free(d_pal); pb_pool_free(d_palw); pb_pool_free(d_qw); pb_pool_free(d_hidx); pb_pool_free(d_overlap); pb_pool_free(d_stats); pb_pool_free(d_grid);
     };
@@ -610,15 +622,28 @@ void pb_dither_riemersma(const double *const planes[3], size_t width, size_t hei
         pb_prof_next_bytes(28.0 * (double)n); // 24 B of colours read + 4 B index written per pixel of the walk
         if (g_dither_subwarp) {
             PB_CUDA_OK(cudaMemcpyToSymbolAsync(c_qw, qw, sizeof qw, 0, cudaMemcpyHostToDevice, st)); // (per device; 128 B)
-            if (smem > 32 * 1024)
-                PB_CUDA_OK(cudaFuncSetAttribute(k_riemersma_spec4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            // the weighted palette padded to four doubles per entry (two 16-byte loads per candidate)
+            std::vector<double> palw4((size_t)K * 4, 0.0);
+            for (int j = 0; j < K; j++) { palw4[4 * j] = palw[3 * j]; palw4[4 * j + 1] = palw[3 * j + 1]; palw4[4 * j + 2] = palw[3 * j + 2]; }
+            d_palw4 = (double *)pb_pool_alloc(palw4.size() * sizeof(double));
+            PB_CUDA_OK(cudaMemcpyAsync(d_palw4, palw4.data(), palw4.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+            PB_CUDA_OK(cudaStreamSynchronize(st)); // (palw4 is a local)
+            const size_t smem4 = (size_t)K * 7 * sizeof(double);
+            const bool smem4_ok = smem4 <= PB_SMEM_PALETTE_LIMIT;
+            if (smem4_ok && smem4 > 32 * 1024)
+                PB_CUDA_OK(cudaFuncSetAttribute(k_riemersma_spec4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
             const size_t per_cta = (size_t)DS_WARPS * DS_CHAINS;
             const size_t g_first = (size_t)srank * per_rank, g_end = g_first + per_rank < nseg ? g_first + per_rank : nseg;
             const size_t mine = g_end > g_first ? g_end - g_first : 0;
             if (mine) {
                 PbProfScope _prof("k_riemersma_spec", st);
-                k_riemersma_spec4<<<(unsigned)((mine + per_cta - 1) / per_cta), DS_WARPS * 32, smem, st>>>(
-                    d_h[0], d_h[1], d_h[2], n, seg, warm, d_pal, d_palw, K, d_hidx, d_overlap, d_grid, pal_in_smem, g_first, g_end);
+                const unsigned gridx = (unsigned)((mine + per_cta - 1) / per_cta);
+                if (smem4_ok)
+                    k_riemersma_spec4<true><<<gridx, DS_WARPS * 32, smem4, st>>>(d_h[0], d_h[1], d_h[2], n, seg, warm, d_pal, d_palw4, K, d_hidx,
+                                                                                 d_overlap, d_grid, g_first, g_end);
+                else
+                    k_riemersma_spec4<false><<<gridx, DS_WARPS * 32, 0, st>>>(d_h[0], d_h[1], d_h[2], n, seg, warm, d_pal, d_palw4, K, d_hidx,
+                                                                              d_overlap, d_grid, g_first, g_end);
             }
             if (world > 1) { // every rank's choices and warm-up records, in place
                 pb_nccl_allgather(d_hidx + g_first * seg, d_hidx, per_rank * seg * sizeof(uint32_t), st);

@@ -27,15 +27,13 @@
 
 namespace {
 
-constexpr int NG = PB_NG;
-constexpr int NCELL = PB_NCELL;
 using GridHdr = PbGridHdr;
 using GridGeom = PbGridGeom;
 __device__ __forceinline__ GridGeom grid_geom(const GridHdr *h) { return pb_grid_geom(h); }
 
-__global__ void k_nn_bbox_init(GridHdr *h, double s0, double s1, double s2, double expand) {
+__global__ void k_nn_bbox_init(GridHdr *h, double s0, double s1, double s2, double expand, int ng) {
     if (threadIdx.x < 3) { h->mn[threadIdx.x] = ~0ULL; h->mx[threadIdx.x] = 0ULL; }
-    if (threadIdx.x == 0) { h->scale[0] = s0; h->scale[1] = s1; h->scale[2] = s2; h->expand = expand; }
+    if (threadIdx.x == 0) { h->scale[0] = s0; h->scale[1] = s1; h->scale[2] = s2; h->expand = expand; h->ng = ng; }
 }
 
 __global__ void __launch_bounds__(256) k_nn_bbox(const double *__restrict__ c0, const double *__restrict__ c1,
@@ -71,6 +69,7 @@ __global__ void __launch_bounds__(128) k_nn_cells(const GridHdr *__restrict__ hd
     __shared__ double s_red[4];
     __shared__ double s_best;
     const GridGeom g = grid_geom(hdr);
+    const int NG = g.ng;
     const int cell = blockIdx.x, cz = cell % NG, cy = (cell / NG) % NG, cx = cell / (NG * NG);
     const int cc[3] = {cx, cy, cz};
     double lo[3], hi[3];
@@ -138,7 +137,7 @@ __global__ void __launch_bounds__(256) k_nearest_grid(const double *__restrict__
         const double x = c0[i], y = c1[i], z = c2[i];
         double bd = 0.0;
         int best = 0;
-        const int cell = pb_grid_cell(g.ok, g.lo, g.inv, x, y, z);
+        const int cell = pb_grid_cell(g.ok, g.lo, g.inv, g.ng, x, y, z);
         if (cell >= 0) {
             const int m = cnt[cell];
             const unsigned short *L = list + (size_t)cell * K;
@@ -164,16 +163,20 @@ __global__ void __launch_bounds__(256) k_nearest_grid(const double *__restrict__
 
 } // namespace
 
-size_t pb_nngrid_scratch_bytes(int K) { return 256 + (size_t)NCELL * 2 + (size_t)NCELL * (size_t)K * 2; }
+size_t pb_nngrid_scratch_bytes(int K) {
+    const size_t ncell = (size_t)pb_grid_ng(K) * pb_grid_ng(K) * pb_grid_ng(K);
+    return 256 + ncell * 2 + ncell * (size_t)K * 2;
+}
 
 // pixels -> bounding box -> per-cell candidate lists (d_scratch: pb_nngrid_scratch_bytes(K))
 void pb_launch_nngrid_build(const double *const planes[3], size_t n, const double *d_palette_rm, int K, void *d_scratch,
                             int sm_count, cudaStream_t st, const double *scale, double expand) {
     GridHdr *hdr = (GridHdr *)d_scratch;
+    const int ng = pb_grid_ng(K), NCELL = ng * ng * ng;
     unsigned short *cnt = (unsigned short *)((char *)d_scratch + 256);
     unsigned short *list = cnt + NCELL;
     { PbProfScope _prof("k_nn_bbox", st, false);
-      k_nn_bbox_init<<<1, 32, 0, st>>>(hdr, scale ? scale[0] : 1.0, scale ? scale[1] : 1.0, scale ? scale[2] : 1.0, expand);
+      k_nn_bbox_init<<<1, 32, 0, st>>>(hdr, scale ? scale[0] : 1.0, scale ? scale[1] : 1.0, scale ? scale[2] : 1.0, expand, ng);
       size_t want = (n + 256 * 8 - 1) / (256 * 8), cap = (size_t)sm_count * 8;
       k_nn_bbox<<<(int)(want < cap ? (want ? want : 1) : cap), 256, 0, st>>>(planes[0], planes[1], planes[2], n, hdr); }
     { PbProfScope _prof("k_nn_cells", st, false);
@@ -187,6 +190,7 @@ void pb_launch_nearest_grid(const double *const planes[3], size_t n, const doubl
                             unsigned long long *d_map, int sm_count, cudaStream_t st) {
     if (n == 0) return;
     const GridHdr *hdr = (const GridHdr *)d_scratch;
+    const int NCELL = pb_grid_ng(K) * pb_grid_ng(K) * pb_grid_ng(K);
     const unsigned short *cnt = (const unsigned short *)((const char *)d_scratch + 256);
     const unsigned short *list = cnt + NCELL;
     size_t want = (n + 255) / 256, cap = (size_t)sm_count * 8;

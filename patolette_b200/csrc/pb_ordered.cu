@@ -723,7 +723,22 @@ __global__ void __launch_bounds__(OF_THREADS, PB_OF_MINB) k_ord_fast(PbPlanes b0
     } else {
         for (int k = 0; k < mycnt; k++) element(k);
     }
-    const unsigned tie = __any_sync(FULL, tie_any) ? ~0u : 0u;
+    // which chains hold the tie(s): a second pass over the block, only when there was one (a few percent of the blocks)
+    unsigned tie = 0;
+    if (__any_sync(FULL, tie_any)) {
+        for (int k = 0; k < mycnt; k++) {
+            double t[C];
+            terms_all<KIND, W>(W ? mine[3 * OS_PLANE + k] : 1.0, mine[k], mine[OS_PLANE + k], mine[2 * OS_PLANE + k], m0, m1, m2, t);
+#pragma unroll
+            for (int c = 0; c < C; c++) {
+                if (!chain_live<KIND, W>(c)) continue;
+                bool tie_c;
+                pb_fast_quant(grid[c], t[c], &tie_c);
+                if (tie_c) tie |= 1u << c;
+            }
+        }
+        tie = __reduce_or_sync(FULL, tie);
+    }
     const bool any_wneg = W && __any_sync(FULL, wneg);
     // ---- compose the lanes in element order; lane c finishes chain c ----------------------------------------
     double r_sum = 0.0, r_mn = 0.0, r_mx = 0.0; // of chain `lane`
