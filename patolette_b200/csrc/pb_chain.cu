@@ -221,7 +221,71 @@ __global__ void __launch_bounds__(BK_WARPS * 32) k_bucket_chains_gq(const double
     if (lane < 10) out[(size_t)b * 10 + lane] = acc;
 }
 
+
+// GQ cell moments, second version: one CTA per bucket.  With one warp per bucket the gathers of that warp bound
+// the kernel (45 cycles per member against 8.4 for the dependent add): here all four warps of the CTA gather -
+// two members per thread and tile of 256, the next tile's gathers in registers while the current tile is being
+// chained - and warp 0 runs the ten chains (lanes 0..9) over the terms the gatherers staged in shared memory.
+constexpr int BG_THREADS = 128, BG_TILE = 256, BG_PER = BG_TILE / BG_THREADS, BG_STRIDE = BG_TILE + 2;
+__global__ void __launch_bounds__(BG_THREADS) k_bucket_chains_gq2(const double *__restrict__ aos, const uint32_t *__restrict__ ord,
+                                                                 const uint32_t *__restrict__ class_start,
+                                                                 double *__restrict__ out) {
+    constexpr int NT = 10;
+    __shared__ double term[2][NT][BG_STRIDE];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const uint32_t beg = class_start[b], end = class_start[b + 1];
+    const uint32_t ntile = (end - beg + BG_TILE - 1) / BG_TILE;
+    double acc = 0.0;
+    Px g[BG_PER];
+    auto gather = [&](uint32_t t) {
+#pragma unroll
+        for (int q = 0; q < BG_PER; q++) {
+            const uint32_t i = beg + t * BG_TILE + q * BG_THREADS + tid;
+            g[q] = Px{0.0, 0.0, 0.0, 0.0};
+            if (t < ntile && i < end) g[q] = load_px(aos, ord[i]);
+        }
+    };
+    auto stage = [&](int buf) {
+#pragma unroll
+        for (int q = 0; q < BG_PER; q++) {
+            const int e = q * BG_THREADS + tid;
+            const double x = g[q].c0, y = g[q].c1, z = g[q].c2;
+            term[buf][0][e] = x;
+            term[buf][1][e] = y;
+            term[buf][2][e] = z;
+            term[buf][3][e] = __dadd_rn(__dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y)), __dmul_rn(z, z));
+            term[buf][4][e] = __dmul_rn(x, x);
+            term[buf][5][e] = __dmul_rn(x, y);
+            term[buf][6][e] = __dmul_rn(y, y);
+            term[buf][7][e] = __dmul_rn(x, z);
+            term[buf][8][e] = __dmul_rn(y, z);
+            term[buf][9][e] = __dmul_rn(z, z);
+        }
+    };
+    gather(0);
+    stage(0);
+    gather(1);
+    __syncthreads();
+    for (uint32_t t = 0; t < ntile; t++) {
+        // tile t is staged in term[t & 1]; the registers hold tile t + 1: stage it, then fetch tile t + 2 - those
+        // loads are in flight while warp 0 chains over tile t
+        stage((t + 1) & 1);
+        gather(t + 2);
+        if (tid < NT) {
+            const uint32_t cnt = min((uint32_t)BG_TILE, end - (beg + t * BG_TILE));
+            const double *vp = term[t & 1][tid];
+#pragma unroll 16
+            for (uint32_t e = 0; e < cnt; e++) acc = __dadd_rn(acc, vp[e]);
+        }
+        __syncthreads();
+    }
+    if (tid < NT) out[(size_t)b * NT + tid] = acc;
+}
+
 } // namespace
+
+static bool g_gq_chain_cta = true; // "gq_chain_cta": one CTA per GQ bucket (k_bucket_chains_gq2) or one warp
+void pb_chain_set_gq_cta(bool on) { g_gq_chain_cta = on; }
 
 void pb_launch_bucket_chains_lq(const double *d_aos, const PbSeg *d_segs, int nseg, bool weighted,
                                 const uint32_t *d_ord, const uint32_t *d_class_start, double *d_out,
@@ -237,7 +301,8 @@ void pb_launch_bucket_chains_lq(const double *d_aos, const PbSeg *d_segs, int ns
 void pb_launch_bucket_chains_gq(const double *d_aos, const uint32_t *d_ord, const uint32_t *d_class_start,
                                 double *d_out, cudaStream_t st) {
     { PbProfScope _prof("k_bucket_chains_gq", st);
-    k_bucket_chains_gq<<<PB_BUCKETS / BK_WARPS, BK_WARPS * 32, 0, st>>>(d_aos, d_ord, d_class_start, d_out);
+    if (g_gq_chain_cta) k_bucket_chains_gq2<<<PB_BUCKETS, BG_THREADS, 0, st>>>(d_aos, d_ord, d_class_start, d_out);
+    else k_bucket_chains_gq<<<PB_BUCKETS / BK_WARPS, BK_WARPS * 32, 0, st>>>(d_aos, d_ord, d_class_start, d_out);
     }
     PB_CUDA_OK(cudaGetLastError());
 }

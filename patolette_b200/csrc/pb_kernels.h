@@ -58,6 +58,7 @@ void pb_launch_pass_centered(const PbPlanes bufs[2], const PbSeg *d_segs, int ns
 void pb_launch_bucket_chains_lq(const double *d_aos, const PbSeg *d_segs, int nseg, bool weighted,
                                 const uint32_t *d_ord, const uint32_t *d_class_start,
                                 double *d_out /* nseg x 512 x 4 */, cudaStream_t st);
+void pb_chain_set_gq_cta(bool on); // test knob: one CTA (default) or one warp per GQ bucket
 void pb_launch_bucket_chains_gq(const double *d_aos, const uint32_t *d_ord,
                                 const uint32_t *d_class_start, double *d_out /* 512 x 10 */,
                                 cudaStream_t st);

@@ -216,32 +216,51 @@ __global__ void __launch_bounds__(256) k_tile_scan_a(int nclass, const PbSeg *__
     const uint32_t ntiles = (sg.n + SC_TILE - 1) / SC_TILE;
     const uint32_t t0 = blockIdx.x * SC_CHUNK;
     if (t0 >= ntiles) return;
-    const uint32_t t1 = min(t0 + (uint32_t)SC_CHUNK, ntiles);
-    const uint32_t *h = tile_hist + (size_t)sg.tbase * nclass;
+    const uint32_t cnt = min((uint32_t)SC_CHUNK, ntiles - t0);
+    const uint32_t *h = tile_hist + ((size_t)sg.tbase + t0) * nclass;
     uint32_t *out = chunk_tot + (size_t)(chunk_row0(sg, seg) + blockIdx.x) * nclass;
     for (int c = threadIdx.x; c < nclass; c += blockDim.x) {
+        uint32_t v[SC_CHUNK]; // every load of the column in flight at once (one memory round trip, not 32)
+#pragma unroll
+        for (int t = 0; t < SC_CHUNK; t++) v[t] = t < (int)cnt ? h[(size_t)t * nclass + c] : 0u;
         uint32_t sum = 0;
-        for (uint32_t t = t0; t < t1; t++) sum += h[(size_t)t * nclass + c];
+#pragma unroll
+        for (int t = 0; t < SC_CHUNK; t++) sum += v[t];
         out[c] = sum;
     }
 }
 
+// exclusive scan of the chunk totals down every class column: one WARP per column, every lane a contiguous run
+// of chunks (independent loads), a warp scan of the 32 partial sums.  (The first version walked the chunks with
+// one thread per column: thousands of dependent load-add-store steps for a 128 M pixel segment.)
 __global__ void __launch_bounds__(256) k_tile_scan_b(int nclass, const PbSeg *__restrict__ segs,
                                                      uint32_t *__restrict__ chunk_tot,
                                                      uint32_t *__restrict__ class_tot) {
-    const int seg = blockIdx.x;
+    const int seg = blockIdx.y;
     const PbSeg sg = segs[seg];
     const uint32_t ntiles = (sg.n + SC_TILE - 1) / SC_TILE, nchunks = (ntiles + SC_CHUNK - 1) / SC_CHUNK;
     uint32_t *ct = chunk_tot + (size_t)chunk_row0(sg, seg) * nclass;
-    for (int c = threadIdx.x; c < nclass; c += blockDim.x) {
-        uint32_t run = 0;
-        for (uint32_t k = 0; k < nchunks; k++) {
-            const uint32_t v = ct[(size_t)k * nclass + c];
-            ct[(size_t)k * nclass + c] = run;
-            run += v;
-        }
-        class_tot[(size_t)seg * (nclass + 1) + c] = run;
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= nclass) return;
+    const uint32_t per = (nchunks + 31) / 32;
+    const uint32_t k0 = min((uint32_t)lane * per, nchunks), k1 = min(k0 + per, nchunks);
+    uint32_t s = 0;
+#pragma unroll 8
+    for (uint32_t k = k0; k < k1; k++) s += ct[(size_t)k * nclass + c];
+    uint32_t incl = s;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
     }
+    uint32_t run = incl - s;
+#pragma unroll 8
+    for (uint32_t k = k0; k < k1; k++) {
+        const uint32_t v = ct[(size_t)k * nclass + c];
+        ct[(size_t)k * nclass + c] = run;
+        run += v;
+    }
+    if (lane == 31) class_tot[(size_t)seg * (nclass + 1) + c] = incl;
 }
 
 __global__ void __launch_bounds__(256) k_tile_scan_c(int nclass, const PbSeg *__restrict__ segs,
@@ -252,15 +271,18 @@ __global__ void __launch_bounds__(256) k_tile_scan_c(int nclass, const PbSeg *__
     const uint32_t ntiles = (sg.n + SC_TILE - 1) / SC_TILE;
     const uint32_t t0 = blockIdx.x * SC_CHUNK;
     if (t0 >= ntiles) return;
-    const uint32_t t1 = min(t0 + (uint32_t)SC_CHUNK, ntiles);
-    uint32_t *h = tile_hist + (size_t)sg.tbase * nclass;
+    const uint32_t cnt = min((uint32_t)SC_CHUNK, ntiles - t0);
+    uint32_t *h = tile_hist + ((size_t)sg.tbase + t0) * nclass;
     const uint32_t *in = chunk_tot + (size_t)(chunk_row0(sg, seg) + blockIdx.x) * nclass;
     for (int c = threadIdx.x; c < nclass; c += blockDim.x) {
+        uint32_t v[SC_CHUNK];
+#pragma unroll
+        for (int t = 0; t < SC_CHUNK; t++) v[t] = t < (int)cnt ? h[(size_t)t * nclass + c] : 0u;
         uint32_t run = in[c];
-        for (uint32_t t = t0; t < t1; t++) {
-            const uint32_t v = h[(size_t)t * nclass + c];
-            h[(size_t)t * nclass + c] = run;
-            run += v;
+#pragma unroll
+        for (int t = 0; t < SC_CHUNK; t++) {
+            if (t < (int)cnt) h[(size_t)t * nclass + c] = run;
+            run += v[t];
         }
     }
 }
@@ -295,27 +317,39 @@ __global__ void k_scatter(ClsCtx cc, int nclass, const PbSeg *__restrict__ segs,
     const PbPlanes &S = sg.buf ? src1 : src0;
     const PbPlanes &D = sg.buf ? dst1 : dst0;
     const uint32_t beg = tile * SC_TILE, end = min(beg + (uint32_t)SC_TILE, sg.n);
-    for (uint32_t row = beg; row < end; row += 32) {
-        const uint32_t i = row + lane;
-        const bool valid = i < end;
-        const uint32_t pos = sg.lo + i;
-        const uint32_t c = valid ? cls_of(cc, seg, pos) : (uint32_t)nclass;
-        const uint32_t peers = __match_any_sync(0xffffffffu, c);
-        const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
-        const uint32_t base = cnt[c];
-        __syncwarp();
-        if (rank == 0) cnt[c] = base + __popc(peers);
-        __syncwarp();
-        if (valid) {
-            const uint32_t dst = base + rank;
-            if (PAYLOAD) {
-                D.c[0][dst] = S.c[0][pos];
-                D.c[1][dst] = S.c[1][pos];
-                D.c[2][dst] = S.c[2][pos];
-                if (S.w) D.w[dst] = S.w[pos];
-                if (D.idx) D.idx[dst] = src_is_identity ? pos : S.idx[pos];
-            } else {
-                ord[dst] = pos;
+    constexpr int RB = 8; // rows whose class ids are fetched together (one memory round trip per 8 rows)
+    for (uint32_t row0 = beg; row0 < end; row0 += 32 * RB) {
+        uint32_t cls[RB];
+#pragma unroll
+        for (int r = 0; r < RB; r++) {
+            const uint32_t i = row0 + r * 32 + lane;
+            cls[r] = i < end ? cls_of(cc, seg, sg.lo + i) : (uint32_t)nclass;
+        }
+#pragma unroll
+        for (int r = 0; r < RB; r++) {
+            const uint32_t row = row0 + r * 32;
+            if (row >= end) break; // warp-uniform
+            const uint32_t i = row + lane;
+            const bool valid = i < end;
+            const uint32_t pos = sg.lo + i;
+            const uint32_t c = cls[r];
+            const uint32_t peers = __match_any_sync(0xffffffffu, c);
+            const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+            const uint32_t base = cnt[c];
+            __syncwarp();
+            if (rank == 0) cnt[c] = base + __popc(peers);
+            __syncwarp();
+            if (valid) {
+                const uint32_t dst = base + rank;
+                if (PAYLOAD) {
+                    D.c[0][dst] = S.c[0][pos];
+                    D.c[1][dst] = S.c[1][pos];
+                    D.c[2][dst] = S.c[2][pos];
+                    if (S.w) D.w[dst] = S.w[pos];
+                    if (D.idx) D.idx[dst] = src_is_identity ? pos : S.idx[pos];
+                } else {
+                    ord[dst] = pos;
+                }
             }
         }
     }
@@ -505,7 +539,7 @@ void pb_launch_class_rank(int cls_mode, int nclass, const PbSeg *d_segs, int nse
     k_tile_scan_a<<<g2, 256, 0, st>>>(nclass, d_segs, d_tile_hist, d_chunk_tot);
     }
     { PbProfScope _prof("k_tile_scan", st, false);
-    k_tile_scan_b<<<nseg, 256, 0, st>>>(nclass, d_segs, d_chunk_tot, d_class_start);
+    k_tile_scan_b<<<dim3((nclass + 7) / 8, nseg), 256, 0, st>>>(nclass, d_segs, d_chunk_tot, d_class_start);
     }
     { PbProfScope _prof("k_tile_scan", st, false);
     k_tile_scan_c<<<g2, 256, 0, st>>>(nclass, d_segs, d_tile_hist, d_chunk_tot);

@@ -1335,6 +1335,7 @@ int patolette_b200_set_sharding(int rank, int world, patolette_b200_allgather_fn
 int patolette_b200_set_option(const char *name, long long value) {
     if (!name) return -1;
     if (!strcmp(name, "dump_cap")) { pb_ordered_set_dump_cap(value); return 0; }
+    if (!strcmp(name, "gq_chain_cta")) { pb_chain_set_gq_cta(value != 0); return 0; }
     if (!strcmp(name, "raw_moments")) { pb_ordered_set_raw_moments(value != 0); return 0; }
     if (!strcmp(name, "fused_pass")) { pb_ordered_set_fused(value != 0); return 0; }
     if (!strcmp(name, "fast_summary")) { pb_ordered_set_fast(value != 0); return 0; }
