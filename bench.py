@@ -529,7 +529,7 @@ def measure_ours(args):
             for _ in range(3):
                 ostep()
             torch.cuda.synchronize()
-            osteps = 5
+            osteps = 10
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(stream)
             for _ in range(osteps):

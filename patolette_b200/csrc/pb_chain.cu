@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(BK_WARPS * 32) k_bucket_chains_lq(const double
 #pragma unroll
             for (int t = 0; t < NT; t++) g[q][t] = 0.0;
             if (i < end) {
-                const Px x = load_px(aos, ord[i]);
+                const Px x = load_px(aos, ord ? ord[i] : i); // (ord == nullptr: aos is the bucket-sorted copy)
                 if (WEIGHTED) {
                     g[q][0] = x.w;
                     g[q][1] = __dmul_rn(x.c0, x.w);
@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(BK_WARPS * 32) k_bucket_chains_gq(const double
 #pragma unroll
             for (int q = 0; q < BK_PER; q++) {
                 const uint32_t i = beg + t * BK_TILE + q * 32 + lane;
-                o[q] = (t < ntile && i < end) ? ord[i] : 0xffffffffu;
+                o[q] = (t < ntile && i < end) ? (ord ? ord[i] : i) : 0xffffffffu;
             }
         };
         auto issue = [&](uint32_t t, const uint32_t *o) { // gathers of tile t into stage t % BK_DEPTH (one commit per call)
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(BG_THREADS) k_bucket_chains_gq2(const double *
         for (int q = 0; q < BG_PER; q++) {
             const uint32_t i = beg + t * BG_TILE + q * BG_THREADS + tid;
             g[q] = Px{0.0, 0.0, 0.0, 0.0};
-            if (t < ntile && i < end) g[q] = load_px(aos, ord[i]);
+            if (t < ntile && i < end) g[q] = load_px(aos, ord ? ord[i] : i);
         }
     };
     auto stage = [&](int buf) {

@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <condition_variable>
 #include <mutex>
+#include <stdexcept>
 #include <thread>
 #include <vector>
 
@@ -19,6 +20,7 @@ struct Pool {
     int active = 0;   // workers that take part in the current job (tid 1..active)
     int pending = 0;  // ... and have not finished it yet
     bool quit = false;
+    bool failed = false; // a worker's share of the current job threw
     std::mutex run_mu; // one job at a time
 
     void worker(int tid) {
@@ -31,8 +33,10 @@ struct Pool {
             if (tid > active) continue;
             const std::function<void(int)> *fn = job;
             lk.unlock();
-            (*fn)(tid);
+            bool threw = false;
+            try { (*fn)(tid); } catch (...) { threw = true; } // an exception must not leave a worker thread (std::terminate)
             lk.lock();
+            if (threw) failed = true;
             if (--pending == 0) done.notify_one();
         }
     }
@@ -78,11 +82,14 @@ void pb_hostpool_run(int threads, const std::function<void(int)> &fn) {
         p.job = &fn;
         p.active = threads - 1;
         p.pending = threads - 1;
+        p.failed = false;
         p.generation++;
     }
     p.wake.notify_all();
-    fn(0);
+    bool threw = false;
+    try { fn(0); } catch (...) { threw = true; } // the workers still have to finish before `fn` goes out of scope
     std::unique_lock<std::mutex> lk(p.mu);
     p.done.wait(lk, [&] { return p.pending == 0; });
     p.job = nullptr;
+    if (threw || p.failed) throw std::runtime_error("patolette_b200: a host pool job failed");
 }

@@ -89,8 +89,10 @@ __global__ void __launch_bounds__(PAR_THREADS) k_buckets(PbPlanes b0, PbPlanes b
         for (uint32_t i = base + threadIdx.x; i < end; i += PAR_THREADS) {
             uint32_t b;
             const double v0 = c0[i], v1 = c1[i], v2 = c2[i];
-            ao[2 * (size_t)i] = make_double2(v0, v1);
-            ao[2 * (size_t)i + 1] = make_double2(v2, cw ? cw[i] : 1.0);
+            if (aos) { // (the gathering per-bucket sums; the default route sorts the payload itself instead)
+                ao[2 * (size_t)i] = make_double2(v0, v1);
+                ao[2 * (size_t)i + 1] = make_double2(v2, cw ? cw[i] : 1.0);
+            }
             if (degenerate) {
                 b = i % PB_BUCKETS; // sort.c:66-75 round-robin
             } else {
@@ -297,11 +299,16 @@ __global__ void k_class_start(int nclass, const PbSeg *__restrict__ segs, uint32
     cs[nclass] = run;
 }
 
-template <bool PAYLOAD>
+// MODE 0: ord[dst] = source position; 1: move the planar payload (planes + weight + index); 2: write the source
+// pixel as an interleaved (c0, c1, c2, w) record at dst - the bucket-sorted copy the per-bucket sums stream through
+// (one full 32-byte sector per pixel: no more traffic than the 4-byte index it replaces, and the sums that follow
+// read sequentially instead of gathering)
+enum { SCAT_ORD = 0, SCAT_PLANES = 1, SCAT_SORTED = 2 };
+template <int MODE>
 __global__ void k_scatter(ClsCtx cc, int nclass, const PbSeg *__restrict__ segs, uint32_t tiles_cap,
                           const uint32_t *__restrict__ tile_hist, const uint32_t *__restrict__ class_start,
                           uint32_t *__restrict__ ord, PbPlanes src0, PbPlanes src1, PbPlanes dst0, PbPlanes dst1,
-                          bool src_is_identity) {
+                          bool src_is_identity, double *__restrict__ sorted) {
     extern __shared__ uint32_t s_cnt[];
     const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int seg = blockIdx.y;
@@ -341,12 +348,16 @@ __global__ void k_scatter(ClsCtx cc, int nclass, const PbSeg *__restrict__ segs,
             __syncwarp();
             if (valid) {
                 const uint32_t dst = base + rank;
-                if (PAYLOAD) {
+                if (MODE == SCAT_PLANES) {
                     D.c[0][dst] = S.c[0][pos];
                     D.c[1][dst] = S.c[1][pos];
                     D.c[2][dst] = S.c[2][pos];
                     if (S.w) D.w[dst] = S.w[pos];
                     if (D.idx) D.idx[dst] = src_is_identity ? pos : S.idx[pos];
+                } else if (MODE == SCAT_SORTED) {
+                    double2 *o = reinterpret_cast<double2 *>(sorted) + 2 * (size_t)dst;
+                    o[0] = make_double2(S.c[0][pos], S.c[1][pos]);
+                    o[1] = make_double2(S.c[2][pos], S.w ? S.w[pos] : 1.0);
                 } else {
                     ord[dst] = pos;
                 }
@@ -561,11 +572,30 @@ void pb_launch_scatter_ord(int cls_mode, int nclass, const PbSeg *d_segs, int ns
     dim3 g((tiles_cap + warps - 1) / warps, nseg);
     PbPlanes none{};
     if ((size_t)warps * (nclass + 1) * 4 > 32 * 1024)
-        PB_CUDA_OK(cudaFuncSetAttribute(k_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        PB_CUDA_OK(cudaFuncSetAttribute(k_scatter<SCAT_ORD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         warps * (nclass + 1) * 4));
     { PbProfScope _prof("k_scatter_ord", st);
-    k_scatter<false><<<g, warps * 32, (size_t)warps * (nclass + 1) * 4, st>>>(
-        cc, nclass, d_segs, tiles_cap, d_tile_hist, d_class_start, d_ord, none, none, none, none, false);
+    k_scatter<SCAT_ORD><<<g, warps * 32, (size_t)warps * (nclass + 1) * 4, st>>>(
+        cc, nclass, d_segs, tiles_cap, d_tile_hist, d_class_start, d_ord, none, none, none, none, false, nullptr);
+    }
+    PB_CUDA_OK(cudaGetLastError());
+}
+
+void pb_launch_scatter_sorted(int cls_mode, int nclass, const PbPlanes src[2], const PbSeg *d_segs, int nseg, uint32_t max_n,
+                              const uint16_t *d_bucket, const PbSplit *d_split, const uint8_t *d_lut,
+                              const uint32_t *d_tile_hist, const uint32_t *d_class_start, double *d_sorted, cudaStream_t st) {
+    if (nseg <= 0) return;
+    const uint32_t tiles_cap = (uint32_t)pb_scatter_tiles(max_n ? max_n : 1);
+    const int warps = scatter_warps(nclass);
+    ClsCtx cc{cls_mode, d_bucket, d_split, d_lut};
+    dim3 g((tiles_cap + warps - 1) / warps, nseg);
+    PbPlanes none{};
+    if ((size_t)warps * (nclass + 1) * 4 > 32 * 1024)
+        PB_CUDA_OK(cudaFuncSetAttribute(k_scatter<SCAT_SORTED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        warps * (nclass + 1) * 4));
+    { PbProfScope _prof("k_scatter_sorted", st);
+    k_scatter<SCAT_SORTED><<<g, warps * 32, (size_t)warps * (nclass + 1) * 4, st>>>(
+        cc, nclass, d_segs, tiles_cap, d_tile_hist, d_class_start, nullptr, src[0], src[1], none, none, false, d_sorted);
     }
     PB_CUDA_OK(cudaGetLastError());
 }
@@ -586,9 +616,9 @@ void pb_launch_scatter_payload(int cls_mode, int nclass, const PbPlanes src[2], 
                                       src_is_identity);
     } else {
         PbProfScope _prof("k_scatter_payload", st);
-        k_scatter<true><<<g, warps * 32, (size_t)warps * (nclass + 1) * 4, st>>>(
+        k_scatter<SCAT_PLANES><<<g, warps * 32, (size_t)warps * (nclass + 1) * 4, st>>>(
             cc, nclass, d_segs, tiles_cap, d_tile_hist, d_class_start, nullptr, src[0], src[1], dst[0], dst[1],
-            src_is_identity);
+            src_is_identity, nullptr);
     }
     PB_CUDA_OK(cudaGetLastError());
 }

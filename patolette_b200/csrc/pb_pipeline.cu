@@ -35,6 +35,7 @@ std::mutex g_call_mu;
 int g_device = 0;
 int g_overlap_override = -1; // patolette_b200_set_option "overlap": -1 default, 0 off, 1 on
 bool g_nn_grid = true;       // patolette_b200_set_option "nn_grid": candidate-list 1-NN (pb_nngrid.cu) vs brute force
+bool g_sorted_payload = true; // "sorted_payload": the bucket sort writes the interleaved pixels themselves (sequential per-bucket sums) instead of indices (gathers)
 
 // ---- chain sharding (patolette_b200_set_sharding) --------------------------------------------------
 // Every rank holds the whole image and runs the same host logic; the ordered sums - the bulk of the step -
@@ -259,7 +260,8 @@ size_t principal_quantizer(size_t K, const CellMoments &m, size_t *q) {
     size_t k_out = 1;
     l_chain(L, ls, 1, N, q);
     const size_t kmax = std::min(max_k, K);
-    const int threads = g_gq_threads > 0 ? g_gq_threads : pb_hostpool_default_threads();
+    // (ranks of an image-sharded job share the host's cores: each takes its share)
+    const int threads = g_gq_threads > 0 ? g_gq_threads : std::max(1, pb_hostpool_default_threads() / std::max(1, pb_nccl_world()));
     for (size_t k = 2; k <= kmax; k++) {
         if (gq_should_terminate(q, k_out + 1, axis, m)) break;
         E2 = E;
@@ -498,12 +500,17 @@ struct Quantizer {
         pb_prof_next_bytes(24.0 * N);
         pb_launch_dots_minmax(gq, segs.p, 1, (uint32_t)N, axes.p, split.p, sm_count, st);
         pb_prof_next_bytes(26.0 * N);
-        pb_launch_buckets(gq, segs.p, 1, (uint32_t)N, axes.p, split.p, bucket.p, aos.p, sm_count, st);
+        pb_launch_buckets(gq, segs.p, 1, (uint32_t)N, axes.p, split.p, bucket.p, g_sorted_payload ? nullptr : aos.p, sm_count, st);
         pb_launch_class_rank(PB_CLS_BUCKET, PB_BUCKETS, segs.p, 1, (uint32_t)N, max_tiles, bucket.p, split.p, lut.p,
                              tile_hist.p, cstart_b.p, st);
-        pb_launch_scatter_ord(PB_CLS_BUCKET, PB_BUCKETS, segs.p, 1, (uint32_t)N, bucket.p, split.p, lut.p,
-                              tile_hist.p, cstart_b.p, ord.p, st);
-        pb_launch_bucket_chains_gq(aos.p, ord.p, cstart_b.p, bsums.p, st);
+        if (g_sorted_payload) {
+            pb_prof_next_bytes((24.0 + 2.0 + 32.0) * N);
+            pb_launch_scatter_sorted(PB_CLS_BUCKET, PB_BUCKETS, gq, segs.p, 1, (uint32_t)N, bucket.p, split.p, lut.p, tile_hist.p,
+                                     cstart_b.p, aos.p, st);
+        } else
+            pb_launch_scatter_ord(PB_CLS_BUCKET, PB_BUCKETS, segs.p, 1, (uint32_t)N, bucket.p, split.p, lut.p,
+                                  tile_hist.p, cstart_b.p, ord.p, st);
+        pb_launch_bucket_chains_gq(aos.p, g_sorted_payload ? nullptr : ord.p, cstart_b.p, bsums.p, st);
         std::vector<double> hs(PB_BUCKETS * 10);
         std::vector<uint32_t> hcs(PB_BUCKETS + 1);
         d2h(hs.data(), bsums.p, hs.size());
@@ -672,18 +679,23 @@ struct Quantizer {
                 PB_CUDA_OK(cudaMemcpyAsync(d.axes, B.haxes, 3 * nb * sizeof(double), cudaMemcpyHostToDevice, d.st));
                 pb_prof_next_bytes(24.0 * B.tot_n);
                 pb_launch_dots_minmax(bufs, d.segs, nb, max_n, d.axes, d.split, sm_count, d.st);
-                pb_prof_next_bytes((26.0 + 32.0) * B.tot_n);
-                pb_launch_buckets(bufs, d.segs, nb, max_n, d.axes, d.split, bucket.p, aos.p, sm_count, d.st);
+                pb_prof_next_bytes((26.0 + (g_sorted_payload ? 0.0 : 32.0)) * B.tot_n);
+                pb_launch_buckets(bufs, d.segs, nb, max_n, d.axes, d.split, bucket.p, g_sorted_payload ? nullptr : aos.p, sm_count, d.st);
                 break;
             case 1:
                 pb_launch_class_rank(PB_CLS_BUCKET, PB_BUCKETS, d.segs, nb, max_n, max_tiles, bucket.p, d.split, lut.p,
                                      d.tile_hist, d.cstart_b, d.st);
-                pb_launch_scatter_ord(PB_CLS_BUCKET, PB_BUCKETS, d.segs, nb, max_n, bucket.p, d.split, lut.p, d.tile_hist,
-                                      d.cstart_b, ord.p, d.st);
+                if (g_sorted_payload) {
+                    pb_prof_next_bytes((bpp + 2.0 + 32.0) * B.tot_n);
+                    pb_launch_scatter_sorted(PB_CLS_BUCKET, PB_BUCKETS, bufs, d.segs, nb, max_n, bucket.p, d.split, lut.p, d.tile_hist,
+                                             d.cstart_b, aos.p, d.st);
+                } else
+                    pb_launch_scatter_ord(PB_CLS_BUCKET, PB_BUCKETS, d.segs, nb, max_n, bucket.p, d.split, lut.p, d.tile_hist,
+                                          d.cstart_b, ord.p, d.st);
                 break;
             case 2:
-                pb_prof_next_bytes((bpp + 4.0) * B.tot_n);
-                pb_launch_bucket_chains_lq(aos.p, d.segs, nb, weighted, ord.p, d.cstart_b, d.bsums, d.st);
+                pb_prof_next_bytes(32.0 * B.tot_n);
+                pb_launch_bucket_chains_lq(aos.p, d.segs, nb, weighted, g_sorted_payload ? nullptr : ord.p, d.cstart_b, d.bsums, d.st);
                 pb_launch_split_select(d.bsums, d.cstart_b, nb, d.split, d.st);
                 break;
             case 3:
@@ -1335,6 +1347,7 @@ int patolette_b200_set_sharding(int rank, int world, patolette_b200_allgather_fn
 int patolette_b200_set_option(const char *name, long long value) {
     if (!name) return -1;
     if (!strcmp(name, "dump_cap")) { pb_ordered_set_dump_cap(value); return 0; }
+    if (!strcmp(name, "sorted_payload")) { g_sorted_payload = value != 0; return 0; }
     if (!strcmp(name, "gq_chain_cta")) { pb_chain_set_gq_cta(value != 0); return 0; }
     if (!strcmp(name, "raw_moments")) { pb_ordered_set_raw_moments(value != 0); return 0; }
     if (!strcmp(name, "fused_pass")) { pb_ordered_set_fused(value != 0); return 0; }

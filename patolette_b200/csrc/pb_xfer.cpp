@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "pb_error.h"
+#include "pb_nccl.h"
 
 namespace {
 
@@ -44,6 +45,7 @@ bool is_pinned(const void *p) {
 
 int worker_count() {
     unsigned hc = std::thread::hardware_concurrency();
+    hc /= (unsigned)std::max(1, pb_nccl_world()); // ranks of an image-sharded job share the host's cores
     int n = hc >= 16 ? 8 : (hc >= 8 ? 4 : 2);
     return std::min(n, MAX_LANES);
 }
