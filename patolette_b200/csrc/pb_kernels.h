@@ -92,6 +92,7 @@ void pb_launch_scatter_ord(int cls_mode, int nclass, const PbSeg *d_segs, int ns
                            cudaStream_t st);
 // sorted[dst] = (c0, c1, c2, w) of the source pixel: the bucket-sorted interleaved copy the per-bucket sums read
 // sequentially (d_ord == nullptr in the pb_launch_bucket_chains_* calls below)
+void pb_scatter_set_cta(bool on); // test knob
 void pb_launch_scatter_sorted(int cls_mode, int nclass, const PbPlanes src[2], const PbSeg *d_segs, int nseg, uint32_t max_n,
                               const uint16_t *d_bucket, const PbSplit *d_split, const uint8_t *d_lut,
                               const uint32_t *d_tile_hist, const uint32_t *d_class_start, double *d_sorted, cudaStream_t st);

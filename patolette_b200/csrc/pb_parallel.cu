@@ -366,6 +366,115 @@ __global__ void k_scatter(ClsCtx cc, int nclass, const PbSeg *__restrict__ segs,
     }
 }
 
+
+// Bucket-sorted interleaved copy, CTA-level: the warp-level walk above writes every pixel's 32-byte record on its
+// own, and with 512 destinations per tile the partially written lines fall out of L2 before their neighbours
+// arrive (measured 1.4 TB/s).  Here a CTA sorts a tile of two scatter tiles (4096 pixels) in shared memory first -
+// payload staged planar, a stable rank per pixel (per-warp class histograms, a prefix over the warps, the
+// __match_any walk) turned into a local permutation - and then writes the tile's pixels in SORTED order: the
+// members of one bucket leave as one contiguous run (8 pixels = 256 bytes on average).
+constexpr int SS_WARPS = 8, SS_THREADS = 32 * SS_WARPS, SS_TILE = 2 * SC_TILE, SS_ROWS = SS_TILE / 32 / SS_WARPS; // 16 rows per warp
+struct SsSmem {
+    double pay[4][SS_TILE];            // planar payload of the tile (c0, c1, c2, w)
+    uint32_t cnt[SS_WARPS][PB_BUCKETS]; // per-warp class counts, then running local slots
+    uint32_t lstart[PB_BUCKETS + 1];   // first local slot of every class
+    uint32_t gbase[PB_BUCKETS];        // first global position of the tile's members of every class
+    uint16_t perm[SS_TILE];            // local source index of every local slot
+    uint16_t cls[SS_TILE];             // class of every local slot
+};
+__global__ void __launch_bounds__(SS_THREADS) k_scatter_sorted_cta(const uint16_t *__restrict__ bucket, const PbSeg *__restrict__ segs,
+                                                                  const uint32_t *__restrict__ tile_hist,
+                                                                  const uint32_t *__restrict__ class_start, PbPlanes src0,
+                                                                  PbPlanes src1, double *__restrict__ sorted) {
+    extern __shared__ __align__(16) unsigned char ss_raw[];
+    SsSmem &sm = *reinterpret_cast<SsSmem *>(ss_raw);
+    const int seg = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const PbSeg sg = segs[seg];
+    const uint32_t beg = blockIdx.x * SS_TILE;
+    if (beg >= sg.n) return;
+    const uint32_t cnt_t = min((uint32_t)SS_TILE, sg.n - beg);
+    const PbPlanes &S = sg.buf ? src1 : src0;
+    const size_t g0 = (size_t)sg.lo + beg;
+    // global bases of the tile's first scatter tile (the second one continues them) + zeroed counters
+    {
+        const uint32_t *hist = tile_hist + ((size_t)sg.tbase + 2 * (size_t)blockIdx.x) * PB_BUCKETS;
+        const uint32_t *cst = class_start + (size_t)seg * (PB_BUCKETS + 1);
+        for (int c = tid; c < PB_BUCKETS; c += SS_THREADS) sm.gbase[c] = hist[c] + cst[c];
+        for (int i = tid; i < SS_WARPS * PB_BUCKETS; i += SS_THREADS) (&sm.cnt[0][0])[i] = 0u;
+    }
+    // payload -> shared memory (coalesced), class ids of this warp's 16 rows -> registers
+#pragma unroll 4
+    for (uint32_t i = tid; i < cnt_t; i += SS_THREADS) {
+        sm.pay[0][i] = S.c[0][g0 + i];
+        sm.pay[1][i] = S.c[1][g0 + i];
+        sm.pay[2][i] = S.c[2][g0 + i];
+        sm.pay[3][i] = S.w ? S.w[g0 + i] : 1.0;
+    }
+    uint32_t cls[SS_ROWS];
+#pragma unroll
+    for (int r = 0; r < SS_ROWS; r++) {
+        const uint32_t i = (warp * SS_ROWS + r) * 32 + lane;
+        cls[r] = i < cnt_t ? (uint32_t)bucket[g0 + i] : 0xffffu;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < SS_ROWS; r++)
+        if (cls[r] != 0xffffu) atomicAdd(&sm.cnt[warp][cls[r]], 1u);
+    __syncthreads();
+    // per class: exclusive prefix over the warps (in place) and the class total
+    for (int c = tid; c < PB_BUCKETS; c += SS_THREADS) {
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < SS_WARPS; w++) { const uint32_t v = sm.cnt[w][c]; sm.cnt[w][c] = run; run += v; }
+        sm.lstart[c + 1] = run; // totals, scanned below
+    }
+    if (tid == 0) sm.lstart[0] = 0;
+    __syncthreads();
+    if (warp == 0) { // inclusive scan of the 512 totals: 16 per lane + a warp scan
+        uint32_t v[PB_BUCKETS / 32], s = 0;
+#pragma unroll
+        for (int k = 0; k < PB_BUCKETS / 32; k++) { s += sm.lstart[1 + lane * (PB_BUCKETS / 32) + k]; v[k] = s; }
+        uint32_t incl = s;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
+        }
+        const uint32_t off = incl - s;
+#pragma unroll
+        for (int k = 0; k < PB_BUCKETS / 32; k++) sm.lstart[1 + lane * (PB_BUCKETS / 32) + k] = v[k] + off;
+    }
+    __syncthreads();
+    for (int i = tid; i < SS_WARPS * PB_BUCKETS; i += SS_THREADS) (&sm.cnt[0][0])[i] += sm.lstart[i % PB_BUCKETS]; // running local slots
+    __syncthreads();
+    // the stable ranking walk: every warp over its own rows, in order
+#pragma unroll
+    for (int r = 0; r < SS_ROWS; r++) {
+        const uint32_t i = (warp * SS_ROWS + r) * 32 + lane;
+        if ((uint32_t)(warp * SS_ROWS + r) * 32 >= cnt_t) break; // warp-uniform
+        const uint32_t c = cls[r];
+        const uint32_t peers = __match_any_sync(0xffffffffu, c);
+        const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+        uint32_t base = 0;
+        if (c != 0xffffu) base = sm.cnt[warp][c];
+        __syncwarp();
+        if (c != 0xffffu && rank == 0) sm.cnt[warp][c] = base + __popc(peers);
+        __syncwarp();
+        if (c != 0xffffu) {
+            sm.perm[base + rank] = (uint16_t)i;
+            sm.cls[base + rank] = (uint16_t)c;
+        }
+    }
+    __syncthreads();
+    // write out in sorted order: consecutive slots of one class -> consecutive global positions
+    double2 *out = reinterpret_cast<double2 *>(sorted);
+    for (uint32_t t = tid; t < cnt_t; t += SS_THREADS) {
+        const uint32_t c = sm.cls[t], i = sm.perm[t];
+        const size_t dst = (size_t)sm.gbase[c] + (t - sm.lstart[c]);
+        out[2 * dst] = make_double2(sm.pay[0][i], sm.pay[1][i]);
+        out[2 * dst + 1] = make_double2(sm.pay[2][i], sm.pay[3][i]);
+    }
+}
+
 // Two-class payload scatter (the split partition, local.c:219-245): ranks come from two ballots per row of
 // 32 positions and two warp-uniform running offsets in registers - no shared-memory counters, no
 // __match_any, no __syncwarp - and four rows are loaded before any is stored (memory-level parallelism).
@@ -581,11 +690,22 @@ void pb_launch_scatter_ord(int cls_mode, int nclass, const PbSeg *d_segs, int ns
     PB_CUDA_OK(cudaGetLastError());
 }
 
+static bool g_scatter_cta = true; // "scatter_cta": CTA-level sort in shared memory for the bucket-sorted copy (default) or the warp-level walk
+void pb_scatter_set_cta(bool on) { g_scatter_cta = on; }
+
 void pb_launch_scatter_sorted(int cls_mode, int nclass, const PbPlanes src[2], const PbSeg *d_segs, int nseg, uint32_t max_n,
                               const uint16_t *d_bucket, const PbSplit *d_split, const uint8_t *d_lut,
                               const uint32_t *d_tile_hist, const uint32_t *d_class_start, double *d_sorted, cudaStream_t st) {
     if (nseg <= 0) return;
     const uint32_t tiles_cap = (uint32_t)pb_scatter_tiles(max_n ? max_n : 1);
+    if (cls_mode == PB_CLS_BUCKET && nclass == PB_BUCKETS && g_scatter_cta) {
+        PB_CUDA_OK(cudaFuncSetAttribute(k_scatter_sorted_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SsSmem)));
+        PbProfScope _prof("k_scatter_sorted", st);
+        k_scatter_sorted_cta<<<dim3((tiles_cap + 1) / 2, nseg), SS_THREADS, sizeof(SsSmem), st>>>(d_bucket, d_segs, d_tile_hist, d_class_start,
+                                                                                          src[0], src[1], d_sorted);
+        PB_CUDA_OK(cudaGetLastError());
+        return;
+    }
     const int warps = scatter_warps(nclass);
     ClsCtx cc{cls_mode, d_bucket, d_split, d_lut};
     dim3 g((tiles_cap + warps - 1) / warps, nseg);

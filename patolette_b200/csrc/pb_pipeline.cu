@@ -1347,6 +1347,7 @@ int patolette_b200_set_sharding(int rank, int world, patolette_b200_allgather_fn
 int patolette_b200_set_option(const char *name, long long value) {
     if (!name) return -1;
     if (!strcmp(name, "dump_cap")) { pb_ordered_set_dump_cap(value); return 0; }
+    if (!strcmp(name, "scatter_cta")) { pb_scatter_set_cta(value != 0); return 0; }
     if (!strcmp(name, "sorted_payload")) { g_sorted_payload = value != 0; return 0; }
     if (!strcmp(name, "gq_chain_cta")) { pb_chain_set_gq_cta(value != 0); return 0; }
     if (!strcmp(name, "raw_moments")) { pb_ordered_set_raw_moments(value != 0); return 0; }

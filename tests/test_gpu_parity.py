@@ -308,7 +308,7 @@ def _cluster_tree(lib, fn, planar, n, K, wts=None):
     return labels, centers[:cnt.value].copy(), cnt.value, gq.value
 
 
-@pytest.mark.parametrize("route", ["default", "fused", "no_raw_moments", "gq_chain_warp", "ord_gather", "classic_summary", "no_term_dump", "one_slot", "no_overlap", "overlap"])
+@pytest.mark.parametrize("route", ["default", "fused", "no_raw_moments", "gq_chain_warp", "ord_gather", "scatter_warp", "classic_summary", "no_term_dump", "one_slot", "no_overlap", "overlap"])
 def test_cluster_tree_1p5M_every_route_matches_oracle(cuda_lib, oracle, route):
     """1.5 M pixels, K=48 (clusters long enough for the group records and the two-level resolve, hovering
     off-diagonal sums, two-parity records): the ordered-sum machinery has several routes to the same bits -
@@ -318,7 +318,7 @@ def test_cluster_tree_1p5M_every_route_matches_oracle(cuda_lib, oracle, route):
     side = int(np.ceil(np.sqrt(n)))
     planar = np.asfortranarray(image_like_colors(side, side, 17)[:n] * 0.5 + 0.5 * uniform_colors(side, side, 18)[:n])
     want = _cluster_tree(oracle.lib, "orc_quantize_clusters", planar, n, K)
-    opts = {"default": [], "fused": [(b"fused_pass", 1)], "no_raw_moments": [(b"raw_moments", 0)], "gq_chain_warp": [(b"gq_chain_cta", 0)], "ord_gather": [(b"sorted_payload", 0)], "classic_summary": [(b"fast_summary", 0)], "no_term_dump": [(b"dump_cap", 0)], "one_slot": [(b"dump_cap", 1)],
+    opts = {"default": [], "fused": [(b"fused_pass", 1)], "no_raw_moments": [(b"raw_moments", 0)], "gq_chain_warp": [(b"gq_chain_cta", 0)], "ord_gather": [(b"sorted_payload", 0)], "scatter_warp": [(b"scatter_cta", 0)], "classic_summary": [(b"fast_summary", 0)], "no_term_dump": [(b"dump_cap", 0)], "one_slot": [(b"dump_cap", 1)],
             "no_overlap": [(b"overlap", 0)], "overlap": [(b"overlap", 1)]}[route]
     try:
         for k, v in opts:
@@ -332,6 +332,7 @@ def test_cluster_tree_1p5M_every_route_matches_oracle(cuda_lib, oracle, route):
         cuda_lib.patolette_b200_set_option(b"raw_moments", 1)
         cuda_lib.patolette_b200_set_option(b"gq_chain_cta", 1)
         cuda_lib.patolette_b200_set_option(b"sorted_payload", 1)
+        cuda_lib.patolette_b200_set_option(b"scatter_cta", 1)
     assert got[2:] == want[2:], "cluster counts differ"
     assert np.array_equal(got[0], want[0]), "cluster membership differs"
     assert_same_floats(got[1], want[1], "cluster centres")
