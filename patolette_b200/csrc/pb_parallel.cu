@@ -369,11 +369,14 @@ __global__ void k_scatter(ClsCtx cc, int nclass, const PbSeg *__restrict__ segs,
 
 // Bucket-sorted interleaved copy, CTA-level: the warp-level walk above writes every pixel's 32-byte record on its
 // own, and with 512 destinations per tile the partially written lines fall out of L2 before their neighbours
-// arrive (measured 1.4 TB/s).  Here a CTA sorts a tile of two scatter tiles (4096 pixels) in shared memory first -
+// arrive (measured 1.4 TB/s).  Here a CTA sorts a tile (one scatter tile, 2048 pixels) in shared memory first -
 // payload staged planar, a stable rank per pixel (per-warp class histograms, a prefix over the warps, the
 // __match_any walk) turned into a local permutation - and then writes the tile's pixels in SORTED order: the
-// members of one bucket leave as one contiguous run (8 pixels = 256 bytes on average).
-constexpr int SS_WARPS = 8, SS_THREADS = 32 * SS_WARPS, SS_TILE = 2 * SC_TILE, SS_ROWS = SS_TILE / 32 / SS_WARPS; // 16 rows per warp
+// members of one bucket leave as one contiguous run (4 pixels = one 128-byte line on average).
+#ifndef PB_SS_TILES
+#define PB_SS_TILES 1 // scatter tiles per CTA: 1 -> 92 KB of shared memory, two CTAs per SM (one CTA's phases overlap the other's)
+#endif
+constexpr int SS_WARPS = 8, SS_THREADS = 32 * SS_WARPS, SS_TILE = PB_SS_TILES * SC_TILE, SS_ROWS = SS_TILE / 32 / SS_WARPS;
 struct SsSmem {
     double pay[4][SS_TILE];            // planar payload of the tile (c0, c1, c2, w)
     uint32_t cnt[SS_WARPS][PB_BUCKETS]; // per-warp class counts, then running local slots
@@ -397,7 +400,7 @@ __global__ void __launch_bounds__(SS_THREADS) k_scatter_sorted_cta(const uint16_
     const size_t g0 = (size_t)sg.lo + beg;
     // global bases of the tile's first scatter tile (the second one continues them) + zeroed counters
     {
-        const uint32_t *hist = tile_hist + ((size_t)sg.tbase + 2 * (size_t)blockIdx.x) * PB_BUCKETS;
+        const uint32_t *hist = tile_hist + ((size_t)sg.tbase + PB_SS_TILES * (size_t)blockIdx.x) * PB_BUCKETS;
         const uint32_t *cst = class_start + (size_t)seg * (PB_BUCKETS + 1);
         for (int c = tid; c < PB_BUCKETS; c += SS_THREADS) sm.gbase[c] = hist[c] + cst[c];
         for (int i = tid; i < SS_WARPS * PB_BUCKETS; i += SS_THREADS) (&sm.cnt[0][0])[i] = 0u;
@@ -701,7 +704,7 @@ void pb_launch_scatter_sorted(int cls_mode, int nclass, const PbPlanes src[2], c
     if (cls_mode == PB_CLS_BUCKET && nclass == PB_BUCKETS && g_scatter_cta) {
         PB_CUDA_OK(cudaFuncSetAttribute(k_scatter_sorted_cta, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SsSmem)));
         PbProfScope _prof("k_scatter_sorted", st);
-        k_scatter_sorted_cta<<<dim3((tiles_cap + 1) / 2, nseg), SS_THREADS, sizeof(SsSmem), st>>>(d_bucket, d_segs, d_tile_hist, d_class_start,
+        k_scatter_sorted_cta<<<dim3((tiles_cap + PB_SS_TILES - 1) / PB_SS_TILES, nseg), SS_THREADS, sizeof(SsSmem), st>>>(d_bucket, d_segs, d_tile_hist, d_class_start,
                                                                                           src[0], src[1], d_sorted);
         PB_CUDA_OK(cudaGetLastError());
         return;
