@@ -155,6 +155,9 @@ PB200_API size_t patolette_b200_profile_json(char *buf, size_t cap);
  * through a two-parity record, SM cycles of the resolving warps in {scan walk, two-parity records,
  * replays}, record groups loaded, cycles of the slowest resolving warp, 3 spare. */
 PB200_API int patolette_b200_ordered_counts(unsigned long long *out16, int reset);
+/* Split-selection statistics since the last reset (pb_certify.cu): {clusters whose optimal bucket was certified from
+ * unordered per-bucket sums, certificates refused, clusters re-evaluated through the exact route, spare}. */
+PB200_API int patolette_b200_split_counts(unsigned long long *out4, int reset);
 /* Host-only stage entry (no GPU needed): the GQ dynamic programme (quantize/global.c:189-298) on 512 x 10
  * per-bucket sums {sum c[3], sum |c|^2, sum c_r*c_s (0,0)(0,1)(1,1)(0,2)(1,2)(2,2)} and 513 class starts.
  * Writes the cut list q[0..cells] into cuts16, returns the cell count (0 on failure). */
@@ -173,6 +176,9 @@ PB200_API int patolette_b200_set_sharding(int rank, int world, patolette_b200_al
  * two-stream half-batch evaluation of the split loop (-1 default, 0 off, 1 on), "gq_threads" = host threads of the GQ
  * dynamic programme (0 default), "nn_grid" / "dither_grid" = nearest
  * map / the dither's per-step search through per-cell candidate lists (1, default) or brute force (0).
+ * "split_certify" = how a split finds its optimal bucket (quantize/local.c:102-177): 1 (default) unordered per-bucket
+ * sums plus a proof that the reference's argmax is the same, refused clusters re-evaluated exactly; 0 the exact route
+ * for every cluster (bucket sort + sequential per-bucket chains); 2 certified route with every certificate refused.
  * "allow_jacobi" = 1 lets a built-in Jacobi solver stand in when no LAPACK dsyev_ can be resolved (default 0: such
  * a call fails with exit code -1, because eigenvector signs - hence palette order - would differ from the reference).
  * Returns 0, -1 if unknown. */

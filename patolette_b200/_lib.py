@@ -46,6 +46,7 @@ SYMBOLS = {
     "patolette_b200_set_stream": (C.c_int, [C.c_void_p, C.c_int]),
     "patolette_b200_release_cache": (C.c_size_t, []),
     "patolette_b200_ordered_counts": (C.c_int, [C.c_void_p, C.c_int]),
+    "patolette_b200_split_counts": (C.c_int, [C.c_void_p, C.c_int]),
     "patolette_b200_ordered_chain_debug": (C.c_int, [C.c_void_p, C.c_int]),
     "patolette_b200_set_option": (C.c_int, [C.c_char_p, C.c_longlong]),
     "patolette_b200_set_sharding": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p]),

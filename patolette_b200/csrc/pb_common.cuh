@@ -22,7 +22,7 @@ struct PbSeg {
     uint32_t buf;   // which ping-pong buffer (0/1) holds it
     uint32_t tbase; // first scatter tile of this segment in the packed per-batch tile table
     uint32_t bbase; // first ordered-sum block of this segment in the packed per-batch block table
-    uint32_t pad;
+    uint32_t pad;   // in: E with sum(w) < 2^E (weighted certified route); out (children): PB_ROUTE_* of the split that made them
 };
 
 // Planar working set: three colour planes, optional weight plane, original index.
@@ -47,6 +47,23 @@ struct PbSplit {
     uint32_t split;      // optimal bucket index          local.c:171
     uint32_t nleft;      // pixels with bucket <= split
     uint32_t degenerate; // max - min < DELTA -> round-robin buckets (sort.c:61-79)
+    uint32_t pad;        // PB_ROUTE_*: how `split` was found (copied into the children's PbSeg::pad)
+};
+
+// How the optimal bucket of a split was obtained (pb_certify.cu): the exact route reproduces the reference's
+// per-bucket sums bit for bit; the certified route forms them in any order and proves that the argmax is the same.
+enum { PB_ROUTE_EXACT = 0, PB_ROUTE_CERTIFIED = 1, PB_ROUTE_REFUSED = 2 };
+
+// Per-segment bucket table of the certified route (zeroed before use): sums of w*c_j in ANY order, pixel counts,
+// sum floor(w) and the number of pixels whose weight could make size_t += double round up (weighted runs),
+// bit patterns of max |c_j| over the segment, and a flag for weights the certificate cannot handle.
+struct PbHist {
+    double s[3][PB_BUCKETS];
+    unsigned long long sz[PB_BUCKETS];
+    uint32_t cnt[PB_BUCKETS];
+    uint32_t risky[PB_BUCKETS];
+    unsigned long long absmax[3];
+    uint32_t bad;
     uint32_t pad;
 };
 

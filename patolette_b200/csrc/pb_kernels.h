@@ -70,6 +70,13 @@ void pb_launch_dots_minmax(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg
 void pb_launch_buckets(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t max_n,
                        const double *d_axes, PbSplit *d_split, uint16_t *d_bucket, double *d_aos, int sm_count,
                        cudaStream_t st);
+// Certified route (pb_certify.cu): bucket ids as pb_launch_buckets plus per-bucket sums in any order (no sort),
+// then the proof that their argmax is the reference's; PbSplit::pad says whether it succeeded.
+void pb_launch_buckets_hist(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t max_n, bool weighted,
+                            const double *d_axes, PbSplit *d_split, uint16_t *d_bucket, PbHist *d_hist, int sm_count,
+                            cudaStream_t st);
+void pb_launch_split_certify(const PbHist *d_hist, int nseg, bool weighted, PbSplit *d_split, int distrust, cudaStream_t st);
+void pb_certify_counts(unsigned long long out[4], bool reset); // {certified, refused, -, -} since the last reset
 void pb_launch_split_select(const double *d_bucket_sums, const uint32_t *d_class_start, int nseg,
                             PbSplit *d_split, cudaStream_t st);
 

@@ -23,6 +23,7 @@ __global__ void k_split_init(PbSplit *sp, int nseg) {
         sp[i].mx_enc = 0ULL;
         sp[i].split = 0;
         sp[i].nleft = 0;
+        sp[i].pad = PB_ROUTE_EXACT;
     }
 }
 
@@ -546,8 +547,8 @@ __global__ void k_make_children(const PbSeg *__restrict__ segs, int nseg, const 
     // each child gets an ordered-sum block region as large as its parent's (its own size is only
     // known on the device): regions of a batch stay disjoint and total 2 * sum(parent blocks + 1)
     const uint32_t pb = (sg.n + 511u) / 512u + 1u;
-    children[2 * i] = PbSeg{sg.lo, nl, sg.buf ^ 1u, 0u, 2u * sg.bbase, 0u};
-    children[2 * i + 1] = PbSeg{sg.lo + nl, sg.n - nl, sg.buf ^ 1u, 0u, 2u * sg.bbase + pb, 0u};
+    children[2 * i] = PbSeg{sg.lo, nl, sg.buf ^ 1u, 0u, 2u * sg.bbase, sp[i].pad};
+    children[2 * i + 1] = PbSeg{sg.lo + nl, sg.n - nl, sg.buf ^ 1u, 0u, 2u * sg.bbase + pb, sp[i].pad};
 }
 
 // ---------------------------------------------------------------------------------

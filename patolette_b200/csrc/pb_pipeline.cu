@@ -35,6 +35,12 @@ std::mutex g_call_mu;
 int g_device = 0;
 int g_overlap_override = -1; // patolette_b200_set_option "overlap": -1 default, 0 off, 1 on
 bool g_nn_grid = true;       // patolette_b200_set_option "nn_grid": candidate-list 1-NN (pb_nngrid.cu) vs brute force
+// "split_certify": 1 (default) = the split's optimal bucket comes from unordered per-bucket sums plus a proof that the
+// reference's argmax is the same (pb_certify.cu), clusters whose certificate is refused are re-evaluated exactly;
+// 0 = every cluster takes the exact route (bucket sort + sequential per-bucket chains); 2 = certified route with every
+// certificate refused (tests: exercises the re-evaluation of every cluster)
+int g_split_certify = 1;
+unsigned long long g_split_redone = 0; // clusters re-evaluated through the exact route since the last reset
 bool g_sorted_payload = true; // "sorted_payload": the bucket sort writes the interleaved pixels themselves (sequential per-bucket sums) instead of indices (gathers)
 
 // ---- chain sharding (patolette_b200_set_sharding) --------------------------------------------------
@@ -359,6 +365,7 @@ struct Quantizer {
     DevArr<PbSeg> segs, children;
     DevArr<PbStats> stats;
     DevArr<PbSplit> split;
+    DevArr<PbHist> hist; // certified route: per-cluster bucket tables
     DevArr<uint8_t> lut;
     DevArr<char> oscratch; // block sums + summaries of the speculative ordered sums
     PbPlanes orig{}, bufs[2]{};
@@ -376,6 +383,7 @@ struct Quantizer {
         DevArr<PbSeg> segs, children;
         DevArr<PbStats> stats;
         DevArr<PbSplit> split;
+        DevArr<PbHist> hist;
         DevArr<char> oscratch;
         cudaStream_t st = nullptr;
         cudaEvent_t fork = nullptr;
@@ -426,6 +434,7 @@ struct Quantizer {
         children.alloc(2 * MAXB);
         stats.alloc(2 * MAXB);
         split.alloc(MAXB);
+        hist.alloc(MAXB);
         lut.alloc(PB_BUCKETS);
         if (sh.on) {
             xres.alloc(MAXB);
@@ -448,6 +457,7 @@ struct Quantizer {
             hx.children.alloc(2 * MAXB);
             hx.stats.alloc(2 * MAXB);
             hx.split.alloc(MAXB);
+            hx.hist.alloc(MAXB);
             hx.oscratch.alloc(pb_ordered_scratch_bytes(max_blocks));
             // higher priority than the first half's stream: its CTAs are placed first, which staggers the two
             // halves (one streams at full speed while the other is inside its latency-bound resolve)
@@ -585,6 +595,23 @@ struct Quantizer {
     // per-bucket sums, optimal cut, stable partition into the other ping-pong buffer, and the
     // mean / covariance / distortion of both children.  One host synchronisation per batch.
     void eval_split(HNode *const nodes[], HPair *const outs[], int count) {
+        // (chain-sharded runs keep the exact route: every rank must make the same sequence of exchanges)
+        const bool certify = g_split_certify != 0 && !sharded();
+        eval_split_impl(nodes, outs, count, !certify);
+        if (!certify) return;
+        // clusters whose certificate was refused: once more, through the exact route.  The parent's planes are
+        // intact (a partition writes the OTHER buffer), the children's ranges and scratch are simply rewritten.
+        HNode *rn[MAXB];
+        HPair *ro[MAXB];
+        int rc = 0;
+        for (int i = 0; i < count; i++)
+            if (outs[i]->valid && outs[i]->l.seg.pad == PB_ROUTE_REFUSED) { rn[rc] = nodes[i]; ro[rc++] = outs[i]; }
+        if (rc) {
+            g_split_redone += (unsigned long long)rc;
+            eval_split_impl(rn, ro, rc, true);
+        }
+    }
+    void eval_split_impl(HNode *const nodes[], HPair *const outs[], int count, bool exact) {
         struct Cand { int i; double axis[3]; };
         Cand cand[MAXB];
         int nc = 0;
@@ -647,6 +674,8 @@ struct Quantizer {
             sg = nd.seg;
             sg.tbase = B.tb;
             sg.bbase = B.bb;
+            // weighted certified route: every partial bucket size stays below sum(w) < 2^E
+            sg.pad = (weighted && !exact) ? (uint32_t)std::min(64, std::max(0, ilogb(nd.st.wsum) + 2)) : 0u;
             B.tb += (uint32_t)pb_scatter_tiles(sg.n);
             B.bb += pb_ordered_blocks(sg.n) + 1;
             memcpy(&B.haxes[3 * B.nb], cand[c].axis, sizeof cand[c].axis);
@@ -657,12 +686,12 @@ struct Quantizer {
         }
         struct Dev { // device scratch of a half
             PbSeg *segs, *children; double *axes, *bsums; PbSplit *split; PbStats *stats;
-            uint32_t *tile_hist, *cstart_b, *cstart_s; char *oscratch; size_t oscratch_n; cudaStream_t st;
+            uint32_t *tile_hist, *cstart_b, *cstart_s; char *oscratch; size_t oscratch_n; cudaStream_t st; PbHist *hist;
         };
         const Dev dev[2] = {
-            {segs.p, children.p, axes.p, bsums.p, split.p, stats.p, tile_hist.p, cstart_b.p, cstart_s.p, oscratch.p, oscratch.n, st},
+            {segs.p, children.p, axes.p, bsums.p, split.p, stats.p, tile_hist.p, cstart_b.p, cstart_s.p, oscratch.p, oscratch.n, st, hist.p},
             {hx.segs.p, hx.children.p, hx.axes.p, hx.bsums.p, hx.split.p, hx.stats.p, hx.tile_hist.p, hx.cstart_b.p, hx.cstart_s.p,
-             hx.oscratch.p, hx.oscratch.n, hx.st}};
+             hx.oscratch.p, hx.oscratch.n, hx.st, hx.hist.p}};
         if (nhalf == 2) { // the second stream starts after everything already queued on the first
             PB_CUDA_OK(cudaEventRecord(hx.fork, st));
             PB_CUDA_OK(cudaStreamWaitEvent(hx.st, hx.fork, 0));
@@ -679,10 +708,16 @@ struct Quantizer {
                 PB_CUDA_OK(cudaMemcpyAsync(d.axes, B.haxes, 3 * nb * sizeof(double), cudaMemcpyHostToDevice, d.st));
                 pb_prof_next_bytes(24.0 * B.tot_n);
                 pb_launch_dots_minmax(bufs, d.segs, nb, max_n, d.axes, d.split, sm_count, d.st);
+                if (!exact) { // certified route: bucket ids + unordered per-bucket sums, no sort
+                    pb_prof_next_bytes((bpp + 2.0) * B.tot_n);
+                    pb_launch_buckets_hist(bufs, d.segs, nb, max_n, weighted, d.axes, d.split, bucket.p, d.hist, sm_count, d.st);
+                    break;
+                }
                 pb_prof_next_bytes((26.0 + (g_sorted_payload ? 0.0 : 32.0)) * B.tot_n);
                 pb_launch_buckets(bufs, d.segs, nb, max_n, d.axes, d.split, bucket.p, g_sorted_payload ? nullptr : aos.p, sm_count, d.st);
                 break;
             case 1:
+                if (!exact) break;
                 pb_launch_class_rank(PB_CLS_BUCKET, PB_BUCKETS, d.segs, nb, max_n, max_tiles, bucket.p, d.split, lut.p,
                                      d.tile_hist, d.cstart_b, d.st);
                 if (g_sorted_payload) {
@@ -694,6 +729,10 @@ struct Quantizer {
                                           d.cstart_b, ord.p, d.st);
                 break;
             case 2:
+                if (!exact) {
+                    pb_launch_split_certify(d.hist, nb, weighted, d.split, g_split_certify == 2 ? 1 : 0, d.st);
+                    break;
+                }
                 pb_prof_next_bytes(32.0 * B.tot_n);
                 pb_launch_bucket_chains_lq(aos.p, d.segs, nb, weighted, g_sorted_payload ? nullptr : ord.p, d.cstart_b, d.bsums, d.st);
                 pb_launch_split_select(d.bsums, d.cstart_b, nb, d.split, d.st);
@@ -758,6 +797,11 @@ struct Quantizer {
                 o->l = HNode{x.seg[0], x.st[0]};
                 o->r = HNode{x.seg[1], x.st[1]};
                 o->l.owner = o->r.owner = exec[c];
+                if (exec[c] < 0 && !exact) { // replicated cluster: every rank ran its own (summation-order dependent)
+                    bool refused = false;    // certificate - all of them must agree on the re-evaluation
+                    for (int r = 0; r < sh.world; r++) refused |= hall[(size_t)r * nc + c].seg[0].pad == PB_ROUTE_REFUSED;
+                    if (refused) o->l.seg.pad = o->r.seg.pad = PB_ROUTE_REFUSED;
+                }
             }
             return;
         }
@@ -1325,6 +1369,15 @@ int patolette_b200_ordered_counts(unsigned long long *out2, int reset) {
     });
 }
 
+int patolette_b200_split_counts(unsigned long long *out4, int reset) {
+    return guarded_stage([&]() -> int {
+        pb_certify_counts(out4, reset != 0);
+        out4[2] = g_split_redone;
+        if (reset) g_split_redone = 0;
+        return 0;
+    });
+}
+
 int patolette_b200_gq_cuts(const double *bucket_sums, const unsigned int *class_start, size_t palette_size, size_t *cuts16) {
     // host only (no CUDA): the GQ dynamic programme on a table of per-bucket sums, for the CPU tests
     static thread_local CellMoments m;
@@ -1353,6 +1406,7 @@ int patolette_b200_set_option(const char *name, long long value) {
     if (!strcmp(name, "raw_moments")) { pb_ordered_set_raw_moments(value != 0); return 0; }
     if (!strcmp(name, "fused_pass")) { pb_ordered_set_fused(value != 0); return 0; }
     if (!strcmp(name, "fast_summary")) { pb_ordered_set_fast(value != 0); return 0; }
+    if (!strcmp(name, "split_certify")) { if (value < 0 || value > 2) return -1; g_split_certify = (int)value; return 0; }
     if (!strcmp(name, "overlap")) { g_overlap_override = (int)value; return 0; }
     if (!strcmp(name, "nn_grid")) { g_nn_grid = value != 0; return 0; }
     if (!strcmp(name, "gq_threads")) { g_gq_threads = (int)value; return 0; }

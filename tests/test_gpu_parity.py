@@ -308,7 +308,7 @@ def _cluster_tree(lib, fn, planar, n, K, wts=None):
     return labels, centers[:cnt.value].copy(), cnt.value, gq.value
 
 
-@pytest.mark.parametrize("route", ["default", "fused", "no_raw_moments", "gq_chain_warp", "ord_gather", "scatter_warp", "classic_summary", "no_term_dump", "one_slot", "no_overlap", "overlap"])
+@pytest.mark.parametrize("route", ["default", "split_exact", "split_redo_all", "fused", "no_raw_moments", "gq_chain_warp", "ord_gather", "scatter_warp", "classic_summary", "no_term_dump", "one_slot", "no_overlap", "overlap"])
 def test_cluster_tree_1p5M_every_route_matches_oracle(cuda_lib, oracle, route):
     """1.5 M pixels, K=48 (clusters long enough for the group records and the two-level resolve, hovering
     off-diagonal sums, two-parity records): the ordered-sum machinery has several routes to the same bits -
@@ -318,7 +318,7 @@ def test_cluster_tree_1p5M_every_route_matches_oracle(cuda_lib, oracle, route):
     side = int(np.ceil(np.sqrt(n)))
     planar = np.asfortranarray(image_like_colors(side, side, 17)[:n] * 0.5 + 0.5 * uniform_colors(side, side, 18)[:n])
     want = _cluster_tree(oracle.lib, "orc_quantize_clusters", planar, n, K)
-    opts = {"default": [], "fused": [(b"fused_pass", 1)], "no_raw_moments": [(b"raw_moments", 0)], "gq_chain_warp": [(b"gq_chain_cta", 0)], "ord_gather": [(b"sorted_payload", 0)], "scatter_warp": [(b"scatter_cta", 0)], "classic_summary": [(b"fast_summary", 0)], "no_term_dump": [(b"dump_cap", 0)], "one_slot": [(b"dump_cap", 1)],
+    opts = {"default": [], "split_exact": [(b"split_certify", 0)], "split_redo_all": [(b"split_certify", 2)], "fused": [(b"fused_pass", 1)], "no_raw_moments": [(b"raw_moments", 0)], "gq_chain_warp": [(b"gq_chain_cta", 0)], "ord_gather": [(b"sorted_payload", 0)], "scatter_warp": [(b"scatter_cta", 0)], "classic_summary": [(b"fast_summary", 0)], "no_term_dump": [(b"dump_cap", 0)], "one_slot": [(b"dump_cap", 1)],
             "no_overlap": [(b"overlap", 0)], "overlap": [(b"overlap", 1)]}[route]
     try:
         for k, v in opts:
@@ -327,6 +327,7 @@ def test_cluster_tree_1p5M_every_route_matches_oracle(cuda_lib, oracle, route):
     finally:
         cuda_lib.patolette_b200_set_option(b"dump_cap", -1)
         cuda_lib.patolette_b200_set_option(b"overlap", -1)
+        cuda_lib.patolette_b200_set_option(b"split_certify", 1)
         cuda_lib.patolette_b200_set_option(b"fast_summary", 1)
         cuda_lib.patolette_b200_set_option(b"fused_pass", 0)
         cuda_lib.patolette_b200_set_option(b"raw_moments", 1)
@@ -336,6 +337,80 @@ def test_cluster_tree_1p5M_every_route_matches_oracle(cuda_lib, oracle, route):
     assert got[2:] == want[2:], "cluster counts differ"
     assert np.array_equal(got[0], want[0]), "cluster membership differs"
     assert_same_floats(got[1], want[1], "cluster centres")
+
+
+def _split_counts(lib, reset=False):
+    c = (C.c_ulonglong * 4)()
+    assert lib.patolette_b200_split_counts(c, 1 if reset else 0) == 0
+    return {"certified": c[0], "refused": c[1], "redone": c[2]}
+
+
+@pytest.mark.parametrize("kind", ["two_blobs", "mirror", "few_colours", "constant", "two_pixels_per_bucket", "weighted_risky",
+                                  "weighted_integer", "weighted_small", "huge_offset"])
+def test_split_certificate_adversarial(cuda_lib, oracle, kind):
+    """The certified route (pb_certify.cu) finds a split's optimal bucket from unordered per-bucket sums and proves
+    that the reference's first maximum is the same; whatever it cannot prove is re-evaluated exactly.  Inputs chosen
+    against the proof: plateaus of empty buckets between two blobs (the FIRST maximum must win), mirrored data (near
+    ties of the objective), a handful of distinct colours (rows of equal buckets: the warp reductions), a constant
+    image (round-robin buckets), weights whose fraction makes size_t += double round up, integer weights, weights
+    below 1, and colours far from the origin (the error bound scales with max |c|).  Partition and centres must be
+    the oracle's bit for bit, whichever route each cluster took."""
+    n, K = 120_000, 40
+    rng = np.random.default_rng(len(kind) * 7 + 1)
+    wts = None
+    if kind == "two_blobs":
+        c = np.where(rng.random((n, 1)) < 0.4, 0.1, 0.8) + rng.random((n, 3)) * 0.02
+    elif kind == "mirror":
+        half = rng.random((n // 2, 3)) * 0.5
+        c = np.concatenate([half, 1.0 - half])
+    elif kind == "few_colours":
+        pal = rng.integers(0, 256, (6, 3)) / 255.0
+        c = pal[rng.integers(0, 6, n) * (rng.random(n) < 0.97)]
+        c[::1000] += rng.random((len(c[::1000]), 3)) * 1e-3
+    elif kind == "constant":
+        c = np.full((n, 3), 0.25)
+    elif kind == "two_pixels_per_bucket":
+        n, K = 1024, 16
+        c = np.repeat(np.linspace(0.0, 1.0, 512), 2)[:, None] * np.array([1.0, 0.5, 0.25]) + rng.random((1024, 3)) * 1e-6
+    elif kind == "weighted_risky":
+        c = rng.random((n, 3))
+        wts = np.floor(1 + 50 * rng.random(n)) + np.where(rng.random(n) < 0.3, 1.0 - 2.0 ** -rng.integers(20, 53, n), 0.5)
+    elif kind == "weighted_integer":
+        c = rng.random((n, 3))
+        wts = np.floor(1 + 20 * rng.random(n) ** 3)
+    elif kind == "weighted_small":
+        c = rng.random((n, 3))
+        wts = rng.random(n) * 1.5  # some below 1: floor(w) = 0, sizes may stay 0 (local.c:157-163 branches)
+    else:
+        c = 1e6 + rng.random((n, 3))
+    planar = np.asfortranarray(c)
+    want = _cluster_tree(oracle.lib, "orc_quantize_clusters", planar, n, K, wts)
+    _split_counts(cuda_lib, reset=True)
+    got = _cluster_tree(cuda_lib, "patolette_b200_quantize_clusters", planar, n, K, wts)
+    counts = _split_counts(cuda_lib)
+    assert got[2:] == want[2:], f"cluster counts differ ({counts})"
+    assert np.array_equal(got[0], want[0]), f"cluster membership differs ({counts})"
+    assert_same_floats(got[1], want[1], "cluster centres")
+    assert counts["redone"] == counts["refused"], counts
+
+
+def test_split_certificate_is_the_common_route(cuda_lib):
+    """On the bench's kind of data (uniform noise) nearly every cluster is certified; with every certificate refused
+    ("split_certify" = 2) every cluster is evaluated twice and the result is the same."""
+    W = H = 1024; K = 64
+    colors = uniform_colors(W, H, 5)
+    _split_counts(cuda_lib, reset=True)
+    code, pal, pmap = cuda_quantize(cuda_lib, W, H, colors, K, dither=False, color_space=2, kmeans_niter=0)
+    c1 = _split_counts(cuda_lib, reset=True)
+    assert code == 0 and c1["certified"] >= 100 and c1["refused"] <= c1["certified"] // 10, c1
+    try:
+        assert cuda_lib.patolette_b200_set_option(b"split_certify", 2) == 0
+        code2, pal2, pmap2 = cuda_quantize(cuda_lib, W, H, colors, K, dither=False, color_space=2, kmeans_niter=0)
+        c2 = _split_counts(cuda_lib, reset=True)
+    finally:
+        cuda_lib.patolette_b200_set_option(b"split_certify", 1)
+    assert code2 == 0 and c2["certified"] == 0 and c2["redone"] == c2["refused"] > 100, c2
+    assert np.array_equal(pmap, pmap2) and np.array_equal(bits(pal), bits(pal2))
 
 
 # ---------------------------------------------------------------------------------- large-size properties
