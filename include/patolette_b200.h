@@ -148,6 +148,10 @@ PB200_API int patolette_b200_set_stream(void *cuda_stream, int enable);
  * events and writes {"kernel": {"launches", "ms", "bytes"}} (returns the size needed). */
 PB200_API int patolette_b200_profile_enable(int on);
 PB200_API size_t patolette_b200_profile_json(char *buf, size_t cap);
+/* Timeline of the profiled launches, one line "kernel stream start_ms end_ms" each, relative to the first launch
+ * (call before profile_json, which consumes the records).  With patolette_b200_set_option("prof_timeline", 1) the
+ * split loop keeps its two streams while profiling, so the lines show what really overlaps. */
+PB200_API size_t patolette_b200_profile_timeline(char *buf, size_t cap);
 
 /* Ordered-sum statistics since the last reset (pb_ordered.cu), 16 counters: (chain, block) pairs
  * accepted from their summary record, pairs replayed, replay reasons {unusable record, state not

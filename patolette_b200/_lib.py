@@ -53,6 +53,7 @@ SYMBOLS = {
     "patolette_b200_gq_cuts": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "patolette_b200_profile_enable": (C.c_int, [C.c_int]),
     "patolette_b200_profile_json": (C.c_size_t, [C.c_char_p, C.c_size_t]),
+    "patolette_b200_profile_timeline": (C.c_size_t, [C.c_char_p, C.c_size_t]),
     "patolette_b200_fp64_peak": (C.c_double, []),
     "patolette_b200_u8": (None, [C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(QuantizationOptions),
                                  C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int)]),

@@ -29,22 +29,39 @@
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int BH_WARPS = 4, BH_THREADS = 32 * BH_WARPS;
-constexpr int BH_ROWS = 4;                 // rows of 32 pixels whose loads are in flight together
+#ifndef PB_BH_WARPS
+#define PB_BH_WARPS 4
+#endif
+#ifndef PB_BH_ROWS
+#define PB_BH_ROWS 4
+#endif
+constexpr int BH_WARPS = PB_BH_WARPS, BH_THREADS = 32 * BH_WARPS;
+constexpr int BH_ROWS = PB_BH_ROWS;        // rows of 32 pixels whose loads are in flight together
 constexpr int BH_WARP_PX = 2048;           // pixels of a CTA visit per warp
 constexpr int BH_CHUNK = BH_WARPS * BH_WARP_PX;
 
+// One table per WARP (no atomics: ATOMS costs 2 cycles per lane, and 64-bit shared-memory atomics are CAS loops).
+// Bucket b owns 32 bytes, two 16-byte halves {s0, s1} and {s2, count}; the halves of every other group of four
+// buckets are swapped, so that a warp's 16-byte accesses to 32 random buckets spread over all eight bank quads.
+// tag: one byte per bucket and row of the batch - which lane updates the bucket this round (see below).
 template <bool W>
 struct WarpTab {
-    double s[3][PB_BUCKETS];
+    double2 m[2 * PB_BUCKETS];
     unsigned long long sz[W ? PB_BUCKETS : 1];
-    uint32_t cnt[PB_BUCKETS];
     uint32_t risky[W ? PB_BUCKETS : 1];
+    uint8_t tag[BH_ROWS][PB_BUCKETS];
 };
 
 __device__ unsigned long long g_certify_counts[4]; // certified, refused, (spare)
 
 // ---- bucket ids (sort.c:61-87, as k_buckets) + per-bucket sums in any order ------------------------------------
+// A warp takes rows of 32 consecutive pixels.  Lanes of a row that share a bucket must not race on the table.
+// (__match_any_sync would name them, but MATCH.ANY costs ~4 cycles per lane on B200: ncu showed the first version
+// of this kernel waiting on it more than on HBM.)  Instead every lane writes its lane number into the bucket's tag
+// byte and reads it back: exactly one lane per bucket finds itself - it updates the table; the others try again
+// among themselves (one more round covers pairs), and what is left after two rounds (three or more pixels of a
+// row in one bucket: flat image regions) is reduced bucket by bucket with warp shuffles.  Per batch of BH_ROWS rows
+// the buckets and tags of all rows are formed first (independent work), then the updates run back to back.
 template <bool W>
 __global__ void __launch_bounds__(BH_THREADS) k_buckets_hist(PbPlanes b0, PbPlanes b1, const PbSeg *__restrict__ segs,
                                                              const double *__restrict__ axes, PbSplit *__restrict__ sp,
@@ -72,36 +89,60 @@ __global__ void __launch_bounds__(BH_THREADS) k_buckets_hist(PbPlanes b0, PbPlan
     if (blockIdx.x == 0 && tid == 0) sp[seg].degenerate = degenerate;
     // fraction of w from which fl(s + w) may reach the next integer (s + w < 2^E, E in PbSeg::pad)
     const double thr = W ? 1.0 - scalbn(1.0, (int)sg.pad - 52) : 0.0;
-    const unsigned below = (1u << lane) - 1u;
     double am0 = 0.0, am1 = 0.0, am2 = 0.0;
     bool bad = false;
 
     auto rmw = [&](uint32_t b, double t0, double t1, double t2, uint32_t c, unsigned long long z, uint32_t rk) {
-        T.s[0][b] += t0;
-        T.s[1][b] += t1;
-        T.s[2][b] += t2;
-        T.cnt[b] += c;
+        const uint32_t sw = (b >> 2) & 1u;
+        double2 *p = T.m + 2 * b;
+        double2 A = p[sw], B = p[sw ^ 1u];
+        A.x += t0;
+        A.y += t1;
+        B.x += t2;
+        B.y = __longlong_as_double(__double_as_longlong(B.y) + (long long)c);
+        p[sw] = A;
+        p[sw ^ 1u] = B;
         if (W) { T.sz[b] += z; T.risky[b] += rk; }
     };
 
-    for (uint32_t base = blockIdx.x * BH_CHUNK; base < sg.n; base += gridDim.x * BH_CHUNK) {
-        const uint32_t wbeg = base + warp * BH_WARP_PX;
-        const uint32_t wend = min(wbeg + (uint32_t)BH_WARP_PX, sg.n);
-        for (uint32_t row0 = wbeg; row0 < wend; row0 += 32 * BH_ROWS) { // (warp-uniform bounds)
-            double v0[BH_ROWS], v1[BH_ROWS], v2[BH_ROWS], vw[BH_ROWS];
+    // The warp walks batches of BH_ROWS rows: sub-chunks of BH_WARP_PX pixels inside the CTA's chunk, chunk after
+    // chunk.  The loads of the NEXT batch are issued before the current one is worked on (register double buffer):
+    // with only 12 warps per SM (the tables fill shared memory) the kernel cannot hide HBM latency by occupancy.
+    double v0[BH_ROWS], v1[BH_ROWS], v2[BH_ROWS], vw[BH_ROWS];
+    double n0[BH_ROWS], n1[BH_ROWS], n2[BH_ROWS], nw[BH_ROWS];
+    auto load = [&](uint32_t r0, uint32_t e, double (&a0)[BH_ROWS], double (&a1)[BH_ROWS], double (&a2)[BH_ROWS], double (&aw)[BH_ROWS]) {
 #pragma unroll
-            for (int r = 0; r < BH_ROWS; r++) {
-                const uint32_t i = row0 + r * 32 + lane;
-                const bool valid = i < wend;
-                v0[r] = valid ? c0[i] : 0.0;
-                v1[r] = valid ? c1[i] : 0.0;
-                v2[r] = valid ? c2[i] : 0.0;
-                vw[r] = (W && valid) ? cw[i] : 1.0;
+        for (int r = 0; r < BH_ROWS; r++) {
+            const uint32_t i = r0 + r * 32 + lane;
+            const bool valid = i < e;
+            a0[r] = valid ? c0[i] : 0.0;
+            a1[r] = valid ? c1[i] : 0.0;
+            a2[r] = valid ? c2[i] : 0.0;
+            aw[r] = (W && valid) ? cw[i] : 1.0;
+        }
+    };
+    uint32_t cbase = blockIdx.x * BH_CHUNK;
+    uint32_t row0 = cbase + warp * BH_WARP_PX;
+    uint32_t wend = min(row0 + (uint32_t)BH_WARP_PX, sg.n);
+    bool have = row0 < sg.n;
+    if (have) load(row0, wend, v0, v1, v2, vw);
+    while (have) { // (warp-uniform)
+        {
+            uint32_t nrow = row0 + 32 * BH_ROWS, nend = wend, nbase = cbase;
+            if (nrow >= wend) {
+                nbase = cbase + gridDim.x * BH_CHUNK;
+                nrow = nbase + warp * BH_WARP_PX;
+                nend = min(nrow + (uint32_t)BH_WARP_PX, sg.n);
             }
+            const bool nhave = nrow < sg.n;
+            if (nhave) load(nrow, nend, n0, n1, n2, nw);
+            // ---- phase A: buckets and tags of every row of the batch ----
+            uint32_t bb[BH_ROWS]; // bucket | 0x80000000 while this lane's pixel still has to reach the table
+            unsigned long long zz[W ? BH_ROWS : 1];
+            uint32_t rr[W ? BH_ROWS : 1];
 #pragma unroll
             for (int r = 0; r < BH_ROWS; r++) {
                 const uint32_t i = row0 + r * 32 + lane;
-                if (row0 + r * 32 >= wend) break; // warp-uniform
                 const bool valid = i < wend;
                 uint32_t b;
                 if (degenerate) {
@@ -112,69 +153,106 @@ __global__ void __launch_bounds__(BH_THREADS) k_buckets_hist(PbPlanes b0, PbPlan
                     const unsigned long long q = (unsigned long long)__dmul_rn((double)PB_BUCKETS, ratio);
                     b = q < PB_BUCKETS - 1 ? (uint32_t)q : PB_BUCKETS - 1;
                 }
-                if (valid) bk[i] = (uint16_t)b;
                 am0 = fmax(am0, fabs(v0[r])); am1 = fmax(am1, fabs(v1[r])); am2 = fmax(am2, fabs(v2[r]));
-                const double w = vw[r];
-                double t0 = v0[r], t1 = v1[r], t2 = v2[r];
-                unsigned long long z = 0;
-                uint32_t rk = 0;
                 if (W) {
-                    t0 = __dmul_rn(t0, w); t1 = __dmul_rn(t1, w); t2 = __dmul_rn(t2, w); // local.c:130-132
+                    const double w = vw[r];
+                    v0[r] = __dmul_rn(v0[r], w); v1[r] = __dmul_rn(v1[r], w); v2[r] = __dmul_rn(v2[r], w); // local.c:130-132
                     const bool okw = w >= 0.0 && w < 9.0e15;
                     bad |= valid && !okw;
                     const double fl = okw ? floor(w) : 0.0;
-                    z = (unsigned long long)fl;
-                    rk = (okw && (w - fl) >= thr) ? 1u : 0u;
+                    zz[r] = (unsigned long long)fl;
+                    rr[r] = (okw && (w - fl) >= thr) ? 1u : 0u;
                 }
-                // lanes of the row that share a bucket must not race on the table
-                const uint32_t key = valid ? b : (0x10000u | (uint32_t)lane);
-                const unsigned peers = __match_any_sync(FULL, key);
-                const int mult = __popc(peers), rank = __popc(peers & below);
-                const unsigned m = __reduce_max_sync(FULL, (unsigned)mult);
-                if (m > 2u) { // buckets with three or more pixels in the row: one warp reduction per bucket
-                    unsigned hm = __ballot_sync(FULL, valid && mult >= 3 && rank == 0);
-                    while (hm) {
-                        const int L = __ffs(hm) - 1;
-                        hm &= hm - 1;
-                        const unsigned mask = __shfl_sync(FULL, peers, L);
-                        const bool in = (mask >> lane) & 1u;
-                        double a0 = in ? t0 : 0.0, a1 = in ? t1 : 0.0, a2 = in ? t2 : 0.0;
-                        unsigned long long az = (W && in) ? z : 0ull;
+                if (valid) {
+                    bk[i] = (uint16_t)b;
+                    T.tag[r][b] = (uint8_t)lane;
+                }
+                bb[r] = b | (valid ? 0x80000000u : 0u);
+            }
+            __syncwarp();
+            bool win[BH_ROWS];
 #pragma unroll
-                        for (int o = 16; o; o >>= 1) {
-                            a0 += __shfl_xor_sync(FULL, a0, o);
-                            a1 += __shfl_xor_sync(FULL, a1, o);
-                            a2 += __shfl_xor_sync(FULL, a2, o);
-                            if (W) az += __shfl_xor_sync(FULL, az, o);
-                        }
-                        const uint32_t ark = W ? __reduce_add_sync(FULL, in ? rk : 0u) : 0u;
-                        if (lane == L) rmw(b, a0, a1, a2, (uint32_t)__popc(mask), az, ark);
-                    }
-                    __syncwarp();
+            for (int r = 0; r < BH_ROWS; r++) win[r] = (bb[r] >> 31) && T.tag[r][bb[r] & 0xffffu] == (uint8_t)lane;
+            // ---- phase B: round 1 - one lane per bucket and row updates the table ----
+            bool pending = false;
+#pragma unroll
+            for (int r = 0; r < BH_ROWS; r++) {
+                if (win[r]) {
+                    rmw(bb[r] & 0xffffu, v0[r], v1[r], v2[r], 1u, W ? zz[W ? r : 0] : 0ull, W ? rr[W ? r : 0] : 0u);
+                    bb[r] &= 0xffffu;
                 }
-                const bool light = valid && mult <= 2;
-                if (light && rank == 0) rmw(b, t0, t1, t2, 1u, z, rk);
-                __syncwarp();
-                if (light && rank == 1) rmw(b, t0, t1, t2, 1u, z, rk);
+                pending |= (bb[r] >> 31) != 0u;
                 __syncwarp();
             }
+            if (__any_sync(FULL, pending)) {
+                // ---- round 2 among the lanes that lost round 1 (covers every bucket with exactly two pixels in a row)
+#pragma unroll
+                for (int r = 0; r < BH_ROWS; r++)
+                    if (bb[r] >> 31) T.tag[r][bb[r] & 0xffffu] = (uint8_t)lane;
+                __syncwarp();
+#pragma unroll
+                for (int r = 0; r < BH_ROWS; r++) win[r] = (bb[r] >> 31) && T.tag[r][bb[r] & 0xffffu] == (uint8_t)lane;
+                pending = false;
+#pragma unroll
+                for (int r = 0; r < BH_ROWS; r++) {
+                    if (win[r]) {
+                        rmw(bb[r] & 0xffffu, v0[r], v1[r], v2[r], 1u, W ? zz[W ? r : 0] : 0ull, W ? rr[W ? r : 0] : 0u);
+                        bb[r] &= 0xffffu;
+                    }
+                    pending |= (bb[r] >> 31) != 0u;
+                    __syncwarp();
+                }
+                if (__any_sync(FULL, pending)) {
+                    // ---- the rest, bucket by bucket: one warp reduction per bucket that still has pixels waiting
+#pragma unroll
+                    for (int r = 0; r < BH_ROWS; r++) {
+                        unsigned rem = __ballot_sync(FULL, (bb[r] >> 31) != 0u);
+                        while (rem) {
+                            const int L = __ffs(rem) - 1;
+                            const uint32_t bL = __shfl_sync(FULL, bb[r], L);
+                            const bool in = bb[r] == bL; // (flag bit included: waiting lanes of that bucket)
+                            const unsigned mask = __ballot_sync(FULL, in);
+                            double a0 = in ? v0[r] : 0.0, a1 = in ? v1[r] : 0.0, a2 = in ? v2[r] : 0.0;
+                            unsigned long long az = (W && in) ? zz[W ? r : 0] : 0ull;
+#pragma unroll
+                            for (int o = 16; o; o >>= 1) {
+                                a0 += __shfl_xor_sync(FULL, a0, o);
+                                a1 += __shfl_xor_sync(FULL, a1, o);
+                                a2 += __shfl_xor_sync(FULL, a2, o);
+                                if (W) az += __shfl_xor_sync(FULL, az, o);
+                            }
+                            const uint32_t ark = W ? __reduce_add_sync(FULL, in ? rr[W ? r : 0] : 0u) : 0u;
+                            if (lane == L) rmw(bL & 0xffffu, a0, a1, a2, (uint32_t)__popc(mask), az, ark);
+                            __syncwarp();
+                            rem &= ~mask;
+                        }
+                    }
+                }
+            }
+            // hand over to the prefetched batch
+#pragma unroll
+            for (int r = 0; r < BH_ROWS; r++) { v0[r] = n0[r]; v1[r] = n1[r]; v2[r] = n2[r]; vw[r] = nw[r]; }
+            row0 = nrow; wend = nend; cbase = nbase; have = nhave;
         }
     }
     __syncthreads();
     PbHist &H = hist[seg];
     for (int b = tid; b < PB_BUCKETS; b += BH_THREADS) {
-        uint32_t c = 0, rk = 0;
+        uint32_t rk = 0;
         unsigned long long z = 0;
+        long long c = 0;
         double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+        const uint32_t sw = (b >> 2) & 1u;
 #pragma unroll
         for (int w = 0; w < BH_WARPS; w++) {
-            c += tabs[w].cnt[b];
-            a0 += tabs[w].s[0][b]; a1 += tabs[w].s[1][b]; a2 += tabs[w].s[2][b];
+            const double2 A = tabs[w].m[2 * b + sw], B = tabs[w].m[2 * b + (sw ^ 1u)];
+            a0 += A.x; a1 += A.y; a2 += B.x;
+            c += __double_as_longlong(B.y);
             if (W) { z += tabs[w].sz[b]; rk += tabs[w].risky[b]; }
         }
         if (c) {
             atomicAdd(&H.s[0][b], a0); atomicAdd(&H.s[1][b], a1); atomicAdd(&H.s[2][b], a2);
-            atomicAdd(&H.cnt[b], c);
+            atomicAdd(&H.cnt[b], (uint32_t)c);
             if (W) { atomicAdd(&H.sz[b], z); if (rk) atomicAdd(&H.risky[b], rk); }
         }
     }
@@ -326,10 +404,12 @@ void pb_launch_buckets_hist(const PbPlanes bufs[2], const PbSeg *d_segs, int nse
     if (weighted) {
         constexpr int smem = (int)(sizeof(WarpTab<true>) * BH_WARPS);
         PB_CUDA_OK(cudaFuncSetAttribute(k_buckets_hist<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        PB_CUDA_OK(cudaFuncSetAttribute(k_buckets_hist<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         k_buckets_hist<true><<<grid, BH_THREADS, smem, st>>>(bufs[0], bufs[1], d_segs, d_axes, d_split, d_bucket, d_hist);
     } else {
         constexpr int smem = (int)(sizeof(WarpTab<false>) * BH_WARPS);
         PB_CUDA_OK(cudaFuncSetAttribute(k_buckets_hist<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        PB_CUDA_OK(cudaFuncSetAttribute(k_buckets_hist<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         k_buckets_hist<false><<<grid, BH_THREADS, smem, st>>>(bufs[0], bufs[1], d_segs, d_axes, d_split, d_bucket, d_hist);
     }
     PB_CUDA_OK(cudaGetLastError());

@@ -653,7 +653,7 @@ struct Quantizer {
         int nlocal = 0;
         for (int c = 0; c < nc; c++) nlocal += mine(c) ? 1 : 0;
         // two half-batches (largest first, each to the lighter half); one when profiling per kernel
-        const int nhalf = (overlap && nlocal >= 2 && !pb_prof_enabled()) ? 2 : 1;
+        const int nhalf = (overlap && nlocal >= 2 && (!pb_prof_enabled() || pb_prof_timeline())) ? 2 : 1;
         struct HalfBatch {
             PbSeg hsegs[MAXB];
             double haxes[3 * MAXB];
@@ -1406,6 +1406,7 @@ int patolette_b200_set_option(const char *name, long long value) {
     if (!strcmp(name, "raw_moments")) { pb_ordered_set_raw_moments(value != 0); return 0; }
     if (!strcmp(name, "fused_pass")) { pb_ordered_set_fused(value != 0); return 0; }
     if (!strcmp(name, "fast_summary")) { pb_ordered_set_fast(value != 0); return 0; }
+    if (!strcmp(name, "prof_timeline")) { pb_prof_set_timeline(value != 0); return 0; }
     if (!strcmp(name, "split_certify")) { if (value < 0 || value > 2) return -1; g_split_certify = (int)value; return 0; }
     if (!strcmp(name, "overlap")) { g_overlap_override = (int)value; return 0; }
     if (!strcmp(name, "nn_grid")) { g_nn_grid = value != 0; return 0; }
@@ -1446,6 +1447,16 @@ int patolette_b200_profile_enable(int on) {
 
 size_t patolette_b200_profile_json(char *buf, size_t cap) {
     std::string js = pb_prof_json();
+    if (buf && cap) {
+        size_t m = js.size() < cap - 1 ? js.size() : cap - 1;
+        memcpy(buf, js.data(), m);
+        buf[m] = 0;
+    }
+    return js.size() + 1;
+}
+
+size_t patolette_b200_profile_timeline(char *buf, size_t cap) {
+    std::string js = pb_prof_timeline_text();
     if (buf && cap) {
         size_t m = js.size() < cap - 1 ? js.size() : cap - 1;
         memcpy(buf, js.data(), m);

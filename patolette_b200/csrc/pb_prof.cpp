@@ -14,7 +14,9 @@ struct Pending {
     const char *name;
     cudaEvent_t a, b;
     double bytes;
+    cudaStream_t st;
 };
+std::atomic<bool> g_timeline{false};
 std::mutex g_mu;
 std::vector<Pending> g_pending;
 struct Acc {
@@ -26,6 +28,8 @@ std::map<std::string, Acc> g_acc;
 } // namespace
 
 void pb_prof_enable(bool on) { g_on = on; }
+void pb_prof_set_timeline(bool on) { g_timeline = on; }
+bool pb_prof_timeline() { return g_on && g_timeline; }
 bool pb_prof_enabled() { return g_on; }
 long pb_prof_launch_count() { return g_launches; }
 void pb_prof_next_bytes(double bytes) { g_next_bytes = bytes; }
@@ -58,8 +62,27 @@ PbProfScope::~PbProfScope() {
     if (a) {
         cudaEventRecord(b, st);
         std::lock_guard<std::mutex> lk(g_mu);
-        g_pending.push_back(Pending{name, a, b, bytes});
+        g_pending.push_back(Pending{name, a, b, bytes, st});
     }
+}
+
+// "name stream start_ms end_ms" per recorded launch, times relative to the first one (events of different streams of
+// one device are comparable).  Leaves the pending list intact: call before pb_prof_json().
+std::string pb_prof_timeline_text() {
+    std::lock_guard<std::mutex> lk(g_mu);
+    std::ostringstream os;
+    if (g_pending.empty()) return os.str();
+    std::map<cudaStream_t, int> ids;
+    for (auto &p : g_pending) cudaEventSynchronize(p.b);
+    const cudaEvent_t base = g_pending.front().a;
+    for (auto &p : g_pending) {
+        float t0 = 0, t1 = 0;
+        cudaEventElapsedTime(&t0, base, p.a);
+        cudaEventElapsedTime(&t1, base, p.b);
+        const int id = ids.emplace(p.st, (int)ids.size()).first->second;
+        os << p.name << " " << id << " " << t0 << " " << t1 << "\n";
+    }
+    return os.str();
 }
 
 std::string pb_prof_json() {

@@ -18,6 +18,11 @@ void pb_prof_reset();
 // Resolve all pending events (synchronises them) and return a JSON object
 // {"kernel": {"launches": n, "ms": total, "bytes": total}, ...}.
 std::string pb_prof_json();
+// Timeline mode: the split loop keeps its two streams while profiling (per-kernel durations then include waiting
+// for the other stream's CTAs) and pb_prof_timeline_text() lists "name stream start_ms end_ms" of every launch.
+void pb_prof_set_timeline(bool on);
+bool pb_prof_timeline();
+std::string pb_prof_timeline_text();
 
 struct PbProfScope {
     cudaEvent_t a = nullptr, b = nullptr;
