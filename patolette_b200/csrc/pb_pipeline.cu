@@ -1414,6 +1414,8 @@ int patolette_b200_set_option(const char *name, long long value) {
     if (!strcmp(name, "gq_full_table")) { g_gq_full_table = value != 0; return 0; }
     if (!strcmp(name, "dither_grid")) { pb_dither_set_grid(value != 0); return 0; }
     if (!strcmp(name, "dither_subwarp")) { pb_dither_set_subwarp(value != 0); return 0; }
+    if (!strcmp(name, "dither_tiles")) { pb_dither_set_tiles(value != 0); return 0; }
+    if (!strcmp(name, "dither_one_wave")) { pb_dither_set_one_wave(value != 0); return 0; }
     if (!strcmp(name, "allow_jacobi")) { pb_lapack_allow_jacobi(value != 0); return 0; }
     return -1;
 }

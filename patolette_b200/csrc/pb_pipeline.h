@@ -26,6 +26,9 @@ void pb_dither_riemersma(const double *const planes[3], size_t width, size_t hei
 void pb_dither_set_grid(bool on);
 // test knob: 4 lanes per speculative chain (default) or one warp per chain
 void pb_dither_set_subwarp(bool on);
+// test knobs: tile-wise permutation kernels / one-wave segment sizing (both default on)
+void pb_dither_set_tiles(bool on);
+void pb_dither_set_one_wave(bool on);
 
 // Largest palette the f32 KMeans slice supports (16-bit assignments; per-warp class counters of the stable
 // sort in shared memory, 4 B x K for one warp).  Above it patolette() returns exit code -6 when

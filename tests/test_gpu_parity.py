@@ -255,6 +255,15 @@ def test_dither_candidate_lists_equal_brute_force(cuda_lib, oracle, kind):
     finally:
         cuda_lib.patolette_b200_set_option(b"dither_subwarp", 1)
     assert np.array_equal(warp, want), f"{int((warp != want).sum())} indices of the warp-per-chain kernel differ from the oracle"
+    # per-pixel permutation kernels and the n / 2048 segment length instead of the tile kernels / one-wave sizing
+    for knob in (b"dither_tiles", b"dither_one_wave"):
+        other = np.full(n, 7, dtype=np.uintp)
+        try:
+            assert cuda_lib.patolette_b200_set_option(knob, 0) == 0
+            assert cuda_lib.patolette_b200_dither(planar.ctypes.data, W, H, pal.ctypes.data, K, other.ctypes.data) == 0
+        finally:
+            cuda_lib.patolette_b200_set_option(knob, 1)
+        assert np.array_equal(other, want), f"{knob}: {int((other != want).sum())} indices differ from the oracle"
 
 
 # ---------------------------------------------------------------------------------- end to end
