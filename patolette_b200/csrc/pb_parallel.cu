@@ -482,7 +482,10 @@ __global__ void __launch_bounds__(SS_THREADS) k_scatter_sorted_cta(const uint16_
 // Two-class payload scatter (the split partition, local.c:219-245): ranks come from two ballots per row of
 // 32 positions and two warp-uniform running offsets in registers - no shared-memory counters, no
 // __match_any, no __syncwarp - and four rows are loaded before any is stored (memory-level parallelism).
-constexpr int SC2_UNROLL = 4;
+#ifndef PB_SC2_UNROLL
+#define PB_SC2_UNROLL 4
+#endif
+constexpr int SC2_UNROLL = PB_SC2_UNROLL;
 __global__ void __launch_bounds__(256) k_scatter2(const uint16_t *__restrict__ bucket, const PbSplit *__restrict__ sp,
                                                   const PbSeg *__restrict__ segs, const uint32_t *__restrict__ tile_hist,
                                                   const uint32_t *__restrict__ class_start, PbPlanes src0, PbPlanes src1,

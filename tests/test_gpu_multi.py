@@ -43,6 +43,19 @@ def _worker(rank, world, port, out):
                                                  weights_slice=None if weights is None else weights[first:first + count], **kw)
         assert ok, msg
         res[name] = (first, count, pal.copy(), pmap.copy())
+    # every split certificate refused: each cluster is evaluated twice, and all ranks must agree on the re-evaluations
+    # (they are collective calls) - same result as the plain run
+    assert lib.patolette_b200_set_option(b"split_certify", 2) == 0
+    for name in ("luv_nodither_weighted", "ictcp_kmeans_dither"):
+        spec = CASES[name]
+        colors, weights, kw = make_case(spec)
+        first, count = pb.shard_range(spec["w"] * spec["h"], rank, world)
+        ok, pal, pmap, msg = pb.quantize_sharded(spec["w"], spec["h"], colors[first:first + count], spec["K"],
+                                                 weights_slice=None if weights is None else weights[first:first + count], **kw)
+        assert ok, msg
+        assert np.array_equal(pal.view(np.uint64), res[name][2].view(np.uint64)) and np.array_equal(pmap, res[name][3]), \
+            f"{name}: the re-evaluated run differs on rank {rank}"
+    lib.patolette_b200_set_option(b"split_certify", 1)
     out[rank] = res
     lib.patolette_b200_comm_destroy()
     dist.destroy_process_group()
