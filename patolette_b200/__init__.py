@@ -124,6 +124,39 @@ def quantize_u8(width, height, rgb, palette_size, dither=True, palette_only=Fals
     return (success, palette, None if palette_only else pmap, message)
 
 
+def save_png(path, width, height, palette, palette_map, compress_level=6):
+    """N4 (extension): write ``(palette, palette_map)`` as an indexed PNG - the step that follows ``quantize()`` in the
+    reference's README (README.md:186-191 reassembles the image with PIL).  Colour type 3, bit depth 8 (palettes up
+    to 256 entries; unused rows - marked -1 by the reference, patolette.c:328-330 - are dropped from PLTE), palette
+    entries rounded as the README does (``(palette * 255).astype(uint8)`` truncates; so does this).  Pure host code
+    on the standard library (zlib + struct); returns the number of bytes written."""
+    import struct
+    import zlib
+    pal = np.asarray(palette, dtype=np.float64)
+    idx = np.asarray(palette_map).reshape(-1)
+    if pal.ndim != 2 or pal.shape[1] != 3:
+        raise ValueError("palette must be K x 3")
+    if idx.size != width * height:
+        raise ValueError(color_mismatch)
+    used = int((pal[:, 0] >= 0).sum()) if pal.size else 0  # trailing rows of -1 are unused slots
+    if used > 256:
+        raise ValueError("an indexed PNG holds at most 256 palette entries")
+    if idx.size and int(idx.max()) >= max(used, 1):
+        raise ValueError("palette_map refers to an unused palette row")
+    plte = (np.clip(pal[:used], 0.0, 1.0) * 255).astype(np.uint8).tobytes()
+    rows = np.zeros((height, width + 1), dtype=np.uint8)  # filter byte 0 (None) + one index per pixel
+    rows[:, 1:] = idx.astype(np.uint8).reshape(height, width)
+
+    def chunk(tag: bytes, data: bytes) -> bytes:
+        return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xffffffff)
+
+    blob = (b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", width, height, 8, 3, 0, 0, 0))
+            + chunk(b"PLTE", plte) + chunk(b"IDAT", zlib.compress(rows.tobytes(), compress_level)) + chunk(b"IEND", b""))
+    with open(path, "wb") as f:
+        f.write(blob)
+    return len(blob)
+
+
 def init_sharding(dist=None, group=None) -> tuple[int, int]:
     """Image-sharded multi-GPU runs (extension): create the library's NCCL communicator over the
     ranks of a torch.distributed process group (one process per GPU; call after ``torch.cuda.set_device`` /

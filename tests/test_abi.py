@@ -124,3 +124,33 @@ def test_route_and_sharding_knobs_validate_their_arguments():
         pb.set_sharding(0, 2)                                           # no allgather given
     pb.set_sharding(1, 2, lambda send: send * 2)
     pb.set_sharding(0, 1)                                               # back to a single rank
+
+
+def test_save_png_round_trips(tmp_path):
+    """N4: the indexed-PNG writer (host code, no GPU): decode the file by hand and compare."""
+    import struct, zlib
+    import numpy as np
+    import patolette_b200 as pb
+    rng = np.random.default_rng(5)
+    w, h, K = 37, 11, 64
+    pal = np.full((K, 3), -1.0, order="F")
+    pal[:40] = rng.random((40, 3))
+    pmap = rng.integers(0, 40, w * h).astype(np.uintp)
+    path = tmp_path / "q.png"
+    size = pb.save_png(str(path), w, h, pal, pmap)
+    blob = path.read_bytes()
+    assert len(blob) == size and blob[:8] == b"\x89PNG\r\n\x1a\n"
+    at, chunks = 8, {}
+    while at < len(blob):
+        n, tag = struct.unpack(">I4s", blob[at:at + 8])
+        data = blob[at + 8:at + 8 + n]
+        assert struct.unpack(">I", blob[at + 8 + n:at + 12 + n])[0] == zlib.crc32(tag + data) & 0xffffffff
+        chunks[tag] = data
+        at += 12 + n
+    assert struct.unpack(">IIBBBBB", chunks[b"IHDR"]) == (w, h, 8, 3, 0, 0, 0)
+    assert chunks[b"PLTE"] == (pal[:40] * 255).astype(np.uint8).tobytes()
+    rows = np.frombuffer(zlib.decompress(chunks[b"IDAT"]), dtype=np.uint8).reshape(h, w + 1)
+    assert (rows[:, 0] == 0).all() and np.array_equal(rows[:, 1:].reshape(-1), pmap.astype(np.uint8))
+    import pytest
+    with pytest.raises(ValueError):
+        pb.save_png(str(path), w, h, np.zeros((300, 3)), pmap)
