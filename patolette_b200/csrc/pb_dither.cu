@@ -28,6 +28,7 @@
 #include "pb_prof.h"
 #include "pb_pipeline.h"
 #include "pb_pool.h"
+#include "pb_tma.cuh"
 
 namespace {
 
@@ -112,7 +113,7 @@ __global__ void __launch_bounds__(256) k_permute_tile(const double *__restrict__
                                                       const double *__restrict__ c2, const uint32_t *__restrict__ rank,
                                                       uint32_t W, uint32_t H, double *__restrict__ h0,
                                                       double *__restrict__ h1, double *__restrict__ h2) {
-    __shared__ double sm[3][1024];
+    __shared__ __align__(128) double sm[3][1024];
     __shared__ uint32_t s_red[8];
     const uint32_t x = blockIdx.x * 32 + (threadIdx.x & 31), y0 = blockIdx.y * 32 + (threadIdx.x >> 5);
     uint32_t r[4], rmin = 0xffffffffu;
@@ -131,6 +132,20 @@ __global__ void __launch_bounds__(256) k_permute_tile(const double *__restrict__
 #pragma unroll
     for (int k = 0; k < 4; k++)
         if (r[k] != 0xffffffffu && r[k] - r0 < 1024u) { sm[0][r[k] - r0] = v0[k]; sm[1][r[k] - r0] = v1[k]; sm[2][r[k] - r0] = v2[k]; }
+    if (((r0 | count) & 1u) == 0u) {
+        // the block's run leaves as three bulk copies (TMA, shared -> global: 8 KB each for a whole block): 16-byte
+        // aligned on both sides because the run starts and ends on an even walk position
+        pb_fence_proxy_async();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            pb_bulk_store(h0 + r0, sm[0], count * 8u);
+            pb_bulk_store(h1 + r0, sm[1], count * 8u);
+            pb_bulk_store(h2 + r0, sm[2], count * 8u);
+            pb_bulk_commit();
+            pb_bulk_wait_read();
+        }
+        return;
+    }
     __syncthreads();
     for (uint32_t t = threadIdx.x; t < count; t += 256) {
         h0[(size_t)r0 + t] = sm[0][t]; h1[(size_t)r0 + t] = sm[1][t]; h2[(size_t)r0 + t] = sm[2][t];
@@ -140,10 +155,12 @@ __global__ void __launch_bounds__(256) k_permute_tile(const double *__restrict__
 __global__ void __launch_bounds__(256) k_unpermute_tile(const uint32_t *__restrict__ rank, const uint32_t *__restrict__ hidx,
                                                         uint32_t W, uint32_t H, size_t first, size_t n,
                                                         unsigned long long *__restrict__ map) {
-    __shared__ uint32_t sm[1024];
+    __shared__ __align__(128) uint32_t sm[1024];
     __shared__ uint32_t s_red[8];
+    __shared__ __align__(8) unsigned long long s_bar;
     const uint32_t x = blockIdx.x * 32 + (threadIdx.x & 31), y0 = blockIdx.y * 32 + (threadIdx.x >> 5);
     uint32_t r[4], rmin = 0xffffffffu;
+    if (threadIdx.x == 0) pb_mbar_init(&s_bar, 1);
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const uint32_t y = y0 + 8 * k;
@@ -151,10 +168,20 @@ __global__ void __launch_bounds__(256) k_unpermute_tile(const uint32_t *__restri
         r[k] = in ? rank[(size_t)y * W + x] : 0xffffffffu;
         rmin = min(rmin, r[k]);
     }
-    const uint32_t r0 = block_min_u32(rmin, s_red);
+    const uint32_t r0 = block_min_u32(rmin, s_red); // (its barrier also publishes the mbarrier's initialisation)
     const uint32_t count = (min(blockIdx.x * 32 + 32, W) - blockIdx.x * 32) * (min(blockIdx.y * 32 + 32, H) - blockIdx.y * 32);
-    for (uint32_t t = threadIdx.x; t < count; t += 256) sm[t] = hidx[(size_t)r0 + t];
-    __syncthreads();
+    if (((r0 | count) & 3u) == 0u) {
+        // the block's choices arrive as one bulk copy (TMA, global -> shared, 4 KB for a whole block) that signals
+        // the mbarrier every thread then waits on
+        if (threadIdx.x == 0) {
+            pb_mbar_expect_tx(&s_bar, count * 4u);
+            pb_bulk_load(sm, hidx + r0, count * 4u, &s_bar);
+        }
+        pb_mbar_wait(&s_bar, 0);
+    } else {
+        for (uint32_t t = threadIdx.x; t < count; t += 256) sm[t] = hidx[(size_t)r0 + t];
+        __syncthreads();
+    }
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         const size_t p = (size_t)(y0 + 8 * k) * W + x;
@@ -387,8 +414,11 @@ __device__ __forceinline__ int dither_nn4(double x, double y, double z, const do
     return best;
 }
 
+#ifndef PB_DS_MINB
+#define PB_DS_MINB 4
+#endif
 template <bool PAL_SMEM> // palette in shared memory (LDS) or - too large - in global memory
-__global__ void __launch_bounds__(DS_WARPS * 32) k_riemersma_spec4(const double *__restrict__ h0, const double *__restrict__ h1,
+__global__ void __launch_bounds__(DS_WARPS * 32, PB_DS_MINB) k_riemersma_spec4(const double *__restrict__ h0, const double *__restrict__ h1,
                                                                   const double *__restrict__ h2, size_t n, size_t seg,
                                                                   size_t warm, const double *__restrict__ pal,
                                                                   const double *__restrict__ palw, int K,
@@ -457,6 +487,8 @@ __global__ void __launch_bounds__(DS_WARPS * 32) k_riemersma_spec4(const double 
         for (int k = 0; k < 16; k++) {
             const double P = px[ch][k];
             // riemersma.c:292-297: error = sum_i queue[i] * weight[i], oldest first; slot k holds the oldest entry
+            // (summing the 15 older taps of the NEXT pixel while this pixel's candidate list is on its way from L2 was
+            // tried: 40 more registers - spills or a CTA less per SM - cost more than the hidden DADD chain saves)
             double err = 0.0;
 #pragma unroll
             for (int t = 0; t < 16; t++) err = __dadd_rn(err, __dmul_rn(q[(k + t) & 15], c_qw[t]));

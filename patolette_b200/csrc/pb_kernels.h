@@ -42,6 +42,8 @@ void pb_ordered_set_dump_cap(long long slots);
 void pb_ordered_set_fast(bool on);
 // test knob: single-pass fused summaries (default) or the separate blocksum + prefix + summary kernels
 void pb_ordered_set_fused(bool on);
+// test knob: block-sum scans of long segments shared by several CTAs (default) or one CTA per chain
+void pb_ordered_set_prefix_slabs(int mode); // 0 off, 1 auto, >= 2 forced slab count
 // test knob: centred-pass block sums derived from the mean pass's raw moments (default) or summed from the pixels
 void pb_ordered_set_raw_moments(bool on);
 // cmask: bit c set = chain c is summed by this call (chain-sharded multi-GPU runs split the chains over the

@@ -282,6 +282,65 @@ __global__ void __launch_bounds__(OP_THREADS) k_ord_prefix(const PbSeg *__restri
     }
 }
 
+// Long segments: the scan of one chain is cut into S slabs so that S CTAs share it (one CTA per chain left the
+// top of the tree - a 268 M pixel cluster has 524 288 blocks - scanning on 7 of 148 SMs for 1 ms per pass):
+// slab sums first, then every slab scans itself on top of the sums of the slabs before it.
+constexpr int OPS_THREADS = 256;
+constexpr int OPS_MAX_SLABS = 32;
+template <int C>
+__global__ void __launch_bounds__(OPS_THREADS) k_ord_prefix_part(const PbSeg *__restrict__ segs, const double *__restrict__ psum,
+                                                                 int first_chain, unsigned cmask, int S, double *__restrict__ part) {
+    __shared__ double s_part[OPS_THREADS / 32];
+    const int seg = blockIdx.y, c = blockIdx.x + first_chain, slab = blockIdx.z, tid = threadIdx.x;
+    if (!(cmask >> c & 1u)) return;
+    const uint32_t nblk = (segs[seg].n + OB - 1) / OB, L = (nblk + S - 1) / S;
+    const uint32_t b0 = min((uint32_t)slab * L, nblk), b1 = min(b0 + L, nblk);
+    const double *io = psum + (size_t)segs[seg].bbase * C + c;
+    double acc = 0.0;
+#pragma unroll 4
+    for (uint32_t b = b0 + tid; b < b1; b += OPS_THREADS) acc += io[(size_t)b * C];
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((tid & 31) == 0) s_part[tid >> 5] = acc;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0.0;
+        for (int w = 0; w < OPS_THREADS / 32; w++) t += s_part[w];
+        part[((size_t)seg * S + slab) * C + c] = t;
+    }
+}
+template <int C>
+__global__ void __launch_bounds__(OPS_THREADS) k_ord_prefix_slab(const PbSeg *__restrict__ segs, double *__restrict__ psum, int first_chain,
+                                                                 unsigned cmask, int S, const double *__restrict__ part) {
+    __shared__ double s_part[OPS_THREADS / 32];
+    const int seg = blockIdx.y, c = blockIdx.x + first_chain, slab = blockIdx.z, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (!(cmask >> c & 1u)) return;
+    const uint32_t nblk = (segs[seg].n + OB - 1) / OB, L = (nblk + S - 1) / S;
+    const uint32_t s0 = min((uint32_t)slab * L, nblk), s1 = min(s0 + L, nblk);
+    double *io = psum + (size_t)segs[seg].bbase * C + c;
+    double offset = 0.0;
+    for (int q = 0; q < slab; q++) offset += part[((size_t)seg * S + q) * C + c];
+    const uint32_t cnt = s1 - s0, per = (cnt + OPS_THREADS - 1) / OPS_THREADS;
+    const uint32_t b0 = s0 + min((uint32_t)tid * per, cnt), b1 = min(b0 + per, s1);
+    double s = 0.0;
+#pragma unroll 8
+    for (uint32_t b = b0; b < b1; b++) s += io[(size_t)b * C];
+    double incl = s;
+    for (int o = 1; o < 32; o <<= 1) {
+        const double v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_part[warp] = incl;
+    __syncthreads();
+    double before = 0.0;
+    for (int w = 0; w < warp; w++) before += s_part[w];
+    double run = offset + before + (incl - s);
+    for (uint32_t b = b0; b < b1; b++) {
+        const double v = io[(size_t)b * C];
+        io[(size_t)b * C] = run;
+        run += v;
+    }
+}
+
 // ---- S3: block summaries with per-element binade prediction ------------------------------------
 // One WARP per block: 16 consecutive elements per lane.  (ncu on the first version - 64 threads x 8 elements,
 // everything unrolled - showed two thirds of the instructions in the per-thread fixed part (span set-up and
@@ -1465,6 +1524,7 @@ long long g_dump_cap_override = -1; // debug/test knob (patolette_b200_set_optio
 // Measured SLOWER at 16384^2 (107 vs 85 ms for the two sweeps): the summaries are bound by instruction issue, not by HBM,
 // and the fused kernel's 52 KB of staging per CTA halves the resident warps.  Kept as a tested route, off by default.
 bool g_fused_pass = false;
+int g_prefix_slabs = 1; // "prefix_slabs": long segments' block-sum scans shared by several CTAs (1, default: slabs of >= 8192 blocks), one CTA per chain (0), or a forced slab count (tests)
 bool g_raw_moments = true;          // "raw_moments": the centred pass derives its block sums from the mean pass's raw moments
 struct RawTag {
     const void *segs = nullptr;
@@ -1569,8 +1629,21 @@ void launch_pass(const PbPlanes bufs[2], const PbSeg *d_segs, int nseg, uint32_t
             k_ord_blocksum<KIND, W><<<grid, OB_THREADS, 0, st>>>(bufs[0], bufs[1], d_segs, d_stats, sc.psum, cmask);
             tag = RawTag{};
         }
-        { PbProfScope p("k_ord_prefix", st, false);
-          k_ord_prefix<C><<<dim3(chain_live<KIND, W>(0) ? C : C - 1, nseg), OP_THREADS, 0, st>>>(d_segs, sc.psum, chain_live<KIND, W>(0) ? 0 : 1, cmask); }
+        {
+            const int nch = chain_live<KIND, W>(0) ? C : C - 1, first = chain_live<KIND, W>(0) ? 0 : 1;
+            int S = g_prefix_slabs >= 2 ? g_prefix_slabs : (int)(blk_cap / 8192);
+            S = S > OPS_MAX_SLABS ? OPS_MAX_SLABS : S;
+            if (g_prefix_slabs && S >= 2 && (size_t)nseg * S * C * sizeof(double) <= (size_t)total_blocks * sizeof(TileStat)) {
+                double *part = reinterpret_cast<double *>(sc.tstat); // (the fused pass's table: idle on this route)
+                { PbProfScope p("k_ord_prefix", st, false);
+                  k_ord_prefix_part<C><<<dim3(nch, nseg, S), OPS_THREADS, 0, st>>>(d_segs, sc.psum, first, cmask, S, part); }
+                { PbProfScope p("k_ord_prefix", st, false);
+                  k_ord_prefix_slab<C><<<dim3(nch, nseg, S), OPS_THREADS, 0, st>>>(d_segs, sc.psum, first, cmask, S, part); }
+            } else {
+                PbProfScope p("k_ord_prefix", st, false);
+                k_ord_prefix<C><<<dim3(nch, nseg), OP_THREADS, 0, st>>>(d_segs, sc.psum, first, cmask);
+            }
+        }
         PB_CUDA_OK(cudaMemsetAsync(sc.list_count, 0, 2 * sizeof(unsigned int), st));
         if (g_fast_summary) {
             dim3 fgrid((blk_cap + OF_WARPS - 1) / OF_WARPS, nseg);
@@ -1617,6 +1690,7 @@ void pb_ordered_chain_debug(unsigned long long out[35], bool reset) {
 void pb_ordered_set_dump_cap(long long slots) { g_dump_cap_override = slots; }
 void pb_ordered_set_fast(bool on) { g_fast_summary = on; }
 void pb_ordered_set_fused(bool on) { g_fused_pass = on; }
+void pb_ordered_set_prefix_slabs(int mode) { g_prefix_slabs = mode < 0 ? 0 : (mode > OPS_MAX_SLABS ? OPS_MAX_SLABS : mode); }
 void pb_ordered_set_raw_moments(bool on) { g_raw_moments = on; }
 
 uint32_t pb_ordered_blocks(uint32_t n) { return (n + OB - 1) / OB; }

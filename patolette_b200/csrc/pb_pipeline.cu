@@ -1404,6 +1404,7 @@ int patolette_b200_set_option(const char *name, long long value) {
     if (!strcmp(name, "sorted_payload")) { g_sorted_payload = value != 0; return 0; }
     if (!strcmp(name, "gq_chain_cta")) { pb_chain_set_gq_cta(value != 0); return 0; }
     if (!strcmp(name, "raw_moments")) { pb_ordered_set_raw_moments(value != 0); return 0; }
+    if (!strcmp(name, "prefix_slabs")) { pb_ordered_set_prefix_slabs((int)value); return 0; }
     if (!strcmp(name, "fused_pass")) { pb_ordered_set_fused(value != 0); return 0; }
     if (!strcmp(name, "fast_summary")) { pb_ordered_set_fast(value != 0); return 0; }
     if (!strcmp(name, "prof_timeline")) { pb_prof_set_timeline(value != 0); return 0; }

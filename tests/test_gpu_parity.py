@@ -317,7 +317,7 @@ def _cluster_tree(lib, fn, planar, n, K, wts=None):
     return labels, centers[:cnt.value].copy(), cnt.value, gq.value
 
 
-@pytest.mark.parametrize("route", ["default", "split_exact", "split_redo_all", "fused", "no_raw_moments", "gq_chain_warp", "ord_gather", "scatter_warp", "classic_summary", "no_term_dump", "one_slot", "no_overlap", "overlap"])
+@pytest.mark.parametrize("route", ["default", "split_exact", "split_redo_all", "prefix_5_slabs", "prefix_one_cta", "fused", "no_raw_moments", "gq_chain_warp", "ord_gather", "scatter_warp", "classic_summary", "no_term_dump", "one_slot", "no_overlap", "overlap"])
 def test_cluster_tree_1p5M_every_route_matches_oracle(cuda_lib, oracle, route):
     """1.5 M pixels, K=48 (clusters long enough for the group records and the two-level resolve, hovering
     off-diagonal sums, two-parity records): the ordered-sum machinery has several routes to the same bits -
@@ -327,7 +327,7 @@ def test_cluster_tree_1p5M_every_route_matches_oracle(cuda_lib, oracle, route):
     side = int(np.ceil(np.sqrt(n)))
     planar = np.asfortranarray(image_like_colors(side, side, 17)[:n] * 0.5 + 0.5 * uniform_colors(side, side, 18)[:n])
     want = _cluster_tree(oracle.lib, "orc_quantize_clusters", planar, n, K)
-    opts = {"default": [], "split_exact": [(b"split_certify", 0)], "split_redo_all": [(b"split_certify", 2)], "fused": [(b"fused_pass", 1)], "no_raw_moments": [(b"raw_moments", 0)], "gq_chain_warp": [(b"gq_chain_cta", 0)], "ord_gather": [(b"sorted_payload", 0)], "scatter_warp": [(b"scatter_cta", 0)], "classic_summary": [(b"fast_summary", 0)], "no_term_dump": [(b"dump_cap", 0)], "one_slot": [(b"dump_cap", 1)],
+    opts = {"default": [], "split_exact": [(b"split_certify", 0)], "split_redo_all": [(b"split_certify", 2)], "prefix_5_slabs": [(b"prefix_slabs", 5)], "prefix_one_cta": [(b"prefix_slabs", 0)], "fused": [(b"fused_pass", 1)], "no_raw_moments": [(b"raw_moments", 0)], "gq_chain_warp": [(b"gq_chain_cta", 0)], "ord_gather": [(b"sorted_payload", 0)], "scatter_warp": [(b"scatter_cta", 0)], "classic_summary": [(b"fast_summary", 0)], "no_term_dump": [(b"dump_cap", 0)], "one_slot": [(b"dump_cap", 1)],
             "no_overlap": [(b"overlap", 0)], "overlap": [(b"overlap", 1)]}[route]
     try:
         for k, v in opts:
@@ -337,6 +337,7 @@ def test_cluster_tree_1p5M_every_route_matches_oracle(cuda_lib, oracle, route):
         cuda_lib.patolette_b200_set_option(b"dump_cap", -1)
         cuda_lib.patolette_b200_set_option(b"overlap", -1)
         cuda_lib.patolette_b200_set_option(b"split_certify", 1)
+        cuda_lib.patolette_b200_set_option(b"prefix_slabs", 1)
         cuda_lib.patolette_b200_set_option(b"fast_summary", 1)
         cuda_lib.patolette_b200_set_option(b"fused_pass", 0)
         cuda_lib.patolette_b200_set_option(b"raw_moments", 1)
