@@ -481,6 +481,20 @@ def measure_ours(args):
         except Exception:
             pass
 
+    # DRAM bytes per launch of the top kernel from the committed `ncu --set full` capture (tools/ncu_summarise.py); the
+    # capture names the image side it was taken at - another size is scaled by the pixel ratio and says so
+    traffic, traffic_src = None, None
+    ent = ncu.get(top_name)
+    if ent and ent.get("dram_bytes_per_launch"):
+        cap_side = ent.get("side") or ncu.get("side")
+        per_launch_px = ent.get("pixels_per_launch")
+        traffic = ent["dram_bytes_per_launch"]
+        traffic_src = f"profiles/{ncu.get('_file')}: dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of {top_name}"
+        my_px = (top["bytes"] / top["launches"]) / max(ent.get("algorithmic_bytes_per_pixel", 0) or 1e30, 1e-30) if ent.get("algorithmic_bytes_per_pixel") else None
+        if per_launch_px and my_px and abs(my_px / per_launch_px - 1) > 0.02:
+            traffic = traffic * my_px / per_launch_px
+            traffic_src += f" (captured on a launch of {per_launch_px / 1e6:.1f} M pixels at side {cap_side}; scaled to this run's average launch of {my_px / 1e6:.1f} M pixels)"
+
     def stage_roofline(names, bytes_per_step, p=prof):
         ms = sum(v["ms"] for k, v in p.items() if any(k.startswith(nm) for nm in names))
         g = bytes_per_step / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
@@ -500,8 +514,8 @@ def measure_ours(args):
     pass_bytes = sum(v["bytes"] for k, v in prof.items() if k.startswith("k_ord_fast") or k.startswith("k_ord_summary_"))
     dither_ms = sum(v["ms"] for k, v in prof.items() if k.startswith("k_riemersma"))
     roofline = {"bound": "hbm", "kernel": top_name, "dominant_overall": kernels[0][0], "achieved": gbs, "peak": peak, "unit": "GB/s",
-                "frac": gbs / peak, "traffic": ncu.get(top_name, {}).get("dram_bytes_per_launch"),
-                "traffic_source": f"profiles/{ncu.get('_file')} (ncu --set full capture of this kernel; not re-measured in this run)" if ncu else None,
+                "frac": gbs / peak, "traffic": traffic,
+                "traffic_source": traffic_src,
                 "peak_source": peak_src,
                 "launches_per_step": top["launches"], "ms_per_step_in_kernel": top["ms"],
                 "algorithmic_bytes_per_step": top["bytes"],
