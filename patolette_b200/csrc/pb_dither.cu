@@ -364,10 +364,14 @@ constexpr int DS_CHAINS = 32 / DS_GROUP;
 constexpr int DS_WARPS = 4;
 __constant__ double c_qw[16]; // queue weights (riemersma.c:360-373), oldest first
 
-// squared distance to palette entry j (weighted palette stored x, y, z, pad: two 16-byte loads)
-__device__ __forceinline__ double dither_dist4(const double *__restrict__ palw4, int j, double x, double y, double z) {
-    const double2 a = *reinterpret_cast<const double2 *>(palw4 + 4 * j), b = *reinterpret_cast<const double2 *>(palw4 + 4 * j + 2);
-    const double dx = __dsub_rn(x, a.x), dy = __dsub_rn(y, a.y), dz = __dsub_rn(z, b.x);
+// squared distance to palette entry j.  The weighted palette is stored as K (x, y) pairs followed by K z values: one
+// 16-byte and one 8-byte load per candidate, consecutive entries in consecutive bank quads / pairs (the first layout,
+// x y z pad per entry, put every 16-byte load of a warp on four of the eight quads: ncu showed the kernel at 72 %
+// of the shared-memory data pipe's peak)
+__device__ __forceinline__ double dither_dist4(const double *__restrict__ pxy, const double *__restrict__ pz, int j, double x, double y,
+                                               double z) {
+    const double2 a = reinterpret_cast<const double2 *>(pxy)[j];
+    const double dx = __dsub_rn(x, a.x), dy = __dsub_rn(y, a.y), dz = __dsub_rn(z, pz[j]);
     return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
 }
 
@@ -375,6 +379,7 @@ __device__ __forceinline__ int dither_nn4(double x, double y, double z, const do
                                           const DitherGrid &G) {
     double bd = 0.0;
     int best = 0x7fffffff;
+    const double *pz = s_palw + 2 * (size_t)K;
     const int cell = G.cnt ? pb_grid_cell(true, G.geom, G.geom + 3, G.ng, x, y, z) : -1; // uniform within the group
     if (cell >= 0) {
         const unsigned short *Lst = G.list + (size_t)cell * K;
@@ -387,18 +392,18 @@ __device__ __forceinline__ int dither_nn4(double x, double y, double z, const do
             const int t = gl + u * DS_GROUP;
             if (t < m) {
                 const int j = pre[u];
-                const double dd = dither_dist4(s_palw, j, x, y, z);
+                const double dd = dither_dist4(s_palw, pz, j, x, y, z);
                 if (best == 0x7fffffff || dd < bd) { bd = dd; best = j; }
             }
         }
         for (int t = gl + 4 * DS_GROUP; t < m; t += DS_GROUP) {
             const int j = Lst[t];
-            const double dd = dither_dist4(s_palw, j, x, y, z);
+            const double dd = dither_dist4(s_palw, pz, j, x, y, z);
             if (best == 0x7fffffff || dd < bd) { bd = dd; best = j; }
         }
     } else {
         for (int j = gl; j < K; j += DS_GROUP) {
-            const double dd = dither_dist4(s_palw, j, x, y, z);
+            const double dd = dither_dist4(s_palw, pz, j, x, y, z);
             if (best == 0x7fffffff || dd < bd) { bd = dd; best = j; }
         }
     }
@@ -425,15 +430,17 @@ __global__ void __launch_bounds__(DS_WARPS * 32, PB_DS_MINB) k_riemersma_spec4(c
                                                                   uint32_t *__restrict__ hidx, uint32_t *__restrict__ overlap,
                                                                   const void *__restrict__ nngrid,
                                                                   size_t g_first, size_t g_end) {
-    extern __shared__ __align__(16) double s_mem[]; // [K][4] weighted palette, then [K][3] palette
-    const double *s_palw = PAL_SMEM ? s_mem : palw, *s_pal = PAL_SMEM ? s_mem + (size_t)K * 4 : pal;
+    extern __shared__ __align__(16) double s_mem[]; // weighted palette: K (x, y) pairs, K z values; then [K][3] palette
+    const double *s_palw = PAL_SMEM ? s_mem : palw, *s_pal = PAL_SMEM ? s_mem + (size_t)K * 3 : pal;
     __shared__ double s_geom[6];
     __shared__ int s_grid_ok, s_grid_ng;
-    __shared__ double s_px[DS_WARPS][DS_CHAINS][3][16];
-    __shared__ int s_choice[DS_WARPS][DS_CHAINS][16];
+    // (rows padded to 17: with 16 the eight chains' rows of one channel - and the three channels of a chain - start in
+    // the same bank, and the per-step loads px[ch][k] / stores choice[k] of a warp serialise 24 / 4 ways)
+    __shared__ double s_px[DS_WARPS][DS_CHAINS][3][17];
+    __shared__ int s_choice[DS_WARPS][DS_CHAINS][17];
     if (PAL_SMEM) {
-        for (int i = threadIdx.x; i < K * 4; i += blockDim.x) s_mem[i] = palw[i];
-        for (int i = threadIdx.x; i < K * 3; i += blockDim.x) s_mem[(size_t)K * 4 + i] = pal[i];
+        for (int i = threadIdx.x; i < K * 3; i += blockDim.x) s_mem[i] = palw[i];
+        for (int i = threadIdx.x; i < K * 3; i += blockDim.x) s_mem[(size_t)K * 3 + i] = pal[i];
     }
     if (threadIdx.x == 0) {
         s_grid_ok = 0;
@@ -459,7 +466,7 @@ __global__ void __launch_bounds__(DS_WARPS * 32, PB_DS_MINB) k_riemersma_spec4(c
     const bool live = g < g_end && a < n;
     const size_t end = live ? min(n, a + seg) : 0;
     size_t pos = live ? (a > warm ? a - warm : 0) : 0; // a - pos is a multiple of 16 (seg and warm are multiples of 128)
-    double(*px)[16] = s_px[warp][grp];
+    double(*px)[17] = s_px[warp][grp];
     int *choice = s_choice[warp][grp];
     uint32_t *ov = overlap + g * 16;
     double q[16];
@@ -689,7 +696,7 @@ void pb_dither_riemersma(const double *const planes[3], size_t width, size_t hei
         if (g_dither_subwarp && g_dither_one_wave) {
             // one wave: as many chains as the chip (all ranks' chips) holds resident at once - a second, partly filled
             // wave costs as much as the first, and fewer, longer segments mean less warm-up work
-            const size_t smem4 = (size_t)K * 7 * sizeof(double);
+            const size_t smem4 = (size_t)K * 6 * sizeof(double);
             const bool smem4_ok = smem4 <= PB_SMEM_PALETTE_LIMIT;
             if (smem4_ok && smem4 > 32 * 1024)
                 PB_CUDA_OK(cudaFuncSetAttribute(k_riemersma_spec4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
@@ -746,13 +753,13 @@ void pb_dither_riemersma(const double *const planes[3], size_t width, size_t hei
         pb_prof_next_bytes(28.0 * (double)n); // 24 B of colours read + 4 B index written per pixel of the walk
         if (g_dither_subwarp) {
             PB_CUDA_OK(cudaMemcpyToSymbolAsync(c_qw, qw, sizeof qw, 0, cudaMemcpyHostToDevice, st)); // (per device; 128 B)
-            // the weighted palette padded to four doubles per entry (two 16-byte loads per candidate)
-            std::vector<double> palw4((size_t)K * 4, 0.0);
-            for (int j = 0; j < K; j++) { palw4[4 * j] = palw[3 * j]; palw4[4 * j + 1] = palw[3 * j + 1]; palw4[4 * j + 2] = palw[3 * j + 2]; }
+            // the weighted palette as K (x, y) pairs + K z values (one 16-byte and one 8-byte load per candidate)
+            std::vector<double> palw4((size_t)K * 3, 0.0);
+            for (int j = 0; j < K; j++) { palw4[2 * j] = palw[3 * j]; palw4[2 * j + 1] = palw[3 * j + 1]; palw4[2 * (size_t)K + j] = palw[3 * j + 2]; }
             d_palw4 = (double *)pb_pool_alloc(palw4.size() * sizeof(double));
             PB_CUDA_OK(cudaMemcpyAsync(d_palw4, palw4.data(), palw4.size() * sizeof(double), cudaMemcpyHostToDevice, st));
             PB_CUDA_OK(cudaStreamSynchronize(st)); // (palw4 is a local)
-            const size_t smem4 = (size_t)K * 7 * sizeof(double);
+            const size_t smem4 = (size_t)K * 6 * sizeof(double);
             const bool smem4_ok = smem4 <= PB_SMEM_PALETTE_LIMIT;
             if (smem4_ok && smem4 > 32 * 1024)
                 PB_CUDA_OK(cudaFuncSetAttribute(k_riemersma_spec4<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
