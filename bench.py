@@ -442,6 +442,18 @@ def measure_ours(args):
                                "api": "patolette_b200.quantize_u8(numpy uint8 [N,3]) -> u8 map", "h2d_bytes_per_step": 3 * n,
                                "d2h_bytes_per_step": n + 24 * K,
                                "stage_ms": {k: round(v, 3) for k, v in pb.last_timings().items()}}
+            # N3: the reference's DEFAULT call, tile_size = 512 - saliency weights on the device
+            # (pb_saliency.cu), then the weighted pipeline; same 8-bit image
+            pb.quantize_u8(w, h, rgb8, K, tile_size=512, **workload_kwargs(wl))
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                ok, pal8, map8, msg = pb.quantize_u8(w, h, rgb8, K, tile_size=512, **workload_kwargs(wl))
+                assert ok, msg
+            dts = (time.perf_counter() - t0) / reps
+            e2e_extra["u8_saliency"] = {"value": n / dts / 1e6, "unit": "Mpixels/s", "ms_per_step": dts * 1e3, "steps": reps,
+                                        "api": "patolette_b200.quantize_u8(numpy uint8 [N,3], tile_size=512) -> u8 map "
+                                               "(saliency weights + weighted pipeline)",
+                                        "stage_ms": {k: round(v, 3) for k, v in pb.last_timings().items()}}
             del rgb8, pal8, map8
     del colors
 

@@ -121,6 +121,32 @@ PB200_API void patolette_b200_u8(size_t width, size_t height, const uint8_t *rgb
                                  size_t palette_size, const patolette__QuantizationOptions *options, double *palette,
                                  void *palette_map, int map_bytes, int device_io, int *exit_code);
 
+/* N3 (saliency weights): quantize() of the reference's Python wrapper with tile_size > 0
+ * (src/patolette/patolette.pyx:332-466; weights from get_weights(), :203-313: three minimum-barrier-distance raster
+ * scans of the channel mean, four border-strip Mahalanobis maps in CIELab, a centre prior and a sigmoid).  The
+ * weights are computed on the device from the sRGB input and feed the pipeline without leaving it.
+ * colors: in_fmt 0 = three f64 planes (column-major N x 3, as patolette()), 1 = N x 3 row-major f64, 2 = N x 3
+ * row-major uint8 (/ 255 on the device).  tile_size = 0 runs unweighted.  map_bytes / device_io as for
+ * patolette_b200_u8.  Extra exit code -7: the image is too small (a side <= 3) or too elongated for the wrapper's
+ * scans and border strips (the reference raises a Python exception there).
+ * The distance map is the reference's bit for bit (float32 min / max / subtract only); the Lab / Mahalanobis /
+ * sigmoid chain runs in f64 with CUDA's pow / cbrt / exp and agrees with numpy + scikit-image to ~1e-13 relative,
+ * not to the last bit (numpy's SIMD pow and the BLAS matmul inside rgb2lab are not reproducible from here). */
+PB200_API void patolette_b200_quantize(size_t width, size_t height, const void *colors, int in_fmt, double tile_size,
+                                       size_t palette_size, const patolette__QuantizationOptions *options,
+                                       double *palette, void *palette_map, int map_bytes, int device_io,
+                                       int *exit_code);
+/* Stage: get_weights(img, tile_size) (patolette.pyx:203-313).  planar: width*height x 3 f64 column-major sRGB,
+ * pixel p = row * width + col; weights: width*height f64 out.  Returns 0, -7 (see above), -1 (a border strip with a
+ * singular covariance: np.linalg.inv raises in the reference), or a negative cudaError. */
+PB200_API int patolette_b200_saliency_weights(size_t width, size_t height, const double *planar, double tile_size,
+                                              double *weights, int device_io);
+/* Stage: mbd(mean(img, axis = 2).astype(float32), 3) (patolette.pyx:153-201, :204-205): width*height float32 out. */
+PB200_API int patolette_b200_saliency_mbd(size_t width, size_t height, const double *planar, float *distance,
+                                          int device_io);
+/* Milliseconds the saliency stage of the last call took (CUDA events; inside the "color" slot of last_timings). */
+PB200_API double patolette_b200_last_saliency_ms(void);
+
 /* Image-sharded multi-GPU runs (one process per GPU).  The library owns an NCCL communicator:
  * rank 0 calls patolette_b200_comm_unique_id() and hands the 128 bytes to every rank (any transport), then all
  * ranks call patolette_b200_comm_init() (collective; after patolette_b200_set_device()).  world = 1 drops it.

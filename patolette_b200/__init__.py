@@ -25,7 +25,7 @@ bad_channel_count = "Expected colors to be in sRGB[0, 1] space. Channel count mi
 bad_tile_size = "tile_size parameter expected to be in the range [0, inf]"
 
 __all__ = ["__doc__", "__version__", "quantize", "ColorSpace_sRGB", "ColorSpace_CIELuv", "ColorSpace_ICtCp",
-           "quantize_u8", "init_sharding", "shard_range", "quantize_sharded", "sharding_description",
+           "quantize_u8", "saliency_weights", "saliency_mbd", "save_png", "init_sharding", "shard_range", "quantize_sharded", "sharding_description",
            "set_sharding", "torch_allgather"]
 
 
@@ -35,13 +35,16 @@ def quantize(width, height, colors, palette_size, dither=True, palette_only=Fals
     """Same contract as the reference ``quantize`` (src/patolette/patolette.pyx:332-466):
     returns ``(success, palette[K,3] F-order f64 | None, palette_map[N] uintp | None, message)``.
 
-    Differences, both explicit:
-      * ``tile_size > 0`` asks the reference for saliency weights computed with scikit-image
-        (patolette.pyx:203-313).  That pre-processing is outside this package's scope
-        (SURVEY.md section 8f, N3): it raises NotImplementedError unless ``weights`` is given.
-        Pass ``tile_size=0`` for the unweighted path.
-      * ``weights`` (keyword-only, extension): per-pixel f64 weights >= 1 handed straight to
-        the C ABI's ``weights`` argument (lib/include/patolette.h:26).
+    ``tile_size > 0`` (the default, 512) weights the pixels by saliency as the reference's wrapper does
+    (``get_weights``, patolette.pyx:203-313): here the weights are computed on the GPU (pb_saliency.cu) from the sRGB
+    input and never leave the device.  The minimum-barrier distance map is the reference's bit for bit; the Lab /
+    Mahalanobis / sigmoid chain agrees with numpy + scikit-image to ~1e-13 relative, not to the last bit, so a
+    weighted palette can differ from the reference's in its last digits (an unweighted one, ``tile_size=0``, never
+    does).  Where the reference's wrapper raises (a side <= 3, border strips that do not fit the image) this raises
+    ``ValueError``.
+
+    Extension: ``weights`` (keyword-only) - per-pixel f64 weights >= 1 handed straight to the C ABI's ``weights``
+    argument (lib/include/patolette.h:26); ``tile_size`` is then ignored.
     """
     colors = np.asarray(colors)
     if colors.ndim != 2:
@@ -53,10 +56,6 @@ def quantize(width, height, colors, palette_size, dither=True, palette_only=Fals
         return (False, None, None, color_mismatch)
     if tile_size < 0:
         return (False, None, None, bad_tile_size)
-    if weights is None and tile_size > 0:
-        raise NotImplementedError(
-            "saliency weights (tile_size > 0) are not part of patolette_b200; pass tile_size=0 "
-            "or supply weights=...")
     lib = _lib.load()
     # The reference copies to Fortran order on the host (patolette.pyx:388-391).  A C-contiguous f64
     # array is instead handed over as is and de-interleaved on the GPU (same values, no host pass).
@@ -72,11 +71,21 @@ def quantize(width, height, colors, palette_size, dither=True, palette_only=Fals
     opts = _lib.QuantizationOptions(bool(dither), bool(palette_only), int(color_space), int(kmeans_niter),
                                     int(kmeans_max_samples), bool(verbose))
     code = C.c_int(0)
-    entry = lib.patolette_b200_interleaved if interleaved else lib.patolette
-    entry(width, height, data.ctypes.data if color_count else None,
-                  None if w is None else w.ctypes.data, palette_size, C.byref(opts),
-                  palette.ctypes.data if palette_size else None,
-                  None if pmap is None else pmap.ctypes.data, C.byref(code))
+    if w is None and tile_size > 0:  # patolette.pyx:411-415
+        if verbose:
+            print("patolette ======== Generating saliency map")
+        lib.patolette_b200_quantize(width, height, data.ctypes.data if color_count else None, 1 if interleaved else 0,
+                                    float(tile_size), palette_size, C.byref(opts),
+                                    palette.ctypes.data if palette_size else None,
+                                    None if pmap is None else pmap.ctypes.data, 8, 0, C.byref(code))
+        if code.value == -7:
+            raise ValueError(lib.get_patolette_exit_code_info_message(-7).decode("utf-8"))
+    else:
+        entry = lib.patolette_b200_interleaved if interleaved else lib.patolette
+        entry(width, height, data.ctypes.data if color_count else None,
+              None if w is None else w.ctypes.data, palette_size, C.byref(opts),
+              palette.ctypes.data if palette_size else None,
+              None if pmap is None else pmap.ctypes.data, C.byref(code))
     global _shard_error
     if _shard_error is not None:  # the all-gather callback failed: surface it instead of exit code -1
         err, _shard_error = _shard_error, None
@@ -91,12 +100,13 @@ def quantize(width, height, colors, palette_size, dither=True, palette_only=Fals
 
 
 def quantize_u8(width, height, rgb, palette_size, dither=True, palette_only=False, color_space=ColorSpace_ICtCp,
-                kmeans_niter=32, kmeans_max_samples=512 ** 2, verbose=False, *, weights=None):
+                kmeans_niter=32, kmeans_max_samples=512 ** 2, verbose=False, *, weights=None, tile_size=0):
     """N1 (extension): quantise an 8-bit image without the host-side f64 conversion of README.md:150-158.
 
     ``rgb``: uint8 array [N, 3] (or [H, W, 3]).  The division by 255 happens on the device in f64 (the same IEEE
-    operation), so the result equals ``quantize(width, height, rgb / 255.0, ..., tile_size=0)``; the map comes back
-    as uint8 (palette_size <= 256) or uint16 instead of uintp.  Returns (success, palette, palette_map, message)."""
+    operation), so the result equals ``quantize(width, height, rgb / 255.0, ..., tile_size=tile_size)``; the map comes
+    back as uint8 (palette_size <= 256) or uint16 instead of uintp.  ``tile_size > 0`` adds the saliency weights
+    (see :func:`quantize`); note the default here is 0.  Returns (success, palette, palette_map, message)."""
     rgb = np.ascontiguousarray(rgb, dtype=np.uint8).reshape(-1, 3)
     if rgb.shape[0] != width * height:
         return (False, None, None, color_mismatch)
@@ -114,14 +124,61 @@ def quantize_u8(width, height, rgb, palette_size, dither=True, palette_only=Fals
     opts = _lib.QuantizationOptions(bool(dither), bool(palette_only), int(color_space), int(kmeans_niter),
                                     int(kmeans_max_samples), bool(verbose))
     code = C.c_int(0)
-    lib.patolette_b200_u8(width, height, rgb.ctypes.data if rgb.size else None, None if w is None else w.ctypes.data,
-                          palette_size, C.byref(opts), palette.ctypes.data if palette_size else None,
-                          None if pmap is None else pmap.ctypes.data, np.dtype(map_dtype).itemsize, 0, C.byref(code))
+    if tile_size < 0:
+        return (False, None, None, bad_tile_size)
+    if w is None and tile_size > 0:
+        lib.patolette_b200_quantize(width, height, rgb.ctypes.data if rgb.size else None, 2, float(tile_size), palette_size,
+                                    C.byref(opts), palette.ctypes.data if palette_size else None,
+                                    None if pmap is None else pmap.ctypes.data, np.dtype(map_dtype).itemsize, 0,
+                                    C.byref(code))
+        if code.value == -7:
+            raise ValueError(lib.get_patolette_exit_code_info_message(-7).decode("utf-8"))
+    else:
+        lib.patolette_b200_u8(width, height, rgb.ctypes.data if rgb.size else None, None if w is None else w.ctypes.data,
+                              palette_size, C.byref(opts), palette.ctypes.data if palette_size else None,
+                              None if pmap is None else pmap.ctypes.data, np.dtype(map_dtype).itemsize, 0, C.byref(code))
     success = code.value == 0
     message = lib.get_patolette_exit_code_info_message(code.value).decode("utf-8")
     if not success:
         return (success, None, None, message)
     return (success, palette, None if palette_only else pmap, message)
+
+
+def _stage_error(lib, rc: int, what: str):
+    if rc == -7:
+        raise ValueError(lib.get_patolette_exit_code_info_message(-7).decode("utf-8"))
+    if rc != 0:
+        raise RuntimeError(f"patolette_b200: {what} failed ({rc})")
+
+
+def saliency_weights(width, height, colors, tile_size=512):
+    """N3 stage (extension): the per-pixel weights ``quantize(..., tile_size)`` uses - ``get_weights(img, tile_size)``
+    of the reference's wrapper (patolette.pyx:203-313) on the GPU.  ``colors``: [N, 3] sRGB in [0, 1], pixel
+    p = row * width + col.  Returns N float64 weights (each >= 1)."""
+    colors = np.asarray(colors)
+    if colors.ndim != 2 or colors.shape[1] != 3 or colors.shape[0] != width * height:
+        raise ValueError(color_mismatch)
+    if not tile_size > 0:
+        raise ValueError(bad_tile_size)
+    lib = _lib.load()
+    data = np.asfortranarray(colors, dtype=np.float64)
+    out = np.empty(width * height, dtype=np.float64)
+    _stage_error(lib, lib.patolette_b200_saliency_weights(width, height, data.ctypes.data, float(tile_size),
+                                                          out.ctypes.data, 0), "saliency_weights")
+    return out
+
+
+def saliency_mbd(width, height, colors):
+    """N3 stage (extension): the minimum-barrier distance map ``mbd(mean(img, axis=2).astype(float32), 3)``
+    (patolette.pyx:153-201) as a [height, width] float32 array - bit for bit the reference's."""
+    colors = np.asarray(colors)
+    if colors.ndim != 2 or colors.shape[1] != 3 or colors.shape[0] != width * height:
+        raise ValueError(color_mismatch)
+    lib = _lib.load()
+    data = np.asfortranarray(colors, dtype=np.float64)
+    out = np.empty((height, width), dtype=np.float32)
+    _stage_error(lib, lib.patolette_b200_saliency_mbd(width, height, data.ctypes.data, out.ctypes.data, 0), "saliency_mbd")
+    return out
 
 
 def save_png(path, width, height, palette, palette_map, compress_level=6):
@@ -291,4 +348,6 @@ def last_timings() -> dict:
     out = (C.c_double * 10)()
     _lib.load().patolette_b200_last_timings(out)
     keys = ["total", "h2d", "color", "gq", "lq", "kmeans", "nearest", "dither", "d2h", "launches"]
-    return dict(zip(keys, list(out)))
+    t = dict(zip(keys, list(out)))
+    t["saliency"] = float(_lib.load().patolette_b200_last_saliency_ms())  # part of "color"
+    return t

@@ -93,6 +93,7 @@ void shard_merge(PbStats *rows, int count, bool mean_pass, bool weighted) {
 cudaStream_t g_user_stream = nullptr;
 bool g_use_user_stream = false;
 double g_timings[10] = {0};
+double g_saliency_ms = 0.0; // time of the saliency stage of the last call (part of the "color" slot)
 
 template <typename T>
 struct DevArr {
@@ -920,7 +921,7 @@ __global__ void __launch_bounds__(256) k_fp64_peak(double *out, int iters, doubl
     if (s == 12345.678) out[0] = s; // never true: keeps the chains alive
 }
 
-const char *k_messages[7] = {
+const char *k_messages[8] = {
     "Quantization successful.",
     "Internal quantization error.",
     "Image dimensions should be greater than 0.",
@@ -928,6 +929,7 @@ const char *k_messages[7] = {
     "Image dimensions are too big.",
     "CUDA error (no usable sm_100 device, or out of device memory).",
     "Palette size above 50000 with KMeans refinement (kmeans_niter > 0) is not supported by patolette_b200.",
+    "Saliency weights (tile_size > 0) need an image with both sides above 3 and border strips that fit: 1 <= floor(0.1 * sqrt(width * height)) < min(width, height).",
 };
 
 // Palette (K x 3 row-major, host) through one of the colour kernels.
@@ -964,6 +966,7 @@ struct IoSpec {
     int in_fmt = 0;         // 0: three f64 planes (column-major N x 3), 1: N x 3 row-major f64, 2: N x 3 row-major uint8 (/ 255 on the device)
     int map_bytes = 8;      // palette_map element: 8 (size_t), 1 or 2
     bool sharded = false;   // data / weights / map hold this rank's pixel slice only (NCCL communicator required)
+    double tile_size = 0.0; // > 0 and no weights given: saliency weights from the sRGB input (patolette.pyx:411-415, row N3)
 };
 enum { IN_PLANAR = 0, IN_INTERLEAVED = 1, IN_U8 = 2 };
 
@@ -976,14 +979,18 @@ void run_patolette(size_t width, size_t height, const void *data_v, const double
     // memory: beyond PB_KMEANS_MAX_K the call fails with its own code instead of silently skipping refinement
     if (opt->kmeans_niter > 0 && K > PB_KMEANS_MAX_K && n >= K) { *exit_code = -6; return; }
     if (io.sharded && !pb_nccl_active()) { *exit_code = -1; return; }
+    // saliency needs the whole image on one device (raster scans, border strips): not offered for pixel slices
+    const bool saliency = io.tile_size > 0.0 && weights == nullptr;
+    if (saliency && io.sharded) { *exit_code = -1; return; }
     memset(g_timings, 0, sizeof g_timings);
+    g_saliency_ms = 0.0;
     const long launches0 = pb_prof_launch_count();
     Quantizer qz;
     qz.sh = make_shard_ctx(n, io.sharded);
     const ShardCtx &sh = qz.sh;
     // the caller's buffers cover pixels [in_off, in_off + in_n) of the image
     const size_t in_n = sh.on ? sh.count : n, in_off = sh.on ? sh.first : 0;
-    qz.init(n, weights != nullptr, sh.on ? sh.S * (size_t)sh.world : n);
+    qz.init(n, weights != nullptr || saliency, sh.on ? sh.S * (size_t)sh.world : n);
     Timer total(qz.st), stage(qz.st);
     total.start();
     struct SideStream { // copies that overlap kernels of the compute stream (pinned host buffers only)
@@ -1019,6 +1026,7 @@ void run_patolette(size_t width, size_t height, const void *data_v, const double
         }
     };
     const bool pinned_in = !device_io && in_n >= ((size_t)1 << 20) && pb_host_is_pinned(data_v);
+    const int to_space_piped = saliency ? -1 : to_space; // the saliency stage reads the sRGB planes first
     DevArr<uint8_t> rgb8;
     if (io.in_fmt == IN_U8) { // N1: uint8 RGB in, / 255 on the device
         const uint8_t *src = (const uint8_t *)data_v;
@@ -1032,8 +1040,9 @@ void run_patolette(size_t width, size_t height, const void *data_v, const double
                       double *const d[3] = {cdst[0] + off, cdst[1] + off, cdst[2] + off};
                       pb_prof_next_bytes(27.0 * len);
                       pb_launch_u8_to_planes(rgb8.p + 3 * off, len, d, qz.sm_count, qz.st);
-                      if (to_space >= 0) colors_transform(qz, to_space, in_off + off, len);
+                      if (to_space_piped >= 0) colors_transform(qz, to_space_piped, in_off + off, len);
                   });
+            piped_color = !saliency;
         } else {
             if (device_io) PB_CUDA_OK(cudaMemcpyAsync(rgb8.p, src, 3 * in_n, in_kind, qz.st));
             else pb_copy_h2d(rgb8.p, src, 3 * in_n, qz.st);
@@ -1057,8 +1066,9 @@ void run_patolette(size_t width, size_t height, const void *data_v, const double
                       PB_CUDA_OK(cudaMemcpyAsync(cdst[j] + off, data + (size_t)j * in_n + off, len * sizeof(double), in_kind, copy_stream.get()));
               },
               [&](size_t off, size_t len) {
-                  if (to_space >= 0) colors_transform(qz, to_space, in_off + off, len);
+                  if (to_space_piped >= 0) colors_transform(qz, to_space_piped, in_off + off, len);
               });
+        piped_color = !saliency;
     } else {
         const double *data = (const double *)data_v;
         for (int j = 0; j < 3 && in_n; j++) {
@@ -1073,6 +1083,14 @@ void run_patolette(size_t width, size_t height, const void *data_v, const double
     set_timing(1, stage.stop());
 
     stage.start(); // patolette.c:201-207
+    if (saliency) { // patolette.pyx:411-415: the weights come from the sRGB image, before the colour transform
+        Timer sal(qz.st);
+        sal.start();
+        const double *planes[3] = {qz.col[0].p, qz.col[1].p, qz.col[2].p};
+        const int rc = pb_saliency_weights(planes, width, height, io.tile_size, qz.wgt.p, qz.sm_count, qz.st);
+        g_saliency_ms = sal.stop();
+        if (rc != 0) { *exit_code = rc; return; }
+    }
     if (!piped_color && to_space >= 0) colors_transform(qz, to_space, in_off, in_n);
     if (sh.on) { // every rank transformed its slice: all-gather the planes over NVLink (in place)
         const size_t sbytes = sh.S * sizeof(double);
@@ -1318,6 +1336,68 @@ void patolette_b200_u8(size_t width, size_t height, const uint8_t *rgb, const do
     });
 }
 
+void patolette_b200_quantize(size_t width, size_t height, const void *colors, int in_fmt, double tile_size,
+                             size_t palette_size, const patolette__QuantizationOptions *options, double *palette,
+                             void *palette_map, int map_bytes, int device_io, int *exit_code) {
+    *exit_code = 0;
+    if (width * height == 0) { *exit_code = -2; return; }
+    if (palette_size < 1) { *exit_code = -3; return; }
+    if (width * height > (size_t)40000 * 40000) { *exit_code = -4; return; }
+    if (in_fmt < IN_PLANAR || in_fmt > IN_U8 || !(tile_size >= 0.0)) { *exit_code = -1; return; }
+    if (!(map_bytes == 1 || map_bytes == 2 || map_bytes == 8) || (map_bytes == 1 && palette_size > 256) ||
+        (map_bytes == 2 && palette_size > 65536)) { *exit_code = -3; return; }
+    guarded_run(exit_code, [&] {
+        IoSpec io;
+        io.in_fmt = in_fmt;
+        io.map_bytes = map_bytes;
+        io.device_io = device_io != 0;
+        io.tile_size = tile_size;
+        run_patolette(width, height, colors, nullptr, palette_size, options, palette, palette_map, exit_code, io);
+    });
+}
+
+// get_weights / mbd of the reference's wrapper as stages (patolette.pyx:203-313, :153-201)
+static int saliency_stage(size_t width, size_t height, const double *planar, double tile_size, void *out, int device_io, bool mbd_only) {
+    const size_t n = width * height;
+    if (n == 0 || !planar || !out || (!mbd_only && !(tile_size > 0.0))) return -1;
+    return guarded_stage([&]() -> int {
+        Quantizer qz;
+        qz.init(n, !mbd_only);
+        const cudaMemcpyKind in_kind = device_io ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+        for (int j = 0; j < 3; j++) {
+            if (device_io) PB_CUDA_OK(cudaMemcpyAsync(qz.col[j].p, planar + (size_t)j * n, n * sizeof(double), in_kind, qz.st));
+            else pb_copy_h2d(qz.col[j].p, planar + (size_t)j * n, n * sizeof(double), qz.st);
+        }
+        const double *planes[3] = {qz.col[0].p, qz.col[1].p, qz.col[2].p};
+        Timer sal(qz.st);
+        sal.start();
+        int rc;
+        DevArr<float> dmap;
+        if (mbd_only) {
+            dmap.alloc(n);
+            rc = pb_saliency_mbd(planes, width, height, dmap.p, qz.sm_count, qz.st);
+        } else {
+            rc = pb_saliency_weights(planes, width, height, tile_size, qz.wgt.p, qz.sm_count, qz.st);
+        }
+        g_saliency_ms = sal.stop();
+        if (rc != 0) return rc;
+        const void *from = mbd_only ? (const void *)dmap.p : (const void *)qz.wgt.p;
+        const size_t bytes = n * (mbd_only ? sizeof(float) : sizeof(double));
+        if (device_io) PB_CUDA_OK(cudaMemcpyAsync(out, from, bytes, cudaMemcpyDeviceToDevice, qz.st));
+        else pb_copy_d2h(out, from, bytes, qz.st);
+        qz.sync();
+        return 0;
+    });
+}
+int patolette_b200_saliency_weights(size_t width, size_t height, const double *planar, double tile_size, double *weights,
+                                    int device_io) {
+    return saliency_stage(width, height, planar, tile_size, weights, device_io, false);
+}
+int patolette_b200_saliency_mbd(size_t width, size_t height, const double *planar, float *distance, int device_io) {
+    return saliency_stage(width, height, planar, 0.0, distance, device_io, true);
+}
+double patolette_b200_last_saliency_ms(void) { return g_saliency_ms; }
+
 void patolette_b200_sharded(size_t width, size_t height, const double *slice, const double *weights_slice,
                             size_t palette_size, const patolette__QuantizationOptions *options, double *palette,
                             size_t *map_slice, int device_io, int *exit_code) {
@@ -1470,7 +1550,7 @@ size_t patolette_b200_profile_timeline(char *buf, size_t cap) {
 
 const char *get_patolette_exit_code_info_message(int exit_code) {
     int i = -exit_code;
-    if (i < 0 || i > 6) i = 1;
+    if (i < 0 || i > 7) i = 1;
     return k_messages[i];
 }
 

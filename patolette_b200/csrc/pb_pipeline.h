@@ -22,6 +22,13 @@ struct PbDitherShard {
 void pb_dither_riemersma(const double *const planes[3], size_t width, size_t height,
                          const std::vector<double> &pal_rm, unsigned long long *d_map, int sm_count,
                          cudaStream_t st, long *launches, const PbDitherShard *shard = nullptr);
+// Saliency weights of the reference's Python wrapper (pb_saliency.cu; patolette.pyx:54-313).  planes: device sRGB
+// planes in [0, 1]; d_weights: device, n doubles.  0, -7 (image too small / too elongated for the wrapper's scans and
+// border strips: the reference raises there) or -1 (a border strip with a singular covariance).
+int pb_saliency_weights(const double *const planes[3], size_t width, size_t height, double tile_size, double *d_weights,
+                        int sm_count, cudaStream_t st);
+// the minimum-barrier distance map alone (patolette.pyx:153-201), float32, n values
+int pb_saliency_mbd(const double *const planes[3], size_t width, size_t height, float *d_out, int sm_count, cudaStream_t st);
 // test knob: candidate-list nearest-neighbour search inside the dither (default on)
 void pb_dither_set_grid(bool on);
 // test knob: 4 lanes per speculative chain (default) or one warp per chain

@@ -1,0 +1,480 @@
+// pb_saliency.cu - row N3: the saliency weights the reference's Python wrapper computes before it calls patolette()
+// (src/patolette/patolette.pyx:54-313: `mbd` = three raster scans of a minimum-barrier distance on the channel mean,
+// `get_weights` = that map + four border-colour Mahalanobis maps in CIELab, a centre prior and a sigmoid).
+//
+// Everything here is per-pixel work, a handful of global maxima - and ONE genuinely sequential part: a raster scan
+// updates pixel (x, y) from its upper and its left neighbour, both already updated.  The data flow is a wavefront, and
+// k_mbd_pass runs it as a systolic array: a warp owns 32 consecutive rows, lane t is row t, and at step s lane t works
+// on column s - t.  The left neighbour is the lane's own previous result (registers), the upper neighbour is lane
+// t-1's result of the previous step (one shuffle); the row above a warp's first row belongs to the previous warp,
+// which publishes how many columns its last row has finished (release store / acquire poll).  rows + cols steps per
+// scan instead of rows * cols.  The scan only takes float32 max / min / subtract, so the distance map is the
+// reference's bit for bit.
+//
+// The rest follows the wrapper in f64 with CUDA's libm (`pow`, `cbrt`, `exp`, `sqrt`): numpy's own vector pow / cbrt and
+// scikit-image's rgb2lab are not reproducible to the last bit from here (and scikit-image is not even installed to
+// compare with), so the weights carry a floating-point tolerance, not bit parity (tests/test_saliency.py states it).
+// Reductions are deterministic: maxima, and sums through per-CTA partials combined in a fixed order.
+#include <math.h>
+
+#include <vector>
+
+#include "pb_common.cuh"
+#include "pb_pipeline.h"
+#include "pb_pool.h"
+#include "pb_prof.h"
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+// skimage.color.rgb2lab, illuminant D65 / observer 2 (colorconv.py: rgb2xyz + xyz2lab)
+__device__ __forceinline__ void rgb_to_lab(double r, double g, double b, double &L, double &A, double &B) {
+    auto lin = [](double c) { return c > 0.04045 ? pow((c + 0.055) / 1.055, 2.4) : c / 12.92; };
+    r = lin(r); g = lin(g); b = lin(b);
+    double x = (r * 0.412453 + g * 0.357580 + b * 0.180423) / 0.95047;
+    double y = (r * 0.212671 + g * 0.715160 + b * 0.072169) / 1.0;
+    double z = (r * 0.019334 + g * 0.119193 + b * 0.950227) / 1.08883;
+    auto f = [](double t) { return t > 0.008856 ? cbrt(t) : 7.787 * t + 16.0 / 116.0; };
+    x = f(x); y = f(y); z = f(z);
+    L = 116.0 * y - 16.0;
+    A = 500.0 * (x - y);
+    B = 200.0 * (y - z);
+}
+
+// patolette.pyx:204 (np.mean over the channels, cast to float32), :157-169 (L = U = img, D = inf inside / 0 on the
+// border), :213 (rgb2lab)
+__global__ void __launch_bounds__(256) k_sal_prepare(const double *__restrict__ c0, const double *__restrict__ c1,
+                                                     const double *__restrict__ c2, uint32_t rows, uint32_t cols,
+                                                     float *__restrict__ img, float *__restrict__ Lm, float *__restrict__ Um,
+                                                     float *__restrict__ Dm, double *__restrict__ lab0, double *__restrict__ lab1,
+                                                     double *__restrict__ lab2) {
+    const size_t n = (size_t)rows * cols;
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (size_t)gridDim.x * blockDim.x) {
+        const double r = c0[p], g = c1[p], b = c2[p];
+        const float m = (float)(((r + g) + b) / 3.0);
+        const uint32_t x = (uint32_t)(p / cols), y = (uint32_t)(p % cols);
+        img[p] = m; Lm[p] = m; Um[p] = m;
+        Dm[p] = (x == 0 || y == 0 || x == rows - 1 || y == cols - 1) ? 0.0f : INFINITY;
+        double L, A, B;
+        rgb_to_lab(r, g, b, L, A, B);
+        lab0[p] = L; lab1[p] = A; lab2[p] = B;
+    }
+}
+
+__device__ __forceinline__ float ld_cg(const float *p) {
+    float v;
+    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int ld_acquire(const int *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int *p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// One raster scan (patolette.pyx:54-100) or inverse scan (:102-151) as a systolic wavefront; see the file header.
+//
+// In scan coordinates (i = visiting order of the rows, c = visiting order of the columns) pixel (i, c) needs
+// (i - 1, c) and (i, c - 1).  A warp owns rows 32 g .. 32 g + 31 (one CTA = one warp; g is taken from a ticket, so a
+// warp's predecessor is always resident or done).  The warp walks SKEWED tiles: in tile k, at step j, lane t works on
+// column 32 k + j - t - so all 32 lanes are busy in every step, the left neighbour is the lane's own previous result
+// and the upper neighbour is lane t - 1's previous result (one shuffle).  A tile's 32 x 32 pixels of img / D / U / L
+// are brought into shared memory with coalesced row segments first and written back the same way, so the 32 dependent
+// steps in between touch no global memory.  Lane 0's upper neighbours (row 32 g - 1, columns 32 k .. 32 k + 31)
+// belong to the previous warp, which finishes them in ITS tiles k and k + 1 and publishes the number of tiles it has
+// written back (release store / acquire poll).  A scan costs about cols / 32 + 2 rows / 32 tile times.
+constexpr int MBD_T = 32;
+__global__ void __launch_bounds__(32) k_mbd_pass(const float *__restrict__ img, float *Lm, float *Um, float *Dm, int rows, int cols,
+                                                 int inverse, int *progress /* [groups] tiles written back, [groups] = ticket */,
+                                                 int groups) {
+    __shared__ float sI[MBD_T][MBD_T + 1], sD[MBD_T][MBD_T + 1], sU[MBD_T][MBD_T + 1], sL[MBD_T][MBD_T + 1];
+    __shared__ float upU_s[MBD_T], upL_s[MBD_T];
+    const int lane = threadIdx.x;
+    int g = 0;
+    if (lane == 0) g = atomicAdd(progress + groups, 1);
+    g = __shfl_sync(FULL, g, 0);
+    // the raster scan visits x = 1 .. rows-2, y = 1 .. cols-2; the inverse scan x = rows-2 .. 2, y = cols-2 .. 2
+    const int R = inverse ? rows - 3 : rows - 2, Cn = inverse ? cols - 3 : cols - 2;
+    const int ntiles = (Cn + 31 + 31) / 32; // steps 0 .. Cn + 30
+    auto row_of = [&](int i) { return inverse ? rows - 2 - i : 1 + i; };
+    auto col_of = [&](int c) { return inverse ? cols - 2 - c : 1 + c; };
+    const int i = g * 32 + lane;
+    const bool row_ok = i < R;
+    float uleft = 0.f, lleft = 0.f; // U, L of the column this row visited last (starts on the border column)
+    if (row_ok) {
+        const size_t b = (size_t)row_of(i) * cols + (inverse ? cols - 1 : 0);
+        uleft = Um[b];
+        lleft = Lm[b];
+    }
+    const size_t uprow = (size_t)(inverse ? row_of(g * 32) + 1 : row_of(g * 32) - 1) * cols; // the row above this warp's first
+    float myU = 0.f, myL = 0.f; // this lane's U, L at the column it visited last (the next lane's upper neighbour)
+    for (int k = 0; k < ntiles; k++) {
+        // ---- tile in: row r of the tile holds columns 32 k - r .. 32 k - r + 31 of scan row 32 g + r
+#pragma unroll 8
+        for (int r = 0; r < 32; r++) {
+            const int ir = g * 32 + r, c = 32 * k + lane - r;
+            if (ir < R && c >= 0 && c < Cn) {
+                const size_t p = (size_t)row_of(ir) * cols + col_of(c);
+                sI[r][lane] = img[p]; sD[r][lane] = Dm[p]; sU[r][lane] = Um[p]; sL[r][lane] = Lm[p];
+            }
+        }
+        // ---- lane 0's upper neighbours
+        {
+            const int c = 32 * k + lane;
+            if (g > 0) { // wait until the previous warp has written back its tiles k and k + 1
+                const int need = k + 2 < ntiles ? k + 2 : ntiles;
+                if (lane == 0)
+                    while (ld_acquire(progress + g - 1) < need) {}
+                __syncwarp();
+                __threadfence();
+            }
+            if (c < Cn) {
+                upU_s[lane] = ld_cg(Um + uprow + col_of(c));
+                upL_s[lane] = ld_cg(Lm + uprow + col_of(c));
+            }
+        }
+        __syncwarp();
+        // ---- 32 dependent steps out of shared memory
+#pragma unroll 4
+        for (int j = 0; j < 32; j++) {
+            float upU = __shfl_up_sync(FULL, myU, 1), upL = __shfl_up_sync(FULL, myL, 1);
+            const int c = 32 * k + j - lane;
+            if (row_ok && c >= 0 && c < Cn) {
+                if (lane == 0) { upU = upU_s[j]; upL = upL_s[j]; }
+                const float ix = sI[lane][j], d = sD[lane][j];
+                float curU = sU[lane][j], curL = sL[lane][j];
+                const float b1 = fmaxf(upU, ix) - fminf(upL, ix), b2 = fmaxf(uleft, ix) - fminf(lleft, ix);
+                if (d <= b1 && d <= b2) {
+                    // unchanged
+                } else if (b1 < d && b1 <= b2) {
+                    curU = fmaxf(upU, ix); curL = fminf(upL, ix);
+                    sD[lane][j] = b1; sU[lane][j] = curU; sL[lane][j] = curL;
+                } else {
+                    curU = fmaxf(uleft, ix); curL = fminf(lleft, ix);
+                    sD[lane][j] = b2; sU[lane][j] = curU; sL[lane][j] = curL;
+                }
+                uleft = curU; lleft = curL; myU = curU; myL = curL;
+            }
+        }
+        __syncwarp();
+        // ---- tile out
+#pragma unroll 4
+        for (int r = 0; r < 32; r++) {
+            const int ir = g * 32 + r, c = 32 * k + lane - r;
+            if (ir < R && c >= 0 && c < Cn) {
+                const size_t p = (size_t)row_of(ir) * cols + col_of(c);
+                Dm[p] = sD[r][lane]; Um[p] = sU[r][lane]; Lm[p] = sL[r][lane];
+            }
+        }
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) st_release(progress + g, k + 1);
+    }
+}
+
+// ---- border strips (patolette.pyx:215-239): rows [0, bt), rows [rows-bt-1, rows-1), cols [0, bt), cols [cols-bt-1, cols-1)
+struct SalStrips { int bt; };
+__device__ __forceinline__ unsigned strip_mask(uint32_t x, uint32_t y, uint32_t rows, uint32_t cols, uint32_t bt) {
+    unsigned m = 0;
+    if (x < bt) m |= 1u;
+    if (x + bt + 1 >= rows && x + 1 < rows) m |= 2u;
+    if (y < bt) m |= 4u;
+    if (y + bt + 1 >= cols && y + 1 < cols) m |= 8u;
+    return m;
+}
+constexpr int SS_CTAS = 512, SS_THREADS = 256;
+// PASS 0: sums of the Lab values per strip; PASS 1: sums of the centred products (00 01 02 11 12 22) per strip.
+// Per-CTA partials, combined in CTA order by k_strip_finish: the same bits in every run.
+template <int PASS>
+__global__ void __launch_bounds__(SS_THREADS) k_strip_partial(const double *__restrict__ l0, const double *__restrict__ l1,
+                                                              const double *__restrict__ l2, uint32_t rows, uint32_t cols, uint32_t bt,
+                                                              const double *__restrict__ means /* [4][3] (PASS 1) */,
+                                                              double *__restrict__ partial /* [CTA][4][6] */) {
+    constexpr int NV = PASS == 0 ? 3 : 6;
+    __shared__ double red[SS_THREADS / 32][4][6];
+    double acc[4][NV];
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+#pragma unroll
+        for (int v = 0; v < NV; v++) acc[k][v] = 0.0;
+    const size_t n = (size_t)rows * cols;
+    for (size_t p = (size_t)blockIdx.x * SS_THREADS + threadIdx.x; p < n; p += (size_t)gridDim.x * SS_THREADS) {
+        const uint32_t x = (uint32_t)(p / cols), y = (uint32_t)(p % cols);
+        const unsigned m = strip_mask(x, y, rows, cols, bt);
+        if (!m) continue;
+        const double a = l0[p], b = l1[p], c = l2[p];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (!(m >> k & 1u)) continue;
+            if (PASS == 0) {
+                acc[k][0] += a; acc[k][1] += b; acc[k][2] += c;
+            } else {
+                const double da = a - means[k * 3], db = b - means[k * 3 + 1], dc = c - means[k * 3 + 2];
+                acc[k][0] += da * da; acc[k][1] += da * db; acc[k][2] += da * dc;
+                acc[k][3] += db * db; acc[k][4] += db * dc; acc[k][5] += dc * dc;
+            }
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+#pragma unroll
+        for (int v = 0; v < NV; v++) {
+            double t = acc[k][v];
+            for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(FULL, t, o);
+            if (lane == 0) red[warp][k][v] = t;
+        }
+    __syncthreads();
+    if (threadIdx.x < 4 * NV) {
+        const int k = threadIdx.x / NV, v = threadIdx.x % NV;
+        double t = 0.0;
+        for (int w = 0; w < SS_THREADS / 32; w++) t += red[w][k][v];
+        partial[((size_t)blockIdx.x * 4 + k) * 6 + v] = t;
+    }
+}
+__global__ void k_strip_finish(const double *__restrict__ partial, int nctas, int nv, double *__restrict__ out /* [4][6] */) {
+    const int k = threadIdx.x / 6, v = threadIdx.x % 6;
+    if (threadIdx.x >= 24 || v >= nv) return;
+    double t = 0.0;
+    for (int c = 0; c < nctas; c++) t += partial[((size_t)c * 4 + k) * 6 + v];
+    out[k * 6 + v] = t;
+}
+
+// ---- the per-pixel chain of get_weights (patolette.pyx:241-313), cut where a global maximum is needed --------------
+struct SalParams {
+    double mean[4][3];
+    double vi[4][9];
+    double umax[4];      // float32-rounded maxima of the four Mahalanobis maps
+    double u_max_final;  // float32-rounded maximum of u_final
+    float sal_max;       // maximum of the distance map
+    double m1, m2;       // maxima of the two later stages
+    double w2, h2, diag; // rows / 2, cols / 2, sqrt(w2^2 + h2^2)
+    double scale;        // rows * cols (as the wrapper forms it), tile_size^2
+    double tile2;
+};
+__device__ __forceinline__ double mahalanobis(const SalParams &P, int k, double a, double b, double c) {
+    const double d0 = a - P.mean[k][0], d1 = b - P.mean[k][1], d2 = c - P.mean[k][2];
+    const double *V = P.vi[k];
+    const double t0 = d0 * V[0] + d1 * V[3] + d2 * V[6], t1 = d0 * V[1] + d1 * V[4] + d2 * V[7], t2 = d0 * V[2] + d1 * V[5] + d2 * V[8];
+    return sqrt(t0 * d0 + t1 * d1 + t2 * d2);
+}
+__device__ __forceinline__ double u_final_of(const SalParams &P, double a, double b, double c) {
+    double u[4], um = 0.0, sum = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) u[k] = mahalanobis(P, k, a, b, c) / P.umax[k];
+    um = fmax(fmax(fmax(u[0], u[1]), u[2]), u[3]);
+    sum = ((u[0] + u[1]) + u[2]) + u[3];
+    return sum - um;
+}
+__device__ __forceinline__ double s1_of(const SalParams &P, float d, double a, double b, double c) {
+    return (double)(d / P.sal_max) + u_final_of(P, a, b, c) / P.u_max_final; // float32 / float32, then f64
+}
+__device__ __forceinline__ double s2_of(const SalParams &P, float d, double a, double b, double c, uint32_t x, uint32_t y) {
+    const double s = s1_of(P, d, a, b, c) / P.m1;
+    const double dx = (double)y - P.h2, dy = (double)x - P.w2;
+    const double C = 1.0 - sqrt(dx * dx + dy * dy) / P.diag;
+    return s * C;
+}
+__device__ __forceinline__ void atomic_max_pos(unsigned long long *slot, double v) { // v >= 0: bit patterns order like the values
+    if (v == v) atomicMax(slot, (unsigned long long)__double_as_longlong(v));
+}
+// STAGE 0: maxima of the four Mahalanobis maps -> out[0..3]; 1: max u_final -> out[0], max D -> out[1];
+// 2: max s1 -> out[0]; 3: max s2 -> out[0]; 4: the weights
+template <int STAGE>
+__global__ void __launch_bounds__(256) k_sal_stage(SalParams P, const double *__restrict__ l0, const double *__restrict__ l1,
+                                                   const double *__restrict__ l2, const float *__restrict__ Dm, uint32_t rows,
+                                                   uint32_t cols, unsigned long long *__restrict__ out, double *__restrict__ weights) {
+    const size_t n = (size_t)rows * cols;
+    double m[4] = {0.0, 0.0, 0.0, 0.0};
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (size_t)gridDim.x * blockDim.x) {
+        const double a = l0[p], b = l1[p], c = l2[p];
+        if (STAGE == 0) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) m[k] = fmax(m[k], mahalanobis(P, k, a, b, c));
+        } else if (STAGE == 1) {
+            m[0] = fmax(m[0], u_final_of(P, a, b, c));
+            m[1] = fmax(m[1], (double)Dm[p]);
+        } else if (STAGE == 2) {
+            m[0] = fmax(m[0], s1_of(P, Dm[p], a, b, c));
+        } else {
+            const uint32_t x = (uint32_t)(p / cols), y = (uint32_t)(p % cols);
+            const double s2 = s2_of(P, Dm[p], a, b, c, x, y);
+            if (STAGE == 3) m[0] = fmax(m[0], s2);
+            else {
+                const double v = s2 / P.m2;
+                const double f = 1.0 / (1.0 + exp(-10.0 * (v - 0.5)));
+                weights[p] = 1.0 + f * f * P.scale / P.tile2;
+            }
+        }
+    }
+    if (STAGE == 4) return;
+    constexpr int NM = STAGE == 0 ? 4 : (STAGE == 1 ? 2 : 1);
+#pragma unroll
+    for (int k = 0; k < NM; k++) {
+        double t = m[k];
+        for (int o = 16; o; o >>= 1) t = fmax(t, __shfl_xor_sync(FULL, t, o));
+        if ((threadIdx.x & 31) == 0) atomic_max_pos(out + k, t);
+    }
+}
+
+bool invert3(const double c[6] /* 00 01 02 11 12 22 */, double vi[9]) {
+    const double a = c[0], b = c[1], cc = c[2], d = c[3], e = c[4], f = c[5];
+    const double A = d * f - e * e, B = -(b * f - cc * e), C = b * e - cc * d;
+    const double det = a * A + b * B + cc * C;
+    if (!(fabs(det) > 0.0) || !std::isfinite(det)) return false;
+    const double D = a * f - cc * cc, E = -(a * e - b * cc), F = a * d - b * b;
+    const double inv[9] = {A / det, B / det, C / det, B / det, D / det, E / det, C / det, E / det, F / det};
+    for (int i = 0; i < 9; i++) vi[i] = inv[i];
+    return true;
+}
+
+} // namespace
+
+// planes: device sRGB planes in [0, 1], pixel p = row * width + col (rows = height, cols = width as the wrapper
+// reshapes, patolette.pyx:411).  Returns 0, -7 for images the scans cannot run on (a side <= 3, :154-155: the reference
+// raises there), -1 when a border strip has a singular covariance (np.linalg.inv raises in the reference).
+int pb_saliency_weights(const double *const planes[3], size_t width, size_t height, double tile_size, double *d_weights, int sm_count,
+                        cudaStream_t st) {
+    const uint32_t rows = (uint32_t)height, cols = (uint32_t)width;
+    if (rows <= 3 || cols <= 3) return -7;
+    const size_t n = (size_t)rows * cols;
+    const uint32_t bt = (uint32_t)floor(0.1 * sqrt((double)(rows * (double)cols)));
+    // patolette.pyx:215-239: the four strips are reshaped to exactly bt rows (columns); a strip that does not fit makes
+    // the reference raise, and bt = 0 gives it empty strips (NaN weights)
+    if (bt < 1 || bt + 1 > rows || bt + 1 > cols) return -7;
+    float *f32 = nullptr;
+    double *lab = nullptr, *small = nullptr;
+    int *progress = nullptr;
+    int rc = 0;
+    auto cleanup = [&]() { pb_pool_free(f32); pb_pool_free(lab); pb_pool_free(small); pb_pool_free(progress); };
+    try {
+        f32 = (float *)pb_pool_alloc(4 * n * sizeof(float));
+        lab = (double *)pb_pool_alloc(3 * n * sizeof(double));
+        const int groups = (int)((rows + 31) / 32);
+        progress = (int *)pb_pool_alloc(((size_t)groups + 1) * sizeof(int));
+        small = (double *)pb_pool_alloc(((size_t)SS_CTAS * 24 + 64) * sizeof(double));
+        float *img = f32, *Lm = f32 + n, *Um = f32 + 2 * n, *Dm = f32 + 3 * n;
+        double *l0 = lab, *l1 = lab + n, *l2 = lab + 2 * n;
+        double *partial = small, *sums = small + (size_t)SS_CTAS * 24;            // [24]
+        unsigned long long *maxima = reinterpret_cast<unsigned long long *>(small + (size_t)SS_CTAS * 24 + 32); // [8]
+        const size_t want = (n + 255) / 256, cap = (size_t)sm_count * 8;
+        const int grid = (int)(want < cap ? want : cap);
+        { PbProfScope p("k_sal_prepare", st);
+          k_sal_prepare<<<grid, 256, 0, st>>>(planes[0], planes[1], planes[2], rows, cols, img, Lm, Um, Dm, l0, l1, l2); }
+        for (int it = 0; it < 3; it++) { // patolette.pyx:183-199: inverse, raster, inverse
+            const int inverse = it % 2 == 0;
+            const int R = inverse ? (int)rows - 3 : (int)rows - 2;
+            if (R <= 0 || (inverse ? (int)cols - 3 : (int)cols - 2) <= 0) continue;
+            PB_CUDA_OK(cudaMemsetAsync(progress, 0, ((size_t)groups + 1) * sizeof(int), st));
+            PbProfScope p("k_mbd_pass", st);
+            k_mbd_pass<<<(R + 31) / 32, 32, 0, st>>>(img, Lm, Um, Dm, (int)rows, (int)cols, inverse, progress, groups);
+        }
+        // strip means and covariances (np.mean, np.cov with ddof = 1), inverses on the host
+        double h[24];
+        SalParams P{};
+        const double cnt[4] = {(double)bt * cols, (double)bt * cols, (double)bt * rows, (double)bt * rows};
+        { PbProfScope p("k_strip_partial", st);
+          k_strip_partial<0><<<SS_CTAS, SS_THREADS, 0, st>>>(l0, l1, l2, rows, cols, bt, nullptr, partial); }
+        { PbProfScope p("k_strip_finish", st, false);
+          k_strip_finish<<<1, 32, 0, st>>>(partial, SS_CTAS, 3, sums); }
+        PB_CUDA_OK(cudaMemcpyAsync(h, sums, sizeof h, cudaMemcpyDeviceToHost, st));
+        PB_CUDA_OK(cudaStreamSynchronize(st));
+        double means[12];
+        for (int k = 0; k < 4; k++)
+            for (int v = 0; v < 3; v++) { means[k * 3 + v] = h[k * 6 + v] / cnt[k]; P.mean[k][v] = means[k * 3 + v]; }
+        double *d_means = small + (size_t)SS_CTAS * 24 + 48; // [12]
+        PB_CUDA_OK(cudaMemcpyAsync(d_means, means, sizeof means, cudaMemcpyHostToDevice, st));
+        { PbProfScope p("k_strip_partial", st);
+          k_strip_partial<1><<<SS_CTAS, SS_THREADS, 0, st>>>(l0, l1, l2, rows, cols, bt, d_means, partial); }
+        { PbProfScope p("k_strip_finish", st, false);
+          k_strip_finish<<<1, 32, 0, st>>>(partial, SS_CTAS, 6, sums); }
+        PB_CUDA_OK(cudaMemcpyAsync(h, sums, sizeof h, cudaMemcpyDeviceToHost, st));
+        PB_CUDA_OK(cudaStreamSynchronize(st));
+        for (int k = 0; k < 4 && rc == 0; k++) {
+            double cov[6];
+            for (int v = 0; v < 6; v++) cov[v] = h[k * 6 + v] / (cnt[k] - 1.0);
+            if (!(cnt[k] > 1.0) || !invert3(cov, P.vi[k])) rc = -1;
+        }
+        if (rc == 0) {
+            auto read_max = [&](int count, double *dst) {
+                unsigned long long hm[8];
+                PB_CUDA_OK(cudaMemcpyAsync(hm, maxima, sizeof hm, cudaMemcpyDeviceToHost, st));
+                PB_CUDA_OK(cudaStreamSynchronize(st));
+                for (int i = 0; i < count; i++) memcpy(&dst[i], &hm[i], 8);
+            };
+            auto zero_max = [&]() { PB_CUDA_OK(cudaMemsetAsync(maxima, 0, 8 * sizeof(unsigned long long), st)); };
+            double m[4];
+            zero_max();
+            { PbProfScope p("k_sal_stage", st); k_sal_stage<0><<<grid, 256, 0, st>>>(P, l0, l1, l2, Dm, rows, cols, maxima, nullptr); }
+            read_max(4, m);
+            for (int k = 0; k < 4; k++) P.umax[k] = (double)(float)m[k]; // cdef float max_u_* (patolette.pyx:268-271)
+            zero_max();
+            { PbProfScope p("k_sal_stage", st); k_sal_stage<1><<<grid, 256, 0, st>>>(P, l0, l1, l2, Dm, rows, cols, maxima, nullptr); }
+            read_max(2, m);
+            P.u_max_final = (double)(float)m[0]; // :282
+            P.sal_max = (float)m[1];             // :283
+            zero_max();
+            { PbProfScope p("k_sal_stage", st); k_sal_stage<2><<<grid, 256, 0, st>>>(P, l0, l1, l2, Dm, rows, cols, maxima, nullptr); }
+            read_max(1, m);
+            P.m1 = m[0]; // :286
+            P.w2 = rows / 2.0; P.h2 = cols / 2.0; P.diag = sqrt(P.w2 * P.w2 + P.h2 * P.h2); // :288-294
+            zero_max();
+            { PbProfScope p("k_sal_stage", st); k_sal_stage<3><<<grid, 256, 0, st>>>(P, l0, l1, l2, Dm, rows, cols, maxima, nullptr); }
+            read_max(1, m);
+            P.m2 = m[0]; // :303
+            P.scale = (double)((size_t)rows * cols);
+            P.tile2 = tile_size * tile_size;
+            { PbProfScope p("k_sal_stage", st); k_sal_stage<4><<<grid, 256, 0, st>>>(P, l0, l1, l2, Dm, rows, cols, maxima, d_weights); }
+            PB_CUDA_OK(cudaGetLastError());
+            PB_CUDA_OK(cudaStreamSynchronize(st));
+        }
+    } catch (...) {
+        cudaDeviceSynchronize();
+        cleanup();
+        throw;
+    }
+    cleanup();
+    return rc;
+}
+
+// the distance map alone (tests: it is the part with bit parity)
+int pb_saliency_mbd(const double *const planes[3], size_t width, size_t height, float *d_out, int sm_count, cudaStream_t st) {
+    const uint32_t rows = (uint32_t)height, cols = (uint32_t)width;
+    if (rows <= 3 || cols <= 3) return -7;
+    const size_t n = (size_t)rows * cols;
+    float *f32 = nullptr;
+    double *lab = nullptr;
+    int *progress = nullptr;
+    auto cleanup = [&]() { pb_pool_free(f32); pb_pool_free(lab); pb_pool_free(progress); };
+    try {
+        f32 = (float *)pb_pool_alloc(4 * n * sizeof(float));
+        lab = (double *)pb_pool_alloc(3 * n * sizeof(double));
+        const int groups = (int)((rows + 31) / 32);
+        progress = (int *)pb_pool_alloc(((size_t)groups + 1) * sizeof(int));
+        float *img = f32, *Lm = f32 + n, *Um = f32 + 2 * n, *Dm = f32 + 3 * n;
+        const size_t want = (n + 255) / 256, cap = (size_t)sm_count * 8;
+        const int grid = (int)(want < cap ? want : cap);
+        { PbProfScope p("k_sal_prepare", st);
+          k_sal_prepare<<<grid, 256, 0, st>>>(planes[0], planes[1], planes[2], rows, cols, img, Lm, Um, Dm, lab, lab + n, lab + 2 * n); }
+        for (int it = 0; it < 3; it++) {
+            const int inverse = it % 2 == 0;
+            const int R = inverse ? (int)rows - 3 : (int)rows - 2;
+            if (R <= 0 || (inverse ? (int)cols - 3 : (int)cols - 2) <= 0) continue;
+            PB_CUDA_OK(cudaMemsetAsync(progress, 0, ((size_t)groups + 1) * sizeof(int), st));
+            PbProfScope p("k_mbd_pass", st);
+            k_mbd_pass<<<(R + 31) / 32, 32, 0, st>>>(img, Lm, Um, Dm, (int)rows, (int)cols, inverse, progress, groups);
+        }
+        PB_CUDA_OK(cudaMemcpyAsync(d_out, Dm, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        PB_CUDA_OK(cudaStreamSynchronize(st));
+    } catch (...) {
+        cudaDeviceSynchronize();
+        cleanup();
+        throw;
+    }
+    cleanup();
+    return 0;
+}

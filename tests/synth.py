@@ -27,6 +27,22 @@ def image_like_colors(width: int, height: int, seed: int) -> np.ndarray:
     return np.round(c * 255) / 255
 
 
+def scene_colors(width: int, height: int, seed: int) -> np.ndarray:
+    """A photograph-like test scene for the saliency weights: soft background gradient, two textured objects off the
+    border, 8-bit values (/255).  The minimum-barrier distances, the border statistics and the centre prior all have
+    something to see (uniform noise has no structure, a pure gradient no objects)."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:height, 0:width].astype(np.float64)
+    u, v = xx / max(width - 1, 1), yy / max(height - 1, 1)
+    img = np.stack([0.25 + 0.35 * u, 0.30 + 0.25 * v, 0.55 - 0.25 * u * v], -1)
+    for cx, cy, rx, ry, col in ((0.38, 0.45, 0.17, 0.24, (0.85, 0.30, 0.15)), (0.70, 0.62, 0.12, 0.10, (0.10, 0.65, 0.35))):
+        inside = ((u - cx) / rx) ** 2 + ((v - cy) / ry) ** 2 < 1.0
+        tex = 0.08 * np.sin(40 * u + 25 * v)[..., None]
+        img = np.where(inside[..., None], np.asarray(col)[None, None, :] + tex, img)
+    img = np.clip(img + 0.04 * rng.standard_normal(img.shape), 0.0, 1.0)
+    return (np.round(img * 255) / 255).reshape(-1, 3)
+
+
 def saliency_like_weights(width: int, height: int, seed: int) -> np.ndarray:
     """w = 1 + 1024 * s^2 in [1, 1025] (mirrors 1 + sal^2 * N / tile^2 of patolette.pyx:313)."""
     rng = np.random.default_rng(seed + 1000)
@@ -108,3 +124,18 @@ def make_case(spec: dict):
     kw = dict(dither=spec["dither"], palette_only=spec.get("palette_only", False), color_space=spec["color_space"],
               kmeans_niter=spec["kmeans_niter"], kmeans_max_samples=spec.get("kmeans_max_samples", 512 ** 2))
     return np.ascontiguousarray(colors, dtype=np.float64), weights, kw
+
+
+# Saliency (row N3) cases: name -> kwargs.  Frozen from the reference's own wrapper by tests/golden/make_golden_saliency.py.
+SALIENCY_CASES = {
+    "scene_96x64_t32": dict(w=96, h=64, seed=21, tile=32.0, kind="scene"),
+    "scene_37x29_t8": dict(w=37, h=29, seed=22, tile=8.0, kind="scene"),
+    "imagelike_70x130_t16": dict(w=70, h=130, seed=23, tile=16.0, kind="image_like"),
+    "scene_160x120_t512": dict(w=160, h=120, seed=24, tile=512.0, kind="scene"),
+    "uniform_48x40_t10": dict(w=48, h=40, seed=25, tile=10.0, kind="uniform"),
+}
+
+
+def saliency_case_colors(spec) -> np.ndarray:
+    f = {"scene": scene_colors, "image_like": image_like_colors, "uniform": uniform_colors}[spec["kind"]]
+    return f(spec["w"], spec["h"], spec["seed"])
