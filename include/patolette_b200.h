@@ -70,10 +70,12 @@ PB200_API patolette__QuantizationOptions *patolette_create_default_options(void)
 PB200_API int patolette_b200_set_device(int device);
 /* Number of visible CUDA devices, or a negative cudaError on failure. */
 PB200_API int patolette_b200_device_count(void);
-/* Shared object that provides LAPACK dsyev_ (the reference links one too,
- * lib/src/math/eigen.c:50).  NULL restores the default search. */
+/* Shared object that provides LAPACK dsyev_ (the reference links one too, lib/src/math/eigen.c:50) for the
+ * "host_lapack" mode (patolette_b200_set_option); NULL restores the default search.  By default no LAPACK is
+ * needed: the solve is the built-in restatement (patolette_b200_eigen3). */
 PB200_API void patolette_b200_set_lapack(const char *path);
-/* "path:symbol" of the dsyev_ in use, or "builtin-jacobi". */
+/* The eigen solver in use: "builtin-dsyev3 ..." (default), or in "host_lapack" mode "path:symbol" of the dsyev_ /
+ * "builtin-jacobi". */
 PB200_API const char *patolette_b200_lapack_source(void);
 
 /* Stage: one of the reference's matrix colour transforms in place on a host
@@ -147,6 +149,15 @@ PB200_API int patolette_b200_saliency_mbd(size_t width, size_t height, const dou
 /* Milliseconds the saliency stage of the last call took (CUDA events; inside the "color" slot of last_timings). */
 PB200_API double patolette_b200_last_saliency_ms(void);
 
+/* N2 (on-chip eigen solve): n symmetric 3 x 3 eigen problems solved exactly as LAPACK's dsyev('V', 'L', 3) solves
+ * them (lib/src/math/eigen.c:83-140) - dsytd2 -> dorgtr -> dsteqr restated operation for operation in
+ * csrc/pb_dsyev3.h, bit-identical eigenvalues AND eigenvectors (sign included).  a9: n matrices, column-major, lower
+ * triangle significant; w3: n x 3 ascending eigenvalues; z9: n x 9 eigenvectors in columns (principal axis = last
+ * column, math/pca.c:136-138); info: n LAPACK info values or NULL.  on_device = 0 runs the host instantiation (no
+ * GPU needed), 1 the device kernel (k_eigen3).  The pipeline itself uses this solver by default;
+ * patolette_b200_set_option("host_lapack", 1) switches back to a run-time resolved dsyev_. */
+PB200_API int patolette_b200_eigen3(const double *a9, size_t n, double *w3, double *z9, int *info, int on_device);
+
 /* Image-sharded multi-GPU runs (one process per GPU).  The library owns an NCCL communicator:
  * rank 0 calls patolette_b200_comm_unique_id() and hands the 128 bytes to every rank (any transport), then all
  * ranks call patolette_b200_comm_init() (collective; after patolette_b200_set_device()).  world = 1 drops it.
@@ -209,8 +220,10 @@ PB200_API int patolette_b200_set_sharding(int rank, int world, patolette_b200_al
  * "split_certify" = how a split finds its optimal bucket (quantize/local.c:102-177): 1 (default) unordered per-bucket
  * sums plus a proof that the reference's argmax is the same, refused clusters re-evaluated exactly; 0 the exact route
  * for every cluster (bucket sort + sequential per-bucket chains); 2 certified route with every certificate refused.
- * "allow_jacobi" = 1 lets a built-in Jacobi solver stand in when no LAPACK dsyev_ can be resolved (default 0: such
- * a call fails with exit code -1, because eigenvector signs - hence palette order - would differ from the reference).
+ * "host_lapack" = 1 solves the 3 x 3 eigen problems with a dsyev_ resolved at run time (patolette_b200_set_lapack)
+ * instead of the built-in restatement (default 0; both give the same bits).  In that mode "allow_jacobi" = 1 lets a
+ * built-in Jacobi solver stand in when no dsyev_ can be resolved (default 0: such a call fails with exit code -1,
+ * because eigenvector signs - hence palette order - would differ from the reference).
  * Returns 0, -1 if unknown. */
 PB200_API int patolette_b200_set_option(const char *name, long long value);
 /* Debug: per chain of the centred pass {cycles scan walk, cycles record walk, cycles replays, replays,

@@ -63,6 +63,7 @@ SYMBOLS = {
     "patolette_b200_saliency_weights": (C.c_int, [C.c_size_t, C.c_size_t, C.c_void_p, C.c_double, C.c_void_p, C.c_int]),
     "patolette_b200_saliency_mbd": (C.c_int, [C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int]),
     "patolette_b200_last_saliency_ms": (C.c_double, []),
+    "patolette_b200_eigen3": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "patolette_b200_comm_unique_id": (C.c_int, [C.c_char_p]),
     "patolette_b200_comm_init": (C.c_int, [C.c_int, C.c_int, C.c_char_p]),
     "patolette_b200_comm_destroy": (None, []),

@@ -19,10 +19,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libpatolette_b200.so")
-CU = ["pb_color.cu", "pb_chain.cu", "pb_ordered.cu", "pb_parallel.cu", "pb_certify.cu", "pb_nngrid.cu", "pb_kmeans.cu", "pb_dither.cu", "pb_saliency.cu", "pb_pipeline.cu"]
+CU = ["pb_color.cu", "pb_chain.cu", "pb_ordered.cu", "pb_parallel.cu", "pb_certify.cu", "pb_nngrid.cu", "pb_kmeans.cu", "pb_dither.cu", "pb_saliency.cu", "pb_eigen.cu", "pb_pipeline.cu"]
 CPP = ["pb_lapack.cpp", "pb_prof.cpp", "pb_pool.cpp", "pb_xfer.cpp", "pb_hostpool.cpp", "pb_nccl.cpp"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--fmad=false",
-              "-std=c++17", "-Xcompiler", "-fPIC,-fvisibility=hidden,-O2", "--expt-relaxed-constexpr", "-DPATOLETTE_B200_BUILD"]
+              "-std=c++17", "-Xcompiler", "-fPIC,-fvisibility=hidden,-O2,-ffp-contract=off", "--expt-relaxed-constexpr", "-DPATOLETTE_B200_BUILD"]
 
 
 def nvcc() -> str:

@@ -22,6 +22,8 @@ void pb_launch_pow(const double *x, double y, double *out, size_t n, int sm_coun
 void pb_launch_deinterleave(const double *d_rgb, size_t n, double *const dst[3], int sm_count, cudaStream_t st);
 // N x 3 interleaved uint8 -> planes of value / 255 (f64, IEEE division); size_t map -> uint8 / uint16 indices
 void pb_launch_u8_to_planes(const uint8_t *d_rgb, size_t n, double *const dst[3], int sm_count, cudaStream_t st);
+// batch of 3 x 3 symmetric eigen solves, LAPACK dsyev-faithful (pb_eigen.cu / pb_dsyev3.h)
+void pb_launch_eigen3(const double *a9, int n, double *w3, double *z9, int *info, cudaStream_t st);
 void pb_launch_narrow_map(const unsigned long long *d_map, size_t n, void *d_out, int bytes, int sm_count, cudaStream_t st);
 
 // ---- ordered-sum kernels, pb_ordered.cu / pb_chain.cu ----------------------------------

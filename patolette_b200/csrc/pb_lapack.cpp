@@ -4,26 +4,32 @@
 // as the principal axis (math/pca.c:136-138).  The SIGN of that eigenvector decides
 // which child of a split is "left" (quantize/local.c:375-376) and therefore the order
 // of the palette, and LAPACK's sign follows no closed-form rule (it falls out of the
-// dsytd2 -> dorgtr -> dsteqr sequence).  To be a drop-in we call the same LAPACK entry
-// point the reference links, resolved at run time:
+// dsytd2 -> dorgtr -> dsteqr sequence).
+//
+// Default (row N2): pb_dsyev3.h - that sequence restated operation for operation for n = 3,
+// bit-identical to the dsyev_ of the LAPACK the reference build links (tests/test_eigen.py:
+// millions of matrices, 0 mismatches).  No run-time dependency, nothing to resolve, no
+// fallback whose signs could differ; the same header runs on the device (pb_eigen.cu).
+//
+// patolette_b200_set_option("host_lapack", 1) restores the round-1 behaviour - call a real
+// dsyev_ resolved at run time:
 //   1. $PATOLETTE_B200_LAPACK (path to a shared object), or the path handed to
 //      patolette_b200_set_lapack() by the Python wrapper (scipy's bundled OpenBLAS);
 //   2. the usual system sonames.
-// This is O(K) host work per image (one 3x3 solve per tree node), not a pixel path.
-// If no LAPACK can be found the library FAILS CLOSED: pb_eigen_solve3 returns false and
-// patolette() ends with exit code -1 (a drop-in must not silently return a permuted
-// palette).  A caller that accepts that divergence opts in with
-// patolette_b200_set_option("allow_jacobi", 1): a cyclic-Jacobi solver then stands in -
-// eigenvector signs, hence palette ORDER, may differ from the reference.
+// In that mode a missing LAPACK FAILS CLOSED: pb_eigen_solve3 returns false and
+// patolette() ends with exit code -1, unless patolette_b200_set_option("allow_jacobi", 1)
+// accepts a cyclic-Jacobi stand-in whose eigenvector signs, hence palette ORDER, may differ.
 #include <dlfcn.h>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <mutex>
 #include <string>
 
+#include "pb_dsyev3.h"
 #include "pb_host.h"
 
 namespace {
@@ -37,6 +43,7 @@ bool g_tried = false;
 std::string g_user_path;
 std::string g_source = "unresolved";
 bool g_allow_jacobi = false;
+std::atomic<bool> g_host_lapack{false}; // false: the built-in restatement (pb_dsyev3.h)
 
 dsyev_fn try_open(const char *path) {
     void *h = dlopen(path, RTLD_NOW | RTLD_LOCAL);
@@ -128,8 +135,14 @@ void pb_lapack_allow_jacobi(bool on) {
     g_dsyev = nullptr;
 }
 
+void pb_lapack_use_host(bool on) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_host_lapack = on;
+}
+
 const char *pb_lapack_source() {
     std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_host_lapack) return "builtin-dsyev3 (LAPACK 3.12.0 dsyev restated for n = 3, pb_dsyev3.h)";
     resolve_locked();
     return g_source.c_str();
 }
@@ -138,6 +151,12 @@ const char *pb_lapack_source() {
 // eigenvectors for ascending eigenvalues w.  Returns false when the workspace QUERY fails
 // (the only failure the reference observes, eigen.c:115-118).
 bool pb_eigen_solve3(double a[9], double w[3]) {
+    if (!g_host_lapack.load(std::memory_order_relaxed)) {
+        // eigen.c:115-140: only a failing workspace query makes the reference give up; the solve's own info is
+        // ignored there, and so it is here
+        (void)pb_eig::dsyev3(a, w);
+        return true;
+    }
     dsyev_fn fn;
     bool jacobi;
     {

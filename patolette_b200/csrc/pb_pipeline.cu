@@ -22,6 +22,7 @@
 #include "pb_hostpool.h"
 #include "pb_kernels.h"
 #include "pb_nccl.h"
+#include "pb_dsyev3.h"
 #include "pb_pipeline.h"
 #include "pb_pool.h"
 #include "pb_prof.h"
@@ -1398,6 +1399,35 @@ int patolette_b200_saliency_mbd(size_t width, size_t height, const double *plana
 }
 double patolette_b200_last_saliency_ms(void) { return g_saliency_ms; }
 
+// N2 stage: n symmetric 3 x 3 solves, on the host (on_device = 0, no GPU involved) or by k_eigen3
+int patolette_b200_eigen3(const double *a9, size_t n, double *w3, double *z9, int *info, int on_device) {
+    if (!a9 || !w3 || !z9 || n > (size_t)1 << 28) return -1;
+    if (!on_device) {
+        for (size_t i = 0; i < n; i++) {
+            double a[9];
+            memcpy(a, a9 + 9 * i, sizeof a);
+            const int rc = pb_eig::dsyev3(a, w3 + 3 * i);
+            memcpy(z9 + 9 * i, a, sizeof a);
+            if (info) info[i] = rc;
+        }
+        return 0;
+    }
+    return guarded_stage([&]() -> int {
+        Quantizer qz;
+        qz.init(0, false);
+        DevArr<double> da, dw, dz;
+        DevArr<int> di;
+        da.alloc(9 * n + 1); dw.alloc(3 * n + 1); dz.alloc(9 * n + 1); di.alloc(n + 1);
+        qz.h2d(da.p, a9, 9 * n);
+        pb_launch_eigen3(da.p, (int)n, dw.p, dz.p, di.p, qz.st);
+        qz.d2h(w3, dw.p, 3 * n);
+        qz.d2h(z9, dz.p, 9 * n);
+        if (info) qz.d2h(info, di.p, n);
+        qz.sync();
+        return 0;
+    });
+}
+
 void patolette_b200_sharded(size_t width, size_t height, const double *slice, const double *weights_slice,
                             size_t palette_size, const patolette__QuantizationOptions *options, double *palette,
                             size_t *map_slice, int device_io, int *exit_code) {
@@ -1498,6 +1528,7 @@ int patolette_b200_set_option(const char *name, long long value) {
     if (!strcmp(name, "dither_tiles")) { pb_dither_set_tiles(value != 0); return 0; }
     if (!strcmp(name, "dither_one_wave")) { pb_dither_set_one_wave(value != 0); return 0; }
     if (!strcmp(name, "allow_jacobi")) { pb_lapack_allow_jacobi(value != 0); return 0; }
+    if (!strcmp(name, "host_lapack")) { pb_lapack_use_host(value != 0); return 0; }
     return -1;
 }
 

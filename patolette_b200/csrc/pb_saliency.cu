@@ -72,6 +72,11 @@ __device__ __forceinline__ int ld_acquire(const int *p) {
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ int ld_relaxed(const int *p) {
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void st_release(int *p, int v) {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -88,10 +93,15 @@ __device__ __forceinline__ void st_release(int *p, int v) {
 // belong to the previous warp, which finishes them in ITS tiles k and k + 1 and publishes the number of tiles it has
 // written back (release store / acquire poll).  A scan costs about cols / 32 + 2 rows / 32 tile times.
 constexpr int MBD_T = 32;
+__device__ __forceinline__ void cp_async4(float *smem_dst, const float *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
 __global__ void __launch_bounds__(32) k_mbd_pass(const float *__restrict__ img, float *Lm, float *Um, float *Dm, int rows, int cols,
                                                  int inverse, int *progress /* [groups] tiles written back, [groups] = ticket */,
                                                  int groups) {
-    __shared__ float sI[MBD_T][MBD_T + 1], sD[MBD_T][MBD_T + 1], sU[MBD_T][MBD_T + 1], sL[MBD_T][MBD_T + 1];
+    // two tile buffers: tile k + 1 is on its way (cp.async: no register staging, every copy in flight at once) while
+    // tile k's 32 dependent steps run
+    __shared__ float sI[2][MBD_T][MBD_T + 1], sD[2][MBD_T][MBD_T + 1], sU[2][MBD_T][MBD_T + 1], sL[2][MBD_T][MBD_T + 1];
     __shared__ float upU_s[MBD_T], upL_s[MBD_T];
     const int lane = threadIdx.x;
     int g = 0;
@@ -111,32 +121,43 @@ __global__ void __launch_bounds__(32) k_mbd_pass(const float *__restrict__ img, 
         lleft = Lm[b];
     }
     const size_t uprow = (size_t)(inverse ? row_of(g * 32) + 1 : row_of(g * 32) - 1) * cols; // the row above this warp's first
-    float myU = 0.f, myL = 0.f; // this lane's U, L at the column it visited last (the next lane's upper neighbour)
-    for (int k = 0; k < ntiles; k++) {
-        // ---- tile in: row r of the tile holds columns 32 k - r .. 32 k - r + 31 of scan row 32 g + r
+    // tile in: row r of the tile holds columns 32 k - r .. 32 k - r + 31 of scan row 32 g + r
+    auto tile_in = [&](int k, int b) {
 #pragma unroll 8
         for (int r = 0; r < 32; r++) {
             const int ir = g * 32 + r, c = 32 * k + lane - r;
             if (ir < R && c >= 0 && c < Cn) {
                 const size_t p = (size_t)row_of(ir) * cols + col_of(c);
-                sI[r][lane] = img[p]; sD[r][lane] = Dm[p]; sU[r][lane] = Um[p]; sL[r][lane] = Lm[p];
+                cp_async4(&sI[b][r][lane], img + p); cp_async4(&sD[b][r][lane], Dm + p);
+                cp_async4(&sU[b][r][lane], Um + p); cp_async4(&sL[b][r][lane], Lm + p);
             }
         }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    tile_in(0, 0);
+    float myU = 0.f, myL = 0.f; // this lane's U, L at the column it visited last (the next lane's upper neighbour)
+    for (int k = 0; k < ntiles; k++) {
+        const int b = k & 1;
+        if (k + 1 < ntiles) tile_in(k + 1, b ^ 1); // (tile k - 1, which used that buffer, has been written back)
         // ---- lane 0's upper neighbours
         {
             const int c = 32 * k + lane;
             if (g > 0) { // wait until the previous warp has written back its tiles k and k + 1
                 const int need = k + 2 < ntiles ? k + 2 : ntiles;
-                if (lane == 0)
-                    while (ld_acquire(progress + g - 1) < need) {}
+                // (lane 0 acquires, the warp barrier extends the order to the other lanes - whose loads below go to L2)
+                if (lane == 0) {
+                    while (ld_relaxed(progress + g - 1) < need) {}
+                    (void)ld_acquire(progress + g - 1);
+                }
                 __syncwarp();
-                __threadfence();
             }
             if (c < Cn) {
                 upU_s[lane] = ld_cg(Um + uprow + col_of(c));
                 upL_s[lane] = ld_cg(Lm + uprow + col_of(c));
             }
         }
+        if (k + 1 < ntiles) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
         // ---- 32 dependent steps out of shared memory
 #pragma unroll 4
@@ -145,32 +166,33 @@ __global__ void __launch_bounds__(32) k_mbd_pass(const float *__restrict__ img, 
             const int c = 32 * k + j - lane;
             if (row_ok && c >= 0 && c < Cn) {
                 if (lane == 0) { upU = upU_s[j]; upL = upL_s[j]; }
-                const float ix = sI[lane][j], d = sD[lane][j];
-                float curU = sU[lane][j], curL = sL[lane][j];
+                const float ix = sI[b][lane][j], d = sD[b][lane][j];
+                float curU = sU[b][lane][j], curL = sL[b][lane][j];
                 const float b1 = fmaxf(upU, ix) - fminf(upL, ix), b2 = fmaxf(uleft, ix) - fminf(lleft, ix);
                 if (d <= b1 && d <= b2) {
                     // unchanged
                 } else if (b1 < d && b1 <= b2) {
                     curU = fmaxf(upU, ix); curL = fminf(upL, ix);
-                    sD[lane][j] = b1; sU[lane][j] = curU; sL[lane][j] = curL;
+                    sD[b][lane][j] = b1; sU[b][lane][j] = curU; sL[b][lane][j] = curL;
                 } else {
                     curU = fmaxf(uleft, ix); curL = fminf(lleft, ix);
-                    sD[lane][j] = b2; sU[lane][j] = curU; sL[lane][j] = curL;
+                    sD[b][lane][j] = b2; sU[b][lane][j] = curU; sL[b][lane][j] = curL;
                 }
                 uleft = curU; lleft = curL; myU = curU; myL = curL;
             }
         }
         __syncwarp();
         // ---- tile out
-#pragma unroll 4
+#pragma unroll 8
         for (int r = 0; r < 32; r++) {
             const int ir = g * 32 + r, c = 32 * k + lane - r;
             if (ir < R && c >= 0 && c < Cn) {
                 const size_t p = (size_t)row_of(ir) * cols + col_of(c);
-                Dm[p] = sD[r][lane]; Um[p] = sU[r][lane]; Lm[p] = sL[r][lane];
+                Dm[p] = sD[b][r][lane]; Um[p] = sU[b][r][lane]; Lm[p] = sL[b][r][lane];
             }
         }
-        __threadfence();
+        // every lane's stores are ordered before the warp barrier, lane 0's release (one MEMBAR.ALL.GPU, not the
+        // sequentially consistent fence + L1 invalidation of __threadfence()) publishes them
         __syncwarp();
         if (lane == 0) st_release(progress + g, k + 1);
     }

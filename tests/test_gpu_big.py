@@ -113,18 +113,31 @@ def _cpu():
     return "unknown cpu"
 
 
-def test_lapack_is_the_reference_one(cuda_lib):
+def test_eigen_solver_is_the_builtin_restatement_and_host_lapack_agrees(cuda_lib):
+    """Default: pb_dsyev3.h (row N2).  "host_lapack" = 1 calls the real dsyev_ instead: same palette, same map."""
     src = cuda_lib.patolette_b200_lapack_source().decode()
-    assert src != "builtin-jacobi" and "dsyev" in src, src
+    assert src.startswith("builtin-dsyev3"), src
+    colors, weights, kw = make_case(dict(w=256, h=192, K=64, seed=5, color_space=2, dither=True, kmeans_niter=3, weighted=True))
+    a = cuda_quantize(cuda_lib, 256, 192, colors, 64, weights=weights, **kw)
+    assert cuda_lib.patolette_b200_set_option(b"host_lapack", 1) == 0
+    try:
+        src = cuda_lib.patolette_b200_lapack_source().decode()
+        assert src != "builtin-jacobi" and "dsyev" in src, src
+        b = cuda_quantize(cuda_lib, 256, 192, colors, 64, weights=weights, **kw)
+    finally:
+        cuda_lib.patolette_b200_set_option(b"host_lapack", 0)
+    assert a[0] == 0 and b[0] == 0
+    assert np.array_equal(a[1].view(np.uint64), b[1].view(np.uint64)) and np.array_equal(a[2], b[2])
 
 
 def test_missing_lapack_fails_closed(cuda_lib):
-    """No dsyev_ -> exit code -1, not a silently different palette; allow_jacobi opts in."""
+    """"host_lapack" mode without a dsyev_ -> exit code -1, not a silently different palette; allow_jacobi opts in."""
     from patolette_b200 import _lib
     colors, weights, kw = make_case(dict(w=64, h=64, K=8, seed=3, color_space=2, dither=False, kmeans_niter=0))
     real = _lib._find_lapack()
     saved = os.environ.pop("PATOLETTE_B200_LAPACK", None)
     try:
+        cuda_lib.patolette_b200_set_option(b"host_lapack", 1)
         cuda_lib.patolette_b200_set_lapack(b"/nonexistent/liblapack.so")
         if cuda_lib.patolette_b200_lapack_source().decode() != "builtin-jacobi":
             pytest.skip("a system LAPACK is installed on this box: the fall-through search found it")
@@ -135,6 +148,7 @@ def test_missing_lapack_fails_closed(cuda_lib):
         assert code == 0 and len(np.unique(pmap)) == 8
     finally:
         cuda_lib.patolette_b200_set_option(b"allow_jacobi", 0)
+        cuda_lib.patolette_b200_set_option(b"host_lapack", 0)
         cuda_lib.patolette_b200_set_lapack(real.encode() if real else None)
         if saved is not None:
             os.environ["PATOLETTE_B200_LAPACK"] = saved
