@@ -6,8 +6,8 @@
 // updates pixel (x, y) from its upper and its left neighbour, both already updated.  The data flow is a wavefront, and
 // k_mbd_pass runs it as a systolic array: a warp owns 32 consecutive rows, lane t is row t, and at step s lane t works
 // on column s - t.  The left neighbour is the lane's own previous result (registers), the upper neighbour is lane
-// t-1's result of the previous step (one shuffle); the row above a warp's first row belongs to the previous warp,
-// which publishes how many columns its last row has finished (release store / acquire poll).  rows + cols steps per
+// t-1's result of the previous step (one shuffle); the row above a warp's first row belongs to the previous CTA,
+// which hands its last row's (U, L) pairs over through an edge buffer with the flag in the data.  rows + cols steps per
 // scan instead of rows * cols.  The scan only takes float32 max / min / subtract, so the distance map is the
 // reference's bit for bit.
 //
@@ -52,7 +52,8 @@ __global__ void __launch_bounds__(256) k_sal_prepare(const double *__restrict__ 
     const size_t n = (size_t)rows * cols;
     for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (size_t)gridDim.x * blockDim.x) {
         const double r = c0[p], g = c1[p], b = c2[p];
-        const float m = (float)(((r + g) + b) / 3.0);
+        float m = (float)(((r + g) + b) / 3.0);
+        m = m == m ? m : 0.0f; // a NaN pixel (undefined in the reference too) must not enter the scans' U / L: NaN marks "not yet produced"
         const uint32_t x = (uint32_t)(p / cols), y = (uint32_t)(p % cols);
         img[p] = m; Lm[p] = m; Um[p] = m;
         Dm[p] = (x == 0 || y == 0 || x == rows - 1 || y == cols - 1) ? 0.0f : INFINITY;
@@ -62,139 +63,204 @@ __global__ void __launch_bounds__(256) k_sal_prepare(const double *__restrict__ 
     }
 }
 
-__device__ __forceinline__ float ld_cg(const float *p) {
-    float v;
-    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p));
+// (relaxed.gpu, not a weak .cg access: ptxas may merge repeated WEAK loads of one address - it did, and hoisted the
+//  poll out of its loop)
+__device__ __forceinline__ float2 ld_edge(const float2 *p) { // one 8-byte load served by L2
+    float2 v;
+    asm volatile("ld.relaxed.gpu.global.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ int ld_acquire(const int *p) {
-    int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
+__device__ __forceinline__ void st_edge(float2 *p, float u, float l) { // one 8-byte store: the pair appears at once
+    asm volatile("st.relaxed.gpu.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(u), "f"(l) : "memory");
 }
-__device__ __forceinline__ int ld_relaxed(const int *p) {
+constexpr int MBD_SPIN_LIMIT = 1 << 23; // seconds of polling (a legitimate wait is at most one scan, ~20 ms): a bug must not hang the device
+__device__ __forceinline__ int ld_flag(const int *p) {
     int v;
     asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release(int *p, int v) {
-    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
+__device__ __forceinline__ void st_flag(int *p, int v) { asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
 // One raster scan (patolette.pyx:54-100) or inverse scan (:102-151) as a systolic wavefront; see the file header.
 //
 // In scan coordinates (i = visiting order of the rows, c = visiting order of the columns) pixel (i, c) needs
-// (i - 1, c) and (i, c - 1).  A warp owns rows 32 g .. 32 g + 31 (one CTA = one warp; g is taken from a ticket, so a
-// warp's predecessor is always resident or done).  The warp walks SKEWED tiles: in tile k, at step j, lane t works on
-// column 32 k + j - t - so all 32 lanes are busy in every step, the left neighbour is the lane's own previous result
-// and the upper neighbour is lane t - 1's previous result (one shuffle).  A tile's 32 x 32 pixels of img / D / U / L
-// are brought into shared memory with coalesced row segments first and written back the same way, so the 32 dependent
-// steps in between touch no global memory.  Lane 0's upper neighbours (row 32 g - 1, columns 32 k .. 32 k + 31)
-// belong to the previous warp, which finishes them in ITS tiles k and k + 1 and publishes the number of tiles it has
-// written back (release store / acquire poll).  A scan costs about cols / 32 + 2 rows / 32 tile times.
-constexpr int MBD_T = 32;
+// (i - 1, c) and (i, c - 1).  A CTA owns rows 32 g .. 32 g + 31 (g is taken from a ticket, so a CTA's predecessor is
+// always resident or done) and walks SKEWED tiles: in tile k, at step j, lane t of the compute warp works on column
+// 32 k + j - t - all 32 lanes are busy in every step, the left neighbour is the lane's own previous result and the
+// upper neighbour is lane t - 1's previous result (one shuffle).  Lane 0's upper neighbours (row 32 g - 1, columns
+// 32 k .. 32 k + 31) belong to the previous CTA, which finishes them in ITS tiles k and k + 1.  They travel through an
+// EDGE buffer with the flag in the data: before a scan every (U, L) pair of it is NaN (bytes 0xff), the producer's
+// lane 31 stores its pair with one 8-byte store the moment the step has produced it, and the consumer polls the
+// pairs it needs until they are numbers (U and L are maxima / minima of image values, which k_sal_prepare keeps
+// NaN-free) - one store-to-load latency per hand-off, no fence, no separate flag.  A scan costs about
+// cols / 32 + 2 rows / 32 tile times.
+//
+// The tile time is the length of ONE warp's dependent instruction stream (a first version that loaded, stepped and
+// stored in a single warp spent most of it on copy instructions - profiles/r02_saliency.md), so the CTA is a
+// pipeline of specialised warps over a ring of MBD_NBUF tile buffers in shared memory:
+//   loaders (MBD_NLD warps)  cp.async the tile's 32 x 32 img / D / U / L values (coalesced row segments), warp 0 of
+//                            them also polls the predecessor's edge pairs;
+//   compute (1 warp)         32 branch-free dependent steps out of shared memory, results in place, edge pairs out;
+//   storers (MBD_NST warps)  write D / U / L back.
+// Hand-offs inside the CTA are monotonic tile counters in shared memory.
+constexpr int MBD_T = 32, MBD_NBUF = 4, MBD_NLD = 2, MBD_NST = 2, MBD_WARPS = 1 + MBD_NLD + MBD_NST;
+struct MbdBuf {
+    float I[MBD_T][MBD_T + 1], D[MBD_T][MBD_T + 1], U[MBD_T][MBD_T + 1], L[MBD_T][MBD_T + 1];
+    float upU[MBD_T], upL[MBD_T];
+};
+struct MbdSmem {
+    MbdBuf buf[MBD_NBUF];
+    volatile int ld_cnt[MBD_NLD]; // tiles a loader warp has landed
+    volatile int comp_cnt;        // tiles computed
+    volatile int st_cnt[MBD_NST]; // tiles a storer warp has written back
+    int g;
+};
 __device__ __forceinline__ void cp_async4(float *smem_dst, const float *gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
-__global__ void __launch_bounds__(32) k_mbd_pass(const float *__restrict__ img, float *Lm, float *Um, float *Dm, int rows, int cols,
-                                                 int inverse, int *progress /* [groups] tiles written back, [groups] = ticket */,
-                                                 int groups) {
-    // two tile buffers: tile k + 1 is on its way (cp.async: no register staging, every copy in flight at once) while
-    // tile k's 32 dependent steps run
-    __shared__ float sI[2][MBD_T][MBD_T + 1], sD[2][MBD_T][MBD_T + 1], sU[2][MBD_T][MBD_T + 1], sL[2][MBD_T][MBD_T + 1];
-    __shared__ float upU_s[MBD_T], upL_s[MBD_T];
-    const int lane = threadIdx.x;
-    int g = 0;
-    if (lane == 0) g = atomicAdd(progress + groups, 1);
-    g = __shfl_sync(FULL, g, 0);
+__global__ void __launch_bounds__(32 * MBD_WARPS) k_mbd_pass(const float *__restrict__ img, float *Lm, float *Um, float *Dm, int rows,
+                                                            int cols, int inverse, int *ctl /* [0] ticket, [1] error */,
+                                                            float2 *edge /* [groups][cols] (U, L) of each group's last row */) {
+    extern __shared__ __align__(16) unsigned char mbd_smem_raw[];
+    MbdSmem &S = *reinterpret_cast<MbdSmem *>(mbd_smem_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        S.g = atomicAdd(ctl, 1);
+        S.comp_cnt = 0;
+        for (int w = 0; w < MBD_NLD; w++) S.ld_cnt[w] = 0;
+        for (int w = 0; w < MBD_NST; w++) S.st_cnt[w] = 0;
+    }
+    __syncthreads();
+    const int g = S.g;
     // the raster scan visits x = 1 .. rows-2, y = 1 .. cols-2; the inverse scan x = rows-2 .. 2, y = cols-2 .. 2
     const int R = inverse ? rows - 3 : rows - 2, Cn = inverse ? cols - 3 : cols - 2;
     const int ntiles = (Cn + 31 + 31) / 32; // steps 0 .. Cn + 30
     auto row_of = [&](int i) { return inverse ? rows - 2 - i : 1 + i; };
     auto col_of = [&](int c) { return inverse ? cols - 2 - c : 1 + c; };
-    const int i = g * 32 + lane;
-    const bool row_ok = i < R;
-    float uleft = 0.f, lleft = 0.f; // U, L of the column this row visited last (starts on the border column)
-    if (row_ok) {
-        const size_t b = (size_t)row_of(i) * cols + (inverse ? cols - 1 : 0);
-        uleft = Um[b];
-        lleft = Lm[b];
-    }
-    const size_t uprow = (size_t)(inverse ? row_of(g * 32) + 1 : row_of(g * 32) - 1) * cols; // the row above this warp's first
-    // tile in: row r of the tile holds columns 32 k - r .. 32 k - r + 31 of scan row 32 g + r
-    auto tile_in = [&](int k, int b) {
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ compute
+        const int i = g * 32 + lane;
+        const bool row_ok = i < R;
+        float uleft = 0.f, lleft = 0.f; // U, L of the column this row visited last (starts on the border column)
+        if (row_ok) {
+            const size_t b = (size_t)row_of(i) * cols + (inverse ? cols - 1 : 0);
+            uleft = Um[b];
+            lleft = Lm[b];
+        }
+        float myU = 0.f, myL = 0.f; // this lane's U, L at the column it visited last (the next lane's upper neighbour)
+        float2 *const my_edge = edge + (size_t)g * cols;
+        for (int k = 0; k < ntiles; k++) {
+            MbdBuf &B = S.buf[k % MBD_NBUF];
+            if (lane == 0) {
+                bool ready;
+                do {
+                    ready = true;
+                    for (int w = 0; w < MBD_NLD; w++) ready = ready && S.ld_cnt[w] > k;
+                } while (!ready);
+                __threadfence_block();
+            }
+            __syncwarp();
 #pragma unroll 8
-        for (int r = 0; r < 32; r++) {
-            const int ir = g * 32 + r, c = 32 * k + lane - r;
-            if (ir < R && c >= 0 && c < Cn) {
-                const size_t p = (size_t)row_of(ir) * cols + col_of(c);
-                cp_async4(&sI[b][r][lane], img + p); cp_async4(&sD[b][r][lane], Dm + p);
-                cp_async4(&sU[b][r][lane], Um + p); cp_async4(&sL[b][r][lane], Lm + p);
+            for (int j = 0; j < 32; j++) {
+                float upU = __shfl_up_sync(FULL, myU, 1), upL = __shfl_up_sync(FULL, myL, 1);
+                const int c = 32 * k + j - lane;
+                const bool active = row_ok && c >= 0 && c < Cn;
+                const float tU = B.upU[j], tL = B.upL[j];
+                upU = lane == 0 ? tU : upU;
+                upL = lane == 0 ? tL : upL;
+                const float ix = B.I[lane][j], d = B.D[lane][j], cu = B.U[lane][j], cl = B.L[lane][j];
+                const float u1 = fmaxf(upU, ix), l1 = fminf(upL, ix), u2 = fmaxf(uleft, ix), l2 = fminf(lleft, ix);
+                const float b1 = u1 - l1, b2 = u2 - l2;
+                const bool keep = d <= b1 && d <= b2, use1 = b1 < d && b1 <= b2;
+                const float nD = keep ? d : (use1 ? b1 : b2), nU = keep ? cu : (use1 ? u1 : u2), nL = keep ? cl : (use1 ? l1 : l2);
+                B.D[lane][j] = nD; B.U[lane][j] = nU; B.L[lane][j] = nL; // (cells outside the scan are never written back)
+                if (lane == 31 && active) st_edge(my_edge + c, nU, nL);
+                uleft = active ? nU : uleft; lleft = active ? nL : lleft;
+                myU = active ? nU : myU; myL = active ? nL : myL;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_block();
+                S.comp_cnt = k + 1;
             }
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    tile_in(0, 0);
-    float myU = 0.f, myL = 0.f; // this lane's U, L at the column it visited last (the next lane's upper neighbour)
-    for (int k = 0; k < ntiles; k++) {
-        const int b = k & 1;
-        if (k + 1 < ntiles) tile_in(k + 1, b ^ 1); // (tile k - 1, which used that buffer, has been written back)
-        // ---- lane 0's upper neighbours
-        {
-            const int c = 32 * k + lane;
-            if (g > 0) { // wait until the previous warp has written back its tiles k and k + 1
-                const int need = k + 2 < ntiles ? k + 2 : ntiles;
-                // (lane 0 acquires, the warp barrier extends the order to the other lanes - whose loads below go to L2)
+    } else if (warp <= MBD_NLD) {
+        // ------------------------------------------------------------------ loaders
+        const int w = warp - 1;
+        const size_t uprow = (size_t)(inverse ? row_of(g * 32) + 1 : row_of(g * 32) - 1) * cols; // the row above the CTA's first
+        for (int k = 0; k < ntiles; k++) {
+            MbdBuf &B = S.buf[k % MBD_NBUF];
+            if (k >= MBD_NBUF) { // the buffer's previous tile must have been written back
                 if (lane == 0) {
-                    while (ld_relaxed(progress + g - 1) < need) {}
-                    (void)ld_acquire(progress + g - 1);
+                    bool free_;
+                    do {
+                        free_ = true;
+                        for (int q = 0; q < MBD_NST; q++) free_ = free_ && S.st_cnt[q] > k - MBD_NBUF;
+                    } while (!free_);
+                    __threadfence_block();
                 }
                 __syncwarp();
             }
-            if (c < Cn) {
-                upU_s[lane] = ld_cg(Um + uprow + col_of(c));
-                upL_s[lane] = ld_cg(Lm + uprow + col_of(c));
-            }
-        }
-        if (k + 1 < ntiles) asm volatile("cp.async.wait_group 1;" ::: "memory");
-        else asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncwarp();
-        // ---- 32 dependent steps out of shared memory
+            // tile in: row r of the tile holds columns 32 k - r .. 32 k - r + 31 of scan row 32 g + r
 #pragma unroll 4
-        for (int j = 0; j < 32; j++) {
-            float upU = __shfl_up_sync(FULL, myU, 1), upL = __shfl_up_sync(FULL, myL, 1);
-            const int c = 32 * k + j - lane;
-            if (row_ok && c >= 0 && c < Cn) {
-                if (lane == 0) { upU = upU_s[j]; upL = upL_s[j]; }
-                const float ix = sI[b][lane][j], d = sD[b][lane][j];
-                float curU = sU[b][lane][j], curL = sL[b][lane][j];
-                const float b1 = fmaxf(upU, ix) - fminf(upL, ix), b2 = fmaxf(uleft, ix) - fminf(lleft, ix);
-                if (d <= b1 && d <= b2) {
-                    // unchanged
-                } else if (b1 < d && b1 <= b2) {
-                    curU = fmaxf(upU, ix); curL = fminf(upL, ix);
-                    sD[b][lane][j] = b1; sU[b][lane][j] = curU; sL[b][lane][j] = curL;
-                } else {
-                    curU = fmaxf(uleft, ix); curL = fminf(lleft, ix);
-                    sD[b][lane][j] = b2; sU[b][lane][j] = curU; sL[b][lane][j] = curL;
+            for (int r = w; r < 32; r += MBD_NLD) {
+                const int ir = g * 32 + r, c = 32 * k + lane - r;
+                if (ir < R && c >= 0 && c < Cn) {
+                    const size_t p = (size_t)row_of(ir) * cols + col_of(c);
+                    cp_async4(&B.I[r][lane], img + p); cp_async4(&B.D[r][lane], Dm + p);
+                    cp_async4(&B.U[r][lane], Um + p); cp_async4(&B.L[r][lane], Lm + p);
                 }
-                uleft = curU; lleft = curL; myU = curU; myL = curL;
+            }
+            if (w == 0) { // lane 0's upper neighbours
+                const int c = 32 * k + lane;
+                if (c < Cn) {
+                    if (g > 0) { // the previous CTA's last row: poll the pair until it has been produced
+                        const float2 *src = edge + (size_t)(g - 1) * cols + c;
+                        float2 v = ld_edge(src);
+                        int spins = 0;
+                        while (v.x != v.x) { // (gives up after seconds, or as soon as anyone else has: never hang the device)
+                            if (++spins >= MBD_SPIN_LIMIT || ((spins & 1023) == 0 && ld_flag(ctl + 1) != 0)) break;
+                            v = ld_edge(src);
+                        }
+                        if (v.x != v.x) st_flag(ctl + 1, 1);
+                        B.upU[lane] = v.x;
+                        B.upL[lane] = v.y;
+                    } else { // the border row
+                        B.upU[lane] = Um[uprow + col_of(c)];
+                        B.upL[lane] = Lm[uprow + col_of(c)];
+                    }
+                }
+            }
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            __threadfence_block();
+            __syncwarp();
+            if (lane == 0) S.ld_cnt[w] = k + 1;
+        }
+    } else {
+        // ------------------------------------------------------------------ storers
+        const int w = warp - 1 - MBD_NLD;
+        for (int k = 0; k < ntiles; k++) {
+            MbdBuf &B = S.buf[k % MBD_NBUF];
+            if (lane == 0) {
+                while (S.comp_cnt <= k) {}
+                __threadfence_block();
+            }
+            __syncwarp();
+#pragma unroll 4
+            for (int r = w; r < 32; r += MBD_NST) {
+                const int ir = g * 32 + r, c = 32 * k + lane - r;
+                if (ir < R && c >= 0 && c < Cn) {
+                    const size_t p = (size_t)row_of(ir) * cols + col_of(c);
+                    Dm[p] = B.D[r][lane]; Um[p] = B.U[r][lane]; Lm[p] = B.L[r][lane];
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_block();
+                S.st_cnt[w] = k + 1; // the buffer may be refilled
             }
         }
-        __syncwarp();
-        // ---- tile out
-#pragma unroll 8
-        for (int r = 0; r < 32; r++) {
-            const int ir = g * 32 + r, c = 32 * k + lane - r;
-            if (ir < R && c >= 0 && c < Cn) {
-                const size_t p = (size_t)row_of(ir) * cols + col_of(c);
-                Dm[p] = sD[b][r][lane]; Um[p] = sU[b][r][lane]; Lm[p] = sL[b][r][lane];
-            }
-        }
-        // every lane's stores are ordered before the warp barrier, lane 0's release (one MEMBAR.ALL.GPU, not the
-        // sequentially consistent fence + L1 invalidation of __threadfence()) publishes them
-        __syncwarp();
-        if (lane == 0) st_release(progress + g, k + 1);
     }
 }
 
@@ -343,6 +409,45 @@ __global__ void __launch_bounds__(256) k_sal_stage(SalParams P, const double *__
     }
 }
 
+// mbd() of the wrapper (patolette.pyx:183-199): inverse, raster, inverse scan over img / L / U / D (device, n floats
+// each, prepared by k_sal_prepare).  Returns 0, or -1 if a scan gave up waiting for its predecessor (a bug guard).
+int mbd_scans(const float *img, float *Lm, float *Um, float *Dm, uint32_t rows, uint32_t cols, cudaStream_t st) {
+    static bool attr_set = false; // (one device per process in practice; the attribute is per function and device)
+    if (!attr_set) {
+        PB_CUDA_OK(cudaFuncSetAttribute(k_mbd_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MbdSmem)));
+        attr_set = true;
+    }
+    const int groups = (int)((rows + 31) / 32);
+    int *ctl = nullptr;
+    float2 *edge = nullptr;
+    int err = 0;
+    try {
+        ctl = (int *)pb_pool_alloc(2 * sizeof(int));
+        edge = (float2 *)pb_pool_alloc((size_t)groups * cols * sizeof(float2));
+        PB_CUDA_OK(cudaMemsetAsync(ctl, 0, 2 * sizeof(int), st));
+        for (int it = 0; it < 3; it++) {
+            const int inverse = it % 2 == 0;
+            const int R = inverse ? (int)rows - 3 : (int)rows - 2;
+            if (R <= 0 || (inverse ? (int)cols - 3 : (int)cols - 2) <= 0) continue;
+            PB_CUDA_OK(cudaMemsetAsync(ctl, 0, sizeof(int), st));                                          // the ticket
+            PB_CUDA_OK(cudaMemsetAsync(edge, 0xff, (size_t)((R + 31) / 32) * cols * sizeof(float2), st)); // "not yet produced"
+            PbProfScope p("k_mbd_pass", st);
+            k_mbd_pass<<<(R + 31) / 32, 32 * MBD_WARPS, sizeof(MbdSmem), st>>>(img, Lm, Um, Dm, (int)rows, (int)cols, inverse, ctl, edge);
+            PB_CUDA_OK(cudaGetLastError());
+        }
+        PB_CUDA_OK(cudaMemcpyAsync(&err, ctl + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+        PB_CUDA_OK(cudaStreamSynchronize(st));
+    } catch (...) {
+        cudaDeviceSynchronize();
+        pb_pool_free(ctl);
+        pb_pool_free(edge);
+        throw;
+    }
+    pb_pool_free(ctl);
+    pb_pool_free(edge);
+    return err ? -1 : 0;
+}
+
 bool invert3(const double c[6] /* 00 01 02 11 12 22 */, double vi[9]) {
     const double a = c[0], b = c[1], cc = c[2], d = c[3], e = c[4], f = c[5];
     const double A = d * f - e * e, B = -(b * f - cc * e), C = b * e - cc * d;
@@ -370,14 +475,11 @@ int pb_saliency_weights(const double *const planes[3], size_t width, size_t heig
     if (bt < 1 || bt + 1 > rows || bt + 1 > cols) return -7;
     float *f32 = nullptr;
     double *lab = nullptr, *small = nullptr;
-    int *progress = nullptr;
     int rc = 0;
-    auto cleanup = [&]() { pb_pool_free(f32); pb_pool_free(lab); pb_pool_free(small); pb_pool_free(progress); };
+    auto cleanup = [&]() { pb_pool_free(f32); pb_pool_free(lab); pb_pool_free(small); };
     try {
         f32 = (float *)pb_pool_alloc(4 * n * sizeof(float));
         lab = (double *)pb_pool_alloc(3 * n * sizeof(double));
-        const int groups = (int)((rows + 31) / 32);
-        progress = (int *)pb_pool_alloc(((size_t)groups + 1) * sizeof(int));
         small = (double *)pb_pool_alloc(((size_t)SS_CTAS * 24 + 64) * sizeof(double));
         float *img = f32, *Lm = f32 + n, *Um = f32 + 2 * n, *Dm = f32 + 3 * n;
         double *l0 = lab, *l1 = lab + n, *l2 = lab + 2 * n;
@@ -387,14 +489,7 @@ int pb_saliency_weights(const double *const planes[3], size_t width, size_t heig
         const int grid = (int)(want < cap ? want : cap);
         { PbProfScope p("k_sal_prepare", st);
           k_sal_prepare<<<grid, 256, 0, st>>>(planes[0], planes[1], planes[2], rows, cols, img, Lm, Um, Dm, l0, l1, l2); }
-        for (int it = 0; it < 3; it++) { // patolette.pyx:183-199: inverse, raster, inverse
-            const int inverse = it % 2 == 0;
-            const int R = inverse ? (int)rows - 3 : (int)rows - 2;
-            if (R <= 0 || (inverse ? (int)cols - 3 : (int)cols - 2) <= 0) continue;
-            PB_CUDA_OK(cudaMemsetAsync(progress, 0, ((size_t)groups + 1) * sizeof(int), st));
-            PbProfScope p("k_mbd_pass", st);
-            k_mbd_pass<<<(R + 31) / 32, 32, 0, st>>>(img, Lm, Um, Dm, (int)rows, (int)cols, inverse, progress, groups);
-        }
+        if (mbd_scans(img, Lm, Um, Dm, rows, cols, st) != 0) { cleanup(); return -1; }
         // strip means and covariances (np.mean, np.cov with ddof = 1), inverses on the host
         double h[24];
         SalParams P{};
@@ -470,26 +565,16 @@ int pb_saliency_mbd(const double *const planes[3], size_t width, size_t height, 
     const size_t n = (size_t)rows * cols;
     float *f32 = nullptr;
     double *lab = nullptr;
-    int *progress = nullptr;
-    auto cleanup = [&]() { pb_pool_free(f32); pb_pool_free(lab); pb_pool_free(progress); };
+    auto cleanup = [&]() { pb_pool_free(f32); pb_pool_free(lab); };
     try {
         f32 = (float *)pb_pool_alloc(4 * n * sizeof(float));
         lab = (double *)pb_pool_alloc(3 * n * sizeof(double));
-        const int groups = (int)((rows + 31) / 32);
-        progress = (int *)pb_pool_alloc(((size_t)groups + 1) * sizeof(int));
         float *img = f32, *Lm = f32 + n, *Um = f32 + 2 * n, *Dm = f32 + 3 * n;
         const size_t want = (n + 255) / 256, cap = (size_t)sm_count * 8;
         const int grid = (int)(want < cap ? want : cap);
         { PbProfScope p("k_sal_prepare", st);
           k_sal_prepare<<<grid, 256, 0, st>>>(planes[0], planes[1], planes[2], rows, cols, img, Lm, Um, Dm, lab, lab + n, lab + 2 * n); }
-        for (int it = 0; it < 3; it++) {
-            const int inverse = it % 2 == 0;
-            const int R = inverse ? (int)rows - 3 : (int)rows - 2;
-            if (R <= 0 || (inverse ? (int)cols - 3 : (int)cols - 2) <= 0) continue;
-            PB_CUDA_OK(cudaMemsetAsync(progress, 0, ((size_t)groups + 1) * sizeof(int), st));
-            PbProfScope p("k_mbd_pass", st);
-            k_mbd_pass<<<(R + 31) / 32, 32, 0, st>>>(img, Lm, Um, Dm, (int)rows, (int)cols, inverse, progress, groups);
-        }
+        if (mbd_scans(img, Lm, Um, Dm, rows, cols, st) != 0) { cleanup(); return -1; }
         PB_CUDA_OK(cudaMemcpyAsync(d_out, Dm, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
         PB_CUDA_OK(cudaStreamSynchronize(st));
     } catch (...) {
