@@ -16,6 +16,8 @@
 // compare with), so the weights carry a floating-point tolerance, not bit parity (tests/test_saliency.py states it).
 // Reductions are deterministic: maxima, and sums through per-CTA partials combined in a fixed order.
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -102,8 +104,9 @@ __device__ __forceinline__ void st_flag(int *p, int v) { asm volatile("st.relaxe
 //                            them also polls the predecessor's edge pairs;
 //   compute (1 warp)         32 branch-free dependent steps out of shared memory, results in place, edge pairs out;
 //   storers (MBD_NST warps)  write D / U / L back.
-// Hand-offs inside the CTA are monotonic tile counters in shared memory.
-constexpr int MBD_T = 32, MBD_NBUF = 4, MBD_NLD = 2, MBD_NST = 2, MBD_WARPS = 1 + MBD_NLD + MBD_NST;
+// Hand-offs inside the CTA are monotonic tile counters in shared memory.  (Measured per tile after the last change:
+// compute 1.75 us, one of two loaders 2.25 us, one of two storers 2.75 us - hence three of each.)
+constexpr int MBD_T = 32, MBD_NBUF = 4, MBD_NLD = 3, MBD_NST = 3, MBD_WARPS = 8;
 struct MbdBuf {
     float I[MBD_T][MBD_T + 1], D[MBD_T][MBD_T + 1], U[MBD_T][MBD_T + 1], L[MBD_T][MBD_T + 1];
     float upU[MBD_T], upL[MBD_T];
@@ -118,12 +121,19 @@ struct MbdSmem {
 __device__ __forceinline__ void cp_async4(float *smem_dst, const float *gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
+// Warp roles by physical warp: 0 = compute, 1..3 = loaders, 5..7 = storers; warp 4 leaves at once, so that the compute
+// warp has its scheduler (warp id mod 4) to itself within the CTA.
+//
+// EVERY poll below is executed by all 32 lanes of the waiting warp (a broadcast read, or a vote): a warp in which only
+// lane 0 polls comes back from the loop DIVERGED, and a diverged warp executes each shuffle of the step loop through
+// the collective slow path (WARPSYNC.COLLECTIVE) - measured 13 us instead of 1.75 us per tile (profiles/r02_saliency.md).
 __global__ void __launch_bounds__(32 * MBD_WARPS) k_mbd_pass(const float *__restrict__ img, float *Lm, float *Um, float *Dm, int rows,
                                                             int cols, int inverse, int *ctl /* [0] ticket, [1] error */,
-                                                            float2 *edge /* [groups][cols] (U, L) of each group's last row */) {
+                                                            float2 *edge /* [groups][cols] (U, L) of each group's last row */,
+                                                            unsigned long long *dbg /* nullptr, or [4][ntiles][8] time stamps */) {
     extern __shared__ __align__(16) unsigned char mbd_smem_raw[];
     MbdSmem &S = *reinterpret_cast<MbdSmem *>(mbd_smem_raw);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31, pwarp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
         S.g = atomicAdd(ctl, 1);
         S.comp_cnt = 0;
@@ -131,14 +141,25 @@ __global__ void __launch_bounds__(32 * MBD_WARPS) k_mbd_pass(const float *__rest
         for (int w = 0; w < MBD_NST; w++) S.st_cnt[w] = 0;
     }
     __syncthreads();
+    if (pwarp == 4) return;
     const int g = S.g;
     // the raster scan visits x = 1 .. rows-2, y = 1 .. cols-2; the inverse scan x = rows-2 .. 2, y = cols-2 .. 2
     const int R = inverse ? rows - 3 : rows - 2, Cn = inverse ? cols - 3 : cols - 2;
     const int ntiles = (Cn + 31 + 31) / 32; // steps 0 .. Cn + 30
     auto row_of = [&](int i) { return inverse ? rows - 2 - i : 1 + i; };
     auto col_of = [&](int c) { return inverse ? cols - 2 - c : 1 + c; };
+    auto nap = [&]() { __nanosleep(32); }; // waiting warps leave the issue slots to the working ones
+    // debug time stamps (PB_MBD_DEBUG=path): groups 0..3, per tile {compute start, compute end, loader-0 start, copies
+    // issued, edge pairs seen, tile landed, storer-0 start, storer-0 end}, nanoseconds
+    auto stamp = [&](int k, int slot) {
+        if (dbg && g < 4 && lane == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            dbg[((size_t)g * ntiles + k) * 8 + slot] = t;
+        }
+    };
 
-    if (warp == 0) {
+    if (pwarp == 0) {
         // ------------------------------------------------------------------ compute
         const int i = g * 32 + lane;
         const bool row_ok = i < R;
@@ -152,15 +173,14 @@ __global__ void __launch_bounds__(32 * MBD_WARPS) k_mbd_pass(const float *__rest
         float2 *const my_edge = edge + (size_t)g * cols;
         for (int k = 0; k < ntiles; k++) {
             MbdBuf &B = S.buf[k % MBD_NBUF];
-            if (lane == 0) {
-                bool ready;
-                do {
-                    ready = true;
-                    for (int w = 0; w < MBD_NLD; w++) ready = ready && S.ld_cnt[w] > k;
-                } while (!ready);
-                __threadfence_block();
-            }
+            bool ready;
+            do {
+                ready = true;
+                for (int w = 0; w < MBD_NLD; w++) ready = ready && S.ld_cnt[w] > k;
+            } while (!ready);
+            __threadfence_block();
             __syncwarp();
+            stamp(k, 0);
 #pragma unroll 8
             for (int j = 0; j < 32; j++) {
                 float upU = __shfl_up_sync(FULL, myU, 1), upL = __shfl_up_sync(FULL, myL, 1);
@@ -180,28 +200,26 @@ __global__ void __launch_bounds__(32 * MBD_WARPS) k_mbd_pass(const float *__rest
                 myU = active ? nU : myU; myL = active ? nL : myL;
             }
             __syncwarp();
-            if (lane == 0) {
-                __threadfence_block();
-                S.comp_cnt = k + 1;
-            }
+            stamp(k, 1);
+            __threadfence_block();
+            S.comp_cnt = k + 1; // (every lane stores the same value)
         }
-    } else if (warp <= MBD_NLD) {
+    } else if (pwarp <= MBD_NLD) {
         // ------------------------------------------------------------------ loaders
-        const int w = warp - 1;
+        const int w = pwarp - 1;
         const size_t uprow = (size_t)(inverse ? row_of(g * 32) + 1 : row_of(g * 32) - 1) * cols; // the row above the CTA's first
         for (int k = 0; k < ntiles; k++) {
             MbdBuf &B = S.buf[k % MBD_NBUF];
             if (k >= MBD_NBUF) { // the buffer's previous tile must have been written back
-                if (lane == 0) {
-                    bool free_;
-                    do {
-                        free_ = true;
-                        for (int q = 0; q < MBD_NST; q++) free_ = free_ && S.st_cnt[q] > k - MBD_NBUF;
-                    } while (!free_);
-                    __threadfence_block();
+                for (;;) {
+                    bool free_ = true;
+                    for (int q = 0; q < MBD_NST; q++) free_ = free_ && S.st_cnt[q] > k - MBD_NBUF;
+                    if (free_) break;
+                    nap();
                 }
-                __syncwarp();
+                __threadfence_block();
             }
+            if (w == 0) stamp(k, 2);
             // tile in: row r of the tile holds columns 32 k - r .. 32 k - r + 31 of scan row 32 g + r
 #pragma unroll 4
             for (int r = w; r < 32; r += MBD_NLD) {
@@ -213,40 +231,46 @@ __global__ void __launch_bounds__(32 * MBD_WARPS) k_mbd_pass(const float *__rest
                 }
             }
             if (w == 0) { // lane 0's upper neighbours
+                stamp(k, 3);
                 const int c = 32 * k + lane;
-                if (c < Cn) {
-                    if (g > 0) { // the previous CTA's last row: poll the pair until it has been produced
-                        const float2 *src = edge + (size_t)(g - 1) * cols + c;
-                        float2 v = ld_edge(src);
-                        int spins = 0;
-                        while (v.x != v.x) { // (gives up after seconds, or as soon as anyone else has: never hang the device)
-                            if (++spins >= MBD_SPIN_LIMIT || ((spins & 1023) == 0 && ld_flag(ctl + 1) != 0)) break;
-                            v = ld_edge(src);
+                const bool need = c < Cn;
+                if (g > 0) { // the previous CTA's last row: poll the pairs until all of them have been produced
+                    const float2 *src = edge + (size_t)(g - 1) * cols + (need ? c : 0);
+                    float2 v = make_float2(__int_as_float(0x7fffffff), 0.f);
+                    int spins = 0;
+                    for (;;) {
+                        if (need && v.x != v.x) v = ld_edge(src);
+                        if (__all_sync(FULL, !need || v.x == v.x)) break;
+                        // (gives up after seconds, or as soon as anyone else has: never hang the device)
+                        const int f = (++spins & 1023) == 0 ? ld_flag(ctl + 1) : 0;
+                        if (spins >= MBD_SPIN_LIMIT || __any_sync(FULL, f != 0)) {
+                            if (lane == 0) st_flag(ctl + 1, 1);
+                            break;
                         }
-                        if (v.x != v.x) st_flag(ctl + 1, 1);
-                        B.upU[lane] = v.x;
-                        B.upL[lane] = v.y;
-                    } else { // the border row
-                        B.upU[lane] = Um[uprow + col_of(c)];
-                        B.upL[lane] = Lm[uprow + col_of(c)];
+                        nap();
                     }
+                    if (need) { B.upU[lane] = v.x; B.upL[lane] = v.y; }
+                } else if (need) { // the border row
+                    B.upU[lane] = Um[uprow + col_of(c)];
+                    B.upL[lane] = Lm[uprow + col_of(c)];
                 }
+                __syncwarp();
+                stamp(k, 4);
             }
             asm volatile("cp.async.wait_all;" ::: "memory");
             __threadfence_block();
             __syncwarp();
-            if (lane == 0) S.ld_cnt[w] = k + 1;
+            if (w == 0) stamp(k, 5);
+            S.ld_cnt[w] = k + 1; // (every lane stores the same value)
         }
     } else {
         // ------------------------------------------------------------------ storers
-        const int w = warp - 1 - MBD_NLD;
+        const int w = pwarp - 5;
         for (int k = 0; k < ntiles; k++) {
             MbdBuf &B = S.buf[k % MBD_NBUF];
-            if (lane == 0) {
-                while (S.comp_cnt <= k) {}
-                __threadfence_block();
-            }
-            __syncwarp();
+            while (S.comp_cnt <= k) nap();
+            __threadfence_block();
+            if (w == 0) stamp(k, 6);
 #pragma unroll 4
             for (int r = w; r < 32; r += MBD_NST) {
                 const int ir = g * 32 + r, c = 32 * k + lane - r;
@@ -256,10 +280,9 @@ __global__ void __launch_bounds__(32 * MBD_WARPS) k_mbd_pass(const float *__rest
                 }
             }
             __syncwarp();
-            if (lane == 0) {
-                __threadfence_block();
-                S.st_cnt[w] = k + 1; // the buffer may be refilled
-            }
+            if (w == 0) stamp(k, 7);
+            __threadfence_block();
+            S.st_cnt[w] = k + 1; // the buffer may be refilled (every lane stores the same value)
         }
     }
 }
@@ -420,11 +443,18 @@ int mbd_scans(const float *img, float *Lm, float *Um, float *Dm, uint32_t rows, 
     const int groups = (int)((rows + 31) / 32);
     int *ctl = nullptr;
     float2 *edge = nullptr;
+    unsigned long long *dbg = nullptr;
+    const char *dbg_path = getenv("PB_MBD_DEBUG"); // debug: time stamps of the first scan's first four CTAs, dumped to this file
+    const size_t dbg_words = dbg_path ? (size_t)4 * (((size_t)cols + 62) / 32 + 1) * 8 : 0;
     int err = 0;
     try {
         ctl = (int *)pb_pool_alloc(2 * sizeof(int));
         edge = (float2 *)pb_pool_alloc((size_t)groups * cols * sizeof(float2));
         PB_CUDA_OK(cudaMemsetAsync(ctl, 0, 2 * sizeof(int), st));
+        if (dbg_words) {
+            dbg = (unsigned long long *)pb_pool_alloc(dbg_words * sizeof(unsigned long long));
+            PB_CUDA_OK(cudaMemsetAsync(dbg, 0, dbg_words * sizeof(unsigned long long), st));
+        }
         for (int it = 0; it < 3; it++) {
             const int inverse = it % 2 == 0;
             const int R = inverse ? (int)rows - 3 : (int)rows - 2;
@@ -432,8 +462,15 @@ int mbd_scans(const float *img, float *Lm, float *Um, float *Dm, uint32_t rows, 
             PB_CUDA_OK(cudaMemsetAsync(ctl, 0, sizeof(int), st));                                          // the ticket
             PB_CUDA_OK(cudaMemsetAsync(edge, 0xff, (size_t)((R + 31) / 32) * cols * sizeof(float2), st)); // "not yet produced"
             PbProfScope p("k_mbd_pass", st);
-            k_mbd_pass<<<(R + 31) / 32, 32 * MBD_WARPS, sizeof(MbdSmem), st>>>(img, Lm, Um, Dm, (int)rows, (int)cols, inverse, ctl, edge);
+            k_mbd_pass<<<(R + 31) / 32, 32 * MBD_WARPS, sizeof(MbdSmem), st>>>(img, Lm, Um, Dm, (int)rows, (int)cols, inverse, ctl, edge,
+                                                                                 it == 0 ? dbg : nullptr);
             PB_CUDA_OK(cudaGetLastError());
+        }
+        if (dbg_words) {
+            std::vector<unsigned long long> h(dbg_words);
+            PB_CUDA_OK(cudaMemcpyAsync(h.data(), dbg, dbg_words * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+            PB_CUDA_OK(cudaStreamSynchronize(st));
+            if (FILE *f = fopen(dbg_path, "wb")) { fwrite(h.data(), sizeof(unsigned long long), dbg_words, f); fclose(f); }
         }
         PB_CUDA_OK(cudaMemcpyAsync(&err, ctl + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
         PB_CUDA_OK(cudaStreamSynchronize(st));
@@ -441,10 +478,12 @@ int mbd_scans(const float *img, float *Lm, float *Um, float *Dm, uint32_t rows, 
         cudaDeviceSynchronize();
         pb_pool_free(ctl);
         pb_pool_free(edge);
+        pb_pool_free(dbg);
         throw;
     }
     pb_pool_free(ctl);
     pb_pool_free(edge);
+    pb_pool_free(dbg);
     return err ? -1 : 0;
 }
 
