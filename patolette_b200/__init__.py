@@ -25,7 +25,7 @@ bad_channel_count = "Expected colors to be in sRGB[0, 1] space. Channel count mi
 bad_tile_size = "tile_size parameter expected to be in the range [0, inf]"
 
 __all__ = ["__doc__", "__version__", "quantize", "ColorSpace_sRGB", "ColorSpace_CIELuv", "ColorSpace_ICtCp",
-           "quantize_u8", "saliency_weights", "saliency_mbd", "save_png", "init_sharding", "shard_range", "quantize_sharded", "sharding_description",
+           "quantize_u8", "saliency_weights", "saliency_mbd", "save_png", "save_gif", "init_sharding", "shard_range", "quantize_sharded", "sharding_description",
            "set_sharding", "torch_allgather"]
 
 
@@ -209,6 +209,58 @@ def save_png(path, width, height, palette, palette_map, compress_level=6):
 
     blob = (b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", width, height, 8, 3, 0, 0, 0))
             + chunk(b"PLTE", plte) + chunk(b"IDAT", zlib.compress(rows.tobytes(), compress_level)) + chunk(b"IEND", b""))
+    with open(path, "wb") as f:
+        f.write(blob)
+    return len(blob)
+
+
+def save_gif(path, width, height, palette, palette_map):
+    """N4 (extension): write ``(palette, palette_map)`` as a GIF89a (global colour table, one image) - palettes up to
+    256 entries, entries rounded as the reference's README does (``(palette * 255).astype(uint8)``, README.md:186-191).
+    The LZW stream is of the "uncompressed" kind (fixed code width, a clear code before the decoder's table would
+    grow): every decoder reads it, the packing is a handful of numpy operations instead of a per-pixel Python loop,
+    and the file is (bits + 1) / 8 bytes per pixel.  Pure host code; returns the number of bytes written."""
+    import struct
+    pal = np.asarray(palette, dtype=np.float64)
+    idx = np.asarray(palette_map).reshape(-1)
+    if pal.ndim != 2 or pal.shape[1] != 3:
+        raise ValueError("palette must be K x 3")
+    if idx.size != width * height:
+        raise ValueError(color_mismatch)
+    if not (0 < width < 65536 and 0 < height < 65536):
+        raise ValueError("a GIF is at most 65535 pixels wide and high")
+    used = int((pal[:, 0] >= 0).sum()) if pal.size else 0  # trailing rows of -1 are unused slots
+    if used > 256:
+        raise ValueError("a GIF holds at most 256 palette entries")
+    if idx.size and int(idx.max()) >= max(used, 1):
+        raise ValueError("palette_map refers to an unused palette row")
+    m = max(2, int(np.ceil(np.log2(max(used, 2)))))  # LZW minimum code size = bits per index
+    table = np.zeros((1 << m, 3), dtype=np.uint8)
+    table[:used] = (np.clip(pal[:used], 0.0, 1.0) * 255).astype(np.uint8)
+    clear, eoi, wbits = 1 << m, (1 << m) + 1, m + 1
+    run = (1 << m) - 2  # data codes between two clear codes: the decoder's table never reaches 2^(m+1) entries
+    n = idx.size
+    nruns = (n + run - 1) // run
+    body = np.empty((nruns, run + 1), dtype=np.uint16)  # [clear, run codes] per row
+    body[:, 0] = clear
+    flat = np.full(nruns * run, eoi, dtype=np.uint16)
+    flat[:n] = idx.astype(np.uint16)
+    body[:, 1:] = flat.reshape(nruns, run)
+    # (every run contributes its clear code and its pixels; the last one may be partial)
+    stream = np.concatenate([body.reshape(-1)[:n + nruns], np.array([eoi], dtype=np.uint16)])
+    bits = ((stream[:, None] >> np.arange(wbits, dtype=np.uint16)) & 1).astype(np.uint8).reshape(-1)
+    data = np.packbits(bits, bitorder="little")
+    nblk = (data.size + 254) // 255
+    padded = np.zeros(nblk * 255, dtype=np.uint8)
+    padded[:data.size] = data
+    blocks = np.empty((nblk, 256), dtype=np.uint8)
+    blocks[:, 0] = 255
+    blocks[:, 1:] = padded.reshape(nblk, 255)
+    tail = data.size - (nblk - 1) * 255
+    blocks[-1, 0] = tail
+    image_data = blocks.reshape(-1)[:(nblk - 1) * 256 + 1 + tail].tobytes() + b"\x00"
+    blob = (b"GIF89a" + struct.pack("<HHBBB", width, height, 0xF0 | (m - 1), 0, 0) + table.tobytes()
+            + b"," + struct.pack("<HHHHB", 0, 0, width, height, 0) + bytes([m]) + image_data + b";")
     with open(path, "wb") as f:
         f.write(blob)
     return len(blob)

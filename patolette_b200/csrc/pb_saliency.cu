@@ -435,11 +435,8 @@ __global__ void __launch_bounds__(256) k_sal_stage(SalParams P, const double *__
 // mbd() of the wrapper (patolette.pyx:183-199): inverse, raster, inverse scan over img / L / U / D (device, n floats
 // each, prepared by k_sal_prepare).  Returns 0, or -1 if a scan gave up waiting for its predecessor (a bug guard).
 int mbd_scans(const float *img, float *Lm, float *Um, float *Dm, uint32_t rows, uint32_t cols, cudaStream_t st) {
-    static bool attr_set = false; // (one device per process in practice; the attribute is per function and device)
-    if (!attr_set) {
-        PB_CUDA_OK(cudaFuncSetAttribute(k_mbd_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MbdSmem)));
-        attr_set = true;
-    }
+    // (per call: the attribute belongs to the function on the CURRENT device, and patolette_b200_set_device may have moved us)
+    PB_CUDA_OK(cudaFuncSetAttribute(k_mbd_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MbdSmem)));
     const int groups = (int)((rows + 31) / 32);
     int *ctl = nullptr;
     float2 *edge = nullptr;

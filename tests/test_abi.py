@@ -154,3 +154,23 @@ def test_save_png_round_trips(tmp_path):
     import pytest
     with pytest.raises(ValueError):
         pb.save_png(str(path), w, h, np.zeros((300, 3)), pmap)
+
+
+def test_save_gif_round_trips(tmp_path):
+    """N4: the GIF writer (fixed-width LZW stream) decodes to the same indices and palette in an independent decoder."""
+    Image = pytest.importorskip("PIL.Image")
+    import patolette_b200 as pb
+    rng = np.random.default_rng(0)
+    for (w, h, K, used) in [(37, 29, 256, 256), (64, 64, 16, 11), (5, 3, 4, 2), (254, 3, 256, 200), (508, 2, 256, 256), (300, 200, 2, 2)]:
+        pal = np.full((K, 3), -1.0)
+        pal[:used] = rng.random((used, 3))
+        idx = rng.integers(0, used, w * h)
+        path = str(tmp_path / "t.gif")
+        assert pb.save_gif(path, w, h, pal, idx) == os.path.getsize(path)
+        im = Image.open(path)
+        a = np.array(im)
+        assert im.mode == "P" and a.shape == (h, w)
+        assert np.array_equal(a.reshape(-1), idx)
+        assert np.array_equal(np.array(im.getpalette()[:3 * used]).reshape(used, 3), (pal[:used] * 255).astype(np.uint8))
+    with pytest.raises(ValueError):
+        pb.save_gif(str(tmp_path / "x.gif"), 2, 2, np.zeros((300, 3)), np.zeros(4, dtype=int))

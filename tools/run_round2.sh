@@ -24,3 +24,7 @@ d=json.load(open('gpurun_out/${tag}_bench.json')); k=d['roofline']['kernels']
 print(round(d['value'],1),'Mpx/s', round(d['ms_per_step'],2),'ms  e2e', round(d['e2e']['value'],1), 'cpu', d.get('cpu_baseline',{}).get('value'))
 print(d['roofline']['kernel'], d['roofline']['frac'], {n:k[n]['ms'] for n in k}); print(d['stage_ms'])
 PY
+# rows N2 / N3 (later in the round): eigen + saliency tests are part of `pytest -m gpu`; stage timings and the scans' timeline
+python tools/time_saliency.py --ref-side 2048 > gpurun_out/${tag}_saliency_time.jsonl 2> gpurun_out/${tag}_saliency_time.err
+python tools/mbd_timeline.py --side 4096 > gpurun_out/${tag}_mbd_timeline.txt 2>&1
+python tools/time_weighted_dither.py > gpurun_out/${tag}_weighted_dither.jsonl 2>&1
