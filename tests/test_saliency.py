@@ -66,6 +66,68 @@ def test_port_matches_live_reference_wrapper():
         np.testing.assert_allclose(sp.get_weights(img, tile), np.asarray(ref.get_weights(img, tile)), rtol=1e-12, atol=0)
 
 
+def _skewed_tile_scan(img, L, U, D, inverse):
+    """The schedule of k_mbd_pass (pb_saliency.cu) in plain Python: 32-row groups, skewed 32 x 32 tiles (tile k, step j,
+    lane t -> column 32 k + j - t), left neighbour in a per-lane register, upper neighbour = the lane above's previous
+    step, lane 0's upper neighbours from the row above the group.  Groups run one after the other here (any order
+    that respects the hand-off gives the same result)."""
+    f32 = np.float32
+    rows, cols = img.shape
+    R, Cn = (rows - 3, cols - 3) if inverse else (rows - 2, cols - 2)
+    if R <= 0 or Cn <= 0:
+        return
+    row_of = (lambda i: rows - 2 - i) if inverse else (lambda i: 1 + i)
+    col_of = (lambda c: cols - 2 - c) if inverse else (lambda c: 1 + c)
+    for g in range((R + 31) // 32):
+        uleft, lleft, myU, myL = [f32(0)] * 32, [f32(0)] * 32, [f32(0)] * 32, [f32(0)] * 32
+        for t in range(32):
+            if g * 32 + t < R:
+                y0 = cols - 1 if inverse else 0
+                uleft[t], lleft[t] = U[row_of(g * 32 + t), y0], L[row_of(g * 32 + t), y0]
+        uprow = row_of(g * 32) + 1 if inverse else row_of(g * 32) - 1
+        for k in range((Cn + 62) // 32):
+            tile = {}
+            for r in range(32):  # tile in
+                for lane in range(32):
+                    ir, c = g * 32 + r, 32 * k + lane - r
+                    if ir < R and 0 <= c < Cn:
+                        p = (row_of(ir), col_of(c))
+                        tile[r, lane] = [img[p], D[p], U[p], L[p]]
+            up = {lane: (U[uprow, col_of(32 * k + lane)], L[uprow, col_of(32 * k + lane)]) for lane in range(32) if 32 * k + lane < Cn}
+            for j in range(32):
+                shU, shL = [f32(0)] + myU[:-1], [f32(0)] + myL[:-1]
+                for lane in range(32):
+                    c = 32 * k + j - lane
+                    if not (g * 32 + lane < R and 0 <= c < Cn):
+                        continue
+                    upU, upL = up[j] if lane == 0 else (shU[lane], shL[lane])
+                    ix, d, cu, cl = tile[lane, j]
+                    u1, l1, u2, l2 = max(upU, ix), min(upL, ix), max(uleft[lane], ix), min(lleft[lane], ix)
+                    b1, b2 = f32(u1 - l1), f32(u2 - l2)
+                    keep, use1 = d <= b1 and d <= b2, b1 < d and b1 <= b2
+                    nD, nU, nL = (d, cu, cl) if keep else ((b1, u1, l1) if use1 else (b2, u2, l2))
+                    tile[lane, j] = [ix, nD, nU, nL]
+                    uleft[lane], lleft[lane], myU[lane], myL[lane] = nU, nL, nU, nL
+            for (r, lane), (ix, d, u, l) in tile.items():  # tile out
+                p = (row_of(g * 32 + r), col_of(32 * k + lane - r))
+                D[p], U[p], L[p] = d, u, l
+
+
+@pytest.mark.parametrize("shape", [(70, 45), (36, 5), (33, 67)])
+def test_skewed_tile_schedule_equals_the_raster_scans(shape):
+    """The wavefront schedule the CUDA kernel uses visits every pixel after its two neighbours: same distance map as the
+    port's literal raster scans (row counts around a 32-row group, column counts around a tile)."""
+    from oracle import saliency_port as sp
+    rng = np.random.default_rng(shape[0])
+    img = np.cumsum(rng.normal(size=shape), axis=1).astype(np.float32)
+    L, U = img.copy(), img.copy()
+    D = np.full(img.shape, np.inf, dtype=np.float32)
+    D[0, :] = 0; D[-1, :] = 0; D[:, 0] = 0; D[:, -1] = 0
+    for it in range(3):
+        _skewed_tile_scan(img, L, U, D, it % 2 == 0)
+    assert np.array_equal(D, sp.mbd(img, 3))
+
+
 def test_tile_size_validation_without_gpu():
     import patolette_b200 as pb
     assert pb.quantize(2, 2, np.zeros((4, 3)), 2, tile_size=-1)[3] == pb.bad_tile_size
