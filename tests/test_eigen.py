@@ -94,6 +94,24 @@ def test_stage_entry_host_instantiation_matches_real_dsyev():
     assert np.array_equal(z0.view(np.uint64), z1.view(np.uint64))
 
 
+@pytest.mark.skipif(scipy_openblas() is None, reason="scipy's OpenBLAS not found")
+def test_special_matrices_match_real_dsyev():
+    """Zeros, identity, repeated eigenvalues, a single off-diagonal entry, subnormal / near-overflow entries, NaN and
+    Inf: same bits as dsyev_ (and no endless loop: dsteqr's iteration cap is part of the restatement)."""
+    def sym(a11, a21, a31, a22, a32, a33):
+        return [a11, a21, a31, a21, a22, a32, a31, a32, a33]
+    nan, inf = float("nan"), float("inf")
+    mats = np.array([sym(0, 0, 0, 0, 0, 0), sym(1, 0, 0, 1, 0, 1), sym(2, 0, 0, 2, 0, 1), sym(1, 1, 1, 1, 1, 1),
+                     sym(1e-320, 0, 0, 1e-320, 0, 0), sym(1e308, 1e308, 0, 1e308, 0, 1e308), sym(0, 1, 0, 0, 0, 0),
+                     sym(0, 0, 1, 0, 0, 0), sym(0, 0, 0, 0, 1, 0), sym(5, 0, 0, -3, 0, 7), sym(1, 1e-200, 0, 1, 0, 1),
+                     sym(3, 0, 4, 0, 0, -3), sym(nan, 0, 0, 1, 0, 1), sym(1, inf, 0, 1, 0, 1), sym(1, 0, 0, nan, 0, 1)],
+                    dtype=np.float64)
+    w0, z0 = real_dsyev(mats)
+    w1, z1, info = ours(mats, 0)
+    assert np.array_equal(w0.view(np.uint64), w1.view(np.uint64))
+    assert np.array_equal(z0.view(np.uint64), z1.view(np.uint64))
+
+
 @pytest.mark.gpu
 def test_device_instantiation_matches_host_and_real_dsyev():
     mats = covariances(1 << 20, 2)
