@@ -453,9 +453,9 @@ def measure_ours(args):
             e2e_extra["u8_saliency"] = {"value": n / dts / 1e6, "unit": "Mpixels/s", "ms_per_step": dts * 1e3, "steps": reps,
                                         "api": "patolette_b200.quantize_u8(numpy uint8 [N,3], tile_size=512) -> u8 map "
                                                "(saliency weights + weighted pipeline)",
-                                        "note": "on this uniform-noise image the saliency-weighted palette makes the dither's "
-                                                "candidate grid miss (dither stage ~4x the unweighted one; same kernel time with "
-                                                "synthetic weights of the same range): profiles/r02_saliency.md",
+                                        "note": "the dither stage of a saliency run is ~4x the unweighted one on this noise image "
+                                                "(not so with caller-supplied weights of the same range); open question, "
+                                                "profiles/r02_saliency.md",
                                         "stage_ms": {k: round(v, 3) for k, v in pb.last_timings().items()}}
             del rgb8, pal8, map8
     del colors

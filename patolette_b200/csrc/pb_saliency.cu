@@ -432,9 +432,25 @@ __global__ void __launch_bounds__(256) k_sal_stage(SalParams P, const double *__
     }
 }
 
+// The scans run three CTAs of 68 KB shared memory per SM, which makes the driver move the SMs' L1 / shared-memory split to
+// the largest shared-memory carve-out, and later kernels without a preference of their own may inherit it.  An empty
+// kernel that asks for the largest L1 hands the SMs back in the state a run without saliency finds them in; the kernels
+// that follow grow the carve-out as they need it.  Measured effect (4096^2, K = 256, dither): the dither stage of a
+// saliency run 12.9 -> 11.6 ms, whole call 53.7 -> 50.6 ms (tools/ab_carveout.py; PB_SAL_KEEP_CARVEOUT=1 skips the
+// kernel for such A/B runs).  It does NOT explain why that stage is slower than on an unweighted run (4.5 ms) - see
+// profiles/r02_saliency.md, open question.
+__global__ void k_prefer_l1() {}
+void restore_l1_preference(int sm_count, cudaStream_t st) {
+    const char *keep = getenv("PB_SAL_KEEP_CARVEOUT");
+    if (keep && keep[0] == '1') return;
+    PB_CUDA_OK(cudaFuncSetAttribute(k_prefer_l1, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxL1));
+    k_prefer_l1<<<16 * (sm_count > 0 ? sm_count : 148), 32, 0, st>>>();
+    PB_CUDA_OK(cudaGetLastError());
+}
+
 // mbd() of the wrapper (patolette.pyx:183-199): inverse, raster, inverse scan over img / L / U / D (device, n floats
 // each, prepared by k_sal_prepare).  Returns 0, or -1 if a scan gave up waiting for its predecessor (a bug guard).
-int mbd_scans(const float *img, float *Lm, float *Um, float *Dm, uint32_t rows, uint32_t cols, cudaStream_t st) {
+int mbd_scans(const float *img, float *Lm, float *Um, float *Dm, uint32_t rows, uint32_t cols, int sm_count, cudaStream_t st) {
     // (per call: the attribute belongs to the function on the CURRENT device, and patolette_b200_set_device may have moved us)
     PB_CUDA_OK(cudaFuncSetAttribute(k_mbd_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MbdSmem)));
     const int groups = (int)((rows + 31) / 32);
@@ -469,6 +485,7 @@ int mbd_scans(const float *img, float *Lm, float *Um, float *Dm, uint32_t rows, 
             PB_CUDA_OK(cudaStreamSynchronize(st));
             if (FILE *f = fopen(dbg_path, "wb")) { fwrite(h.data(), sizeof(unsigned long long), dbg_words, f); fclose(f); }
         }
+        restore_l1_preference(sm_count, st);
         PB_CUDA_OK(cudaMemcpyAsync(&err, ctl + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
         PB_CUDA_OK(cudaStreamSynchronize(st));
     } catch (...) {
@@ -525,7 +542,7 @@ int pb_saliency_weights(const double *const planes[3], size_t width, size_t heig
         const int grid = (int)(want < cap ? want : cap);
         { PbProfScope p("k_sal_prepare", st);
           k_sal_prepare<<<grid, 256, 0, st>>>(planes[0], planes[1], planes[2], rows, cols, img, Lm, Um, Dm, l0, l1, l2); }
-        if (mbd_scans(img, Lm, Um, Dm, rows, cols, st) != 0) { cleanup(); return -1; }
+        if (mbd_scans(img, Lm, Um, Dm, rows, cols, sm_count, st) != 0) { cleanup(); return -1; }
         // strip means and covariances (np.mean, np.cov with ddof = 1), inverses on the host
         double h[24];
         SalParams P{};
@@ -610,7 +627,7 @@ int pb_saliency_mbd(const double *const planes[3], size_t width, size_t height, 
         const int grid = (int)(want < cap ? want : cap);
         { PbProfScope p("k_sal_prepare", st);
           k_sal_prepare<<<grid, 256, 0, st>>>(planes[0], planes[1], planes[2], rows, cols, img, Lm, Um, Dm, lab, lab + n, lab + 2 * n); }
-        if (mbd_scans(img, Lm, Um, Dm, rows, cols, st) != 0) { cleanup(); return -1; }
+        if (mbd_scans(img, Lm, Um, Dm, rows, cols, sm_count, st) != 0) { cleanup(); return -1; }
         PB_CUDA_OK(cudaMemcpyAsync(d_out, Dm, n * sizeof(float), cudaMemcpyDeviceToDevice, st));
         PB_CUDA_OK(cudaStreamSynchronize(st));
     } catch (...) {
